@@ -1,0 +1,551 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see roms_oracle.hpp).  Set-up restatement: tile bounds, s-coordinate,
+// barotropic filter weights, analytical grid / initial conditions / forcing, metrics.
+#include "roms_oracle.hpp"
+#include <cstring>
+
+namespace orc {
+
+static const double pi = 3.14159265358979323846;       // mod_scalars.F:788
+static const double deg2rad = pi / 180.0;              // mod_scalars.F:789
+static const double Eradius = 6371315.0;               // mod_scalars.F:434
+
+// Defaults: ROMS/External/roms_{upwelling,seamount,benchmark1}.in + ROMS/Include/<app>.h
+Cfg make_cfg(int app, int Lm, int Mm, int N) {
+  Cfg c; c.app = app;
+  if (app == APP_UPWELLING) {
+    c.Lm = 41; c.Mm = 80; c.N = 16; c.NT = 2; c.dt = 300.0; c.ndtfast = 30;
+    c.nonlin_eos = 0; c.curvgrid = 0; c.spherical = 0; c.mix_geo_ts = 0; c.uv_qdrag = 0; c.salinity = 1; c.ana_vmix = 1;
+    c.hadv = HADV_U3; c.vadv = VADV_C4;
+    c.R0 = 1027.0; c.T0 = 14.0; c.S0 = 35.0; c.Tcoef = 1.7e-4; c.Scoef = 0.0;
+    c.tnu2[0] = c.tnu2[1] = 0.0; c.visc2 = 5.0; c.Akt_bak[0] = c.Akt_bak[1] = 1e-6; c.Akv_bak = 1e-5;
+    c.gamma2 = 1.0; c.theta_s = 3.0; c.theta_b = 0.0; c.Tcline = 25.0;
+  } else if (app == APP_SEAMOUNT) {
+    c.Lm = 49; c.Mm = 48; c.N = 13; c.NT = 1; c.dt = 60.0; c.ndtfast = 20;
+    c.nonlin_eos = 0; c.curvgrid = 0; c.spherical = 0; c.mix_geo_ts = 1; c.uv_qdrag = 1; c.salinity = 0; c.ana_vmix = 0;
+    c.hadv = HADV_A4; c.vadv = VADV_A4;
+    c.R0 = 1027.0; c.T0 = 10.0; c.S0 = 32.0; c.Tcoef = 1.7e-4; c.Scoef = 7.6e-4;
+    c.tnu2[0] = c.tnu2[1] = 0.0; c.visc2 = 0.0; c.Akt_bak[0] = c.Akt_bak[1] = 1e-6; c.Akv_bak = 1e-5;
+    c.gamma2 = -1.0; c.theta_s = 6.5; c.theta_b = 2.0; c.Tcline = 100.0;
+  } else {
+    // BENCHMARK grid + initial conditions with the "reduced" physics set (option A)
+    c.Lm = 512; c.Mm = 64; c.N = 30; c.NT = 2; c.dt = 150.0; c.ndtfast = 20;
+    c.nonlin_eos = 1; c.curvgrid = 1; c.spherical = 1; c.mix_geo_ts = 0; c.uv_qdrag = 1; c.salinity = 1; c.ana_vmix = 0;
+    c.hadv = HADV_U3; c.vadv = VADV_C4;
+    c.R0 = 1027.0; c.T0 = 10.0; c.S0 = 35.0; c.Tcoef = 1.7e-4; c.Scoef = 7.6e-4;
+    c.tnu2[0] = c.tnu2[1] = 500.0; c.visc2 = 5000.0; c.Akt_bak[0] = c.Akt_bak[1] = 1e-5; c.Akv_bak = 1e-4;
+    c.gamma2 = 1.0; c.theta_s = 0.0; c.theta_b = 0.0; c.Tcline = 400.0;
+  }
+  if (Lm > 0) c.Lm = Lm;
+  if (Mm > 0) c.Mm = Mm;
+  if (N > 0) c.N = N;
+  return c;
+}
+
+// ROMS/Utility/get_bounds.F: tile_bounds_2d (:933-1007), var_bounds (:1009-1853), get_domain_edges (:411-619),
+// get_bounds (:2-258; DISTRIBUTE branch :60-190, shared-memory branch :229-253), ROMS/Include/tile.h
+void compute_bounds(const Cfg& c, int tile, bool distribute, Bnd& b) {
+  const int Lm = c.Lm, Mm = c.Mm;
+  b.tile = tile;
+  int my_Istr, my_Iend, my_Jstr, my_Jend;
+  {
+    int ChunkSizeI = (Lm + c.NtileI - 1) / c.NtileI;
+    int ChunkSizeJ = (Mm + c.NtileJ - 1) / c.NtileJ;
+    int MarginI = (c.NtileI * ChunkSizeI - Lm) / 2;
+    int MarginJ = (c.NtileJ * ChunkSizeJ - Mm) / 2;
+    b.Jtile = tile / c.NtileI;
+    b.Itile = tile - b.Jtile * c.NtileI;
+    my_Istr = 1 + b.Itile * ChunkSizeI - MarginI;
+    my_Iend = my_Istr + ChunkSizeI - 1;
+    my_Istr = std::max(my_Istr, 1);
+    my_Iend = std::min(my_Iend, Lm);
+    my_Jstr = 1 + b.Jtile * ChunkSizeJ - MarginJ;
+    my_Jend = my_Jstr + ChunkSizeJ - 1;
+    my_Jstr = std::max(my_Jstr, 1);
+    my_Jend = std::min(my_Jend, Mm);
+  }
+  b.Western_Edge = (b.Itile == 0);
+  b.Eastern_Edge = (b.Itile == c.NtileI - 1);
+  b.Southern_Edge = (b.Jtile == 0);
+  b.Northern_Edge = (b.Jtile == c.NtileJ - 1);
+  b.SouthWest_Corner = b.SouthWest_Test = b.Western_Edge && b.Southern_Edge;
+  b.SouthEast_Corner = b.SouthEast_Test = b.Eastern_Edge && b.Southern_Edge;
+  b.NorthWest_Corner = b.NorthWest_Test = b.Western_Edge && b.Northern_Edge;
+  b.NorthEast_Corner = b.NorthEast_Test = b.Eastern_Edge && b.Northern_Edge;
+  const bool EW = c.EWperiodic, NS = c.NSperiodic;
+  // --- var_bounds, xi-direction
+  if (b.Western_Edge && !EW) {
+    b.Istr = my_Istr; b.IstrP = my_Istr; b.IstrR = my_Istr - 1; b.IstrT = b.IstrR; b.IstrU = my_Istr + 1;
+    b.IstrB = b.IstrT + 1; b.IstrM = b.IstrP + 1;
+    b.Istrm3 = std::max(0, my_Istr - 3); b.Istrm2 = std::max(0, my_Istr - 2); b.IstrUm2 = std::max(1, b.IstrU - 2);
+    b.Istrm1 = std::max(1, my_Istr - 1); b.IstrUm1 = std::max(2, b.IstrU - 1);
+  } else {
+    b.Istr = my_Istr; b.IstrP = my_Istr; b.IstrR = my_Istr; b.IstrT = b.IstrR; b.IstrU = my_Istr; b.IstrB = my_Istr;
+    b.IstrM = b.IstrU;
+    b.Istrm3 = my_Istr - 3; b.Istrm2 = my_Istr - 2; b.IstrUm2 = b.IstrU - 2; b.Istrm1 = my_Istr - 1; b.IstrUm1 = b.IstrU - 1;
+  }
+  if (b.Eastern_Edge && !EW) {
+    b.Iend = my_Iend; b.IendR = my_Iend + 1; b.IendP = b.IendR; b.IendT = b.IendR; b.IendB = b.IendT - 1;
+    b.Iendp1 = std::min(my_Iend + 1, Lm); b.Iendp2i = std::min(my_Iend + 2, Lm); b.Iendp2 = std::min(my_Iend + 2, Lm + 1);
+    b.Iendp3 = std::min(my_Iend + 3, Lm + 1);
+  } else {
+    b.Iend = my_Iend; b.IendR = my_Iend; b.IendP = b.IendR; b.IendT = b.IendR; b.IendB = my_Iend;
+    b.Iendp1 = my_Iend + 1; b.Iendp2i = my_Iend + 2; b.Iendp2 = my_Iend + 2; b.Iendp3 = my_Iend + 3;
+  }
+  // --- eta-direction
+  if (b.Southern_Edge && !NS) {
+    b.Jstr = my_Jstr; b.JstrP = my_Jstr; b.JstrR = my_Jstr - 1; b.JstrT = b.JstrR; b.JstrV = my_Jstr + 1;
+    b.JstrB = b.JstrT + 1; b.JstrM = b.JstrP + 1;
+    b.Jstrm3 = std::max(0, my_Jstr - 3); b.Jstrm2 = std::max(0, my_Jstr - 2); b.JstrVm2 = std::max(1, b.JstrV - 2);
+    b.Jstrm1 = std::max(1, my_Jstr - 1); b.JstrVm1 = std::max(2, b.JstrV - 1);
+  } else {
+    b.Jstr = my_Jstr; b.JstrP = my_Jstr; b.JstrR = my_Jstr; b.JstrT = b.JstrR; b.JstrV = my_Jstr; b.JstrB = my_Jstr;
+    b.JstrM = b.JstrV;
+    b.Jstrm3 = my_Jstr - 3; b.Jstrm2 = my_Jstr - 2; b.JstrVm2 = b.JstrV - 2; b.Jstrm1 = my_Jstr - 1; b.JstrVm1 = b.JstrV - 1;
+  }
+  if (b.Northern_Edge && !NS) {
+    b.Jend = my_Jend; b.JendR = my_Jend + 1; b.JendP = b.JendR; b.JendT = b.JendR; b.JendB = b.JendT - 1;
+    b.Jendp1 = std::min(my_Jend + 1, Mm); b.Jendp2i = std::min(my_Jend + 2, Mm); b.Jendp2 = std::min(my_Jend + 2, Mm + 1);
+    b.Jendp3 = std::min(my_Jend + 3, Mm + 1);
+  } else {
+    b.Jend = my_Jend; b.JendR = my_Jend; b.JendP = b.JendR; b.JendT = b.JendR; b.JendB = my_Jend;
+    b.Jendp1 = my_Jend + 1; b.Jendp2i = my_Jend + 2; b.Jendp2 = my_Jend + 2; b.Jendp3 = my_Jend + 3;
+  }
+  // --- private scratch extents (tile.h, non-NESTING)
+  b.IminS = b.Istr - 3; b.ImaxS = b.Iend + 3; b.JminS = b.Jstr - 3; b.JmaxS = b.Jend + 3;
+  // --- array bounds (get_bounds, gtype=0)
+  const int Ng = c.Nghost;
+  int Imin = EW ? -Ng : 0, Imax = EW ? Lm + Ng : Lm + 1;
+  int Jmin = NS ? -Ng : 0, Jmax = NS ? Mm + Ng : Mm + 1;
+  if (distribute) {
+    b.LBi = (b.Itile == 0) ? Imin : b.Istr - Ng;
+    b.UBi = (b.Itile == c.NtileI - 1) ? Imax : b.Iend + Ng;
+    b.LBj = (b.Jtile == 0) ? Jmin : b.Jstr - Ng;
+    b.UBj = (b.Jtile == c.NtileJ - 1) ? Jmax : b.Jend + Ng;
+  } else {
+    b.LBi = Imin; b.UBi = Imax; b.LBj = Jmin; b.UBj = Jmax;
+  }
+}
+
+F2 Model::new2() {
+  pool.emplace_back((size_t)(UBi - LBi + 1) * (UBj - LBj + 1), 0.0);
+  return F2(pool.back().data(), LBi, UBi, LBj, UBj);
+}
+F3 Model::new3(int k0, int k1) {
+  pool.emplace_back((size_t)(UBi - LBi + 1) * (UBj - LBj + 1) * (k1 - k0 + 1), 0.0);
+  return F3(pool.back().data(), LBi, UBi, LBj, UBj, k0, k1);
+}
+
+// Array shapes: mod_ocean.F:341-411, mod_grid.F, mod_coupling.F, mod_mixing.F, mod_forces.F (all IniVal = 0)
+void Model::allocate() {
+  if (!c.EWperiodic || c.NSperiodic) { std::fprintf(stderr, "oracle: only EW-periodic / NS-closed supported\n"); std::abort(); }
+  int ntile = c.NtileI * c.NtileJ;
+  tiles.resize(ntile);
+  for (int t_ = 0; t_ < ntile; ++t_) compute_bounds(c, t_, false, tiles[t_]);
+  LBi = tiles[0].LBi; UBi = tiles[0].UBi; LBj = tiles[0].LBj; UBj = tiles[0].UBj;
+  const int N = c.N;
+  pool.clear(); pool.reserve(400);
+  F2* g2[] = {&h, &f, &pm, &pn, &om_r, &on_r, &om_u, &on_u, &om_v, &on_v, &om_p, &on_p, &omn, &fomn, &pmon_r, &pnom_r,
+              &pmon_u, &pnom_u, &pmon_v, &pnom_v, &pmon_p, &pnom_p, &dndx, &dmde, &xr, &yr, &latr, &lonr, &rdrag, &rdrag2,
+              &visc2_r, &visc2_p, &diff2[0], &diff2[1], &Zt_avg1, &DU_avg1, &DU_avg2, &DV_avg1, &DV_avg2, &rufrc, &rvfrc,
+              &rhoA, &rhoS, &sustr, &svstr, &bustr, &bvstr, &stflx[0], &stflx[1], &btflx[0], &btflx[1], &stflux[0], &stflux[1], &btflux[0], &btflux[1]};
+  for (F2* p_ : g2) *p_ = new2();
+  for (int k = 1; k <= 3; ++k) { zeta[k] = new2(); ubar[k] = new2(); vbar[k] = new2(); }
+  for (int k = 1; k <= 2; ++k) { rzeta[k] = new2(); rubar[k] = new2(); rvbar[k] = new2(); }
+  for (int k = 1; k <= 2; ++k) { u[k] = new3(1, N); v[k] = new3(1, N); ru[k] = new3(0, N); rv[k] = new3(0, N); }
+  for (int k = 1; k <= 3; ++k) for (int it = 0; it < c.NT; ++it) t[k][it] = new3(1, N);
+  rho = new3(1, N); pden = new3(1, N); Hz = new3(1, N); z_r = new3(1, N); Huon = new3(1, N); Hvom = new3(1, N);
+  W = new3(0, N); wvel = new3(0, N); z_w = new3(0, N); Akv = new3(0, N);
+  for (int it = 0; it < c.NT; ++it) Akt[it] = new3(0, N);
+  sc_r.assign(N + 1, 0.0); Cs_r.assign(N + 1, 0.0); sc_w.assign(N + 1, 0.0); Cs_w.assign(N + 1, 0.0);
+  // mod_mixing.F:1422-1443: Akv/Akt background at k=1..N-1, IniVal at k=0,N
+  for (int k = 1; k <= N - 1; ++k)
+    for (int j = LBj; j <= UBj; ++j)
+      for (int i = LBi; i <= UBi; ++i) {
+        Akv(i, j, k) = c.Akv_bak;
+        for (int it = 0; it < c.NT; ++it) Akt[it](i, j, k) = c.Akt_bak[it];
+      }
+  // mod_grid.F:1257-1261
+  for (int j = LBj; j <= UBj; ++j)
+    for (int i = LBi; i <= UBi; ++i) {
+      if (c.uv_qdrag) rdrag2(i, j) = c.rdrg2; else rdrag(i, j) = c.rdrg;
+    }
+}
+
+// ROMS/Utility/set_scoord.F:170-178 (hc), :393-440 (Vstretching=4)
+void set_scoord(Model& m) {
+  const Cfg& c = m.c; const int N = c.N;
+  if (c.Vtransform != 2 || c.Vstretching != 4) { std::fprintf(stderr, "oracle: only Vtransform=2/Vstretching=4\n"); std::abort(); }
+  m.hc = c.Tcline;
+  const double ds = 1.0 / (double)N;
+  m.sc_w[N] = 0.0; m.Cs_w[N] = 0.0;
+  for (int k = N - 1; k >= 1; --k) {
+    double sc_w = ds * (double)(k - N);
+    m.sc_w[k] = sc_w;
+    double Csur;
+    if (c.theta_s > 0.0) Csur = (1.0 - std::cosh(c.theta_s * sc_w)) / (std::cosh(c.theta_s) - 1.0);
+    else Csur = -(sc_w * sc_w);
+    if (c.theta_b > 0.0) m.Cs_w[k] = (std::exp(c.theta_b * Csur) - 1.0) / (1.0 - std::exp(-c.theta_b));
+    else m.Cs_w[k] = Csur;
+  }
+  m.sc_w[0] = -1.0; m.Cs_w[0] = -1.0;
+  for (int k = 1; k <= N; ++k) {
+    double sc_r = ds * ((double)(k - N) - 0.5);
+    m.sc_r[k] = sc_r;
+    double Csur;
+    if (c.theta_s > 0.0) Csur = (1.0 - std::cosh(c.theta_s * sc_r)) / (std::cosh(c.theta_s) - 1.0);
+    else Csur = -(sc_r * sc_r);
+    if (c.theta_b > 0.0) m.Cs_r[k] = (std::exp(c.theta_b * Csur) - 1.0) / (1.0 - std::exp(-c.theta_b));
+    else m.Cs_r[k] = Csur;
+  }
+}
+
+// ROMS/Utility/set_weights.F (POWER_LAW: globaldefs.h:119-122; Falpha=2, Fbeta=4, Fgamma=0.284 mod_scalars.F:310-312).
+// r16 = SELECTED_REAL_KIND(15,300) = binary64 on Linux/gfortran (mod_kinds.F) => plain double.
+// out_chk = the five integrals of FORMAT 40: "values must be 1, 1, approx 1/2, 1, 1".
+void set_weights(Model& m, double out_chk[5]) {
+  const int ndtfast = m.c.ndtfast;
+  const double Falpha = 2.0, Fbeta = 4.0, Fgamma = 0.284;
+  std::vector<double>& w1 = m.weight1; std::vector<double>& w2 = m.weight2;
+  w1.assign(2 * ndtfast + 2, 0.0); w2.assign(2 * ndtfast + 2, 0.0);
+  int nfast = 0;
+  double scale = (Falpha + 1.0) * (Falpha + Fbeta + 1.0) / ((Falpha + 2.0) * (Falpha + Fbeta + 2.0) * (double)ndtfast);
+  double gamma = Fgamma * std::max(0.0, 1.0 - 10.0 / (double)ndtfast);
+  double wsum, shift, cff;
+  for (int iter = 1; iter <= 16; ++iter) {
+    nfast = 0;
+    for (int i = 1; i <= 2 * ndtfast; ++i) {
+      cff = scale * (double)i;
+      w1[i] = std::pow(cff, Falpha) - std::pow(cff, Falpha + Fbeta) - gamma * cff;
+      if (w1[i] > 0.0) nfast = i;
+      if (nfast > 0 && w1[i] < 0.0) w1[i] = 0.0;
+    }
+    wsum = 0.0; shift = 0.0;
+    for (int i = 1; i <= nfast; ++i) { wsum = wsum + w1[i]; shift = shift + w1[i] * (double)i; }
+    scale = scale * shift / (wsum * (double)ndtfast);
+  }
+  for (int iter = 1; iter <= ndtfast; ++iter) {
+    wsum = 0.0; shift = 0.0;
+    for (int i = 1; i <= nfast; ++i) { wsum = wsum + w1[i]; shift = shift + (double)i * w1[i]; }
+    shift = shift / wsum;
+    cff = (double)ndtfast - shift;
+    if (cff > 1.0) {
+      nfast = nfast + 1;
+      for (int i = nfast; i >= 2; --i) w1[i] = w1[i - 1];
+      w1[1] = 0.0;
+    } else if (cff > 0.0) {
+      wsum = 1.0 - cff;
+      for (int i = nfast; i >= 2; --i) w1[i] = wsum * w1[i] + cff * w1[i - 1];
+      w1[1] = wsum * w1[1];
+    } else if (cff < -1.0) {
+      nfast = nfast - 1;
+      for (int i = 1; i <= nfast; ++i) w1[i] = w1[i + 1];
+      w1[nfast + 1] = 0.0;
+    } else if (cff < 0.0) {
+      wsum = 1.0 + cff;
+      for (int i = 1; i <= nfast - 1; ++i) w1[i] = wsum * w1[i] - cff * w1[i + 1];
+      w1[nfast] = wsum * w1[nfast];
+    }
+  }
+  for (int j = 1; j <= nfast; ++j) {
+    cff = w1[j];
+    for (int i = 1; i <= j; ++i) w2[i] = w2[i] + cff;
+  }
+  wsum = 0.0; cff = 0.0;
+  for (int i = 1; i <= nfast; ++i) { wsum = wsum + w1[i]; cff = cff + w2[i]; }
+  wsum = 1.0 / wsum; cff = 1.0 / cff;
+  for (int i = 1; i <= nfast; ++i) { w1[i] = wsum * w1[i]; w2[i] = cff * w2[i]; }
+  m.nfast = nfast;
+  m.dtfast = m.c.dt / (double)ndtfast;
+  if (out_chk) {
+    double c0 = 0, cff1 = 0, cff2 = 0, ws = 0, sh = 0;
+    for (int i = 1; i <= nfast; ++i) {
+      c0 += w1[i]; cff1 += w1[i] * (double)i; cff2 += w1[i] * (double)(i * i); ws += w2[i]; sh += w2[i] * ((double)i - 0.5);
+    }
+    cff1 = cff1 / (double)ndtfast; cff2 = cff2 / ((double)ndtfast * (double)ndtfast); sh = sh / (double)ndtfast;
+    out_chk[0] = cff1; out_chk[1] = cff2; out_chk[2] = sh; out_chk[3] = c0; out_chk[4] = ws;
+  }
+}
+
+// ROMS/Functionals/ana_grid.h: sizes :243-249 (BENCHMARK), :345-351 (SEAMOUNT), :384-390 (UPWELLING); coordinates
+// :459-478 / :513-529; pm,pn :674-719; dndx,dmde :761-766; f :862-888; h :919-926, :1021-1028, :1047-1072
+void ana_grid(Model& m, const Bnd& b) {
+  const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
+  const int Lm = c.Lm, Mm = c.Mm;
+  double Xsize, Esize, depth, f0, beta;
+  if (c.app == APP_BENCHMARK) { Xsize = 360.0; Esize = 20.0; depth = 4000.0; f0 = -1.0e-4; beta = 2.0e-11; }
+  else if (c.app == APP_SEAMOUNT) { Xsize = 320.0e3; Esize = 320.0e3; depth = 5000.0; f0 = 1.0e-4; beta = 0.0; }
+  else { Xsize = 1000.0 * (double)Lm; Esize = 1000.0 * (double)Mm; depth = 150.0; f0 = -8.26e-5; beta = 0.0; }
+  int Imin = b.Western_Edge ? Istr - 1 : Istr, Imax = b.Eastern_Edge ? Iend + 1 : Iend;
+  int Jmin = b.Southern_Edge ? Jstr - 1 : Jstr, Jmax = b.Northern_Edge ? Jend + 1 : Jend;
+  const double dx = Xsize / (double)Lm, dy = Esize / (double)Mm;
+  if (c.app == APP_BENCHMARK) {
+    for (int j = Jmin; j <= Jmax; ++j) {
+      double val1 = -70.0 + dy * ((double)j - 0.5);
+      for (int i = Imin; i <= Imax; ++i) { m.lonr(i, j) = dx * ((double)i - 0.5); m.latr(i, j) = val1; }
+    }
+  } else {
+    for (int j = Jmin; j <= Jmax; ++j)
+      for (int i = Imin; i <= Imax; ++i) { m.xr(i, j) = dx * ((double)(i - 1) + 0.5); m.yr(i, j) = dy * ((double)(j - 1) + 0.5); }
+  }
+  const int J0 = std::min(JstrT, Jstr - 1), J1 = std::max(Jend + 1, JendT);
+  const int I0 = std::min(IstrT, Istr - 1), I1 = std::max(Iend + 1, IendT);
+  S2 wrkX(IminS, ImaxS, JminS, JmaxS), wrkY(IminS, ImaxS, JminS, JmaxS);
+  if (c.app == APP_BENCHMARK) {
+    double val1 = (double)Lm / (2.0 * pi * Eradius);
+    double val2 = (double)Mm * 360.0 / (2.0 * pi * Eradius * Esize);
+    for (int j = J0; j <= J1; ++j) {
+      double cff = 1.0 / std::cos((-70.0 + dy * ((double)j - 0.5)) * deg2rad);
+      for (int i = I0; i <= I1; ++i) { wrkX(i, j) = val1 * cff; wrkY(i, j) = val2; }
+    }
+  } else {
+    for (int j = J0; j <= J1; ++j)
+      for (int i = I0; i <= I1; ++i) { wrkX(i, j) = 1.0 / dx; wrkY(i, j) = 1.0 / dy; }
+  }
+  for (int j = JstrT; j <= JendT; ++j)
+    for (int i = IstrT; i <= IendT; ++i) { m.pm(i, j) = wrkX(i, j); m.pn(i, j) = wrkY(i, j); }
+  exchange_r2d(m, b, m.pm); exchange_r2d(m, b, m.pn);
+  if (c.curvgrid) {
+    for (int j = Jstr; j <= Jend; ++j)
+      for (int i = Istr; i <= Iend; ++i) {
+        m.dndx(i, j) = 0.5 * ((1.0 / wrkY(i + 1, j)) - (1.0 / wrkY(i - 1, j)));
+        m.dmde(i, j) = 0.5 * ((1.0 / wrkX(i, j + 1)) - (1.0 / wrkX(i, j - 1)));
+      }
+    exchange_r2d(m, b, m.dndx); exchange_r2d(m, b, m.dmde);
+  }
+  if (c.app == APP_BENCHMARK) {
+    double val1 = 2.0 * (2.0 * pi * 366.25 / 365.25) / 86400.0;
+    for (int j = JstrT; j <= JendT; ++j)
+      for (int i = IstrT; i <= IendT; ++i) m.f(i, j) = val1 * std::sin(m.latr(i, j) * deg2rad);
+  } else {
+    double val1 = 0.5 * Esize;
+    for (int j = JstrT; j <= JendT; ++j)
+      for (int i = IstrT; i <= IendT; ++i) m.f(i, j) = f0 + beta * (m.yr(i, j) - val1);
+  }
+  exchange_r2d(m, b, m.f);
+  if (c.app == APP_BENCHMARK) {
+    for (int j = JstrT; j <= JendT; ++j)
+      for (int i = IstrT; i <= IendT; ++i) m.h(i, j) = 500.0 + 1750.0 * (1.0 + std::tanh((68.0 + m.latr(i, j)) / dy));
+  } else if (c.app == APP_SEAMOUNT) {
+    for (int j = JstrT; j <= JendT; ++j)
+      for (int i = IstrT; i <= IendT; ++i) {
+        double val1 = (m.xr(i, j) - 0.5 * Xsize) / 40000.0;
+        double val2 = (m.yr(i, j) - 0.5 * Esize) / 40000.0;
+        m.h(i, j) = depth - 4500.0 * std::exp(-(val1 * val1 + val2 * val2));
+      }
+  } else {  // UPWELLING, EWperiodic branch
+    for (int j = JstrT; j <= JendT; ++j) {
+      double val1 = (j <= Mm / 2) ? (double)j : (double)(Mm + 1 - j);
+      double val2 = std::min(depth, 84.5 + 66.526 * std::tanh((val1 - 10.0) / 7.0));
+      for (int i = IstrT; i <= IendT; ++i) m.h(i, j) = val2;
+    }
+  }
+  exchange_r2d(m, b, m.h);
+}
+
+// ROMS/Utility/metrics.F:355-534
+void metrics(Model& m, const Bnd& b) {
+  ORC_UNPACK_BOUNDS(b);
+  F2 &pm = m.pm, &pn = m.pn;
+  for (int j = JstrT; j <= JendT; ++j)
+    for (int i = IstrT; i <= IendT; ++i) {
+      m.om_r(i, j) = 1.0 / pm(i, j); m.on_r(i, j) = 1.0 / pn(i, j);
+      m.omn(i, j) = 1.0 / (pm(i, j) * pn(i, j)); m.fomn(i, j) = m.f(i, j) * m.omn(i, j);
+    }
+  exchange_r2d(m, b, m.om_r); exchange_r2d(m, b, m.on_r); exchange_r2d(m, b, m.omn); exchange_r2d(m, b, m.fomn);
+  for (int j = JstrT; j <= JendT; ++j)
+    for (int i = IstrT; i <= IendT; ++i) { m.pnom_r(i, j) = pn(i, j) / pm(i, j); m.pmon_r(i, j) = pm(i, j) / pn(i, j); }
+  exchange_r2d(m, b, m.pnom_r); exchange_r2d(m, b, m.pmon_r);
+  for (int j = JstrT; j <= JendT; ++j)
+    for (int i = IstrP; i <= IendT; ++i) {
+      m.pmon_u(i, j) = (pm(i - 1, j) + pm(i, j)) / (pn(i - 1, j) + pn(i, j));
+      m.pnom_u(i, j) = (pn(i - 1, j) + pn(i, j)) / (pm(i - 1, j) + pm(i, j));
+      m.om_u(i, j) = 2.0 / (pm(i - 1, j) + pm(i, j));
+      m.on_u(i, j) = 2.0 / (pn(i - 1, j) + pn(i, j));
+    }
+  exchange_u2d(m, b, m.pmon_u); exchange_u2d(m, b, m.pnom_u); exchange_u2d(m, b, m.om_u); exchange_u2d(m, b, m.on_u);
+  for (int j = JstrP; j <= JendT; ++j)
+    for (int i = IstrT; i <= IendT; ++i) {
+      m.pmon_v(i, j) = (pm(i, j - 1) + pm(i, j)) / (pn(i, j - 1) + pn(i, j));
+      m.pnom_v(i, j) = (pn(i, j - 1) + pn(i, j)) / (pm(i, j - 1) + pm(i, j));
+      m.om_v(i, j) = 2.0 / (pm(i, j - 1) + pm(i, j));
+      m.on_v(i, j) = 2.0 / (pn(i, j - 1) + pn(i, j));
+    }
+  exchange_v2d(m, b, m.pmon_v); exchange_v2d(m, b, m.pnom_v); exchange_v2d(m, b, m.om_v); exchange_v2d(m, b, m.on_v);
+  for (int j = JstrP; j <= JendT; ++j)
+    for (int i = IstrP; i <= IendT; ++i) {
+      m.pnom_p(i, j) = (pn(i - 1, j - 1) + pn(i - 1, j) + pn(i, j - 1) + pn(i, j)) / (pm(i - 1, j - 1) + pm(i - 1, j) + pm(i, j - 1) + pm(i, j));
+      m.pmon_p(i, j) = (pm(i - 1, j - 1) + pm(i - 1, j) + pm(i, j - 1) + pm(i, j)) / (pn(i - 1, j - 1) + pn(i - 1, j) + pn(i, j - 1) + pn(i, j));
+      m.om_p(i, j) = 4.0 / (pm(i - 1, j - 1) + pm(i - 1, j) + pm(i, j - 1) + pm(i, j));
+      m.on_p(i, j) = 4.0 / (pn(i - 1, j - 1) + pn(i - 1, j) + pn(i, j - 1) + pn(i, j));
+    }
+  exchange_p2d(m, b, m.pnom_p); exchange_p2d(m, b, m.pmon_p); exchange_p2d(m, b, m.om_p); exchange_p2d(m, b, m.on_p);
+}
+
+// ROMS/Utility/ini_hmixcoef.F:257-290 (uniform; VISC_GRID/DIFF_GRID/sponges not active)
+void ini_hmixcoef(Model& m, const Bnd& b) {
+  (void)b;
+  for (int j = m.LBj; j <= m.UBj; ++j)
+    for (int i = m.LBi; i <= m.UBi; ++i) {
+      m.visc2_p(i, j) = m.c.visc2; m.visc2_r(i, j) = m.c.visc2;
+      for (int it = 0; it < m.c.NT; ++it) m.diff2[it](i, j) = m.c.tnu2[it];
+    }
+}
+
+// ROMS/Functionals/ana_initial.h: u,v,ubar,vbar,zeta = 0 (default branches); tracers :523-540 (BENCHMARK),
+// :787-794 (SEAMOUNT), :806-818 (UPWELLING).  Time level 1.
+void ana_initial(Model& m, const Bnd& b) {
+  const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
+  const int N = c.N;
+  for (int j = JstrT; j <= JendT; ++j) for (int i = IstrP; i <= IendT; ++i) m.ubar[1](i, j) = 0.0;
+  for (int j = JstrP; j <= JendT; ++j) for (int i = IstrT; i <= IendT; ++i) m.vbar[1](i, j) = 0.0;
+  for (int j = JstrT; j <= JendT; ++j) for (int i = IstrT; i <= IendT; ++i) m.zeta[1](i, j) = 0.0;
+  for (int k = 1; k <= N; ++k) {
+    for (int j = JstrT; j <= JendT; ++j) for (int i = IstrP; i <= IendT; ++i) m.u[1](i, j, k) = 0.0;
+    for (int j = JstrP; j <= JendT; ++j) for (int i = IstrT; i <= IendT; ++i) m.v[1](i, j, k) = 0.0;
+  }
+  if (c.app == APP_BENCHMARK) {
+    double q = 44.69 / 39.382; double val1 = q * q;
+    double r = 42.689 / 44.69; double val2 = val1 * (c.rho0 * 800.0 / c.g) * (5.0e-5 / (r * r));
+    for (int k = 1; k <= N; ++k)
+      for (int j = JstrT; j <= JendT; ++j)
+        for (int i = IstrT; i <= IendT; ++i) {
+          m.t[1][0](i, j, k) = val2 * std::exp(m.z_r(i, j, k) / 800.0) * (0.6 - 0.4 * std::tanh(m.z_r(i, j, k) / 800.0));
+          if (c.salinity) m.t[1][1](i, j, k) = 35.0;
+        }
+  } else if (c.app == APP_SEAMOUNT) {
+    for (int k = 1; k <= N; ++k)
+      for (int j = JstrT; j <= JendT; ++j)
+        for (int i = IstrT; i <= IendT; ++i) m.t[1][0](i, j, k) = c.T0 + 7.5 * std::exp(m.z_r(i, j, k) / 1000.0);
+  } else {
+    for (int k = 1; k <= N; ++k)
+      for (int j = JstrT; j <= JendT; ++j)
+        for (int i = IstrT; i <= IendT; ++i) {
+          m.t[1][0](i, j, k) = c.T0 + 8.0 * std::exp(m.z_r(i, j, k) / 50.0);
+          if (c.salinity) m.t[1][1](i, j, k) = c.S0;
+        }
+  }
+}
+
+// ROMS/Functionals/ana_smflux.h: UPWELLING :306-330, :413-430; default (sustr=svstr=0) otherwise.
+// BENCHMARK "reduced" set: the shipped application takes its stress from bulk_flux (out of
+// scope); we use a steady analytical zonal stress sustr = (0.1/rho0)*SIN(pi*(j-0.5)/Mm), svstr = 0.
+void ana_smflux(Model& m, const Bnd& b) {
+  const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
+  if (c.app == APP_UPWELLING) {
+    double windamp;
+    const double dstart = 0.0;
+    if ((m.tdays - dstart) <= 2.0) windamp = -0.1 * std::sin(pi * (m.tdays - dstart) / 4.0) / c.rho0;
+    else windamp = -0.1 / c.rho0;
+    for (int j = JstrT; j <= JendT; ++j) for (int i = IstrP; i <= IendT; ++i) m.sustr(i, j) = windamp;
+  } else if (c.app == APP_BENCHMARK) {
+    for (int j = JstrT; j <= JendT; ++j) {
+      double val = 0.1 / c.rho0 * std::sin(pi * ((double)j - 0.5) / (double)c.Mm);
+      for (int i = IstrP; i <= IendT; ++i) m.sustr(i, j) = val;
+    }
+  } else {
+    for (int j = JstrT; j <= JendT; ++j) for (int i = IstrP; i <= IendT; ++i) m.sustr(i, j) = 0.0;
+  }
+  for (int j = JstrP; j <= JendT; ++j) for (int i = IstrT; i <= IendT; ++i) m.svstr(i, j) = 0.0;
+  exchange_u2d(m, b, m.sustr); exchange_v2d(m, b, m.svstr);
+}
+
+// ana_stflux.h / ana_btflux.h / ana_ssflux / ana_bsflux: zero for all three applications
+void ana_stflux_btflux(Model& m, const Bnd& b) {
+  ORC_UNPACK_BOUNDS(b);
+  for (int it = 0; it < m.c.NT; ++it)
+    for (int j = JstrT; j <= JendT; ++j)
+      for (int i = IstrT; i <= IendT; ++i) { m.stflux[it](i, j) = 0.0; m.btflux[it](i, j) = 0.0; }
+}
+
+// ROMS/Functionals/ana_vmix.h:200-208 (Akv, UPWELLING), :327-337 (Akt), exchanges at the end
+void ana_vmix(Model& m, const Bnd& b) {
+  const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
+  const int N = c.N;
+  for (int k = 1; k <= N - 1; ++k)
+    for (int j = JstrT; j <= JendT; ++j)
+      for (int i = IstrT; i <= IendT; ++i) m.Akv(i, j, k) = 2.0e-3 + 8.0e-3 * std::exp(m.z_w(i, j, k) / 150.0);
+  exchange_w3d(m, b, m.Akv);
+  for (int k = 1; k <= N - 1; ++k)
+    for (int j = JstrT; j <= JendT; ++j)
+      for (int i = IstrT; i <= IendT; ++i) {
+        m.Akt[0](i, j, k) = c.Akt_bak[0];
+        if (c.salinity) m.Akt[1](i, j, k) = c.Akt_bak[1];
+      }
+  for (int it = 0; it < c.NT; ++it) exchange_w3d(m, b, m.Akt[it]);
+}
+
+// ROMS/Nonlinear/ini_fields.F:836-1137 (ini_zeta_tile), non-PerfectRST, closed/periodic LBC
+void ini_zeta(Model& m, const Bnd& b) {
+  ORC_UNPACK_BOUNDS(b);
+  const int kstp = m.kstp, knew = m.knew;
+  for (int j = JstrB; j <= JendB; ++j)
+    for (int i = IstrB; i <= IendB; ++i) { double cff1 = m.zeta[kstp](i, j); m.zeta[kstp](i, j) = cff1; m.zeta[knew](i, j) = cff1; }
+  zetabc(m, b, kstp); zetabc(m, b, knew);
+  exchange_r2d(m, b, m.zeta[kstp]); exchange_r2d(m, b, m.zeta[knew]);
+  for (int j = JstrT; j <= JendT; ++j) for (int i = IstrT; i <= IendT; ++i) m.Zt_avg1(i, j) = m.zeta[kstp](i, j);
+  exchange_r2d(m, b, m.Zt_avg1);
+}
+
+// ROMS/Nonlinear/ini_fields.F:106-777 (ini_fields_tile), non-PerfectRST
+void ini_fields(Model& m, const Bnd& b) {
+  const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
+  const int N = c.N, nstp = m.nstp, nnew = m.nnew, kstp = m.kstp, knew = m.knew;
+  for (int j = JstrB; j <= JendB; ++j) {
+    for (int k = 1; k <= N; ++k) for (int i = IstrM; i <= IendB; ++i) { double cff1 = m.u[nstp](i, j, k); m.u[nstp](i, j, k) = cff1; m.u[nnew](i, j, k) = cff1; }
+    if (j >= JstrM)
+      for (int k = 1; k <= N; ++k) for (int i = IstrB; i <= IendB; ++i) { double cff2 = m.v[nstp](i, j, k); m.v[nstp](i, j, k) = cff2; m.v[nnew](i, j, k) = cff2; }
+  }
+  u3dbc(m, b, nstp); v3dbc(m, b, nstp); u3dbc(m, b, nnew); v3dbc(m, b, nnew);
+  exchange_u3d(m, b, m.u[nstp]); exchange_v3d(m, b, m.v[nstp]); exchange_u3d(m, b, m.u[nnew]); exchange_v3d(m, b, m.v[nnew]);
+  SK DC(IminS, ImaxS, 0, N), CF(IminS, ImaxS, 0, N);
+  for (int j = JstrB; j <= JendB; ++j) {
+    for (int i = IstrM; i <= IendB; ++i) { DC(i, 0) = 0.0; CF(i, 0) = 0.0; }
+    for (int k = 1; k <= N; ++k)
+      for (int i = IstrM; i <= IendB; ++i) {
+        DC(i, k) = 0.5 * (m.Hz(i, j, k) + m.Hz(i - 1, j, k));
+        DC(i, 0) = DC(i, 0) + DC(i, k);
+        CF(i, 0) = CF(i, 0) + DC(i, k) * m.u[nstp](i, j, k);
+      }
+    for (int i = IstrM; i <= IendB; ++i) { double cff1 = 1.0 / DC(i, 0); double cff2 = CF(i, 0) * cff1; m.ubar[kstp](i, j) = cff2; m.ubar[knew](i, j) = cff2; }
+    if (j >= JstrM) {
+      for (int i = IstrB; i <= IendB; ++i) { DC(i, 0) = 0.0; CF(i, 0) = 0.0; }
+      for (int k = 1; k <= N; ++k)
+        for (int i = IstrB; i <= IendB; ++i) {
+          DC(i, k) = 0.5 * (m.Hz(i, j, k) + m.Hz(i, j - 1, k));
+          DC(i, 0) = DC(i, 0) + DC(i, k);
+          CF(i, 0) = CF(i, 0) + DC(i, k) * m.v[nstp](i, j, k);
+        }
+      for (int i = IstrB; i <= IendB; ++i) { double cff1 = 1.0 / DC(i, 0); double cff2 = CF(i, 0) * cff1; m.vbar[kstp](i, j) = cff2; m.vbar[knew](i, j) = cff2; }
+    }
+  }
+  u2dbc(m, b, kstp); v2dbc(m, b, kstp); u2dbc(m, b, knew); v2dbc(m, b, knew);
+  exchange_u2d(m, b, m.ubar[kstp]); exchange_v2d(m, b, m.vbar[kstp]); exchange_u2d(m, b, m.ubar[knew]); exchange_v2d(m, b, m.vbar[knew]);
+  for (int it = 0; it < c.NT; ++it) {
+    for (int k = 1; k <= N; ++k)
+      for (int j = JstrB; j <= JendB; ++j)
+        for (int i = IstrB; i <= IendB; ++i) { double cff1 = m.t[nstp][it](i, j, k); m.t[nstp][it](i, j, k) = cff1; m.t[nnew][it](i, j, k) = cff1; }
+    t3dbc(m, b, nstp, it); t3dbc(m, b, nnew, it);
+  }
+  for (int it = 0; it < c.NT; ++it) { exchange_r3d(m, b, m.t[nstp][it]); exchange_r3d(m, b, m.t[nnew][it]); }
+}
+
+// ROMS/Nonlinear/initial.F:126-170 (indices), :271-357 (grid, mixing, depths, analytical IC), :542-574
+void initialize(Model& m) {
+  m.iif = 1; m.indx1 = 1; m.kstp = 1; m.krhs = 1; m.knew = 1; m.PREDICTOR_2D_STEP = false;
+  m.iic = 0; m.nstp = 1; m.nrhs = 1; m.nnew = 1;
+  m.tdays = 0.0; m.time = 0.0; m.ntstart = 1; m.ntfirst = 1; m.exit_flag = 0;
+  set_scoord(m);
+  set_weights(m, nullptr);
+  for (const Bnd& b : m.tiles) ana_grid(m, b);
+  for (const Bnd& b : m.tiles) metrics(m, b);
+  for (const Bnd& b : m.tiles) ini_hmixcoef(m, b);
+  for (const Bnd& b : m.tiles) set_depth(m, b);        // initial.F:337 (Zt_avg1 = 0)
+  for (const Bnd& b : m.tiles) ana_initial(m, b);      // initial.F:354
+  for (const Bnd& b : m.tiles) set_depth(m, b);        // initial.F:545
+  for (const Bnd& b : m.tiles) set_massflux(m, b);     // initial.F:556
+  for (const Bnd& b : m.tiles) { omega(m, b); }        // initial.F:570
+  for (const Bnd& b : m.tiles) { rho_eos(m, b); }      // initial.F:571
+  m.iic = m.ntstart;                                   // initial.F:855
+}
+
+}  // namespace orc
