@@ -1,0 +1,166 @@
+/*
+ * roms_b200.h -- C-ABI of the B200-native ROMS nonlinear baroclinic time step (main3d chain).
+ *
+ * This is the drop-in boundary for ONE path of ROMS: the phases that ROMS/Nonlinear/main3d.F:307-814 runs every
+ * baroclinic step.  The reference has no FFI; its seam is the `xxx(ng,tile)` -> `xxx_tile(ng,tile,LBi,UBi,LBj,UBj,
+ * IminS,ImaxS,JminS,JmaxS,<time idx>,<arrays...>)` convention (e.g. ROMS/Nonlinear/rhs3d.F:25 -> :174,
+ * ROMS/Nonlinear/prsgrd32.h:40 -> :106).  A Fortran host binds these entry points with ISO_C_BINDING
+ * (see INTEGRATION.md for the INTERFACE blocks and the one-line CALL replacements).
+ *
+ * Conventions
+ *  - plain C: pointers, ints, doubles.  No C++/torch types.  All reals are IEEE binary64 (ROMS r8, mod_kinds.F).
+ *  - every array argument is a WHOLE Fortran array in Fortran (column-major) order, i fastest:
+ *      2-D  A(LBi:UBi, LBj:UBj)            n = ni*nj
+ *      3-D  A(LBi:UBi, LBj:UBj, 1:N|0:N)   n = ni*nj*nk      (one time level / one tracer per call)
+ *    host pointers are never retained after the call returns.
+ *  - return value = ROMS exit_flag codes (ROMS/Modules/mod_scalars.F:523-532): 0 NoError, 1 blow-up, 2 input error,
+ *    5 configuration error, 8 fatal algorithm error (CUDA / NCCL failure).  The Fortran shim assigns it to exit_flag.
+ *  - the library is re-entrant per handle; one handle == one (ng,tile) == one GPU.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point returns 8.
+ */
+#ifndef ROMS_B200_H
+#define ROMS_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct roms_b200_state* roms_b200_handle;
+
+/* ROMS_APPLICATION (only selects defaults of the analytical per-step forcing kept on the device: ANA_VMIX). */
+enum { ROMS_B200_APP_UPWELLING = 0, ROMS_B200_APP_SEAMOUNT = 1, ROMS_B200_APP_BENCHMARK = 2 };
+/* Hadvection / Vadvection keywords of roms_*.in (ROMS/Modules/mod_param.F:382-394, T_ADV) */
+enum { ROMS_B200_HADV_U3 = 0, ROMS_B200_HADV_A4 = 1, ROMS_B200_HADV_C4 = 2, ROMS_B200_HADV_C2 = 3 };
+enum { ROMS_B200_VADV_C4 = 0, ROMS_B200_VADV_A4 = 1, ROMS_B200_VADV_C2 = 2 };
+
+/* Live cpp switches (ROMS/Include/{upwelling,seamount,benchmark}.h) + roms_*.in keywords for this path. */
+typedef struct roms_b200_config {
+  int Lm, Mm, N, NT;            /* mod_param.F: interior points, levels, tracers                                  */
+  int NtileI, NtileJ, tile;     /* domain partition and this handle's tile (get_bounds.F:933-1007)                 */
+  int ndtfast;                  /* NDTFAST; nfast and weights are uploaded with roms_b200_set_weights              */
+  double dt;                    /* DT (s)                                                                          */
+  int nonlin_eos;               /* NONLIN_EOS (rho_eos.F:111) else linear EOS (rho_eos.F:576)                      */
+  int dj_gradps;                /* DJ_GRADPS -> prsgrd32.h, else prsgrd31.h (prsgrd.F:16-26)                       */
+  int curvgrid;                 /* CURVGRID terms (rhs3d.F:515-564, step2d_LF_AM3.h:1333-1382)                     */
+  int mix_geo_ts;               /* MIX_GEO_TS -> t3dmix2_geo.h, else MIX_S_TS -> t3dmix2_s.h                       */
+  int uv_qdrag;                 /* UV_QDRAG (set_vbc.F:591-624) else UV_LDRAG (set_vbc.F:629-652)                  */
+  int salinity;                 /* SALINITY                                                                        */
+  int ana_vmix;                 /* ANA_VMIX, UPWELLING profile (ana_vmix.h:200-208,327-337), refreshed every step  */
+  int wvelocity_every_step;     /* main3d.F:475                                                                    */
+  int hadv, vadv;               /* tracer advection schemes                                                        */
+  double rho0, g;               /* mod_scalars.F                                                                   */
+  double R0, T0, S0, Tcoef, Scoef;   /* linear EOS                                                                 */
+  double Akt_bak[2], Akv_bak;   /* background mixing (ANA_VMIX)                                                    */
+  double gamma2;                /* slipperiness (u2dbc_im.F:973)                                                   */
+  double lambda;                /* implicit weight of vertical diffusion (mod_scalars.F), 1.0                      */
+  double hc;                    /* s-coordinate critical depth (set_scoord.F:170-178)                              */
+  int itemp, isalt;             /* 1-based tracer indices                                                          */
+  int device;                   /* CUDA device ordinal                                                             */
+} roms_b200_config;
+
+/* Fills *cfg with the shipped defaults of roms_<app>.in (Lm,Mm,N = 0 keeps the shipped grid size). */
+int roms_b200_default_config(int app, int Lm, int Mm, int N, roms_b200_config* cfg);
+
+/* Tile index sets.  Replaces get_bounds / var_bounds / tile.h (ROMS/Utility/get_bounds.F:2-258, :933-1853).
+ * distribute != 0 gives the DISTRIBUTE array bounds (:165-185), else the shared-memory ones (:229-253).
+ * out[57] in the order documented in roms_b200_bounds_names(). */
+int roms_b200_bounds(int Lm, int Mm, int NtileI, int NtileJ, int tile, int distribute, int* out57);
+const char* roms_b200_bounds_names(void);   /* comma-separated names of the 57 integers */
+
+/* ---- resident form -------------------------------------------------------------------------------------------- */
+int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out);
+int roms_b200_destroy(roms_b200_handle h);
+/* array bounds of this handle's tile: LBi, UBi, LBj, UBj */
+int roms_b200_array_bounds(roms_b200_handle h, int* out4);
+
+/* Field transfer by name.  Names follow the reference's module members: grid (mod_grid.F) "h","f","pm","pn","om_r",
+ * "on_r","om_u","on_u","om_v","on_v","om_p","on_p","omn","fomn","pmon_r","pnom_r","pmon_u","pnom_u","pmon_v","pnom_v",
+ * "pmon_p","pnom_p","dndx","dmde","rdrag","rdrag2"; mixing (mod_mixing.F) "visc2_r","visc2_p","diff2_<itrc>","Akv",
+ * "Akt_<itrc>"; ocean (mod_ocean.F) "zeta<1-3>","ubar<1-3>","vbar<1-3>","rzeta<1-2>","rubar<1-2>","rvbar<1-2>",
+ * "u<1-2>","v<1-2>","t<1-3>_<itrc>","ru<1-2>","rv<1-2>","rho","pden","W","wvel"; depths "Hz","z_r","z_w","Huon","Hvom";
+ * coupling (mod_coupling.F) "Zt_avg1","DU_avg1","DU_avg2","DV_avg1","DV_avg2","rufrc","rvfrc","rhoA","rhoS";
+ * forces (mod_forces.F) "sustr","svstr","bustr","bvstr","stflx_<itrc>","btflx_<itrc>","stflux_<itrc>","btflux_<itrc>".
+ * <itrc> is 0-based.  n = number of doubles in the whole Fortran array (checked). */
+int roms_b200_set_field(roms_b200_handle h, const char* name, const double* host, size_t n);
+int roms_b200_get_field(roms_b200_handle h, const char* name, double* host, size_t n);
+/* s-coordinate vectors (mod_scalars.F SCALARS%): which = 0 sc_r, 1 Cs_r, 2 sc_w, 3 Cs_w; n = N+1 values indexed by k */
+int roms_b200_set_scoord(roms_b200_handle h, int which, const double* v, int n);
+/* barotropic filter (set_weights.F): weight(1,:), weight(2,:) with 2*ndtfast+2 values each (slot 0 unused), nfast */
+int roms_b200_set_weights(roms_b200_handle h, int nfast, const double* w1, const double* w2, int n);
+
+/* time-index state machine (mod_stepping.F:64-72, main3d.F:189-191,599-611,656-661):
+ * idx[13] = iic, ntstart, ntfirst, nstp, nnew, nrhs, iif, indx1, kstp, krhs, knew, PREDICTOR_2D_STEP, exit_flag;
+ * tm[2] = time (s), tdays */
+int roms_b200_set_indices(roms_b200_handle h, const int* idx13, const double* tm2);
+int roms_b200_get_indices(roms_b200_handle h, int* idx13, double* tm2);
+
+/* One phase of main3d on this tile, enqueue + synchronise.  Phase ids: */
+enum {
+  ROMS_B200_SET_MASSFLUX = 1,  /* set_massflux.F:73      */  ROMS_B200_RHO_EOS = 2,      /* rho_eos.F:111/:576     */
+  ROMS_B200_SET_VBC = 3,       /* set_vbc.F:104          */  ROMS_B200_ANA_VMIX = 4,     /* ana_vmix.h             */
+  ROMS_B200_OMEGA = 5,         /* omega.F:73             */  ROMS_B200_WVELOCITY = 6,    /* wvelocity.F:61         */
+  ROMS_B200_SET_ZETA = 7,      /* set_zeta.F:59          */  ROMS_B200_PRE_STEP3D = 8,   /* pre_step3d.F:123       */
+  ROMS_B200_PRSGRD = 9,        /* prsgrd32.h:106/31:97   */  ROMS_B200_T3DMIX = 10,      /* t3dmix2_s.h:89/_geo:90 */
+  ROMS_B200_RHS3D = 11,        /* rhs3d.F:174            */  ROMS_B200_UV3DMIX = 12,     /* uv3dmix2_s.h:114       */
+  ROMS_B200_STEP2D = 13,       /* step2d_LF_AM3.h:137    */  ROMS_B200_SET_DEPTH = 14,   /* set_depth.F:82         */
+  ROMS_B200_STEP3D_UV = 15,    /* step3d_uv.F:111        */  ROMS_B200_OMEGA2 = 16,      /* main3d.F:789           */
+  ROMS_B200_STEP3D_T = 17,     /* step3d_t.F:108         */  ROMS_B200_DIAG = 18,        /* diag.F:80              */
+  ROMS_B200_SET_DATA = 19,     /* (host forcing; no-op)  */  ROMS_B200_STEP2D_LOOP = 20  /* main3d.F:592-700       */
+};
+int roms_b200_run_phase(roms_b200_handle h, int phase);
+
+/* nsteps baroclinic steps, device resident (main3d.F:189-917 without get_data/output).  Asynchronous: returns after
+ * enqueueing; roms_b200_sync waits.  Forcing (sustr, svstr, stflux, btflux) is whatever was last uploaded. */
+int roms_b200_main3d_step(roms_b200_handle h, int nsteps);
+int roms_b200_sync(roms_b200_handle h);
+/* One step the way main3d sees it from the host: H2D of this step's surface forcing (the set_data products
+ * sustr(LBi:UBi,LBj:UBj), svstr, and optionally stflux for each tracer; NULL keeps the resident value), the step,
+ * then D2H of the diag scalars.  out12 = avgke, avgpe, avgkp, volume, max_speed, maxCu, maxCv, maxCw,
+ * ubarmax, vbarmax, umax, vmax (diag.F:293-437, ana_diag.h:116-142).  Synchronous. */
+int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double* svstr, const double* stflux_temp,
+                          size_t n2d, double* out12);
+int roms_b200_diag(roms_b200_handle h, double* out12);
+
+/* timing helpers for bench.py: elapsed device ms between two internal CUDA events bracketing the last
+ * roms_b200_main3d_step call; per-phase accumulated device ms since the last reset (wclock regions, timers.F). */
+int roms_b200_last_step_ms(roms_b200_handle h, float* ms);
+int roms_b200_profile_enable(roms_b200_handle h, int on);
+int roms_b200_profile_get(roms_b200_handle h, double* ms_by_phase32, long long* launches);
+long long roms_b200_launch_count(roms_b200_handle h);
+
+/* multi-GPU: ring neighbours in xi (NtileI>1, NtileJ==1).  comm is an ncclComm_t created by the caller (one rank per
+ * tile); the library then performs mp_exchange2d/3d/4d (ROMS/Utility/mp_exchange.F:1413-2128) with grouped
+ * ncclSend/ncclRecv on its own stream. */
+int roms_b200_attach_nccl(roms_b200_handle h, void* nccl_comm, int rank, int nranks);
+int roms_b200_nccl_unique_id(char* out128);
+int roms_b200_nccl_init_rank(const char* id128, int rank, int nranks, void** comm_out);
+
+/* ---- per-routine host-pointer form (mirrors the _tile argument lists; used by the parity tests) ---------------- */
+/* roms_b200_tile_t carries what tile.h/set_bounds.h give a _tile routine. */
+typedef struct roms_b200_tile_t {
+  roms_b200_config cfg;        /* cfg.tile selects the tile                                                       */
+  int iic, ntfirst;            /* start-up branches (pre_step3d.F:947, step3d_uv.F:305, step2d_LF_AM3.h:1885)      */
+  int nstp, nnew, nrhs;        /* 3-D time indices                                                                */
+  int iif, kstp, krhs, knew, predictor;   /* 2-D time indices, PREDICTOR_2D_STEP                                   */
+} roms_b200_tile_t;
+
+/* rho_eos_tile (rho_eos.F:111 / :576): t = t(:,:,:,nrhs,itemp), s = t(:,:,:,nrhs,isalt) or NULL */
+int roms_b200_rho_eos_tile(const roms_b200_tile_t* b, const double* Hz, const double* z_r, const double* z_w,
+                           const double* t, const double* s, double* rhoA, double* rhoS, double* pden, double* rho);
+/* prsgrd32_tile / prsgrd31_tile (prsgrd32.h:106, prsgrd31.h:97): ru, rv = ru(:,:,0:N,nrhs), rv(:,:,0:N,nrhs) */
+int roms_b200_prsgrd_tile(const roms_b200_tile_t* b, const double* Hz, const double* om_v, const double* on_u,
+                          const double* z_r, const double* z_w, const double* rho, double* ru, double* rv);
+/* set_massflux_tile (set_massflux.F:73) */
+int roms_b200_set_massflux_tile(const roms_b200_tile_t* b, const double* u, const double* v, const double* Hz,
+                                const double* om_v, const double* on_u, double* Huon, double* Hvom);
+/* omega_tile (omega.F:73) */
+int roms_b200_omega_tile(const roms_b200_tile_t* b, const double* Huon, const double* Hvom, const double* z_w, double* W);
+/* set_depth_tile (set_depth.F:82), Vtransform = 2: sc/Cs vectors have N+1 entries indexed by k */
+int roms_b200_set_depth_tile(const roms_b200_tile_t* b, const double* h, const double* Zt_avg1, const double* sc_r,
+                             const double* Cs_r, const double* sc_w, const double* Cs_w, double* Hz, double* z_r, double* z_w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROMS_B200_H */

@@ -154,6 +154,11 @@ void run_phase(Model& m, int phase, int nthreads) {
     case PH_SET_DEPTH: for_tiles(m, nthreads, [&](const Bnd& b) { set_depth(m, b); }); break;
     case PH_STEP3D_UV: for_tiles(m, nthreads, [&](const Bnd& b) { step3d_uv(m, b); }); break;
     case PH_STEP3D_T: for_tiles(m, nthreads, [&](const Bnd& b) { step3d_t(m, b); }); break;
+    case PH_INI:                                                       // main3d.F:189-191, :269-285 (first step only)
+      m.nstp = 1 + ((m.iic - m.ntstart) % 2); m.nnew = 3 - m.nstp; m.nrhs = m.nstp;
+      for_tiles(m, nthreads, [&](const Bnd& b) { ini_zeta(m, b); set_depth(m, b); });
+      for_tiles(m, nthreads, [&](const Bnd& b) { ini_fields(m, b); });
+      break;
     default: std::fprintf(stderr, "oracle: unknown phase %d\n", phase); std::abort();
   }
 }

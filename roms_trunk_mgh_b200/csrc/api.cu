@@ -1,0 +1,527 @@
+// C-ABI (include/roms_b200.h) + device-resident state + the main3d orchestration for one tile on one B200.
+// The product path has no CPU fallback: every compute entry point needs a CUDA device and returns exit_flag 8 otherwise.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include <map>
+#include <algorithm>
+#include "../../include/roms_b200.h"
+#include "dev.cuh"
+#include "kernels.h"
+
+using namespace rb;
+
+namespace {
+
+enum { NoError = 0, BlowUp = 1, InputError = 2, ConfigError = 5, FatalError = 8 };
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      std::fprintf(stderr, "roms_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return FatalError;                                                                                 \
+    }                                                                                                    \
+  } while (0)
+
+// ---- tile index sets: ROMS/Utility/get_bounds.F (tile_bounds_2d :933-1007, var_bounds :1009-1853, get_bounds :60-258)
+struct Bounds {
+  int tile, Itile, Jtile, LBi, UBi, LBj, UBj, IminS, ImaxS, JminS, JmaxS;
+  int Istr, IstrB, IstrP, IstrR, IstrT, IstrM, IstrU, Iend, IendB, IendP, IendR, IendT;
+  int Jstr, JstrB, JstrP, JstrR, JstrT, JstrM, JstrV, Jend, JendB, JendP, JendR, JendT;
+  int Istrm3, Istrm2, Istrm1, IstrUm2, IstrUm1, Iendp1, Iendp2, Iendp2i, Iendp3;
+  int Jstrm3, Jstrm2, Jstrm1, JstrVm2, JstrVm1, Jendp1, Jendp2, Jendp2i, Jendp3;
+  int west, east, south, north;
+};
+
+void tile_range(int n, int ntile, int t, int& s, int& e) {
+  const int chunk = (n + ntile - 1) / ntile;
+  const int margin = (ntile * chunk - n) / 2;
+  s = 1 + t * chunk - margin;
+  e = s + chunk - 1;
+  s = std::max(s, 1);
+  e = std::min(e, n);
+}
+
+// EW periodic, NS closed (the LBC set of all supported applications)
+void make_bounds(int Lm, int Mm, int NtileI, int NtileJ, int tile, bool distribute, Bounds& b) {
+  const int Ng = 2;
+  b.tile = tile; b.Jtile = tile / NtileI; b.Itile = tile - b.Jtile * NtileI;
+  int is, ie, js, je;
+  tile_range(Lm, NtileI, b.Itile, is, ie);
+  tile_range(Mm, NtileJ, b.Jtile, js, je);
+  b.west = b.Itile == 0; b.east = b.Itile == NtileI - 1; b.south = b.Jtile == 0; b.north = b.Jtile == NtileJ - 1;
+  // xi: periodic -> no clipping on any tile
+  b.Istr = b.IstrP = b.IstrR = b.IstrT = b.IstrU = b.IstrB = b.IstrM = is;
+  b.Istrm3 = is - 3; b.Istrm2 = is - 2; b.Istrm1 = is - 1; b.IstrUm2 = is - 2; b.IstrUm1 = is - 1;
+  b.Iend = b.IendR = b.IendP = b.IendT = b.IendB = ie;
+  b.Iendp1 = ie + 1; b.Iendp2 = ie + 2; b.Iendp2i = ie + 2; b.Iendp3 = ie + 3;
+  // eta: closed walls on the southern / northern edge tiles
+  b.Jstr = b.JstrP = js;
+  if (b.south) {
+    b.JstrR = js - 1; b.JstrT = b.JstrR; b.JstrV = js + 1; b.JstrB = b.JstrT + 1; b.JstrM = b.JstrP + 1;
+    b.Jstrm3 = std::max(0, js - 3); b.Jstrm2 = std::max(0, js - 2); b.JstrVm2 = std::max(1, b.JstrV - 2);
+    b.Jstrm1 = std::max(1, js - 1); b.JstrVm1 = std::max(2, b.JstrV - 1);
+  } else {
+    b.JstrR = b.JstrT = b.JstrV = b.JstrB = b.JstrM = js;
+    b.Jstrm3 = js - 3; b.Jstrm2 = js - 2; b.JstrVm2 = js - 2; b.Jstrm1 = js - 1; b.JstrVm1 = js - 1;
+  }
+  b.Jend = je;
+  if (b.north) {
+    b.JendR = je + 1; b.JendP = b.JendR; b.JendT = b.JendR; b.JendB = b.JendT - 1;
+    b.Jendp1 = std::min(je + 1, Mm); b.Jendp2i = std::min(je + 2, Mm); b.Jendp2 = std::min(je + 2, Mm + 1); b.Jendp3 = std::min(je + 3, Mm + 1);
+  } else {
+    b.JendR = b.JendP = b.JendT = b.JendB = je;
+    b.Jendp1 = je + 1; b.Jendp2i = je + 2; b.Jendp2 = je + 2; b.Jendp3 = je + 3;
+  }
+  b.IminS = is - 3; b.ImaxS = ie + 3; b.JminS = js - 3; b.JmaxS = je + 3;
+  const int Imin = -Ng, Imax = Lm + Ng, Jmin = 0, Jmax = Mm + 1;
+  if (distribute) {
+    b.LBi = (b.Itile == 0) ? Imin : is - Ng;
+    b.UBi = (b.Itile == NtileI - 1) ? Imax : ie + Ng;
+    b.LBj = (b.Jtile == 0) ? Jmin : js - Ng;
+    b.UBj = (b.Jtile == NtileJ - 1) ? Jmax : je + Ng;
+  } else {
+    b.LBi = Imin; b.UBi = Imax; b.LBj = Jmin; b.UBj = Jmax;
+  }
+}
+
+struct FieldInfo { double** slot; int LBk, nk; double* base; };
+
+}  // namespace
+
+struct roms_b200_state {
+  roms_b200_config cfg;
+  Bounds b;
+  Par par;
+  Flds fl;
+  int ni, nj, ioff;
+  std::map<std::string, FieldInfo> reg;
+  std::vector<void*> allocs;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // stepping state (mod_stepping.F)
+  int iic = 1, ntstart = 1, ntfirst = 1, nstp = 1, nnew = 1, nrhs = 1, iif = 1, indx1 = 1, kstp = 1, krhs = 1, knew = 1, predictor = 0, exit_flag = 0;
+  double time = 0.0, tdays = 0.0;
+  int nfast = 0;
+  std::vector<double> w1, w2;
+  double dtfast = 0.0;
+  // diag
+  double* d_diag_partial = nullptr; double* d_diag_out = nullptr; double* h_diag_out = nullptr;
+  double* h_pinned = nullptr; size_t pinned_n = 0;
+  // profiling
+  int profile = 0; double phase_ms[32]; long long launches = 0;
+  bool all_diff2_zero = true;
+};
+
+namespace {
+
+int alloc_field(roms_b200_state* h, const std::string& name, double** slot, int LBk, int nk) {
+  const size_t n = (size_t)h->par.PL * nk;
+  double* base = nullptr;
+  CK(cudaMalloc(&base, n * sizeof(double)));
+  CK(cudaMemsetAsync(base, 0, n * sizeof(double), h->stream));
+  h->allocs.push_back(base);
+  // element (i,j,k) lives at base[(i-LBi+ioff) + (j-LBj)*P + (k-LBk)*PL]
+  *slot = base + h->ioff - h->b.LBi - (ptrdiff_t)h->b.LBj * h->par.P - (ptrdiff_t)LBk * h->par.PL;
+  h->reg[name] = FieldInfo{slot, LBk, nk, base};
+  return NoError;
+}
+
+void fill_par(roms_b200_state* h) {
+  Par& p = h->par;
+  p.nstp = h->nstp; p.nnew = h->nnew; p.nrhs = h->nrhs;
+  p.istart = (h->iic == h->ntfirst) ? 0 : (h->iic == h->ntfirst + 1 ? 1 : 2);
+  p.iif = h->iif; p.kstp = h->kstp; p.krhs = h->krhs; p.knew = h->knew; p.ptsk = 3 - h->kstp; p.predictor = h->predictor; p.nfast = h->nfast;
+  p.dtfast = h->dtfast;
+  auto W1 = [&](int i) { return (i >= 0 && i < (int)h->w1.size()) ? h->w1[i] : 0.0; };
+  auto W2 = [&](int i) { return (i >= 0 && i < (int)h->w2.size()) ? h->w2[i] : 0.0; };
+  p.w1_m1 = W1(h->iif - 1); p.w2_0 = W2(h->iif); p.w2_p1 = W2(h->iif + 1);
+}
+
+struct PhaseTimer {
+  roms_b200_state* h; int phase; cudaEvent_t a = nullptr, b = nullptr;
+  PhaseTimer(roms_b200_state* h_, int ph) : h(h_), phase(ph) {
+    if (h->profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, h->stream); }
+  }
+  ~PhaseTimer() {
+    if (h->profile) {
+      cudaEventRecord(b, h->stream); cudaEventSynchronize(b);
+      float ms = 0; cudaEventElapsedTime(&ms, a, b); h->phase_ms[phase & 31] += ms;
+      cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+  }
+};
+
+int run_phase_async(roms_b200_state* h, int phase) {
+  fill_par(h);
+  const Par& p = h->par; const Flds& f = h->fl; cudaStream_t s = h->stream;
+  PhaseTimer pt(h, phase);
+  switch (phase) {
+    case ROMS_B200_SET_DATA: break;
+    case ROMS_B200_SET_MASSFLUX: launch_set_massflux(p, f, s); h->launches += 1; break;
+    case ROMS_B200_RHO_EOS: launch_rho_eos(p, f, s); h->launches += 1; break;
+    case ROMS_B200_SET_VBC: launch_set_vbc(p, f, s); h->launches += 1; break;
+    case ROMS_B200_ANA_VMIX: if (h->cfg.ana_vmix) { launch_ana_vmix(p, f, s); h->launches += 1; } break;
+    case ROMS_B200_OMEGA: case ROMS_B200_OMEGA2: launch_omega(p, f, s); h->launches += 1; break;
+    case ROMS_B200_WVELOCITY: launch_wvelocity(p, f, h->nstp, s); h->launches += 1; break;
+    case ROMS_B200_SET_ZETA: launch_set_zeta(p, f, s); h->launches += 1; break;
+    case ROMS_B200_PRE_STEP3D: launch_pre_step3d(p, f, s); h->launches += 2; break;
+    case ROMS_B200_PRSGRD: launch_prsgrd(p, f, h->cfg.dj_gradps, s); h->launches += h->cfg.dj_gradps ? 2 : 1; break;
+    case ROMS_B200_T3DMIX:
+      if (h->cfg.mix_geo_ts) {
+        if (!h->all_diff2_zero) { launch_t3dmix2_geo(p, f, s); h->launches += 1; }   // diff2 == 0: exact no-op
+      } else { launch_t3dmix2_s(p, f, s); h->launches += 1; }
+      break;
+    case ROMS_B200_RHS3D: launch_rhs3d(p, f, s); h->launches += 1; break;
+    case ROMS_B200_UV3DMIX: launch_uv3dmix2(p, f, s); h->launches += 1; break;
+    case ROMS_B200_STEP2D: launch_step2d(p, f, s); h->launches += 1; break;
+    case ROMS_B200_SET_DEPTH: launch_set_depth(p, f, s); h->launches += 1; break;
+    case ROMS_B200_STEP3D_UV: launch_step3d_uv(p, f, s); h->launches += 2; break;
+    case ROMS_B200_STEP3D_T: launch_step3d_t(p, f, s); h->launches += 1; break;
+    case ROMS_B200_DIAG: launch_diag(p, f, h->d_diag_partial, h->d_diag_out, h->knew, s); h->launches += 3; break;
+    case ROMS_B200_STEP2D_LOOP: {
+      // main3d.F:592-700
+      for (int my_iif = 1; my_iif <= h->nfast + 1; ++my_iif) {
+        const int next_indx1 = 3 - h->indx1;
+        if (!h->predictor && my_iif <= h->nfast + 1) {
+          h->predictor = 1; h->iif = my_iif;
+          h->kstp = (h->iif == 1) ? h->indx1 : 3 - h->indx1;
+          h->knew = 3; h->krhs = h->indx1;
+        }
+        if (my_iif <= h->nfast + 1) { fill_par(h); launch_step2d(h->par, f, s); h->launches += 1; }
+        if (h->predictor) {
+          h->predictor = 0; h->knew = next_indx1; h->kstp = 3 - h->knew; h->krhs = 3;
+          if (h->iif < h->nfast + 1) h->indx1 = next_indx1;
+        }
+        if (h->iif < h->nfast + 1) { fill_par(h); launch_step2d(h->par, f, s); h->launches += 1; }
+      }
+      break;
+    }
+    default: return ConfigError;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { std::fprintf(stderr, "roms_b200: launch error in phase %d: %s\n", phase, cudaGetErrorString(e)); return FatalError; }
+  return NoError;
+}
+
+// main3d.F:189-917 for one step (without the first-step ini_zeta/ini_fields block and without get_data/output)
+int one_step(roms_b200_state* h, bool with_diag) {
+  h->nstp = 1 + ((h->iic - h->ntstart) % 2); h->nnew = 3 - h->nstp; h->nrhs = h->nstp;
+  h->tdays = h->time / 86400.0;
+  static const int seq1[] = {ROMS_B200_SET_MASSFLUX, ROMS_B200_RHO_EOS};
+  for (int ph : seq1) { int rc = run_phase_async(h, ph); if (rc) return rc; }
+  if (with_diag) { int rc = run_phase_async(h, ROMS_B200_DIAG); if (rc) return rc; }
+  static const int seq2[] = {ROMS_B200_SET_VBC, ROMS_B200_ANA_VMIX, ROMS_B200_OMEGA};
+  for (int ph : seq2) { int rc = run_phase_async(h, ph); if (rc) return rc; }
+  if (h->cfg.wvelocity_every_step) { int rc = run_phase_async(h, ROMS_B200_WVELOCITY); if (rc) return rc; }
+  static const int seq3[] = {ROMS_B200_SET_ZETA,  ROMS_B200_PRE_STEP3D, ROMS_B200_PRSGRD,    ROMS_B200_T3DMIX,   ROMS_B200_RHS3D, ROMS_B200_UV3DMIX,
+                             ROMS_B200_STEP2D_LOOP, ROMS_B200_SET_DEPTH, ROMS_B200_STEP3D_UV, ROMS_B200_OMEGA2, ROMS_B200_STEP3D_T};
+  for (int ph : seq3) { int rc = run_phase_async(h, ph); if (rc) return rc; }
+  h->iic += 1; h->time += h->cfg.dt;
+  return NoError;
+}
+
+int finish_diag(roms_b200_state* h, double* out12) {
+  CK(cudaMemcpyAsync(h->h_diag_out, h->d_diag_out, 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const double* d = h->h_diag_out;
+  const double vol = d[2];
+  out12[0] = d[0] / vol; out12[1] = d[1] / vol; out12[2] = out12[0] + out12[1]; out12[3] = vol;
+  out12[4] = d[7]; out12[5] = d[4]; out12[6] = d[5]; out12[7] = d[6];
+  out12[8] = d[11]; out12[9] = d[12]; out12[10] = d[9]; out12[11] = d[10];
+  // blow-up detection: diag.F:506-538, limits mod_scalars.F:548-549
+  const bool bad = !(out12[0] == out12[0]) || !(out12[1] == out12[1]) || std::abs(out12[0]) > 1e300 || std::abs(out12[1]) > 1e300;
+  if (bad || d[7] > 20.0 || d[8] > 200.0) h->exit_flag = BlowUp;
+  return h->exit_flag;
+}
+
+}  // namespace
+
+extern "C" {
+
+int roms_b200_default_config(int app, int Lm, int Mm, int N, roms_b200_config* c) {
+  if (!c) return InputError;
+  std::memset(c, 0, sizeof(*c));
+  c->NtileI = 1; c->NtileJ = 1; c->tile = 0; c->rho0 = 1025.0; c->g = 9.81; c->lambda = 1.0; c->itemp = 1; c->isalt = 2;
+  c->dj_gradps = 1; c->wvelocity_every_step = 1; c->R0 = 1027.0; c->Tcoef = 1.7e-4; c->device = 0;
+  if (app == ROMS_B200_APP_UPWELLING) {          // ROMS/Include/upwelling.h, ROMS/External/roms_upwelling.in
+    c->Lm = 41; c->Mm = 80; c->N = 16; c->NT = 2; c->dt = 300.0; c->ndtfast = 30; c->salinity = 1; c->ana_vmix = 1;
+    c->hadv = ROMS_B200_HADV_U3; c->vadv = ROMS_B200_VADV_C4; c->T0 = 14.0; c->S0 = 35.0; c->Scoef = 0.0;
+    c->Akt_bak[0] = c->Akt_bak[1] = 1e-6; c->Akv_bak = 1e-5; c->gamma2 = 1.0; c->hc = 25.0;
+  } else if (app == ROMS_B200_APP_SEAMOUNT) {    // seamount.h, roms_seamount.in
+    c->Lm = 49; c->Mm = 48; c->N = 13; c->NT = 1; c->dt = 60.0; c->ndtfast = 20; c->mix_geo_ts = 1; c->uv_qdrag = 1;
+    c->hadv = ROMS_B200_HADV_A4; c->vadv = ROMS_B200_VADV_A4; c->T0 = 10.0; c->S0 = 32.0; c->Scoef = 7.6e-4;
+    c->Akt_bak[0] = c->Akt_bak[1] = 1e-6; c->Akv_bak = 1e-5; c->gamma2 = -1.0; c->hc = 100.0;
+  } else if (app == ROMS_B200_APP_BENCHMARK) {   // benchmark.h grid/IC with the reduced physics set, roms_benchmark1.in
+    c->Lm = 512; c->Mm = 64; c->N = 30; c->NT = 2; c->dt = 150.0; c->ndtfast = 20; c->nonlin_eos = 1; c->curvgrid = 1;
+    c->uv_qdrag = 1; c->salinity = 1; c->hadv = ROMS_B200_HADV_U3; c->vadv = ROMS_B200_VADV_C4; c->T0 = 10.0; c->S0 = 35.0;
+    c->Scoef = 7.6e-4; c->Akt_bak[0] = c->Akt_bak[1] = 1e-5; c->Akv_bak = 1e-4; c->gamma2 = 1.0; c->hc = 400.0;
+  } else return ConfigError;
+  if (Lm > 0) c->Lm = Lm;
+  if (Mm > 0) c->Mm = Mm;
+  if (N > 0) c->N = N;
+  return NoError;
+}
+
+static const char* kBoundNames =
+    "tile,Itile,Jtile,LBi,UBi,LBj,UBj,IminS,ImaxS,JminS,JmaxS,Istr,IstrB,IstrP,IstrR,IstrT,IstrM,IstrU,Iend,IendB,IendP,IendR,IendT,"
+    "Jstr,JstrB,JstrP,JstrR,JstrT,JstrM,JstrV,Jend,JendB,JendP,JendR,JendT,Istrm3,Istrm2,Istrm1,IstrUm2,IstrUm1,Iendp1,Iendp2,Iendp2i,"
+    "Iendp3,Jstrm3,Jstrm2,Jstrm1,JstrVm2,JstrVm1,Jendp1,Jendp2,Jendp2i,Jendp3,Western_Edge,Eastern_Edge,Southern_Edge,Northern_Edge";
+const char* roms_b200_bounds_names(void) { return kBoundNames; }
+
+int roms_b200_bounds(int Lm, int Mm, int NtileI, int NtileJ, int tile, int distribute, int* o) {
+  if (!o || Lm < 1 || Mm < 1 || NtileI < 1 || NtileJ < 1 || tile < 0 || tile >= NtileI * NtileJ) return InputError;
+  Bounds b; make_bounds(Lm, Mm, NtileI, NtileJ, tile, distribute != 0, b);
+  const int v[57] = {b.tile, b.Itile, b.Jtile, b.LBi, b.UBi, b.LBj, b.UBj, b.IminS, b.ImaxS, b.JminS, b.JmaxS, b.Istr, b.IstrB, b.IstrP, b.IstrR,
+                     b.IstrT, b.IstrM, b.IstrU, b.Iend, b.IendB, b.IendP, b.IendR, b.IendT, b.Jstr, b.JstrB, b.JstrP, b.JstrR, b.JstrT, b.JstrM,
+                     b.JstrV, b.Jend, b.JendB, b.JendP, b.JendR, b.JendT, b.Istrm3, b.Istrm2, b.Istrm1, b.IstrUm2, b.IstrUm1, b.Iendp1, b.Iendp2,
+                     b.Iendp2i, b.Iendp3, b.Jstrm3, b.Jstrm2, b.Jstrm1, b.JstrVm2, b.JstrVm1, b.Jendp1, b.Jendp2, b.Jendp2i, b.Jendp3,
+                     b.west, b.east, b.south, b.north};
+  std::memcpy(o, v, sizeof(v));
+  return NoError;
+}
+
+int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
+  if (!cfg || !out) return InputError;
+  *out = nullptr;
+  if (cfg->N < 4 || cfg->N > MAXN || cfg->NT < 1 || cfg->NT > MAXNT || cfg->Lm < 8 || cfg->Mm < 4) return ConfigError;
+  if (cfg->NtileJ != 1 || cfg->NtileI < 1 || cfg->tile < 0 || cfg->tile >= cfg->NtileI) {
+    std::fprintf(stderr, "roms_b200: only NtileI x 1 partitions are supported (NtileJ must be 1)\n");
+    return ConfigError;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    std::fprintf(stderr, "roms_b200: no CUDA device; this library has no CPU fallback\n");
+    return FatalError;
+  }
+  CK(cudaSetDevice(cfg->device));
+  roms_b200_state* h = new roms_b200_state();
+  h->cfg = *cfg;
+  make_bounds(cfg->Lm, cfg->Mm, cfg->NtileI, cfg->NtileJ, cfg->tile, cfg->NtileI > 1, h->b);
+  const Bounds& b = h->b;
+  h->ni = b.UBi - b.LBi + 1; h->nj = b.UBj - b.LBj + 1;
+  // origin shift: put i = Istr on a 128-byte boundary
+  h->ioff = (16 - ((b.Istr - b.LBi) % 16)) % 16;
+  Par& p = h->par;
+  std::memset(&p, 0, sizeof(p));
+  p.Lm = cfg->Lm; p.Mm = cfg->Mm; p.N = cfg->N; p.NT = cfg->NT;
+  p.P = ((h->ioff + h->ni + 15) / 16) * 16; p.PL = p.P * h->nj;
+  if ((long long)p.PL * (cfg->N + 1) >= (1LL << 31)) { delete h; return ConfigError; }
+  p.LBi = b.LBi; p.UBi = b.UBi; p.LBj = b.LBj; p.UBj = b.UBj;
+  p.Istr = b.Istr; p.Iend = b.Iend; p.Jstr = b.Jstr; p.Jend = b.Jend; p.IstrU = b.IstrU; p.JstrV = b.JstrV; p.JstrR = b.JstrR; p.JendR = b.JendR;
+  p.Jstrm1 = b.Jstrm1; p.Jendp1 = b.Jendp1; p.Jendp2 = b.Jendp2; p.JstrVm1 = b.JstrVm1; p.JstrVm2 = b.JstrVm2;
+  p.ew_wrap = (cfg->NtileI == 1) ? 1 : 0;
+  p.nonlin_eos = cfg->nonlin_eos; p.curvgrid = cfg->curvgrid; p.uv_qdrag = cfg->uv_qdrag; p.salinity = cfg->salinity;
+  p.hadv = cfg->hadv; p.vadv = cfg->vadv; p.itemp = cfg->itemp; p.isalt = cfg->isalt;
+  p.dt = cfg->dt; p.g = cfg->g; p.rho0 = cfg->rho0; p.R0 = cfg->R0; p.T0 = cfg->T0; p.S0 = cfg->S0; p.Tcoef = cfg->Tcoef; p.Scoef = cfg->Scoef;
+  p.gamma2 = cfg->gamma2; p.lambda = cfg->lambda; p.hc = cfg->hc; p.Akv_bak = cfg->Akv_bak;
+  for (int it = 0; it < MAXNT; ++it) p.Akt_bak[it] = cfg->Akt_bak[it];
+  h->dtfast = cfg->dt / (double)cfg->ndtfast;
+  std::memset(h->phase_ms, 0, sizeof(h->phase_ms));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+  Flds& f = h->fl;
+  std::memset(&f, 0, sizeof(f));
+  const int N = cfg->N;
+  int rc = 0;
+#define A2(name) rc |= alloc_field(h, #name, &f.name, 0, 1)
+#define A3(name, k0, nk) rc |= alloc_field(h, #name, &f.name, k0, nk)
+  A2(h); A2(f); A2(pm); A2(pn); A2(om_r); A2(on_r); A2(om_u); A2(on_u); A2(om_v); A2(on_v); A2(om_p); A2(on_p); A2(omn); A2(fomn);
+  A2(pmon_r); A2(pnom_r); A2(pmon_u); A2(pnom_u); A2(pmon_v); A2(pnom_v); A2(pmon_p); A2(pnom_p); A2(dndx); A2(dmde); A2(rdrag); A2(rdrag2);
+  A2(visc2_r); A2(visc2_p); A2(Zt_avg1); A2(DU_avg1); A2(DU_avg2); A2(DV_avg1); A2(DV_avg2); A2(rufrc); A2(rvfrc); A2(rhoA); A2(rhoS);
+  A2(sustr); A2(svstr); A2(bustr); A2(bvstr);
+  A3(rho, 1, N); A3(pden, 1, N); A3(Hz, 1, N); A3(z_r, 1, N); A3(Huon, 1, N); A3(Hvom, 1, N); A3(W, 0, N + 1); A3(wvel, 0, N + 1);
+  A3(z_w, 0, N + 1); A3(Akv, 0, N + 1); A3(P3, 1, N);
+#undef A2
+#undef A3
+  for (int k = 1; k <= 3; ++k) {
+    rc |= alloc_field(h, "zeta" + std::to_string(k), &f.zeta[k], 0, 1);
+    rc |= alloc_field(h, "ubar" + std::to_string(k), &f.ubar[k], 0, 1);
+    rc |= alloc_field(h, "vbar" + std::to_string(k), &f.vbar[k], 0, 1);
+  }
+  for (int k = 1; k <= 2; ++k) {
+    rc |= alloc_field(h, "rzeta" + std::to_string(k), &f.rzeta[k], 0, 1);
+    rc |= alloc_field(h, "rubar" + std::to_string(k), &f.rubar[k], 0, 1);
+    rc |= alloc_field(h, "rvbar" + std::to_string(k), &f.rvbar[k], 0, 1);
+    rc |= alloc_field(h, "u" + std::to_string(k), &f.u[k], 1, N);
+    rc |= alloc_field(h, "v" + std::to_string(k), &f.v[k], 1, N);
+    rc |= alloc_field(h, "ru" + std::to_string(k), &f.ru[k], 0, N + 1);
+    rc |= alloc_field(h, "rv" + std::to_string(k), &f.rv[k], 0, N + 1);
+  }
+  for (int it = 0; it < cfg->NT; ++it) {
+    const std::string s = std::to_string(it);
+    for (int k = 1; k <= 3; ++k) rc |= alloc_field(h, "t" + std::to_string(k) + "_" + s, &f.t[k][it], 1, N);
+    rc |= alloc_field(h, "Akt_" + s, &f.Akt[it], 0, N + 1);
+    rc |= alloc_field(h, "diff2_" + s, &f.diff2[it], 0, 1);
+    rc |= alloc_field(h, "stflx_" + s, &f.stflx[it], 0, 1);
+    rc |= alloc_field(h, "btflx_" + s, &f.btflx[it], 0, 1);
+    rc |= alloc_field(h, "stflux_" + s, &f.stflux[it], 0, 1);
+    rc |= alloc_field(h, "btflux_" + s, &f.btflux[it], 0, 1);
+  }
+  if (rc) { roms_b200_destroy(h); return FatalError; }
+  double* sc = nullptr;
+  CK(cudaMalloc(&sc, 4 * (MAXN + 1) * sizeof(double)));
+  CK(cudaMemsetAsync(sc, 0, 4 * (MAXN + 1) * sizeof(double), h->stream));
+  h->allocs.push_back(sc);
+  f.sc_r = sc; f.Cs_r = sc + (MAXN + 1); f.sc_w = sc + 2 * (MAXN + 1); f.Cs_w = sc + 3 * (MAXN + 1);
+  CK(cudaMalloc(&h->d_diag_partial, (size_t)diag_partial_doubles(p) * sizeof(double)));
+  h->allocs.push_back(h->d_diag_partial);
+  CK(cudaMalloc(&h->d_diag_out, 16 * sizeof(double)));
+  h->allocs.push_back(h->d_diag_out);
+  CK(cudaMallocHost(&h->h_diag_out, 16 * sizeof(double)));
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return NoError;
+}
+
+int roms_b200_destroy(roms_b200_handle h) {
+  if (!h) return NoError;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_diag_out) cudaFreeHost(h->h_diag_out);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return NoError;
+}
+
+int roms_b200_array_bounds(roms_b200_handle h, int* o) {
+  if (!h || !o) return InputError;
+  o[0] = h->b.LBi; o[1] = h->b.UBi; o[2] = h->b.LBj; o[3] = h->b.UBj;
+  return NoError;
+}
+
+static int xfer(roms_b200_handle h, const char* name, double* host, size_t n, bool up) {
+  if (!h || !name || !host) return InputError;
+  auto it = h->reg.find(name);
+  if (it == h->reg.end()) { std::fprintf(stderr, "roms_b200: unknown field '%s'\n", name); return InputError; }
+  const FieldInfo& fi = it->second;
+  const size_t want = (size_t)h->ni * h->nj * fi.nk;
+  if (n != want) { std::fprintf(stderr, "roms_b200: field '%s' expects %zu doubles, got %zu\n", name, want, n); return InputError; }
+  CK(cudaSetDevice(h->cfg.device));
+  double* dev = fi.base + h->ioff;
+  const size_t dp = (size_t)h->par.P * sizeof(double), sp = (size_t)h->ni * sizeof(double);
+  if (up) CK(cudaMemcpy2DAsync(dev, dp, host, sp, sp, (size_t)h->nj * fi.nk, cudaMemcpyHostToDevice, h->stream));
+  else CK(cudaMemcpy2DAsync(host, sp, dev, dp, sp, (size_t)h->nj * fi.nk, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (up && std::strncmp(name, "diff2_", 6) == 0) {
+    bool z = true;
+    for (size_t q = 0; q < n; ++q) if (host[q] != 0.0) { z = false; break; }
+    if (!z) h->all_diff2_zero = false;
+  }
+  return NoError;
+}
+int roms_b200_set_field(roms_b200_handle h, const char* name, const double* host, size_t n) { return xfer(h, name, const_cast<double*>(host), n, true); }
+int roms_b200_get_field(roms_b200_handle h, const char* name, double* host, size_t n) { return xfer(h, name, host, n, false); }
+
+int roms_b200_set_scoord(roms_b200_handle h, int which, const double* v, int n) {
+  if (!h || !v || which < 0 || which > 3 || n < h->cfg.N + 1 || n > MAXN + 1) return InputError;
+  double* dst = which == 0 ? h->fl.sc_r : which == 1 ? h->fl.Cs_r : which == 2 ? h->fl.sc_w : h->fl.Cs_w;
+  CK(cudaMemcpyAsync(dst, v, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return NoError;
+}
+
+int roms_b200_set_weights(roms_b200_handle h, int nfast, const double* w1, const double* w2, int n) {
+  if (!h || !w1 || !w2 || nfast < 1 || n < nfast + 2) return InputError;
+  h->nfast = nfast; h->w1.assign(w1, w1 + n); h->w2.assign(w2, w2 + n);
+  return NoError;
+}
+
+int roms_b200_set_indices(roms_b200_handle h, const int* v, const double* tm) {
+  if (!h || !v || !tm) return InputError;
+  h->iic = v[0]; h->ntstart = v[1]; h->ntfirst = v[2]; h->nstp = v[3]; h->nnew = v[4]; h->nrhs = v[5]; h->iif = v[6]; h->indx1 = v[7];
+  h->kstp = v[8]; h->krhs = v[9]; h->knew = v[10]; h->predictor = v[11]; h->exit_flag = v[12]; h->time = tm[0]; h->tdays = tm[1];
+  return NoError;
+}
+int roms_b200_get_indices(roms_b200_handle h, int* v, double* tm) {
+  if (!h || !v || !tm) return InputError;
+  const int w[13] = {h->iic, h->ntstart, h->ntfirst, h->nstp, h->nnew, h->nrhs, h->iif, h->indx1, h->kstp, h->krhs, h->knew, h->predictor, h->exit_flag};
+  std::memcpy(v, w, sizeof(w)); tm[0] = h->time; tm[1] = h->tdays;
+  return NoError;
+}
+
+int roms_b200_run_phase(roms_b200_handle h, int phase) {
+  if (!h) return InputError;
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = run_phase_async(h, phase);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return NoError;
+}
+
+int roms_b200_main3d_step(roms_b200_handle h, int nsteps) {
+  if (!h || nsteps < 0) return InputError;
+  if (h->nfast < 1) { std::fprintf(stderr, "roms_b200: set_weights must be called before stepping\n"); return ConfigError; }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int s = 0; s < nsteps; ++s) { int rc = one_step(h, false); if (rc) return rc; }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  return NoError;
+}
+
+int roms_b200_sync(roms_b200_handle h) {
+  if (!h) return InputError;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  return NoError;
+}
+
+int roms_b200_last_step_ms(roms_b200_handle h, float* ms) {
+  if (!h || !ms) return InputError;
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return NoError;
+}
+
+int roms_b200_diag(roms_b200_handle h, double* out12) {
+  if (!h || !out12) return InputError;
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = run_phase_async(h, ROMS_B200_DIAG);
+  if (rc) return rc;
+  return finish_diag(h, out12);
+}
+
+int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double* svstr, const double* stflux_temp, size_t n2d, double* out12) {
+  if (!h || !out12) return InputError;
+  if (h->nfast < 1) return ConfigError;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t want = (size_t)h->ni * h->nj;
+  if ((sustr || svstr || stflux_temp) && n2d != want) return InputError;
+  if (!h->h_pinned) { CK(cudaMallocHost(&h->h_pinned, 3 * want * sizeof(double))); h->pinned_n = want; }
+  const size_t dp = (size_t)h->par.P * sizeof(double), sp = (size_t)h->ni * sizeof(double);
+  const double* src[3] = {sustr, svstr, stflux_temp};
+  const char* nm[3] = {"sustr", "svstr", "stflux_0"};
+  for (int q = 0; q < 3; ++q) {
+    if (!src[q]) continue;
+    double* stage = h->h_pinned + q * want;
+    std::memcpy(stage, src[q], want * sizeof(double));              // staged through pinned memory
+    double* dev = h->reg[nm[q]].base + h->ioff;
+    CK(cudaMemcpy2DAsync(dev, dp, stage, sp, sp, (size_t)h->nj, cudaMemcpyHostToDevice, h->stream));
+  }
+  int rc = one_step(h, true);
+  if (rc) return rc;
+  return finish_diag(h, out12);
+}
+
+int roms_b200_profile_enable(roms_b200_handle h, int on) {
+  if (!h) return InputError;
+  h->profile = on; std::memset(h->phase_ms, 0, sizeof(h->phase_ms));
+  return NoError;
+}
+int roms_b200_profile_get(roms_b200_handle h, double* ms32, long long* launches) {
+  if (!h || !ms32) return InputError;
+  std::memcpy(ms32, h->phase_ms, sizeof(h->phase_ms));
+  if (launches) *launches = h->launches;
+  return NoError;
+}
+long long roms_b200_launch_count(roms_b200_handle h) { return h ? h->launches : -1; }
+
+}  // extern "C"

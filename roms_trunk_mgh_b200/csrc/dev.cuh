@@ -1,0 +1,93 @@
+// Device-side common definitions for the B200 (sm_100a) implementation of the ROMS nonlinear baroclinic step.
+//
+// HBM layout: every 2-D / 3-D field of one tile is stored i-fastest with a common row pitch P (doubles) and plane
+// stride PL = P * nj; the pointer kept in Flds is pre-offset so that A[i + j*P + k*PL] addresses Fortran element
+// A(i,j,k) directly.  P is a multiple of 16 doubles and the origin is shifted so that i = Istr sits on a 128-byte
+// boundary: warps that walk the xi axis issue fully coalesced 256-byte requests.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rb {
+
+constexpr int MAXNT = 2;
+constexpr int MAXN = 64;          // upper bound on vertical levels for thread-private column arrays
+
+struct Par {
+  // sizes / layout
+  int Lm, Mm, N, NT;
+  int P, PL;                      // row pitch, plane stride (doubles)
+  int LBi, UBi, LBj, UBj;
+  // tile ranges (get_bounds.F var_bounds; EW periodic, NS closed, NtileJ == 1)
+  int Istr, Iend, Jstr, Jend;     // Jstr = 1, Jend = Mm
+  int IstrU, JstrV;               // IstrU = Istr (periodic), JstrV = 2
+  int JstrR, JendR;               // 0, Mm+1
+  int Jstrm1, Jendp1, Jendp2, JstrVm1, JstrVm2;
+  int ew_wrap;                    // 1: this tile owns the whole xi range -> periodic ghosts are filled by the producer
+  // stepping
+  int nstp, nnew, nrhs;           // 1..2
+  int istart;                     // 0: iic == ntfirst, 1: iic == ntfirst+1, 2: later
+  int iif, kstp, krhs, knew, ptsk, predictor, nfast;
+  // options
+  int nonlin_eos, curvgrid, uv_qdrag, salinity, hadv, vadv, itemp, isalt;
+  // scalars
+  double dt, dtfast, g, rho0, R0, T0, S0, Tcoef, Scoef, gamma2, lambda, hc;
+  double Akv_bak, Akt_bak[MAXNT];
+  double w1_m1, w2_0, w2_p1;      // weight(1,iif-1), weight(2,iif), weight(2,iif+1) for the current step2d call
+};
+
+// Field table (all pointers pre-offset; [0] slots of time-indexed arrays are unused so Fortran indices apply)
+struct Flds {
+  // grid
+  double *h, *f, *pm, *pn, *om_r, *on_r, *om_u, *on_u, *om_v, *on_v, *om_p, *on_p, *omn, *fomn, *pmon_r, *pnom_r, *pmon_u, *pnom_u,
+      *pmon_v, *pnom_v, *pmon_p, *pnom_p, *dndx, *dmde, *rdrag, *rdrag2, *visc2_r, *visc2_p;
+  double* diff2[MAXNT];
+  // 2-D state
+  double *zeta[4], *ubar[4], *vbar[4], *rzeta[3], *rubar[3], *rvbar[3];
+  double *Zt_avg1, *DU_avg1, *DU_avg2, *DV_avg1, *DV_avg2, *rufrc, *rvfrc, *rhoA, *rhoS, *sustr, *svstr, *bustr, *bvstr;
+  double *stflx[MAXNT], *btflx[MAXNT], *stflux[MAXNT], *btflux[MAXNT];
+  // 3-D state
+  double *u[3], *v[3], *ru[3], *rv[3];
+  double* t[4][MAXNT];
+  double *rho, *pden, *Hz, *z_r, *Huon, *Hvom, *W, *wvel, *z_w, *Akv;
+  double* Akt[MAXNT];
+  // scratch
+  double* P3;                      // prsgrd32 pressure (1:N)
+  // 1-D (device)
+  double *sc_r, *Cs_r, *sc_w, *Cs_w;
+};
+
+// ---- stores that also fill the periodic (xi) ghost images when this tile wraps onto itself -----------------------
+// exchange_2d.F / exchange_3d.F: A(Lm+1:Lm+2) = A(1:2), A(-2:0) = A(Lm-2:Lm)
+__device__ __forceinline__ void st_w(double* __restrict__ A, int o, int i, double x, const Par& p) {
+  A[o + i] = x;
+  if (p.ew_wrap) {
+    if (i <= 2) A[o + i + p.Lm] = x;
+    if (i >= p.Lm - 2) A[o + i - p.Lm] = x;
+  }
+}
+// rho-type with zero-gradient closed walls (zetabc.F:536-545/685-694, t3dbc_im.F:477-489/611-623, bc_r2d/bc_w3d):
+// o = offset of row j (without i)
+__device__ __forceinline__ void st_r_grad(double* __restrict__ A, int o, int i, int j, double x, const Par& p) {
+  st_w(A, o, i, x, p);
+  if (j == 1) st_w(A, o - p.P, i, x, p);
+  if (j == p.Mm) st_w(A, o + p.P, i, x, p);
+}
+// u-type with closed walls south/north: A(i,0) = gamma2*A(i,1), A(i,Mm+1) = gamma2*A(i,Mm) (u2dbc_im.F:963-979, u3dbc_im.F:507-529)
+__device__ __forceinline__ void st_u_closed(double* __restrict__ A, int o, int i, int j, double x, const Par& p) {
+  st_w(A, o, i, x, p);
+  if (j == 1) st_w(A, o - p.P, i, p.gamma2 * x, p);
+  if (j == p.Mm) st_w(A, o + p.P, i, p.gamma2 * x, p);
+}
+// v-type with closed walls: A(i,1) = 0, A(i,Mm+1) = 0 (v2dbc_im.F:436-441/785-790, v3dbc_im.F:222-230/364-372);
+// called for j in 2..Mm
+__device__ __forceinline__ void st_v_closed(double* __restrict__ A, int o, int i, int j, double x, const Par& p) {
+  st_w(A, o, i, x, p);
+  if (j == 2) st_w(A, o - p.P, i, 0.0, p);
+  if (j == p.Mm) st_w(A, o + p.P, i, 0.0, p);
+}
+
+__device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }   // Fortran MAX (first arg on ties)
+__device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
+
+}  // namespace rb

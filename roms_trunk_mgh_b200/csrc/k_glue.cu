@@ -1,0 +1,299 @@
+// Glue kernels of the main3d chain: set_massflux, rho_eos, set_vbc, omega, wvelocity, set_zeta, set_depth, ana_vmix.
+// All are HBM-bound streaming or thread-per-column kernels; xi (i) is the coalesced axis.
+#include "dev.cuh"
+#include "kernels.h"
+
+namespace rb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// set_massflux_tile (ROMS/Nonlinear/set_massflux.F:140-174).  One thread per (i,j,k).
+__global__ void __launch_bounds__(256) k_set_massflux(Par p, Flds f) {
+  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;          // 0..Mm+1
+  const int k = 1 + blockIdx.z;
+  if (i > p.Iend || j > p.Mm + 1) return;
+  const int o2 = j * p.P, o = o2 + k * p.PL;
+  const double* __restrict__ Hz = f.Hz;
+  const double hz = Hz[o + i];
+  {
+    const double x = 0.5 * (hz + Hz[o + i - 1]) * f.u[p.nrhs][o + i] * f.on_u[o2 + i];
+    st_w(f.Huon, o, i, x, p);
+  }
+  if (j >= 1) {
+    const double x = 0.5 * (hz + Hz[o - p.P + i]) * f.v[p.nrhs][o + i] * f.om_v[o2 + i];
+    st_w(f.Hvom, o, i, x, p);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rho_eos_tile: nonlinear (ROMS/Nonlinear/rho_eos.F:252-483, coefficients mod_eoscoef.F:24-64) and linear (:696-799).
+// One thread per column, top-down so that the VAR_RHO_2D integrals rhoA/rhoS accumulate in registers.
+__device__ __forceinline__ void eos_nl(double Tt, double Ts, double Tp, double& den, double& den1) {
+  const double A00 = +1.909256e+04, A01 = +2.098925e+02, A02 = -3.041638e+00, A03 = -1.852732e-03, A04 = -1.361629e-05;
+  const double B00 = +1.044077e+02, B01 = -6.500517e+00, B02 = +1.553190e-01, B03 = +2.326469e-04;
+  const double D00 = -5.587545e+00, D01 = +7.390729e-01, D02 = -1.909078e-02;
+  const double E00 = +4.721788e-01, E01 = +1.028859e-02, E02 = -2.512549e-04, E03 = -5.939910e-07;
+  const double F00 = -1.571896e-02, F01 = -2.598241e-04, F02 = +7.267926e-06;
+  const double G00 = +2.042967e-03, G01 = +1.045941e-05, G02 = -5.782165e-10, G03 = +1.296821e-07;
+  const double H00 = -2.595994e-07, H01 = -1.248266e-09, H02 = -3.508914e-09;
+  const double Q00 = +9.99842594e+02, Q01 = +6.793952e-02, Q02 = -9.095290e-03, Q03 = +1.001685e-04, Q04 = -1.120083e-06, Q05 = +6.536332e-09;
+  const double U00 = +8.24493e-01, U01 = -4.08990e-03, U02 = +7.64380e-05, U03 = -8.24670e-07, U04 = +5.38750e-09;
+  const double V00 = -5.72466e-03, V01 = +1.02270e-04, V02 = -1.65460e-06;
+  const double W00 = +4.8314e-04;
+  const double sqrtTs = sqrt(Ts);
+  const double Tpr10 = 0.1 * Tp;
+  const double C0 = Q00 + Tt * (Q01 + Tt * (Q02 + Tt * (Q03 + Tt * (Q04 + Tt * Q05))));
+  const double C1 = U00 + Tt * (U01 + Tt * (U02 + Tt * (U03 + Tt * U04)));
+  const double C2 = V00 + Tt * (V01 + Tt * V02);
+  den1 = C0 + Ts * (C1 + sqrtTs * C2 + Ts * W00);
+  const double C3 = A00 + Tt * (A01 + Tt * (A02 + Tt * (A03 + Tt * A04)));
+  const double C4 = B00 + Tt * (B01 + Tt * (B02 + Tt * B03));
+  const double C5 = D00 + Tt * (D01 + Tt * D02);
+  const double C6 = E00 + Tt * (E01 + Tt * (E02 + Tt * E03));
+  const double C7 = F00 + Tt * (F01 + Tt * F02);
+  const double C8 = G01 + Tt * (G02 + Tt * G03);
+  const double C9 = H00 + Tt * (H01 + Tt * H02);
+  const double bulk0 = C3 + Ts * (C4 + sqrtTs * C5);
+  const double bulk1 = C6 + Ts * (C7 + sqrtTs * G00);
+  const double bulk2 = C8 + Ts * C9;
+  const double bulk = bulk0 - Tp * (bulk1 - Tp * bulk2);
+  const double cff = 1.0 / (bulk + Tpr10);
+  den = den1 * bulk * cff;
+}
+
+__global__ void __launch_bounds__(256) k_rho_eos(Par p, Flds f) {
+  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;          // JstrT..JendT = 0..Mm+1
+  if (i > p.Iend || j > p.Mm + 1) return;
+  const int o2 = j * p.P;
+  const double* __restrict__ T = f.t[p.nrhs][p.itemp - 1];
+  const double* __restrict__ S = (p.salinity && p.NT >= 2) ? f.t[p.nrhs][p.isalt - 1] : nullptr;
+  const double* __restrict__ Hz = f.Hz;
+  double rhoA = 0.0, rhoS = 0.0;
+  for (int k = p.N; k >= 1; --k) {
+    const int o = o2 + k * p.PL;
+    double den, pd;
+    if (p.nonlin_eos) {
+      const double Tt = dmax(-2.0, T[o + i]);
+      const double Ts = S ? dmax(0.0, S[o + i]) : 0.0;
+      double d, d1;
+      eos_nl(Tt, Ts, f.z_r[o + i], d, d1);
+      den = d - 1000.0;
+      pd = d1 - 1000.0;
+    } else {
+      double r = p.R0 - p.R0 * p.Tcoef * (T[o + i] - p.T0);
+      if (S) r = r + p.R0 * p.Scoef * (S[o + i] - p.S0);
+      r = r - 1000.0;
+      den = r; pd = r;
+    }
+    st_w(f.rho, o, i, den, p);
+    st_w(f.pden, o, i, pd, p);
+    const double hz = Hz[o + i];
+    const double cff1 = den * hz;
+    if (k == p.N) { rhoS = 0.5 * cff1 * hz; rhoA = cff1; }
+    else { rhoS = rhoS + hz * (rhoA + 0.5 * cff1); rhoA = rhoA + cff1; }
+  }
+  const double cff2 = 1.0 / p.rho0;
+  const double cff1 = 1.0 / (f.z_w[o2 + p.N * p.PL + i] - f.z_w[o2 + i]);
+  st_w(f.rhoA, o2, i, cff2 * cff1 * rhoA, p);
+  st_w(f.rhoS, o2, i, 2.0 * cff1 * cff1 * cff2 * rhoS, p);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// set_vbc_tile (ROMS/Nonlinear/set_vbc.F:278-283, :340-355, :591-624 quadratic, :629-652 linear, BCs :657-662)
+__global__ void __launch_bounds__(256) k_set_vbc(Par p, Flds f) {
+  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;          // 0..Mm+1
+  if (i > p.Iend || j > p.Mm + 1) return;
+  const int o2 = j * p.P, o1 = o2 + p.PL;                       // k = 1
+  {
+    const int it = p.itemp - 1;
+    f.stflx[it][o2 + i] = f.stflux[it][o2 + i];
+    f.btflx[it][o2 + i] = f.btflux[it][o2 + i];
+    if (p.salinity && p.NT >= 2) {
+      const int is = p.isalt - 1;
+      const double* __restrict__ S = f.t[p.nrhs][is];
+      const double EmP = f.stflux[is][o2 + i];
+      f.stflx[is][o2 + i] = EmP * S[o2 + p.N * p.PL + i];
+      f.btflx[is][o2 + i] = f.btflx[is][o2 + i] * S[o1 + i];
+    }
+  }
+  const double* __restrict__ u = f.u[p.nrhs];
+  const double* __restrict__ v = f.v[p.nrhs];
+  if (j >= 1 && j <= p.Mm) {
+    double bu;
+    if (p.uv_qdrag) {
+      const double cff1 = 0.25 * (v[o1 + i] + v[o1 + p.P + i] + v[o1 + i - 1] + v[o1 + p.P + i - 1]);
+      const double uu = u[o1 + i];
+      const double cff2 = sqrt(uu * uu + cff1 * cff1);
+      bu = 0.5 * (f.rdrag2[o2 + i - 1] + f.rdrag2[o2 + i]) * uu * cff2;
+    } else {
+      bu = 0.5 * (f.rdrag[o2 + i - 1] + f.rdrag[o2 + i]) * u[o1 + i];
+    }
+    st_u_closed(f.bustr, o2, i, j, bu, p);
+  }
+  if (j >= 2 && j <= p.Mm) {
+    double bv;
+    if (p.uv_qdrag) {
+      const double cff1 = 0.25 * (u[o1 + i] + u[o1 + i + 1] + u[o1 - p.P + i] + u[o1 - p.P + i + 1]);
+      const double vv = v[o1 + i];
+      const double cff2 = sqrt(cff1 * cff1 + vv * vv);
+      bv = 0.5 * (f.rdrag2[o2 - p.P + i] + f.rdrag2[o2 + i]) * vv * cff2;
+    } else {
+      bv = 0.5 * (f.rdrag[o2 - p.P + i] + f.rdrag[o2 + i]) * v[o1 + i];
+    }
+    st_v_closed(f.bvstr, o2, i, j, bv, p);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// omega_tile (ROMS/Nonlinear/omega.F:147-218).  Thread per column: upward prefix sum, then removal of the part
+// proportional to the barotropic divergence, then bc_w3d (gradient) + periodic images.
+__global__ void __launch_bounds__(128) k_omega(Par p, Flds f) {
+  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > p.Iend || j > p.Mm) return;
+  const int o2 = j * p.P;
+  const double* __restrict__ Huon = f.Huon;
+  const double* __restrict__ Hvom = f.Hvom;
+  const double* __restrict__ z_w = f.z_w;
+  double Wl[MAXN + 1];
+  double w = 0.0;
+  Wl[0] = 0.0;
+  for (int k = 1; k <= p.N; ++k) {
+    const int o = o2 + k * p.PL;
+    w = w - (Huon[o + i + 1] - Huon[o + i] + Hvom[o + p.P + i] - Hvom[o + i]);
+    Wl[k] = w;
+  }
+  const double zw0 = z_w[o2 + i];
+  const double wrk = w / (z_w[o2 + p.N * p.PL + i] - zw0);
+  st_r_grad(f.W, o2, i, j, 0.0, p);
+  for (int k = p.N - 1; k >= 1; --k) {
+    const int o = o2 + k * p.PL;
+    const double x = Wl[k] - wrk * (z_w[o + i] - zw0);
+    st_r_grad(f.W, o, i, j, x, p);
+  }
+  st_r_grad(f.W, o2 + p.N * p.PL, i, j, 0.0, p);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wvelocity_tile (ROMS/Nonlinear/wvelocity.F:156-256): diagnostic true vertical velocity at W-points.
+__global__ void __launch_bounds__(128) k_wvelocity(Par p, Flds f, int Ninp) {
+  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > p.Iend || j > p.Mm) return;
+  const int o2 = j * p.P, P = p.P, N = p.N;
+  const double* __restrict__ u = f.u[Ninp];
+  const double* __restrict__ v = f.v[Ninp];
+  const double* __restrict__ z_r = f.z_r;
+  const double* __restrict__ z_w = f.z_w;
+  const double* __restrict__ W = f.W;
+  const double pmi = f.pm[o2 + i], pni = f.pn[o2 + i];
+  const double pmU0 = f.pm[o2 + i - 1] + pmi, pmU1 = pmi + f.pm[o2 + i + 1];
+  const double pnV0 = f.pn[o2 - P + i] + pni, pnV1 = pni + f.pn[o2 + P + i];
+  double vert[MAXN + 1];
+  for (int k = 1; k <= N; ++k) {
+    const int o = o2 + k * p.PL;
+    const double zr = z_r[o + i];
+    const double wu0 = u[o + i] * (zr - z_r[o + i - 1]) * pmU0;
+    const double wu1 = u[o + i + 1] * (z_r[o + i + 1] - zr) * pmU1;
+    double vt = 0.25 * (wu0 + wu1);
+    const double wv0 = v[o + i] * (zr - z_r[o - P + i]) * pnV0;
+    const double wv1 = v[o + P + i] * (z_r[o + P + i] - zr) * pnV1;
+    vt = vt + 0.25 * (wv0 + wv1);
+    vert[k] = vt;
+  }
+  const double cff1 = 3.0 / 8.0, cff2 = 3.0 / 4.0, cff3 = 1.0 / 8.0, cff4 = 9.0 / 16.0, cff5 = 1.0 / 16.0;
+  const double zw0 = z_w[o2 + i], zwN = z_w[o2 + N * p.PL + i];
+  const double wrk = (f.DU_avg1[o2 + i] - f.DU_avg1[o2 + i + 1] + f.DV_avg1[o2 + i] - f.DV_avg1[o2 + P + i]) / (zwN - zw0);
+  const double pmn = pmi * pni;
+  {
+    const double slope = (z_r[o2 + p.PL + i] - zw0) / (z_r[o2 + 2 * p.PL + i] - z_r[o2 + p.PL + i]);
+    const double w0 = cff1 * (vert[1] - slope * (vert[2] - vert[1])) + cff2 * vert[1] - cff3 * vert[2];
+    st_r_grad(f.wvel, o2, i, j, w0, p);
+    const int o = o2 + p.PL;
+    const double w1 = pmn * (W[o + i] + wrk * (z_w[o + i] - zw0)) + cff1 * vert[1] + cff2 * vert[2] - cff3 * vert[3];
+    st_r_grad(f.wvel, o, i, j, w1, p);
+  }
+  for (int k = 2; k <= N - 2; ++k) {
+    const int o = o2 + k * p.PL;
+    const double x = pmn * (W[o + i] + wrk * (z_w[o + i] - zw0)) + cff4 * (vert[k] + vert[k + 1]) - cff5 * (vert[k - 1] + vert[k + 2]);
+    st_r_grad(f.wvel, o, i, j, x, p);
+  }
+  {
+    const int oN = o2 + N * p.PL, oM = oN - p.PL;
+    const double slope = (zwN - z_r[oN + i]) / (z_r[oN + i] - z_r[oM + i]);
+    const double wN = pmn * wrk * (zwN - zw0) + cff1 * (vert[N] + slope * (vert[N] - vert[N - 1])) + cff2 * vert[N] - cff3 * vert[N - 1];
+    st_r_grad(f.wvel, oN, i, j, wN, p);
+    const double wM = pmn * (W[oM + i] + wrk * (z_w[oM + i] - zw0)) + cff1 * vert[N] + cff2 * vert[N - 1] - cff3 * vert[N - 2];
+    st_r_grad(f.wvel, oM, i, j, wM, p);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// set_zeta_tile (ROMS/Nonlinear/set_zeta.F:95-109)
+__global__ void __launch_bounds__(256) k_set_zeta(Par p, Flds f) {
+  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > p.Iend || j > p.Mm + 1) return;
+  const int o2 = j * p.P;
+  const double z = f.Zt_avg1[o2 + i];
+  st_w(f.zeta[1], o2, i, z, p);
+  st_w(f.zeta[2], o2, i, z, p);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// set_depth_tile (ROMS/Nonlinear/set_depth.F:210-262, Vtransform = 2)
+__global__ void __launch_bounds__(256) k_set_depth(Par p, Flds f) {
+  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;          // 0..Mm+1
+  if (i > p.Iend || j > p.Mm + 1) return;
+  const int o2 = j * p.P;
+  const double hwater = f.h[o2 + i];
+  const double zt = f.Zt_avg1[o2 + i];
+  double zw_prev = -hwater;
+  st_w(f.z_w, o2, i, zw_prev, p);
+  const double hinv = 1.0 / (p.hc + hwater);
+  for (int k = 1; k <= p.N; ++k) {
+    const int o = o2 + k * p.PL;
+    const double cff_r = p.hc * f.sc_r[k], cff_w = p.hc * f.sc_w[k];
+    const double cff1_r = f.Cs_r[k], cff1_w = f.Cs_w[k];
+    const double cff2_r = (cff_r + cff1_r * hwater) * hinv;
+    const double cff2_w = (cff_w + cff1_w * hwater) * hinv;
+    const double zw = zt + (zt + hwater) * cff2_w;
+    const double zr = zt + (zt + hwater) * cff2_r;
+    st_w(f.z_w, o, i, zw, p);
+    st_w(f.z_r, o, i, zr, p);
+    st_w(f.Hz, o, i, zw - zw_prev, p);
+    zw_prev = zw;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ana_vmix (ROMS/Functionals/ana_vmix.h:200-208 Akv, :327-337 Akt; UPWELLING), k = 1..N-1
+__global__ void __launch_bounds__(256) k_ana_vmix(Par p, Flds f) {
+  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = 1 + blockIdx.z;
+  if (i > p.Iend || j > p.Mm + 1) return;
+  const int o = j * p.P + k * p.PL;
+  st_w(f.Akv, o, i, 2.0e-3 + 8.0e-3 * exp(f.z_w[o + i] / 150.0), p);
+  st_w(f.Akt[p.itemp - 1], o, i, p.Akt_bak[p.itemp - 1], p);
+  if (p.salinity && p.NT >= 2) st_w(f.Akt[p.isalt - 1], o, i, p.Akt_bak[p.isalt - 1], p);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static inline dim3 g2(const Par& p, dim3 b, int nj, int nz = 1) {
+  return dim3((p.Iend - p.Istr + 1 + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz);
+}
+
+void launch_set_massflux(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_massflux<<<g2(p, b, p.Mm + 2, p.N), b, 0, s>>>(p, f); }
+void launch_rho_eos(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_rho_eos<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
+void launch_set_vbc(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_vbc<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
+void launch_omega(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 2); k_omega<<<g2(p, b, p.Mm), b, 0, s>>>(p, f); }
+void launch_wvelocity(const Par& p, const Flds& f, int Ninp, cudaStream_t s) { dim3 b(64, 2); k_wvelocity<<<g2(p, b, p.Mm), b, 0, s>>>(p, f, Ninp); }
+void launch_set_zeta(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_zeta<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
+void launch_set_depth(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_depth<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
+void launch_ana_vmix(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_ana_vmix<<<g2(p, b, p.Mm + 2, p.N - 1), b, 0, s>>>(p, f); }
+
+}  // namespace rb

@@ -1,0 +1,27 @@
+// Host-side launch wrappers of the sm_100a kernels (one per ROMS routine on the main3d path).
+#pragma once
+#include "dev.cuh"
+
+namespace rb {
+void launch_set_massflux(const Par& p, const Flds& f, cudaStream_t s);
+void launch_rho_eos(const Par& p, const Flds& f, cudaStream_t s);
+void launch_set_vbc(const Par& p, const Flds& f, cudaStream_t s);
+void launch_omega(const Par& p, const Flds& f, cudaStream_t s);
+void launch_wvelocity(const Par& p, const Flds& f, int Ninp, cudaStream_t s);
+void launch_set_zeta(const Par& p, const Flds& f, cudaStream_t s);
+void launch_set_depth(const Par& p, const Flds& f, cudaStream_t s);
+void launch_ana_vmix(const Par& p, const Flds& f, cudaStream_t s);
+void launch_pre_step3d(const Par& p, const Flds& f, cudaStream_t s);
+void launch_prsgrd(const Par& p, const Flds& f, int dj_gradps, cudaStream_t s);
+void launch_t3dmix2_s(const Par& p, const Flds& f, cudaStream_t s);
+void launch_t3dmix2_geo(const Par& p, const Flds& f, cudaStream_t s);
+void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s);
+void launch_uv3dmix2(const Par& p, const Flds& f, cudaStream_t s);
+void launch_step2d(const Par& p, const Flds& f, cudaStream_t s);
+void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s);
+void launch_step3d_t(const Par& p, const Flds& f, cudaStream_t s);
+// diag: partial[] must hold 16 doubles per block row; out16 on device
+void launch_diag(const Par& p, const Flds& f, double* partial, double* out16, int knew, cudaStream_t s);
+int diag_partial_doubles(const Par& p);
+// number of kernel launches each wrapper performs (for the gpu_launches claim)
+}  // namespace rb

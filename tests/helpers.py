@@ -1,0 +1,70 @@
+"""Shared helpers for the parity tests: build an oracle model and a device Tile holding the same state."""
+import numpy as np
+
+import orc
+from roms_trunk_mgh_b200 import _lib
+from roms_trunk_mgh_b200.ocean import Tile, field_names
+
+APP_OPTS = ["nonlin_eos", "dj_gradps", "curvgrid", "mix_geo_ts", "uv_qdrag", "hadv", "vadv", "ana_vmix", "wvelocity_every_step"]
+
+
+def cfg_from_oracle(o, device=0):
+    """roms_b200_config carrying exactly the oracle's switches and parameters."""
+    app = int(o.opt("app"))
+    cfg = _lib.default_config(app, int(o.opt("Lm")), int(o.opt("Mm")), int(o.opt("N")))
+    cfg.NT = int(o.opt("NT"))
+    for k in APP_OPTS:
+        setattr(cfg, k, int(o.opt(k)))
+    cfg.salinity = int(o.opt("salinity"))
+    cfg.dt = o.opt("dt"); cfg.ndtfast = int(o.opt("ndtfast"))
+    cfg.rho0 = o.opt("rho0"); cfg.g = o.opt("g")
+    cfg.R0 = o.opt("R0"); cfg.T0 = o.opt("T0"); cfg.S0 = o.opt("S0"); cfg.Tcoef = o.opt("Tcoef"); cfg.Scoef = o.opt("Scoef")
+    cfg.Akt_bak[0] = cfg.Akt_bak[1] = o.opt("Akt_bak"); cfg.Akv_bak = o.opt("Akv_bak")
+    cfg.gamma2 = o.opt("gamma2"); cfg.lambda_ = o.opt("lambda"); cfg.hc = o.opt("hc")
+    cfg.device = device
+    return cfg
+
+
+def copy_state(o, t):
+    """Upload every field, vector and index of oracle `o` into device tile `t`."""
+    NT = int(o.opt("NT")); N = int(o.opt("N"))
+    n2, n3 = field_names(NT)
+    for n in n2 + n3:
+        t.set(n, o.field(n))
+    t.set_scoord(o.vector(0, N + 1), o.vector(1, N + 1), o.vector(2, N + 1), o.vector(3, N + 1))
+    nd = int(o.opt("ndtfast"))
+    t.set_weights(int(o.opt("nfast")), o.vector(4, 2 * nd + 2), o.vector(5, 2 * nd + 2))
+    t.set_indices(o.indices())
+
+
+def make_pair(app, strict=True, spinup=0, **kw):
+    o = orc.Oracle(app, **kw)
+    o.run_phase("set_data")
+    o.run_phase("ini")
+    if spinup:
+        o.step(spinup)
+    t = Tile(cfg_from_oracle(o), strict=strict)
+    copy_state(o, t)
+    return o, t
+
+
+def compare(o, t, names, exact=True, rtol=0.0, label=""):
+    """Compare fields; returns list of (name, max_abs_diff, max_abs_ref) for mismatching fields."""
+    bad = []
+    for n in names:
+        a = o.field(n); b = t.get(n)
+        if exact:
+            if not np.array_equal(a, b):
+                d = np.abs(a - b)
+                bad.append((n, float(np.nanmax(d)), float(np.nanmax(np.abs(a))), int(np.count_nonzero(d > 0))))
+        else:
+            scale = float(np.max(np.abs(a)))
+            d = float(np.max(np.abs(a - b)))
+            if not np.isfinite(d) or d > rtol * max(scale, 1e-300):
+                bad.append((n, d, scale, -1))
+    return bad
+
+
+def all_names(NT):
+    n2, n3 = field_names(NT)
+    return n2 + n3
