@@ -87,6 +87,10 @@ __device__ __forceinline__ void st_v_closed(double* __restrict__ A, int o, int i
   if (j == p.Mm) st_w(A, o + p.P, i, 0.0, p);
 }
 
+// Fire-and-forget prefetch of the line holding *p into L2: needs no destination register, so a thread can have many
+// in flight.  The latency-bound column / multi-stage kernels use it to start the DRAM fetch of later stages early.
+__device__ __forceinline__ void pf_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }   // Fortran MAX (first arg on ties)
 __device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
 

@@ -72,4 +72,27 @@ __device__ __forceinline__ double vflux(const double* tc, int k, int N, double W
   }
 }
 
+// Same flux from a rolling four-value window (tkm1 = t(k-1), tk, tkp1, tkp2 = t(k+2); out-of-column values are never
+// used by the end formulas).
+template <int VADV>
+__device__ __forceinline__ double vflux4(double tkm1, double tk, double tkp1, double tkp2, int k, int N, double Wk) {
+  if (VADV == 0) {
+    if (k == 1) return Wk * (0.5 * tk + (7.0 / 12.0) * tkp1 - (1.0 / 12.0) * tkp2);
+    if (k == N - 1) return Wk * (0.5 * tkp1 + (7.0 / 12.0) * tk - (1.0 / 12.0) * tkm1);
+    return Wk * ((7.0 / 12.0) * (tk + tkp1) - (1.0 / 12.0) * (tkm1 + tkp2));
+  } else if (VADV == 1) {
+    const double eps = 1.0e-16;
+    const double dk = tkp1 - tk;
+    const double dkm1 = (k > 1) ? (tk - tkm1) : dk;
+    const double dkp1 = (k + 1 <= N - 1) ? (tkp2 - tkp1) : dk;
+    double c = 2.0 * dk * dkm1;
+    const double CFk = (c > eps) ? c / (dk + dkm1) : 0.0;
+    c = 2.0 * dkp1 * dk;
+    const double CFkp = (c > eps) ? c / (dkp1 + dk) : 0.0;
+    return Wk * 0.5 * (tk + tkp1 - (1.0 / 3.0) * (CFkp - CFk));
+  } else {
+    return Wk * 0.5 * (tk + tkp1);
+  }
+}
+
 }  // namespace rb

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(128) k_step3d_t(Par p, Flds f) {
 static inline dim3 g2(dim3 b, int ni, int nj, int nz = 1) { return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz); }
 
 void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s) {
+  if (launch_step3d_uv_n(p, f, s)) return;          // compile-time-N fast path (k_step3d_n.cu)
   dim3 b(64, 2);
   k_step3d_uv<0><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
   k_step3d_uv<1><<<g2(b, p.Iend - p.Istr + 1, p.Mm - 1), b, 0, s>>>(p, f);
@@ -186,6 +187,7 @@ static void launch_s3t_v(const Par& p, const Flds& f, cudaStream_t s) {
   else k_step3d_t<H, 2><<<g, b, 0, s>>>(p, f);
 }
 void launch_step3d_t(const Par& p, const Flds& f, cudaStream_t s) {
+  if (launch_step3d_t_n(p, f, s)) return;           // compile-time-N fast path (k_step3d_n.cu)
   if (p.hadv == 0) launch_s3t_v<0>(p, f, s);
   else if (p.hadv == 1) launch_s3t_v<1>(p, f, s);
   else if (p.hadv == 2) launch_s3t_v<2>(p, f, s);

@@ -79,6 +79,7 @@ if __name__ == "__main__":
     apps = sys.argv[2:] or ["seamount", "benchmark", "upwelling"]
     table = {"upwelling": (orc.APP_UPWELLING, {}), "seamount": (orc.APP_SEAMOUNT, {}),
              "benchmark": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10)),
+             "benchmark30": (orc.APP_BENCHMARK, dict(Lm=96, Mm=40, N=30)),
              "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, mix_geo_ts=1)),
              "benchmark_p31": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, dj_gradps=0, nonlin_eos=0))}
     total = 0

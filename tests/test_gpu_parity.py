@@ -1,0 +1,208 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C-ABI, against the CPU oracle.
+
+Bars (north_star: "within a stated relative tolerance on zeta/u/v/temp/salt after N steps, with bit-exact index/mask handling"):
+  * strict library (-fmad=false): every field of the model state BIT-EXACT after every phase and after multi-step runs --
+    this is the index / branch / mask / operation-order gate.  Only exception: ANA_VMIX evaluates exp() on the device
+    (UPWELLING), whose last bit differs from glibc's; there the bar is 1e-13 relative.
+  * production library (FMA contraction on): max-norm relative difference <= 1e-8 on zeta,u,v and <= 1e-12 on tracers
+    after 10..50 steps (measured: <= 2e-9 / 6e-14 over 200 steps, tests/gpu_tolerance_probe.py).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import orc
+from helpers import all_names, cfg_from_oracle, compare, copy_state, make_pair
+from roms_trunk_mgh_b200 import _lib, synth
+from roms_trunk_mgh_b200.ocean import Tile
+
+pytestmark = pytest.mark.gpu
+
+STEP_PHASES = ["set_massflux", "rho_eos", "set_vbc", "ana_vmix", "omega", "wvelocity", "set_zeta", "pre_step3d", "prsgrd", "t3dmix",
+               "rhs3d", "uv3dmix", "step2d_loop", "set_depth", "step3d_uv", "omega2", "step3d_t"]
+CASES = {
+    "seamount": (orc.APP_SEAMOUNT, {}),                                              # A4/A4 tracers, QDRAG, no-slip, NT=1
+    "benchmark": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10)),                      # nonlinear EOS, CURVGRID, U3/C4, MIX_S_TS
+    "benchmark30": (orc.APP_BENCHMARK, dict(Lm=96, Mm=40, N=30)),                    # compile-time-N fast paths
+    "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, mix_geo_ts=1)),    # MIX_GEO_TS with tnu2 = 500
+    "benchmark_p31": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, dj_gradps=0, nonlin_eos=0)),   # prsgrd31 + linear EOS
+    "ragged": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7)),                          # sizes that are no multiple of any tile
+}
+
+
+def begin_step(o, t):
+    d = o.indices()
+    d["nstp"] = 1 + ((d["iic"] - d["ntstart"]) % 2); d["nnew"] = 3 - d["nstp"]; d["nrhs"] = d["nstp"]
+    d["tdays"] = d["time"] / 86400.0
+    o.set_indices(d)
+    o.run_phase("set_data")
+    t.set("sustr", o.field("sustr")); t.set("svstr", o.field("svstr"))
+    t.set_indices(o.indices())
+
+
+def test_native_library_is_loaded():
+    _lib.load(False); _lib.load(True)
+    maps = open("/proc/self/maps").read()
+    assert "libroms_b200.so" in maps and "libroms_b200_strict.so" in maps
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("spinup", [0, 1, 3])      # iic == ntfirst (Euler), ntfirst+1 (AB2), later (AB3) start-up branches
+def test_strict_bit_exact_every_phase(case, spinup):
+    app, kw = CASES[case]
+    o, t = make_pair(app, strict=True, spinup=spinup, **kw)
+    names = all_names(int(o.opt("NT")))
+    begin_step(o, t)
+    for ph in STEP_PHASES:
+        o.run_phase(ph); t.run_phase(ph)
+        if ph == "step2d_loop":
+            assert o.indices() == t.indices()        # the 2-D time-index state machine (main3d.F:592-700)
+        bad = compare(o, t, names, exact=True)
+        assert not bad, f"{case} spinup={spinup} phase {ph}: {bad}"
+    t.close()
+
+
+@pytest.mark.parametrize("case", ["seamount", "benchmark30"])
+def test_strict_bit_exact_multistep_and_diag(case):
+    app, kw = CASES[case]
+    o, t = make_pair(app, strict=True, **kw)
+    for _ in range(8):
+        o.step(1); t.main3d(1)
+    assert not compare(o, t, all_names(int(o.opt("NT"))), exact=True)
+    do, dt_ = o.diag(), t.diag()
+    for k in do:
+        assert do[k] == dt_[k], (k, do[k], dt_[k])     # same summation order as diag.F:293-318 -> identical
+    t.close()
+
+
+def test_strict_upwelling_ana_vmix_tolerance():
+    o, t = make_pair(orc.APP_UPWELLING, strict=True)
+    for _ in range(6):
+        o.step(1); t.set("sustr", o.field("sustr")); t.main3d(1)
+    bad = compare(o, t, all_names(2), exact=False, rtol=1e-13)
+    assert not bad, bad
+    t.close()
+
+
+@pytest.mark.parametrize("app,kw,nsteps", [(orc.APP_UPWELLING, {}, 50), (orc.APP_SEAMOUNT, {}, 30), (orc.APP_BENCHMARK, dict(Lm=128, Mm=64, N=30), 20)])
+def test_production_tolerance(app, kw, nsteps):
+    o, t = make_pair(app, strict=False, **kw)
+    for _ in range(nsteps):
+        o.step(1); t.set("sustr", o.field("sustr")); t.main3d(1)
+    NT = int(o.opt("NT"))
+    assert not compare(o, t, ["zeta1", "zeta2", "u1", "u2", "v1", "v2", "ubar1", "vbar1"], exact=False, rtol=1e-8)
+    assert not compare(o, t, [f"t{k}_{it}" for k in (1, 2) for it in range(NT)], exact=False, rtol=1e-12)
+    assert t.indices()["iic"] == o.indices()["iic"]
+    t.close()
+
+
+def test_host_pointer_tile_entry_points():
+    """Form (1) of the boundary: roms_b200_<name>_tile with whole Fortran arrays in host memory."""
+    o, t = make_pair(orc.APP_BENCHMARK, strict=True, spinup=2, Lm=64, Mm=32, N=10)
+    t.close()
+    L = _lib.load(True)
+    cfg = cfg_from_oracle(o)
+    d = o.indices()
+    ta = _lib.TileArgs(cfg=cfg, iic=d["iic"], ntfirst=d["ntfirst"], nstp=d["nstp"], nnew=d["nnew"], nrhs=d["nrhs"], iif=1, kstp=1, krhs=1, knew=1, predictor=0)
+    P = lambda a: a.ctypes.data_as(_lib.DP)  # noqa: E731
+    nr = d["nrhs"]
+    # rho_eos_tile
+    o.run_phase("rho_eos")
+    outs = [np.zeros_like(o.field(n)) for n in ("rhoA", "rhoS", "pden", "rho")]
+    rc = L.roms_b200_rho_eos_tile(C.byref(ta), P(o.field("Hz")), P(o.field("z_r")), P(o.field("z_w")), P(o.field(f"t{nr}_0")), P(o.field(f"t{nr}_1")), *[P(a) for a in outs])
+    assert rc == 0
+    for a, n in zip(outs, ("rhoA", "rhoS", "pden", "rho")):
+        assert np.array_equal(a, o.field(n)), n
+    # set_massflux_tile
+    o.run_phase("set_massflux")
+    Hu, Hv = np.zeros_like(o.field("Huon")), np.zeros_like(o.field("Hvom"))
+    rc = L.roms_b200_set_massflux_tile(C.byref(ta), P(o.field(f"u{nr}")), P(o.field(f"v{nr}")), P(o.field("Hz")), P(o.field("om_v")), P(o.field("on_u")), P(Hu), P(Hv))
+    assert rc == 0 and np.array_equal(Hu, o.field("Huon")) and np.array_equal(Hv, o.field("Hvom"))
+    # omega_tile
+    o.run_phase("omega")
+    W = np.zeros_like(o.field("W"))
+    rc = L.roms_b200_omega_tile(C.byref(ta), P(o.field("Huon")), P(o.field("Hvom")), P(o.field("z_w")), P(W))
+    assert rc == 0 and np.array_equal(W, o.field("W"))
+    # prsgrd_tile
+    o.run_phase("prsgrd")
+    ru, rv = o.field(f"ru{nr}").copy(), o.field(f"rv{nr}").copy()
+    ru[1:] = 0.0; rv[1:] = 0.0
+    rc = L.roms_b200_prsgrd_tile(C.byref(ta), P(o.field("Hz")), P(o.field("om_v")), P(o.field("on_u")), P(o.field("z_r")), P(o.field("z_w")), P(o.field("rho")), P(ru), P(rv))
+    b = orc.bounds(64, 32, 1, 1, 0)
+    sl = (slice(1, None), slice(1, 33), slice(3, 3 + 64))          # k = 1..N, j = 1..Mm, i = 1..Lm
+    assert rc == 0 and np.array_equal(ru[sl], o.field(f"ru{nr}")[sl]) and np.array_equal(rv[:, 2:33, 3:67][1:], o.field(f"rv{nr}")[:, 2:33, 3:67][1:])
+    # set_depth_tile
+    N = 10
+    Hz, zr, zw = np.zeros_like(o.field("Hz")), np.zeros_like(o.field("z_r")), np.zeros_like(o.field("z_w"))
+    rc = L.roms_b200_set_depth_tile(C.byref(ta), P(o.field("h")), P(o.field("Zt_avg1")), P(o.vector(0, N + 1)), P(o.vector(1, N + 1)), P(o.vector(2, N + 1)), P(o.vector(3, N + 1)), P(Hz), P(zr), P(zw))
+    o.run_phase("set_depth")
+    assert rc == 0 and np.array_equal(Hz, o.field("Hz")) and np.array_equal(zr, o.field("z_r")) and np.array_equal(zw, o.field("z_w"))
+    assert b["Istr"] == 1
+
+
+def test_error_behaviour():
+    """exit_flag convention (mod_scalars.F:523-532): input errors 2, configuration 5; blow-up 1 from diag."""
+    t = synth.make_tile(synth.APP_SEAMOUNT)
+    L = t.L
+    bad = np.zeros(10)
+    assert L.roms_b200_set_field(t.h, b"zeta1", bad.ctypes.data_as(_lib.DP), bad.size) == 2      # wrong size
+    assert L.roms_b200_set_field(t.h, b"nonsense", bad.ctypes.data_as(_lib.DP), bad.size) == 2   # unknown field
+    assert L.roms_b200_run_phase(t.h, 99) == 5
+    u = t.get("u1"); u[:] = 50.0; t.set("u1", u); t.set("u2", u)                                  # > max_speed = 20 m/s
+    d = t.diag()
+    assert t.indices()["exit_flag"] == 1 and d["max_speed"] > 20.0
+    t.close()
+
+
+def test_step_forced_e2e_api_matches_resident_path():
+    a = synth.make_tile(synth.APP_BENCHMARK, 96, 40, 30)
+    b = synth.make_tile(synth.APP_BENCHMARK, 96, 40, 30)
+    g, bb = a.synth["grid"], a.synth["bounds"]
+    sustr = synth.tile_slice(synth.sustr_at(synth.APP_BENCHMARK, g, a.cfg, 0.0), 96, bb)
+    z = np.zeros_like(sustr)
+    for _ in range(4):
+        da, rc = a.step_forced(sustr, z, z)
+        assert rc == 0
+        b.main3d(1)
+    for n in ("zeta1", "u1", "v2", "t1_0", "t2_1"):
+        assert np.array_equal(a.get(n), b.get(n)), n
+    assert np.isfinite(da["avgke"]) and da["avgke"] > 0.0 and da["volume"] > 0.0
+    a.close(); b.close()
+
+
+def test_full_size_benchmark1_properties_and_parity():
+    """BENCHMARK1 (512x64x30) at full size: size-independent invariants + parity against the oracle for a few steps."""
+    t = synth.make_tile(synth.APP_BENCHMARK, 512, 64, 30)
+    d0 = t.diag()
+    t.main3d(25)
+    d1 = t.diag()
+    assert abs(d1["volume"] - d0["volume"]) <= 1e-12 * d0["volume"]            # closed/periodic box conserves volume
+    S = t.get("t1_1")[:, 1:-1, 3:-2]
+    assert np.max(np.abs(S - 35.0)) < 1e-10                                    # constant tracer stays constant
+    assert np.isfinite(d1["avgke"]) and d1["avgke"] > 0 and d1["max_speed"] < 1.0 and t.indices()["exit_flag"] == 0
+    # periodic images and closed-wall rows of the prognostic fields are consistent
+    z = t.get("zeta1")[0]
+    assert np.array_equal(z[:, 0:3], z[:, 512:515]) and np.array_equal(z[:, 515:517], z[:, 3:5])
+    assert np.array_equal(z[0], z[1]) and np.all(t.get("v1")[:, 1, :] == 0.0)
+    t.close()
+    o, tt = make_pair(orc.APP_BENCHMARK, strict=False, Lm=512, Mm=64, N=30)
+    for _ in range(3):
+        o.step(1, 8); tt.main3d(1)
+    assert not compare(o, tt, ["zeta1", "u1", "u2", "v1", "v2"], exact=False, rtol=1e-8)
+    assert not compare(o, tt, ["t1_0", "t2_0", "t1_1", "t2_1"], exact=False, rtol=1e-12)
+    tt.close()
+
+
+def test_full_size_benchmark3_smoke():
+    """BENCHMARK3 (2048x256x30), the bench workload: runs, conserves volume, stays finite, images consistent."""
+    t = synth.make_tile(synth.APP_BENCHMARK, 2048, 256, 30)
+    d0 = t.diag()
+    t.main3d(5)
+    d1 = t.diag()
+    assert abs(d1["volume"] - d0["volume"]) <= 1e-12 * d0["volume"]
+    assert np.isfinite(d1["avgke"]) and d1["max_speed"] < 1.0
+    u = t.get("u1")
+    assert np.array_equal(u[:, :, 0:3], u[:, :, 2048:2051])
+    t.close()

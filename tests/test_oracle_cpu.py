@@ -1,0 +1,186 @@
+"""CPU tests (no GPU): pin the oracle against every known answer the reference holds for this path, check its
+tiling invariance (the reference's own acceptance criterion, ROMS/Bin/verify.sh:985-1045), physical invariants, the
+host-side synthetic set-up, and that the C-ABI library loads and exports every declared symbol."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+import orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_kat.json")))
+
+
+# ---- known answers quoted in the reference ---------------------------------------------------------------------
+def test_eos_check_values():
+    """ROMS/Nonlinear/rho_eos.F:21-29: T=3 C, S=35.5, Z=-5000 m -> den, den1, bulk."""
+    k = GOLD["rho_eos_check_values"]
+    den, den1, bulk = orc.eos_point(k["T"], k["S"], k["Z"])
+    assert abs(den - k["den"]) < 5e-10 * k["den"]          # quoted to 14 significant digits
+    assert abs(den1 - k["den1"]) < 5e-10 * k["den1"]
+    assert abs(bulk - k["bulk"]) < 5e-10 * k["bulk"]
+
+
+@pytest.mark.parametrize("ndtfast,nfast", [(30, 42), (20, 29)])
+def test_set_weights(ndtfast, nfast):
+    """ROMS/Utility/set_weights.F FORMAT 40: 'values must be 1, 1, approx 1/2, 1, 1'; nfast = 42 for ndtfast = 30."""
+    nf, chk, w1, w2 = orc.set_weights(ndtfast)
+    assert nf == nfast
+    assert abs(chk[0] - 1.0) < 1e-12          # centroid of the primary weights == ndtfast
+    assert abs(chk[1] - 1.0) < 0.1            # second moment ("1")
+    assert abs(chk[2] - 0.5) < 0.05           # "approx 1/2"
+    assert abs(chk[3] - 1.0) < 1e-12 and abs(chk[4] - 1.0) < 1e-12
+    assert np.all(w1[nf + 1:] == 0.0)         # power-law shape: slightly negative first weights are by design (Fgamma)
+
+
+def test_set_weights_golden_row():
+    """The UPWELLING stdout table of set_weights (ndtfast = 30): integrals row, 12 decimals as printed by FORMAT 40."""
+    _, chk, _, _ = orc.set_weights(30)
+    for got, want in zip(chk, GOLD["set_weights_ndtfast30_integrals"]):
+        assert abs(got - want) < 5e-13
+
+
+# ---- index sets ------------------------------------------------------------------------------------------------
+GRIDS = [(41, 80), (49, 48), (512, 64), (1024, 128), (2048, 256)]
+
+
+@pytest.mark.parametrize("Lm,Mm", GRIDS)
+def test_bounds_partition(Lm, Mm):
+    """tile_bounds_2d (get_bounds.F:985-1004): tiles partition 1..Lm x 1..Mm exactly; edge flags and clipped ranges."""
+    for NtileI in (1, 2, 4, 8):
+        for NtileJ in (1, 2):
+            cover = np.zeros((Mm + 2, Lm + 2), dtype=int)
+            for tile in range(NtileI * NtileJ):
+                b = orc.bounds(Lm, Mm, NtileI, NtileJ, tile)
+                cover[b["Jstr"]:b["Jend"] + 1, b["Istr"]:b["Iend"] + 1] += 1
+                assert b["IstrU"] == b["Istr"] and b["IstrR"] == b["Istr"]        # EW periodic: no clipping in xi
+                assert b["Istrm1"] == b["Istr"] - 1 and b["Iendp2"] == b["Iend"] + 2
+                if b["Southern_Edge"]:
+                    assert (b["JstrV"], b["JstrR"], b["Jstrm1"], b["JstrVm2"]) == (b["Jstr"] + 1, b["Jstr"] - 1, 1, 1)
+                else:
+                    assert (b["JstrV"], b["JstrR"], b["Jstrm1"]) == (b["Jstr"], b["Jstr"], b["Jstr"] - 1)
+                if b["Northern_Edge"]:
+                    assert (b["JendR"], b["Jendp1"], b["Jendp2"]) == (Mm + 1, Mm, Mm + 1)
+                d = orc.bounds(Lm, Mm, NtileI, NtileJ, tile, distribute=True)
+                assert d["LBi"] == (-2 if d["Western_Edge"] else d["Istr"] - 2)
+                assert d["UBi"] == (Lm + 2 if d["Eastern_Edge"] else d["Iend"] + 2)
+            assert np.all(cover[1:Mm + 1, 1:Lm + 1] == 1)
+
+
+# ---- the reference's acceptance criterion: results do not depend on the tiling --------------------------------
+@pytest.mark.parametrize("app,kw,tilings", [
+    (orc.APP_UPWELLING, {}, [(2, 2, 1), (3, 3, 4)]),
+    (orc.APP_SEAMOUNT, {}, [(4, 1, 2), (2, 3, 3)]),
+    (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10), [(2, 2, 2), (8, 1, 4)]),
+])
+def test_tiling_invariance(app, kw, tilings):
+    nsteps = 6
+    a = orc.Oracle(app, kind="chk", **kw)
+    a.step(nsteps)
+    n2, n3 = orc.state_field_names(int(a.opt("NT")))
+    for ni, nj, nth in tilings:
+        b = orc.Oracle(app, NtileI=ni, NtileJ=nj, kind="chk", **kw)
+        b.step(nsteps, nth)
+        bad = [n for n in n2 + n3 if not np.array_equal(a.field(n), b.field(n))]
+        assert not bad, f"{ni}x{nj} tiles differ from 1x1 in {bad}"
+
+
+# ---- physical invariants ---------------------------------------------------------------------------------------
+def test_upwelling_initial_diag_and_conservation():
+    o = orc.Oracle(orc.APP_UPWELLING)
+    o.run_phase("set_data"); o.run_phase("ini")
+    d0 = o.diag()
+    # restated grid / depths / EOS: potential energy and volume of the resting UPWELLING channel
+    assert abs(d0["avgpe"] - GOLD["upwelling_step0"]["avgpe"]) < 1e-6 * d0["avgpe"]
+    assert abs(d0["volume"] - GOLD["upwelling_step0"]["volume"]) < 1e-6 * d0["volume"]
+    assert d0["avgke"] == 0.0
+    o.step(20)
+    d1 = o.diag()
+    assert abs(d1["volume"] - d0["volume"]) < 1e-12 * d0["volume"]          # periodic/closed box: volume conserved
+    S = o.field("t1_1")[:, 1:-1, 3:-2]                                       # salinity stays 35 to round-off
+    assert np.max(np.abs(S - 35.0)) < 1e-11
+    assert o.indices()["exit_flag"] == 0
+
+
+def test_seamount_rest_state_pgf_error():
+    """SEAMOUNT: exact solution is rest; any motion is pressure-gradient truncation error, smaller for the
+    spline density Jacobian (prsgrd32) than for the standard one (prsgrd31)."""
+    res = {}
+    for dj in (1, 0):
+        o = orc.Oracle(orc.APP_SEAMOUNT, dj_gradps=dj)
+        o.step(10)
+        d = o.diag()
+        res[dj] = d["max_speed"]
+        assert d["max_speed"] < 5e-2 and o.indices()["exit_flag"] == 0
+    assert res[1] < res[0]
+
+
+def test_upwelling_regression_golden():
+    """Self-generated regression vector (tests/golden/make_golden.py): pins the oracle against accidental edits."""
+    g = np.load(os.path.join(HERE, "golden", "upwelling_10steps.npz"))
+    o = orc.Oracle(orc.APP_UPWELLING)
+    o.step(10)
+    for n in ("zeta1", "u1", "v1", "t1_0"):
+        a = o.field(n)
+        ref = g[n]
+        assert np.max(np.abs(a - ref)) <= 1e-13 * max(np.max(np.abs(ref)), 1e-30), n
+
+
+# ---- host-side synthetic set-up vs the oracle's restatement ----------------------------------------------------
+@pytest.mark.parametrize("app,kw", [(orc.APP_UPWELLING, {}), (orc.APP_SEAMOUNT, {}), (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10))])
+def test_synth_matches_oracle_setup(app, kw):
+    from roms_trunk_mgh_b200 import synth
+    cfg, F, sc, (nfast, w1, w2) = synth.build(app, **kw)
+    o = orc.Oracle(app, **kw)
+    o.run_phase("set_data"); o.run_phase("ini")
+    N = cfg.N
+    assert nfast == int(o.opt("nfast"))
+    np.testing.assert_allclose(w1, o.vector(4, w1.size), rtol=1e-13, atol=1e-16)
+    np.testing.assert_allclose(w2, o.vector(5, w2.size), rtol=1e-13, atol=1e-16)
+    for which, v in enumerate(sc):
+        np.testing.assert_allclose(v, o.vector(which, N + 1), rtol=1e-14, atol=1e-16)
+    for name, a in F.items():
+        ref = o.field(name)
+        a3 = a if a.ndim == 3 else a[None]
+        scale = max(np.max(np.abs(ref)), 1e-300)
+        assert np.max(np.abs(a3 - ref)) <= 2e-13 * scale, name
+
+
+# ---- the C-ABI library -----------------------------------------------------------------------------------------
+def test_cabi_exports_every_declared_symbol():
+    from roms_trunk_mgh_b200 import _lib
+    import re
+    hdr = open(os.path.join(os.path.dirname(HERE), "include", "roms_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(roms_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(_lib.EXPORTS)
+    for strict in (False, True):
+        L = ctypes.CDLL(_lib.lib_path(strict))
+        for sym in declared:
+            assert hasattr(L, sym), sym
+
+
+def test_cabi_bounds_match_oracle():
+    """roms_b200_bounds (product) vs the oracle's get_bounds restatement: all 57 integers, all supported partitions."""
+    from roms_trunk_mgh_b200 import _lib
+    for Lm, Mm in GRIDS:
+        for NtileI in (1, 2, 4, 8):
+            for tile in range(NtileI):
+                for dist in (False, True):
+                    a = _lib.bounds(Lm, Mm, NtileI, 1, tile, dist)
+                    b = orc.bounds(Lm, Mm, NtileI, 1, tile, dist)
+                    assert a == b, (Lm, Mm, NtileI, tile, dist)
+
+
+def test_cabi_rejects_bad_config_and_has_no_cpu_fallback():
+    from roms_trunk_mgh_b200 import _lib
+    cfg = _lib.default_config(0)
+    cfg.NtileJ = 2
+    h = ctypes.c_void_p()
+    assert _lib.load().roms_b200_create(ctypes.byref(cfg), ctypes.byref(h)) == 5      # configuration error
+    cfg = _lib.default_config(0)
+    import torch
+    if not torch.cuda.is_available():
+        assert _lib.load().roms_b200_create(ctypes.byref(cfg), ctypes.byref(h)) == 8  # no device -> fatal, never a CPU path
