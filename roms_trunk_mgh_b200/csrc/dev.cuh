@@ -90,6 +90,16 @@ __device__ __forceinline__ void st_v_closed(double* __restrict__ A, int o, int i
 // Fire-and-forget prefetch of the line holding *p into L2: needs no destination register, so a thread can have many
 // in flight.  The latency-bound column / multi-stage kernels use it to start the DRAM fetch of later stages early.
 __device__ __forceinline__ void pf_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+constexpr int PFD = 4;            // prefetch distance (levels ahead) of the column-marching kernels
+
+// Asynchronous 8-byte global -> shared copy (LDGSTS): no destination register, completion via wait_group.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }   // Fortran MAX (first arg on ties)
 __device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }

@@ -48,6 +48,31 @@ __device__ __forceinline__ void hadv_fluxes(const double* __restrict__ T, const 
   FEjp = hflux<HADV>(dy0, dyp1, dyp2, t0, sp1, Hvom[o + P + i]);
 }
 
+// Same fluxes from operands that were loaded up front (all global loads of a k-iteration are issued back to back so
+// that the thread waits for memory once per level instead of once per dependent group).
+struct AdvIn { double tm2, tm1, t0, tp1, tp2, sm2, sm1, sp1, sp2, hu0, hu1, hv0, hv1; };
+__device__ __forceinline__ AdvIn adv_load(const double* __restrict__ T, const double* __restrict__ Huon, const double* __restrict__ Hvom,
+                                          int o, int i, int j, const Par& p) {
+  const int P = p.P;
+  AdvIn a;
+  const int om2 = (j > 1) ? -2 * P : -P, op2 = (j < p.Mm) ? 2 * P : P;     // clamped rows keep the loads unconditional
+  a.tm2 = T[o + i - 2]; a.tm1 = T[o + i - 1]; a.t0 = T[o + i]; a.tp1 = T[o + i + 1]; a.tp2 = T[o + i + 2];
+  a.sm2 = T[o + om2 + i]; a.sm1 = T[o - P + i]; a.sp1 = T[o + P + i]; a.sp2 = T[o + op2 + i];
+  a.hu0 = Huon[o + i]; a.hu1 = Huon[o + i + 1]; a.hv0 = Hvom[o + i]; a.hv1 = Hvom[o + P + i];
+  return a;
+}
+template <int HADV>
+__device__ __forceinline__ void hadv_fluxes_v(const AdvIn& a, int j, int Mm, double& FXi, double& FXip, double& FEj, double& FEjp) {
+  const double dxm1 = a.tm1 - a.tm2, dx0 = a.t0 - a.tm1, dxp1 = a.tp1 - a.t0, dxp2 = a.tp2 - a.tp1;
+  FXi = hflux<HADV>(dxm1, dx0, dxp1, a.tm1, a.t0, a.hu0);
+  FXip = hflux<HADV>(dx0, dxp1, dxp2, a.t0, a.tp1, a.hu1);
+  const double dy0 = a.t0 - a.sm1, dyp1 = a.sp1 - a.t0;
+  const double dym1 = (j > 1) ? (a.sm1 - a.sm2) : dy0;
+  const double dyp2 = (j < Mm) ? (a.sp2 - a.sp1) : dyp1;
+  FEj = hflux<HADV>(dym1, dy0, dyp1, a.sm1, a.t0, a.hv0);
+  FEjp = hflux<HADV>(dy0, dyp1, dyp2, a.t0, a.sp1, a.hv1);
+}
+
 // Vertical advective flux through the top of level k (k = 1..N-1) from a column tc[0..N+1].
 // CENTERED4 (pre_step3d.F:751-785), AKIMA4 (:667-707), CENTERED2 (:709-727); same in step3d_t.F:938-1126.
 template <int VADV>

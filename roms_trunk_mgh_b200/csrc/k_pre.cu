@@ -30,38 +30,54 @@ __global__ void __launch_bounds__(128) k_pre_step3d_t(Par p, Flds f) {
   double cff, cff1h, cff2h;
   if (p.istart == 0) { cff = 0.5 * p.dt; cff1h = 1.0; cff2h = 0.0; }
   else { cff = (1.0 - Gamma) * p.dt; cff1h = 0.5 + Gamma; cff2h = 0.5 - Gamma; }
-  double tc[MAXN + 2];
-  for (int k = 1; k <= N; ++k) tc[k] = tst[o2 + k * p.PL + i];
-  tc[0] = tc[1]; tc[N + 1] = tc[N];
+  // Rolling vertical window of t(nstp) (tkm1 = t(k-1) ... tkp2 = t(k+2)) and software-pipelined operand loads: the loads
+  // of level k+1 are issued, back to back, before level k is computed, so a thread waits for memory once per level.
+  struct Lvl { AdvIn a; double tnw, hz, W, zr1, akt, tk3; };
+  auto load_level = [&](int k) -> Lvl {
+    const int o = o2 + k * p.PL;
+    Lvl L;
+    L.a = adv_load(tst, Huon, Hvom, o, i, j, p);
+    L.tnw = tnw[o + i]; L.hz = Hz[o + i]; L.W = W[o + i]; L.akt = Akt[o + i];
+    L.zr1 = z_r[o + ((k < N) ? p.PL : 0) + i];                   // z_r(k+1) (k = N: unused)
+    L.tk3 = tst[o2 + ((k + 2 <= N) ? (k + 2) : N) * p.PL + i];   // t(k+2), clamped
+    return L;
+  };
   const double cff3 = p.dt * (1.0 - p.lambda);
   double FCm = 0.0;                                   // advective FC(k-1)
   double FDm = p.dt * f.btflx[itrc][o2 + i];          // diffusive FC(k-1), FC(0) = dt*btflx
   double Wm = W[o2 + i];                              // W(k-1)
+  double zrk = z_r[o2 + p.PL + i];                    // z_r(k)
+  Lvl cur = load_level(1);
+  double tkm1 = cur.a.t0, tk = cur.a.t0, tkp1 = tst[o2 + 2 * p.PL + i], tkp2 = cur.tk3;
   for (int k = 1; k <= N; ++k) {
     const int o = o2 + k * p.PL;
-    const double hz = Hz[o + i];
+    Lvl nxt = cur;
+    if (k < N) nxt = load_level(k + 1);
+    const double hz = cur.hz;
     double FXi, FXip, FEj, FEjp;
-    hadv_fluxes<HADV>(tst, Huon, Hvom, o, i, j, p, FXi, FXip, FEj, FEjp);
+    hadv_fluxes_v<HADV>(cur.a, j, p.Mm, FXi, FXip, FEj, FEjp);
     const double div = FXip - FXi + FEjp - FEj;
-    double t3v = hz * (cff1h * tc[k] + cff2h * tnw[o + i]) - cff * pm * pn * div;
-    const double Wk = W[o + i];
-    const double FCk = (k < N) ? vflux<VADV>(tc, k, N, Wk) : 0.0;
-    const double DC = 1.0 / (hz - cff * pm * pn * (Huon[o + i + 1] - Huon[o + i] + Hvom[o + P + i] - Hvom[o + i] + (Wk - Wm)));
+    double t3v = hz * (cff1h * tk + cff2h * cur.tnw) - cff * pm * pn * div;
+    const double Wk = cur.W;
+    const double FCk = (k < N) ? vflux4<VADV>(tkm1, tk, tkp1, tkp2, k, N, Wk) : 0.0;
+    const double DC = 1.0 / (hz - cff * pm * pn * (cur.a.hu1 - cur.a.hu0 + cur.a.hv1 - cur.a.hv0 + (Wk - Wm)));
     const double cff1 = cff * pm * pn;
     t3v = DC * (t3v - cff1 * (FCk - FCm));
     st_r_grad(t3, o, i, j, t3v, p);
     // t(nnew) = Hz*t(nstp) + explicit part of the vertical diffusion (zero for lambda = 1) + surface/bottom fluxes
     double FDk;
     if (k < N) {
-      const double c = 1.0 / (z_r[o + p.PL + i] - z_r[o + i]);
-      FDk = cff3 * c * Akt[o + i] * (tc[k + 1] - tc[k]);
+      const double c = 1.0 / (cur.zr1 - zrk);
+      FDk = cff3 * c * cur.akt * (tkp1 - tk);
     } else {
       FDk = p.dt * f.stflx[itrc][o2 + i];
     }
-    const double c1 = hz * tc[k];
+    const double c1 = hz * tk;
     const double c2 = FDk - FDm;
     tnw[o + i] = c1 + c2;
-    FCm = FCk; FDm = FDk; Wm = Wk;
+    FCm = FCk; FDm = FDk; Wm = Wk; zrk = cur.zr1;
+    tkm1 = tk; tk = tkp1; tkp1 = tkp2; tkp2 = nxt.tk3;
+    cur = nxt;
   }
 }
 

@@ -38,6 +38,10 @@ __global__ void __launch_bounds__(128) k_rhs3d(Par p, Flds f) {
   double FCu_m = 0.0, FCv_m = 0.0, rufrc = 0.0, rvfrc = 0.0;
   for (int k = 1; k <= N; ++k) {
     const int o = o2 + k * p.PL + i;                     // includes i
+    if (k + PFD <= N) {                                  // start the DRAM fetch of level k+PFD
+      const int q = o + PFD * p.PL;
+      pf_l2(u + q); pf_l2(v + q); pf_l2(Hz + q); pf_l2(Huon + q); pf_l2(Hvom + q); pf_l2(W + q); pf_l2(ru + q); pf_l2(rv + q);
+    }
     const double hz0 = Hz[o], hzW = Hz[o - 1], hzS = Hz[o - P];
     const double u0 = u[o], uE = u[o + 1], uW = u[o - 1], uN = u[o + P], uS = u[o - P];
     const double v0 = v[o], vN = v[o + P], vW = v[o - 1], vE = v[o + 1], vS = v[o - P];
@@ -208,6 +212,7 @@ __global__ void __launch_bounds__(128) k_uv3dmix2(Par p, Flds f) {
   double rufrc = f.rufrc[o2], rvfrc = dov ? f.rvfrc[o2] : 0.0;
   for (int k = 1; k <= N; ++k) {
     const int o3 = o2 + k * p.PL;
+    if (k + PFD <= N) { const int q = o3 + PFD * p.PL; pf_l2(u + q); pf_l2(v + q); pf_l2(Hz + q); pf_l2(un + q); pf_l2(vn + q); }
     const double cr0 = rho_cff(o2, o3), crW = rho_cff(o2 - 1, o3 - 1);
     const double cp0 = psi_cff(o2, o3), cpN = psi_cff(o2 + P, o3 + P);
     {

@@ -11,20 +11,25 @@
 //            psi-point fluxes: advective UFe, VFx (:1141-1150,:1213-1222), viscous UFe, VFx (:1415-1430)
 //   stage 3  fast-time averages (:614-682), pressure gradient (:944-1019), flux divergences, 2-D/3-D coupling
 //            (:1884-2065), LF / AM3 stepping (:2098-2255), rhs history (:2420-2430), closed-wall BCs, periodic images.
+// The kernel is latency-bound, not bandwidth-bound, so every stage issues ALL of its global loads back to back before the
+// first use (one memory wait per stage), the CTA has enough threads (NTH) to cover the (TX+1)x(TY+1) flux regions in a
+// single pass, and stage 0 also fetches the operands of stage 1.
 #include "dev.cuh"
 #include "kernels.h"
 
 namespace rb {
 
 constexpr int TX = 32, TY = 8;           // output tile
+constexpr int NTH = 320;                 // threads per CTA (>= (TX+1)*(TY+1) = 297)
 constexpr int HL = 3, HH = 2;            // low / high halo of the staged inputs
 constexpr int SW = TX + HL + HH;         // staged width  (37)
-constexpr int SH = TY + HL + HH;         // staged height (21)
+constexpr int SH = TY + HL + HH;         // staged height (13)
 constexpr int ZW = TX + 1, ZH = TY + 1;  // flux / zeta regions: one extra column and row
 constexpr int NS = SW * SH, NZ = ZW * ZH;
 constexpr int SMEM_DOUBLES = 5 * NS + 17 * NZ;
+static_assert(NZ <= NTH && NS <= 2 * NTH, "tile / thread-count mismatch");
 
-__global__ void __launch_bounds__(TX * TY, 3) k_step2d(Par p, Flds f) {
+__global__ void __launch_bounds__(NTH, 2) k_step2d(Par p, Flds f) {
   extern __shared__ double smem[];
   double* sD = smem; double* sU = sD + NS; double* sV = sU + NS; double* sDU = sV + NS; double* sDV = sDU + NS;
   // regions with origin (i0-1, j0-1): zeta-stage and rho-point fluxes
@@ -33,8 +38,8 @@ __global__ void __launch_bounds__(TX * TY, 3) k_step2d(Par p, Flds f) {
   double* kUFx = cVFe + NZ; double* kVFe = kUFx + NZ; double* vUFx = kVFe + NZ; double* vVFe = vUFx + NZ;
   // regions with origin (i0, j0): psi-point fluxes
   double* aUFe = vVFe + NZ; double* aVFx = aUFe + NZ; double* vUFe = aVFx + NZ; double* vVFx = vUFe + NZ;
-  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
-  const int i0 = p.Istr + blockIdx.x * TX, j0 = blockIdx.y * TY;       // tile origin (rho point of thread 0,0)
+  const int tid = threadIdx.x;
+  const int i0 = p.Istr + blockIdx.x * TX, j0 = blockIdx.y * TY;       // tile origin
   const int P = p.P, Mm = p.Mm;
   const bool PRED = p.predictor != 0;
   const bool FIRST = (p.iif == 1);
@@ -45,54 +50,47 @@ __global__ void __launch_bounds__(TX * TY, 3) k_step2d(Par p, Flds f) {
   const double* __restrict__ pm = f.pm;
   const double* __restrict__ pn = f.pn;
 
-  // ---- prefetch (L2) what stages 2-3 will read at this thread's own point, so that their DRAM latency overlaps stages 0-1
-  {
-    const int ip = i0 + tx, jp = j0 + ty;
-    if (ip <= p.Iend && jp <= Mm + 1) {
-      const int q = jp * P + ip;
-      pf_l2(zs + q); pf_l2(pm + q); pf_l2(pn + q); pf_l2(f.rhoS + q); pf_l2(f.rhoA + q); pf_l2(f.fomn + q);
-      pf_l2(f.visc2_r + q); pf_l2(f.pmon_r + q); pf_l2(f.pnom_r + q); pf_l2(f.on_r + q); pf_l2(f.om_r + q);
-      pf_l2(f.visc2_p + q); pf_l2(f.pmon_p + q); pf_l2(f.pnom_p + q); pf_l2(f.om_p + q); pf_l2(f.on_p + q);
-      pf_l2(f.DU_avg2 + q); pf_l2(f.DV_avg2 + q); pf_l2(f.rufrc + q); pf_l2(f.rvfrc + q);
-      pf_l2(f.ubar[p.kstp] + q); pf_l2(f.vbar[p.kstp] + q);
-      if (p.curvgrid) { pf_l2(f.dndx + q); pf_l2(f.dmde + q); }
-      if (PRED) { pf_l2(f.Zt_avg1 + q); pf_l2(f.DU_avg1 + q); pf_l2(f.DV_avg1 + q); }
-      else { pf_l2(f.rzeta[p.kstp] + q); pf_l2(f.rzeta[p.ptsk] + q); pf_l2(f.rubar[p.kstp] + q); pf_l2(f.rubar[p.ptsk] + q);
-             pf_l2(f.rvbar[p.kstp] + q); pf_l2(f.rvbar[p.ptsk] + q); }
-    }
-  }
-  // ---- stage 0: Drhs, ubar, vbar on the staged region
+  // ---- stages 0/1: Drhs, ubar, vbar, DUon, DVom on the staged region (two items per thread, loads first)
   {
     const double* __restrict__ ur = f.ubar[p.krhs];
     const double* __restrict__ vr = f.vbar[p.krhs];
-    for (int s = tid; s < NS; s += TX * TY) {
+    double zv[2], hv[2], uv[2], vv[2], onu[2], omv[2];
+    bool ok[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int s = tid + r * NTH;
       const int a = s % SW, b = s / SW;
       const int i = i0 - HL + a, j = j0 - HL + b;
-      double d = 0.0, u = 0.0, v = 0.0;
-      if (i >= p.LBi && i <= p.UBi && j >= 0 && j <= Mm + 1) {
-        const int q = j * P + i;
-        d = zr[q] + h[q]; u = ur[q]; v = vr[q];
+      ok[r] = (s < NS) && i >= p.LBi && i <= p.UBi && j >= 0 && j <= Mm + 1;
+      const int q = ok[r] ? (j * P + i) : (j0 * P + i0);               // safe dummy address
+      zv[r] = zr[q]; hv[r] = h[q]; uv[r] = ur[q]; vv[r] = vr[q]; onu[r] = f.on_u[q]; omv[r] = f.om_v[q];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int s = tid + r * NTH;
+      if (s < NS) { sD[s] = ok[r] ? (zv[r] + hv[r]) : 0.0; sU[s] = ok[r] ? uv[r] : 0.0; sV[s] = ok[r] ? vv[r] : 0.0; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int s = tid + r * NTH;
+      if (s < NS) {
+        const int a = s % SW, b = s / SW;
+        const int i = i0 - HL + a, j = j0 - HL + b;
+        double du = 0.0, dv = 0.0;
+        if (ok[r] && i > p.LBi && a >= 1) {
+          const double c = 0.5 * onu[r];
+          const double c1 = c * (sD[s] + sD[s - 1]);
+          du = sU[s] * c1;
+        }
+        if (ok[r] && j >= 1 && b >= 1) {
+          const double c = 0.5 * omv[r];
+          const double c1 = c * (sD[s] + sD[s - SW]);
+          dv = sV[s] * c1;
+        }
+        sDU[s] = du; sDV[s] = dv;
       }
-      sD[s] = d; sU[s] = u; sV[s] = v;
     }
-  }
-  __syncthreads();
-  // ---- stage 1: DUon (needs Drhs(i-1)), DVom (needs Drhs(j-1))
-  for (int s = tid; s < NS; s += TX * TY) {
-    const int a = s % SW, b = s / SW;
-    const int i = i0 - HL + a, j = j0 - HL + b;
-    double du = 0.0, dv = 0.0;
-    if (i > p.LBi && i <= p.UBi && j >= 0 && j <= Mm + 1 && a >= 1) {
-      const double c = 0.5 * f.on_u[j * P + i];
-      const double c1 = c * (sD[s] + sD[s - 1]);
-      du = sU[s] * c1;
-    }
-    if (i >= p.LBi && i <= p.UBi && j >= 1 && j <= Mm + 1 && b >= 1) {
-      const double c = 0.5 * f.om_v[j * P + i];
-      const double c1 = c * (sD[s] + sD[s - SW]);
-      dv = sV[s] * c1;
-    }
-    sDU[s] = du; sDV[s] = dv;
   }
   __syncthreads();
 
@@ -110,40 +108,45 @@ __global__ void __launch_bounds__(TX * TY, 3) k_step2d(Par p, Flds f) {
 #define GYV(di, dj) (V_(di, (dj)-1) - 2.0 * V_(di, dj) + V_(di, (dj) + 1))
 #define GYDV(di, dj) (DV_(di, (dj)-1) - 2.0 * DV_(di, dj) + DV_(di, (dj) + 1))
 
-  if (active) {
+  if (active && tid < NZ) {
     const double c6 = 1.0 / 6.0;
-    // ---- stage 2a: rho-point quantities on the region with origin (i0-1, j0-1)
-    const double fac = 1000.0 / p.rho0;
-    for (int s = tid; s < NZ; s += TX * TY) {
-      const int za = s % ZW, zb = s / ZW;
+    const int za = tid % ZW, zb = tid / ZW;
+    // ---- stage 2a: rho-point quantities at (i0-1+za, j0-1+zb)
+    {
       const int i = i0 - 1 + za, j = j0 - 1 + zb;
       const int c0 = (zb + HL - 1) * SW + (za + HL - 1);               // staged index of (i,j)
       double Dnew = 0.0, zwrk = 0.0, gz = 0.0, gz2 = 0.0, gsa = 0.0;
       double a_ufx = 0.0, a_vfe = 0.0, c_ufx = 0.0, c_vfe = 0.0, k_ufx = 0.0, k_vfe = 0.0, v_ufx = 0.0, v_vfe = 0.0;
       if (j >= 1 && j <= Mm && i <= p.Iend) {
         const int q = j * P + i;
+        // all global operands of this stage, issued back to back
+        const double zs_q = zs[q], zr_q = zr[q], pm_q = pm[q], pn_q = pn[q], h_q = h[q], rS = f.rhoS[q], rA = f.rhoA[q];
+        const double fomn_q = f.fomn[q], visc_q = f.visc2_r[q], pmon_q = f.pmon_r[q], pnom_q = f.pnom_r[q];
+        const double pnE = pn[q + 1], pnW = pn[q - 1], pmN = pm[q + P], pmS = pm[q - P], onr = f.on_r[q], omr = f.om_r[q];
+        double dndx_q = 0.0, dmde_q = 0.0, rz_s = 0.0, rz_p = 0.0;
+        if (p.curvgrid) { dndx_q = f.dndx[q]; dmde_q = f.dmde[q]; }
+        if (!FIRST && !PRED) { rz_s = f.rzeta[p.kstp][q]; rz_p = f.rzeta[p.ptsk][q]; }
         // new free surface (:770-851)
         const double dd = (DU_(0, 0) - DU_(1, 0)) + (DV_(0, 0) - DV_(0, 1));
         double zeta_new;
-        const double pmn = pm[q] * pn[q];
+        const double pmn = pm_q * pn_q;
         if (FIRST) {
-          zeta_new = zs[q] + pmn * p.dtfast * dd;
-          zwrk = 0.5 * (zs[q] + zeta_new);
+          zeta_new = zs_q + pmn * p.dtfast * dd;
+          zwrk = 0.5 * (zs_q + zeta_new);
         } else if (PRED) {
           const double cff1 = 2.0 * p.dtfast, cff4 = 4.0 / 25.0, cff5 = 1.0 - 2.0 * cff4;
-          zeta_new = zs[q] + pmn * cff1 * dd;
-          zwrk = cff5 * zr[q] + cff4 * (zs[q] + zeta_new);
+          zeta_new = zs_q + pmn * cff1 * dd;
+          zwrk = cff5 * zr_q + cff4 * (zs_q + zeta_new);
         } else {
           const double cff1 = p.dtfast * 5.0 / 12.0, cff2 = p.dtfast * 8.0 / 12.0, cff3 = p.dtfast * 1.0 / 12.0, cff4 = 2.0 / 5.0, cff5 = 1.0 - cff4;
           const double cff = cff1 * dd;
-          zeta_new = zs[q] + pmn * (cff + cff2 * f.rzeta[p.kstp][q] - cff3 * f.rzeta[p.ptsk][q]);
-          zwrk = cff5 * zeta_new + cff4 * zr[q];
+          zeta_new = zs_q + pmn * (cff + cff2 * rz_s - cff3 * rz_p);
+          zwrk = cff5 * zeta_new + cff4 * zr_q;
         }
-        Dnew = zeta_new + h[q];
-        const double rS = f.rhoS[q];
-        gz = (fac + rS) * zwrk;
+        Dnew = zeta_new + h_q;
+        gz = (1000.0 / p.rho0 + rS) * zwrk;
         gz2 = gz * zwrk;
-        gsa = zwrk * (rS - f.rhoA[q]);
+        gsa = zwrk * (rS - rA);
         if (za >= 1 && zb >= 1) {                                      // own points of this tile
           st_r_grad(f.zeta[p.knew], j * P, i, j, zeta_new, p);
           if (PRED) st_w(f.rzeta[p.krhs], j * P, i, dd, p);
@@ -159,34 +162,35 @@ __global__ void __launch_bounds__(TX * TY, 3) k_step2d(Par p, Flds f) {
         const double D0 = D_(0, 0);
         const double vS = V_(0, 0) + V_(0, 1), uS = U_(0, 0) + U_(1, 0);
         {
-          const double c = 0.5 * D0 * f.fomn[q];
+          const double c = 0.5 * D0 * fomn_q;
           c_ufx = c * vS; c_vfe = c * uS;
         }
         if (p.curvgrid) {
           const double c1 = 0.5 * vS, c2 = 0.5 * uS;
-          const double c = D0 * (c1 * f.dndx[q] - c2 * f.dmde[q]);
+          const double c = D0 * (c1 * dndx_q - c2 * dmde_q);
           k_ufx = c * c1; k_vfe = c * c2;
         }
         // viscous stress at rho(i,j) (:1400-1414)
         {
-          const double cr = f.visc2_r[q] * D0 * 0.5 *
-                            (f.pmon_r[q] * ((pn[q] + pn[q + 1]) * U_(1, 0) - (pn[q - 1] + pn[q]) * U_(0, 0)) -
-                             f.pnom_r[q] * ((pm[q] + pm[q + P]) * V_(0, 1) - (pm[q - P] + pm[q]) * V_(0, 0)));
-          const double onr = f.on_r[q], omr = f.om_r[q];
+          const double cr = visc_q * D0 * 0.5 *
+                            (pmon_q * ((pn_q + pnE) * U_(1, 0) - (pnW + pn_q) * U_(0, 0)) -
+                             pnom_q * ((pm_q + pmN) * V_(0, 1) - (pmS + pm_q) * V_(0, 0)));
           v_ufx = onr * onr * cr; v_vfe = omr * omr * cr;
         }
       }
-      sDnew[s] = Dnew; sZw[s] = zwrk; sG[s] = gz; sG2[s] = gz2; sGSA[s] = gsa;
-      aUFx[s] = a_ufx; aVFe[s] = a_vfe; cUFx[s] = c_ufx; cVFe[s] = c_vfe; kUFx[s] = k_ufx; kVFe[s] = k_vfe; vUFx[s] = v_ufx; vVFe[s] = v_vfe;
+      sDnew[tid] = Dnew; sZw[tid] = zwrk; sG[tid] = gz; sG2[tid] = gz2; sGSA[tid] = gsa;
+      aUFx[tid] = a_ufx; aVFe[tid] = a_vfe; cUFx[tid] = c_ufx; cVFe[tid] = c_vfe; kUFx[tid] = k_ufx; kVFe[tid] = k_vfe; vUFx[tid] = v_ufx; vVFe[tid] = v_vfe;
     }
-    // ---- stage 2b: psi-point fluxes on the region with origin (i0, j0)
-    for (int s = tid; s < NZ; s += TX * TY) {
-      const int za = s % ZW, zb = s / ZW;
+    // ---- stage 2b: psi-point fluxes at (i0+za, j0+zb)
+    {
       const int i = i0 + za, j = j0 + zb;
       const int c0 = (zb + HL) * SW + (za + HL);
       double a_ufe = 0.0, a_vfx = 0.0, v_ufe = 0.0, v_vfx = 0.0;
       if (j >= 1 && j <= Mm + 1 && i <= p.Iend + 1) {
         const int q = j * P + i;
+        const double visc_q = f.visc2_p[q], pmon_q = f.pmon_p[q], pnom_q = f.pnom_p[q], omp = f.om_p[q], onp = f.on_p[q];
+        const double pn_q = pn[q], pnS = pn[q - P], pnW = pn[q - 1], pnSW = pn[q - P - 1];
+        const double pm_q = pm[q], pmS = pm[q - P], pmW = pm[q - 1], pmSW = pm[q - P - 1];
         // advective UFe at psi(i,j) (:1141-1150): grad = d2y(ubar), rows 1..Mm with wall copies (0)=(1), (Mm+1)=(Mm)
         {
           const int d0 = (j > Mm) ? -1 : 0, dm = (j - 1 < 1) ? 0 : -1;
@@ -198,22 +202,42 @@ __global__ void __launch_bounds__(TX * TY, 3) k_step2d(Par p, Flds f) {
         // viscous stress at psi(i,j) (:1394-1430)
         {
           const double Dp = 0.25 * (D_(0, 0) + D_(-1, 0) + D_(0, -1) + D_(-1, -1));
-          const double cp = f.visc2_p[q] * Dp * 0.5 *
-                            (f.pmon_p[q] * ((pn[q - P] + pn[q]) * V_(0, 0) - (pn[q - P - 1] + pn[q - 1]) * V_(-1, 0)) +
-                             f.pnom_p[q] * ((pm[q - 1] + pm[q]) * U_(0, 0) - (pm[q - P - 1] + pm[q - P]) * U_(0, -1)));
-          const double omp = f.om_p[q], onp = f.on_p[q];
+          const double cp = visc_q * Dp * 0.5 *
+                            (pmon_q * ((pnS + pn_q) * V_(0, 0) - (pnSW + pnW) * V_(-1, 0)) +
+                             pnom_q * ((pmW + pm_q) * U_(0, 0) - (pmSW + pmS) * U_(0, -1)));
           v_ufe = omp * omp * cp; v_vfx = onp * onp * cp;
         }
       }
-      aUFe[s] = a_ufe; aVFx[s] = a_vfx; vUFe[s] = v_ufe; vVFx[s] = v_vfx;
+      aUFe[tid] = a_ufe; aVFx[tid] = a_vfx; vUFe[tid] = v_ufe; vVFx[tid] = v_vfx;
     }
   }
   __syncthreads();
 
   // ---- stage 3: one thread per rho point of the tile
+  if (tid >= TX * TY) return;
+  const int tx = tid % TX, ty = tid / TX;
   const int i = i0 + tx, j = j0 + ty;
   if (i > p.Iend || j > Mm + 1) return;
   const int o = j * P + i;
+  const bool inner = active && j >= 1 && j <= Mm;
+  const bool dov = inner && (j >= p.JstrV);
+  const int oS = (j >= 1) ? o - P : o;                                  // row j-1 (clamped so the loads stay in bounds)
+  // all global operands of this stage, issued back to back
+  const double zr_o = zr[o];
+  const double av_du2 = f.DU_avg2[o], av_dv2 = f.DV_avg2[o];
+  double av_zt = 0.0, av_du1 = 0.0, av_dv1 = 0.0;
+  if (PRED && !FIRST) { av_zt = f.Zt_avg1[o]; av_du1 = f.DU_avg1[o]; av_dv1 = f.DV_avg1[o]; }
+  const double h0 = h[o], hW = h[o - 1], hS = h[oS];
+  const double rA0 = f.rhoA[o], rAW = f.rhoA[o - 1], rAS = f.rhoA[oS];
+  const double pm0 = pm[o], pmW = pm[o - 1], pmS = pm[oS], pn0 = pn[o], pnW = pn[o - 1], pnS = pn[oS];
+  const double onu = f.on_u[o], omv = f.om_v[o];
+  const double zs0 = zs[o], zsW = zs[o - 1], zsS = zs[oS];
+  const double us = f.ubar[p.kstp][o], vs = f.vbar[p.kstp][o];
+  const double rufrc_o = f.rufrc[o], rvfrc_o = f.rvfrc[o];
+  double rub_s = 0.0, rub_p = 0.0, rvb_s = 0.0, rvb_p = 0.0, ru_n = 0.0, ru_so = 0.0, rv_n = 0.0, rv_so = 0.0;
+  if (!FIRST && !PRED) { rub_s = f.rubar[p.kstp][o]; rub_p = f.rubar[p.ptsk][o]; rvb_s = f.rvbar[p.kstp][o]; rvb_p = f.rvbar[p.ptsk][o]; }
+  if (FIRST && PRED && p.istart >= 1) { ru_n = f.ru[p.nnew][o]; rv_n = f.rv[p.nnew][o]; ru_so = f.ru[p.nstp][o]; rv_so = f.rv[p.nstp][o]; }
+
   // fast-time averages (:614-682); rows 0..Mm+1 for Zt/DU, rows 1..Mm+1 for DV
   {
     const int c0 = (ty + HL) * SW + (tx + HL);
@@ -228,35 +252,30 @@ __global__ void __launch_bounds__(TX * TY, 3) k_step2d(Par p, Flds f) {
       } else {
         const double cff1 = p.w1_m1;
         const double cff2 = (8.0 / 12.0) * p.w2_0 - (1.0 / 12.0) * p.w2_p1;
-        st_w(f.Zt_avg1, j * P, i, f.Zt_avg1[o] + cff1 * zr[o], p);
-        st_w(f.DU_avg1, j * P, i, f.DU_avg1[o] + cff1 * DUo, p);
-        f.DU_avg2[o] = f.DU_avg2[o] + cff2 * DUo;
+        st_w(f.Zt_avg1, j * P, i, av_zt + cff1 * zr_o, p);
+        st_w(f.DU_avg1, j * P, i, av_du1 + cff1 * DUo, p);
+        f.DU_avg2[o] = av_du2 + cff2 * DUo;
         if (j >= 1) {
-          st_w(f.DV_avg1, j * P, i, f.DV_avg1[o] + cff1 * DVo, p);
-          f.DV_avg2[o] = f.DV_avg2[o] + cff2 * DVo;
+          st_w(f.DV_avg1, j * P, i, av_dv1 + cff1 * DVo, p);
+          f.DV_avg2[o] = av_dv2 + cff2 * DVo;
         }
       }
     } else {
       const double cff2 = FIRST ? p.w2_0 : (5.0 / 12.0) * p.w2_0;
-      f.DU_avg2[o] = f.DU_avg2[o] + cff2 * DUo;
-      if (j >= 1) f.DV_avg2[o] = f.DV_avg2[o] + cff2 * DVo;
+      f.DU_avg2[o] = av_du2 + cff2 * DUo;
+      if (j >= 1) f.DV_avg2[o] = av_dv2 + cff2 * DVo;
     }
   }
-  if (!active) return;
-  if (j < 1 || j > Mm) return;
-  const bool dov = (j >= p.JstrV);
+  if (!inner) return;
   const int z0 = (ty + 1) * ZW + (tx + 1), zW = z0 - 1, zS = z0 - ZW;   // rho-region indices of (i,j), (i-1,j), (i,j-1)
   const int p0 = ty * ZW + tx, pE = p0 + 1, pN = p0 + ZW;               // psi-region indices of (i,j), (i+1,j), (i,j+1)
-  const double* __restrict__ rhoA = f.rhoA;
-  const double h0 = h[o], hW = h[o - 1], rA0 = rhoA[o];
-  const double pmU = pm[o] + pm[o - 1], pnU = pn[o] + pn[o - 1];
 
   // ---- u-point (i,j)
   {
     const double cff1 = 0.5 * p.g, cff2 = 1.0 / 3.0;
-    double rhs_u = cff1 * f.on_u[o] *
+    double rhs_u = cff1 * onu *
                    ((hW + h0) * (sG[zW] - sG[z0]) +
-                    (hW - h0) * (sGSA[zW] + sGSA[z0] + cff2 * (rhoA[o - 1] - rA0) * (sZw[zW] - sZw[z0])) +
+                    (hW - h0) * (sGSA[zW] + sGSA[z0] + cff2 * (rAW - rA0) * (sZw[zW] - sZw[z0])) +
                     (sG2[zW] - sG2[z0]));
     {
       const double a1 = aUFx[z0] - aUFx[zW];
@@ -267,46 +286,43 @@ __global__ void __launch_bounds__(TX * TY, 3) k_step2d(Par p, Flds f) {
     rhs_u = rhs_u + 0.5 * (cUFx[z0] + cUFx[zW]);
     if (p.curvgrid) rhs_u = rhs_u + 0.5 * (kUFx[z0] + kUFx[zW]);
     {
-      const double a1 = 0.5 * (pn[o - 1] + pn[o]) * (vUFx[z0] - vUFx[zW]);
-      const double a2 = 0.5 * (pm[o - 1] + pm[o]) * (vUFe[pN] - vUFe[p0]);
+      const double a1 = 0.5 * (pnW + pn0) * (vUFx[z0] - vUFx[zW]);
+      const double a2 = 0.5 * (pmW + pm0) * (vUFe[pN] - vUFe[p0]);
       const double fc = a1 + a2;
       rhs_u = rhs_u + fc;
     }
-    // coupling with the 3-D equations (:1884-2065)
+    // coupling with the 3-D equations (:1884-2065); level k = 0 planes of ru carry the AB3 history of the 2-D forcing
     if (FIRST && PRED) {
-      double* __restrict__ ru_s = f.ru[p.nstp];      // level k = 0 planes carry the AB3 history of the 2-D forcing
-      const double rf = f.rufrc[o] - rhs_u;
+      const double rf = rufrc_o - rhs_u;
       if (p.istart == 0) rhs_u = rhs_u + rf;
-      else if (p.istart == 1) rhs_u = rhs_u + 1.5 * rf - 0.5 * f.ru[p.nnew][o];
-      else rhs_u = rhs_u + (23.0 / 12.0) * rf - (16.0 / 12.0) * f.ru[p.nnew][o] + (5.0 / 12.0) * ru_s[o];
+      else if (p.istart == 1) rhs_u = rhs_u + 1.5 * rf - 0.5 * ru_n;
+      else rhs_u = rhs_u + (23.0 / 12.0) * rf - (16.0 / 12.0) * ru_n + (5.0 / 12.0) * ru_so;
       f.rufrc[o] = rf;
-      ru_s[o] = rf;
+      f.ru[p.nstp][o] = rf;
     } else {
-      rhs_u = rhs_u + f.rufrc[o];
+      rhs_u = rhs_u + rufrc_o;
     }
     // time stepping (:2098-2255), rhs history (:2420-2430), BCs (:2451-2460), periodic images (:2509-2524)
-    const double Dstp = (zs[o] + h0) + (zs[o - 1] + hW);
-    const double cff = pmU * pnU;
+    const double Dstp = (zs0 + h0) + (zsW + hW);
+    const double cff = (pm0 + pmW) * (pn0 + pnW);
     const double fc = 1.0 / (sDnew[z0] + sDnew[zW]);
-    const double us = f.ubar[p.kstp][o];
     double x;
     if (FIRST || PRED) {
       const double c1 = FIRST ? 0.5 * p.dtfast : p.dtfast;
       x = (us * Dstp + cff * c1 * rhs_u) * fc;
     } else {
       const double c1 = 0.5 * p.dtfast * 5.0 / 12.0, c2 = 0.5 * p.dtfast * 8.0 / 12.0, c3 = 0.5 * p.dtfast * 1.0 / 12.0;
-      x = (us * Dstp + cff * (c1 * rhs_u + c2 * f.rubar[p.kstp][o] - c3 * f.rubar[p.ptsk][o])) * fc;
+      x = (us * Dstp + cff * (c1 * rhs_u + c2 * rub_s - c3 * rub_p)) * fc;
     }
     st_u_closed(f.ubar[p.knew], j * P, i, j, x, p);
     if (PRED) f.rubar[p.krhs][o] = rhs_u;
   }
   // ---- v-point (i,j)
   if (dov) {
-    const double hS = h[o - P];
     const double cff1 = 0.5 * p.g, cff2 = 1.0 / 3.0;
-    double rhs_v = cff1 * f.om_v[o] *
+    double rhs_v = cff1 * omv *
                    ((hS + h0) * (sG[zS] - sG[z0]) +
-                    (hS - h0) * (sGSA[zS] + sGSA[z0] + cff2 * (rhoA[o - P] - rA0) * (sZw[zS] - sZw[z0])) +
+                    (hS - h0) * (sGSA[zS] + sGSA[z0] + cff2 * (rAS - rA0) * (sZw[zS] - sZw[z0])) +
                     (sG2[zS] - sG2[z0]));
     {
       const double a1 = aVFx[pE] - aVFx[p0];
@@ -317,33 +333,31 @@ __global__ void __launch_bounds__(TX * TY, 3) k_step2d(Par p, Flds f) {
     rhs_v = rhs_v - 0.5 * (cVFe[z0] + cVFe[zS]);
     if (p.curvgrid) rhs_v = rhs_v - 0.5 * (kVFe[z0] + kVFe[zS]);
     {
-      const double a1 = 0.5 * (pn[o - P] + pn[o]) * (vVFx[pE] - vVFx[p0]);
-      const double a2 = 0.5 * (pm[o - P] + pm[o]) * (vVFe[z0] - vVFe[zS]);
+      const double a1 = 0.5 * (pnS + pn0) * (vVFx[pE] - vVFx[p0]);
+      const double a2 = 0.5 * (pmS + pm0) * (vVFe[z0] - vVFe[zS]);
       const double fc = a1 - a2;
       rhs_v = rhs_v + fc;
     }
     if (FIRST && PRED) {
-      double* __restrict__ rv_s = f.rv[p.nstp];
-      const double rf = f.rvfrc[o] - rhs_v;
+      const double rf = rvfrc_o - rhs_v;
       if (p.istart == 0) rhs_v = rhs_v + rf;
-      else if (p.istart == 1) rhs_v = rhs_v + 1.5 * rf - 0.5 * f.rv[p.nnew][o];
-      else rhs_v = rhs_v + (23.0 / 12.0) * rf - (16.0 / 12.0) * f.rv[p.nnew][o] + (5.0 / 12.0) * rv_s[o];
+      else if (p.istart == 1) rhs_v = rhs_v + 1.5 * rf - 0.5 * rv_n;
+      else rhs_v = rhs_v + (23.0 / 12.0) * rf - (16.0 / 12.0) * rv_n + (5.0 / 12.0) * rv_so;
       f.rvfrc[o] = rf;
-      rv_s[o] = rf;
+      f.rv[p.nstp][o] = rf;
     } else {
-      rhs_v = rhs_v + f.rvfrc[o];
+      rhs_v = rhs_v + rvfrc_o;
     }
-    const double Dstp = (zs[o] + h0) + (zs[o - P] + hS);
-    const double cff = (pm[o] + pm[o - P]) * (pn[o] + pn[o - P]);
+    const double Dstp = (zs0 + h0) + (zsS + hS);
+    const double cff = (pm0 + pmS) * (pn0 + pnS);
     const double fc = 1.0 / (sDnew[z0] + sDnew[zS]);
-    const double vs = f.vbar[p.kstp][o];
     double x;
     if (FIRST || PRED) {
       const double c1 = FIRST ? 0.5 * p.dtfast : p.dtfast;
       x = (vs * Dstp + cff * c1 * rhs_v) * fc;
     } else {
       const double c1 = 0.5 * p.dtfast * 5.0 / 12.0, c2 = 0.5 * p.dtfast * 8.0 / 12.0, c3 = 0.5 * p.dtfast * 1.0 / 12.0;
-      x = (vs * Dstp + cff * (c1 * rhs_v + c2 * f.rvbar[p.kstp][o] - c3 * f.rvbar[p.ptsk][o])) * fc;
+      x = (vs * Dstp + cff * (c1 * rhs_v + c2 * rvb_s - c3 * rvb_p)) * fc;
     }
     st_v_closed(f.vbar[p.knew], j * P, i, j, x, p);
     if (PRED) f.rvbar[p.krhs][o] = rhs_v;
@@ -351,12 +365,11 @@ __global__ void __launch_bounds__(TX * TY, 3) k_step2d(Par p, Flds f) {
 }
 
 void launch_step2d(const Par& p, const Flds& f, cudaStream_t s) {
-  dim3 b(TX, TY);
   dim3 g((p.Iend - p.Istr + 1 + TX - 1) / TX, (p.Mm + 2 + TY - 1) / TY);
   const size_t smem = (size_t)SMEM_DOUBLES * sizeof(double);
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_step2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }
-  k_step2d<<<g, b, smem, s>>>(p, f);
+  k_step2d<<<g, NTH, smem, s>>>(p, f);
 }
 
 }  // namespace rb

@@ -63,16 +63,28 @@ __global__ void __launch_bounds__(TN) k_step3d_uv_n(Par p, Flds f) {
   if (p.istart == 0) cffAB = 0.25 * p.dt;
   else if (p.istart == 1) cffAB = 0.25 * p.dt * 3.0 / 2.0;
   else cffAB = 0.25 * p.dt * 23.0 / 12.0;
-  sAK[0] = 0.5 * (Akv[o2 - s] + Akv[o2]);
-  const double DC0 = cffAB * (f.pm[o2] + f.pm[o2 - s]) * (f.pn[o2] + f.pn[o2 - s]);
+  // Stage the whole column of every 3-D operand with cp.async (global -> shared, no register cost): ~210 independent 8-byte
+  // copies per thread are in flight at once, which is what saturates HBM for this otherwise latency-bound solver.
+  double* sX = sm + 3 * (NN + 1) * TN + tid; double* sR = sm + 4 * (NN + 1) * TN + tid;
+  double* sKb = sm + 5 * (NN + 1) * TN + tid; double* sHUV = sm + 6 * (NN + 1) * TN + tid;
+  cp_async8(sAK, Akv + o2); cp_async8(sKb, Akv + o2 - s);
 #pragma unroll
   for (int k = 1; k <= NN; ++k) {
     const int o = o2 + k * PL;
-    sAK[k * TN] = 0.5 * (Akv[o - s] + Akv[o]);
-    const double hk = 0.5 * (Hz[o - s] + Hz[o]);
+    cp_async8(sAK + k * TN, Akv + o); cp_async8(sKb + k * TN, Akv + o - s);
+    cp_async8(sHzk + k * TN, Hz + o); cp_async8(sOHz + k * TN, Hz + o - s);
+    cp_async8(sX + k * TN, X + o); cp_async8(sR + k * TN, R + o); cp_async8(sHUV + k * TN, HUV + o);
+  }
+  cp_async_wait_all();
+  sAK[0] = 0.5 * (sKb[0] + sAK[0]);
+  const double DC0 = cffAB * (f.pm[o2] + f.pm[o2 - s]) * (f.pn[o2] + f.pn[o2 - s]);
+#pragma unroll
+  for (int k = 1; k <= NN; ++k) {
+    sAK[k * TN] = 0.5 * (sKb[k * TN] + sAK[k * TN]);
+    const double hk = 0.5 * (sOHz[k * TN] + sHzk[k * TN]);
     const double ok = 1.0 / hk;
     sHzk[k * TN] = hk; sOHz[k * TN] = ok;
-    double xv = X[o] + DC0 * R[o];
+    double xv = sX[k * TN] + DC0 * sR[k * TN];
     xv = xv * ok;
     x[k] = xv;
   }
@@ -113,7 +125,7 @@ __global__ void __launch_bounds__(TN) k_step3d_uv_n(Par p, Flds f) {
       const double xs = (scale == 0.0) ? 0.0 : scale * x[k];
       const double xk = wall ? (xs - cf0) : xs;
       st_w(X, o - i, i, xk, p);
-      const double hv = 0.5 * (HUV[o] + xk * CF[k]);
+      const double hv = 0.5 * ((own ? sHUV[k * TN] : HUV[o]) + xk * CF[k]);
       DC[k] = hv;
       fc0 = fc0 + hv;
     }
@@ -187,7 +199,7 @@ static size_t smem_n(int NN) { return (size_t)3 * (NN + 1) * TN * sizeof(double)
 bool launch_step3d_uv_n(const Par& p, const Flds& f, cudaStream_t s) {
   if (p.N != 30) return false;
   static bool once = false;
-  const size_t sm = smem_n(30);
+  const size_t sm = (size_t)7 * 31 * TN * sizeof(double);      // Hzk, oHz, AK, X, R, Akv(i-1), Huon/Hvom columns
   if (!once) {
     cudaFuncSetAttribute(k_step3d_uv_n<0, 30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     cudaFuncSetAttribute(k_step3d_uv_n<1, 30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
