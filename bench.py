@@ -141,6 +141,8 @@ def main():
     if world > 1:
         from roms_trunk_mgh_b200 import multigpu
         multigpu.attach(t, dist, rank, world)
+        for ph in ("set_depth", "set_massflux", "omega", "rho_eos"):      # start-up phases again, now with live ghosts
+            t.run_phase(ph)
     t.main3d(a.spinup)
     t.main3d(W)
 

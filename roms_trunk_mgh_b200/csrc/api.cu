@@ -8,11 +8,11 @@
 #include <vector>
 #include <map>
 #include <algorithm>
-#include "../../include/roms_b200.h"
-#include "dev.cuh"
+#include "state.h"
 #include "kernels.h"
 
 using namespace rb;
+using namespace rbi;
 
 namespace {
 
@@ -28,15 +28,6 @@ enum { NoError = 0, BlowUp = 1, InputError = 2, ConfigError = 5, FatalError = 8 
   } while (0)
 
 // ---- tile index sets: ROMS/Utility/get_bounds.F (tile_bounds_2d :933-1007, var_bounds :1009-1853, get_bounds :60-258)
-struct Bounds {
-  int tile, Itile, Jtile, LBi, UBi, LBj, UBj, IminS, ImaxS, JminS, JmaxS;
-  int Istr, IstrB, IstrP, IstrR, IstrT, IstrM, IstrU, Iend, IendB, IendP, IendR, IendT;
-  int Jstr, JstrB, JstrP, JstrR, JstrT, JstrM, JstrV, Jend, JendB, JendP, JendR, JendT;
-  int Istrm3, Istrm2, Istrm1, IstrUm2, IstrUm1, Iendp1, Iendp2, Iendp2i, Iendp3;
-  int Jstrm3, Jstrm2, Jstrm1, JstrVm2, JstrVm1, Jendp1, Jendp2, Jendp2i, Jendp3;
-  int west, east, south, north;
-};
-
 void tile_range(int n, int ntile, int t, int& s, int& e) {
   const int chunk = (n + ntile - 1) / ntile;
   const int margin = (ntile * chunk - n) / 2;
@@ -89,33 +80,7 @@ void make_bounds(int Lm, int Mm, int NtileI, int NtileJ, int tile, bool distribu
   }
 }
 
-struct FieldInfo { double** slot; int LBk, nk; double* base; };
-
 }  // namespace
-
-struct roms_b200_state {
-  roms_b200_config cfg;
-  Bounds b;
-  Par par;
-  Flds fl;
-  int ni, nj, ioff;
-  std::map<std::string, FieldInfo> reg;
-  std::vector<void*> allocs;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  // stepping state (mod_stepping.F)
-  int iic = 1, ntstart = 1, ntfirst = 1, nstp = 1, nnew = 1, nrhs = 1, iif = 1, indx1 = 1, kstp = 1, krhs = 1, knew = 1, predictor = 0, exit_flag = 0;
-  double time = 0.0, tdays = 0.0;
-  int nfast = 0;
-  std::vector<double> w1, w2;
-  double dtfast = 0.0;
-  // diag
-  double* d_diag_partial = nullptr; double* d_diag_out = nullptr; double* h_diag_out = nullptr;
-  double* h_pinned = nullptr; size_t pinned_n = 0;
-  // profiling
-  int profile = 0; double phase_ms[32]; long long launches = 0;
-  bool all_diff2_zero = true;
-};
 
 namespace {
 
@@ -126,7 +91,7 @@ int alloc_field(roms_b200_state* h, const std::string& name, double** slot, int 
   CK(cudaMemsetAsync(base, 0, n * sizeof(double), h->stream));
   h->allocs.push_back(base);
   // element (i,j,k) lives at base[(i-LBi+ioff) + (j-LBj)*P + (k-LBk)*PL]
-  *slot = base + h->ioff - h->b.LBi - (ptrdiff_t)h->b.LBj * h->par.P - (ptrdiff_t)LBk * h->par.PL;
+  *slot = base + h->ioff - h->LBi_dev - (ptrdiff_t)h->b.LBj * h->par.P - (ptrdiff_t)LBk * h->par.PL;
   h->reg[name] = FieldInfo{slot, LBk, nk, base};
   return NoError;
 }
@@ -155,6 +120,40 @@ struct PhaseTimer {
     }
   }
 };
+
+// Fields whose xi-ghost columns must be refreshed after a phase (the mp_exchange call sites of SURVEY.md section 2.4).
+std::vector<std::string> halo_fields(roms_b200_state* h, int phase) {
+  std::vector<std::string> v;
+  auto T = [&](int tl) { for (int it = 0; it < h->cfg.NT; ++it) v.push_back("t" + std::to_string(tl) + "_" + std::to_string(it)); };
+  const std::string nn = std::to_string(h->nnew), kn = std::to_string(h->knew), kr = std::to_string(h->krhs);
+  switch (phase) {
+    case ROMS_B200_SET_MASSFLUX: v = {"Huon", "Hvom"}; break;                       // set_massflux.F:177
+    case ROMS_B200_RHO_EOS: v = {"rho", "pden", "rhoA", "rhoS"}; break;             // rho_eos.F:530-553
+    case ROMS_B200_SET_VBC: v = {"bustr", "bvstr"}; break;                          // set_vbc.F:664
+    case ROMS_B200_ANA_VMIX:
+      if (h->cfg.ana_vmix) { v = {"Akv"}; for (int it = 0; it < h->cfg.NT; ++it) v.push_back("Akt_" + std::to_string(it)); }
+      break;
+    case ROMS_B200_OMEGA: case ROMS_B200_OMEGA2: v = {"W"}; break;                  // omega.F:220
+    case ROMS_B200_WVELOCITY: v = {"wvel"}; break;                                  // wvelocity.F:258
+    case ROMS_B200_SET_ZETA: v = {"zeta1", "zeta2"}; break;                         // set_zeta.F:118
+    case ROMS_B200_PRE_STEP3D: T(3); break;                                         // pre_step3d.F:1145
+    case ROMS_B200_STEP2D:                                                          // step2d_LF_AM3.h:586-2519
+      if (h->iif > h->nfast) v = {"Zt_avg1", "DU_avg1", "DV_avg1"};                 // :714
+      else if (h->predictor) v = {"zeta" + kn, "rzeta" + kr, "ubar" + kn, "vbar" + kn};
+      else v = {"zeta" + kn, "ubar" + kn, "vbar" + kn};
+      break;
+    case ROMS_B200_SET_DEPTH: v = {"z_w", "z_r", "Hz"}; break;                      // set_depth.F:269-279
+    case ROMS_B200_STEP3D_UV: v = {"u" + nn, "v" + nn, "Huon", "Hvom", "ubar1", "ubar2", "vbar1", "vbar2"}; break;   // step3d_uv.F:1464-1471
+    case ROMS_B200_STEP3D_T: T(h->nnew); break;                                     // step3d_t.F:1626
+    default: break;
+  }
+  return v;
+}
+
+int phase_halo(roms_b200_state* h, int phase) {
+  if (!h->halo) return NoError;
+  return halo_exchange(h, halo_fields(h, phase));
+}
 
 int run_phase_async(roms_b200_state* h, int phase) {
   fill_par(h);
@@ -192,17 +191,19 @@ int run_phase_async(roms_b200_state* h, int phase) {
           h->kstp = (h->iif == 1) ? h->indx1 : 3 - h->indx1;
           h->knew = 3; h->krhs = h->indx1;
         }
-        if (my_iif <= h->nfast + 1) { fill_par(h); launch_step2d(h->par, f, s); h->launches += 1; }
+        if (my_iif <= h->nfast + 1) { fill_par(h); launch_step2d(h->par, f, s); h->launches += 1; if (phase_halo(h, ROMS_B200_STEP2D)) return FatalError; }
         if (h->predictor) {
           h->predictor = 0; h->knew = next_indx1; h->kstp = 3 - h->knew; h->krhs = 3;
           if (h->iif < h->nfast + 1) h->indx1 = next_indx1;
         }
-        if (h->iif < h->nfast + 1) { fill_par(h); launch_step2d(h->par, f, s); h->launches += 1; }
+        if (h->iif < h->nfast + 1) { fill_par(h); launch_step2d(h->par, f, s); h->launches += 1; if (phase_halo(h, ROMS_B200_STEP2D)) return FatalError; }
       }
       break;
     }
     default: return ConfigError;
   }
+  if (phase != ROMS_B200_STEP2D_LOOP && phase != ROMS_B200_DIAG) { if (phase_halo(h, phase)) return FatalError; }
+  if (phase == ROMS_B200_DIAG && h->halo) { if (halo_reduce_diag(h)) return FatalError; }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { std::fprintf(stderr, "roms_b200: launch error in phase %d: %s\n", phase, cudaGetErrorString(e)); return FatalError; }
   return NoError;
@@ -304,14 +305,16 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   make_bounds(cfg->Lm, cfg->Mm, cfg->NtileI, cfg->NtileJ, cfg->tile, cfg->NtileI > 1, h->b);
   const Bounds& b = h->b;
   h->ni = b.UBi - b.LBi + 1; h->nj = b.UBj - b.LBj + 1;
+  h->LBi_dev = b.Istr - 3;                       // == b.LBi on the western tile; one extra ghost column elsewhere
+  h->ni_dev = b.UBi - h->LBi_dev + 1;
   // origin shift: put i = Istr on a 128-byte boundary
-  h->ioff = (16 - ((b.Istr - b.LBi) % 16)) % 16;
+  h->ioff = (16 - ((b.Istr - h->LBi_dev) % 16)) % 16;
   Par& p = h->par;
   std::memset(&p, 0, sizeof(p));
   p.Lm = cfg->Lm; p.Mm = cfg->Mm; p.N = cfg->N; p.NT = cfg->NT;
-  p.P = ((h->ioff + h->ni + 15) / 16) * 16; p.PL = p.P * h->nj;
+  p.P = ((h->ioff + h->ni_dev + 15) / 16) * 16; p.PL = p.P * h->nj;
   if ((long long)p.PL * (cfg->N + 1) >= (1LL << 31)) { delete h; return ConfigError; }
-  p.LBi = b.LBi; p.UBi = b.UBi; p.LBj = b.LBj; p.UBj = b.UBj;
+  p.LBi = h->LBi_dev; p.UBi = b.UBi; p.LBj = b.LBj; p.UBj = b.UBj;
   p.Istr = b.Istr; p.Iend = b.Iend; p.Jstr = b.Jstr; p.Jend = b.Jend; p.IstrU = b.IstrU; p.JstrV = b.JstrV; p.JstrR = b.JstrR; p.JendR = b.JendR;
   p.Jstrm1 = b.Jstrm1; p.Jendp1 = b.Jendp1; p.Jendp2 = b.Jendp2; p.JstrVm1 = b.JstrVm1; p.JstrVm2 = b.JstrVm2;
   p.ew_wrap = (cfg->NtileI == 1) ? 1 : 0;
@@ -382,6 +385,7 @@ int roms_b200_destroy(roms_b200_handle h) {
   if (!h) return NoError;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  halo_destroy(h);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_diag_out) cudaFreeHost(h->h_diag_out);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -406,10 +410,11 @@ static int xfer(roms_b200_handle h, const char* name, double* host, size_t n, bo
   const size_t want = (size_t)h->ni * h->nj * fi.nk;
   if (n != want) { std::fprintf(stderr, "roms_b200: field '%s' expects %zu doubles, got %zu\n", name, want, n); return InputError; }
   CK(cudaSetDevice(h->cfg.device));
-  double* dev = fi.base + h->ioff;
+  double* dev = fi.base + h->ioff + (h->b.LBi - h->LBi_dev);
   const size_t dp = (size_t)h->par.P * sizeof(double), sp = (size_t)h->ni * sizeof(double);
   if (up) CK(cudaMemcpy2DAsync(dev, dp, host, sp, sp, (size_t)h->nj * fi.nk, cudaMemcpyHostToDevice, h->stream));
   else CK(cudaMemcpy2DAsync(host, sp, dev, dp, sp, (size_t)h->nj * fi.nk, cudaMemcpyDeviceToHost, h->stream));
+  if (up && h->halo) { if (halo_exchange(h, {std::string(name)})) return FatalError; }
   CK(cudaStreamSynchronize(h->stream));
   if (up && std::strncmp(name, "diff2_", 6) == 0) {
     bool z = true;
@@ -503,8 +508,13 @@ int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double*
     if (!src[q]) continue;
     double* stage = h->h_pinned + q * want;
     std::memcpy(stage, src[q], want * sizeof(double));              // staged through pinned memory
-    double* dev = h->reg[nm[q]].base + h->ioff;
+    double* dev = h->reg[nm[q]].base + h->ioff + (h->b.LBi - h->LBi_dev);
     CK(cudaMemcpy2DAsync(dev, dp, stage, sp, sp, (size_t)h->nj, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (h->halo) {
+    std::vector<std::string> up;
+    for (int q = 0; q < 3; ++q) if (src[q]) up.push_back(nm[q]);
+    if (halo_exchange(h, up)) return FatalError;
   }
   int rc = one_step(h, true);
   if (rc) return rc;

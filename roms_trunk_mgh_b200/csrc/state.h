@@ -1,0 +1,61 @@
+// Internal (not part of the C-ABI): the device-resident state behind a roms_b200_handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/roms_b200.h"
+#include "dev.cuh"
+
+namespace rbi {
+
+// tile index sets: ROMS/Utility/get_bounds.F (tile_bounds_2d :933-1007, var_bounds :1009-1853, get_bounds :60-258)
+struct Bounds {
+  int tile, Itile, Jtile, LBi, UBi, LBj, UBj, IminS, ImaxS, JminS, JmaxS;
+  int Istr, IstrB, IstrP, IstrR, IstrT, IstrM, IstrU, Iend, IendB, IendP, IendR, IendT;
+  int Jstr, JstrB, JstrP, JstrR, JstrT, JstrM, JstrV, Jend, JendB, JendP, JendR, JendT;
+  int Istrm3, Istrm2, Istrm1, IstrUm2, IstrUm1, Iendp1, Iendp2, Iendp2i, Iendp3;
+  int Jstrm3, Jstrm2, Jstrm1, JstrVm2, JstrVm1, Jendp1, Jendp2, Jendp2i, Jendp3;
+  int west, east, south, north;
+};
+
+struct FieldInfo { double** slot; int LBk, nk; double* base; };
+
+struct Halo;   // NCCL ring context (api_nccl.cu)
+
+}  // namespace rbi
+
+struct roms_b200_state {
+  roms_b200_config cfg;
+  rbi::Bounds b;          // the reference's bounds of this tile (host-facing array extents LBi:UBi, LBj:UBj)
+  rb::Par par;
+  rb::Flds fl;
+  int ni, nj, ioff;       // host array extents; device origin shift
+  int LBi_dev, ni_dev;    // device arrays carry 3 west ghost columns on every tile (the fused step2d kernel needs Drhs(i-3))
+  std::map<std::string, rbi::FieldInfo> reg;
+  std::vector<void*> allocs;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // stepping state (mod_stepping.F)
+  int iic = 1, ntstart = 1, ntfirst = 1, nstp = 1, nnew = 1, nrhs = 1, iif = 1, indx1 = 1, kstp = 1, krhs = 1, knew = 1, predictor = 0, exit_flag = 0;
+  double time = 0.0, tdays = 0.0;
+  int nfast = 0;
+  std::vector<double> w1, w2;
+  double dtfast = 0.0;
+  // diag
+  double* d_diag_partial = nullptr; double* d_diag_out = nullptr; double* h_diag_out = nullptr;
+  double* h_pinned = nullptr; size_t pinned_n = 0;
+  // profiling
+  int profile = 0; double phase_ms[32]; long long launches = 0;
+  bool all_diff2_zero = true;
+  // multi-GPU
+  rbi::Halo* halo = nullptr;
+};
+
+namespace rbi {
+// Halo exchange of the named fields along the xi ring (mp_exchange2d/3d/4d semantics); no-op without an attached comm.
+int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names);
+// cross-tile reduction of the 16-double diag buffer: [0..2] sum, [3..12] max
+int halo_reduce_diag(roms_b200_state* h);
+void halo_destroy(roms_b200_state* h);
+}  // namespace rbi

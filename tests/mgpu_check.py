@@ -1,0 +1,66 @@
+"""Multi-GPU tiling-invariance check (run under torchrun on N GPUs of one box):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+
+Every rank owns one xi-tile of a BENCHMARK-shaped grid (NtileI = N, NtileJ = 1) and steps it with NCCL halo exchanges; rank 0
+also steps the whole domain as a single tile.  The reference's acceptance criterion (ROMS/Bin/verify.sh:985-1045) is that
+results do not depend on the tiling: all prognostic fields must agree BITWISE."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from roms_trunk_mgh_b200 import _lib, multigpu, synth  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    Lm, Mm, N = (int(x) for x in (sys.argv[1:4] if len(sys.argv) >= 4 else (256, 64, 30)))
+    nsteps = int(sys.argv[4]) if len(sys.argv) >= 5 else 6
+    t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, NtileI=world, tile=rank, device=local)
+    multigpu.attach(t, dist, rank, world)
+    # redo the start-up phases now that ghosts can be exchanged (make_tile ran them before the ring existed)
+    for ph in ("set_depth", "set_massflux", "omega", "rho_eos"):
+        t.run_phase(ph)
+    t.main3d(nsteps)
+    d = t.diag()
+    names = ["zeta1", "zeta2", "ubar1", "vbar1", "u1", "u2", "v1", "v2", "t1_0", "t2_0", "t1_1", "t2_1", "Huon", "Hvom", "W", "rho"]
+    allb = [_lib.bounds(Lm, Mm, world, 1, r, distribute=True) for r in range(world)]
+    ok = True
+    ref = None
+    if rank == 0:
+        ref = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, device=local)
+        ref.main3d(nsteps)
+    for n in names:
+        a = torch.from_numpy(t.get(n)).cuda()
+        # gather variable-width tiles: pad to the widest
+        w = max(b["UBi"] - b["LBi"] + 1 for b in allb)
+        pad = torch.zeros(a.shape[:-1] + (w,), dtype=a.dtype, device="cuda"); pad[..., :a.shape[-1]] = a
+        bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, bufs, dst=0)
+        if rank == 0:
+            parts = [bufs[r][..., :allb[r]["UBi"] - allb[r]["LBi"] + 1].cpu().numpy() for r in range(world)]
+            G = multigpu.assemble_global(parts, allb, Lm)
+            R = ref.get(n)
+            same = np.array_equal(G, R)
+            if not same:
+                ok = False
+                dd = np.abs(G - R)
+                print(f"  {n}: MISMATCH max {dd.max():.3e} of {np.abs(R).max():.3e} at {np.unravel_index(dd.argmax(), dd.shape)}", flush=True)
+    if rank == 0:
+        dr = ref.diag()
+        print("diag tiled :", {k: f"{v:.12e}" for k, v in d.items() if k in ("avgke", "avgpe", "volume", "max_speed")})
+        print("diag single:", {k: f"{v:.12e}" for k, v in dr.items() if k in ("avgke", "avgpe", "volume", "max_speed")})
+        print(f"MGPU_CHECK world={world} grid={Lm}x{Mm}x{N} steps={nsteps}:", "BITWISE-IDENTICAL" if ok else "FAILED", flush=True)
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(int(flag.item()))
+
+
+if __name__ == "__main__":
+    main()
