@@ -107,6 +107,16 @@ def main():
     ap.add_argument("--spinup", type=int, default=20, help="untimed steps before warm-up so that all upstream branches are live")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    # keep stdout clean for the single JSON line: libraries (NCCL's version banner, ...) that print to fd 1 go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
+
+    def emit(line):
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
+
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     Lm, Mm, N = GRIDS[a.grid]
     ncores = os.cpu_count() or 1
@@ -124,7 +134,7 @@ def main():
                 "cpu_baseline": {"value": val, "unit": "grid-point-steps/s", "cores": nth, "kind": "port",
                                  "sample": f"{steps} steps after {warm} warm-up on the full {a.grid.upper()} grid, {tiles[0]}x{tiles[1]} tiles on {nth} threads"},
                 "e2e": {"value": val, "unit": "grid-point-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import numpy as np
@@ -202,8 +212,15 @@ def main():
             dur = prof[dom] * 1e-3
             kname = dom
         ach = bytes_per_launch / dur / 1e9
+        traffic = None
+        try:   # DRAM bytes per launch from the committed ncu --set full capture (profiles/), single-GPU full-size tile only
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if world == 1 and a.grid == "benchmark3" and kname in tj:
+                traffic = tj[kname]["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
         roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "launch_ms": dur * 1e3, "share_of_step": prof[dom] / max(sum(prof.values()), 1e-30)}
+                "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": dur * 1e3, "share_of_step": prof[dom] / max(sum(prof.values()), 1e-30)}
     step_gbs = balg * value / 1e9
     line = {"metric": METRIC, "value": value, "unit": "grid-point-steps/s", "n_gpus": world, "steps": a.steps, "warmup": W,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -224,7 +241,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "grid-point-steps/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
