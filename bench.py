@@ -42,12 +42,39 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  NVML in-process
+    (a sample every 5 ms, so that even a 100 ms timed region is covered); nvidia-smi -lms as the fall-back."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, dev=0):
-        self.dev, self.rows, self.p = dev, [], None
+        self.dev, self.sm, self.mx, self.reasons, self.p, self.run, self.th = dev, [], [], set(), None, False, None
+
+    def _nvml_loop(self, nv, h):
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        self.run = True
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.dev]) if vis and vis.split(",")[self.dev].isdigit() else self.dev
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.th = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.th = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -59,19 +86,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.p:
-            self.p.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
+            r = [c.strip() for c in line.split(",")]
+            if r and r[0].replace(".", "").isdigit():
+                self.sm.append(float(r[0]))
+            if len(r) > 1 and r[1].replace(".", "").isdigit():
+                self.mx.append(float(r[1]))
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(name)
+
+    def stop(self):
+        self.run = False
+        if self.th:
+            self.th.join(timeout=1.0)
+        if self.p:
+            self.p.terminate()
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def cpu_run(grid, steps, warmup, nthreads, kind="fast"):

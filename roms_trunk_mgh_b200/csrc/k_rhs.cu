@@ -32,22 +32,29 @@ __global__ void __launch_bounds__(128) k_rhs3d(Par p, Flds f) {
     dndx0 = f.dndx[o2 + i]; dndxW = f.dndx[o2 + i - 1]; dndxS = f.dndx[o2 - P + i];
     dmde0 = f.dmde[o2 + i]; dmdeW = f.dmde[o2 + i - 1]; dmdeS = f.dmde[o2 - P + i];
   }
-  // clamped rows for the closed-wall copies of the second differences (rhs3d.F:742-755, :886-901)
-  const int jm1c = (j - 1 < 1) ? 1 : j - 1;            // uee row for UFe(i,j):   uee(i,j-1), row 0 -> 1
-  const int jp1c = (j + 1 > Mm) ? Mm : j + 1;          // uee row for UFe(i,j+1): uee(i,j+1), row Mm+1 -> Mm
+  // Row offsets clamped at the closed walls: they serve the wall copies of the second differences (rhs3d.F:742-755,
+  // :886-901) and keep every load in bounds so that all operands of a level can be fetched unconditionally.
+  const int S2 = (j >= 2) ? -2 * P : -P, N2 = (j + 2 <= Mm + 1) ? 2 * P : P;
   double FCu_m = 0.0, FCv_m = 0.0, rufrc = 0.0, rvfrc = 0.0;
   for (int k = 1; k <= N; ++k) {
     const int o = o2 + k * p.PL + i;                     // includes i
-    if (k + PFD <= N) {                                  // start the DRAM fetch of level k+PFD
-      const int q = o + PFD * p.PL;
-      pf_l2(u + q); pf_l2(v + q); pf_l2(Hz + q); pf_l2(Huon + q); pf_l2(Hvom + q); pf_l2(W + q); pf_l2(ru + q); pf_l2(rv + q);
-    }
+    const int oU = (k < N) ? o + p.PL : o, oUU = (k + 2 <= N) ? o + 2 * p.PL : oU, oD = (k > 1) ? o - p.PL : o;
+    // ---- all global operands of this level, issued back to back (one memory wait per level)
     const double hz0 = Hz[o], hzW = Hz[o - 1], hzS = Hz[o - P];
-    const double u0 = u[o], uE = u[o + 1], uW = u[o - 1], uN = u[o + P], uS = u[o - P];
-    const double v0 = v[o], vN = v[o + P], vW = v[o - 1], vE = v[o + 1], vS = v[o - P];
-    const double uSE = u[o - P + 1], vNW = v[o + P - 1];
+    const double uW2 = u[o - 2], uW = u[o - 1], u0 = u[o], uE = u[o + 1], uE2 = u[o + 2];
+    const double uS2 = u[o + S2], uS = u[o - P], uN = u[o + P], uN2 = u[o + N2], uSE = u[o - P + 1];
+    const double vW2 = v[o - 2], vW = v[o - 1], v0 = v[o], vE = v[o + 1], vE2 = v[o + 2];
+    const double vS2 = v[o + S2], vS = v[o - P], vN = v[o + P], vN2 = v[o + N2], vNW = v[o + P - 1];
+    const double HuW2 = Huon[o - 2], HuW = Huon[o - 1], Hu0 = Huon[o], HuE = Huon[o + 1], HuE2 = Huon[o + 2];
+    const double HuS2 = Huon[o + S2], HuS = Huon[o - P], HuN = Huon[o + P];
+    const double HuES2 = Huon[o + 1 + S2], HuSE = Huon[o + 1 - P], HuNE = Huon[o + 1 + P];
+    const double HvW2 = Hvom[o - 2], HvW = Hvom[o - 1], Hv0 = Hvom[o], HvE = Hvom[o + 1];
+    const double HvNW2 = Hvom[o + P - 2], HvNW = Hvom[o + P - 1], HvN = Hvom[o + P], HvNE = Hvom[o + P + 1];
+    const double HvS2 = Hvom[o + S2], HvS = Hvom[o - P], HvN2 = Hvom[o + N2];
+    const double W0 = W[o], WW = W[o - 1], WE = W[o + 1], WW2 = W[o - 2], WS = W[o - P], WN = W[o + P], WS2 = W[o + S2];
+    const double uUp = u[oU], uUp2 = u[oUU], uDn = u[oD], vUp = v[oU], vUp2 = v[oUU], vDn = v[oD];
     double rux = ru[o];
-    double rvx = dov ? rv[o] : 0.0;
+    double rvx = rv[o];
     // ---- Coriolis (rhs3d.F:473-507): UFx at rho(i,j), rho(i-1,j); VFe at rho(i,j), rho(i,j-1)
     {
       const double c0 = 0.5 * hz0 * fomn0;
@@ -79,9 +86,8 @@ __global__ void __launch_bounds__(128) k_rhs3d(Par p, Flds f) {
     }
     // ---- horizontal advection of u (rhs3d.F:658-798, :946-963)
     {
-      const double uxxW = d2x(u, o - 1), uxx0 = d2x(u, o), uxxE = d2x(u, o + 1);
-      const double HxxW = d2x(Huon, o - 1), Hxx0 = d2x(Huon, o), HxxE = d2x(Huon, o + 1);
-      const double HuW = Huon[o - 1], Hu0 = Huon[o], HuE = Huon[o + 1];
+      const double uxxW = uW2 - 2.0 * uW + u0, uxx0 = uW - 2.0 * u0 + uE, uxxE = u0 - 2.0 * uE + uE2;
+      const double HxxW = HuW2 - 2.0 * HuW + Hu0, Hxx0 = HuW - 2.0 * Hu0 + HuE, HxxE = Hu0 - 2.0 * HuE + HuE2;
       // UFx(i,j) at rho(i,j) and UFx(i-1,j)
       double c1 = u0 + uE;
       double c = (c1 > 0.0) ? uxx0 : uxxE;
@@ -89,11 +95,12 @@ __global__ void __launch_bounds__(128) k_rhs3d(Par p, Flds f) {
       c1 = uW + u0;
       c = (c1 > 0.0) ? uxxW : uxx0;
       const double UFxW = 0.25 * (c1 + Gadv * c) * (HuW + Hu0 + Gadv * 0.5 * (HxxW + Hxx0));
-      // UFe(i,j) and UFe(i,j+1) at psi points; uee rows clamped at the walls
-      const int ob = o - j * P;                          // row 0 offset of this (i,k)
-      const double uee_jm1 = d2y(u, ob + jm1c * P, P), uee_j = d2y(u, o, P), uee_jp1 = d2y(u, ob + jp1c * P, P);
-      const double Hv0 = Hvom[o], HvW = Hvom[o - 1], HvN = Hvom[o + P], HvNW = Hvom[o + P - 1];
-      const double Hvxx0 = d2x(Hvom, o), HvxxW = d2x(Hvom, o - 1), HvxxN = d2x(Hvom, o + P), HvxxNW = d2x(Hvom, o + P - 1);
+      // UFe(i,j) and UFe(i,j+1) at psi points; uee(i,0) = uee(i,1), uee(i,Mm+1) = uee(i,Mm)
+      const double uee_j = uS - 2.0 * u0 + uN;
+      const double uee_jm1 = (j > 1) ? (uS2 - 2.0 * uS + u0) : uee_j;
+      const double uee_jp1 = (j < Mm) ? (u0 - 2.0 * uN + uN2) : uee_j;
+      const double Hvxx0 = HvW - 2.0 * Hv0 + HvE, HvxxW = HvW2 - 2.0 * HvW + Hv0;
+      const double HvxxN = HvNW - 2.0 * HvN + HvNE, HvxxNW = HvNW2 - 2.0 * HvNW + HvN;
       c1 = u0 + uS;
       double c2 = Hv0 + HvW;
       c = (c2 > 0.0) ? uee_jm1 : uee_j;
@@ -108,9 +115,9 @@ __global__ void __launch_bounds__(128) k_rhs3d(Par p, Flds f) {
     }
     // ---- horizontal advection of v (rhs3d.F:800-940, :965-982)
     if (dov) {
-      const double vxxW = d2x(v, o - 1), vxx0 = d2x(v, o), vxxE = d2x(v, o + 1);
-      const double Hu0 = Huon[o], HuS = Huon[o - P], HuE = Huon[o + 1], HuSE = Huon[o - P + 1];
-      const double Huee0 = d2y(Huon, o, P), HueeS = d2y(Huon, o - P, P), HueeE = d2y(Huon, o + 1, P), HueeSE = d2y(Huon, o - P + 1, P);
+      const double vxxW = vW2 - 2.0 * vW + v0, vxx0 = vW - 2.0 * v0 + vE, vxxE = v0 - 2.0 * vE + vE2;
+      const double Huee0 = HuS - 2.0 * Hu0 + HuN, HueeS = HuS2 - 2.0 * HuS + Hu0;
+      const double HueeE = HuSE - 2.0 * HuE + HuNE, HueeSE = HuES2 - 2.0 * HuSE + HuE;
       // VFx(i,j), VFx(i+1,j) at psi points
       double c1 = v0 + vW;
       double c2 = Hu0 + HuS;
@@ -120,12 +127,10 @@ __global__ void __launch_bounds__(128) k_rhs3d(Par p, Flds f) {
       c2 = HuE + HuSE;
       c = (c2 > 0.0) ? vxx0 : vxxE;
       const double VFxE = 0.25 * (c1 + Gadv * c) * (c2 + Gadv * 0.5 * (HueeE + HueeSE));
-      // VFe(i,j), VFe(i,j-1) at rho points; vee/Hvee defined for rows 2..Mm, copies vee(1)=vee(2), vee(Mm+1)=vee(Mm)
-      const int ob = o - j * P;
-      const int ja = (j < 2) ? 2 : j, jb = (j + 1 > Mm) ? Mm : j + 1, jc = (j - 1 < 2) ? 2 : j - 1;
-      const double vee_j = d2y(v, ob + ja * P, P), vee_jp = d2y(v, ob + jb * P, P), vee_jm = d2y(v, ob + jc * P, P);
-      const double Hvee_j = d2y(Hvom, ob + ja * P, P), Hvee_jp = d2y(Hvom, ob + jb * P, P), Hvee_jm = d2y(Hvom, ob + jc * P, P);
-      const double Hv0 = Hvom[o], HvN = Hvom[o + P], HvS = Hvom[o - P];
+      // VFe(i,j), VFe(i,j-1) at rho points; vee/Hvee rows 2..Mm with copies (1)=(2), (Mm+1)=(Mm)
+      const double vee_j = vS - 2.0 * v0 + vN, Hvee_j = HvS - 2.0 * Hv0 + HvN;
+      const double vee_jp = (j < Mm) ? (v0 - 2.0 * vN + vN2) : vee_j, Hvee_jp = (j < Mm) ? (Hv0 - 2.0 * HvN + HvN2) : Hvee_j;
+      const double vee_jm = (j > 2) ? (vS2 - 2.0 * vS + v0) : vee_j, Hvee_jm = (j > 2) ? (HvS2 - 2.0 * HvS + Hv0) : Hvee_j;
       c1 = v0 + vN;
       c = (c1 > 0.0) ? vee_j : vee_jp;
       const double VFe0 = 0.25 * (c1 + Gadv * c) * (Hv0 + HvN + Gadv * 0.5 * (Hvee_j + Hvee_jp));
@@ -141,14 +146,13 @@ __global__ void __launch_bounds__(128) k_rhs3d(Par p, Flds f) {
       const double c1 = 9.0 / 16.0, c2 = 1.0 / 16.0;
       double FCu = 0.0, FCv = 0.0;
       if (k < N) {
-        const int ou = o + p.PL;
-        const double ukm = (k > 1) ? u[o - p.PL] : u0;
-        const double ukpp = (k + 2 <= N) ? u[ou + p.PL] : u[ou];
-        FCu = (c1 * (u0 + u[ou]) - c2 * (ukm + ukpp)) * (c1 * (W[o] + W[o - 1]) - c2 * (W[o + 1] + W[o - 2]));
+        const double ukm = (k > 1) ? uDn : u0;
+        const double ukpp = (k + 2 <= N) ? uUp2 : uUp;
+        FCu = (c1 * (u0 + uUp) - c2 * (ukm + ukpp)) * (c1 * (W0 + WW) - c2 * (WE + WW2));
         if (dov) {
-          const double vkm = (k > 1) ? v[o - p.PL] : v0;
-          const double vkpp = (k + 2 <= N) ? v[ou + p.PL] : v[ou];
-          FCv = (c1 * (v0 + v[ou]) - c2 * (vkm + vkpp)) * (c1 * (W[o] + W[o - P]) - c2 * (W[o + P] + W[o - 2 * P]));
+          const double vkm = (k > 1) ? vDn : v0;
+          const double vkpp = (k + 2 <= N) ? vUp2 : vUp;
+          FCv = (c1 * (v0 + vUp) - c2 * (vkm + vkpp)) * (c1 * (W0 + WS) - c2 * (WN + WS2));
         }
       }
       rux = rux - (FCu - FCu_m);
@@ -190,17 +194,22 @@ __global__ void __launch_bounds__(128) k_uv3dmix2(Par p, Flds f) {
   const double* __restrict__ pm = f.pm;
   const double* __restrict__ pn = f.pn;
   const bool dov = (j >= p.JstrV);
-  // rho-point stress at cell c (offset oc): needs pn(c-1..c+1 in i), pm(c-1..c+1 in j)
-  auto rho_cff = [&](int oc2, int oc3) -> double {
-    return Hz[oc3] * 0.5 *
-           (f.pmon_r[oc2] * ((pn[oc2] + pn[oc2 + 1]) * u[oc3 + 1] - (pn[oc2 - 1] + pn[oc2]) * u[oc3]) -
-            f.pnom_r[oc2] * ((pm[oc2] + pm[oc2 + P]) * v[oc3 + P] - (pm[oc2 - P] + pm[oc2]) * v[oc3]));
+  // level-independent factors of the rho-point stress at a cell c and of the psi-point stress at the SW corner of c
+  struct R2 { double pmon, pnom, pnE, pnW, pmN, pmS; };
+  struct P2 { double pmon, pnom, pnv0, pnvW, pmu0, pmuS; };
+  auto r2 = [&](int c) -> R2 {
+    return R2{f.pmon_r[c], f.pnom_r[c], pn[c] + pn[c + 1], pn[c - 1] + pn[c], pm[c] + pm[c + P], pm[c - P] + pm[c]};
   };
-  // psi-point stress at corner c (SW corner of cell c)
-  auto psi_cff = [&](int oc2, int oc3) -> double {
-    return 0.125 * (Hz[oc3 - 1] + Hz[oc3] + Hz[oc3 - P - 1] + Hz[oc3 - P]) *
-           (f.pmon_p[oc2] * ((pn[oc2 - P] + pn[oc2]) * v[oc3] - (pn[oc2 - P - 1] + pn[oc2 - 1]) * v[oc3 - 1]) +
-            f.pnom_p[oc2] * ((pm[oc2 - 1] + pm[oc2]) * u[oc3] - (pm[oc2 - P - 1] + pm[oc2 - P]) * u[oc3 - P]));
+  auto p2 = [&](int c) -> P2 {
+    return P2{f.pmon_p[c], f.pnom_p[c], pn[c - P] + pn[c], pn[c - P - 1] + pn[c - 1], pm[c - 1] + pm[c], pm[c - P - 1] + pm[c - P]};
+  };
+  const R2 R0 = r2(o2), RW = r2(o2 - 1), RS = r2(o2 - P);
+  const P2 Q0 = p2(o2), QN = p2(o2 + P), QE = p2(o2 + 1);
+  auto rho_cff = [](const R2& m, double hz, double uE, double u0, double vN, double v0) -> double {
+    return hz * 0.5 * (m.pmon * (m.pnE * uE - m.pnW * u0) - m.pnom * (m.pmN * vN - m.pmS * v0));
+  };
+  auto psi_cff = [](const P2& m, double hW, double h0, double hSW, double hS, double v0, double vW, double u0, double uS) -> double {
+    return 0.125 * (hW + h0 + hSW + hS) * (m.pmon * (m.pnv0 * v0 - m.pnvW * vW) + m.pnom * (m.pmu0 * u0 - m.pmuS * uS));
   };
   const double onr2_0 = f.on_r[o2] * f.on_r[o2] * f.visc2_r[o2], onr2_W = f.on_r[o2 - 1] * f.on_r[o2 - 1] * f.visc2_r[o2 - 1];
   const double omr2_0 = f.om_r[o2] * f.om_r[o2] * f.visc2_r[o2], omr2_S = f.om_r[o2 - P] * f.om_r[o2 - P] * f.visc2_r[o2 - P];
@@ -211,10 +220,16 @@ __global__ void __launch_bounds__(128) k_uv3dmix2(Par p, Flds f) {
   const double pmVb = pm[o2 - P] + pm[o2], pnVb = pn[o2 - P] + pn[o2];
   double rufrc = f.rufrc[o2], rvfrc = dov ? f.rvfrc[o2] : 0.0;
   for (int k = 1; k <= N; ++k) {
-    const int o3 = o2 + k * p.PL;
-    if (k + PFD <= N) { const int q = o3 + PFD * p.PL; pf_l2(u + q); pf_l2(v + q); pf_l2(Hz + q); pf_l2(un + q); pf_l2(vn + q); }
-    const double cr0 = rho_cff(o2, o3), crW = rho_cff(o2 - 1, o3 - 1);
-    const double cp0 = psi_cff(o2, o3), cpN = psi_cff(o2 + P, o3 + P);
+    const int o = o2 + k * p.PL;
+    // all operands of the level, issued back to back
+    const double h0 = Hz[o], hW = Hz[o - 1], hE = Hz[o + 1], hS = Hz[o - P], hSW = Hz[o - P - 1], hSE = Hz[o - P + 1];
+    const double hN = Hz[o + P], hNW = Hz[o + P - 1];
+    const double uW = u[o - 1], u0 = u[o], uE = u[o + 1], uS = u[o - P], uSE = u[o - P + 1], uN = u[o + P];
+    const double vW = v[o - 1], v0 = v[o], vE = v[o + 1], vS = v[o - P], vN = v[o + P], vNW = v[o + P - 1];
+    const double un0 = un[o];
+    const double vn0 = dov ? vn[o] : 0.0;
+    const double cr0 = rho_cff(R0, h0, uE, u0, vN, v0), crW = rho_cff(RW, hW, u0, uW, vNW, vW);
+    const double cp0 = psi_cff(Q0, hW, h0, hSW, hS, v0, vW, u0, uS), cpN = psi_cff(QN, hNW, hN, hW, h0, vN, vNW, uN, u0);
     {
       const double UFx0 = onr2_0 * cr0, UFxW = onr2_W * crW;
       const double UFe0 = omp2_0 * cp0, UFeN = omp2_N * cpN;
@@ -223,10 +238,10 @@ __global__ void __launch_bounds__(128) k_uv3dmix2(Par p, Flds f) {
       const double cff2 = 0.5 * pmU * (UFeN - UFe0);
       const double cff3 = cff * (cff1 + cff2);
       rufrc = rufrc + cff1 + cff2;
-      un[o3] = un[o3] + cff3;
+      un[o] = un0 + cff3;
     }
     if (dov) {
-      const double crS = rho_cff(o2 - P, o3 - P), cpE = psi_cff(o2 + 1, o3 + 1);
+      const double crS = rho_cff(RS, hS, uSE, uS, v0, vS), cpE = psi_cff(QE, h0, hE, hS, hSE, vE, v0, uE, uSE);
       const double VFx0 = onp2_0 * cp0, VFxE = onp2_E * cpE;
       const double VFe0 = omr2_0 * cr0, VFeS = omr2_S * crS;
       const double cff = p.dt * 0.25 * pmV * pnV;
@@ -234,7 +249,7 @@ __global__ void __launch_bounds__(128) k_uv3dmix2(Par p, Flds f) {
       const double cff2 = 0.5 * pmVb * (VFe0 - VFeS);
       const double cff3 = cff * (cff1 - cff2);
       rvfrc = rvfrc + cff1 - cff2;
-      vn[o3] = vn[o3] + cff3;
+      vn[o] = vn0 + cff3;
     }
   }
   f.rufrc[o2] = rufrc;

@@ -1,32 +1,32 @@
 // step3d_uv_tile and step3d_t_tile: correctors with implicit vertical mixing (parabolic-spline tridiagonal systems,
-// SPLINES_VVISC / SPLINES_VDIFF).  Thread-per-column Thomas solver: the forward sweep keeps CF(k), DC(k) in
-// thread-private arrays, the back substitution runs in the same thread; xi stays the coalesced axis.
+// SPLINES_VVISC / SPLINES_VDIFF).
+//
+// Thread-per-column Thomas solver, xi is the coalesced axis.  The solver is a dependent chain (one FP64 division per
+// level), so what matters on B200 is how many columns an SM keeps in flight: the kernels below hold per column only the
+// two forward-sweep arrays CF(k), DC(k) in shared memory ([k][thread], conflict free, 2*N*8 bytes per column) and stream
+// everything else level by level with software-pipelined loads, which keeps them near 100 registers and 14 warps per
+// SM for N = 30.  Values needed again by the back substitution (the pre-solve right-hand side, Hz, Ak) are re-read
+// while they are still in L2 (the columns in flight are ~20 MB) instead of being kept in registers.  Arithmetic and
+// summation order are exactly those of the reference loops.
 #include "dev.cuh"
 #include "kernels.h"
 #include "k_adv.cuh"
 
 namespace rb {
 
-// Parabolic-spline implicit vertical mixing for one column (step3d_uv.F:344-396, step3d_t.F:1370-1427).
-// x[1..N] in/out, Hzk[1..N], oHz[1..N], AK[0..N].
-__device__ __forceinline__ void spline_implicit(double* x, const double* Hzk, const double* oHz, const double* AK, int N, double dt,
-                                                double* CF, double* DC) {
-  CF[0] = 0.0; DC[0] = 0.0;
-  for (int k = 1; k <= N - 1; ++k) {
-    const double FCk = (1.0 / 6.0) * Hzk[k] - dt * AK[k - 1] * oHz[k];
-    const double CFk = (1.0 / 6.0) * Hzk[k + 1] - dt * AK[k + 1] * oHz[k + 1];
-    const double BCk = (1.0 / 3.0) * (Hzk[k] + Hzk[k + 1]) + dt * AK[k] * (oHz[k] + oHz[k + 1]);
-    const double cff = 1.0 / (BCk - FCk * CF[k - 1]);
-    CF[k] = cff * CFk;
-    DC[k] = cff * (x[k + 1] - x[k] - FCk * DC[k - 1]);
-  }
-  DC[N] = 0.0;
-  for (int k = N - 1; k >= 1; --k) DC[k] = DC[k] - CF[k] * DC[k + 1];
-  for (int k = 1; k <= N; ++k) {
-    DC[k] = DC[k] * AK[k];
-    const double cff = dt * oHz[k] * (DC[k] - DC[k - 1]);
-    x[k] = x[k] + cff;
-  }
+constexpr int TS = 64;       // threads (columns) per block
+constexpr int CH = 5;        // levels per batch of independent loads in the downward / coupling passes
+
+// One forward-elimination step of the spline system for row m = k-1 once level k is known
+// (step3d_uv.F:344-375, step3d_t.F:1370-1405): h/o/AK suffix m = level k-1, k = level k, AKmm = AK(k-2).
+__device__ __forceinline__ void spline_forward(double hm, double om, double hk, double ok, double AKmm, double AKm, double AKk,
+                                               double dx, double dt, double& CFp, double& DCp) {
+  const double FCv = (1.0 / 6.0) * hm - dt * AKmm * om;
+  const double CFv = (1.0 / 6.0) * hk - dt * AKk * ok;
+  const double BCv = (1.0 / 3.0) * (hm + hk) + dt * AKm * (om + ok);
+  const double cff = 1.0 / (BCv - FCv * CFp);
+  CFp = cff * CFv;
+  DCp = cff * (dx - FCv * DCp);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -34,11 +34,16 @@ __device__ __forceinline__ void spline_implicit(double* x, const double* Hzk, co
 // :956-965 closed-wall BCs; :1002-1432 coupling with DU_avg1/DU_avg2, ubar/vbar reset, corrected Huon/Hvom;
 // :1438-1461 periodic images).  DIR = 0: u-points, DIR = 1: v-points.
 template <int DIR>
-__global__ void __launch_bounds__(128) k_step3d_uv(Par p, Flds f) {
-  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = (DIR ? 2 : 1) + blockIdx.y * blockDim.y + threadIdx.y;     // u: Jstr..Jend, v: JstrV..Jend
-  if (i > p.Iend || j > p.Mm) return;
-  const int N = p.N, P = p.P, Mm = p.Mm, o2 = j * P + i;
+__global__ void __launch_bounds__(TS, 7) k_step3d_uv(Par p, Flds f) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  const int N = p.N;
+  double* sA = sm + tid;                 // CF(k) -> x(k) -> hv(k)      slot (k-1)*TS
+  double* sB = sm + N * TS + tid;        // DC(k) -> Hzk(k) -> d(k)
+  const int i = p.Istr + blockIdx.x * TS + tid;
+  const int j = (DIR ? 2 : 1) + blockIdx.y;                                // u: Jstr..Jend, v: JstrV..Jend
+  if (i > p.Iend) return;
+  const int P = p.P, Mm = p.Mm, PL = p.PL, o2 = j * P + i;
   const int s = DIR ? P : 1;                                               // stride to the (i-1) / (j-1) neighbour
   double* __restrict__ X = DIR ? f.v[p.nnew] : f.u[p.nnew];
   const double* __restrict__ R = DIR ? f.rv[p.nrhs] : f.ru[p.nrhs];
@@ -50,46 +55,107 @@ __global__ void __launch_bounds__(128) k_step3d_uv(Par p, Flds f) {
   const double* __restrict__ met = DIR ? f.om_v : f.on_u;                  // on_u (u) / om_v (v)
   double* __restrict__ bar1 = DIR ? f.vbar[1] : f.ubar[1];
   double* __restrict__ bar2 = DIR ? f.vbar[2] : f.ubar[2];
-  double x[MAXN + 1], Hzk[MAXN + 1], oHz[MAXN + 1], AK[MAXN + 1], CF[MAXN + 1], DC[MAXN + 1];
   double cffAB;
   if (p.istart == 0) cffAB = 0.25 * p.dt;
   else if (p.istart == 1) cffAB = 0.25 * p.dt * 3.0 / 2.0;
   else cffAB = 0.25 * p.dt * 23.0 / 12.0;
-  AK[0] = 0.5 * (Akv[o2 - s] + Akv[o2]);
   const double DC0 = cffAB * (f.pm[o2] + f.pm[o2 - s]) * (f.pn[o2] + f.pn[o2 - s]);
-  for (int k = 1; k <= N; ++k) {
-    const int o = o2 + k * p.PL;
-    AK[k] = 0.5 * (Akv[o - s] + Akv[o]);
-    Hzk[k] = 0.5 * (Hz[o - s] + Hz[o]);
-    oHz[k] = 1.0 / Hzk[k];
-    double xv = X[o] + DC0 * R[o];
-    xv = xv * oHz[k];
-    x[k] = xv;
-  }
-  spline_implicit(x, Hzk, oHz, AK, N, p.dt, CF, DC);
-  // replace the vertical mean with the one from the barotropic sub-cycle (:469-605)
+  const double dt = p.dt;
+
+  // ---- pass 1 (upward): right-hand side x(k) and the forward elimination; loads of level k+1 are issued before level k
+  // is computed
+  struct Lvl { double ak0, ak1, h0, h1, x, r; };
+  auto load_level = [&](int k) -> Lvl {
+    const int o = o2 + k * PL;
+    pf_l2(HUV + o);                                                        // first touched by the coupling pass
+    return Lvl{Akv[o - s], Akv[o], Hz[o - s], Hz[o], X[o], R[o]};
+  };
+  double AKm = 0.5 * (Akv[o2 - s] + Akv[o2]), AKmm = 0.0, AKN;
   {
-    double cf0 = Hzk[1], dc0 = x[1] * Hzk[1];
-    for (int k = 2; k <= N; ++k) { cf0 = cf0 + Hzk[k]; dc0 = dc0 + x[k] * Hzk[k]; }
+    Lvl cur = load_level(1);
+    double hm = 0.0, om = 0.0, xm = 0.0, CFp = 0.0, DCp = 0.0;
+    for (int k = 1; k <= N; ++k) {
+      Lvl nxt = cur;
+      if (k < N) nxt = load_level(k + 1);
+      const double AKk = 0.5 * (cur.ak0 + cur.ak1);
+      const double hk = 0.5 * (cur.h0 + cur.h1);
+      const double ok = 1.0 / hk;
+      double xv = cur.x + DC0 * cur.r;
+      xv = xv * ok;
+      if (k >= 2) {
+        spline_forward(hm, om, hk, ok, AKmm, AKm, AKk, xv - xm, dt, CFp, DCp);
+        sA[(k - 2) * TS] = CFp; sB[(k - 2) * TS] = DCp;
+      }
+      AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = xv;
+      cur = nxt;
+    }
+    AKN = AKm;
+  }
+  // ---- pass 2 (downward): back substitution fused with the update x(k) += dt*oHz(k)*(AK(k)*DC(k) - AK(k-1)*DC(k-1));
+  // x(k) and Hzk(k) replace CF(k), DC(k) in shared memory (both already consumed at level k+1)
+  {
+    double dk = 0.0;                       // DC(N) = 0
+    double ak = dk * AKN;
+    for (int kt = N; kt >= 1; kt -= CH) {
+      double lx[CH], lr[CH], lh0[CH], lh1[CH], la0[CH], la1[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int k = (kt - q >= 1) ? kt - q : 1;
+        const int o = o2 + k * PL;
+        lx[q] = X[o]; lr[q] = R[o]; lh0[q] = Hz[o - s]; lh1[q] = Hz[o]; la0[q] = Akv[o - PL - s]; la1[q] = Akv[o - PL];
+      }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int k = kt - q;
+        if (k >= 1) {
+          const double hk = 0.5 * (lh0[q] + lh1[q]);
+          const double ok = 1.0 / hk;
+          double xv = lx[q] + DC0 * lr[q];
+          xv = xv * ok;
+          double dkm1 = 0.0, akm1 = 0.0;
+          if (k > 1) {
+            dkm1 = sB[(k - 2) * TS] - sA[(k - 2) * TS] * dk;
+            akm1 = dkm1 * (0.5 * (la0[q] + la1[q]));
+          }
+          const double cff = dt * ok * (ak - akm1);
+          sA[(k - 1) * TS] = xv + cff;
+          sB[(k - 1) * TS] = hk;
+          dk = dkm1; ak = akm1;
+        }
+      }
+    }
+  }
+  // ---- replace the vertical mean with the one from the barotropic sub-cycle (:469-605)
+  double dcm;
+  {
+    double cf0 = sB[0], dc0 = sA[0] * sB[0];
+    for (int k = 2; k <= N; ++k) { const double hk = sB[(k - 1) * TS]; cf0 = cf0 + hk; dc0 = dc0 + sA[(k - 1) * TS] * hk; }
     const double m = met[o2];
     const double cff1 = 1.0 / (cf0 * m);
-    dc0 = (dc0 * m - Davg1[o2]) * cff1;
-    for (int k = 1; k <= N; ++k) x[k] = x[k] - dc0;
+    dcm = (dc0 * m - Davg1[o2]) * cff1;
   }
   // ---- coupling (:1002-1432) for this row, then for the wall rows owned by the edge threads
   //   u: rows 0 and Mm+1 carry u = gamma2*u(wall-adjacent row) (u3dbc) and get their own coupling pass
   //   v: row 1 (the wall itself, v = 0 from v3dbc) is handled by the j = 2 thread, row Mm+1 by the j = Mm thread
-  auto couple = [&](int jj, const double* xx) {
+  // own row: x(k) - dcm from shared memory; wall rows: scale * (the own-row values just stored to X)
+  auto couple = [&](int jj, double scale, bool own) {
     const int q2 = jj * P + i;
-    double* dck = CF;                                  // CF/DC are free after the implicit solve
-    double* hvk = DC;
     double dc0 = 0.0, cf0 = 0.0, fc0 = 0.0;
-    const double cff = 0.5 * met[q2];
+    const double mq = met[q2];
+    const double cff = 0.5 * mq;
     for (int k = 1; k <= N; ++k) {
-      const int o = q2 + k * p.PL;
-      dck[k] = cff * (Hz[o] + Hz[o - s]);
-      dc0 = dc0 + dck[k];
-      cf0 = cf0 + dck[k] * xx[k];
+      double d, xs;
+      if (own) {
+        d = mq * sB[(k - 1) * TS];                       // (0.5*m)*(a+b) == m*(0.5*(a+b)) bitwise
+        xs = sA[(k - 1) * TS] - dcm;
+      } else {
+        const int o = q2 + k * PL;
+        d = cff * (Hz[o] + Hz[o - s]);
+        xs = (scale == 0.0) ? 0.0 : scale * X[o2 + k * PL];
+      }
+      sA[(k - 1) * TS] = xs; sB[(k - 1) * TS] = d;
+      dc0 = dc0 + d;
+      cf0 = cf0 + d * xs;
     }
     dc0 = 1.0 / dc0;
     cf0 = dc0 * (cf0 - Davg1[q2]);
@@ -98,27 +164,33 @@ __global__ void __launch_bounds__(128) k_step3d_uv(Par p, Flds f) {
     st_w(bar2, q2 - i, i, b, p);
     // boundary rows only: remove the mismatch of the vertical mean (:1132-1188, :1350-1406)
     const bool wall = DIR ? (jj == 1 || jj == Mm + 1) : (jj == 0 || jj == Mm + 1);
-    for (int k = N; k >= 1; --k) {
-      const int o = q2 + k * p.PL;
-      const double xk = wall ? (xx[k] - cf0) : xx[k];
-      st_w(X, o - i, i, xk, p);
-      const double hv = 0.5 * (HUV[o] + xk * dck[k]);
-      hvk[k] = hv;
-      fc0 = fc0 + hv;
+    for (int kt = N; kt >= 1; kt -= CH) {
+      double lh[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) { const int k = (kt - q >= 1) ? kt - q : 1; lh[q] = HUV[q2 + k * PL]; }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int k = kt - q;
+        if (k >= 1) {
+          const double xs = sA[(k - 1) * TS];
+          const double xk = wall ? (xs - cf0) : xs;
+          st_w(X, q2 + k * PL - i, i, xk, p);
+          const double hv = 0.5 * (lh[q] + xk * sB[(k - 1) * TS]);
+          sA[(k - 1) * TS] = hv;
+          fc0 = fc0 + hv;
+        }
+      }
     }
     fc0 = dc0 * (fc0 - Davg2[q2]);
-    for (int k = 1; k <= N; ++k) {
-      const int o = q2 + k * p.PL;
-      st_w(HUV, o - i, i, hvk[k] - dck[k] * fc0, p);
-    }
+    for (int k = 1; k <= N; ++k) st_w(HUV, q2 + k * PL - i, i, sA[(k - 1) * TS] - sB[(k - 1) * TS] * fc0, p);
   };
-  couple(j, x);
+  couple(j, 1.0, true);
   if (DIR == 0) {
-    if (j == 1) { double xb[MAXN + 1]; for (int k = 1; k <= N; ++k) xb[k] = p.gamma2 * x[k]; couple(0, xb); }
-    if (j == Mm) { double xb[MAXN + 1]; for (int k = 1; k <= N; ++k) xb[k] = p.gamma2 * x[k]; couple(Mm + 1, xb); }
+    if (j == 1) couple(0, p.gamma2, false);
+    if (j == Mm) couple(Mm + 1, p.gamma2, false);
   } else {
-    if (j == 2) { double xb[MAXN + 1]; for (int k = 1; k <= N; ++k) xb[k] = 0.0; couple(1, xb); }
-    if (j == Mm) { double xb[MAXN + 1]; for (int k = 1; k <= N; ++k) xb[k] = 0.0; couple(Mm + 1, xb); }
+    if (j == 2) couple(1, 0.0, false);
+    if (j == Mm) couple(Mm + 1, 0.0, false);
   }
 }
 
@@ -126,68 +198,130 @@ __global__ void __launch_bounds__(128) k_step3d_uv(Par p, Flds f) {
 // step3d_t_tile (ROMS/Nonlinear/step3d_t.F:388-876 horizontal advection of t(:,:,:,3,:), :883-1210 vertical advection,
 // :1366-1427 implicit diffusion, :1551-1621 t3dbc + periodic images).  One thread per column and tracer.
 template <int HADV, int VADV>
-__global__ void __launch_bounds__(128) k_step3d_t(Par p, Flds f) {
-  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+__global__ void __launch_bounds__(TS, 7) k_step3d_t(Par p, Flds f) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  const int N = p.N;
+  double* sCF = sm + tid;
+  double* sDC = sm + N * TS + tid;
+  const int i = p.Istr + blockIdx.x * TS + tid;
+  const int j = 1 + blockIdx.y;
   const int itrc = blockIdx.z;
-  if (i > p.Iend || j > p.Mm) return;
-  const int N = p.N, P = p.P, o2 = j * P;
+  if (i > p.Iend) return;
+  const int P = p.P, PL = p.PL, o2 = j * P;
   const double* __restrict__ t3 = f.t[3][itrc];
-  double* __restrict__ tn = f.t[p.nnew][itrc];
+  double* tn = f.t[p.nnew][itrc];
   const double* __restrict__ Hz = f.Hz;
   const double* __restrict__ Huon = f.Huon;
   const double* __restrict__ Hvom = f.Hvom;
   const double* __restrict__ W = f.W;
   const double* __restrict__ Akt = f.Akt[itrc];
   const double pm = f.pm[o2 + i], pn = f.pn[o2 + i];
-  double x[MAXN + 1], hz[MAXN + 1], oHz[MAXN + 1], AK[MAXN + 1], CF[MAXN + 1], DC[MAXN + 1], tc[MAXN + 2];
-  for (int k = 1; k <= N; ++k) tc[k] = t3[o2 + k * p.PL + i];
-  tc[0] = tc[1]; tc[N + 1] = tc[N];
-  AK[0] = Akt[o2 + i];
   const double cffh = p.dt * pm * pn;
-  double FCm = 0.0;
-  for (int k = 1; k <= N; ++k) {
-    const int o = o2 + k * p.PL;
-    hz[k] = Hz[o + i];
-    oHz[k] = 1.0 / hz[k];
-    AK[k] = Akt[o + i];
-    // horizontal: t(nnew) -= dt*pm*pn*(div)  (:861-873)
-    double FXi, FXip, FEj, FEjp;
-    hadv_fluxes<HADV>(t3, Huon, Hvom, o, i, j, p, FXi, FXip, FEj, FEjp);
-    const double c1 = cffh * (FXip - FXi);
-    const double c2 = cffh * (FEjp - FEj);
-    const double c3 = c1 + c2;
-    double tv = tn[o + i] - c3;
-    // vertical (:1189-1207)
-    const double FCk = (k < N) ? vflux<VADV>(tc, k, N, W[o + i]) : 0.0;
-    const double cv = cffh * (FCk - FCm);
-    tv = tv - cv;
-    tv = tv * oHz[k];
-    x[k] = tv;
-    FCm = FCk;
+  const double dt = p.dt;
+  // ---- pass 1 (upward): t(nnew) - advection, /Hz -> x(k), parked in t(nnew); forward elimination
+  struct Lvl { AdvIn a; double tn, hz, W, akt, tk3; };
+  auto load_level = [&](int k) -> Lvl {
+    const int o = o2 + k * PL;
+    Lvl L;
+    L.a = adv_load(t3, Huon, Hvom, o, i, j, p);
+    L.tn = tn[o + i]; L.hz = Hz[o + i]; L.W = W[o + i]; L.akt = Akt[o + i];
+    L.tk3 = t3[o2 + ((k + 2 <= N) ? (k + 2) : N) * PL + i];                // t(k+2), clamped
+    return L;
+  };
+  double AKm = Akt[o2 + i], AKmm = 0.0, AKN;
+  {
+    Lvl cur = load_level(1);
+    double tkm1 = cur.a.t0, tk = cur.a.t0, tkp1 = t3[o2 + 2 * PL + i], tkp2 = cur.tk3;
+    double FCm = 0.0, hm = 0.0, om = 0.0, xm = 0.0, CFp = 0.0, DCp = 0.0;
+    for (int k = 1; k <= N; ++k) {
+      Lvl nxt = cur;
+      if (k < N) nxt = load_level(k + 1);
+      const double hk = cur.hz;
+      const double ok = 1.0 / hk;
+      const double AKk = cur.akt;
+      // horizontal: t(nnew) -= dt*pm*pn*(div)  (:861-873)
+      double FXi, FXip, FEj, FEjp;
+      hadv_fluxes_v<HADV>(cur.a, j, p.Mm, FXi, FXip, FEj, FEjp);
+      const double c1 = cffh * (FXip - FXi);
+      const double c2 = cffh * (FEjp - FEj);
+      const double c3 = c1 + c2;
+      double tv = cur.tn - c3;
+      // vertical (:1189-1207)
+      const double FCk = (k < N) ? vflux4<VADV>(tkm1, tk, tkp1, tkp2, k, N, cur.W) : 0.0;
+      const double cv = cffh * (FCk - FCm);
+      tv = tv - cv;
+      tv = tv * ok;
+      tn[o2 + k * PL + i] = tv;
+      if (k >= 2) {
+        spline_forward(hm, om, hk, ok, AKmm, AKm, AKk, tv - xm, dt, CFp, DCp);
+        sCF[(k - 2) * TS] = CFp; sDC[(k - 2) * TS] = DCp;
+      }
+      AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = tv; FCm = FCk;
+      tkm1 = tk; tk = tkp1; tkp1 = tkp2; tkp2 = nxt.tk3;
+      cur = nxt;
+    }
+    AKN = AKm;
   }
-  spline_implicit(x, hz, oHz, AK, N, p.dt, CF, DC);
-  for (int k = 1; k <= N; ++k) st_r_grad(tn, o2 + k * p.PL, i, j, x[k], p);
+  // ---- pass 2 (downward): back substitution + update + t3dbc / periodic images
+  {
+    double dk = 0.0;
+    double ak = dk * AKN;
+    for (int kt = N; kt >= 1; kt -= CH) {
+      double lx[CH], lh[CH], la[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int k = (kt - q >= 1) ? kt - q : 1;
+        const int o = o2 + k * PL + i;
+        lx[q] = tn[o]; lh[q] = Hz[o]; la[q] = Akt[o - PL];
+      }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int k = kt - q;
+        if (k >= 1) {
+          const double ok = 1.0 / lh[q];
+          double dkm1 = 0.0, akm1 = 0.0;
+          if (k > 1) {
+            dkm1 = sDC[(k - 2) * TS] - sCF[(k - 2) * TS] * dk;
+            akm1 = dkm1 * la[q];
+          }
+          const double cff = dt * ok * (ak - akm1);
+          st_r_grad(tn, o2 + k * PL, i, j, lx[q] + cff, p);
+          dk = dkm1; ak = akm1;
+        }
+      }
+    }
+  }
 }
 
-static inline dim3 g2(dim3 b, int ni, int nj, int nz = 1) { return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz); }
+static size_t smem_cols(int N) { return (size_t)2 * N * TS * sizeof(double); }
+template <typename K>
+static void allow_smem(K kern, size_t bytes) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
 
 void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s) {
-  if (launch_step3d_uv_n(p, f, s)) return;          // compile-time-N fast path (k_step3d_n.cu)
-  dim3 b(64, 2);
-  k_step3d_uv<0><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
-  k_step3d_uv<1><<<g2(b, p.Iend - p.Istr + 1, p.Mm - 1), b, 0, s>>>(p, f);
+  const size_t sm = smem_cols(p.N);
+  static size_t allowed = 0;
+  if (sm > allowed) { allow_smem(k_step3d_uv<0>, sm); allow_smem(k_step3d_uv<1>, sm); allowed = sm; }
+  const int nbx = (p.Iend - p.Istr + 1 + TS - 1) / TS;
+  k_step3d_uv<0><<<dim3(nbx, p.Mm), TS, sm, s>>>(p, f);
+  k_step3d_uv<1><<<dim3(nbx, p.Mm - 1), TS, sm, s>>>(p, f);
 }
 
+template <int H, int V>
+static void launch_s3t(const Par& p, const Flds& f, cudaStream_t s) {
+  const size_t sm = smem_cols(p.N);
+  static size_t allowed = 0;
+  if (sm > allowed) { allow_smem(k_step3d_t<H, V>, sm); allowed = sm; }
+  const int nbx = (p.Iend - p.Istr + 1 + TS - 1) / TS;
+  k_step3d_t<H, V><<<dim3(nbx, p.Mm, p.NT), TS, sm, s>>>(p, f);
+}
 template <int H>
 static void launch_s3t_v(const Par& p, const Flds& f, cudaStream_t s) {
-  dim3 b(64, 2); dim3 g = g2(b, p.Iend - p.Istr + 1, p.Mm, p.NT);
-  if (p.vadv == 0) k_step3d_t<H, 0><<<g, b, 0, s>>>(p, f);
-  else if (p.vadv == 1) k_step3d_t<H, 1><<<g, b, 0, s>>>(p, f);
-  else k_step3d_t<H, 2><<<g, b, 0, s>>>(p, f);
+  if (p.vadv == 0) launch_s3t<H, 0>(p, f, s);
+  else if (p.vadv == 1) launch_s3t<H, 1>(p, f, s);
+  else launch_s3t<H, 2>(p, f, s);
 }
 void launch_step3d_t(const Par& p, const Flds& f, cudaStream_t s) {
-  if (launch_step3d_t_n(p, f, s)) return;           // compile-time-N fast path (k_step3d_n.cu)
   if (p.hadv == 0) launch_s3t_v<0>(p, f, s);
   else if (p.hadv == 1) launch_s3t_v<1>(p, f, s);
   else if (p.hadv == 2) launch_s3t_v<2>(p, f, s);

@@ -20,9 +20,6 @@ void launch_uv3dmix2(const Par& p, const Flds& f, cudaStream_t s);
 void launch_step2d(const Par& p, const Flds& f, cudaStream_t s);
 void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s);
 void launch_step3d_t(const Par& p, const Flds& f, cudaStream_t s);
-// compile-time-N fast paths; return false when the configuration is not covered (caller falls back to the generic kernels)
-bool launch_step3d_uv_n(const Par& p, const Flds& f, cudaStream_t s);
-bool launch_step3d_t_n(const Par& p, const Flds& f, cudaStream_t s);
 // diag: partial[] must hold 16 doubles per block row; out16 on device
 void launch_diag(const Par& p, const Flds& f, double* partial, double* out16, int knew, cudaStream_t s);
 int diag_partial_doubles(const Par& p);
