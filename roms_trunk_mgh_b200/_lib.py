@@ -51,6 +51,9 @@ IP = C.POINTER(C.c_int)
 
 
 def lib_path(strict=False):
+    # ROMS_B200_LIB: kernel-tuning aid (tools/variant.py builds alternative production libraries); never set by tests
+    if not strict and os.environ.get("ROMS_B200_LIB"):
+        return os.environ["ROMS_B200_LIB"]
     return os.path.join(LIBDIR, "libroms_b200_strict.so" if strict else "libroms_b200.so")
 
 

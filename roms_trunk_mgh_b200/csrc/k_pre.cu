@@ -83,75 +83,91 @@ __global__ void __launch_bounds__(128) k_pre_step3d_t(Par p, Flds f) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // pre_step3d_tile, momentum part (ROMS/Nonlinear/pre_step3d.F:917-1118): u,v(nnew) = Hz*u(nstp) + AB3 rhs + explicit
-// vertical viscosity flux divergence.  One thread per column, handles the u-point and the v-point of cell (i,j).
+// vertical viscosity flux divergence.  One thread per column, handles the u-point and the v-point of cell (i,j) in one
+// upward march so that Hz, z_r and Akv are read once; the operands of level k+1 are requested before level k is computed.
 __global__ void __launch_bounds__(128) k_pre_step3d_uv(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > p.Iend || j > p.Mm) return;
-  const int N = p.N, P = p.P, o2 = j * P;
+  const int N = p.N, P = p.P, PL = p.PL, o2 = j * P + i;
   const int indx = 3 - p.nrhs;
+  const int istart = p.istart;
+  const bool dov = (j >= p.JstrV);
   const double* __restrict__ Hz = f.Hz;
   const double* __restrict__ z_r = f.z_r;
   const double* __restrict__ Akv = f.Akv;
-  const double pm0 = f.pm[o2 + i], pn0 = f.pn[o2 + i];
+  const double* __restrict__ ust = f.u[p.nstp];
+  const double* __restrict__ vst = f.v[p.nstp];
+  double* __restrict__ unw = f.u[p.nnew];
+  double* __restrict__ vnw = f.v[p.nnew];
+  const double* __restrict__ ru_r = f.ru[p.nrhs];
+  const double* __restrict__ ru_i = f.ru[indx];
+  const double* __restrict__ rv_r = f.rv[p.nrhs];
+  const double* __restrict__ rv_i = f.rv[indx];
+  const double pm0 = f.pm[o2], pn0 = f.pn[o2];
   const double cff3 = p.dt * (1.0 - p.lambda);
-  {
-    const double* __restrict__ ust = f.u[p.nstp];
-    double* __restrict__ unw = f.u[p.nnew];
-    const double* __restrict__ ru_r = f.ru[p.nrhs];
-    const double* __restrict__ ru_i = f.ru[indx];
-    const double cff = p.dt * 0.25;
-    const double DC0 = cff * (pm0 + f.pm[o2 + i - 1]) * (pn0 + f.pn[o2 + i - 1]);
-    double FCm = p.dt * f.bustr[o2 + i];
-    double uk = ust[o2 + p.PL + i];
-    for (int k = 1; k <= N; ++k) {
-      const int o = o2 + k * p.PL;
-      double FCk, ukp = 0.0;
+  const double cff = p.dt * 0.25;
+  const double DCu = cff * (pm0 + f.pm[o2 - 1]) * (pn0 + f.pn[o2 - 1]);
+  const double DCv = cff * (pm0 + f.pm[o2 - P]) * (pn0 + f.pn[o2 - P]);
+  struct Lvl { double hz0, hzW, hzS, zr0, zrW, zrS, ak0, akW, akS, up, vp, rur, rui, rvr, rvi; };
+  auto load_level = [&](int k) -> Lvl {
+    const int o = o2 + k * PL;
+    const int ou = (k < N) ? o + PL : o;                 // level k+1 operands (unused at k = N)
+    Lvl L;
+    L.hz0 = Hz[o]; L.hzW = Hz[o - 1]; L.hzS = Hz[o - P];
+    L.zr0 = z_r[ou]; L.zrW = z_r[ou - 1]; L.zrS = z_r[ou - P];
+    L.ak0 = Akv[o]; L.akW = Akv[o - 1]; L.akS = Akv[o - P];
+    L.up = ust[ou]; L.vp = vst[ou];
+    L.rur = L.rui = L.rvr = L.rvi = 0.0;
+    if (istart >= 1) { L.rui = ru_i[o]; L.rvi = rv_i[o]; }
+    if (istart == 2) { L.rur = ru_r[o]; L.rvr = rv_r[o]; }
+    return L;
+  };
+  double FCum = p.dt * f.bustr[o2], FCvm = p.dt * f.bvstr[o2];
+  const double sus = f.sustr[o2], svs = f.svstr[o2];
+  double uk = ust[o2 + PL], vk = vst[o2 + PL];
+  double zk0 = z_r[o2 + PL], zkW = z_r[o2 + PL - 1], zkS = z_r[o2 + PL - P];
+  Lvl cur = load_level(1);
+  for (int k = 1; k <= N; ++k) {
+    const int o = o2 + k * PL;
+    Lvl nxt = cur;
+    if (k < N) nxt = load_level(k + 1);
+    {
+      double FCk;
       if (k < N) {
-        ukp = ust[o + p.PL + i];
-        const double c = 1.0 / (z_r[o + p.PL + i] + z_r[o + p.PL + i - 1] - z_r[o + i] - z_r[o + i - 1]);
-        FCk = cff3 * c * (ukp - uk) * (Akv[o + i] + Akv[o + i - 1]);
+        const double c = 1.0 / (cur.zr0 + cur.zrW - zk0 - zkW);
+        FCk = cff3 * c * (cur.up - uk) * (cur.ak0 + cur.akW);
       } else {
-        FCk = p.dt * f.sustr[o2 + i];
+        FCk = p.dt * sus;
       }
-      const double a = uk * 0.5 * (Hz[o + i] + Hz[o + i - 1]);
-      const double d = FCk - FCm;
+      const double a = uk * 0.5 * (cur.hz0 + cur.hzW);
+      const double d = FCk - FCum;
       double x;
-      if (p.istart == 0) x = a + d;
-      else if (p.istart == 1) { const double c3 = 0.5 * DC0; x = a - c3 * ru_i[o + i] + d; }
-      else x = a + DC0 * ((5.0 / 12.0) * ru_r[o + i] - (16.0 / 12.0) * ru_i[o + i]) + d;
-      unw[o + i] = x;
-      FCm = FCk; uk = ukp;
+      if (istart == 0) x = a + d;
+      else if (istart == 1) { const double c3 = 0.5 * DCu; x = a - c3 * cur.rui + d; }
+      else x = a + DCu * ((5.0 / 12.0) * cur.rur - (16.0 / 12.0) * cur.rui) + d;
+      unw[o] = x;
+      FCum = FCk;
     }
-  }
-  if (j >= p.JstrV) {
-    const double* __restrict__ vst = f.v[p.nstp];
-    double* __restrict__ vnw = f.v[p.nnew];
-    const double* __restrict__ rv_r = f.rv[p.nrhs];
-    const double* __restrict__ rv_i = f.rv[indx];
-    const double cff = p.dt * 0.25;
-    const double DC0 = cff * (pm0 + f.pm[o2 - P + i]) * (pn0 + f.pn[o2 - P + i]);
-    double FCm = p.dt * f.bvstr[o2 + i];
-    double vk = vst[o2 + p.PL + i];
-    for (int k = 1; k <= N; ++k) {
-      const int o = o2 + k * p.PL;
-      double FCk, vkp = 0.0;
+    if (dov) {
+      double FCk;
       if (k < N) {
-        vkp = vst[o + p.PL + i];
-        const double c = 1.0 / (z_r[o + p.PL + i] + z_r[o + p.PL - P + i] - z_r[o + i] - z_r[o - P + i]);
-        FCk = cff3 * c * (vkp - vk) * (Akv[o + i] + Akv[o - P + i]);
+        const double c = 1.0 / (cur.zr0 + cur.zrS - zk0 - zkS);
+        FCk = cff3 * c * (cur.vp - vk) * (cur.ak0 + cur.akS);
       } else {
-        FCk = p.dt * f.svstr[o2 + i];
+        FCk = p.dt * svs;
       }
-      const double a = vk * 0.5 * (Hz[o + i] + Hz[o - P + i]);
-      const double d = FCk - FCm;
+      const double a = vk * 0.5 * (cur.hz0 + cur.hzS);
+      const double d = FCk - FCvm;
       double x;
-      if (p.istart == 0) x = a + d;
-      else if (p.istart == 1) { const double c3 = 0.5 * DC0; x = a - c3 * rv_i[o + i] + d; }
-      else x = a + DC0 * ((5.0 / 12.0) * rv_r[o + i] - (16.0 / 12.0) * rv_i[o + i]) + d;
-      vnw[o + i] = x;
-      FCm = FCk; vk = vkp;
+      if (istart == 0) x = a + d;
+      else if (istart == 1) { const double c3 = 0.5 * DCv; x = a - c3 * cur.rvi + d; }
+      else x = a + DCv * ((5.0 / 12.0) * cur.rvr - (16.0 / 12.0) * cur.rvi) + d;
+      vnw[o] = x;
+      FCvm = FCk;
     }
+    uk = cur.up; vk = cur.vp; zk0 = cur.zr0; zkW = cur.zrW; zkS = cur.zrS;
+    cur = nxt;
   }
 }
 
@@ -162,34 +178,53 @@ __global__ void __launch_bounds__(128) k_prsgrd32_P(Par p, Flds f) {
   const int i = p.Istr - 1 + blockIdx.x * blockDim.x + threadIdx.x;   // IstrU-1 .. Iend
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;            // JstrV-1 .. Jend
   if (i > p.Iend || j > p.Mm) return;
-  const int N = p.N, o2 = j * p.P;
+  const int N = p.N, PL = p.PL, o2 = j * p.P + i;
   const double OneFifth = 0.2, OneTwelfth = 1.0 / 12.0, eps = 1.0e-10;
   const double GRho = p.g / p.rho0, HalfGRho = 0.5 * GRho;
-  double rc[MAXN + 1], zc[MAXN + 1];
-  for (int k = 1; k <= N; ++k) { rc[k] = f.rho[o2 + k * p.PL + i]; zc[k] = f.z_r[o2 + k * p.PL + i]; }
-  const double zwN = f.z_w[o2 + N * p.PL + i];
+  const double* __restrict__ rho = f.rho;
+  const double* __restrict__ z_r = f.z_r;
+  double* __restrict__ P3 = f.P3;
+  // rolling window (k+1, k, k-1) of rho and z_r, marching downward; the loads of a batch of levels are issued together
+  constexpr int CH = 5;
+  const int oN = o2 + N * PL;
+  double r_kp = rho[oN], z_kp = z_r[oN];                               // level k+1 (starts at N)
+  double r_k = rho[oN - PL], z_k = z_r[oN - PL];                       // level k   (starts at N-1)
+  const double zwN = f.z_w[oN];
   // harmonic means at level N: raw(N) = raw(N-1)
-  double rawR_k = rc[N] - rc[N - 1], rawZ_k = zc[N] - zc[N - 1];     // raw(N) := raw(N-1)
-  double rawR_km = rawR_k, rawZ_km = rawZ_k;                          // raw(N-1)
+  double rawR_k = r_kp - r_k, rawZ_k = z_kp - z_k;                     // raw(N) := raw(N-1)
+  double rawR_km = rawR_k, rawZ_km = rawZ_k;                           // raw(N-1)
   double c = 2.0 * rawR_k * rawR_km;
-  double dR_kp = (c > eps) ? c / (rawR_k + rawR_km) : 0.0;            // dR(N)
-  double dZ_kp = 2.0 * rawZ_k * rawZ_km / (rawZ_k + rawZ_km);         // dZ(N)
-  const double cff1 = 1.0 / (zc[N] - zc[N - 1]);
-  const double cff2 = 0.5 * (rc[N] - rc[N - 1]) * (zwN - zc[N]) * cff1;
-  double Pk = p.g * zwN + GRho * (rc[N] + cff2) * (zwN - zc[N]);
-  f.P3[o2 + N * p.PL + i] = Pk;
-  for (int k = N - 1; k >= 1; --k) {
-    // dR(k) = harmonic(raw(k), raw(k-1)); raw(0) = raw(1)
-    rawR_k = rc[k + 1] - rc[k]; rawZ_k = zc[k + 1] - zc[k];
-    if (k > 1) { rawR_km = rc[k] - rc[k - 1]; rawZ_km = zc[k] - zc[k - 1]; } else { rawR_km = rawR_k; rawZ_km = rawZ_k; }
-    c = 2.0 * rawR_k * rawR_km;
-    const double dR_k = (c > eps) ? c / (rawR_k + rawR_km) : 0.0;
-    const double dZ_k = 2.0 * rawZ_k * rawZ_km / (rawZ_k + rawZ_km);
-    Pk = Pk + HalfGRho * ((rc[k + 1] + rc[k]) * (zc[k + 1] - zc[k]) -
-                          OneFifth * ((dR_kp - dR_k) * (zc[k + 1] - zc[k] - OneTwelfth * (dZ_kp + dZ_k)) -
-                                      (dZ_kp - dZ_k) * (rc[k + 1] - rc[k] - OneTwelfth * (dR_kp + dR_k))));
-    f.P3[o2 + k * p.PL + i] = Pk;
-    dR_kp = dR_k; dZ_kp = dZ_k;
+  double dR_kp = (c > eps) ? c / (rawR_k + rawR_km) : 0.0;             // dR(N)
+  double dZ_kp = 2.0 * rawZ_k * rawZ_km / (rawZ_k + rawZ_km);          // dZ(N)
+  const double cff1 = 1.0 / (z_kp - z_k);
+  const double cff2 = 0.5 * (r_kp - r_k) * (zwN - z_kp) * cff1;
+  double Pk = p.g * zwN + GRho * (r_kp + cff2) * (zwN - z_kp);
+  P3[oN] = Pk;
+  for (int kt = N - 1; kt >= 1; kt -= CH) {
+    double lr[CH], lz[CH];
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      const int km = (kt - q - 1 >= 1) ? kt - q - 1 : 1;               // level k-1 (clamped; unused when k = 1)
+      lr[q] = rho[o2 + km * PL]; lz[q] = z_r[o2 + km * PL];
+    }
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      const int k = kt - q;
+      if (k >= 1) {
+        // dR(k) = harmonic(raw(k), raw(k-1)); raw(0) = raw(1)
+        rawR_k = r_kp - r_k; rawZ_k = z_kp - z_k;
+        if (k > 1) { rawR_km = r_k - lr[q]; rawZ_km = z_k - lz[q]; } else { rawR_km = rawR_k; rawZ_km = rawZ_k; }
+        c = 2.0 * rawR_k * rawR_km;
+        const double dR_k = (c > eps) ? c / (rawR_k + rawR_km) : 0.0;
+        const double dZ_k = 2.0 * rawZ_k * rawZ_km / (rawZ_k + rawZ_km);
+        Pk = Pk + HalfGRho * ((r_kp + r_k) * (z_kp - z_k) -
+                              OneFifth * ((dR_kp - dR_k) * (z_kp - z_k - OneTwelfth * (dZ_kp + dZ_k)) -
+                                          (dZ_kp - dZ_k) * (r_kp - r_k - OneTwelfth * (dR_kp + dR_k))));
+        P3[o2 + k * PL] = Pk;
+        dR_kp = dR_k; dZ_kp = dZ_k;
+        r_kp = r_k; z_kp = z_k; r_k = lr[q]; z_k = lz[q];
+      }
+    }
   }
 }
 
@@ -283,30 +318,60 @@ __global__ void __launch_bounds__(128) k_prsgrd31(Par p, Flds f) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// t3dmix2_s_tile (ROMS/Nonlinear/t3dmix2_s.h:198-301): harmonic mixing of tracers along s-surfaces.
-__global__ void __launch_bounds__(256) k_t3dmix2_s(Par p, Flds f) {
+// t3dmix2_s_tile (ROMS/Nonlinear/t3dmix2_s.h:198-301): harmonic mixing of tracers along s-surfaces.  One thread per
+// column; the level-independent leading factors 0.25*(diff2+diff2)*pmon_u / pnom_v of the four face fluxes are formed
+// once, and the operands of level k+1 are requested before level k is computed.
+template <int NTR>
+__global__ void __launch_bounds__(128) k_t3dmix2_s(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-  const int k = 1 + blockIdx.z;
   if (i > p.Iend || j > p.Mm) return;
-  const int P = p.P, o2 = j * P, o = o2 + k * p.PL;
+  const int N = p.N, P = p.P, PL = p.PL, o2 = j * P + i;
   const double* __restrict__ Hz = f.Hz;
-  const double hz0 = Hz[o + i], hzW = Hz[o + i - 1], hzE = Hz[o + i + 1], hzS = Hz[o - P + i], hzN = Hz[o + P + i];
-  const double cff = p.dt * f.pm[o2 + i] * f.pn[o2 + i];
-  for (int it = 0; it < p.NT; ++it) {
-    const double* __restrict__ tr = f.t[p.nrhs][it];
-    double* __restrict__ tn = f.t[p.nnew][it];
+  const double cff = p.dt * f.pm[o2] * f.pn[o2];
+  const double* __restrict__ tr[NTR];
+  double* __restrict__ tn[NTR];
+  double cW[NTR], cE[NTR], cS[NTR], cN[NTR];
+#pragma unroll
+  for (int it = 0; it < NTR; ++it) {
+    tr[it] = f.t[p.nrhs][it]; tn[it] = f.t[p.nnew][it];
     const double* __restrict__ d2 = f.diff2[it];
-    const double t0 = tr[o + i];
-    const double d0 = d2[o2 + i];
-    const double FXi = 0.25 * (d0 + d2[o2 + i - 1]) * f.pmon_u[o2 + i] * (hz0 + hzW) * (t0 - tr[o + i - 1]);
-    const double FXip = 0.25 * (d2[o2 + i + 1] + d0) * f.pmon_u[o2 + i + 1] * (hzE + hz0) * (tr[o + i + 1] - t0);
-    const double FEj = 0.25 * (d0 + d2[o2 - P + i]) * f.pnom_v[o2 + i] * (hz0 + hzS) * (t0 - tr[o - P + i]);
-    const double FEjp = 0.25 * (d2[o2 + P + i] + d0) * f.pnom_v[o2 + P + i] * (hzN + hz0) * (tr[o + P + i] - t0);
-    const double cff1 = cff * (FXip - FXi);
-    const double cff2 = cff * (FEjp - FEj);
-    const double cff3 = cff1 + cff2;
-    tn[o + i] = tn[o + i] + cff3;
+    const double d0 = d2[o2];
+    cW[it] = 0.25 * (d0 + d2[o2 - 1]) * f.pmon_u[o2];
+    cE[it] = 0.25 * (d2[o2 + 1] + d0) * f.pmon_u[o2 + 1];
+    cS[it] = 0.25 * (d0 + d2[o2 - P]) * f.pnom_v[o2];
+    cN[it] = 0.25 * (d2[o2 + P] + d0) * f.pnom_v[o2 + P];
+  }
+  struct Lvl { double hz0, hzW, hzE, hzS, hzN, t0[NTR], tW[NTR], tE[NTR], tS[NTR], tN[NTR], tn[NTR]; };
+  auto load_level = [&](int k) -> Lvl {
+    const int o = o2 + k * PL;
+    Lvl L;
+    L.hz0 = Hz[o]; L.hzW = Hz[o - 1]; L.hzE = Hz[o + 1]; L.hzS = Hz[o - P]; L.hzN = Hz[o + P];
+#pragma unroll
+    for (int it = 0; it < NTR; ++it) {
+      L.t0[it] = tr[it][o]; L.tW[it] = tr[it][o - 1]; L.tE[it] = tr[it][o + 1]; L.tS[it] = tr[it][o - P]; L.tN[it] = tr[it][o + P];
+      L.tn[it] = tn[it][o];
+    }
+    return L;
+  };
+  Lvl cur = load_level(1);
+  for (int k = 1; k <= N; ++k) {
+    const int o = o2 + k * PL;
+    Lvl nxt = cur;
+    if (k < N) nxt = load_level(k + 1);
+#pragma unroll
+    for (int it = 0; it < NTR; ++it) {
+      const double t0 = cur.t0[it];
+      const double FXi = cW[it] * (cur.hz0 + cur.hzW) * (t0 - cur.tW[it]);
+      const double FXip = cE[it] * (cur.hzE + cur.hz0) * (cur.tE[it] - t0);
+      const double FEj = cS[it] * (cur.hz0 + cur.hzS) * (t0 - cur.tS[it]);
+      const double FEjp = cN[it] * (cur.hzN + cur.hz0) * (cur.tN[it] - t0);
+      const double cff1 = cff * (FXip - FXi);
+      const double cff2 = cff * (FEjp - FEj);
+      const double cff3 = cff1 + cff2;
+      tn[it][o] = cur.tn[it] + cff3;
+    }
+    cur = nxt;
   }
 }
 
@@ -340,8 +405,9 @@ void launch_prsgrd(const Par& p, const Flds& f, int dj_gradps, cudaStream_t s) {
   }
 }
 void launch_t3dmix2_s(const Par& p, const Flds& f, cudaStream_t s) {
-  dim3 b(64, 4);
-  k_t3dmix2_s<<<g2(p, b, p.Iend - p.Istr + 1, p.Mm, p.N), b, 0, s>>>(p, f);
+  dim3 b(64, 2); dim3 g = g2(p, b, p.Iend - p.Istr + 1, p.Mm);
+  if (p.NT == 1) k_t3dmix2_s<1><<<g, b, 0, s>>>(p, f);
+  else k_t3dmix2_s<2><<<g, b, 0, s>>>(p, f);
 }
 
 }  // namespace rb

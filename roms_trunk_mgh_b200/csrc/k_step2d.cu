@@ -19,8 +19,14 @@
 
 namespace rb {
 
-constexpr int TX = 32, TY = 8;           // output tile
-constexpr int NTH = 320;                 // threads per CTA (>= (TX+1)*(TY+1) = 297)
+#ifndef S2D_TY
+#define S2D_TY 8
+#endif
+#ifndef S2D_NTH
+#define S2D_NTH 320
+#endif
+constexpr int TX = 32, TY = S2D_TY;      // output tile
+constexpr int NTH = S2D_NTH;             // threads per CTA (>= (TX+1)*(TY+1) = 297)
 constexpr int HL = 3, HH = 2;            // low / high halo of the staged inputs
 constexpr int SW = TX + HL + HH;         // staged width  (37)
 constexpr int SH = TY + HL + HH;         // staged height (13)
@@ -29,7 +35,10 @@ constexpr int NS = SW * SH, NZ = ZW * ZH;
 constexpr int SMEM_DOUBLES = 5 * NS + 17 * NZ;
 static_assert(NZ <= NTH && NS <= 2 * NTH, "tile / thread-count mismatch");
 
-__global__ void __launch_bounds__(NTH, 2) k_step2d(Par p, Flds f) {
+#ifndef S2D_MINB
+#define S2D_MINB 2
+#endif
+__global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
   extern __shared__ double smem[];
   double* sD = smem; double* sU = sD + NS; double* sV = sU + NS; double* sDU = sV + NS; double* sDV = sDU + NS;
   // regions with origin (i0-1, j0-1): zeta-stage and rho-point fluxes

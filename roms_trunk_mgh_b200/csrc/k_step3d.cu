@@ -14,8 +14,17 @@
 
 namespace rb {
 
-constexpr int TS = 64;       // threads (columns) per block
-constexpr int CH = 5;        // levels per batch of independent loads in the downward / coupling passes
+#ifndef S3D_TS
+#define S3D_TS 64
+#endif
+#ifndef S3D_CH
+#define S3D_CH 5
+#endif
+#ifndef S3D_MINB
+#define S3D_MINB 7
+#endif
+constexpr int TS = S3D_TS;   // threads (columns) per block
+constexpr int CH = S3D_CH;   // levels per batch of independent loads in the downward / coupling passes
 
 // One forward-elimination step of the spline system for row m = k-1 once level k is known
 // (step3d_uv.F:344-375, step3d_t.F:1370-1405): h/o/AK suffix m = level k-1, k = level k, AKmm = AK(k-2).
@@ -34,7 +43,7 @@ __device__ __forceinline__ void spline_forward(double hm, double om, double hk, 
 // :956-965 closed-wall BCs; :1002-1432 coupling with DU_avg1/DU_avg2, ubar/vbar reset, corrected Huon/Hvom;
 // :1438-1461 periodic images).  DIR = 0: u-points, DIR = 1: v-points.
 template <int DIR>
-__global__ void __launch_bounds__(TS, 7) k_step3d_uv(Par p, Flds f) {
+__global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   const int N = p.N;
@@ -198,7 +207,7 @@ __global__ void __launch_bounds__(TS, 7) k_step3d_uv(Par p, Flds f) {
 // step3d_t_tile (ROMS/Nonlinear/step3d_t.F:388-876 horizontal advection of t(:,:,:,3,:), :883-1210 vertical advection,
 // :1366-1427 implicit diffusion, :1551-1621 t3dbc + periodic images).  One thread per column and tracer.
 template <int HADV, int VADV>
-__global__ void __launch_bounds__(TS, 7) k_step3d_t(Par p, Flds f) {
+__global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_t(Par p, Flds f) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   const int N = p.N;
