@@ -11,9 +11,11 @@ namespace rb {
 // 3-D input is read once per level and both outputs are written once.
 template <int HADV, int VADV>
 __global__ void __launch_bounds__(128) k_pre_step3d_t(Par p, Flds f) {
-  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  // the tracer index is the fastest grid dimension: the CTAs of all tracers of one tile run back to back, so the shared
+  // operands (Huon, Hvom, W, Hz, z_r) of the second tracer come from L2
+  const int itrc = blockIdx.x % p.NT;
+  const int i = p.Istr + (blockIdx.x / p.NT) * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-  const int itrc = blockIdx.z;
   if (i > p.Iend || j > p.Mm) return;
   const int N = p.N, P = p.P, o2 = j * P;
   const double* __restrict__ tst = f.t[p.nstp][itrc];
@@ -47,12 +49,9 @@ __global__ void __launch_bounds__(128) k_pre_step3d_t(Par p, Flds f) {
   double FDm = p.dt * f.btflx[itrc][o2 + i];          // diffusive FC(k-1), FC(0) = dt*btflx
   double Wm = W[o2 + i];                              // W(k-1)
   double zrk = z_r[o2 + p.PL + i];                    // z_r(k)
-  Lvl cur = load_level(1);
-  double tkm1 = cur.a.t0, tk = cur.a.t0, tkp1 = tst[o2 + 2 * p.PL + i], tkp2 = cur.tk3;
-  for (int k = 1; k <= N; ++k) {
+  double tkm1 = tst[o2 + p.PL + i], tk = tkm1, tkp1 = tst[o2 + 2 * p.PL + i], tkp2 = tst[o2 + 3 * p.PL + i];
+  auto level = [&](const Lvl& cur, const Lvl& nxt, int k) {
     const int o = o2 + k * p.PL;
-    Lvl nxt = cur;
-    if (k < N) nxt = load_level(k + 1);
     const double hz = cur.hz;
     double FXi, FXip, FEj, FEjp;
     hadv_fluxes_v<HADV>(cur.a, j, p.Mm, FXi, FXip, FEj, FEjp);
@@ -77,7 +76,16 @@ __global__ void __launch_bounds__(128) k_pre_step3d_t(Par p, Flds f) {
     tnw[o + i] = c1 + c2;
     FCm = FCk; FDm = FDk; Wm = Wk; zrk = cur.zr1;
     tkm1 = tk; tk = tkp1; tkp1 = tkp2; tkp2 = nxt.tk3;
-    cur = nxt;
+  };
+  {
+    // level k+1 is requested before level k is computed
+    Lvl cur = load_level(1);
+    for (int k = 1; k <= N; ++k) {
+      Lvl nxt = cur;
+      if (k < N) nxt = load_level(k + 1);
+      level(cur, nxt, k);
+      cur = nxt;
+    }
   }
 }
 
@@ -127,11 +135,8 @@ __global__ void __launch_bounds__(128) k_pre_step3d_uv(Par p, Flds f) {
   const double sus = f.sustr[o2], svs = f.svstr[o2];
   double uk = ust[o2 + PL], vk = vst[o2 + PL];
   double zk0 = z_r[o2 + PL], zkW = z_r[o2 + PL - 1], zkS = z_r[o2 + PL - P];
-  Lvl cur = load_level(1);
-  for (int k = 1; k <= N; ++k) {
+  auto level = [&](const Lvl& cur, const Lvl&, int k) {
     const int o = o2 + k * PL;
-    Lvl nxt = cur;
-    if (k < N) nxt = load_level(k + 1);
     {
       double FCk;
       if (k < N) {
@@ -167,7 +172,16 @@ __global__ void __launch_bounds__(128) k_pre_step3d_uv(Par p, Flds f) {
       FCvm = FCk;
     }
     uk = cur.up; vk = cur.vp; zk0 = cur.zr0; zkW = cur.zrW; zkS = cur.zrS;
-    cur = nxt;
+  };
+  {
+    // level k+1 is requested before level k is computed
+    Lvl cur = load_level(1);
+    for (int k = 1; k <= N; ++k) {
+      Lvl nxt = cur;
+      if (k < N) nxt = load_level(k + 1);
+      level(cur, nxt, k);
+      cur = nxt;
+    }
   }
 }
 
@@ -354,11 +368,8 @@ __global__ void __launch_bounds__(128) k_t3dmix2_s(Par p, Flds f) {
     }
     return L;
   };
-  Lvl cur = load_level(1);
-  for (int k = 1; k <= N; ++k) {
+  auto level = [&](const Lvl& cur, const Lvl&, int k) {
     const int o = o2 + k * PL;
-    Lvl nxt = cur;
-    if (k < N) nxt = load_level(k + 1);
 #pragma unroll
     for (int it = 0; it < NTR; ++it) {
       const double t0 = cur.t0[it];
@@ -371,7 +382,16 @@ __global__ void __launch_bounds__(128) k_t3dmix2_s(Par p, Flds f) {
       const double cff3 = cff1 + cff2;
       tn[it][o] = cur.tn[it] + cff3;
     }
-    cur = nxt;
+  };
+  {
+    // level k+1 is requested before level k is computed
+    Lvl cur = load_level(1);
+    for (int k = 1; k <= N; ++k) {
+      Lvl nxt = cur;
+      if (k < N) nxt = load_level(k + 1);
+      level(cur, nxt, k);
+      cur = nxt;
+    }
   }
 }
 
@@ -380,7 +400,8 @@ static inline dim3 g2(const Par& p, dim3 b, int ni, int nj, int nz = 1) { return
 
 template <int H>
 static void launch_pre_t_v(const Par& p, const Flds& f, cudaStream_t s) {
-  dim3 b(64, 2); dim3 g = g2(p, b, p.Iend - p.Istr + 1, p.Mm, p.NT);
+  dim3 b(64, 2); dim3 g = g2(p, b, p.Iend - p.Istr + 1, p.Mm);
+  g.x *= p.NT;
   if (p.vadv == 0) k_pre_step3d_t<H, 0><<<g, b, 0, s>>>(p, f);
   else if (p.vadv == 1) k_pre_step3d_t<H, 1><<<g, b, 0, s>>>(p, f);
   else k_pre_step3d_t<H, 2><<<g, b, 0, s>>>(p, f);

@@ -10,7 +10,13 @@ __device__ __forceinline__ double d2x(const double* __restrict__ A, int o) { ret
 __device__ __forceinline__ double d2y(const double* __restrict__ A, int o, int P) { return A[o - P] - 2.0 * A[o] + A[o + P]; }
 
 // ROMS/Nonlinear/rhs3d.F:174-1671
-__global__ void __launch_bounds__(128) k_rhs3d(Par p, Flds f) {
+#ifndef RHS_MINB
+#define RHS_MINB 2
+#endif
+#ifndef RHS_BX
+#define RHS_BX 64
+#endif
+__global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > p.Iend || j > p.Mm) return;
@@ -181,7 +187,10 @@ __global__ void __launch_bounds__(128) k_rhs3d(Par p, Flds f) {
 // ---------------------------------------------------------------------------------------------------------------
 // uv3dmix2_s_tile (ROMS/Nonlinear/uv3dmix2_s.h:239-330): harmonic viscosity along s-surfaces, stress-tensor form.
 // rufrc/rvfrc accumulate level by level (k = 1..N) exactly as the reference does.
-__global__ void __launch_bounds__(128) k_uv3dmix2(Par p, Flds f) {
+#ifndef UVM_MINB
+#define UVM_MINB 3
+#endif
+__global__ void __launch_bounds__(128, UVM_MINB) k_uv3dmix2(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > p.Iend || j > p.Mm) return;
@@ -219,15 +228,25 @@ __global__ void __launch_bounds__(128) k_uv3dmix2(Par p, Flds f) {
   const double pmV = pm[o2] + pm[o2 - P], pnV = pn[o2] + pn[o2 - P];
   const double pmVb = pm[o2 - P] + pm[o2], pnVb = pn[o2 - P] + pn[o2];
   double rufrc = f.rufrc[o2], rvfrc = dov ? f.rvfrc[o2] : 0.0;
-  for (int k = 1; k <= N; ++k) {
+  // operands of one level; level k+1 is requested before level k is computed
+  struct Lvl { double h0, hW, hE, hS, hSW, hSE, hN, hNW, uW, u0, uE, uS, uSE, uN, vW, v0, vE, vS, vN, vNW, un0, vn0; };
+  auto load_level = [&](int k) -> Lvl {
     const int o = o2 + k * p.PL;
-    // all operands of the level, issued back to back
-    const double h0 = Hz[o], hW = Hz[o - 1], hE = Hz[o + 1], hS = Hz[o - P], hSW = Hz[o - P - 1], hSE = Hz[o - P + 1];
-    const double hN = Hz[o + P], hNW = Hz[o + P - 1];
-    const double uW = u[o - 1], u0 = u[o], uE = u[o + 1], uS = u[o - P], uSE = u[o - P + 1], uN = u[o + P];
-    const double vW = v[o - 1], v0 = v[o], vE = v[o + 1], vS = v[o - P], vN = v[o + P], vNW = v[o + P - 1];
-    const double un0 = un[o];
-    const double vn0 = dov ? vn[o] : 0.0;
+    Lvl L;
+    L.h0 = Hz[o]; L.hW = Hz[o - 1]; L.hE = Hz[o + 1]; L.hS = Hz[o - P]; L.hSW = Hz[o - P - 1]; L.hSE = Hz[o - P + 1];
+    L.hN = Hz[o + P]; L.hNW = Hz[o + P - 1];
+    L.uW = u[o - 1]; L.u0 = u[o]; L.uE = u[o + 1]; L.uS = u[o - P]; L.uSE = u[o - P + 1]; L.uN = u[o + P];
+    L.vW = v[o - 1]; L.v0 = v[o]; L.vE = v[o + 1]; L.vS = v[o - P]; L.vN = v[o + P]; L.vNW = v[o + P - 1];
+    L.un0 = un[o];
+    L.vn0 = dov ? vn[o] : 0.0;
+    return L;
+  };
+  auto level = [&](const Lvl& cur, const Lvl&, int k) {
+    const int o = o2 + k * p.PL;
+    const double h0 = cur.h0, hW = cur.hW, hE = cur.hE, hS = cur.hS, hSW = cur.hSW, hSE = cur.hSE, hN = cur.hN, hNW = cur.hNW;
+    const double uW = cur.uW, u0 = cur.u0, uE = cur.uE, uS = cur.uS, uSE = cur.uSE, uN = cur.uN;
+    const double vW = cur.vW, v0 = cur.v0, vE = cur.vE, vS = cur.vS, vN = cur.vN, vNW = cur.vNW;
+    const double un0 = cur.un0, vn0 = cur.vn0;
     const double cr0 = rho_cff(R0, h0, uE, u0, vN, v0), crW = rho_cff(RW, hW, u0, uW, vNW, vW);
     const double cp0 = psi_cff(Q0, hW, h0, hSW, hS, v0, vW, u0, uS), cpN = psi_cff(QN, hNW, hN, hW, h0, vN, vNW, uN, u0);
     {
@@ -251,13 +270,23 @@ __global__ void __launch_bounds__(128) k_uv3dmix2(Par p, Flds f) {
       rvfrc = rvfrc + cff1 - cff2;
       vn[o] = vn0 + cff3;
     }
+  };
+  {
+    // level k+1 is requested before level k is computed
+    Lvl cur = load_level(1);
+    for (int k = 1; k <= N; ++k) {
+      Lvl nxt = cur;
+      if (k < N) nxt = load_level(k + 1);
+      level(cur, nxt, k);
+      cur = nxt;
+    }
   }
   f.rufrc[o2] = rufrc;
   if (dov) f.rvfrc[o2] = rvfrc;
 }
 
 static inline dim3 g2(dim3 b, int ni, int nj, int nz = 1) { return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz); }
-void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 2); k_rhs3d<<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f); }
+void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(RHS_BX, 128 / RHS_BX); k_rhs3d<<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f); }
 void launch_uv3dmix2(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 2); k_uv3dmix2<<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f); }
 
 }  // namespace rb

@@ -81,11 +81,8 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
   };
   double AKm = 0.5 * (Akv[o2 - s] + Akv[o2]), AKmm = 0.0, AKN;
   {
-    Lvl cur = load_level(1);
     double hm = 0.0, om = 0.0, xm = 0.0, CFp = 0.0, DCp = 0.0;
-    for (int k = 1; k <= N; ++k) {
-      Lvl nxt = cur;
-      if (k < N) nxt = load_level(k + 1);
+    auto level = [&](const Lvl& cur, const Lvl&, int k) {
       const double AKk = 0.5 * (cur.ak0 + cur.ak1);
       const double hk = 0.5 * (cur.h0 + cur.h1);
       const double ok = 1.0 / hk;
@@ -96,6 +93,13 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
         sA[(k - 2) * TS] = CFp; sB[(k - 2) * TS] = DCp;
       }
       AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = xv;
+    };
+    // level k+1 is requested before level k is computed
+    Lvl cur = load_level(1);
+    for (int k = 1; k <= N; ++k) {
+      Lvl nxt = cur;
+      if (k < N) nxt = load_level(k + 1);
+      level(cur, nxt, k);
       cur = nxt;
     }
     AKN = AKm;
@@ -213,9 +217,10 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_t(Par p, Flds f) {
   const int N = p.N;
   double* sCF = sm + tid;
   double* sDC = sm + N * TS + tid;
-  const int i = p.Istr + blockIdx.x * TS + tid;
+  // tracer index fastest: the CTAs of all tracers of one tile run back to back and share Huon, Hvom, W, Hz through L2
+  const int itrc = blockIdx.x % p.NT;
+  const int i = p.Istr + (blockIdx.x / p.NT) * TS + tid;
   const int j = 1 + blockIdx.y;
-  const int itrc = blockIdx.z;
   if (i > p.Iend) return;
   const int P = p.P, PL = p.PL, o2 = j * P;
   const double* __restrict__ t3 = f.t[3][itrc];
@@ -240,12 +245,9 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_t(Par p, Flds f) {
   };
   double AKm = Akt[o2 + i], AKmm = 0.0, AKN;
   {
-    Lvl cur = load_level(1);
-    double tkm1 = cur.a.t0, tk = cur.a.t0, tkp1 = t3[o2 + 2 * PL + i], tkp2 = cur.tk3;
+    double tkm1 = t3[o2 + PL + i], tk = tkm1, tkp1 = t3[o2 + 2 * PL + i], tkp2 = t3[o2 + 3 * PL + i];
     double FCm = 0.0, hm = 0.0, om = 0.0, xm = 0.0, CFp = 0.0, DCp = 0.0;
-    for (int k = 1; k <= N; ++k) {
-      Lvl nxt = cur;
-      if (k < N) nxt = load_level(k + 1);
+    auto level = [&](const Lvl& cur, const Lvl& nxt, int k) {
       const double hk = cur.hz;
       const double ok = 1.0 / hk;
       const double AKk = cur.akt;
@@ -268,6 +270,13 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_t(Par p, Flds f) {
       }
       AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = tv; FCm = FCk;
       tkm1 = tk; tk = tkp1; tkp1 = tkp2; tkp2 = nxt.tk3;
+    };
+    // level k+1 is requested before level k is computed
+    Lvl cur = load_level(1);
+    for (int k = 1; k <= N; ++k) {
+      Lvl nxt = cur;
+      if (k < N) nxt = load_level(k + 1);
+      level(cur, nxt, k);
       cur = nxt;
     }
     AKN = AKm;
@@ -322,7 +331,7 @@ static void launch_s3t(const Par& p, const Flds& f, cudaStream_t s) {
   static size_t allowed = 0;
   if (sm > allowed) { allow_smem(k_step3d_t<H, V>, sm); allowed = sm; }
   const int nbx = (p.Iend - p.Istr + 1 + TS - 1) / TS;
-  k_step3d_t<H, V><<<dim3(nbx, p.Mm, p.NT), TS, sm, s>>>(p, f);
+  k_step3d_t<H, V><<<dim3(nbx * p.NT, p.Mm), TS, sm, s>>>(p, f);
 }
 template <int H>
 static void launch_s3t_v(const Par& p, const Flds& f, cudaStream_t s) {
