@@ -178,11 +178,13 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl")
     NtileI = world
+    xchg = "none (single tile, periodic images written by the producing kernel)"
     t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, NtileI=NtileI, tile=rank, device=local)
     nfast = synth.set_weights(t.cfg.ndtfast)[0]
     if world > 1:
         from roms_trunk_mgh_b200 import multigpu
         multigpu.attach(t, dist, rank, world)
+        xchg = ("nvlink-peer-mailbox" if t.peer else "nccl-send-recv") + ("" if os.environ.get("ROMS_B200_NO_OVERLAP") == "1" else "+edge-first-overlap")
         for ph in ("set_depth", "set_massflux", "omega", "rho_eos"):      # start-up phases again, now with live ghosts
             t.run_phase(ph)
     t.main3d(a.spinup)
@@ -257,7 +259,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "grid-point-steps/s", "n_gpus": world, "steps": a.steps, "warmup": W,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{a.grid.upper()} {Lm}x{Mm}x{N}, NT=2, reduced physics set (nonlinear EOS, DJ_GRADPS, U3/C4, UV_VIS2, TS_DIF2 MIX_S_TS, "
-                                   f"UV_QDRAG, CURVGRID), ndtfast={t.cfg.ndtfast}, nfast={nfast}", "tiles": f"{NtileI}x1",
+                                   f"UV_QDRAG, CURVGRID), ndtfast={t.cfg.ndtfast}, nfast={nfast}", "tiles": f"{NtileI}x1", "halo_exchange": xchg,
+                       "launch": "stream" if os.environ.get("ROMS_B200_NO_GRAPH") == "1" else "cuda-graph per step",
                        "l2": "working set per step (~3.5 GB) exceeds L2 (126 MB); no explicit flush", "spinup_steps": a.spinup},
             "e2e": {"value": e2e_val, "unit": "grid-point-steps/s", "h2d_bytes_per_step": int(3 * sustr.size * 8), "d2h_bytes_per_step": 12 * 8,
                     "steps": ke},

@@ -135,6 +135,16 @@ long long roms_b200_launch_count(roms_b200_handle h);
 int roms_b200_attach_nccl(roms_b200_handle h, void* nccl_comm, int rank, int nranks);
 int roms_b200_nccl_unique_id(char* out128);
 int roms_b200_nccl_init_rank(const char* id128, int rank, int nranks, void** comm_out);
+/* Optional NVLink peer path for the same exchanges (the NCCL path stays the fall-back): every tile owns a mailbox in HBM
+ * that its two ring neighbours map through CUDA IPC and store into directly, so one exchange is a push kernel (remote
+ * stores + flag) and an unpack kernel (flag wait + local copy) with no NCCL rendezvous -- what the ~118 small
+ * mp_exchange2d calls of the barotropic loop (step2d_LF_AM3.h:586,884,924,2519) need.  Protocol, all ranks:
+ * peer_export -> 64-byte IPC handle; exchange handles on the host; peer_attach(west's, east's); agree that every rank
+ * succeeded; peer_enable(1).  peer_error returns 1 if a wait for a neighbour ever timed out (results invalid). */
+int roms_b200_peer_export(roms_b200_handle h, char* out64);
+int roms_b200_peer_attach(roms_b200_handle h, const char* west64, const char* east64);
+int roms_b200_peer_enable(roms_b200_handle h, int on);
+int roms_b200_peer_error(roms_b200_handle h);
 
 /* ---- per-routine host-pointer form (mirrors the _tile argument lists; used by the parity tests) ---------------- */
 /* roms_b200_tile_t carries what tile.h/set_bounds.h give a _tile routine. */

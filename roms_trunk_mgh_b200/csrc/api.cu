@@ -150,40 +150,91 @@ std::vector<std::string> halo_fields(roms_b200_state* h, int phase) {
   return v;
 }
 
-int phase_halo(roms_b200_state* h, int phase) {
-  if (!h->halo) return NoError;
-  return halo_exchange(h, halo_fields(h, phase));
+// ---- two-stream schedule of a tile that sits in a ring -------------------------------------------------------------
+// main stream : full-tile kernels of the phases that need no exchange, and the INTERIOR part (all but the first / last
+//               EDGE_W columns) of the phases whose output is exchanged
+// comm stream : (high priority) the EDGE part of those phases, then their halo exchange
+// An interior kernel never touches ghost columns, so it only waits for the previous edge kernel (ev_edge), not for the
+// exchange that follows it: exchange n overlaps interior n AND interior n+1.  An edge kernel needs the ghosts of exchange
+// n-1 (same stream) and the interior results so far (ev_main).  Full-tile kernels wait for the latest exchange (ev_halo).
+// Every point is still computed exactly once from the same inputs, so results do not depend on the split.
+void join_halo(roms_b200_state* h) {
+  if (h->halo_pending) { cudaStreamWaitEvent(h->stream, h->ev_halo, 0); h->halo_pending = false; h->edge_pending = false; }
+}
+
+template <class F>
+void launch_full(roms_b200_state* h, F fn) {
+  join_halo(h);
+  fn(h->par, h->stream);
+}
+
+// Launch `fn` over the tile and refresh the xi-ghost columns of the fields `phase` produces (mp_exchange2d/3d/4d).
+template <class F>
+int launch_with_halo(roms_b200_state* h, int phase, F fn) {
+  const Par& p = h->par;
+  if (!h->halo) { fn(p, h->stream); return NoError; }
+  const std::vector<std::string> names = halo_fields(h, phase);
+  const int ni = p.Iend - p.Istr + 1;
+  if (names.empty() || !h->overlap || ni < 4 * EDGE_W) {
+    launch_full(h, fn);
+    return halo_exchange(h, names, h->stream);
+  }
+  if (h->edge_pending) { cudaStreamWaitEvent(h->stream, h->ev_edge, 0); h->edge_pending = false; }
+  cudaEventRecord(h->ev_main, h->stream);
+  cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0);
+  Par e = p; e.gap_at = EDGE_W; e.gap_len = ni - 2 * EDGE_W;
+  fn(e, h->comm_stream);
+  cudaEventRecord(h->ev_edge, h->comm_stream);
+  const int rc = halo_exchange(h, names, h->comm_stream);
+  cudaEventRecord(h->ev_halo, h->comm_stream);
+  Par q = p; q.Istr = p.Istr + EDGE_W; q.Iend = p.Iend - EDGE_W;
+  fn(q, h->stream);
+  h->edge_pending = true; h->halo_pending = true;
+  h->launches += 1;
+  return rc;
 }
 
 int run_phase_async(roms_b200_state* h, int phase) {
   fill_par(h);
   const Par& p = h->par; const Flds& f = h->fl; cudaStream_t s = h->stream;
   PhaseTimer pt(h, phase);
+  int rc = NoError;
   switch (phase) {
     case ROMS_B200_SET_DATA: break;
-    case ROMS_B200_SET_MASSFLUX: launch_set_massflux(p, f, s); h->launches += 1; break;
-    case ROMS_B200_RHO_EOS: launch_rho_eos(p, f, s); h->launches += 1; break;
-    case ROMS_B200_SET_VBC: launch_set_vbc(p, f, s); h->launches += 1; break;
-    case ROMS_B200_ANA_VMIX: if (h->cfg.ana_vmix) { launch_ana_vmix(p, f, s); h->launches += 1; } break;
-    case ROMS_B200_OMEGA: case ROMS_B200_OMEGA2: launch_omega(p, f, s); h->launches += 1; break;
-    case ROMS_B200_WVELOCITY: launch_wvelocity(p, f, h->nstp, s); h->launches += 1; break;
-    case ROMS_B200_SET_ZETA: launch_set_zeta(p, f, s); h->launches += 1; break;
-    case ROMS_B200_PRE_STEP3D: launch_pre_step3d(p, f, s); h->launches += 2; break;
-    case ROMS_B200_PRSGRD: launch_prsgrd(p, f, h->cfg.dj_gradps, s); h->launches += h->cfg.dj_gradps ? 2 : 1; break;
+    case ROMS_B200_SET_MASSFLUX: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_massflux(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_RHO_EOS: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_rho_eos(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_SET_VBC: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_vbc(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_ANA_VMIX:
+      if (h->cfg.ana_vmix) { rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_ana_vmix(q, f, st); }); h->launches += 1; }
+      break;
+    case ROMS_B200_OMEGA: case ROMS_B200_OMEGA2:
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_omega(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_WVELOCITY: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_wvelocity(q, f, h->nstp, st); }); h->launches += 1; break;
+    case ROMS_B200_SET_ZETA: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_zeta(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_PRE_STEP3D:
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_pre_step3d_t(q, f, st); });
+      launch_full(h, [&](const Par& q, cudaStream_t st) { launch_pre_step3d_uv(q, f, st); });
+      h->launches += 2; break;
+    case ROMS_B200_PRSGRD: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_prsgrd(q, f, h->cfg.dj_gradps, st); }); h->launches += h->cfg.dj_gradps ? 2 : 1; break;
     case ROMS_B200_T3DMIX:
       if (h->cfg.mix_geo_ts) {
-        if (!h->all_diff2_zero) { launch_t3dmix2_geo(p, f, s); h->launches += 1; }   // diff2 == 0: exact no-op
-      } else { launch_t3dmix2_s(p, f, s); h->launches += 1; }
+        if (!h->all_diff2_zero) { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix2_geo(q, f, st); }); h->launches += 1; }   // diff2 == 0: exact no-op
+      } else { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix2_s(q, f, st); }); h->launches += 1; }
       break;
-    case ROMS_B200_RHS3D: launch_rhs3d(p, f, s); h->launches += 1; break;
-    case ROMS_B200_UV3DMIX: launch_uv3dmix2(p, f, s); h->launches += 1; break;
-    case ROMS_B200_STEP2D: launch_step2d(p, f, s); h->launches += 1; break;
-    case ROMS_B200_SET_DEPTH: launch_set_depth(p, f, s); h->launches += 1; break;
-    case ROMS_B200_STEP3D_UV: launch_step3d_uv(p, f, s); h->launches += 2; break;
-    case ROMS_B200_STEP3D_T: launch_step3d_t(p, f, s); h->launches += 1; break;
-    case ROMS_B200_DIAG: launch_diag(p, f, h->d_diag_partial, h->d_diag_out, h->knew, s); h->launches += 3; break;
+    case ROMS_B200_RHS3D: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_rhs3d(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_UV3DMIX: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_uv3dmix2(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_STEP2D: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_step2d(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_SET_DEPTH: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_depth(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_STEP3D_UV: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_step3d_uv(q, f, st); }); h->launches += 2; break;
+    case ROMS_B200_STEP3D_T: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_step3d_t(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_DIAG: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_diag(q, f, h->d_diag_partial, h->d_diag_out, h->knew, st); }); h->launches += 3; break;
     case ROMS_B200_STEP2D_LOOP: {
       // main3d.F:592-700
+      auto sub_step = [&]() {
+        fill_par(h);
+        h->launches += 1;
+        return launch_with_halo(h, ROMS_B200_STEP2D, [&](const Par& q, cudaStream_t st) { launch_step2d(q, f, st); });
+      };
       for (int my_iif = 1; my_iif <= h->nfast + 1; ++my_iif) {
         const int next_indx1 = 3 - h->indx1;
         if (!h->predictor && my_iif <= h->nfast + 1) {
@@ -191,28 +242,27 @@ int run_phase_async(roms_b200_state* h, int phase) {
           h->kstp = (h->iif == 1) ? h->indx1 : 3 - h->indx1;
           h->knew = 3; h->krhs = h->indx1;
         }
-        if (my_iif <= h->nfast + 1) { fill_par(h); launch_step2d(h->par, f, s); h->launches += 1; if (phase_halo(h, ROMS_B200_STEP2D)) return FatalError; }
+        if (my_iif <= h->nfast + 1) { if (sub_step()) return FatalError; }
         if (h->predictor) {
           h->predictor = 0; h->knew = next_indx1; h->kstp = 3 - h->knew; h->krhs = 3;
           if (h->iif < h->nfast + 1) h->indx1 = next_indx1;
         }
-        if (h->iif < h->nfast + 1) { fill_par(h); launch_step2d(h->par, f, s); h->launches += 1; if (phase_halo(h, ROMS_B200_STEP2D)) return FatalError; }
+        if (h->iif < h->nfast + 1) { if (sub_step()) return FatalError; }
       }
       break;
     }
     default: return ConfigError;
   }
-  if (phase != ROMS_B200_STEP2D_LOOP && phase != ROMS_B200_DIAG) { if (phase_halo(h, phase)) return FatalError; }
+  if (rc) return FatalError;
   if (phase == ROMS_B200_DIAG && h->halo) { if (halo_reduce_diag(h)) return FatalError; }
+  if (h->profile) join_halo(h);      // per-phase timing: charge the exposed part of the exchange to its phase
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { std::fprintf(stderr, "roms_b200: launch error in phase %d: %s\n", phase, cudaGetErrorString(e)); return FatalError; }
   return NoError;
 }
 
 // main3d.F:189-917 for one step (without the first-step ini_zeta/ini_fields block and without get_data/output)
-int one_step(roms_b200_state* h, bool with_diag) {
-  h->nstp = 1 + ((h->iic - h->ntstart) % 2); h->nnew = 3 - h->nstp; h->nrhs = h->nstp;
-  h->tdays = h->time / 86400.0;
+int step_phases(roms_b200_state* h, bool with_diag) {
   static const int seq1[] = {ROMS_B200_SET_MASSFLUX, ROMS_B200_RHO_EOS};
   for (int ph : seq1) { int rc = run_phase_async(h, ph); if (rc) return rc; }
   if (with_diag) { int rc = run_phase_async(h, ROMS_B200_DIAG); if (rc) return rc; }
@@ -222,6 +272,54 @@ int one_step(roms_b200_state* h, bool with_diag) {
   static const int seq3[] = {ROMS_B200_SET_ZETA,  ROMS_B200_PRE_STEP3D, ROMS_B200_PRSGRD,    ROMS_B200_T3DMIX,   ROMS_B200_RHS3D, ROMS_B200_UV3DMIX,
                              ROMS_B200_STEP2D_LOOP, ROMS_B200_SET_DEPTH, ROMS_B200_STEP3D_UV, ROMS_B200_OMEGA2, ROMS_B200_STEP3D_T};
   for (int ph : seq3) { int rc = run_phase_async(h, ph); if (rc) return rc; }
+  join_halo(h);                      // the step ends with both streams joined (also required to end a graph capture)
+  return NoError;
+}
+
+// One baroclinic step.  After the two start-up steps (AB3 / LF-AM3 start-up branches) the launch sequence of a step
+// depends only on (nstp, indx1, with_diag): it is captured once per such state into a CUDA graph -- ~80 kernels on one
+// GPU, ~400 kernel / NCCL / event nodes on two streams with a ring attached -- and replayed afterwards, which removes
+// the host launch cost from the critical path (the barotropic sub-steps are ~10 us kernels on an 8-GPU tiling).
+int one_step(roms_b200_state* h, bool with_diag) {
+  h->nstp = 1 + ((h->iic - h->ntstart) % 2); h->nnew = 3 - h->nstp; h->nrhs = h->nstp;
+  h->tdays = h->time / 86400.0;
+  const bool steady = h->iic >= h->ntfirst + 2 && h->predictor == 0;
+  if (h->use_graphs && steady && !h->profile) {
+    const int key = h->nstp | (h->indx1 << 2) | ((with_diag ? 1 : 0) << 4);
+    auto it = h->graphs.find(key);
+    StepGraph* g = (it == h->graphs.end()) ? nullptr : (StepGraph*)it->second;
+    if (!g) {
+      const int s_indx1 = h->indx1, s_iif = h->iif, s_kstp = h->kstp, s_krhs = h->krhs, s_knew = h->knew, s_pred = h->predictor;
+      const long long l0 = h->launches;
+      cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+      bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+      int rc = ok ? step_phases(h, with_diag) : FatalError;
+      if (ok) ok = cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && graph != nullptr;
+      if (ok && rc == NoError) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      if (!ok || rc != NoError) {
+        // capture is not possible here (e.g. an NCCL build without graph support): go back to plain launches for good
+        cudaGetLastError();
+        std::fprintf(stderr, "roms_b200: CUDA graph capture of the time step failed; using stream launches\n");
+        h->use_graphs = 0;
+        h->indx1 = s_indx1; h->iif = s_iif; h->kstp = s_kstp; h->krhs = s_krhs; h->knew = s_knew; h->predictor = s_pred; h->launches = l0;
+        const int rc2 = step_phases(h, with_diag);
+        if (rc2) return rc2;
+        h->iic += 1; h->time += h->cfg.dt;
+        return NoError;
+      }
+      g = new StepGraph{exec, h->indx1, h->iif, h->kstp, h->krhs, h->knew, h->predictor, h->launches - l0};
+      h->graphs[key] = g;
+      h->launches = l0;
+    }
+    CK(cudaGraphLaunch(g->exec, h->stream));
+    h->indx1 = g->indx1; h->iif = g->iif; h->kstp = g->kstp; h->krhs = g->krhs; h->knew = g->knew; h->predictor = g->predictor;
+    h->launches += g->launches;
+    h->iic += 1; h->time += h->cfg.dt;
+    return NoError;
+  }
+  const int rc = step_phases(h, with_diag);
+  if (rc) return rc;
   h->iic += 1; h->time += h->cfg.dt;
   return NoError;
 }
@@ -318,6 +416,7 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   p.Istr = b.Istr; p.Iend = b.Iend; p.Jstr = b.Jstr; p.Jend = b.Jend; p.IstrU = b.IstrU; p.JstrV = b.JstrV; p.JstrR = b.JstrR; p.JendR = b.JendR;
   p.Jstrm1 = b.Jstrm1; p.Jendp1 = b.Jendp1; p.Jendp2 = b.Jendp2; p.JstrVm1 = b.JstrVm1; p.JstrVm2 = b.JstrVm2;
   p.ew_wrap = (cfg->NtileI == 1) ? 1 : 0;
+  p.gap_at = 0x7fffffff; p.gap_len = 0;
   p.nonlin_eos = cfg->nonlin_eos; p.curvgrid = cfg->curvgrid; p.uv_qdrag = cfg->uv_qdrag; p.salinity = cfg->salinity;
   p.hadv = cfg->hadv; p.vadv = cfg->vadv; p.itemp = cfg->itemp; p.isalt = cfg->isalt;
   p.dt = cfg->dt; p.g = cfg->g; p.rho0 = cfg->rho0; p.R0 = cfg->R0; p.T0 = cfg->T0; p.S0 = cfg->S0; p.Tcoef = cfg->Tcoef; p.Scoef = cfg->Scoef;
@@ -326,6 +425,7 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   h->dtfast = cfg->dt / (double)cfg->ndtfast;
   std::memset(h->phase_ms, 0, sizeof(h->phase_ms));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  { const char* ng = std::getenv("ROMS_B200_NO_GRAPH"); h->use_graphs = !(ng && ng[0] == '1'); }
   CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
   Flds& f = h->fl;
   std::memset(&f, 0, sizeof(f));
@@ -385,6 +485,7 @@ int roms_b200_destroy(roms_b200_handle h) {
   if (!h) return NoError;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  drop_graphs(h);
   halo_destroy(h);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_diag_out) cudaFreeHost(h->h_diag_out);
@@ -414,7 +515,7 @@ static int xfer(roms_b200_handle h, const char* name, double* host, size_t n, bo
   const size_t dp = (size_t)h->par.P * sizeof(double), sp = (size_t)h->ni * sizeof(double);
   if (up) CK(cudaMemcpy2DAsync(dev, dp, host, sp, sp, (size_t)h->nj * fi.nk, cudaMemcpyHostToDevice, h->stream));
   else CK(cudaMemcpy2DAsync(host, sp, dev, dp, sp, (size_t)h->nj * fi.nk, cudaMemcpyDeviceToHost, h->stream));
-  if (up && h->halo) { if (halo_exchange(h, {std::string(name)})) return FatalError; }
+  if (up && h->halo) { if (halo_exchange(h, {std::string(name)}, h->stream)) return FatalError; }
   CK(cudaStreamSynchronize(h->stream));
   if (up && std::strncmp(name, "diff2_", 6) == 0) {
     bool z = true;
@@ -437,6 +538,7 @@ int roms_b200_set_scoord(roms_b200_handle h, int which, const double* v, int n) 
 int roms_b200_set_weights(roms_b200_handle h, int nfast, const double* w1, const double* w2, int n) {
   if (!h || !w1 || !w2 || nfast < 1 || n < nfast + 2) return InputError;
   h->nfast = nfast; h->w1.assign(w1, w1 + n); h->w2.assign(w2, w2 + n);
+  drop_graphs(h);
   return NoError;
 }
 
@@ -444,6 +546,7 @@ int roms_b200_set_indices(roms_b200_handle h, const int* v, const double* tm) {
   if (!h || !v || !tm) return InputError;
   h->iic = v[0]; h->ntstart = v[1]; h->ntfirst = v[2]; h->nstp = v[3]; h->nnew = v[4]; h->nrhs = v[5]; h->iif = v[6]; h->indx1 = v[7];
   h->kstp = v[8]; h->krhs = v[9]; h->knew = v[10]; h->predictor = v[11]; h->exit_flag = v[12]; h->time = tm[0]; h->tdays = tm[1];
+  drop_graphs(h);
   return NoError;
 }
 int roms_b200_get_indices(roms_b200_handle h, int* v, double* tm) {
@@ -457,6 +560,7 @@ int roms_b200_run_phase(roms_b200_handle h, int phase) {
   if (!h) return InputError;
   CK(cudaSetDevice(h->cfg.device));
   int rc = run_phase_async(h, phase);
+  join_halo(h);
   if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));
   return NoError;
@@ -514,7 +618,7 @@ int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double*
   if (h->halo) {
     std::vector<std::string> up;
     for (int q = 0; q < 3; ++q) if (src[q]) up.push_back(nm[q]);
-    if (halo_exchange(h, up)) return FatalError;
+    if (halo_exchange(h, up, h->stream)) return FatalError;
   }
   int rc = one_step(h, true);
   if (rc) return rc;

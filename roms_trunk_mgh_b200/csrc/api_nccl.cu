@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "state.h"
 
 namespace rbi {
@@ -53,7 +54,18 @@ struct Halo {
   int rank = 0, nranks = 1, east = 0, west = 0;
   double *sendE = nullptr, *sendW = nullptr, *recvW = nullptr, *recvE = nullptr;   // device buffers
   size_t cap = 0;                                                                  // doubles per buffer (per ghost column count 1)
+  // NVLink peer path: every rank owns a mailbox (header + two parity slots of receive buffers) that its neighbours map
+  // through CUDA IPC and write into directly, so an exchange is one push kernel (remote stores + flag) and one unpack
+  // kernel (flag wait + local copy) -- no NCCL rendezvous on the critical path of the barotropic sub-steps.
+  double* box = nullptr; double* boxW = nullptr; double* boxE = nullptr;           // mine / west neighbour's / east neighbour's
+  void* mapW = nullptr; void* mapE = nullptr;                                      // IPC mappings to close
+  size_t box_cap = 0;                                                              // doubles per ghost column a slot can hold
+  bool peer_on = false;
 };
+
+constexpr int BOX_HDR = 64;                       // header doubles: [0] flagW [1] flagE [2] sent [3] rcvd [4],[5] block counters [6] error
+__host__ __device__ inline size_t box_slot(size_t cap) { return cap * (NW + NE); }
+__host__ __device__ inline size_t box_doubles(size_t cap) { return BOX_HDR + 2 * box_slot(cap); }
 
 struct FieldTab { double* p[MAXF]; int k0[MAXF]; int nk[MAXF]; int off[MAXF]; int n; };   // off = plane offset (in planes) in the buffer
 
@@ -69,9 +81,74 @@ __global__ void k_pack(FieldTab t, int P, int PL, int nj, int ic, int nc, int to
   if (unpack) *a = buf[idx]; else buf[idx] = *a;
 }
 
-int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names) {
+__device__ __forceinline__ double* field_elem(const FieldTab& t, int plane, int j, int i, int P, int PL) {
+  int fi = 0;
+  while (fi + 1 < t.n && plane >= t.off[fi + 1]) ++fi;
+  return t.p[fi] + i + j * P + (t.k0[fi] + (plane - t.off[fi])) * PL;
+}
+
+// Push both outgoing messages straight into the neighbours' mailboxes, then raise their flags.  Message layout as k_pack.
+__global__ void __launch_bounds__(256) k_halo_push(FieldTab t, int P, int PL, int nj, int Istr, int Iend, int totE, int totW, size_t cap,
+                                                   unsigned long long* hdr, double* boxE, double* boxW) {
+  const unsigned long long e = hdr[2] + 1;                  // epoch of this exchange (bumped by the last CTA below)
+  const size_t base = BOX_HDR + (e & 1) * box_slot(cap);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < totE) {                                         // my last NW columns -> east neighbour's west ghosts
+    const int c = idx % NW, r = idx / NW, j = r % nj, plane = r / nj;
+    boxE[base + idx] = *field_elem(t, plane, j, Iend - NW + 1 + c, P, PL);
+  } else if (idx < totE + totW) {                           // my first NE columns -> west neighbour's east ghosts
+    const int q = idx - totE;
+    const int c = q % NE, r = q / NE, j = r % nj, plane = r / nj;
+    boxW[base + cap * NW + q] = *field_elem(t, plane, j, Istr + c, P, PL);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(&hdr[4], 1ULL) == gridDim.x - 1) {        // last CTA: all remote stores are fenced
+      hdr[4] = 0; hdr[2] = e;
+      __threadfence_system();
+      *(volatile unsigned long long*)(boxE + 0) = e;        // east neighbour: "message from your west"
+      *(volatile unsigned long long*)(boxW + 1) = e;        // west neighbour: "message from your east"
+    }
+  }
+}
+
+// Wait for both incoming messages of this epoch, then copy them from the mailbox into the ghost columns.
+__global__ void __launch_bounds__(256) k_halo_unpack(FieldTab t, int P, int PL, int nj, int Istr, int Iend, int totE, int totW, size_t cap,
+                                                     unsigned long long* hdr, const double* box) {
+  const unsigned long long e = hdr[3] + 1;
+  if (threadIdx.x == 0) {
+    const volatile unsigned long long* fl = (const volatile unsigned long long*)hdr;
+    const long long t0 = clock64();
+    while (fl[0] < e || fl[1] < e) {
+      if (clock64() - t0 > (5LL << 30)) { hdr[6] = 1; break; }   // ~3 s: give up instead of hanging the GPU (host reports it)
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const size_t base = BOX_HDR + (e & 1) * box_slot(cap);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < totE) {                                         // from the west neighbour -> columns Istr-NW .. Istr-1
+    const int c = idx % NW, r = idx / NW, j = r % nj, plane = r / nj;
+    *field_elem(t, plane, j, Istr - NW + c, P, PL) = __ldcg(box + base + idx);
+  } else if (idx < totE + totW) {                           // from the east neighbour -> columns Iend+1 .. Iend+NE
+    const int q = idx - totE;
+    const int c = q % NE, r = q / NE, j = r % nj, plane = r / nj;
+    *field_elem(t, plane, j, Iend + 1 + c, P, PL) = __ldcg(box + base + cap * NW + q);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&hdr[5], 1ULL) == gridDim.x - 1) { hdr[5] = 0; hdr[3] = e; }
+  }
+}
+
+int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names, cudaStream_t s) {
   Halo* H = h->halo;
   if (!H || names.empty()) return 0;
+  static const int dbg_mode = [] { const char* e = std::getenv("ROMS_B200_XCHG_DEBUG"); return e ? std::atoi(e) : 0; }();   // timing experiments only
+  if (dbg_mode == 2) return 0;
   NcclApi& N = nccl();
   FieldTab t; t.n = 0; int planes = 0;
   for (const std::string& nm : names) {
@@ -82,6 +159,14 @@ int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names) {
   }
   const int nj = h->nj, P = h->par.P, PL = h->par.PL;
   const size_t need = (size_t)planes * nj;                       // doubles per ghost column
+  if (H->peer_on && need <= H->box_cap) {
+    const int totE = (int)need * NW, totW = (int)need * NE, tot = totE + totW;
+    unsigned long long* hdr = (unsigned long long*)H->box;
+    k_halo_push<<<(tot + 255) / 256, 256, 0, s>>>(t, P, PL, nj, h->b.Istr, h->b.Iend, totE, totW, H->box_cap, hdr, H->boxE, H->boxW);
+    k_halo_unpack<<<(tot + 255) / 256, 256, 0, s>>>(t, P, PL, nj, h->b.Istr, h->b.Iend, totE, totW, H->box_cap, hdr, H->box);
+    h->launches += 2;
+    return cudaGetLastError() == cudaSuccess ? 0 : 8;
+  }
   if (need > H->cap) {
     for (double** b : {&H->sendE, &H->sendW, &H->recvW, &H->recvE}) { if (*b) cudaFree(*b); *b = nullptr; }
     H->cap = need + need / 4;
@@ -89,19 +174,20 @@ int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names) {
         cudaMalloc(&H->sendW, H->cap * NE * sizeof(double)) != cudaSuccess || cudaMalloc(&H->recvE, H->cap * NE * sizeof(double)) != cudaSuccess)
       return 8;
   }
-  cudaStream_t s = h->stream;
   const int Istr = h->b.Istr, Iend = h->b.Iend;
   const int totE = (int)need * NW, totW = (int)need * NE;
   // eastward message: my last NW interior columns -> east neighbour's west ghosts; westward: my first NE columns
   k_pack<<<(totE + 255) / 256, 256, 0, s>>>(t, P, PL, nj, Iend - NW + 1, NW, totE, H->sendE, 0);
   k_pack<<<(totW + 255) / 256, 256, 0, s>>>(t, P, PL, nj, Istr, NE, totW, H->sendW, 0);
   int rc = 0;
+  if (dbg_mode != 1) {
   rc |= N.GroupStart();
   rc |= N.Send(H->sendE, (size_t)totE, ncclFloat64, H->east, H->comm, s);
   rc |= N.Recv(H->recvW, (size_t)totE, ncclFloat64, H->west, H->comm, s);
   rc |= N.Send(H->sendW, (size_t)totW, ncclFloat64, H->west, H->comm, s);
   rc |= N.Recv(H->recvE, (size_t)totW, ncclFloat64, H->east, H->comm, s);
   rc |= N.GroupEnd();
+  }
   if (rc) { std::fprintf(stderr, "roms_b200: NCCL error in halo_exchange\n"); return 8; }
   k_pack<<<(totE + 255) / 256, 256, 0, s>>>(t, P, PL, nj, Istr - NW, NW, totE, H->recvW, 1);
   k_pack<<<(totW + 255) / 256, 256, 0, s>>>(t, P, PL, nj, Iend + 1, NE, totW, H->recvE, 1);
@@ -120,13 +206,22 @@ int halo_reduce_diag(roms_b200_state* h) {
   return rc ? 8 : 0;
 }
 
+void drop_graphs(roms_b200_state* h) {
+  for (auto& kv : h->graphs) { StepGraph* g = (StepGraph*)kv.second; if (g) { cudaGraphExecDestroy(g->exec); delete g; } }
+  h->graphs.clear();
+}
+
 void halo_destroy(roms_b200_state* h) {
   Halo* H = h->halo;
   if (!H) return;
   for (double* b : {H->sendE, H->sendW, H->recvW, H->recvE}) if (b) cudaFree(b);
+  if (H->mapW) cudaIpcCloseMemHandle(H->mapW);
+  if (H->mapE && H->mapE != H->mapW) cudaIpcCloseMemHandle(H->mapE);
+  if (H->box) cudaFree(H->box);
   if (H->own_comm && H->comm && nccl().CommDestroy) nccl().CommDestroy(H->comm);
   delete H;
   h->halo = nullptr;
+  if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); cudaEventDestroy(h->ev_edge); cudaEventDestroy(h->ev_halo); cudaEventDestroy(h->ev_main); h->comm_stream = nullptr; }
 }
 
 }  // namespace rbi
@@ -164,15 +259,79 @@ int roms_b200_attach_nccl(roms_b200_handle h, void* nccl_comm, int rank, int nra
   Halo* H = new Halo();
   H->comm = (ncclComm_t)nccl_comm; H->rank = rank; H->nranks = nranks;
   H->east = (rank + 1) % nranks; H->west = (rank + nranks - 1) % nranks;
+  drop_graphs(h);
   h->halo = H;
+  if (!h->comm_stream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return 8;
+    cudaEventCreateWithFlags(&h->ev_edge, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming);
+  }
+  const char* no = std::getenv("ROMS_B200_NO_OVERLAP");
+  h->overlap = !(no && no[0] == '1');
   std::vector<std::string> batch;
   for (auto& kv : h->reg) {
     if (kv.first == "P3") continue;
     batch.push_back(kv.first);
-    if ((int)batch.size() == 8) { int rc = halo_exchange(h, batch); if (rc) return rc; batch.clear(); }
+    if ((int)batch.size() == 8) { int rc = halo_exchange(h, batch, h->stream); if (rc) return rc; batch.clear(); }
   }
-  if (!batch.empty()) { int rc = halo_exchange(h, batch); if (rc) return rc; }
+  if (!batch.empty()) { int rc = halo_exchange(h, batch, h->stream); if (rc) return rc; }
   return cudaStreamSynchronize(h->stream) == cudaSuccess ? 0 : 8;
+}
+
+// ---- NVLink peer path (optional; the NCCL path stays the fall-back) ---------------------------------------------
+// 1. every rank: roms_b200_peer_export -> 64-byte CUDA IPC handle of its mailbox; 2. exchange the handles (host side);
+// 3. roms_b200_peer_attach(west's, east's); 4. agree collectively that every rank succeeded; 5. roms_b200_peer_enable.
+int roms_b200_peer_export(roms_b200_handle h, char* out64) {
+  if (!h || !h->halo || !out64) return 2;
+  Halo* H = h->halo;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return 8;
+  if (!H->box) {
+    H->box_cap = (size_t)(4 * (h->cfg.N + 1) + 8) * h->nj;        // the largest per-step exchange (step3d_uv: 4N + 4 planes)
+    const size_t bytes = box_doubles(H->box_cap) * sizeof(double);
+    if (cudaMalloc(&H->box, bytes) != cudaSuccess) { cudaGetLastError(); return 8; }
+    if (cudaMemset(H->box, 0, bytes) != cudaSuccess) return 8;
+  }
+  cudaIpcMemHandle_t mh;
+  if (cudaIpcGetMemHandle(&mh, H->box) != cudaSuccess) { cudaGetLastError(); return 8; }
+  static_assert(sizeof(mh) == 64, "CUDA IPC handle size");
+  std::memcpy(out64, &mh, 64);
+  return 0;
+}
+
+int roms_b200_peer_attach(roms_b200_handle h, const char* west64, const char* east64) {
+  if (!h || !h->halo || !west64 || !east64) return 2;
+  Halo* H = h->halo;
+  if (!H->box) return 5;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return 8;
+  cudaIpcMemHandle_t mw, me;
+  std::memcpy(&mw, west64, 64); std::memcpy(&me, east64, 64);
+  if (cudaIpcOpenMemHandle(&H->mapW, mw, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); H->mapW = nullptr; return 8; }
+  if (std::memcmp(west64, east64, 64) == 0) H->mapE = H->mapW;        // two ranks: both neighbours are the same tile
+  else if (cudaIpcOpenMemHandle(&H->mapE, me, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); H->mapE = nullptr; return 8; }
+  H->boxW = (double*)H->mapW; H->boxE = (double*)H->mapE;
+  return 0;
+}
+
+int roms_b200_peer_enable(roms_b200_handle h, int on) {
+  if (!h || !h->halo) return 2;
+  Halo* H = h->halo;
+  if (on && !(H->box && H->boxW && H->boxE)) return 5;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return 8;
+  cudaStreamSynchronize(h->stream);
+  drop_graphs(h);
+  H->peer_on = on != 0;
+  return 0;
+}
+
+// 1 if a peer exchange timed out waiting for a neighbour (results are then invalid), else 0
+int roms_b200_peer_error(roms_b200_handle h) {
+  if (!h || !h->halo || !h->halo->box) return 0;
+  unsigned long long w = 0;
+  cudaMemcpy(&w, (unsigned long long*)h->halo->box + 6, sizeof(w), cudaMemcpyDeviceToHost);
+  return w != 0;
 }
 
 }  // extern "C"

@@ -24,6 +24,9 @@ struct Par {
   int JstrR, JendR;               // 0, Mm+1
   int Jstrm1, Jendp1, Jendp2, JstrVm1, JstrVm2;
   int ew_wrap;                    // 1: this tile owns the whole xi range -> periodic ghosts are filled by the producer
+  // Split launches (multi-GPU overlap): a launch covers columns Istr..Iend minus a gap of gap_len columns that starts
+  // gap_at columns after Istr.  Full launch: gap_len = 0.  "Edge" launch: the first and last EDGE_W columns of the tile.
+  int gap_at, gap_len;
   // stepping
   int nstp, nnew, nrhs;           // 1..2
   int istart;                     // 0: iic == ntfirst, 1: iic == ntfirst+1, 2: later
@@ -56,6 +59,12 @@ struct Flds {
   // 1-D (device)
   double *sc_r, *Cs_r, *sc_w, *Cs_w;
 };
+
+constexpr int EDGE_W = 64;        // width of the tile edges computed ahead of the halo exchange (multiple of every CTA width)
+// First column of the CTA whose columns start `off` columns into the launch (off is a multiple of the CTA width).
+__device__ __forceinline__ int xcol0(const Par& p, int off) { return p.Istr + off + ((off >= p.gap_at) ? p.gap_len : 0); }
+// Number of columns a launch covers (host side: grid sizing).
+__host__ __device__ inline int xspan(const Par& p) { return p.Iend - p.Istr + 1 - p.gap_len; }
 
 // ---- stores that also fill the periodic (xi) ghost images when this tile wraps onto itself -----------------------
 // exchange_2d.F / exchange_3d.F: A(Lm+1:Lm+2) = A(1:2), A(-2:0) = A(Lm-2:Lm)

@@ -8,7 +8,7 @@ namespace rb {
 // ---------------------------------------------------------------------------------------------------------------
 // set_massflux_tile (ROMS/Nonlinear/set_massflux.F:140-174).  One thread per (i,j,k).
 __global__ void __launch_bounds__(256) k_set_massflux(Par p, Flds f) {
-  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;          // 0..Mm+1
   const int k = 1 + blockIdx.z;
   if (i > p.Iend || j > p.Mm + 1) return;
@@ -62,7 +62,7 @@ __device__ __forceinline__ void eos_nl(double Tt, double Ts, double Tp, double& 
 }
 
 __global__ void __launch_bounds__(256) k_rho_eos(Par p, Flds f) {
-  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;          // JstrT..JendT = 0..Mm+1
   if (i > p.Iend || j > p.Mm + 1) return;
   const int o2 = j * p.P;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) k_rho_eos(Par p, Flds f) {
 // ---------------------------------------------------------------------------------------------------------------
 // set_vbc_tile (ROMS/Nonlinear/set_vbc.F:278-283, :340-355, :591-624 quadratic, :629-652 linear, BCs :657-662)
 __global__ void __launch_bounds__(256) k_set_vbc(Par p, Flds f) {
-  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;          // 0..Mm+1
   if (i > p.Iend || j > p.Mm + 1) return;
   const int o2 = j * p.P, o1 = o2 + p.PL;                       // k = 1
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) k_set_vbc(Par p, Flds f) {
 // omega_tile (ROMS/Nonlinear/omega.F:147-218).  Thread per column: upward prefix sum, then removal of the part
 // proportional to the barotropic divergence, then bc_w3d (gradient) + periodic images.
 __global__ void __launch_bounds__(128) k_omega(Par p, Flds f) {
-  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > p.Iend || j > p.Mm) return;
   const int o2 = j * p.P;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(128) k_omega(Par p, Flds f) {
 // ---------------------------------------------------------------------------------------------------------------
 // wvelocity_tile (ROMS/Nonlinear/wvelocity.F:156-256): diagnostic true vertical velocity at W-points.
 __global__ void __launch_bounds__(128) k_wvelocity(Par p, Flds f, int Ninp) {
-  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > p.Iend || j > p.Mm) return;
   const int o2 = j * p.P, P = p.P, N = p.N;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(128) k_wvelocity(Par p, Flds f, int Ninp) {
 // ---------------------------------------------------------------------------------------------------------------
 // set_zeta_tile (ROMS/Nonlinear/set_zeta.F:95-109)
 __global__ void __launch_bounds__(256) k_set_zeta(Par p, Flds f) {
-  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i > p.Iend || j > p.Mm + 1) return;
   const int o2 = j * p.P;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) k_set_zeta(Par p, Flds f) {
 // ---------------------------------------------------------------------------------------------------------------
 // set_depth_tile (ROMS/Nonlinear/set_depth.F:210-262, Vtransform = 2)
 __global__ void __launch_bounds__(256) k_set_depth(Par p, Flds f) {
-  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;          // 0..Mm+1
   if (i > p.Iend || j > p.Mm + 1) return;
   const int o2 = j * p.P;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) k_set_depth(Par p, Flds f) {
 // ---------------------------------------------------------------------------------------------------------------
 // ana_vmix (ROMS/Functionals/ana_vmix.h:200-208 Akv, :327-337 Akt; UPWELLING), k = 1..N-1
 __global__ void __launch_bounds__(256) k_ana_vmix(Par p, Flds f) {
-  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int k = 1 + blockIdx.z;
   if (i > p.Iend || j > p.Mm + 1) return;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) k_ana_vmix(Par p, Flds f) {
 
 // ---------------------------------------------------------------------------------------------------------------
 static inline dim3 g2(const Par& p, dim3 b, int nj, int nz = 1) {
-  return dim3((p.Iend - p.Istr + 1 + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz);
+  return dim3((xspan(p) + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz);
 }
 
 void launch_set_massflux(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_massflux<<<g2(p, b, p.Mm + 2, p.N), b, 0, s>>>(p, f); }

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(128) k_pre_step3d_t(Par p, Flds f) {
   // the tracer index is the fastest grid dimension: the CTAs of all tracers of one tile run back to back, so the shared
   // operands (Huon, Hvom, W, Hz, z_r) of the second tracer come from L2
   const int itrc = blockIdx.x % p.NT;
-  const int i = p.Istr + (blockIdx.x / p.NT) * blockDim.x + threadIdx.x;
+  const int i = xcol0(p, (blockIdx.x / p.NT) * blockDim.x) + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > p.Iend || j > p.Mm) return;
   const int N = p.N, P = p.P, o2 = j * P;
@@ -400,17 +400,19 @@ static inline dim3 g2(const Par& p, dim3 b, int ni, int nj, int nz = 1) { return
 
 template <int H>
 static void launch_pre_t_v(const Par& p, const Flds& f, cudaStream_t s) {
-  dim3 b(64, 2); dim3 g = g2(p, b, p.Iend - p.Istr + 1, p.Mm);
+  dim3 b(64, 2); dim3 g = g2(p, b, xspan(p), p.Mm);
   g.x *= p.NT;
   if (p.vadv == 0) k_pre_step3d_t<H, 0><<<g, b, 0, s>>>(p, f);
   else if (p.vadv == 1) k_pre_step3d_t<H, 1><<<g, b, 0, s>>>(p, f);
   else k_pre_step3d_t<H, 2><<<g, b, 0, s>>>(p, f);
 }
-void launch_pre_step3d(const Par& p, const Flds& f, cudaStream_t s) {
+void launch_pre_step3d_t(const Par& p, const Flds& f, cudaStream_t s) {
   if (p.hadv == 0) launch_pre_t_v<0>(p, f, s);
   else if (p.hadv == 1) launch_pre_t_v<1>(p, f, s);
   else if (p.hadv == 2) launch_pre_t_v<2>(p, f, s);
   else launch_pre_t_v<3>(p, f, s);
+}
+void launch_pre_step3d_uv(const Par& p, const Flds& f, cudaStream_t s) {
   dim3 b(64, 2);
   k_pre_step3d_uv<<<g2(p, b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
 }

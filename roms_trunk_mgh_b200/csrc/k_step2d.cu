@@ -33,7 +33,7 @@ constexpr int SH = TY + HL + HH;         // staged height (13)
 constexpr int ZW = TX + 1, ZH = TY + 1;  // flux / zeta regions: one extra column and row
 constexpr int NS = SW * SH, NZ = ZW * ZH;
 constexpr int SMEM_DOUBLES = 5 * NS + 17 * NZ;
-static_assert(NZ <= NTH && NS <= 2 * NTH, "tile / thread-count mismatch");
+static_assert(TX == 32 && TX * ZH + ZH <= NTH && NS <= 2 * NTH, "tile / thread-count mismatch");
 
 #ifndef S2D_MINB
 #define S2D_MINB 2
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
   // regions with origin (i0, j0): psi-point fluxes
   double* aUFe = vVFe + NZ; double* aVFx = aUFe + NZ; double* vUFe = aVFx + NZ; double* vVFx = vUFe + NZ;
   const int tid = threadIdx.x;
-  const int i0 = p.Istr + blockIdx.x * TX, j0 = blockIdx.y * TY;       // tile origin
+  const int i0 = xcol0(p, blockIdx.x * TX), j0 = blockIdx.y * TY;       // tile origin
   const int P = p.P, Mm = p.Mm;
   const bool PRED = p.predictor != 0;
   const bool FIRST = (p.iif == 1);
@@ -117,9 +117,13 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
 #define GYV(di, dj) (V_(di, (dj)-1) - 2.0 * V_(di, dj) + V_(di, (dj) + 1))
 #define GYDV(di, dj) (DV_(di, (dj)-1) - 2.0 * DV_(di, dj) + DV_(di, (dj) + 1))
 
-  if (active && tid < NZ) {
+  // Stage-2 thread map: warps 0..ZH-1 take one region row each (32 columns, so a warp never straddles a row: conflict-free
+  // 64-bit shared-memory accesses), the first ZH lanes of warp ZH take the 33rd column.
+  const int za = (tid < TX * ZH) ? (tid & (TX - 1)) : TX;
+  const int zb = (tid < TX * ZH) ? (tid / TX) : (tid - TX * ZH);
+  const int zi = zb * ZW + za;
+  if (active && tid < TX * ZH + ZH) {
     const double c6 = 1.0 / 6.0;
-    const int za = tid % ZW, zb = tid / ZW;
     // ---- stage 2a: rho-point quantities at (i0-1+za, j0-1+zb)
     {
       const int i = i0 - 1 + za, j = j0 - 1 + zb;
@@ -187,8 +191,8 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
           v_ufx = onr * onr * cr; v_vfe = omr * omr * cr;
         }
       }
-      sDnew[tid] = Dnew; sZw[tid] = zwrk; sG[tid] = gz; sG2[tid] = gz2; sGSA[tid] = gsa;
-      aUFx[tid] = a_ufx; aVFe[tid] = a_vfe; cUFx[tid] = c_ufx; cVFe[tid] = c_vfe; kUFx[tid] = k_ufx; kVFe[tid] = k_vfe; vUFx[tid] = v_ufx; vVFe[tid] = v_vfe;
+      sDnew[zi] = Dnew; sZw[zi] = zwrk; sG[zi] = gz; sG2[zi] = gz2; sGSA[zi] = gsa;
+      aUFx[zi] = a_ufx; aVFe[zi] = a_vfe; cUFx[zi] = c_ufx; cVFe[zi] = c_vfe; kUFx[zi] = k_ufx; kVFe[zi] = k_vfe; vUFx[zi] = v_ufx; vVFe[zi] = v_vfe;
     }
     // ---- stage 2b: psi-point fluxes at (i0+za, j0+zb)
     {
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
           v_ufe = omp * omp * cp; v_vfx = onp * onp * cp;
         }
       }
-      aUFe[tid] = a_ufe; aVFx[tid] = a_vfx; vUFe[tid] = v_ufe; vVFx[tid] = v_vfx;
+      aUFe[zi] = a_ufe; aVFx[zi] = a_vfx; vUFe[zi] = v_ufe; vVFx[zi] = v_vfx;
     }
   }
   __syncthreads();
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
 }
 
 void launch_step2d(const Par& p, const Flds& f, cudaStream_t s) {
-  dim3 g((p.Iend - p.Istr + 1 + TX - 1) / TX, (p.Mm + 2 + TY - 1) / TY);
+  dim3 g((xspan(p) + TX - 1) / TX, (p.Mm + 2 + TY - 1) / TY);
   const size_t smem = (size_t)SMEM_DOUBLES * sizeof(double);
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_step2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }

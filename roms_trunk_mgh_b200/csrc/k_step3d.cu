@@ -25,6 +25,7 @@ namespace rb {
 #endif
 constexpr int TS = S3D_TS;   // threads (columns) per block
 constexpr int CH = S3D_CH;   // levels per batch of independent loads in the downward / coupling passes
+static_assert(EDGE_W % TS == 0, "split launches need CTA widths that divide EDGE_W");
 
 // One forward-elimination step of the spline system for row m = k-1 once level k is known
 // (step3d_uv.F:344-375, step3d_t.F:1370-1405): h/o/AK suffix m = level k-1, k = level k, AKmm = AK(k-2).
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
   const int N = p.N;
   double* sA = sm + tid;                 // CF(k) -> x(k) -> hv(k)      slot (k-1)*TS
   double* sB = sm + N * TS + tid;        // DC(k) -> Hzk(k) -> d(k)
-  const int i = p.Istr + blockIdx.x * TS + tid;
+  const int i = xcol0(p, blockIdx.x * TS) + tid;
   const int j = (DIR ? 2 : 1) + blockIdx.y;                                // u: Jstr..Jend, v: JstrV..Jend
   if (i > p.Iend) return;
   const int P = p.P, Mm = p.Mm, PL = p.PL, o2 = j * P + i;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_t(Par p, Flds f) {
   double* sDC = sm + N * TS + tid;
   // tracer index fastest: the CTAs of all tracers of one tile run back to back and share Huon, Hvom, W, Hz through L2
   const int itrc = blockIdx.x % p.NT;
-  const int i = p.Istr + (blockIdx.x / p.NT) * TS + tid;
+  const int i = xcol0(p, (blockIdx.x / p.NT) * TS) + tid;
   const int j = 1 + blockIdx.y;
   if (i > p.Iend) return;
   const int P = p.P, PL = p.PL, o2 = j * P;
@@ -320,7 +321,7 @@ void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s) {
   const size_t sm = smem_cols(p.N);
   static size_t allowed = 0;
   if (sm > allowed) { allow_smem(k_step3d_uv<0>, sm); allow_smem(k_step3d_uv<1>, sm); allowed = sm; }
-  const int nbx = (p.Iend - p.Istr + 1 + TS - 1) / TS;
+  const int nbx = (xspan(p) + TS - 1) / TS;
   k_step3d_uv<0><<<dim3(nbx, p.Mm), TS, sm, s>>>(p, f);
   k_step3d_uv<1><<<dim3(nbx, p.Mm - 1), TS, sm, s>>>(p, f);
 }
@@ -330,7 +331,7 @@ static void launch_s3t(const Par& p, const Flds& f, cudaStream_t s) {
   const size_t sm = smem_cols(p.N);
   static size_t allowed = 0;
   if (sm > allowed) { allow_smem(k_step3d_t<H, V>, sm); allowed = sm; }
-  const int nbx = (p.Iend - p.Istr + 1 + TS - 1) / TS;
+  const int nbx = (xspan(p) + TS - 1) / TS;
   k_step3d_t<H, V><<<dim3(nbx * p.NT, p.Mm), TS, sm, s>>>(p, f);
 }
 template <int H>

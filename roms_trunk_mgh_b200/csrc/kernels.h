@@ -11,7 +11,8 @@ void launch_wvelocity(const Par& p, const Flds& f, int Ninp, cudaStream_t s);
 void launch_set_zeta(const Par& p, const Flds& f, cudaStream_t s);
 void launch_set_depth(const Par& p, const Flds& f, cudaStream_t s);
 void launch_ana_vmix(const Par& p, const Flds& f, cudaStream_t s);
-void launch_pre_step3d(const Par& p, const Flds& f, cudaStream_t s);
+void launch_pre_step3d_t(const Par& p, const Flds& f, cudaStream_t s);    // tracer predictor (halo-exchanged: split-launch aware)
+void launch_pre_step3d_uv(const Par& p, const Flds& f, cudaStream_t s);   // momentum loading
 void launch_prsgrd(const Par& p, const Flds& f, int dj_gradps, cudaStream_t s);
 void launch_t3dmix2_s(const Par& p, const Flds& f, cudaStream_t s);
 void launch_t3dmix2_geo(const Par& p, const Flds& f, cudaStream_t s);

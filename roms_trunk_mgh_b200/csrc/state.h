@@ -48,14 +48,29 @@ struct roms_b200_state {
   // profiling
   int profile = 0; double phase_ms[32]; long long launches = 0;
   bool all_diff2_zero = true;
-  // multi-GPU
+  // multi-GPU: ring context, and the second (high-priority) stream on which halo exchanges run while the tile interior is
+  // being computed on `stream` (api.cu launch_with_halo)
   rbi::Halo* halo = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_edge = nullptr, ev_halo = nullptr, ev_main = nullptr;
+  int overlap = 0;
+  bool edge_pending = false, halo_pending = false;   // main stream has not yet waited for the latest ev_edge / ev_halo
+  // CUDA graphs of whole time steps, keyed by the stepping state at the start of the step (api.cu one_step)
+  int use_graphs = 1;
+  std::map<int, void*> graphs;     // key -> rbi::StepGraph*
 };
 
 namespace rbi {
+// One captured time step (CUDA graph) and the host-side stepping state it leaves behind.
+struct StepGraph { cudaGraphExec_t exec; int indx1, iif, kstp, krhs, knew, predictor; long long launches; };
+}  // namespace rbi
+
+namespace rbi {
 // Halo exchange of the named fields along the xi ring (mp_exchange2d/3d/4d semantics); no-op without an attached comm.
-int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names);
+int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names, cudaStream_t s);
 // cross-tile reduction of the 16-double diag buffer: [0..2] sum, [3..12] max
 int halo_reduce_diag(roms_b200_state* h);
 void halo_destroy(roms_b200_state* h);
+// forget the captured time-step graphs (anything they bake in has changed: weights, stepping indices, the ring)
+void drop_graphs(roms_b200_state* h);
 }  // namespace rbi

@@ -6,6 +6,7 @@ the communicator to a Tile, (c) scatters / gathers whole global arrays for set-u
 numpy model of the ring exchange that the CPU (gloo) tests run.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -30,8 +31,9 @@ def broadcast_bytes(dist, payload, src=0):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def attach(tile, dist, rank, world):
-    """Create the NCCL ring communicator for `tile` (rank == tile index) and fill all ghost columns.  Collective."""
+def attach(tile, dist, rank, world, peer=True):
+    """Create the NCCL ring communicator for `tile` (rank == tile index) and fill all ghost columns; then, unless
+    peer=False or ROMS_B200_NO_PEER=1, move the exchanges to the NVLink peer path.  Collective."""
     L = tile.L
     idbuf = C.create_string_buffer(128)
     if rank == 0:
@@ -47,7 +49,33 @@ def attach(tile, dist, rank, world):
     if rc:
         raise RuntimeError(f"roms_b200_attach_nccl -> {rc}")
     tile._nccl_comm = comm
+    tile.peer = False
+    if peer and os.environ.get("ROMS_B200_NO_PEER") != "1":
+        tile.peer = enable_peer(tile, dist, rank, world)
     return comm
+
+
+def enable_peer(tile, dist, rank, world):
+    """Switch the ring exchanges of `tile` to the NVLink peer path (CUDA IPC mailboxes written by the neighbours' kernels).
+    Collective; falls back to NCCL send/recv on every rank unless every rank could map both neighbours.  Returns the mode."""
+    import torch
+    L = tile.L
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    hbuf = C.create_string_buffer(64)
+    ok = L.roms_b200_peer_export(tile.h, hbuf) == 0
+    mine = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8).to(dev)
+    allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    west, east = ring_neighbours(rank, world)
+    if ok:
+        ok = L.roms_b200_peer_attach(tile.h, bytes(allh[west].cpu().numpy().tobytes()), bytes(allh[east].cpu().numpy().tobytes())) == 0
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ok = bool(flag.item())
+    if ok:
+        ok = L.roms_b200_peer_enable(tile.h, 1) == 0
+    dist.barrier()
+    return ok
 
 
 def interior_columns(bounds):

@@ -23,6 +23,9 @@ def main():
     nsteps = int(sys.argv[4]) if len(sys.argv) >= 5 else 6
     t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, NtileI=world, tile=rank, device=local)
     multigpu.attach(t, dist, rank, world)
+    if rank == 0:
+        print(f"exchange path: {'NVLink peer mailboxes' if t.peer else 'NCCL send/recv'}; overlap={os.environ.get('ROMS_B200_NO_OVERLAP') != '1'}; "
+              f"graphs={os.environ.get('ROMS_B200_NO_GRAPH') != '1'}", flush=True)
     # redo the start-up phases now that ghosts can be exchanged (make_tile ran them before the ring existed)
     for ph in ("set_depth", "set_massflux", "omega", "rho_eos"):
         t.run_phase(ph)
@@ -56,8 +59,11 @@ def main():
         print("diag tiled :", {k: f"{v:.12e}" for k, v in d.items() if k in ("avgke", "avgpe", "volume", "max_speed")})
         print("diag single:", {k: f"{v:.12e}" for k, v in dr.items() if k in ("avgke", "avgpe", "volume", "max_speed")})
         print(f"MGPU_CHECK world={world} grid={Lm}x{Mm}x{N} steps={nsteps}:", "BITWISE-IDENTICAL" if ok else "FAILED", flush=True)
-    flag = torch.tensor([0 if ok else 1], device="cuda")
-    dist.broadcast(flag, 0)
+    perr = t.L.roms_b200_peer_error(t.h)
+    if perr:
+        print(f"rank {rank}: peer exchange timed out", flush=True)
+    flag = torch.tensor([0 if ok and not perr else 1], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
     dist.destroy_process_group()
     sys.exit(int(flag.item()))
 
