@@ -121,6 +121,12 @@ int roms_b200_sync(roms_b200_handle h);
 int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double* svstr, const double* stflux_temp,
                           size_t n2d, double* out12);
 int roms_b200_diag(roms_b200_handle h, double* out12);
+/* Pin a caller-owned host range (cudaHostRegister) so that roms_b200_step_forced copies from it directly instead of
+ * staging through the library's own pinned buffer.  Meant for the module arrays the Fortran host allocates once
+ * (FORCES(ng)%sustr/svstr/stflux, mod_forces.F:185-463): register after ROMS_allocate_arrays, the range must stay
+ * mapped until roms_b200_unregister_host / roms_b200_destroy. */
+int roms_b200_register_host(roms_b200_handle h, void* p, size_t bytes);
+int roms_b200_unregister_host(roms_b200_handle h, void* p);
 
 /* timing helpers for bench.py: elapsed device ms between two internal CUDA events bracketing the last
  * roms_b200_main3d_step call; per-phase accumulated device ms since the last reset (wclock regions, timers.F). */
@@ -136,8 +142,8 @@ int roms_b200_attach_nccl(roms_b200_handle h, void* nccl_comm, int rank, int nra
 int roms_b200_nccl_unique_id(char* out128);
 int roms_b200_nccl_init_rank(const char* id128, int rank, int nranks, void** comm_out);
 /* Optional NVLink peer path for the same exchanges (the NCCL path stays the fall-back): every tile owns a mailbox in HBM
- * that its two ring neighbours map through CUDA IPC and store into directly, so one exchange is a push kernel (remote
- * stores + flag) and an unpack kernel (flag wait + local copy) with no NCCL rendezvous -- what the ~118 small
+ * that its two ring neighbours map through CUDA IPC and store into directly, so one exchange is a single kernel (remote
+ * stores + flag, then flag wait + local copy) with no NCCL rendezvous -- what the ~118 small
  * mp_exchange2d calls of the barotropic loop (step2d_LF_AM3.h:586,884,924,2519) need.  Protocol, all ranks:
  * peer_export -> 64-byte IPC handle; exchange handles on the host; peer_attach(west's, east's); agree that every rank
  * succeeded; peer_enable(1).  peer_error returns 1 if a wait for a neighbour ever timed out (results invalid). */

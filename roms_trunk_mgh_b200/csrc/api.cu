@@ -324,6 +324,13 @@ int one_step(roms_b200_state* h, bool with_diag) {
   return NoError;
 }
 
+// true if [p, p+bytes) lies inside a host range the caller pinned with roms_b200_register_host
+bool is_registered(roms_b200_state* h, const void* p, size_t bytes) {
+  const char* a = (const char*)p;
+  for (auto& r : h->host_pinned) if (a >= (const char*)r.first && a + bytes <= (const char*)r.first + r.second) return true;
+  return false;
+}
+
 int finish_diag(roms_b200_state* h, double* out12) {
   CK(cudaMemcpyAsync(h->h_diag_out, h->d_diag_out, 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -490,6 +497,8 @@ int roms_b200_destroy(roms_b200_handle h) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_diag_out) cudaFreeHost(h->h_diag_out);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  for (auto& r : h->host_pinned) cudaHostUnregister(r.first);
+  h->host_pinned.clear();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -604,16 +613,25 @@ int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double*
   CK(cudaSetDevice(h->cfg.device));
   const size_t want = (size_t)h->ni * h->nj;
   if ((sustr || svstr || stflux_temp) && n2d != want) return InputError;
-  if (!h->h_pinned) { CK(cudaMallocHost(&h->h_pinned, 3 * want * sizeof(double))); h->pinned_n = want; }
+  if (!h->h_pinned) {
+    CK(cudaMallocHost(&h->h_pinned, 3 * want * sizeof(double))); h->pinned_n = want;
+    CK(cudaMalloc(&h->d_stage, 3 * want * sizeof(double))); h->allocs.push_back(h->d_stage);
+  }
   const size_t dp = (size_t)h->par.P * sizeof(double), sp = (size_t)h->ni * sizeof(double);
   const double* src[3] = {sustr, svstr, stflux_temp};
   const char* nm[3] = {"sustr", "svstr", "stflux_0"};
   for (int q = 0; q < 3; ++q) {
     if (!src[q]) continue;
-    double* stage = h->h_pinned + q * want;
-    std::memcpy(stage, src[q], want * sizeof(double));              // staged through pinned memory
+    const double* stage = src[q];
+    if (!is_registered(h, src[q], want * sizeof(double))) {         // pageable caller memory: stage through the pinned buffer
+      double* st = h->h_pinned + q * want;
+      std::memcpy(st, src[q], want * sizeof(double));
+      stage = st;
+    }
     double* dev = h->reg[nm[q]].base + h->ioff + (h->b.LBi - h->LBi_dev);
-    CK(cudaMemcpy2DAsync(dev, dp, stage, sp, sp, (size_t)h->nj, cudaMemcpyHostToDevice, h->stream));
+    // one dense DMA over PCIe, then the re-pitch on the device (a row-by-row 2-D copy from host memory is several times slower)
+    CK(cudaMemcpyAsync(h->d_stage + q * want, stage, want * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(dev, dp, h->d_stage + q * want, sp, sp, (size_t)h->nj, cudaMemcpyDeviceToDevice, h->stream));
   }
   if (h->halo) {
     std::vector<std::string> up;
@@ -623,6 +641,27 @@ int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double*
   int rc = one_step(h, true);
   if (rc) return rc;
   return finish_diag(h, out12);
+}
+
+int roms_b200_register_host(roms_b200_handle h, void* p, size_t bytes) {
+  if (!h || !p || !bytes) return InputError;
+  CK(cudaSetDevice(h->cfg.device));
+  if (is_registered(h, p, bytes)) return NoError;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return FatalError; }
+  h->host_pinned.emplace_back(p, bytes);
+  return NoError;
+}
+int roms_b200_unregister_host(roms_b200_handle h, void* p) {
+  if (!h || !p) return InputError;
+  for (size_t q = 0; q < h->host_pinned.size(); ++q) {
+    if (h->host_pinned[q].first == p) {
+      cudaStreamSynchronize(h->stream);
+      cudaHostUnregister(p);
+      h->host_pinned.erase(h->host_pinned.begin() + q);
+      return NoError;
+    }
+  }
+  return InputError;
 }
 
 int roms_b200_profile_enable(roms_b200_handle h, int on) {

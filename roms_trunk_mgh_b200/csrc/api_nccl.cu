@@ -55,16 +55,16 @@ struct Halo {
   double *sendE = nullptr, *sendW = nullptr, *recvW = nullptr, *recvE = nullptr;   // device buffers
   size_t cap = 0;                                                                  // doubles per buffer (per ghost column count 1)
   // NVLink peer path: every rank owns a mailbox (header + two parity slots of receive buffers) that its neighbours map
-  // through CUDA IPC and write into directly, so an exchange is one push kernel (remote stores + flag) and one unpack
-  // kernel (flag wait + local copy) -- no NCCL rendezvous on the critical path of the barotropic sub-steps.
+  // through CUDA IPC and write into directly, so an exchange is ONE kernel (remote stores + flag, flag wait + local
+  // copy: k_halo_xchg) -- no NCCL rendezvous on the critical path of the barotropic sub-steps.
   double* box = nullptr; double* boxW = nullptr; double* boxE = nullptr;           // mine / west neighbour's / east neighbour's
   void* mapW = nullptr; void* mapE = nullptr;                                      // IPC mappings to close
   size_t box_cap = 0;                                                              // doubles per ghost column a slot can hold
   bool peer_on = false;
 };
 
-constexpr int BOX_HDR = 64;                       // header doubles: [0] flagW [1] flagE [2] sent [3] rcvd [4],[5] block counters [6] error
-__host__ __device__ inline size_t box_slot(size_t cap) { return cap * (NW + NE); }
+constexpr int BOX_HDR = 64;                       // header doubles: [2] epoch [4] block counter [6] error
+__host__ __device__ inline size_t box_slot(size_t cap) { return 2 * cap * (NW + NE); }   // 16-byte line per double
 __host__ __device__ inline size_t box_doubles(size_t cap) { return BOX_HDR + 2 * box_slot(cap); }
 
 struct FieldTab { double* p[MAXF]; int k0[MAXF]; int nk[MAXF]; int off[MAXF]; int n; };   // off = plane offset (in planes) in the buffer
@@ -87,60 +87,54 @@ __device__ __forceinline__ double* field_elem(const FieldTab& t, int plane, int 
   return t.p[fi] + i + j * P + (t.k0[fi] + (plane - t.off[fi])) * PL;
 }
 
-// Push both outgoing messages straight into the neighbours' mailboxes, then raise their flags.  Message layout as k_pack.
-__global__ void __launch_bounds__(256) k_halo_push(FieldTab t, int P, int PL, int nj, int Istr, int Iend, int totE, int totW, size_t cap,
-                                                   unsigned long long* hdr, double* boxE, double* boxW) {
-  const unsigned long long e = hdr[2] + 1;                  // epoch of this exchange (bumped by the last CTA below)
-  const size_t base = BOX_HDR + (e & 1) * box_slot(cap);
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < totE) {                                         // my last NW columns -> east neighbour's west ghosts
-    const int c = idx % NW, r = idx / NW, j = r % nj, plane = r / nj;
-    boxE[base + idx] = *field_elem(t, plane, j, Iend - NW + 1 + c, P, PL);
-  } else if (idx < totE + totW) {                           // my first NE columns -> west neighbour's east ghosts
-    const int q = idx - totE;
-    const int c = q % NE, r = q / NE, j = r % nj, plane = r / nj;
-    boxW[base + cap * NW + q] = *field_elem(t, plane, j, Istr + c, P, PL);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    if (atomicAdd(&hdr[4], 1ULL) == gridDim.x - 1) {        // last CTA: all remote stores are fenced
-      hdr[4] = 0; hdr[2] = e;
-      __threadfence_system();
-      *(volatile unsigned long long*)(boxE + 0) = e;        // east neighbour: "message from your west"
-      *(volatile unsigned long long*)(boxW + 1) = e;        // west neighbour: "message from your east"
-    }
-  }
+// One exchange on the peer path is ONE kernel and uses no fences or separate flags: every double travels as a 16-byte
+// line {lo, tag, hi, tag} (tag = low 32 bits of the exchange epoch, the flag-in-data scheme of NCCL's LL protocol, which
+// only relies on 8-byte store atomicity over NVLink).  A thread (1) stores its outgoing line straight into the neighbour's
+// mailbox, then (2) spins on the line the neighbour stores into the own mailbox at the same position until both tags show
+// this epoch and copies the value into the ghost column.  Latency = one NVLink store flight.  Nothing a thread waits for
+// depends on another thread of this kernel (the neighbour's stores belong to its own, earlier-ordered work), so the spin
+// cannot deadlock.  Two parity slots suffice: a neighbour can only send epoch e+2 after it has received my epoch e+1, which
+// I send after my epoch-e kernel (including its unpack) has completed.
+__device__ __forceinline__ void ll_store(double* line, double v, unsigned tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"((unsigned)b), "r"(tag), "r"((unsigned)(b >> 32)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ bool ll_load(const double* line, unsigned tag, double& v) {
+  unsigned lo, t0, hi, t1;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(line) : "memory");
+  v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+  return t0 == tag && t1 == tag;
 }
 
-// Wait for both incoming messages of this epoch, then copy them from the mailbox into the ghost columns.
-__global__ void __launch_bounds__(256) k_halo_unpack(FieldTab t, int P, int PL, int nj, int Istr, int Iend, int totE, int totW, size_t cap,
-                                                     unsigned long long* hdr, const double* box) {
-  const unsigned long long e = hdr[3] + 1;
-  if (threadIdx.x == 0) {
-    const volatile unsigned long long* fl = (const volatile unsigned long long*)hdr;
-    const long long t0 = clock64();
-    while (fl[0] < e || fl[1] < e) {
-      if (clock64() - t0 > (5LL << 30)) { hdr[6] = 1; break; }   // ~3 s: give up instead of hanging the GPU (host reports it)
-      __nanosleep(64);
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
+__global__ void __launch_bounds__(256) k_halo_xchg(FieldTab t, int P, int PL, int nj, int Istr, int Iend, int totE, int totW, size_t cap,
+                                                   unsigned long long* hdr, double* box, double* boxE, double* boxW) {
+  const unsigned long long e = hdr[2] + 1;                  // epoch of this exchange (bumped by the last CTA below)
+  const unsigned tag = (unsigned)e;
   const size_t base = BOX_HDR + (e & 1) * box_slot(cap);
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < totE) {                                         // from the west neighbour -> columns Istr-NW .. Istr-1
-    const int c = idx % NW, r = idx / NW, j = r % nj, plane = r / nj;
-    *field_elem(t, plane, j, Istr - NW + c, P, PL) = __ldcg(box + base + idx);
-  } else if (idx < totE + totW) {                           // from the east neighbour -> columns Iend+1 .. Iend+NE
-    const int q = idx - totE;
-    const int c = q % NE, r = q / NE, j = r % nj, plane = r / nj;
-    *field_elem(t, plane, j, Iend + 1 + c, P, PL) = __ldcg(box + base + cap * NW + q);
+  const bool east = idx < totE, west = !east && idx < totE + totW;
+  const int q = east ? idx : idx - totE;
+  const int nc = east ? NW : NE;
+  const int c = q % nc, r = q / nc, j = r % nj, plane = r / nj;
+  const size_t slotW = base + 2 * (size_t)q;                          // line of element q in the "from the west" half
+  const size_t slotE = base + 2 * (cap * NW + (size_t)q);             // ... in the "from the east" half
+  if (east) ll_store(boxE + slotW, *field_elem(t, plane, j, Iend - NW + 1 + c, P, PL), tag);   // my last NW columns -> east neighbour's west ghosts
+  else if (west) ll_store(boxW + slotE, *field_elem(t, plane, j, Istr + c, P, PL), tag);       // my first NE columns -> west neighbour's east ghosts
+  if (east || west) {
+    const double* line = box + (east ? slotW : slotE);
+    double v;
+    const long long t0 = clock64();
+    while (!ll_load(line, tag, v)) {
+      if (clock64() - t0 > (5LL << 30)) { hdr[6] = 1; break; }        // ~3 s: give up instead of hanging the GPU (host reports it)
+      __nanosleep(20);
+    }
+    if (east) *field_elem(t, plane, j, Istr - NW + c, P, PL) = v;     // from the west neighbour
+    else *field_elem(t, plane, j, Iend + 1 + c, P, PL) = v;           // from the east neighbour
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(&hdr[5], 1ULL) == gridDim.x - 1) { hdr[5] = 0; hdr[3] = e; }
+    if (atomicAdd(&hdr[4], 1ULL) == gridDim.x - 1) { hdr[4] = 0; hdr[2] = e; }
   }
 }
 
@@ -162,9 +156,8 @@ int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names, cud
   if (H->peer_on && need <= H->box_cap) {
     const int totE = (int)need * NW, totW = (int)need * NE, tot = totE + totW;
     unsigned long long* hdr = (unsigned long long*)H->box;
-    k_halo_push<<<(tot + 255) / 256, 256, 0, s>>>(t, P, PL, nj, h->b.Istr, h->b.Iend, totE, totW, H->box_cap, hdr, H->boxE, H->boxW);
-    k_halo_unpack<<<(tot + 255) / 256, 256, 0, s>>>(t, P, PL, nj, h->b.Istr, h->b.Iend, totE, totW, H->box_cap, hdr, H->box);
-    h->launches += 2;
+    k_halo_xchg<<<(tot + 255) / 256, 256, 0, s>>>(t, P, PL, nj, h->b.Istr, h->b.Iend, totE, totW, H->box_cap, hdr, H->box, H->boxE, H->boxW);
+    h->launches += 1;
     return cudaGetLastError() == cudaSuccess ? 0 : 8;
   }
   if (need > H->cap) {

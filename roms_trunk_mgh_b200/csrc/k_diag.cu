@@ -57,21 +57,46 @@ __global__ void __launch_bounds__(128) k_diag_col(Par p, Flds f, double* __restr
   s[3 * ncol] = mC; s[4 * ncol] = mCu; s[5 * ncol] = mCv; s[6 * ncol] = mCw; s[7 * ncol] = mspeed; s[8 * ncol] = mrho;
 }
 
-// stage 2: one thread per i, collapse j in ascending order (diag.F:298-310)
-__global__ void k_diag_rows(Par p, const double* __restrict__ S, double* __restrict__ R) {
+// stage 2: one thread per i, collapse j in ascending order (diag.F:298-310).  The three sums keep the reference's order; their
+// operands are fetched RB rows at a time so that the loads of a batch are in flight together (the additions are the only
+// dependent chain).  The maxima are order-free apart from the first-maximum-wins rule of the Courant number.
+constexpr int RB = 8;
+__global__ void __launch_bounds__(64) k_diag_rows(Par p, const double* __restrict__ S, double* __restrict__ R) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   if (i > p.Iend) return;
   const int P = p.P, ncol = P * (p.Mm + 2);
+  const double* __restrict__ s0 = S + (i - p.Istr);
   double ke = 0.0, pe = 0.0, vol = 0.0, mC = 0.0, mCu = 0.0, mCv = 0.0, mCw = 0.0, msp = 0.0, mrho = -1.0e37;
   double umax = 0.0, vmax = 0.0, ubm = 0.0, vbm = 0.0;
-  for (int j = 0; j <= p.Mm + 1; ++j) {
-    const double* s = S + j * P + (i - p.Istr);
-    if (j >= 1 && j <= p.Mm) {
-      ke = ke + s[0]; pe = pe + s[ncol]; vol = vol + s[2 * ncol];
-      if (s[3 * ncol] > mC) { mC = s[3 * ncol]; mCu = s[4 * ncol]; mCv = s[5 * ncol]; mCw = s[6 * ncol]; }
-      msp = dmax(msp, s[7 * ncol]); mrho = dmax(mrho, s[8 * ncol]);
+  for (int jb = 1; jb <= p.Mm; jb += RB) {
+    double a[RB], b[RB], c[RB], d[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      const int j = min(jb + q, p.Mm);
+      a[q] = s0[j * P]; b[q] = s0[j * P + ncol]; c[q] = s0[j * P + 2 * ncol]; d[q] = s0[j * P + 3 * ncol];
     }
-    umax = dmax(umax, s[9 * ncol]); vmax = dmax(vmax, s[10 * ncol]); ubm = dmax(ubm, s[11 * ncol]); vbm = dmax(vbm, s[12 * ncol]);
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      if (jb + q <= p.Mm) {
+        ke = ke + a[q]; pe = pe + b[q]; vol = vol + c[q];
+        if (d[q] > mC) { const double* s = s0 + (jb + q) * P; mC = d[q]; mCu = s[4 * ncol]; mCv = s[5 * ncol]; mCw = s[6 * ncol]; }
+      }
+    }
+  }
+  for (int jb = 0; jb <= p.Mm + 1; jb += RB) {
+    double a[RB], b[RB], c[RB], d[RB], e[RB], g[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      const int j = min(jb + q, p.Mm + 1);
+      a[q] = s0[j * P + 7 * ncol]; b[q] = s0[j * P + 8 * ncol]; c[q] = s0[j * P + 9 * ncol]; d[q] = s0[j * P + 10 * ncol];
+      e[q] = s0[j * P + 11 * ncol]; g[q] = s0[j * P + 12 * ncol];
+    }
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      const int j = min(jb + q, p.Mm + 1);
+      if (j >= 1 && j <= p.Mm) { msp = dmax(msp, a[q]); mrho = dmax(mrho, b[q]); }
+      umax = dmax(umax, c[q]); vmax = dmax(vmax, d[q]); ubm = dmax(ubm, e[q]); vbm = dmax(vbm, g[q]);
+    }
   }
   double* r = R + (size_t)(i - p.Istr) * NDV;
   r[0] = ke; r[1] = pe; r[2] = vol; r[3] = mC; r[4] = mCu; r[5] = mCv; r[6] = mCw; r[7] = msp; r[8] = mrho;
@@ -79,19 +104,30 @@ __global__ void k_diag_rows(Par p, const double* __restrict__ S, double* __restr
 }
 
 // stage 3: sum over i in ascending order (diag.F:311-318).  out16 = avgke*vol, avgpe*vol, volume, maxC, Cu, Cv, Cw,
-// maxspeed, maxrho, umax, vmax, ubarmax, vbarmax  (tile-local; the caller finishes the division / cross-tile reduce)
-__global__ void k_diag_final(Par p, const double* __restrict__ R, double* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// maxspeed, maxrho, umax, vmax, ubarmax, vbarmax  (tile-local; the caller finishes the division / cross-tile reduce).
+// One CTA: all threads stage a chunk of R in shared memory (coalesced), thread 0 adds it up in the reference's order.
+constexpr int FCH = 256;
+__global__ void __launch_bounds__(256) k_diag_final(Par p, const double* __restrict__ R, double* __restrict__ out) {
+  __shared__ double sh[FCH * NDV];
   double ke = 0.0, pe = 0.0, vol = 0.0, mC = 0.0, mCu = 0.0, mCv = 0.0, mCw = 0.0, msp = 0.0, mrho = -1.0e37;
   double umax = 0.0, vmax = 0.0, ubm = 0.0, vbm = 0.0;
   const int ni = p.Iend - p.Istr + 1;
-  for (int q = 0; q < ni; ++q) {
-    const double* r = R + (size_t)q * NDV;
-    vol = vol + r[2]; pe = pe + r[1]; ke = ke + r[0];
-    if (r[3] > mC) { mC = r[3]; mCu = r[4]; mCv = r[5]; mCw = r[6]; }
-    msp = dmax(msp, r[7]); mrho = dmax(mrho, r[8]);
-    umax = dmax(umax, r[9]); vmax = dmax(vmax, r[10]); ubm = dmax(ubm, r[11]); vbm = dmax(vbm, r[12]);
+  for (int q0 = 0; q0 < ni; q0 += FCH) {
+    const int n = min(FCH, ni - q0);
+    __syncthreads();
+    for (int x = threadIdx.x; x < n * NDV; x += blockDim.x) sh[x] = R[(size_t)q0 * NDV + x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int q = 0; q < n; ++q) {
+        const double* r = sh + q * NDV;
+        vol = vol + r[2]; pe = pe + r[1]; ke = ke + r[0];
+        if (r[3] > mC) { mC = r[3]; mCu = r[4]; mCv = r[5]; mCw = r[6]; }
+        msp = dmax(msp, r[7]); mrho = dmax(mrho, r[8]);
+        umax = dmax(umax, r[9]); vmax = dmax(vmax, r[10]); ubm = dmax(ubm, r[11]); vbm = dmax(vbm, r[12]);
+      }
+    }
   }
+  if (threadIdx.x != 0) return;
   out[0] = ke; out[1] = pe; out[2] = vol; out[3] = mC; out[4] = mCu; out[5] = mCv; out[6] = mCw; out[7] = msp; out[8] = mrho;
   out[9] = umax; out[10] = vmax; out[11] = ubm; out[12] = vbm;
 }
@@ -105,8 +141,8 @@ void launch_diag(const Par& p, const Flds& f, double* partial, double* out16, in
   dim3 b(64, 2);
   dim3 g((p.Iend - p.Istr + 1 + b.x - 1) / b.x, (p.Mm + 2 + b.y - 1) / b.y);
   k_diag_col<<<g, b, 0, s>>>(p, f, Sq, knew);
-  k_diag_rows<<<(p.Iend - p.Istr + 1 + 127) / 128, 128, 0, s>>>(p, Sq, R);
-  k_diag_final<<<1, 32, 0, s>>>(p, R, out16);
+  k_diag_rows<<<(p.Iend - p.Istr + 1 + 63) / 64, 64, 0, s>>>(p, Sq, R);
+  k_diag_final<<<1, 256, 0, s>>>(p, R, out16);
 }
 
 }  // namespace rb

@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
   }
 }
 
-void launch_step2d(const Par& p, const Flds& f, cudaStream_t s) {
+// selected with ROMS_B200_STEP2D=tile (A/B measurements); the default is the row-marching kernel of k_step2d_m.cu
+void launch_step2d_tile(const Par& p, const Flds& f, cudaStream_t s) {
   dim3 g((xspan(p) + TX - 1) / TX, (p.Mm + 2 + TY - 1) / TY);
   const size_t smem = (size_t)SMEM_DOUBLES * sizeof(double);
   static bool once = false;

@@ -44,7 +44,8 @@ struct roms_b200_state {
   double dtfast = 0.0;
   // diag
   double* d_diag_partial = nullptr; double* d_diag_out = nullptr; double* h_diag_out = nullptr;
-  double* h_pinned = nullptr; size_t pinned_n = 0;
+  double* h_pinned = nullptr; size_t pinned_n = 0; double* d_stage = nullptr;
+  std::vector<std::pair<void*, size_t>> host_pinned;    // caller memory pinned with roms_b200_register_host
   // profiling
   int profile = 0; double phase_ms[32]; long long launches = 0;
   bool all_diff2_zero = true;

@@ -126,6 +126,14 @@ class Tile:
             raise RomsB200Error("step_forced", rc)
         return dict(zip(DIAG_NAMES, list(out))), rc
 
+    def register_host(self, *arrays):
+        """Pin caller-owned forcing arrays (they must outlive the Tile or be released with unregister_host): step_forced
+        then copies from them directly.  Mirrors what a Fortran host does once for FORCES(ng)%sustr, %svstr, %stflux."""
+        for a in arrays:
+            assert a.flags["C_CONTIGUOUS"] and a.dtype == np.float64
+            self._ck("register_host", self.L.roms_b200_register_host(self.h, a.ctypes.data, a.nbytes))
+            self._pinned = getattr(self, "_pinned", []) + [a]          # keep the arrays alive
+
     def diag(self):
         out = (C.c_double * 12)()
         rc = self.L.roms_b200_diag(self.h, out)
