@@ -110,6 +110,53 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+// Software-pipelined upward sweep over the levels of a column: level k+1 is requested before level k is computed.
+// body(cur, nxt, k): nxt is level k+1, or a copy of level N when k == N.
+// PINGPONG: the two level buffers swap roles every iteration (unrolled by two), which removes the register-to-register copy
+// of a whole level per iteration but keeps two bodies' worth of values live; measured per kernel (profiles/README.md), it
+// pays where the register budget has room (t3dmix2_s, step3d_uv) and costs spills where it has not (step3d_t, uv3dmix2).
+template <bool PINGPONG, class Load, class Body>
+__device__ __forceinline__ void sweep_levels(int N, Load load, Body body) {
+  if (!PINGPONG) {
+    auto cur = load(1);
+    for (int k = 1; k <= N; ++k) {
+      auto nxt = cur;
+      if (k < N) nxt = load(k + 1);
+      body(cur, nxt, k);
+      cur = nxt;
+    }
+  } else {
+    auto A = load(1);
+    int k = 1;
+    for (; k + 1 <= N; k += 2) {
+      auto B = load(k + 1);
+      body(A, B, k);
+      if (k + 2 <= N) A = load(k + 2); else A = B;
+      body(B, A, k + 1);
+    }
+    if (k <= N) body(A, A, k);
+  }
+}
+
+// The same sweep with D levels in flight (a ring of D level buffers, unrolled by D): for kernels whose levels are small, so
+// that one level ahead does not put enough bytes in flight to cover the DRAM latency.
+template <int D, class Load, class Body>
+__device__ __forceinline__ void sweep_levels_deep(int N, Load load, Body body) {
+  decltype(load(1)) buf[D];
+#pragma unroll
+  for (int q = 0; q < D; ++q) buf[q] = load((1 + q <= N) ? 1 + q : N);
+  for (int k = 1; k <= N; k += D) {
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      const int kk = k + q;
+      if (kk <= N) {
+        body(buf[q], (kk < N) ? buf[(q + 1) % D] : buf[q], kk);
+        if (kk + D <= N) buf[q] = load(kk + D);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }   // Fortran MAX (first arg on ties)
 __device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
 

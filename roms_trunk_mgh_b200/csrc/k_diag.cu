@@ -105,31 +105,49 @@ __global__ void __launch_bounds__(64) k_diag_rows(Par p, const double* __restric
 
 // stage 3: sum over i in ascending order (diag.F:311-318).  out16 = avgke*vol, avgpe*vol, volume, maxC, Cu, Cv, Cw,
 // maxspeed, maxrho, umax, vmax, ubarmax, vbarmax  (tile-local; the caller finishes the division / cross-tile reduce).
-// One CTA: all threads stage a chunk of R in shared memory (coalesced), thread 0 adds it up in the reference's order.
+// One CTA: all threads stage a chunk of R in shared memory (coalesced); thread 0 adds the three sums in the reference's
+// order, warp 1 reduces the maxima (order-free; the Courant number keeps the first maximum: larger value, then lower i).
 constexpr int FCH = 256;
 __global__ void __launch_bounds__(256) k_diag_final(Par p, const double* __restrict__ R, double* __restrict__ out) {
   __shared__ double sh[FCH * NDV];
-  double ke = 0.0, pe = 0.0, vol = 0.0, mC = 0.0, mCu = 0.0, mCv = 0.0, mCw = 0.0, msp = 0.0, mrho = -1.0e37;
-  double umax = 0.0, vmax = 0.0, ubm = 0.0, vbm = 0.0;
+  double ke = 0.0, pe = 0.0, vol = 0.0;
+  double mC = 0.0, msp = 0.0, mrho = -1.0e37, umax = 0.0, vmax = 0.0, ubm = 0.0, vbm = 0.0;
+  int iC = 0x7fffffff;
   const int ni = p.Iend - p.Istr + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q0 = 0; q0 < ni; q0 += FCH) {
     const int n = min(FCH, ni - q0);
     __syncthreads();
     for (int x = threadIdx.x; x < n * NDV; x += blockDim.x) sh[x] = R[(size_t)q0 * NDV + x];
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int q = 0; q < n; ++q) {
+      for (int q = 0; q < n; ++q) { const double* r = sh + q * NDV; vol = vol + r[2]; pe = pe + r[1]; ke = ke + r[0]; }
+    } else if (warp == 1) {
+      for (int q = lane; q < n; q += 32) {
         const double* r = sh + q * NDV;
-        vol = vol + r[2]; pe = pe + r[1]; ke = ke + r[0];
-        if (r[3] > mC) { mC = r[3]; mCu = r[4]; mCv = r[5]; mCw = r[6]; }
+        if (r[3] > mC) { mC = r[3]; iC = q0 + q; }
         msp = dmax(msp, r[7]); mrho = dmax(mrho, r[8]);
         umax = dmax(umax, r[9]); vmax = dmax(vmax, r[10]); ubm = dmax(ubm, r[11]); vbm = dmax(vbm, r[12]);
       }
     }
   }
-  if (threadIdx.x != 0) return;
-  out[0] = ke; out[1] = pe; out[2] = vol; out[3] = mC; out[4] = mCu; out[5] = mCv; out[6] = mCw; out[7] = msp; out[8] = mrho;
-  out[9] = umax; out[10] = vmax; out[11] = ubm; out[12] = vbm;
+  if (warp == 1) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const double oC = __shfl_xor_sync(0xffffffffu, mC, d); const int oi = __shfl_xor_sync(0xffffffffu, iC, d);
+      if (oC > mC || (oC == mC && oi < iC)) { mC = oC; iC = oi; }
+      msp = dmax(msp, __shfl_xor_sync(0xffffffffu, msp, d)); mrho = dmax(mrho, __shfl_xor_sync(0xffffffffu, mrho, d));
+      umax = dmax(umax, __shfl_xor_sync(0xffffffffu, umax, d)); vmax = dmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+      ubm = dmax(ubm, __shfl_xor_sync(0xffffffffu, ubm, d)); vbm = dmax(vbm, __shfl_xor_sync(0xffffffffu, vbm, d));
+    }
+    if (lane == 0) {
+      double mCu = 0.0, mCv = 0.0, mCw = 0.0;
+      if (mC > 0.0 && iC < ni) { const double* r = R + (size_t)iC * NDV; mCu = r[4]; mCv = r[5]; mCw = r[6]; }
+      out[3] = mC; out[4] = mCu; out[5] = mCv; out[6] = mCw; out[7] = msp; out[8] = mrho;
+      out[9] = umax; out[10] = vmax; out[11] = ubm; out[12] = vbm;
+    }
+  }
+  if (threadIdx.x == 0) { out[0] = ke; out[1] = pe; out[2] = vol; }
 }
 
 int diag_partial_doubles(const Par& p) { return NDV * p.P * (p.Mm + 2) + NDV * (p.Iend - p.Istr + 1); }

@@ -10,7 +10,19 @@ namespace rb {
 // continuity, :837-906 t(nnew) loading, :1126-1142 t3dbc + periodic images).  One thread per column and tracer; every
 // 3-D input is read once per level and both outputs are written once.
 template <int HADV, int VADV>
-__global__ void __launch_bounds__(128) k_pre_step3d_t(Par p, Flds f) {
+#ifndef PRT_PP
+#define PRT_PP false
+#endif
+#ifndef PRT_MINB
+#define PRT_MINB 3
+#endif
+#ifndef PRU_PP
+#define PRU_PP false
+#endif
+#ifndef PRU_MINB
+#define PRU_MINB 3
+#endif
+__global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
   // the tracer index is the fastest grid dimension: the CTAs of all tracers of one tile run back to back, so the shared
   // operands (Huon, Hvom, W, Hz, z_r) of the second tracer come from L2
   const int itrc = blockIdx.x % p.NT;
@@ -78,14 +90,7 @@ __global__ void __launch_bounds__(128) k_pre_step3d_t(Par p, Flds f) {
     tkm1 = tk; tk = tkp1; tkp1 = tkp2; tkp2 = nxt.tk3;
   };
   {
-    // level k+1 is requested before level k is computed
-    Lvl cur = load_level(1);
-    for (int k = 1; k <= N; ++k) {
-      Lvl nxt = cur;
-      if (k < N) nxt = load_level(k + 1);
-      level(cur, nxt, k);
-      cur = nxt;
-    }
+    sweep_levels<PRT_PP>(N, load_level, level);
   }
 }
 
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(128) k_pre_step3d_t(Par p, Flds f) {
 // pre_step3d_tile, momentum part (ROMS/Nonlinear/pre_step3d.F:917-1118): u,v(nnew) = Hz*u(nstp) + AB3 rhs + explicit
 // vertical viscosity flux divergence.  One thread per column, handles the u-point and the v-point of cell (i,j) in one
 // upward march so that Hz, z_r and Akv are read once; the operands of level k+1 are requested before level k is computed.
-__global__ void __launch_bounds__(128) k_pre_step3d_uv(Par p, Flds f) {
+__global__ void __launch_bounds__(128, PRU_MINB) k_pre_step3d_uv(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > p.Iend || j > p.Mm) return;
@@ -174,14 +179,7 @@ __global__ void __launch_bounds__(128) k_pre_step3d_uv(Par p, Flds f) {
     uk = cur.up; vk = cur.vp; zk0 = cur.zr0; zkW = cur.zrW; zkS = cur.zrS;
   };
   {
-    // level k+1 is requested before level k is computed
-    Lvl cur = load_level(1);
-    for (int k = 1; k <= N; ++k) {
-      Lvl nxt = cur;
-      if (k < N) nxt = load_level(k + 1);
-      level(cur, nxt, k);
-      cur = nxt;
-    }
+    sweep_levels<PRU_PP>(N, load_level, level);
   }
 }
 
@@ -384,14 +382,7 @@ __global__ void __launch_bounds__(128) k_t3dmix2_s(Par p, Flds f) {
     }
   };
   {
-    // level k+1 is requested before level k is computed
-    Lvl cur = load_level(1);
-    for (int k = 1; k <= N; ++k) {
-      Lvl nxt = cur;
-      if (k < N) nxt = load_level(k + 1);
-      level(cur, nxt, k);
-      cur = nxt;
-    }
+    sweep_levels<true>(N, load_level, level);
   }
 }
 

@@ -9,7 +9,9 @@ namespace rb {
 __device__ __forceinline__ double d2x(const double* __restrict__ A, int o) { return A[o - 1] - 2.0 * A[o] + A[o + 1]; }
 __device__ __forceinline__ double d2y(const double* __restrict__ A, int o, int P) { return A[o - P] - 2.0 * A[o] + A[o + P]; }
 
-// ROMS/Nonlinear/rhs3d.F:174-1671
+// ROMS/Nonlinear/rhs3d.F:174-1671.  (A variant that gave the xi- and eta-momentum equations of a column to two threads of the
+// same CTA -- half the live operands, 122 registers, twice the resident warps -- was exact but slower, 0.65 vs 0.56 ms: the
+// kernel is bound by L1 / issue throughput, and the split adds ~10% loads.  profiles/README.md.)
 #ifndef RHS_MINB
 #define RHS_MINB 2
 #endif
@@ -272,14 +274,7 @@ __global__ void __launch_bounds__(128, UVM_MINB) k_uv3dmix2(Par p, Flds f) {
     }
   };
   {
-    // level k+1 is requested before level k is computed
-    Lvl cur = load_level(1);
-    for (int k = 1; k <= N; ++k) {
-      Lvl nxt = cur;
-      if (k < N) nxt = load_level(k + 1);
-      level(cur, nxt, k);
-      cur = nxt;
-    }
+    sweep_levels<false>(N, load_level, level);
   }
   f.rufrc[o2] = rufrc;
   if (dov) f.rvfrc[o2] = rvfrc;

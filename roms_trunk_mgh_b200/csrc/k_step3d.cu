@@ -23,6 +23,18 @@ namespace rb {
 #ifndef S3D_MINB
 #define S3D_MINB 7
 #endif
+#ifndef S3U_DEPTH
+#define S3U_DEPTH 0        // levels in flight in pass 1 of k_step3d_uv (0: sweep_levels<S3U_PP>)
+#endif
+#ifndef S3U_PP
+#define S3U_PP true
+#endif
+#ifndef S3T_PP
+#define S3T_PP true      // ping-pong level buffers in k_step3d_t (see sweep_levels): pays once the register budget allows ~164
+#endif
+#ifndef S3T_MINB
+#define S3T_MINB 6
+#endif
 constexpr int TS = S3D_TS;   // threads (columns) per block
 constexpr int CH = S3D_CH;   // levels per batch of independent loads in the downward / coupling passes
 static_assert(EDGE_W % TS == 0, "split launches need CTA widths that divide EDGE_W");
@@ -95,14 +107,11 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
       }
       AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = xv;
     };
-    // level k+1 is requested before level k is computed
-    Lvl cur = load_level(1);
-    for (int k = 1; k <= N; ++k) {
-      Lvl nxt = cur;
-      if (k < N) nxt = load_level(k + 1);
-      level(cur, nxt, k);
-      cur = nxt;
-    }
+    #if S3U_DEPTH >= 2
+    sweep_levels_deep<S3U_DEPTH>(N, load_level, level);
+#else
+    sweep_levels<S3U_PP>(N, load_level, level);
+#endif
     AKN = AKm;
   }
   // ---- pass 2 (downward): back substitution fused with the update x(k) += dt*oHz(k)*(AK(k)*DC(k) - AK(k-1)*DC(k-1));
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
 // step3d_t_tile (ROMS/Nonlinear/step3d_t.F:388-876 horizontal advection of t(:,:,:,3,:), :883-1210 vertical advection,
 // :1366-1427 implicit diffusion, :1551-1621 t3dbc + periodic images).  One thread per column and tracer.
 template <int HADV, int VADV>
-__global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_t(Par p, Flds f) {
+__global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   const int N = p.N;
@@ -272,14 +281,7 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_t(Par p, Flds f) {
       AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = tv; FCm = FCk;
       tkm1 = tk; tk = tkp1; tkp1 = tkp2; tkp2 = nxt.tk3;
     };
-    // level k+1 is requested before level k is computed
-    Lvl cur = load_level(1);
-    for (int k = 1; k <= N; ++k) {
-      Lvl nxt = cur;
-      if (k < N) nxt = load_level(k + 1);
-      level(cur, nxt, k);
-      cur = nxt;
-    }
+    sweep_levels<S3T_PP>(N, load_level, level);
     AKN = AKm;
   }
   // ---- pass 2 (downward): back substitution + update + t3dbc / periodic images

@@ -206,3 +206,43 @@ def test_full_size_benchmark3_smoke():
     u = t.get("u1")
     assert np.array_equal(u[:, :, 0:3], u[:, :, 2048:2051])
     t.close()
+
+
+def _variant(case, nsteps, **env):
+    import subprocess
+    import sys
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_variant_check.py"), case, str(nsteps)],
+                       env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "VARIANT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    return [ln.split()[1] for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
+
+
+@pytest.mark.parametrize("case", ["seamount", "benchmark30", "wide"])
+def test_kernel_and_launch_variants_are_bit_exact(case):
+    """The row-marching step2d kernel (k_step2d_m.cu, both CTA widths) and plain stream launches (no CUDA graph) give the
+    same bits as the default path (tile kernel, graph replay) and as the oracle."""
+    ref = _variant(case, 6)
+    assert _variant(case, 6, ROMS_B200_STEP2D="march") == ref
+    assert _variant(case, 6, ROMS_B200_STEP2D="march", ROMS_B200_S2M_TX="64", ROMS_B200_S2M_JL="5") == ref
+    assert _variant(case, 6, ROMS_B200_NO_GRAPH="1") == ref
+
+
+def test_step_forced_from_registered_host_memory():
+    """roms_b200_register_host: forcing copied straight from pinned caller memory gives the same step as the staged copy."""
+    app, kw = CASES["benchmark"]
+    res = []
+    for registered in (False, True):
+        o, t = make_pair(app, strict=True, **kw)
+        su = np.ascontiguousarray(o.field("sustr")) * 1.25
+        sv = np.ascontiguousarray(o.field("svstr")) + 1e-5
+        if registered:
+            t.register_host(su, sv)
+        for _ in range(3):
+            d, rc = t.step_forced(su, sv, None)
+            assert rc == 0
+        res.append(({n: t.get(n) for n in ("zeta1", "u1", "v2", "t1_0")}, d))
+        t.close()
+    for n in res[0][0]:
+        assert np.array_equal(res[0][0][n], res[1][0][n]), n
+    assert res[0][1] == res[1][1]
