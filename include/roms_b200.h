@@ -176,6 +176,24 @@ int roms_b200_omega_tile(const roms_b200_tile_t* b, const double* Huon, const do
 int roms_b200_set_depth_tile(const roms_b200_tile_t* b, const double* h, const double* Zt_avg1, const double* sc_r,
                              const double* Cs_r, const double* sc_w, const double* Cs_w, double* Hz, double* z_r, double* z_w);
 
+
+/* ---- generic per-routine form: every routine of the chain ------------------------------------------------------ */
+/* The remaining _tile routines (set_vbc.F:104, wvelocity.F:61, set_zeta.F:59, pre_step3d.F:123, t3dmix2_s.h:89 /
+ * t3dmix2_geo.h:90, rhs3d.F:174, uv3dmix2_s.h:114, step2d_LF_AM3.h:137, step3d_uv.F:111, step3d_t.F:108, ana_vmix.h)
+ * take 20-70 whole arrays each; this entry point passes them by NAME (the names of roms_b200_set_field: the members of
+ * OCEAN/GRID/COUPLING/MIXING/FORCES, time level spelled out, tracer index as suffix _0, _1) instead of by position.
+ * phase = a ROMS_B200_* routine id; mode[i]: 1 input, 2 output (current content uploaded first, so untouched elements
+ * are preserved like an INTENT(inout) dummy), 3 both; every array is the whole Fortran array (LBi:UBi,LBj:UBj[,k]).
+ * scoord4 = sc_r, Cs_r, sc_w, Cs_w (N+1 entries each, set_depth only, else NULL); weight1/weight2 = weight(1,:),
+ * weight(2,:) of set_weights.F with nweight entries each and nfast (step2d only, else NULL).  Nothing is retained. */
+int roms_b200_routine_tile(const roms_b200_tile_t* b, int phase, int nargs, const char* const* names, double* const* arrays,
+                           const int* mode, const double* scoord4, int nfast, const double* weight1, const double* weight2,
+                           int nweight);
+/* "in:<comma-separated names>;out:<names>" a routine needs (`*` = one entry per tracer), NULL for an unknown phase */
+const char* roms_b200_routine_args(int phase);
+/* vertical extent of a named field: first level (0 or 1) and number of planes (1, N or N+1) */
+int roms_b200_field_levels(roms_b200_handle h, const char* name, int* LBk, int* nk);
+
 #ifdef __cplusplus
 }
 #endif

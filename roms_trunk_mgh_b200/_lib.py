@@ -44,7 +44,7 @@ EXPORTS = ["roms_b200_default_config", "roms_b200_bounds", "roms_b200_bounds_nam
            "roms_b200_launch_count", "roms_b200_attach_nccl", "roms_b200_nccl_unique_id", "roms_b200_nccl_init_rank",
            "roms_b200_peer_export", "roms_b200_peer_attach", "roms_b200_peer_enable", "roms_b200_peer_error",
            "roms_b200_rho_eos_tile", "roms_b200_prsgrd_tile", "roms_b200_set_massflux_tile", "roms_b200_omega_tile",
-           "roms_b200_set_depth_tile"]
+           "roms_b200_set_depth_tile", "roms_b200_routine_tile", "roms_b200_routine_args", "roms_b200_field_levels"]
 
 _cache = {}
 DP = C.POINTER(C.c_double)
@@ -105,6 +105,10 @@ def load(strict=False):
     L.roms_b200_set_massflux_tile.argtypes = [TP] + [DP] * 7
     L.roms_b200_omega_tile.argtypes = [TP] + [DP] * 4
     L.roms_b200_set_depth_tile.argtypes = [TP] + [DP] * 9
+    L.roms_b200_routine_tile.argtypes = [TP, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(DP), IP, DP, C.c_int, DP, DP, C.c_int]
+    L.roms_b200_routine_args.argtypes = [C.c_int]
+    L.roms_b200_routine_args.restype = C.c_char_p
+    L.roms_b200_field_levels.argtypes = [H, C.c_char_p, IP, IP]
     _cache[key] = L
     return L
 

@@ -84,12 +84,26 @@ void make_bounds(int Lm, int Mm, int NtileI, int NtileJ, int tile, bool distribu
 
 namespace {
 
+// 2-D fields every step2d call reads or writes and that change during the barotropic loop
+bool is_hot2d(const std::string& n) {
+  static const char* k[] = {"zeta1", "zeta2", "zeta3", "ubar1", "ubar2", "ubar3", "vbar1", "vbar2", "vbar3", "rzeta1", "rzeta2", "rubar1", "rubar2",
+                            "rvbar1", "rvbar2", "Zt_avg1", "DU_avg1", "DU_avg2", "DV_avg1", "DV_avg2"};
+  for (const char* s : k) if (n == s) return true;
+  return false;
+}
+constexpr int NHOT2D = 20;
+
 int alloc_field(roms_b200_state* h, const std::string& name, double** slot, int LBk, int nk) {
   const size_t n = (size_t)h->par.PL * nk;
   double* base = nullptr;
-  CK(cudaMalloc(&base, n * sizeof(double)));
+  const size_t bytes = ((n * sizeof(double) + 255) / 256) * 256;
+  if (nk == 1 && h->hot_arena && is_hot2d(name) && h->hot_used + bytes <= h->hot_cap) {
+    base = (double*)(h->hot_arena + h->hot_used); h->hot_used += bytes;
+  } else {
+    CK(cudaMalloc(&base, n * sizeof(double)));
+    h->allocs.push_back(base);
+  }
   CK(cudaMemsetAsync(base, 0, n * sizeof(double), h->stream));
-  h->allocs.push_back(base);
   // element (i,j,k) lives at base[(i-LBi+ioff) + (j-LBj)*P + (k-LBk)*PL]
   *slot = base + h->ioff - h->LBi_dev - (ptrdiff_t)h->b.LBj * h->par.P - (ptrdiff_t)LBk * h->par.PL;
   h->reg[name] = FieldInfo{slot, LBk, nk, base};
@@ -194,6 +208,23 @@ int launch_with_halo(roms_b200_state* h, int phase, F fn) {
   return rc;
 }
 
+// L2 residency of the barotropic state (ROMS_B200_L2PERSIST=<MB>, 0 = off): while the step2d loop runs, accesses to the hot
+// arena are marked persisting so the time-varying 2-D fields are served from L2 between sub-steps instead of being evicted by
+// the streamed static metric arrays.
+void l2_window(roms_b200_state* h, cudaStream_t s, bool on) {
+  if (!h->l2_window_bytes || !s) return;
+  cudaStreamAttrValue a;
+  std::memset(&a, 0, sizeof(a));
+  a.accessPolicyWindow.base_ptr = h->hot_arena;
+  a.accessPolicyWindow.num_bytes = on ? h->l2_window_bytes : 0;
+  a.accessPolicyWindow.hitRatio = on ? h->l2_hit : 0.f;
+  a.accessPolicyWindow.hitProp = on ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+  a.accessPolicyWindow.missProp = on ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+  cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a);
+}
+
+bool fused_tmix(const roms_b200_state* h) { return h->in_step && h->fuse_tmix && !h->cfg.mix_geo_ts; }
+
 int run_phase_async(roms_b200_state* h, int phase) {
   fill_par(h);
   const Par& p = h->par; const Flds& f = h->fl; cudaStream_t s = h->stream;
@@ -212,11 +243,14 @@ int run_phase_async(roms_b200_state* h, int phase) {
     case ROMS_B200_WVELOCITY: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_wvelocity(q, f, h->nstp, st); }); h->launches += 1; break;
     case ROMS_B200_SET_ZETA: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_zeta(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_PRE_STEP3D:
+      h->par.fuse_tmix = fused_tmix(h) ? 1 : 0;
       rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_pre_step3d_t(q, f, st); });
+      h->par.fuse_tmix = 0;
       launch_full(h, [&](const Par& q, cudaStream_t st) { launch_pre_step3d_uv(q, f, st); });
       h->launches += 2; break;
     case ROMS_B200_PRSGRD: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_prsgrd(q, f, h->cfg.dj_gradps, st); }); h->launches += h->cfg.dj_gradps ? 2 : 1; break;
     case ROMS_B200_T3DMIX:
+      if (fused_tmix(h)) break;                                                     // already applied by pre_step3d_t
       if (h->cfg.mix_geo_ts) {
         if (!h->all_diff2_zero) { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix2_geo(q, f, st); }); h->launches += 1; }   // diff2 == 0: exact no-op
       } else { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix2_s(q, f, st); }); h->launches += 1; }
@@ -235,6 +269,7 @@ int run_phase_async(roms_b200_state* h, int phase) {
         h->launches += 1;
         return launch_with_halo(h, ROMS_B200_STEP2D, [&](const Par& q, cudaStream_t st) { launch_step2d(q, f, st); });
       };
+      l2_window(h, h->stream, true); l2_window(h, h->comm_stream, true);
       for (int my_iif = 1; my_iif <= h->nfast + 1; ++my_iif) {
         const int next_indx1 = 3 - h->indx1;
         if (!h->predictor && my_iif <= h->nfast + 1) {
@@ -249,6 +284,7 @@ int run_phase_async(roms_b200_state* h, int phase) {
         }
         if (h->iif < h->nfast + 1) { if (sub_step()) return FatalError; }
       }
+      l2_window(h, h->stream, false); l2_window(h, h->comm_stream, false);
       break;
     }
     default: return ConfigError;
@@ -261,8 +297,45 @@ int run_phase_async(roms_b200_state* h, int phase) {
   return NoError;
 }
 
+// Stream attributes are meant to be inherited by captured kernel nodes; if this driver did not do so, give every kernel
+// node of the step the window explicitly (kernels outside the barotropic loop hardly touch the arena).
+void apply_l2_window_to_graph(roms_b200_state* h, cudaGraph_t graph) {
+  size_t n = 0;
+  if (cudaGraphGetNodes(graph, nullptr, &n) != cudaSuccess || n == 0) { cudaGetLastError(); return; }
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (cudaGraphGetNodes(graph, nodes.data(), &n) != cudaSuccess) { cudaGetLastError(); return; }
+  size_t have = 0, kernels = 0;
+  for (cudaGraphNode_t nd : nodes) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nd, &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
+    ++kernels;
+    cudaKernelNodeAttrValue v; std::memset(&v, 0, sizeof(v));
+    if (cudaGraphKernelNodeGetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &v) == cudaSuccess && v.accessPolicyWindow.num_bytes > 0) ++have;
+  }
+  cudaGetLastError();
+  static bool said = false;
+  if (!said) { std::fprintf(stderr, "roms_b200: graph capture: %zu of %zu kernel nodes inherited the L2 window\n", have, kernels); said = true; }
+  if (have > 0) return;
+  cudaKernelNodeAttrValue v; std::memset(&v, 0, sizeof(v));
+  v.accessPolicyWindow.base_ptr = h->hot_arena; v.accessPolicyWindow.num_bytes = h->l2_window_bytes; v.accessPolicyWindow.hitRatio = h->l2_hit;
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  for (cudaGraphNode_t nd : nodes) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nd, &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
+    cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &v);
+  }
+  cudaGetLastError();
+}
+
 // main3d.F:189-917 for one step (without the first-step ini_zeta/ini_fields block and without get_data/output)
+int step_phases_body(roms_b200_state* h, bool with_diag);
 int step_phases(roms_b200_state* h, bool with_diag) {
+  h->in_step = true;
+  const int rc = step_phases_body(h, with_diag);
+  h->in_step = false;
+  return rc;
+}
+int step_phases_body(roms_b200_state* h, bool with_diag) {
   static const int seq1[] = {ROMS_B200_SET_MASSFLUX, ROMS_B200_RHO_EOS};
   for (int ph : seq1) { int rc = run_phase_async(h, ph); if (rc) return rc; }
   if (with_diag) { int rc = run_phase_async(h, ROMS_B200_DIAG); if (rc) return rc; }
@@ -295,6 +368,7 @@ int one_step(roms_b200_state* h, bool with_diag) {
       bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
       int rc = ok ? step_phases(h, with_diag) : FatalError;
       if (ok) ok = cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && graph != nullptr;
+      if (ok && rc == NoError && h->l2_window_bytes) apply_l2_window_to_graph(h, graph);
       if (ok && rc == NoError) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
       if (graph) cudaGraphDestroy(graph);
       if (!ok || rc != NoError) {
@@ -433,11 +507,33 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   std::memset(h->phase_ms, 0, sizeof(h->phase_ms));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   { const char* ng = std::getenv("ROMS_B200_NO_GRAPH"); h->use_graphs = !(ng && ng[0] == '1'); }
+  { const char* e = std::getenv("ROMS_B200_FUSE_TMIX"); h->fuse_tmix = !(e && e[0] == '0'); }
   CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
   Flds& f = h->fl;
   std::memset(&f, 0, sizeof(f));
   const int N = cfg->N;
   int rc = 0;
+  {
+    const char* e = std::getenv("ROMS_B200_L2PERSIST");
+    const long want_mb = e ? std::atol(e) : 0;
+    if (want_mb > 0) {
+      const size_t per = (((size_t)p.PL * sizeof(double) + 255) / 256) * 256;
+      h->hot_cap = per * NHOT2D;
+      if (cudaMalloc(&h->hot_arena, h->hot_cap) == cudaSuccess) {
+        h->allocs.push_back(h->hot_arena);
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cfg->device);
+        size_t setaside = std::min((size_t)want_mb << 20, (size_t)max_persist);
+        if (setaside > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside) == cudaSuccess) {
+          h->l2_window_bytes = std::min(h->hot_cap, (size_t)max_window);
+          h->l2_hit = (float)std::min(1.0, (double)setaside / (double)h->l2_window_bytes);
+        } else cudaGetLastError();
+        std::fprintf(stderr, "roms_b200: L2 persistence: arena %.1f MB, set-aside %.1f MB (device max %.1f MB), window %.1f MB, hitRatio %.2f\n",
+                     h->hot_cap / 1048576.0, setaside / 1048576.0, max_persist / 1048576.0, h->l2_window_bytes / 1048576.0, h->l2_hit);
+      } else { cudaGetLastError(); h->hot_arena = nullptr; h->hot_cap = 0; }
+    }
+  }
 #define A2(name) rc |= alloc_field(h, #name, &f.name, 0, 1)
 #define A3(name, k0, nk) rc |= alloc_field(h, #name, &f.name, k0, nk)
   A2(h); A2(f); A2(pm); A2(pn); A2(om_r); A2(on_r); A2(om_u); A2(on_u); A2(om_v); A2(on_v); A2(om_p); A2(on_p); A2(omn); A2(fomn);
@@ -535,6 +631,15 @@ static int xfer(roms_b200_handle h, const char* name, double* host, size_t n, bo
 }
 int roms_b200_set_field(roms_b200_handle h, const char* name, const double* host, size_t n) { return xfer(h, name, const_cast<double*>(host), n, true); }
 int roms_b200_get_field(roms_b200_handle h, const char* name, double* host, size_t n) { return xfer(h, name, host, n, false); }
+
+int roms_b200_field_levels(roms_b200_handle h, const char* name, int* LBk, int* nk) {
+  if (!h || !name) return InputError;
+  auto it = h->reg.find(name);
+  if (it == h->reg.end()) return InputError;
+  if (LBk) *LBk = it->second.LBk;
+  if (nk) *nk = it->second.nk;
+  return NoError;
+}
 
 int roms_b200_set_scoord(roms_b200_handle h, int which, const double* v, int n) {
   if (!h || !v || which < 0 || which > 3 || n < h->cfg.N + 1 || n > MAXN + 1) return InputError;

@@ -106,4 +106,76 @@ int roms_b200_set_depth_tile(const roms_b200_tile_t* b, const double* h, const d
   return T.rc;
 }
 
+// ---- generic form: any routine of the chain -----------------------------------------------------------------------
+// The dummy-argument lists of the remaining _tile routines run to 40-70 whole arrays (step2d_LF_AM3.h:137-215,
+// rhs3d.F:174-252, step3d_uv.F:111-170, ...); they are passed by name instead of by position.  The names are the
+// reference's own (OCEAN/GRID/COUPLING/MIXING/FORCES members), with the time level spelled out as roms_b200_set_field does.
+namespace {
+struct RoutineArgs { int phase; const char* in; const char* out; };
+// 3-D time levels: both levels of u, v, ru, rv and all three of t are listed (which of them a call reads is decided by
+// nstp/nnew/nrhs in roms_b200_tile_t); `*` = one entry per tracer.
+const RoutineArgs kRoutineArgs[] = {
+    {ROMS_B200_SET_MASSFLUX, "u1,u2,v1,v2,Hz,on_u,om_v", "Huon,Hvom"},
+    {ROMS_B200_RHO_EOS, "t1_*,t2_*,z_r,z_w,Hz", "rho,pden,rhoA,rhoS"},
+    {ROMS_B200_SET_VBC, "u1,u2,v1,v2,t1_*,t2_*,rdrag,rdrag2,stflux_*,btflux_*", "bustr,bvstr,stflx_*,btflx_*"},
+    {ROMS_B200_ANA_VMIX, "z_w", "Akv,Akt_*"},
+    {ROMS_B200_OMEGA, "Huon,Hvom,z_w", "W"},
+    {ROMS_B200_WVELOCITY, "u1,u2,v1,v2,z_r,z_w,W,DU_avg1,DV_avg1,pm,pn", "wvel"},
+    {ROMS_B200_SET_ZETA, "Zt_avg1", "zeta1,zeta2"},
+    {ROMS_B200_PRE_STEP3D,
+     "Hz,Huon,Hvom,W,z_r,Akv,Akt_*,pm,pn,stflx_*,btflx_*,sustr,svstr,bustr,bvstr,ru1,ru2,rv1,rv2,u1,u2,v1,v2,t1_*,t2_*",
+     "t3_*,t1_*,t2_*,u1,u2,v1,v2"},
+    {ROMS_B200_PRSGRD, "Hz,z_r,z_w,rho,on_u,om_v", "ru1,ru2,rv1,rv2"},
+    {ROMS_B200_T3DMIX, "Hz,z_r,pm,pn,on_u,om_v,pmon_u,pnom_v,diff2_*,t1_*,t2_*", "t1_*,t2_*"},
+    {ROMS_B200_RHS3D, "Hz,Huon,Hvom,W,u1,u2,v1,v2,fomn,dndx,dmde,om_u,on_u,om_v,on_v,sustr,svstr,bustr,bvstr,ru1,ru2,rv1,rv2",
+     "ru1,ru2,rv1,rv2,rufrc,rvfrc"},
+    {ROMS_B200_UV3DMIX,
+     "Hz,u1,u2,v1,v2,pm,pn,om_r,on_r,om_p,on_p,pmon_r,pnom_r,pmon_p,pnom_p,visc2_r,visc2_p,rufrc,rvfrc", "u1,u2,v1,v2,rufrc,rvfrc"},
+    {ROMS_B200_STEP2D,
+     "h,pm,pn,on_u,om_v,fomn,dndx,dmde,om_r,on_r,om_p,on_p,pmon_r,pnom_r,pmon_p,pnom_p,visc2_r,visc2_p,rhoA,rhoS,rufrc,rvfrc,"
+     "zeta1,zeta2,zeta3,ubar1,ubar2,ubar3,vbar1,vbar2,vbar3,rzeta1,rzeta2,rubar1,rubar2,rvbar1,rvbar2,Zt_avg1,DU_avg1,DU_avg2,"
+     "DV_avg1,DV_avg2,ru1,ru2,rv1,rv2",
+     "zeta1,zeta2,zeta3,ubar1,ubar2,ubar3,vbar1,vbar2,vbar3,rzeta1,rzeta2,rubar1,rubar2,rvbar1,rvbar2,Zt_avg1,DU_avg1,DU_avg2,"
+     "DV_avg1,DV_avg2,rufrc,rvfrc,ru1,ru2,rv1,rv2"},
+    {ROMS_B200_SET_DEPTH, "h,Zt_avg1", "z_r,z_w,Hz"},
+    {ROMS_B200_STEP3D_UV, "Akv,Hz,ru1,ru2,rv1,rv2,DU_avg1,DU_avg2,DV_avg1,DV_avg2,pm,pn,on_u,om_v,u1,u2,v1,v2,Huon,Hvom",
+     "u1,u2,v1,v2,Huon,Hvom,ubar1,ubar2,vbar1,vbar2"},
+    {ROMS_B200_OMEGA2, "Huon,Hvom,z_w", "W"},
+    {ROMS_B200_STEP3D_T, "Hz,Huon,Hvom,W,Akt_*,pm,pn,t1_*,t2_*,t3_*", "t1_*,t2_*"},
+};
+}  // namespace
+
+/* "in:<names>;out:<names>" of a routine (see kRoutineArgs), or NULL for an unknown phase. */
+const char* roms_b200_routine_args(int phase) {
+  static std::string buf[32];
+  for (const RoutineArgs& r : kRoutineArgs)
+    if (r.phase == phase) { buf[phase & 31] = std::string("in:") + r.in + ";out:" + r.out; return buf[phase & 31].c_str(); }
+  return nullptr;
+}
+
+/* Run ONE routine on whole Fortran arrays in host memory.  mode[i]: 1 = input, 2 = output (its current content is uploaded
+ * first, so elements the routine does not touch are preserved, as with an INTENT(inout) dummy), 3 = both.  scoord4 =
+ * sc_r, Cs_r, sc_w, Cs_w with N+1 entries each (set_depth; NULL otherwise); weight1/2 = set_weights.F products with
+ * nweight entries each (step2d; NULL otherwise). */
+int roms_b200_routine_tile(const roms_b200_tile_t* b, int phase, int nargs, const char* const* names, double* const* arrays,
+                           const int* mode, const double* scoord4, int nfast, const double* weight1, const double* weight2, int nweight) {
+  if (!b || nargs < 0 || (nargs > 0 && (!names || !arrays || !mode))) return 2;
+  if (!roms_b200_routine_args(phase)) return 5;
+  Tmp T(b);
+  if (T.rc) return T.rc;
+  const int N = T.N;
+  std::vector<int> nk(nargs, 0);
+  for (int a = 0; a < nargs && !T.rc; ++a) {
+    if (!names[a] || !arrays[a] || mode[a] < 1 || mode[a] > 3) return 2;
+    T.rc = roms_b200_field_levels(T.h, names[a], nullptr, &nk[a]);
+    if (!T.rc) T.up(names[a], arrays[a], nk[a]);
+  }
+  if (scoord4) for (int w = 0; w < 4 && !T.rc; ++w) T.rc = roms_b200_set_scoord(T.h, w, scoord4 + (size_t)w * (N + 1), N + 1);
+  if (weight1 && weight2 && !T.rc) T.rc = roms_b200_set_weights(T.h, nfast, weight1, weight2, nweight);
+  T.run(phase);
+  for (int a = 0; a < nargs && !T.rc; ++a)
+    if (mode[a] & 2) T.down(names[a], arrays[a], nk[a]);
+  return T.rc;
+}
+
 }  // extern "C"

@@ -33,6 +33,7 @@ struct Par {
   int iif, kstp, krhs, knew, ptsk, predictor, nfast;
   // options
   int nonlin_eos, curvgrid, uv_qdrag, salinity, hadv, vadv, itemp, isalt;
+  int fuse_tmix;                  // pre_step3d_t also applies t3dmix2_s (whole-step path only; 0 for single-phase calls)
   // scalars
   double dt, dtfast, g, rho0, R0, T0, S0, Tcoef, Scoef, gamma2, lambda, hc;
   double Akv_bak, Akt_bak[MAXNT];
@@ -100,12 +101,26 @@ __device__ __forceinline__ void st_v_closed(double* __restrict__ A, int o, int i
 // in flight.  The latency-bound column / multi-stage kernels use it to start the DRAM fetch of later stages early.
 __device__ __forceinline__ void pf_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr int PFD = 4;            // prefetch distance (levels ahead) of the column-marching kernels
+// L2 prefetch of the element D levels above a[o] (one lane per 128-byte line issues it): the column-marching kernels keep
+// one or two levels of operands in registers, which does not put enough bytes in flight to cover the DRAM latency; the
+// prefetch turns the later register loads into L2 hits without costing registers.
+template <int D>
+__device__ __forceinline__ void pf_up(const double* a, int o, int k, int N, int PL) {
+  if (D > 0) { if ((threadIdx.x & 15) == 0 && k + D <= N) pf_l2(a + o + D * PL); }
+}
 
 // Asynchronous 8-byte global -> shared copy (LDGSTS): no destination register, completion via wait_group.
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
 }
+template <int D>
+__device__ __forceinline__ void pf_dn(const double* a, int o, int k, int PL) {
+  if (D > 0) { if ((threadIdx.x & 15) == 0 && k - D >= 1) pf_l2(a + o - D * PL); }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }

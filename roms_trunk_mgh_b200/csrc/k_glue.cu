@@ -149,6 +149,9 @@ __global__ void __launch_bounds__(256) k_set_vbc(Par p, Flds f) {
 // ---------------------------------------------------------------------------------------------------------------
 // omega_tile (ROMS/Nonlinear/omega.F:147-218).  Thread per column: upward prefix sum, then removal of the part
 // proportional to the barotropic divergence, then bc_w3d (gradient) + periodic images.
+#ifndef GLUE_PF
+#define GLUE_PF 0          // L2 prefetch distance (levels) of the streaming column kernels k_omega, k_wvelocity
+#endif
 __global__ void __launch_bounds__(128) k_omega(Par p, Flds f) {
   const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -162,6 +165,7 @@ __global__ void __launch_bounds__(128) k_omega(Par p, Flds f) {
   Wl[0] = 0.0;
   for (int k = 1; k <= p.N; ++k) {
     const int o = o2 + k * p.PL;
+    pf_up<GLUE_PF>(Huon, o + i, k, p.N, p.PL); pf_up<GLUE_PF>(Hvom, o + i, k, p.N, p.PL); pf_up<GLUE_PF>(z_w, o + i, k, p.N, p.PL);
     w = w - (Huon[o + i + 1] - Huon[o + i] + Hvom[o + p.P + i] - Hvom[o + i]);
     Wl[k] = w;
   }
@@ -194,6 +198,8 @@ __global__ void __launch_bounds__(128) k_wvelocity(Par p, Flds f, int Ninp) {
   double vert[MAXN + 1];
   for (int k = 1; k <= N; ++k) {
     const int o = o2 + k * p.PL;
+    pf_up<GLUE_PF>(z_r, o + i, k, N, p.PL); pf_up<GLUE_PF>(u, o + i, k, N, p.PL); pf_up<GLUE_PF>(v, o + i, k, N, p.PL);
+    pf_up<GLUE_PF>(W, o + i, k, N, p.PL); pf_up<GLUE_PF>(z_w, o + i, k, N, p.PL);
     const double zr = z_r[o + i];
     const double wu0 = u[o + i] * (zr - z_r[o + i - 1]) * pmU0;
     const double wu1 = u[o + i + 1] * (z_r[o + i + 1] - zr) * pmU1;

@@ -9,7 +9,10 @@ namespace rb {
 // pre_step3d_tile, tracer part (ROMS/Nonlinear/pre_step3d.F:342-582 horizontal, :619-826 vertical + artificial
 // continuity, :837-906 t(nnew) loading, :1126-1142 t3dbc + periodic images).  One thread per column and tracer; every
 // 3-D input is read once per level and both outputs are written once.
-template <int HADV, int VADV>
+// MIXS: also apply t3dmix2_s (ROMS/Nonlinear/t3dmix2_s.h:198-301) to t(nnew) in the same pass -- its operands t(nrhs = nstp) at
+// i+-1, j+-1 are already in registers for the advective fluxes, only the four Hz neighbours are extra loads -- so the separate
+// kernel (7 units of traffic) disappears from the time step.  The additions happen in the reference's order.
+template <int HADV, int VADV, bool MIXS>
 #ifndef PRT_PP
 #define PRT_PP false
 #endif
@@ -21,6 +24,12 @@ template <int HADV, int VADV>
 #endif
 #ifndef PRU_MINB
 #define PRU_MINB 3
+#endif
+#ifndef PRT_PF
+#define PRT_PF 4          // L2 prefetch distance (levels) in k_pre_step3d_t
+#endif
+#ifndef PRU_PF
+#define PRU_PF 4          // same for k_pre_step3d_uv
 #endif
 __global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
   // the tracer index is the fastest grid dimension: the CTAs of all tracers of one tile run back to back, so the shared
@@ -46,12 +55,26 @@ __global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
   else { cff = (1.0 - Gamma) * p.dt; cff1h = 0.5 + Gamma; cff2h = 0.5 - Gamma; }
   // Rolling vertical window of t(nstp) (tkm1 = t(k-1) ... tkp2 = t(k+2)) and software-pipelined operand loads: the loads
   // of level k+1 are issued, back to back, before level k is computed, so a thread waits for memory once per level.
-  struct Lvl { AdvIn a; double tnw, hz, W, zr1, akt, tk3; };
+  double mW = 0.0, mE = 0.0, mS = 0.0, mN = 0.0, mcff = 0.0;
+  if (MIXS) {
+    const double* __restrict__ d2 = f.diff2[itrc];
+    const int q = o2 + i;
+    const double d0 = d2[q];
+    mW = 0.25 * (d0 + d2[q - 1]) * f.pmon_u[q];
+    mE = 0.25 * (d2[q + 1] + d0) * f.pmon_u[q + 1];
+    mS = 0.25 * (d0 + d2[q - P]) * f.pnom_v[q];
+    mN = 0.25 * (d2[q + P] + d0) * f.pnom_v[q + P];
+    mcff = p.dt * pm * pn;
+  }
+  struct Lvl { AdvIn a; double tnw, hz, W, zr1, akt, tk3, hzW, hzE, hzS, hzN; };
   auto load_level = [&](int k) -> Lvl {
     const int o = o2 + k * p.PL;
     Lvl L;
+    pf_up<PRT_PF>(tst, o + i, k, N, p.PL); pf_up<PRT_PF>(Huon, o + i, k, N, p.PL); pf_up<PRT_PF>(Hvom, o + i, k, N, p.PL); pf_up<PRT_PF>(tnw, o + i, k, N, p.PL);
+    pf_up<PRT_PF>(Hz, o + i, k, N, p.PL); pf_up<PRT_PF>(W, o + i, k, N, p.PL); pf_up<PRT_PF>(Akt, o + i, k, N, p.PL); pf_up<PRT_PF>(z_r, o + i, k, N, p.PL);
     L.a = adv_load(tst, Huon, Hvom, o, i, j, p);
     L.tnw = tnw[o + i]; L.hz = Hz[o + i]; L.W = W[o + i]; L.akt = Akt[o + i];
+    if (MIXS) { L.hzW = Hz[o + i - 1]; L.hzE = Hz[o + i + 1]; L.hzS = Hz[o - P + i]; L.hzN = Hz[o + P + i]; }
     L.zr1 = z_r[o + ((k < N) ? p.PL : 0) + i];                   // z_r(k+1) (k = N: unused)
     L.tk3 = tst[o2 + ((k + 2 <= N) ? (k + 2) : N) * p.PL + i];   // t(k+2), clamped
     return L;
@@ -85,7 +108,19 @@ __global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
     }
     const double c1 = hz * tk;
     const double c2 = FDk - FDm;
-    tnw[o + i] = c1 + c2;
+    double tnv = c1 + c2;
+    if (MIXS) {
+      const double t0 = cur.a.t0;
+      const double MXi = mW * (hz + cur.hzW) * (t0 - cur.a.tm1);
+      const double MXip = mE * (cur.hzE + hz) * (cur.a.tp1 - t0);
+      const double MEj = mS * (hz + cur.hzS) * (t0 - cur.a.sm1);
+      const double MEjp = mN * (cur.hzN + hz) * (cur.a.sp1 - t0);
+      const double m1 = mcff * (MXip - MXi);
+      const double m2 = mcff * (MEjp - MEj);
+      const double m3 = m1 + m2;
+      tnv = tnv + m3;
+    }
+    tnw[o + i] = tnv;
     FCm = FCk; FDm = FDk; Wm = Wk; zrk = cur.zr1;
     tkm1 = tk; tk = tkp1; tkp1 = tkp2; tkp2 = nxt.tk3;
   };
@@ -127,6 +162,9 @@ __global__ void __launch_bounds__(128, PRU_MINB) k_pre_step3d_uv(Par p, Flds f) 
     const int o = o2 + k * PL;
     const int ou = (k < N) ? o + PL : o;                 // level k+1 operands (unused at k = N)
     Lvl L;
+    pf_up<PRU_PF>(Hz, o, k, N, PL); pf_up<PRU_PF>(z_r, o, k, N, PL); pf_up<PRU_PF>(Akv, o, k, N, PL); pf_up<PRU_PF>(ust, o, k, N, PL); pf_up<PRU_PF>(vst, o, k, N, PL);
+    if (istart >= 1) { pf_up<PRU_PF>(ru_i, o, k, N, PL); pf_up<PRU_PF>(rv_i, o, k, N, PL); }
+    if (istart == 2) { pf_up<PRU_PF>(ru_r, o, k, N, PL); pf_up<PRU_PF>(rv_r, o, k, N, PL); }
     L.hz0 = Hz[o]; L.hzW = Hz[o - 1]; L.hzS = Hz[o - P];
     L.zr0 = z_r[ou]; L.zrW = z_r[ou - 1]; L.zrS = z_r[ou - P];
     L.ak0 = Akv[o]; L.akW = Akv[o - 1]; L.akS = Akv[o - P];
@@ -393,9 +431,15 @@ template <int H>
 static void launch_pre_t_v(const Par& p, const Flds& f, cudaStream_t s) {
   dim3 b(64, 2); dim3 g = g2(p, b, xspan(p), p.Mm);
   g.x *= p.NT;
-  if (p.vadv == 0) k_pre_step3d_t<H, 0><<<g, b, 0, s>>>(p, f);
-  else if (p.vadv == 1) k_pre_step3d_t<H, 1><<<g, b, 0, s>>>(p, f);
-  else k_pre_step3d_t<H, 2><<<g, b, 0, s>>>(p, f);
+  if (p.fuse_tmix) {
+    if (p.vadv == 0) k_pre_step3d_t<H, 0, true><<<g, b, 0, s>>>(p, f);
+    else if (p.vadv == 1) k_pre_step3d_t<H, 1, true><<<g, b, 0, s>>>(p, f);
+    else k_pre_step3d_t<H, 2, true><<<g, b, 0, s>>>(p, f);
+    return;
+  }
+  if (p.vadv == 0) k_pre_step3d_t<H, 0, false><<<g, b, 0, s>>>(p, f);
+  else if (p.vadv == 1) k_pre_step3d_t<H, 1, false><<<g, b, 0, s>>>(p, f);
+  else k_pre_step3d_t<H, 2, false><<<g, b, 0, s>>>(p, f);
 }
 void launch_pre_step3d_t(const Par& p, const Flds& f, cudaStream_t s) {
   if (p.hadv == 0) launch_pre_t_v<0>(p, f, s);

@@ -18,6 +18,12 @@ __device__ __forceinline__ double d2y(const double* __restrict__ A, int o, int P
 #ifndef RHS_BX
 #define RHS_BX 64
 #endif
+#ifndef RHS_PF
+#define RHS_PF 4          // L2 prefetch distance (levels) in k_rhs3d
+#endif
+#ifndef UVM_PF
+#define UVM_PF 4          // same for k_uv3dmix2
+#endif
 __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -48,6 +54,8 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
     const int o = o2 + k * p.PL + i;                     // includes i
     const int oU = (k < N) ? o + p.PL : o, oUU = (k + 2 <= N) ? o + 2 * p.PL : oU, oD = (k > 1) ? o - p.PL : o;
     // ---- all global operands of this level, issued back to back (one memory wait per level)
+    pf_up<RHS_PF>(Hz, o, k, N, p.PL); pf_up<RHS_PF>(u, o, k, N, p.PL); pf_up<RHS_PF>(v, o, k, N, p.PL); pf_up<RHS_PF>(Huon, o, k, N, p.PL);
+    pf_up<RHS_PF>(Hvom, o, k, N, p.PL); pf_up<RHS_PF>(W, o, k, N, p.PL); pf_up<RHS_PF>(ru, o, k, N, p.PL); pf_up<RHS_PF>(rv, o, k, N, p.PL);
     const double hz0 = Hz[o], hzW = Hz[o - 1], hzS = Hz[o - P];
     const double uW2 = u[o - 2], uW = u[o - 1], u0 = u[o], uE = u[o + 1], uE2 = u[o + 2];
     const double uS2 = u[o + S2], uS = u[o - P], uN = u[o + P], uN2 = u[o + N2], uSE = u[o - P + 1];
@@ -235,6 +243,7 @@ __global__ void __launch_bounds__(128, UVM_MINB) k_uv3dmix2(Par p, Flds f) {
   auto load_level = [&](int k) -> Lvl {
     const int o = o2 + k * p.PL;
     Lvl L;
+    pf_up<UVM_PF>(Hz, o, k, N, p.PL); pf_up<UVM_PF>(u, o, k, N, p.PL); pf_up<UVM_PF>(v, o, k, N, p.PL); pf_up<UVM_PF>(un, o, k, N, p.PL); pf_up<UVM_PF>(vn, o, k, N, p.PL);
     L.h0 = Hz[o]; L.hW = Hz[o - 1]; L.hE = Hz[o + 1]; L.hS = Hz[o - P]; L.hSW = Hz[o - P - 1]; L.hSE = Hz[o - P + 1];
     L.hN = Hz[o + P]; L.hNW = Hz[o + P - 1];
     L.uW = u[o - 1]; L.u0 = u[o]; L.uE = u[o + 1]; L.uS = u[o - P]; L.uSE = u[o - P + 1]; L.uN = u[o + P];

@@ -33,7 +33,7 @@ constexpr int SH = TY + HL + HH;         // staged height (13)
 constexpr int ZW = TX + 1, ZH = TY + 1;  // flux / zeta regions: one extra column and row
 constexpr int NS = SW * SH, NZ = ZW * ZH;
 constexpr int SMEM_DOUBLES = 5 * NS + 17 * NZ;
-static_assert(TX == 32 && TX * ZH + ZH <= NTH && NS <= 2 * NTH, "tile / thread-count mismatch");
+static_assert(TX == 32 && TX * ZH + ZH <= NTH && NS <= 2 * NTH && TX * TY + 64 <= NTH, "tile / thread-count mismatch");
 
 #ifndef S2D_MINB
 #define S2D_MINB 2
@@ -48,7 +48,10 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
   // regions with origin (i0, j0): psi-point fluxes
   double* aUFe = vVFe + NZ; double* aVFx = aUFe + NZ; double* vUFe = aVFx + NZ; double* vVFx = vUFe + NZ;
   const int tid = threadIdx.x;
-  const int i0 = xcol0(p, blockIdx.x * TX), j0 = blockIdx.y * TY;       // tile origin
+  // Tile origin.  The row blocks cover the interior rows 1..Mm; the two wall rows 0 and Mm+1 (fast-time averages only) are
+  // taken by the two warps that idle in stage 3, in the first / last row block -- for Mm = 256 that is 32 instead of 33
+  // row blocks, i.e. 2048 CTAs = 6.9 waves of 2 x 148 resident CTAs instead of 7.1 (a whole extra wave).
+  const int i0 = xcol0(p, blockIdx.x * TX), j0 = 1 + blockIdx.y * TY;
   const int P = p.P, Mm = p.Mm;
   const bool PRED = p.predictor != 0;
   const bool FIRST = (p.iif == 1);
@@ -226,11 +229,20 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
   }
   __syncthreads();
 
-  // ---- stage 3: one thread per rho point of the tile
-  if (tid >= TX * TY) return;
-  const int tx = tid % TX, ty = tid / TX;
+  // ---- stage 3: one thread per rho point of the tile (+ one warp each for wall rows 0 and Mm+1)
+  int tx, ty;
+  if (tid < TX * TY) {
+    tx = tid % TX; ty = tid / TX;
+    if (j0 + ty > Mm) return;
+  } else {
+    const int w = (tid - TX * TY) >> 5;
+    tx = tid & 31;
+    if (w == 0 && blockIdx.y == 0) ty = -1;                              // row 0
+    else if (w == 1 && j0 <= Mm && j0 + TY - 1 >= Mm) ty = Mm + 1 - j0;  // row Mm+1, in the block that holds row Mm
+    else return;
+  }
   const int i = i0 + tx, j = j0 + ty;
-  if (i > p.Iend || j > Mm + 1) return;
+  if (i > p.Iend) return;
   const int o = j * P + i;
   const bool inner = active && j >= 1 && j <= Mm;
   const bool dov = inner && (j >= p.JstrV);
@@ -379,7 +391,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
 
 // selected with ROMS_B200_STEP2D=tile (A/B measurements); the default is the row-marching kernel of k_step2d_m.cu
 void launch_step2d_tile(const Par& p, const Flds& f, cudaStream_t s) {
-  dim3 g((xspan(p) + TX - 1) / TX, (p.Mm + 2 + TY - 1) / TY);
+  dim3 g((xspan(p) + TX - 1) / TX, (p.Mm + TY - 1) / TY);
   const size_t smem = (size_t)SMEM_DOUBLES * sizeof(double);
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_step2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }

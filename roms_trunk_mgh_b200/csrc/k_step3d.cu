@@ -35,6 +35,24 @@ namespace rb {
 #ifndef S3T_MINB
 #define S3T_MINB 6
 #endif
+#ifndef S3U_RING
+#define S3U_RING 0        // > 0: pass 1 of k_step3d_uv streams its operands through a per-thread shared-memory ring of this many
+#endif                    // levels filled with cp.async (LDGSTS): levels in flight without a register cost
+#ifndef S3T_RING
+#define S3T_RING 0        // same for pass 1 of k_step3d_t (18 operands per level)
+#endif
+#ifndef S3U_PF
+#define S3U_PF 4          // L2 prefetch distance (levels) of pass 1 in k_step3d_uv
+#endif
+#ifndef S3T_PF
+#define S3T_PF 8          // same for k_step3d_t
+#endif
+#ifndef S3U_PF2
+#define S3U_PF2 0         // L2 prefetch distance (levels, downward) of pass 2 in k_step3d_uv
+#endif
+#ifndef S3T_PF2
+#define S3T_PF2 0         // same for k_step3d_t
+#endif
 constexpr int TS = S3D_TS;   // threads (columns) per block
 constexpr int CH = S3D_CH;   // levels per batch of independent loads in the downward / coupling passes
 static_assert(EDGE_W % TS == 0, "split launches need CTA widths that divide EDGE_W");
@@ -90,6 +108,7 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
   auto load_level = [&](int k) -> Lvl {
     const int o = o2 + k * PL;
     pf_l2(HUV + o);                                                        // first touched by the coupling pass
+    pf_up<S3U_PF>(Akv, o, k, N, PL); pf_up<S3U_PF>(Hz, o, k, N, PL); pf_up<S3U_PF>(X, o, k, N, PL); pf_up<S3U_PF>(R, o, k, N, PL);
     return Lvl{Akv[o - s], Akv[o], Hz[o - s], Hz[o], X[o], R[o]};
   };
   double AKm = 0.5 * (Akv[o2 - s] + Akv[o2]), AKmm = 0.0, AKN;
@@ -107,7 +126,34 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
       }
       AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = xv;
     };
-    #if S3U_DEPTH >= 2
+#if S3U_RING > 0
+    // Register-free deep prefetch: every thread copies the six operands of level k + S3U_RING straight into its own slots of a
+    // shared-memory ring (one commit group per level) and only ever reads back what it copied itself, so no barrier is needed;
+    // S3U_RING levels (x 48 bytes per thread) are in flight while the dependent FP64 chain of level k runs.
+    {
+      constexpr int D = S3U_RING;
+      double* ring = sm + 2 * N * TS + tid;                                // [D][6][TS]
+      auto issue = [&](int k) {
+        if (k <= N) {
+          const int o = o2 + k * PL;
+          double* r = ring + ((k - 1) % D) * 6 * TS;
+          cp_async8(r, Akv + o - s); cp_async8(r + TS, Akv + o); cp_async8(r + 2 * TS, Hz + o - s); cp_async8(r + 3 * TS, Hz + o);
+          cp_async8(r + 4 * TS, X + o); cp_async8(r + 5 * TS, R + o);
+          pf_l2(HUV + o);
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int k = 1; k <= D; ++k) issue(k);
+      for (int k = 1; k <= N; ++k) {
+        cp_async_wait<D - 1>();
+        const double* r = ring + ((k - 1) % D) * 6 * TS;
+        const Lvl cur{r[0], r[TS], r[2 * TS], r[3 * TS], r[4 * TS], r[5 * TS]};
+        issue(k + D);
+        level(cur, cur, k);
+      }
+    }
+#elif S3U_DEPTH >= 2
     sweep_levels_deep<S3U_DEPTH>(N, load_level, level);
 #else
     sweep_levels<S3U_PP>(N, load_level, level);
@@ -125,6 +171,7 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
       for (int q = 0; q < CH; ++q) {
         const int k = (kt - q >= 1) ? kt - q : 1;
         const int o = o2 + k * PL;
+        pf_dn<S3U_PF2>(X, o, k, PL); pf_dn<S3U_PF2>(R, o, k, PL); pf_dn<S3U_PF2>(Hz, o, k, PL); pf_dn<S3U_PF2>(Akv, o - PL, k, PL);
         lx[q] = X[o]; lr[q] = R[o]; lh0[q] = Hz[o - s]; lh1[q] = Hz[o]; la0[q] = Akv[o - PL - s]; la1[q] = Akv[o - PL];
       }
 #pragma unroll
@@ -248,6 +295,8 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
   auto load_level = [&](int k) -> Lvl {
     const int o = o2 + k * PL;
     Lvl L;
+    pf_up<S3T_PF>(t3, o + i, k, N, PL); pf_up<S3T_PF>(Huon, o + i, k, N, PL); pf_up<S3T_PF>(Hvom, o + i, k, N, PL); pf_up<S3T_PF>(tn, o + i, k, N, PL);
+    pf_up<S3T_PF>(Hz, o + i, k, N, PL); pf_up<S3T_PF>(W, o + i, k, N, PL); pf_up<S3T_PF>(Akt, o + i, k, N, PL);
     L.a = adv_load(t3, Huon, Hvom, o, i, j, p);
     L.tn = tn[o + i]; L.hz = Hz[o + i]; L.W = W[o + i]; L.akt = Akt[o + i];
     L.tk3 = t3[o2 + ((k + 2 <= N) ? (k + 2) : N) * PL + i];                // t(k+2), clamped
@@ -281,7 +330,39 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
       AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = tv; FCm = FCk;
       tkm1 = tk; tk = tkp1; tkp1 = tkp2; tkp2 = nxt.tk3;
     };
+#if S3T_RING > 0
+    {
+      constexpr int D = S3T_RING, NF = 18;
+      double* ring = sm + 2 * N * TS + tid;                                // [D][NF][TS]
+      const int om2 = (j > 1) ? -2 * P : -P, op2 = (j < p.Mm) ? 2 * P : P; // clamped rows, as in adv_load
+      auto issue = [&](int k) {
+        if (k <= N) {
+          const int o = o2 + k * PL + i;
+          double* r = ring + ((k - 1) % D) * NF * TS;
+          cp_async8(r, t3 + o - 2); cp_async8(r + TS, t3 + o - 1); cp_async8(r + 2 * TS, t3 + o); cp_async8(r + 3 * TS, t3 + o + 1);
+          cp_async8(r + 4 * TS, t3 + o + 2); cp_async8(r + 5 * TS, t3 + o + om2); cp_async8(r + 6 * TS, t3 + o - P);
+          cp_async8(r + 7 * TS, t3 + o + P); cp_async8(r + 8 * TS, t3 + o + op2);
+          cp_async8(r + 9 * TS, Huon + o); cp_async8(r + 10 * TS, Huon + o + 1); cp_async8(r + 11 * TS, Hvom + o); cp_async8(r + 12 * TS, Hvom + o + P);
+          cp_async8(r + 13 * TS, tn + o); cp_async8(r + 14 * TS, Hz + o); cp_async8(r + 15 * TS, W + o); cp_async8(r + 16 * TS, Akt + o);
+          cp_async8(r + 17 * TS, t3 + o2 + ((k + 3 <= N) ? (k + 3) : N) * PL + i);   // tk3 of level k+1: what `level` takes from nxt
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int k = 1; k <= D; ++k) issue(k);
+      for (int k = 1; k <= N; ++k) {
+        cp_async_wait<D - 1>();
+        const double* r = ring + ((k - 1) % D) * NF * TS;
+        Lvl cur;
+        cur.a = AdvIn{r[0], r[TS], r[2 * TS], r[3 * TS], r[4 * TS], r[5 * TS], r[6 * TS], r[7 * TS], r[8 * TS], r[9 * TS], r[10 * TS], r[11 * TS], r[12 * TS]};
+        cur.tn = r[13 * TS]; cur.hz = r[14 * TS]; cur.W = r[15 * TS]; cur.akt = r[16 * TS]; cur.tk3 = r[17 * TS];
+        issue(k + D);
+        level(cur, cur, k);                                                // only nxt.tk3 is read from the second argument
+      }
+    }
+#else
     sweep_levels<S3T_PP>(N, load_level, level);
+#endif
     AKN = AKm;
   }
   // ---- pass 2 (downward): back substitution + update + t3dbc / periodic images
@@ -294,6 +375,7 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
       for (int q = 0; q < CH; ++q) {
         const int k = (kt - q >= 1) ? kt - q : 1;
         const int o = o2 + k * PL + i;
+        pf_dn<S3T_PF2>(tn, o, k, PL); pf_dn<S3T_PF2>(Hz, o, k, PL); pf_dn<S3T_PF2>(Akt, o - PL, k, PL);
         lx[q] = tn[o]; lh[q] = Hz[o]; la[q] = Akt[o - PL];
       }
 #pragma unroll
@@ -316,11 +398,13 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
 }
 
 static size_t smem_cols(int N) { return (size_t)2 * N * TS * sizeof(double); }
+static size_t smem_cols_t(int N) { return (size_t)(2 * N + 18 * S3T_RING) * TS * sizeof(double); }
+static size_t smem_cols_uv(int N) { return (size_t)(2 * N + 6 * S3U_RING) * TS * sizeof(double); }
 template <typename K>
 static void allow_smem(K kern, size_t bytes) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
 
 void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s) {
-  const size_t sm = smem_cols(p.N);
+  const size_t sm = smem_cols_uv(p.N);
   static size_t allowed = 0;
   if (sm > allowed) { allow_smem(k_step3d_uv<0>, sm); allow_smem(k_step3d_uv<1>, sm); allowed = sm; }
   const int nbx = (xspan(p) + TS - 1) / TS;
@@ -330,7 +414,7 @@ void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s) {
 
 template <int H, int V>
 static void launch_s3t(const Par& p, const Flds& f, cudaStream_t s) {
-  const size_t sm = smem_cols(p.N);
+  const size_t sm = smem_cols_t(p.N);
   static size_t allowed = 0;
   if (sm > allowed) { allow_smem(k_step3d_t<H, V>, sm); allowed = sm; }
   const int nbx = (xspan(p) + TS - 1) / TS;

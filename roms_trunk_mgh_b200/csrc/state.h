@@ -34,6 +34,10 @@ struct roms_b200_state {
   int LBi_dev, ni_dev;    // device arrays carry 3 west ghost columns on every tile (the fused step2d kernel needs Drhs(i-3))
   std::map<std::string, rbi::FieldInfo> reg;
   std::vector<void*> allocs;
+  // time-varying 2-D fields of the barotropic sub-steps live in one arena so that an L2 access-policy window can keep them
+  // resident across the 59 step2d launches of a baroclinic step (api.cu l2_window)
+  char* hot_arena = nullptr; size_t hot_cap = 0, hot_used = 0;
+  size_t l2_window_bytes = 0; float l2_hit = 0.f;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // stepping state (mod_stepping.F)
@@ -57,6 +61,8 @@ struct roms_b200_state {
   int overlap = 0;
   bool edge_pending = false, halo_pending = false;   // main stream has not yet waited for the latest ev_edge / ev_halo
   // CUDA graphs of whole time steps, keyed by the stepping state at the start of the step (api.cu one_step)
+  int fuse_tmix = 1;      // whole-step path: t3dmix2_s folded into pre_step3d_t (ROMS_B200_FUSE_TMIX=0 keeps the separate kernel)
+  bool in_step = false;   // inside step_phases (cross-routine fusions are only legal there: run_phase keeps routine granularity)
   int use_graphs = 1;
   std::map<int, void*> graphs;     // key -> rbi::StepGraph*
 };

@@ -162,6 +162,28 @@ def test_cabi_exports_every_declared_symbol():
             assert hasattr(L, sym), sym
 
 
+def test_cabi_routine_args_name_known_fields():
+    """roms_b200_routine_args (host-side table of the generic per-routine entry point): every routine of the chain has an
+    argument list and every name in it is a field roms_b200_set_field knows."""
+    from roms_trunk_mgh_b200 import _lib
+    from roms_trunk_mgh_b200.ocean import field_names
+    L = _lib.load(False)
+    n2, n3 = field_names(2)
+    known = set(n2 + n3)
+    for name, ph in _lib.PHASES.items():
+        spec = L.roms_b200_routine_args(ph)
+        if name in ("diag", "set_data", "step2d_loop"):
+            assert spec is None
+            continue
+        assert spec is not None, name
+        ins, outs = [x.split(":")[1].split(",") for x in spec.decode().split(";")]
+        assert outs and ins
+        for n in ins + outs:
+            for it in range(2):
+                assert n.replace("*", str(it)) in known, (name, n)
+    assert L.roms_b200_routine_args(999) is None
+
+
 def test_cabi_bounds_match_oracle():
     """roms_b200_bounds (product) vs the oracle's get_bounds restatement: all 57 integers, all supported partitions."""
     from roms_trunk_mgh_b200 import _lib
