@@ -152,41 +152,48 @@ __global__ void __launch_bounds__(256) k_set_vbc(Par p, Flds f) {
 #ifndef GLUE_PF
 #define GLUE_PF 0          // L2 prefetch distance (levels) of the streaming column kernels k_omega, k_wvelocity
 #endif
+// NC > 0: the number of levels is the compile-time constant NC (all BENCHMARK grids have N = 30), so the column of partial sums
+// stays in registers; NC = 0 keeps it in a thread-local array (local memory: ~0.5 KB per column of extra L1/L2 traffic).
+template <int NC>
 __global__ void __launch_bounds__(128) k_omega(Par p, Flds f) {
   const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > p.Iend || j > p.Mm) return;
   const int o2 = j * p.P;
+  const int N = NC > 0 ? NC : p.N;
   const double* __restrict__ Huon = f.Huon;
   const double* __restrict__ Hvom = f.Hvom;
   const double* __restrict__ z_w = f.z_w;
-  double Wl[MAXN + 1];
+  double Wl[(NC > 0 ? NC : MAXN) + 1];
   double w = 0.0;
   Wl[0] = 0.0;
-  for (int k = 1; k <= p.N; ++k) {
+#pragma unroll
+  for (int k = 1; k <= N; ++k) {
     const int o = o2 + k * p.PL;
-    pf_up<GLUE_PF>(Huon, o + i, k, p.N, p.PL); pf_up<GLUE_PF>(Hvom, o + i, k, p.N, p.PL); pf_up<GLUE_PF>(z_w, o + i, k, p.N, p.PL);
+    pf_up<GLUE_PF>(Huon, o + i, k, N, p.PL); pf_up<GLUE_PF>(Hvom, o + i, k, N, p.PL); pf_up<GLUE_PF>(z_w, o + i, k, N, p.PL);
     w = w - (Huon[o + i + 1] - Huon[o + i] + Hvom[o + p.P + i] - Hvom[o + i]);
     Wl[k] = w;
   }
   const double zw0 = z_w[o2 + i];
-  const double wrk = w / (z_w[o2 + p.N * p.PL + i] - zw0);
+  const double wrk = w / (z_w[o2 + N * p.PL + i] - zw0);
   st_r_grad(f.W, o2, i, j, 0.0, p);
-  for (int k = p.N - 1; k >= 1; --k) {
+#pragma unroll
+  for (int k = N - 1; k >= 1; --k) {
     const int o = o2 + k * p.PL;
     const double x = Wl[k] - wrk * (z_w[o + i] - zw0);
     st_r_grad(f.W, o, i, j, x, p);
   }
-  st_r_grad(f.W, o2 + p.N * p.PL, i, j, 0.0, p);
+  st_r_grad(f.W, o2 + N * p.PL, i, j, 0.0, p);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // wvelocity_tile (ROMS/Nonlinear/wvelocity.F:156-256): diagnostic true vertical velocity at W-points.
+template <int NC>    // NC > 0: compile-time number of levels, vert() in registers (see k_omega)
 __global__ void __launch_bounds__(128) k_wvelocity(Par p, Flds f, int Ninp) {
   const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > p.Iend || j > p.Mm) return;
-  const int o2 = j * p.P, P = p.P, N = p.N;
+  const int o2 = j * p.P, P = p.P, N = NC > 0 ? NC : p.N;
   const double* __restrict__ u = f.u[Ninp];
   const double* __restrict__ v = f.v[Ninp];
   const double* __restrict__ z_r = f.z_r;
@@ -195,7 +202,8 @@ __global__ void __launch_bounds__(128) k_wvelocity(Par p, Flds f, int Ninp) {
   const double pmi = f.pm[o2 + i], pni = f.pn[o2 + i];
   const double pmU0 = f.pm[o2 + i - 1] + pmi, pmU1 = pmi + f.pm[o2 + i + 1];
   const double pnV0 = f.pn[o2 - P + i] + pni, pnV1 = pni + f.pn[o2 + P + i];
-  double vert[MAXN + 1];
+  double vert[(NC > 0 ? NC : MAXN) + 1];
+#pragma unroll
   for (int k = 1; k <= N; ++k) {
     const int o = o2 + k * p.PL;
     pf_up<GLUE_PF>(z_r, o + i, k, N, p.PL); pf_up<GLUE_PF>(u, o + i, k, N, p.PL); pf_up<GLUE_PF>(v, o + i, k, N, p.PL);
@@ -221,6 +229,7 @@ __global__ void __launch_bounds__(128) k_wvelocity(Par p, Flds f, int Ninp) {
     const double w1 = pmn * (W[o + i] + wrk * (z_w[o + i] - zw0)) + cff1 * vert[1] + cff2 * vert[2] - cff3 * vert[3];
     st_r_grad(f.wvel, o, i, j, w1, p);
   }
+#pragma unroll
   for (int k = 2; k <= N - 2; ++k) {
     const int o = o2 + k * p.PL;
     const double x = pmn * (W[o + i] + wrk * (z_w[o + i] - zw0)) + cff4 * (vert[k] + vert[k + 1]) - cff5 * (vert[k - 1] + vert[k + 2]);
@@ -296,8 +305,16 @@ static inline dim3 g2(const Par& p, dim3 b, int nj, int nz = 1) {
 void launch_set_massflux(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_massflux<<<g2(p, b, p.Mm + 2, p.N), b, 0, s>>>(p, f); }
 void launch_rho_eos(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_rho_eos<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
 void launch_set_vbc(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_vbc<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
-void launch_omega(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 2); k_omega<<<g2(p, b, p.Mm), b, 0, s>>>(p, f); }
-void launch_wvelocity(const Par& p, const Flds& f, int Ninp, cudaStream_t s) { dim3 b(64, 2); k_wvelocity<<<g2(p, b, p.Mm), b, 0, s>>>(p, f, Ninp); }
+void launch_omega(const Par& p, const Flds& f, cudaStream_t s) {
+  dim3 b(64, 2);
+  if (p.N == 30) k_omega<30><<<g2(p, b, p.Mm), b, 0, s>>>(p, f);
+  else k_omega<0><<<g2(p, b, p.Mm), b, 0, s>>>(p, f);
+}
+void launch_wvelocity(const Par& p, const Flds& f, int Ninp, cudaStream_t s) {
+  dim3 b(64, 2);
+  if (p.N == 30) k_wvelocity<30><<<g2(p, b, p.Mm), b, 0, s>>>(p, f, Ninp);
+  else k_wvelocity<0><<<g2(p, b, p.Mm), b, 0, s>>>(p, f, Ninp);
+}
 void launch_set_zeta(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_zeta<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
 void launch_set_depth(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_depth<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
 void launch_ana_vmix(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_ana_vmix<<<g2(p, b, p.Mm + 2, p.N - 1), b, 0, s>>>(p, f); }

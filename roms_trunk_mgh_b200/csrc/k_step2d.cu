@@ -38,7 +38,28 @@ static_assert(TX == 32 && TX * ZH + ZH <= NTH && NS <= 2 * NTH && TX * TY + 64 <
 #ifndef S2D_MINB
 #define S2D_MINB 2
 #endif
+#ifndef S2D_EVICT
+#define S2D_EVICT 1      // 1: the static operands (metrics, h, rhoA/rhoS, rufrc/rvfrc) are loaded with an L2 evict-first hint so that
+#endif                   // they do not displace the time-varying barotropic state (86 MB at BENCHMARK3) from the 126 MB L2
+#if S2D_EVICT
+__device__ __forceinline__ unsigned long long evict_first_policy() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double lds_pol(const double* a, unsigned long long pol) {
+  double v;
+  asm("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
+  return v;
+}
+#define lds_(a) lds_pol(a, l2pol)
+#else
+#define lds_(a) (*(a))
+#endif
 __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
+#if S2D_EVICT
+  const unsigned long long l2pol = evict_first_policy();
+#endif
   extern __shared__ double smem[];
   double* sD = smem; double* sU = sD + NS; double* sV = sU + NS; double* sDU = sV + NS; double* sDV = sDU + NS;
   // regions with origin (i0-1, j0-1): zeta-stage and rho-point fluxes
@@ -75,7 +96,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
       const int i = i0 - HL + a, j = j0 - HL + b;
       ok[r] = (s < NS) && i >= p.LBi && i <= p.UBi && j >= 0 && j <= Mm + 1;
       const int q = ok[r] ? (j * P + i) : (j0 * P + i0);               // safe dummy address
-      zv[r] = zr[q]; hv[r] = h[q]; uv[r] = ur[q]; vv[r] = vr[q]; onu[r] = f.on_u[q]; omv[r] = f.om_v[q];
+      zv[r] = zr[q]; hv[r] = lds_(h + q); uv[r] = ur[q]; vv[r] = vr[q]; onu[r] = lds_(f.on_u + q); omv[r] = lds_(f.om_v + q);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -136,11 +157,11 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
       if (j >= 1 && j <= Mm && i <= p.Iend) {
         const int q = j * P + i;
         // all global operands of this stage, issued back to back
-        const double zs_q = zs[q], zr_q = zr[q], pm_q = pm[q], pn_q = pn[q], h_q = h[q], rS = f.rhoS[q], rA = f.rhoA[q];
-        const double fomn_q = f.fomn[q], visc_q = f.visc2_r[q], pmon_q = f.pmon_r[q], pnom_q = f.pnom_r[q];
-        const double pnE = pn[q + 1], pnW = pn[q - 1], pmN = pm[q + P], pmS = pm[q - P], onr = f.on_r[q], omr = f.om_r[q];
+        const double zs_q = zs[q], zr_q = zr[q], pm_q = lds_(pm + q), pn_q = lds_(pn + q), h_q = lds_(h + q), rS = lds_(f.rhoS + q), rA = lds_(f.rhoA + q);
+        const double fomn_q = lds_(f.fomn + q), visc_q = lds_(f.visc2_r + q), pmon_q = lds_(f.pmon_r + q), pnom_q = lds_(f.pnom_r + q);
+        const double pnE = lds_(pn + q + 1), pnW = lds_(pn + q - 1), pmN = lds_(pm + q + P), pmS = lds_(pm + q - P), onr = lds_(f.on_r + q), omr = lds_(f.om_r + q);
         double dndx_q = 0.0, dmde_q = 0.0, rz_s = 0.0, rz_p = 0.0;
-        if (p.curvgrid) { dndx_q = f.dndx[q]; dmde_q = f.dmde[q]; }
+        if (p.curvgrid) { dndx_q = lds_(f.dndx + q); dmde_q = lds_(f.dmde + q); }
         if (!FIRST && !PRED) { rz_s = f.rzeta[p.kstp][q]; rz_p = f.rzeta[p.ptsk][q]; }
         // new free surface (:770-851)
         const double dd = (DU_(0, 0) - DU_(1, 0)) + (DV_(0, 0) - DV_(0, 1));
@@ -204,9 +225,9 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
       double a_ufe = 0.0, a_vfx = 0.0, v_ufe = 0.0, v_vfx = 0.0;
       if (j >= 1 && j <= Mm + 1 && i <= p.Iend + 1) {
         const int q = j * P + i;
-        const double visc_q = f.visc2_p[q], pmon_q = f.pmon_p[q], pnom_q = f.pnom_p[q], omp = f.om_p[q], onp = f.on_p[q];
-        const double pn_q = pn[q], pnS = pn[q - P], pnW = pn[q - 1], pnSW = pn[q - P - 1];
-        const double pm_q = pm[q], pmS = pm[q - P], pmW = pm[q - 1], pmSW = pm[q - P - 1];
+        const double visc_q = lds_(f.visc2_p + q), pmon_q = lds_(f.pmon_p + q), pnom_q = lds_(f.pnom_p + q), omp = lds_(f.om_p + q), onp = lds_(f.on_p + q);
+        const double pn_q = lds_(pn + q), pnS = lds_(pn + q - P), pnW = lds_(pn + q - 1), pnSW = lds_(pn + q - P - 1);
+        const double pm_q = lds_(pm + q), pmS = lds_(pm + q - P), pmW = lds_(pm + q - 1), pmSW = lds_(pm + q - P - 1);
         // advective UFe at psi(i,j) (:1141-1150): grad = d2y(ubar), rows 1..Mm with wall copies (0)=(1), (Mm+1)=(Mm)
         {
           const int d0 = (j > Mm) ? -1 : 0, dm = (j - 1 < 1) ? 0 : -1;
@@ -252,13 +273,13 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
   const double av_du2 = f.DU_avg2[o], av_dv2 = f.DV_avg2[o];
   double av_zt = 0.0, av_du1 = 0.0, av_dv1 = 0.0;
   if (PRED && !FIRST) { av_zt = f.Zt_avg1[o]; av_du1 = f.DU_avg1[o]; av_dv1 = f.DV_avg1[o]; }
-  const double h0 = h[o], hW = h[o - 1], hS = h[oS];
-  const double rA0 = f.rhoA[o], rAW = f.rhoA[o - 1], rAS = f.rhoA[oS];
-  const double pm0 = pm[o], pmW = pm[o - 1], pmS = pm[oS], pn0 = pn[o], pnW = pn[o - 1], pnS = pn[oS];
-  const double onu = f.on_u[o], omv = f.om_v[o];
+  const double h0 = lds_(h + o), hW = lds_(h + o - 1), hS = lds_(h + oS);
+  const double rA0 = lds_(f.rhoA + o), rAW = lds_(f.rhoA + o - 1), rAS = lds_(f.rhoA + oS);
+  const double pm0 = lds_(pm + o), pmW = lds_(pm + o - 1), pmS = lds_(pm + oS), pn0 = lds_(pn + o), pnW = lds_(pn + o - 1), pnS = lds_(pn + oS);
+  const double onu = lds_(f.on_u + o), omv = lds_(f.om_v + o);
   const double zs0 = zs[o], zsW = zs[o - 1], zsS = zs[oS];
   const double us = f.ubar[p.kstp][o], vs = f.vbar[p.kstp][o];
-  const double rufrc_o = f.rufrc[o], rvfrc_o = f.rvfrc[o];
+  const double rufrc_o = lds_(f.rufrc + o), rvfrc_o = lds_(f.rvfrc + o);
   double rub_s = 0.0, rub_p = 0.0, rvb_s = 0.0, rvb_p = 0.0, ru_n = 0.0, ru_so = 0.0, rv_n = 0.0, rv_so = 0.0;
   if (!FIRST && !PRED) { rub_s = f.rubar[p.kstp][o]; rub_p = f.rubar[p.ptsk][o]; rvb_s = f.rvbar[p.kstp][o]; rvb_p = f.rvbar[p.ptsk][o]; }
   if (FIRST && PRED && p.istart >= 1) { ru_n = f.ru[p.nnew][o]; rv_n = f.rv[p.nnew][o]; ru_so = f.ru[p.nstp][o]; rv_so = f.rv[p.nstp][o]; }
