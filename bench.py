@@ -23,7 +23,9 @@ sys.path.insert(0, ROOT)
 
 GRIDS = {"benchmark1": (512, 64, 30), "benchmark2": (1024, 128, 30), "benchmark3": (2048, 256, 30),
          # tuning aid: on 2 GPUs this gives every rank the 256x256 tile BENCHMARK3 has on 8 GPUs
-         "b3tile8x2": (512, 256, 30)}
+         "b3tile8x2": (512, 256, 30),
+         # ... and this one the 512x256 tile of 4 GPUs
+         "b3tile4x2": (1024, 256, 30)}
 METRIC = "grid-point-steps/sec (3D baroclinic)"
 
 
@@ -187,6 +189,8 @@ def main():
         from roms_trunk_mgh_b200 import multigpu
         multigpu.attach(t, dist, rank, world)
         xchg = ("nvlink-peer-mailbox" if t.peer else "nccl-send-recv") + ("" if os.environ.get("ROMS_B200_NO_OVERLAP") == "1" else "+edge-first-overlap")
+        if t.peer and os.environ.get("ROMS_B200_FUSED_XCHG", "2") != "0":
+            xchg += "+step2d-exchange-fused-into-kernel"
         for ph in ("set_depth", "set_massflux", "omega", "rho_eos"):      # start-up phases again, now with live ghosts
             t.run_phase(ph)
     t.main3d(a.spinup)

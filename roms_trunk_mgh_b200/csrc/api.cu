@@ -183,16 +183,18 @@ void launch_full(roms_b200_state* h, F fn) {
 }
 
 // Launch `fn` over the tile and refresh the xi-ghost columns of the fields `phase` produces (mp_exchange2d/3d/4d).
+// in_kernel_exchange: the kernels fn launches move the halo themselves (fused step2d exchange); only the split schedule is kept
 template <class F>
-int launch_with_halo(roms_b200_state* h, int phase, F fn) {
+int launch_with_halo(roms_b200_state* h, int phase, F fn, bool in_kernel_exchange = false) {
   const Par& p = h->par;
   if (!h->halo) { fn(p, h->stream); return NoError; }
-  const std::vector<std::string> names = halo_fields(h, phase);
+  std::vector<std::string> names = halo_fields(h, phase);
   const int ni = p.Iend - p.Istr + 1;
   if (names.empty() || !h->overlap || ni < 4 * EDGE_W) {
     launch_full(h, fn);
-    return halo_exchange(h, names, h->stream);
+    return in_kernel_exchange ? (int)NoError : halo_exchange(h, names, h->stream);
   }
+  if (in_kernel_exchange) names.clear();
   if (h->edge_pending) { cudaStreamWaitEvent(h->stream, h->ev_edge, 0); h->edge_pending = false; }
   cudaEventRecord(h->ev_main, h->stream);
   cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0);
@@ -264,12 +266,38 @@ int run_phase_async(roms_b200_state* h, int phase) {
     case ROMS_B200_DIAG: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_diag(q, f, h->d_diag_partial, h->d_diag_out, h->knew, st); }); h->launches += 3; break;
     case ROMS_B200_STEP2D_LOOP: {
       // main3d.F:592-700
+      // Sub-step calls are numbered c = 1 .. 2*nfast+1.  On the NVLink peer path the xi-halo of calls 1 .. 2*nfast-1 travels
+      // inside the kernels themselves (push at the end of call c, pull at the start of call c+1: dev.cuh Xchg); the last
+      // corrector and the averaging-only call keep the stand-alone exchange so that the 3-D kernels find complete ghosts.
+      Xchg xbase;
+      const bool fused = fused_xchg_fill(h, xbase) && (p.Iend - p.Istr + 1) >= 8;
+      int call = 0;
+      double* prev_send[XF] = {nullptr, nullptr, nullptr, nullptr};
+      int prev_n = 0;
       auto sub_step = [&]() {
         fill_par(h);
         h->launches += 1;
-        return launch_with_halo(h, ROMS_B200_STEP2D, [&](const Par& q, cudaStream_t st) { launch_step2d(q, f, st); });
+        ++call;
+        if (!fused) return launch_with_halo(h, ROMS_B200_STEP2D, [&](const Par& q, cudaStream_t st) { launch_step2d(q, f, st); });
+        Xchg x = xbase;
+        x.recv = (call >= 2 && call <= 2 * h->nfast) ? 1 : 0;
+        x.send = (call <= 2 * h->nfast - 1) ? 1 : 0;
+        x.nrecv = prev_n;
+        for (int q = 0; q < XF; ++q) x.recvf[q] = prev_send[q];
+        x.nsend = h->predictor ? 4 : 3;
+        prev_send[0] = f.zeta[h->knew]; prev_send[1] = f.ubar[h->knew]; prev_send[2] = f.vbar[h->knew]; prev_send[3] = f.rzeta[h->krhs];
+        prev_n = x.nsend;
+        if (x.send) {
+          // mode 1: one full-tile launch, the exchange is inside the kernel; mode 2: keep the edge-first two-stream split (the
+          // edge launch pulls and pushes, the interior launch of the next sub-step only waits for this edge launch)
+          if (h->fused_mode == 2) {
+            return launch_with_halo(h, ROMS_B200_STEP2D, [&](const Par& q, cudaStream_t st) { launch_step2d(q, f, st, q.gap_len > 0 || q.Istr == h->par.Istr ? &x : nullptr); }, true);
+          }
+          launch_full(h, [&](const Par& q, cudaStream_t st) { launch_step2d(q, f, st, &x); });
+          return (int)NoError;
+        }
+        return launch_with_halo(h, ROMS_B200_STEP2D, [&](const Par& q, cudaStream_t st) { launch_step2d(q, f, st, x.recv ? &x : nullptr); });
       };
-      l2_window(h, h->stream, true); l2_window(h, h->comm_stream, true);
       for (int my_iif = 1; my_iif <= h->nfast + 1; ++my_iif) {
         const int next_indx1 = 3 - h->indx1;
         if (!h->predictor && my_iif <= h->nfast + 1) {
@@ -508,6 +536,7 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   { const char* ng = std::getenv("ROMS_B200_NO_GRAPH"); h->use_graphs = !(ng && ng[0] == '1'); }
   { const char* e = std::getenv("ROMS_B200_FUSE_TMIX"); h->fuse_tmix = !(e && e[0] == '0'); }
+  { const char* e = std::getenv("ROMS_B200_FUSED_XCHG"); h->fused_mode = e ? std::atoi(e) : 2; }
   CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
   Flds& f = h->fl;
   std::memset(&f, 0, sizeof(f));

@@ -61,6 +61,10 @@ struct Halo {
   void* mapW = nullptr; void* mapE = nullptr;                                      // IPC mappings to close
   size_t box_cap = 0;                                                              // doubles per ghost column a slot can hold
   bool peer_on = false;
+  // second mailbox in the same allocation (after the first): the exchange fused into the barotropic sub-step kernel
+  // (dev.cuh Xchg, k_step2d.cu); off2 = its offset in doubles, identical on every rank
+  size_t off2 = 0;
+  bool fused_on = false;
 };
 
 constexpr int BOX_HDR = 64;                       // header doubles: [2] epoch [4] block counter [6] error
@@ -94,18 +98,8 @@ __device__ __forceinline__ double* field_elem(const FieldTab& t, int plane, int 
 // this epoch and copies the value into the ghost column.  Latency = one NVLink store flight.  Nothing a thread waits for
 // depends on another thread of this kernel (the neighbour's stores belong to its own, earlier-ordered work), so the spin
 // cannot deadlock.  Two parity slots suffice: a neighbour can only send epoch e+2 after it has received my epoch e+1, which
-// I send after my epoch-e kernel (including its unpack) has completed.
-__device__ __forceinline__ void ll_store(double* line, double v, unsigned tag) {
-  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"((unsigned)b), "r"(tag), "r"((unsigned)(b >> 32)), "r"(tag) : "memory");
-}
-__device__ __forceinline__ bool ll_load(const double* line, unsigned tag, double& v) {
-  unsigned lo, t0, hi, t1;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(line) : "memory");
-  v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
-  return t0 == tag && t1 == tag;
-}
-
+// I send after my epoch-e kernel (including its unpack) has completed.  (ll_store / ll_load: dev.cuh.)
+using rb::ll_load; using rb::ll_store;
 __global__ void __launch_bounds__(256) k_halo_xchg(FieldTab t, int P, int PL, int nj, int Istr, int Iend, int totE, int totW, size_t cap,
                                                    unsigned long long* hdr, double* box, double* boxE, double* boxW) {
   const unsigned long long e = hdr[2] + 1;                  // epoch of this exchange (bumped by the last CTA below)
@@ -186,6 +180,16 @@ int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names, cud
   k_pack<<<(totW + 255) / 256, 256, 0, s>>>(t, P, PL, nj, Iend + 1, NE, totW, H->recvE, 1);
   h->launches += 4;
   return cudaGetLastError() == cudaSuccess ? 0 : 8;
+}
+
+// Mailbox pointers of the fused sub-step exchange; false when the ring is not on the NVLink peer path (or ROMS_B200_FUSED_XCHG=0).
+bool fused_xchg_fill(roms_b200_state* h, rb::Xchg& x) {
+  Halo* H = h->halo;
+  if (!H || !H->peer_on || !H->fused_on || !H->off2) return false;
+  std::memset(&x, 0, sizeof(x));
+  x.Istr = h->b.Istr; x.Iend = h->b.Iend; x.nj = h->nj;
+  x.box = H->box + H->off2; x.boxE = H->boxE + H->off2; x.boxW = H->boxW + H->off2;
+  return true;
 }
 
 int halo_reduce_diag(roms_b200_state* h) {
@@ -283,7 +287,8 @@ int roms_b200_peer_export(roms_b200_handle h, char* out64) {
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return 8;
   if (!H->box) {
     H->box_cap = (size_t)(4 * (h->cfg.N + 1) + 8) * h->nj;        // the largest per-step exchange (step3d_uv: 4N + 4 planes)
-    const size_t bytes = box_doubles(H->box_cap) * sizeof(double);
+    H->off2 = (box_doubles(H->box_cap) + 15) / 16 * 16;
+    const size_t bytes = (H->off2 + rb::xbox_doubles(h->nj)) * sizeof(double);
     if (cudaMalloc(&H->box, bytes) != cudaSuccess) { cudaGetLastError(); return 8; }
     if (cudaMemset(H->box, 0, bytes) != cudaSuccess) return 8;
   }
@@ -316,15 +321,17 @@ int roms_b200_peer_enable(roms_b200_handle h, int on) {
   cudaStreamSynchronize(h->stream);
   drop_graphs(h);
   H->peer_on = on != 0;
+  { const char* e = std::getenv("ROMS_B200_FUSED_XCHG"); H->fused_on = H->peer_on && !(e && e[0] == '0'); }
   return 0;
 }
 
 // 1 if a peer exchange timed out waiting for a neighbour (results are then invalid), else 0
 int roms_b200_peer_error(roms_b200_handle h) {
   if (!h || !h->halo || !h->halo->box) return 0;
-  unsigned long long w = 0;
+  unsigned long long w = 0, w2 = 0;
   cudaMemcpy(&w, (unsigned long long*)h->halo->box + 6, sizeof(w), cudaMemcpyDeviceToHost);
-  return w != 0;
+  if (h->halo->off2) cudaMemcpy(&w2, (unsigned long long*)(h->halo->box + h->halo->off2) + 2, sizeof(w2), cudaMemcpyDeviceToHost);
+  return (w | w2) != 0;
 }
 
 }  // extern "C"

@@ -172,6 +172,39 @@ __device__ __forceinline__ void sweep_levels_deep(int N, Load load, Body body) {
   }
 }
 
+// ---- halo exchange fused into the barotropic sub-step kernel (multi-GPU ring over NVLink peer memory) ----------------
+// One exchange = the edge columns of up to XF 2-D fields (3 columns eastward, 2 westward, every row).  A sub-step kernel
+// PUSHES the edge values it produces straight into the neighbours' mailboxes as it stores them, and the NEXT sub-step
+// kernel starts by PULLING what its neighbours pushed into the ghost columns of its own arrays: no separate pack /
+// exchange / unpack kernels between the ~58 dependent sub-steps of a baroclinic step.  Every double travels as a 16-byte
+// line {lo, tag, hi, tag} (tag = low 32 bits of the exchange epoch; the flag-in-data scheme of NCCL's LL protocol, which
+// only relies on 8-byte store atomicity), so no fences or separate flags are needed.  XSLOTS epochs are kept apart.
+constexpr int XNW = 3, XNE = 2, XF = 4, XSLOTS = 4, XHDR = 16;     // XHDR doubles of header: [0] epoch, [1] CTA counter, [2] error
+struct Xchg {
+  int send, recv;                  // push this sub-step's edge columns / first pull the previous sub-step's
+  int nsend, nrecv;                // number of fields (3: zeta, ubar, vbar; 4: + rzeta)
+  int Istr, Iend, nj;              // tile bounds (a split launch may cover only part of them), rows per column
+  double* recvf[XF];               // arrays whose ghost columns the pull fills
+  double* boxE; double* boxW;      // east / west neighbour's mailbox (peer mapped)
+  double* box;                     // my mailbox; its header holds the epoch counter
+};
+__host__ __device__ inline size_t xslot_doubles(int nj) { return (size_t)2 * XF * nj * (XNW + XNE); }
+__host__ __device__ inline size_t xbox_doubles(int nj) { return XHDR + XSLOTS * xslot_doubles(nj); }
+// line of (field, row, column c) in the half of a slot filled by the west (c < XNW) / east (c < XNE) neighbour
+__device__ __forceinline__ size_t xline_w(int nj, int fld, int j, int c) { return 2 * (size_t)((fld * nj + j) * XNW + c); }
+__device__ __forceinline__ size_t xline_e(int nj, int fld, int j, int c) { return 2 * (size_t)(XF * nj * XNW + (fld * nj + j) * XNE + c); }
+
+__device__ __forceinline__ void ll_store(double* line, double v, unsigned tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"((unsigned)b), "r"(tag), "r"((unsigned)(b >> 32)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ bool ll_load(const double* line, unsigned tag, double& v) {
+  unsigned lo, t0, hi, t1;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(line) : "memory");
+  v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+  return t0 == tag && t1 == tag;
+}
+
 __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }   // Fortran MAX (first arg on ties)
 __device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
 

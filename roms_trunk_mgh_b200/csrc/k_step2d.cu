@@ -14,6 +14,7 @@
 // The kernel is latency-bound, not bandwidth-bound, so every stage issues ALL of its global loads back to back before the
 // first use (one memory wait per stage), the CTA has enough threads (NTH) to cover the (TX+1)x(TY+1) flux regions in a
 // single pass, and stage 0 also fetches the operands of stage 1.
+#include <cstring>
 #include "dev.cuh"
 #include "kernels.h"
 
@@ -56,7 +57,8 @@ __device__ __forceinline__ double lds_pol(const double* a, unsigned long long po
 #else
 #define lds_(a) (*(a))
 #endif
-__global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
+template <bool XCH>      // XCH: with the fused halo exchange (multi-GPU peer path); the single-tile instance carries none of it
+__global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x) {
 #if S2D_EVICT
   const unsigned long long l2pol = evict_first_policy();
 #endif
@@ -72,7 +74,16 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
   // Tile origin.  The row blocks cover the interior rows 1..Mm; the two wall rows 0 and Mm+1 (fast-time averages only) are
   // taken by the two warps that idle in stage 3, in the first / last row block -- for Mm = 256 that is 32 instead of 33
   // row blocks, i.e. 2048 CTAs = 6.9 waves of 2 x 148 resident CTAs instead of 7.1 (a whole extra wave).
-  const int i0 = xcol0(p, blockIdx.x * TX), j0 = 1 + blockIdx.y * TY;
+  // With the fused exchange the CTAs of the two edge column blocks are scheduled first (CTAs start in linear block order):
+  // their pushes are then on the wire while the interior of this sub-step is still being computed, and the next sub-step's
+  // edge CTAs -- first again -- find them delivered.
+  int bx = blockIdx.x, by = blockIdx.y;
+  if (XCH && gridDim.x >= 3) {
+    const int nbx = gridDim.x, nby = gridDim.y, bid = bx + nbx * by;
+    if (bid < 2 * nby) { bx = (bid & 1) ? nbx - 1 : 0; by = bid >> 1; }
+    else { const int r = bid - 2 * nby; bx = 1 + r % (nbx - 2); by = r / (nbx - 2); }
+  }
+  const int i0 = xcol0(p, bx * TX), j0 = 1 + by * TY;
   const int P = p.P, Mm = p.Mm;
   const bool PRED = p.predictor != 0;
   const bool FIRST = (p.iif == 1);
@@ -82,6 +93,47 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
   const double* __restrict__ zs = f.zeta[p.kstp];
   const double* __restrict__ pm = f.pm;
   const double* __restrict__ pn = f.pn;
+
+  // ---- fused halo exchange (dev.cuh Xchg): epochs; pull the ghost columns the previous sub-step's neighbours pushed.
+  // One thread per CTA reads the epoch (every thread doing so would serialise ~10^4 requests per launch on one L2 line).
+  __shared__ unsigned long long s_epoch;
+  unsigned long long xe0 = 0;
+  unsigned xtag = 0;
+  size_t xbase = 0;
+  if (XCH && (x.send | x.recv)) {
+    const bool needW = (i0 - HL < x.Istr), needE = (i0 + TX - 1 + HH > x.Iend);
+    if (tid == 0) s_epoch = *(volatile unsigned long long*)x.box;      // epoch of the latest completed push (same on every rank)
+    if (x.recv && (needW || needE)) {                                  // CTA-uniform
+      __syncthreads();
+      xe0 = s_epoch;
+      const unsigned tag = (unsigned)xe0;
+      const double* slot = x.box + XHDR + (xe0 & (XSLOTS - 1)) * xslot_doubles(x.nj);
+      const int nW = needW ? x.nrecv * SH * XNW : 0, nE = needE ? x.nrecv * SH * XNE : 0;
+      for (int idx = tid; idx < nW + nE; idx += NTH) {
+        const bool w = idx < nW;
+        const int q = w ? idx : idx - nW, nc = w ? XNW : XNE;
+        const int c = q % nc, r = (q / nc) % SH, fld = q / (nc * SH);
+        const int j = j0 - HL + r;
+        if (j >= 0 && j <= Mm + 1) {
+          const double* line = slot + (w ? xline_w(x.nj, fld, j, c) : xline_e(x.nj, fld, j, c));
+          double v;
+          const long long t0 = clock64();
+          while (!ll_load(line, tag, v)) {
+            if (clock64() - t0 > (5LL << 30)) { ((unsigned long long*)x.box)[2] = 1; break; }   // ~3 s: give up, the host reports it
+            __nanosleep(20);
+          }
+          x.recvf[fld][j * P + (w ? x.Istr - XNW + c : x.Iend + 1 + c)] = v;
+        }
+      }
+      __syncthreads();      // every ghost value this CTA reads below was written by this CTA above
+    }
+  }
+  auto push = [&](int fld, int i, int j, double v) {
+    if (i >= x.Iend - (XNW - 1)) ll_store(x.boxE + xbase + xline_w(x.nj, fld, j, i - (x.Iend - (XNW - 1))), v, xtag);   // -> east neighbour's west ghosts
+    if (i <= x.Istr + (XNE - 1)) ll_store(x.boxW + xbase + xline_e(x.nj, fld, j, i - x.Istr), v, xtag);                 // -> west neighbour's east ghosts
+  };
+
+  const Xchg& xc = x;     // (`x` is shadowed by the new velocity in stage 3)
 
   // ---- stages 0/1: Drhs, ubar, vbar, DUon, DVom on the staged region (two items per thread, loads first)
   {
@@ -104,6 +156,17 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
       if (s < NS) { sD[s] = ok[r] ? (zv[r] + hv[r]) : 0.0; sU[s] = ok[r] ? uv[r] : 0.0; sV[s] = ok[r] ? vv[r] : 0.0; }
     }
     __syncthreads();
+    if (XCH && x.send) {
+      xe0 = s_epoch;
+      const unsigned long long e = xe0 + 1;
+      xtag = (unsigned)e; xbase = XHDR + (e & (XSLOTS - 1)) * xslot_doubles(x.nj);
+      if (tid == 0) {
+        // this CTA has read the epoch; the CTA that completes the count publishes the new one (it is only read by later
+        // kernels of this stream)
+        unsigned long long* hdr = (unsigned long long*)x.box;
+        if (atomicAdd(&hdr[1], 1ULL) == (unsigned long long)gridDim.x * gridDim.y - 1) { hdr[1] = 0; __threadfence(); hdr[0] = e; }
+      }
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int s = tid + r * NTH;
@@ -187,6 +250,16 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
         if (za >= 1 && zb >= 1) {                                      // own points of this tile
           st_r_grad(f.zeta[p.knew], j * P, i, j, zeta_new, p);
           if (PRED) st_w(f.rzeta[p.krhs], j * P, i, dd, p);
+          if (XCH && x.send && (i >= x.Iend - (XNW - 1) || i <= x.Istr + (XNE - 1))) {
+            push(0, i, j, zeta_new);
+            if (j == 1) push(0, i, 0, zeta_new);
+            if (j == Mm) push(0, i, Mm + 1, zeta_new);
+            if (PRED) {                                                // rzeta has no wall-row values of its own: forward what is there
+              push(3, i, j, dd);
+              if (j == 1) push(3, i, 0, f.rzeta[p.krhs][i]);
+              if (j == Mm) push(3, i, Mm + 1, f.rzeta[p.krhs][(Mm + 1) * P + i]);
+            }
+          }
         }
         // advective UFx at rho(i,j) (:1104-1112)
         a_ufx = 0.25 * (U_(0, 0) + U_(1, 0) - c6 * (GXU(0, 0) + GXU(1, 0))) * (DU_(0, 0) + DU_(1, 0) - c6 * (GXDU(0, 0) + GXDU(1, 0)));
@@ -258,7 +331,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
   } else {
     const int w = (tid - TX * TY) >> 5;
     tx = tid & 31;
-    if (w == 0 && blockIdx.y == 0) ty = -1;                              // row 0
+    if (w == 0 && by == 0) ty = -1;                              // row 0
     else if (w == 1 && j0 <= Mm && j0 + TY - 1 >= Mm) ty = Mm + 1 - j0;  // row Mm+1, in the block that holds row Mm
     else return;
   }
@@ -362,6 +435,11 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
     }
     st_u_closed(f.ubar[p.knew], j * P, i, j, x, p);
     if (PRED) f.rubar[p.krhs][o] = rhs_u;
+    if (XCH && xc.send && (i >= xc.Iend - (XNW - 1) || i <= xc.Istr + (XNE - 1))) {
+      push(1, i, j, x);
+      if (j == 1) push(1, i, 0, p.gamma2 * x);
+      if (j == Mm) push(1, i, Mm + 1, p.gamma2 * x);
+    }
   }
   // ---- v-point (i,j)
   if (dov) {
@@ -407,16 +485,28 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f) {
     }
     st_v_closed(f.vbar[p.knew], j * P, i, j, x, p);
     if (PRED) f.rvbar[p.krhs][o] = rhs_v;
+    if (XCH && xc.send && (i >= xc.Iend - (XNW - 1) || i <= xc.Istr + (XNE - 1))) {
+      push(2, i, j, x);
+      if (j == 2) { push(2, i, 1, 0.0); push(2, i, 0, f.vbar[p.knew][i]); }   // row 1 is the wall (v = 0); row 0 is never written
+      if (j == Mm) push(2, i, Mm + 1, 0.0);
+    }
   }
 }
 
 // selected with ROMS_B200_STEP2D=tile (A/B measurements); the default is the row-marching kernel of k_step2d_m.cu
-void launch_step2d_tile(const Par& p, const Flds& f, cudaStream_t s) {
+void launch_step2d_tile(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x) {
   dim3 g((xspan(p) + TX - 1) / TX, (p.Mm + TY - 1) / TY);
   const size_t smem = (size_t)SMEM_DOUBLES * sizeof(double);
   static bool once = false;
-  if (!once) { cudaFuncSetAttribute(k_step2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }
-  k_step2d<<<g, NTH, smem, s>>>(p, f);
+  if (!once) {
+    cudaFuncSetAttribute(k_step2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_step2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    once = true;
+  }
+  Xchg none;
+  std::memset(&none, 0, sizeof(none));
+  if (x && (x->send || x->recv)) k_step2d<true><<<g, NTH, smem, s>>>(p, f, *x);
+  else k_step2d<false><<<g, NTH, smem, s>>>(p, f, none);
 }
 
 }  // namespace rb

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(TXM + 32, (TXM == 128) ? S2M_MINB : S2M_MINB64
 }
 
 // ---- tile kernel (k_step2d.cu), kept for A/B measurements: ROMS_B200_STEP2D=tile ----------------------------------------
-void launch_step2d_tile(const Par& p, const Flds& f, cudaStream_t s);
+void launch_step2d_tile(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x);
 
 template <int TXM>
 static int occupancy_m() {
@@ -433,12 +433,12 @@ static void launch_m(const Par& p, const Flds& f, cudaStream_t s, int JL) {
   k_step2d_m<TXM><<<g, TXM + 32, smem, s>>>(p, f, JL);
 }
 
-void launch_step2d(const Par& p, const Flds& f, cudaStream_t s) {
+void launch_step2d(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x) {
   // default: the tile kernel.  The marching kernel is exact and moves half the bytes through L1, but a 2048x256 field gives it
   // only ~2.5 warps per scheduler, too few to hide the FP64 and DRAM latency of a row iteration (profiles/README.md): 92 us
   // per launch against 58 us.  ROMS_B200_STEP2D=march selects it.
   static const int mode = [] { const char* e = std::getenv("ROMS_B200_STEP2D"); return (e && e[0] == 'm') ? 1 : 0; }();
-  if (mode == 0) { launch_step2d_tile(p, f, s); return; }
+  if (mode == 0 || x) { launch_step2d_tile(p, f, s, x); return; }      // the fused halo exchange lives in the tile kernel
   static const int jl_env = [] { const char* e = std::getenv("ROMS_B200_S2M_JL"); return e ? std::atoi(e) : 0; }();      // tuning aids
   static const int tx_env = [] { const char* e = std::getenv("ROMS_B200_S2M_TX"); return e ? std::atoi(e) : 0; }();
   static const int nsm = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();

@@ -18,7 +18,8 @@ void launch_t3dmix2_s(const Par& p, const Flds& f, cudaStream_t s);
 void launch_t3dmix2_geo(const Par& p, const Flds& f, cudaStream_t s);
 void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s);
 void launch_uv3dmix2(const Par& p, const Flds& f, cudaStream_t s);
-void launch_step2d(const Par& p, const Flds& f, cudaStream_t s);
+// x != nullptr: this sub-step also pulls / pushes its xi-halo through NVLink peer memory (dev.cuh Xchg)
+void launch_step2d(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x = nullptr);
 void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s);
 void launch_step3d_t(const Par& p, const Flds& f, cudaStream_t s);
 // diag: partial[] must hold 16 doubles per block row; out16 on device

@@ -62,6 +62,7 @@ struct roms_b200_state {
   bool edge_pending = false, halo_pending = false;   // main stream has not yet waited for the latest ev_edge / ev_halo
   // CUDA graphs of whole time steps, keyed by the stepping state at the start of the step (api.cu one_step)
   int fuse_tmix = 1;      // whole-step path: t3dmix2_s folded into pre_step3d_t (ROMS_B200_FUSE_TMIX=0 keeps the separate kernel)
+  int fused_mode = 2;     // step2d halo exchange inside the kernels: 0 off, 1 one launch per sub-step, 2 edge / interior split launches
   bool in_step = false;   // inside step_phases (cross-routine fusions are only legal there: run_phase keeps routine granularity)
   int use_graphs = 1;
   std::map<int, void*> graphs;     // key -> rbi::StepGraph*
@@ -75,6 +76,8 @@ struct StepGraph { cudaGraphExec_t exec; int indx1, iif, kstp, krhs, knew, predi
 namespace rbi {
 // Halo exchange of the named fields along the xi ring (mp_exchange2d/3d/4d semantics); no-op without an attached comm.
 int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names, cudaStream_t s);
+// mailboxes of the exchange fused into the step2d kernel (false: not available, use halo_exchange)
+bool fused_xchg_fill(roms_b200_state* h, rb::Xchg& x);
 // cross-tile reduction of the 16-double diag buffer: [0..2] sum, [3..12] max
 int halo_reduce_diag(roms_b200_state* h);
 void halo_destroy(roms_b200_state* h);
