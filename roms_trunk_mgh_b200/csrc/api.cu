@@ -367,6 +367,13 @@ int step_phases_body(roms_b200_state* h, bool with_diag) {
   static const int seq1[] = {ROMS_B200_SET_MASSFLUX, ROMS_B200_RHO_EOS};
   for (int ph : seq1) { int rc = run_phase_async(h, ph); if (rc) return rc; }
   if (with_diag) { int rc = run_phase_async(h, ROMS_B200_DIAG); if (rc) return rc; }
+  if (h->ev_forcing) {
+    // forcing uploaded by roms_b200_step_forced on the copy stream: needed from set_vbc on.  Inside a graph capture this
+    // becomes an event-wait node on the (external) event, evaluated at every replay.
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(h->stream, &cs);
+    cudaStreamWaitEvent(h->stream, h->ev_forcing, cs == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : 0);
+  }
   static const int seq2[] = {ROMS_B200_SET_VBC, ROMS_B200_ANA_VMIX, ROMS_B200_OMEGA};
   for (int ph : seq2) { int rc = run_phase_async(h, ph); if (rc) return rc; }
   if (h->cfg.wvelocity_every_step) { int rc = run_phase_async(h, ROMS_B200_WVELOCITY); if (rc) return rc; }
@@ -619,6 +626,7 @@ int roms_b200_destroy(roms_b200_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   drop_graphs(h);
   halo_destroy(h);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_forcing); cudaEventDestroy(h->ev_step_in); }
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_diag_out) cudaFreeHost(h->h_diag_out);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -754,6 +762,21 @@ int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double*
   const size_t dp = (size_t)h->par.P * sizeof(double), sp = (size_t)h->ni * sizeof(double);
   const double* src[3] = {sustr, svstr, stflux_temp};
   const char* nm[3] = {"sustr", "svstr", "stflux_0"};
+  // single tile: upload on the copy stream, overlapped with set_massflux / rho_eos / diag of this step (step_phases_body waits
+  // for ev_forcing before set_vbc).  With a ring attached the uploaded fields also need a halo exchange: keep them on the
+  // compute stream.
+  cudaStream_t cps = h->stream;
+  if (!h->halo && (sustr || svstr || stflux_temp)) {
+    if (!h->copy_stream) {
+      CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&h->ev_forcing, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_step_in, cudaEventDisableTiming));
+      drop_graphs(h);                       // the captured steps must contain the wait node
+    }
+    cps = h->copy_stream;
+    CK(cudaEventRecord(h->ev_step_in, h->stream));          // earlier asynchronous steps may still read the forcing arrays
+    CK(cudaStreamWaitEvent(cps, h->ev_step_in, 0));
+  }
   for (int q = 0; q < 3; ++q) {
     if (!src[q]) continue;
     const double* stage = src[q];
@@ -764,9 +787,10 @@ int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double*
     }
     double* dev = h->reg[nm[q]].base + h->ioff + (h->b.LBi - h->LBi_dev);
     // one dense DMA over PCIe, then the re-pitch on the device (a row-by-row 2-D copy from host memory is several times slower)
-    CK(cudaMemcpyAsync(h->d_stage + q * want, stage, want * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpy2DAsync(dev, dp, h->d_stage + q * want, sp, sp, (size_t)h->nj, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_stage + q * want, stage, want * sizeof(double), cudaMemcpyHostToDevice, cps));
+    CK(cudaMemcpy2DAsync(dev, dp, h->d_stage + q * want, sp, sp, (size_t)h->nj, cudaMemcpyDeviceToDevice, cps));
   }
+  if (cps != h->stream) CK(cudaEventRecord(h->ev_forcing, cps));
   if (h->halo) {
     std::vector<std::string> up;
     for (int q = 0; q < 3; ++q) if (src[q]) up.push_back(nm[q]);

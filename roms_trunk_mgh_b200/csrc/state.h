@@ -50,6 +50,9 @@ struct roms_b200_state {
   double* d_diag_partial = nullptr; double* d_diag_out = nullptr; double* h_diag_out = nullptr;
   double* h_pinned = nullptr; size_t pinned_n = 0; double* d_stage = nullptr;
   std::vector<std::pair<void*, size_t>> host_pinned;    // caller memory pinned with roms_b200_register_host
+  // step_forced: this step's surface forcing is uploaded on its own stream while the first phases of the step (which do not
+  // read it) already run; the step waits for ev_forcing just before set_vbc
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_forcing = nullptr, ev_step_in = nullptr;
   // profiling
   int profile = 0; double phase_ms[32]; long long launches = 0;
   bool all_diff2_zero = true;
