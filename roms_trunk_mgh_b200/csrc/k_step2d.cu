@@ -39,6 +39,9 @@ static_assert(TX == 32 && TX * ZH + ZH <= NTH && NS <= 2 * NTH && TX * TY + 64 <
 #ifndef S2D_MINB
 #define S2D_MINB 2
 #endif
+#ifndef S2D_PF
+#define S2D_PF 0        // L2 prefetch of the stage 2b / 3 operands at kernel start: measured slower (3.37 vs 3.09 ms per loop)
+#endif
 #ifndef S2D_EVICT
 #define S2D_EVICT 1      // 1: the static operands (metrics, h, rhoA/rhoS, rufrc/rvfrc) are loaded with an L2 evict-first hint so that
 #endif                   // they do not displace the time-varying barotropic state (86 MB at BENCHMARK3) from the 126 MB L2
@@ -135,6 +138,39 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
 
   const Xchg& xc = x;     // (`x` is shadowed by the new velocity in stage 3)
 
+  // Stage-2 thread map: warps 0..ZH-1 take one region row each (32 columns, so a warp never straddles a row: conflict-free
+  // 64-bit shared-memory accesses), the first ZH lanes of warp ZH take the 33rd column.
+  const int za = (tid < TX * ZH) ? (tid & (TX - 1)) : TX;
+  const int zb = (tid < TX * ZH) ? (tid / TX) : (tid - TX * ZH);
+  const int zi = zb * ZW + za;
+  // The global operands of stage 2a do not depend on shared memory: they are requested up front, together with those of
+  // stage 0, so that the CTA pays one DRAM latency for both.
+  const bool okA = active && tid < TX * ZH + ZH && (j0 - 1 + zb) >= 1 && (j0 - 1 + zb) <= Mm && (i0 - 1 + za) <= p.Iend;
+  const int qA = okA ? (j0 - 1 + zb) * P + (i0 - 1 + za) : (j0 * P + i0);
+  const double zs_q = zs[qA], zr_q = zr[qA], pm_q = lds_(pm + qA), pn_q = lds_(pn + qA), h_q = lds_(h + qA), rS = lds_(f.rhoS + qA), rA = lds_(f.rhoA + qA);
+  const double fomn_q = lds_(f.fomn + qA), visc_q = lds_(f.visc2_r + qA), pmon_q = lds_(f.pmon_r + qA), pnom_q = lds_(f.pnom_r + qA);
+  const double pnE_a = lds_(pn + qA + 1), pnW_a = lds_(pn + qA - 1), pmN_a = lds_(pm + qA + P), pmS_a = lds_(pm + qA - P), onr = lds_(f.on_r + qA), omr = lds_(f.om_r + qA);
+  double dndx_q = 0.0, dmde_q = 0.0, rz_s = 0.0, rz_p = 0.0;
+  if (p.curvgrid) { dndx_q = lds_(f.dndx + qA); dmde_q = lds_(f.dmde + qA); }
+  if (!FIRST && !PRED) { rz_s = f.rzeta[p.kstp][qA]; rz_p = f.rzeta[p.ptsk][qA]; }
+#if S2D_PF
+  // L2 prefetch of the operands of stages 2b and 3 (18 arrays x TY rows x two 128-byte lines, one request per thread): no
+  // register cost, and the loads issued two barriers later find their lines in L2.
+  {
+    const int a = tid >> 4, r = (tid >> 1) & 7, half = tid & 1;
+    const double* pa = nullptr;
+    switch (a) {
+      case 0: pa = f.DU_avg2; break; case 1: pa = f.DV_avg2; break; case 2: pa = f.rufrc; break; case 3: pa = f.rvfrc; break;
+      case 4: pa = f.ubar[p.kstp]; break; case 5: pa = f.vbar[p.kstp]; break;
+      case 6: pa = f.visc2_p; break; case 7: pa = f.pmon_p; break; case 8: pa = f.pnom_p; break; case 9: pa = f.om_p; break; case 10: pa = f.on_p; break;
+      case 11: if (PRED && !FIRST) pa = f.Zt_avg1; break; case 12: if (PRED && !FIRST) pa = f.DU_avg1; break; case 13: if (PRED && !FIRST) pa = f.DV_avg1; break;
+      case 14: if (!PRED && !FIRST) pa = f.rubar[p.kstp]; break; case 15: if (!PRED && !FIRST) pa = f.rubar[p.ptsk]; break;
+      case 16: if (!PRED && !FIRST) pa = f.rvbar[p.kstp]; break; case 17: if (!PRED && !FIRST) pa = f.rvbar[p.ptsk]; break;
+      default: break;
+    }
+    if (pa && r < TY && j0 + r <= Mm + 1) pf_l2(pa + (j0 + r) * P + i0 + half * 16);
+  }
+#endif
   // ---- stages 0/1: Drhs, ubar, vbar, DUon, DVom on the staged region (two items per thread, loads first)
   {
     const double* __restrict__ ur = f.ubar[p.krhs];
@@ -204,11 +240,6 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
 #define GYV(di, dj) (V_(di, (dj)-1) - 2.0 * V_(di, dj) + V_(di, (dj) + 1))
 #define GYDV(di, dj) (DV_(di, (dj)-1) - 2.0 * DV_(di, dj) + DV_(di, (dj) + 1))
 
-  // Stage-2 thread map: warps 0..ZH-1 take one region row each (32 columns, so a warp never straddles a row: conflict-free
-  // 64-bit shared-memory accesses), the first ZH lanes of warp ZH take the 33rd column.
-  const int za = (tid < TX * ZH) ? (tid & (TX - 1)) : TX;
-  const int zb = (tid < TX * ZH) ? (tid / TX) : (tid - TX * ZH);
-  const int zi = zb * ZW + za;
   if (active && tid < TX * ZH + ZH) {
     const double c6 = 1.0 / 6.0;
     // ---- stage 2a: rho-point quantities at (i0-1+za, j0-1+zb)
@@ -217,15 +248,8 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
       const int c0 = (zb + HL - 1) * SW + (za + HL - 1);               // staged index of (i,j)
       double Dnew = 0.0, zwrk = 0.0, gz = 0.0, gz2 = 0.0, gsa = 0.0;
       double a_ufx = 0.0, a_vfe = 0.0, c_ufx = 0.0, c_vfe = 0.0, k_ufx = 0.0, k_vfe = 0.0, v_ufx = 0.0, v_vfe = 0.0;
-      if (j >= 1 && j <= Mm && i <= p.Iend) {
-        const int q = j * P + i;
-        // all global operands of this stage, issued back to back
-        const double zs_q = zs[q], zr_q = zr[q], pm_q = lds_(pm + q), pn_q = lds_(pn + q), h_q = lds_(h + q), rS = lds_(f.rhoS + q), rA = lds_(f.rhoA + q);
-        const double fomn_q = lds_(f.fomn + q), visc_q = lds_(f.visc2_r + q), pmon_q = lds_(f.pmon_r + q), pnom_q = lds_(f.pnom_r + q);
-        const double pnE = lds_(pn + q + 1), pnW = lds_(pn + q - 1), pmN = lds_(pm + q + P), pmS = lds_(pm + q - P), onr = lds_(f.on_r + q), omr = lds_(f.om_r + q);
-        double dndx_q = 0.0, dmde_q = 0.0, rz_s = 0.0, rz_p = 0.0;
-        if (p.curvgrid) { dndx_q = lds_(f.dndx + q); dmde_q = lds_(f.dmde + q); }
-        if (!FIRST && !PRED) { rz_s = f.rzeta[p.kstp][q]; rz_p = f.rzeta[p.ptsk][q]; }
+      if (okA) {
+        const int q = qA;
         // new free surface (:770-851)
         const double dd = (DU_(0, 0) - DU_(1, 0)) + (DV_(0, 0) - DV_(0, 1));
         double zeta_new;
@@ -283,8 +307,8 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
         // viscous stress at rho(i,j) (:1400-1414)
         {
           const double cr = visc_q * D0 * 0.5 *
-                            (pmon_q * ((pn_q + pnE) * U_(1, 0) - (pnW + pn_q) * U_(0, 0)) -
-                             pnom_q * ((pm_q + pmN) * V_(0, 1) - (pmS + pm_q) * V_(0, 0)));
+                            (pmon_q * ((pn_q + pnE_a) * U_(1, 0) - (pnW_a + pn_q) * U_(0, 0)) -
+                             pnom_q * ((pm_q + pmN_a) * V_(0, 1) - (pmS_a + pm_q) * V_(0, 0)));
           v_ufx = onr * onr * cr; v_vfe = omr * omr * cr;
         }
       }
@@ -321,22 +345,25 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
       aUFe[zi] = a_ufe; aVFx[zi] = a_vfx; vUFe[zi] = v_ufe; vVFx[zi] = v_vfx;
     }
   }
-  __syncthreads();
-
-  // ---- stage 3: one thread per rho point of the tile (+ one warp each for wall rows 0 and Mm+1)
+  // ---- stage 3: one thread per rho point of the tile (+ one warp each for wall rows 0 and Mm+1).  None of its global
+  // operands depends on what stage 2 stored, so they are requested BEFORE the barrier that ends stage 2: the loads are in
+  // flight while the slower warps of the CTA finish their fluxes.
   int tx, ty;
+  bool live = true;
   if (tid < TX * TY) {
     tx = tid % TX; ty = tid / TX;
-    if (j0 + ty > Mm) return;
+    if (j0 + ty > Mm) live = false;
   } else {
     const int w = (tid - TX * TY) >> 5;
     tx = tid & 31;
+    ty = 0;
     if (w == 0 && by == 0) ty = -1;                              // row 0
     else if (w == 1 && j0 <= Mm && j0 + TY - 1 >= Mm) ty = Mm + 1 - j0;  // row Mm+1, in the block that holds row Mm
-    else return;
+    else live = false;
   }
+  if (i0 + tx > p.Iend) live = false;
+  if (!live) { tx = 0; ty = 0; }                                        // dummy point of this tile: keeps the loads in bounds
   const int i = i0 + tx, j = j0 + ty;
-  if (i > p.Iend) return;
   const int o = j * P + i;
   const bool inner = active && j >= 1 && j <= Mm;
   const bool dov = inner && (j >= p.JstrV);
@@ -356,6 +383,8 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
   double rub_s = 0.0, rub_p = 0.0, rvb_s = 0.0, rvb_p = 0.0, ru_n = 0.0, ru_so = 0.0, rv_n = 0.0, rv_so = 0.0;
   if (!FIRST && !PRED) { rub_s = f.rubar[p.kstp][o]; rub_p = f.rubar[p.ptsk][o]; rvb_s = f.rvbar[p.kstp][o]; rvb_p = f.rvbar[p.ptsk][o]; }
   if (FIRST && PRED && p.istart >= 1) { ru_n = f.ru[p.nnew][o]; rv_n = f.rv[p.nnew][o]; ru_so = f.ru[p.nstp][o]; rv_so = f.rv[p.nstp][o]; }
+  __syncthreads();
+  if (!live) return;
 
   // fast-time averages (:614-682); rows 0..Mm+1 for Zt/DU, rows 1..Mm+1 for DV
   {

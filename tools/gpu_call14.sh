@@ -1,0 +1,4 @@
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" > gpurun_out/rc.log
+python tools/sweep.py step2d_loop base > gpurun_out/sweep5.log 2>&1
