@@ -21,6 +21,9 @@ __device__ __forceinline__ double d2y(const double* __restrict__ A, int o, int P
 #ifndef RHS_PF
 #define RHS_PF 4          // L2 prefetch distance (levels) in k_rhs3d
 #endif
+#ifndef UVM_BX
+#define UVM_BX 64
+#endif
 #ifndef UVM_PF
 #define UVM_PF 4          // same for k_uv3dmix2
 #endif
@@ -291,6 +294,6 @@ __global__ void __launch_bounds__(128, UVM_MINB) k_uv3dmix2(Par p, Flds f) {
 
 static inline dim3 g2(dim3 b, int ni, int nj, int nz = 1) { return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz); }
 void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(RHS_BX, 128 / RHS_BX); k_rhs3d<<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f); }
-void launch_uv3dmix2(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 2); k_uv3dmix2<<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f); }
+void launch_uv3dmix2(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(UVM_BX, 128 / UVM_BX); k_uv3dmix2<<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f); }
 
 }  // namespace rb

@@ -33,7 +33,7 @@ namespace rb {
 #define S3T_PP true      // ping-pong level buffers in k_step3d_t (see sweep_levels): pays once the register budget allows ~164
 #endif
 #ifndef S3T_MINB
-#define S3T_MINB 6
+#define S3T_MINB 5
 #endif
 #ifndef S3U_RING
 #define S3U_RING 0        // > 0: pass 1 of k_step3d_uv streams its operands through a per-thread shared-memory ring of this many
