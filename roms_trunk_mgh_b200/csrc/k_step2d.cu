@@ -11,9 +11,11 @@
 //            psi-point fluxes: advective UFe, VFx (:1141-1150,:1213-1222), viscous UFe, VFx (:1415-1430)
 //   stage 3  fast-time averages (:614-682), pressure gradient (:944-1019), flux divergences, 2-D/3-D coupling
 //            (:1884-2065), LF / AM3 stepping (:2098-2255), rhs history (:2420-2430), closed-wall BCs, periodic images.
-// The kernel is latency-bound, not bandwidth-bound, so every stage issues ALL of its global loads back to back before the
-// first use (one memory wait per stage), the CTA has enough threads (NTH) to cover the (TX+1)x(TY+1) flux regions in a
-// single pass, and stage 0 also fetches the operands of stage 1.
+// The kernel is bound by the L1 / shared-memory data pipe and by latency, not by HBM bandwidth (profiles/README.md), so the
+// global operands of a stage are requested as early as the register budget allows -- those of stages 0, 1 and 2a at the top
+// of the kernel, those of stage 3 before the barrier that ends stage 2 -- and the CTA has enough threads (NTH) to cover the
+// (TX+1)x(TY+1) flux regions in a single pass.  On a ring of tiles the xi-halo exchange of the sub-step is part of this
+// kernel (template XCH, dev.cuh Xchg).
 #include <cstring>
 #include "dev.cuh"
 #include "kernels.h"
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
   }
 }
 
-// selected with ROMS_B200_STEP2D=tile (A/B measurements); the default is the row-marching kernel of k_step2d_m.cu
+// the default step2d kernel (launch_step2d in k_step2d_m.cu dispatches; ROMS_B200_STEP2D=march selects the marching variant)
 void launch_step2d_tile(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x) {
   dim3 g((xspan(p) + TX - 1) / TX, (p.Mm + TY - 1) / TY);
   const size_t smem = (size_t)SMEM_DOUBLES * sizeof(double);
