@@ -205,6 +205,11 @@ __device__ __forceinline__ bool ll_load(const double* line, unsigned tag, double
   return t0 == tag && t1 == tag;
 }
 
+// Function attributes (opt-in dynamic shared memory) are per device: launch wrappers remember what they set per device, so
+// a process that drives several tiles on several GPUs (one handle each) gets them on every one.
+constexpr int MAXDEV = 64;
+inline int cur_dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < MAXDEV) ? d : 0; }
+
 __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }   // Fortran MAX (first arg on ties)
 __device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
 

@@ -528,7 +528,8 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
 void launch_step2d_tile(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x) {
   dim3 g((xspan(p) + TX - 1) / TX, (p.Mm + TY - 1) / TY);
   const size_t smem = (size_t)SMEM_DOUBLES * sizeof(double);
-  static bool once = false;
+  static bool done[MAXDEV] = {false};
+  bool& once = done[cur_dev()];
   if (!once) {
     cudaFuncSetAttribute(k_step2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_step2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -417,7 +417,8 @@ template <int TXM>
 static int occupancy_m() {
   constexpr int CW = TXM + 5;
   const size_t smem = (size_t)(5 * 4 + 9 + 4) * CW * sizeof(double);
-  static int occ = 0;
+  static int occs[MAXDEV] = {0};
+  int& occ = occs[cur_dev()];
   if (!occ) {
     cudaFuncSetAttribute(k_step2d_m<TXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step2d_m<TXM>, TXM + 32, smem) != cudaSuccess || occ < 1) occ = 1;

@@ -405,8 +405,9 @@ static void allow_smem(K kern, size_t bytes) { cudaFuncSetAttribute(kern, cudaFu
 
 void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s) {
   const size_t sm = smem_cols_uv(p.N);
-  static size_t allowed = 0;
-  if (sm > allowed) { allow_smem(k_step3d_uv<0>, sm); allow_smem(k_step3d_uv<1>, sm); allowed = sm; }
+  static size_t allowed[MAXDEV] = {0};
+  size_t& al = allowed[cur_dev()];
+  if (sm > al) { allow_smem(k_step3d_uv<0>, sm); allow_smem(k_step3d_uv<1>, sm); al = sm; }
   const int nbx = (xspan(p) + TS - 1) / TS;
   k_step3d_uv<0><<<dim3(nbx, p.Mm), TS, sm, s>>>(p, f);
   k_step3d_uv<1><<<dim3(nbx, p.Mm - 1), TS, sm, s>>>(p, f);
@@ -415,8 +416,9 @@ void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s) {
 template <int H, int V>
 static void launch_s3t(const Par& p, const Flds& f, cudaStream_t s) {
   const size_t sm = smem_cols_t(p.N);
-  static size_t allowed = 0;
-  if (sm > allowed) { allow_smem(k_step3d_t<H, V>, sm); allowed = sm; }
+  static size_t allowed[MAXDEV] = {0};
+  size_t& al = allowed[cur_dev()];
+  if (sm > al) { allow_smem(k_step3d_t<H, V>, sm); al = sm; }
   const int nbx = (xspan(p) + TS - 1) / TS;
   k_step3d_t<H, V><<<dim3(nbx * p.NT, p.Mm), TS, sm, s>>>(p, f);
 }
