@@ -18,7 +18,10 @@ namespace rb {
 #define S3D_TS 64
 #endif
 #ifndef S3D_CH
-#define S3D_CH 5
+#define S3D_CH 6
+#endif
+#ifndef S3T_CH
+#define S3T_CH 10
 #endif
 #ifndef S3D_MINB
 #define S3D_MINB 7
@@ -54,7 +57,8 @@ namespace rb {
 #define S3T_PF2 0         // same for k_step3d_t
 #endif
 constexpr int TS = S3D_TS;   // threads (columns) per block
-constexpr int CH = S3D_CH;   // levels per batch of independent loads in the downward / coupling passes
+constexpr int CH = S3D_CH;   // levels per batch of independent loads in the downward / coupling passes of k_step3d_uv
+constexpr int CHT = S3T_CH;  // ... and in the back substitution of k_step3d_t (profiles/r01_sweep_batch_depth.log)
 static_assert(EDGE_W % TS == 0, "split launches need CTA widths that divide EDGE_W");
 
 // One forward-elimination step of the spline system for row m = k-1 once level k is known
@@ -369,17 +373,17 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
   {
     double dk = 0.0;
     double ak = dk * AKN;
-    for (int kt = N; kt >= 1; kt -= CH) {
-      double lx[CH], lh[CH], la[CH];
+    for (int kt = N; kt >= 1; kt -= CHT) {
+      double lx[CHT], lh[CHT], la[CHT];
 #pragma unroll
-      for (int q = 0; q < CH; ++q) {
+      for (int q = 0; q < CHT; ++q) {
         const int k = (kt - q >= 1) ? kt - q : 1;
         const int o = o2 + k * PL + i;
         pf_dn<S3T_PF2>(tn, o, k, PL); pf_dn<S3T_PF2>(Hz, o, k, PL); pf_dn<S3T_PF2>(Akt, o - PL, k, PL);
         lx[q] = tn[o]; lh[q] = Hz[o]; la[q] = Akt[o - PL];
       }
 #pragma unroll
-      for (int q = 0; q < CH; ++q) {
+      for (int q = 0; q < CHT; ++q) {
         const int k = kt - q;
         if (k >= 1) {
           const double ok = 1.0 / lh[q];
