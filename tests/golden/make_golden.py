@@ -35,4 +35,14 @@ json.dump(kat, open(os.path.join(HERE, "reference_kat.json"), "w"), indent=1)
 o = orc.Oracle(orc.APP_UPWELLING)
 o.step(10)
 np.savez_compressed(os.path.join(HERE, "upwelling_10steps.npz"), **{n: o.field(n).copy() for n in ("zeta1", "u1", "v1", "t1_0")})
+# SEAMOUNT (A4/A4 tracers, MIX_GEO_TS, QDRAG, no-slip) and a small BENCHMARK (nonlinear EOS, CURVGRID, U3/C4, MIX_S_TS): the
+# state the GPU parity tests must reproduce (tests/test_gpu_parity.py::test_cuda_path_against_committed_golden_vectors)
+GOLD_CASES = {"seamount_6steps": (orc.APP_SEAMOUNT, {}, 6), "benchmark_64x32x10_6steps": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10), 6)}
+for name, (app, kw, nsteps) in GOLD_CASES.items():
+    o = orc.Oracle(app, **kw)
+    o.run_phase("set_data"); o.run_phase("ini")
+    o.step(nsteps)
+    NT = int(o.opt("NT"))
+    names = ["zeta1", "ubar1", "vbar1", "u1", "v1", "rho", "W"] + [f"t1_{it}" for it in range(NT)]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **{n: o.field(n).copy() for n in names})
 print("golden fixtures written")

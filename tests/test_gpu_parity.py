@@ -349,3 +349,31 @@ def test_tiling_invariance_across_gpus(mode):
            "--master-port", "29533", os.path.join(here, "mgpu_check.py"), "512", "64", "30", "6"]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "BITWISE-IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+GOLDEN = {"seamount_6steps": ("seamount", 6), "benchmark_64x32x10_6steps": ("benchmark", 6), "upwelling_10steps": ("upwelling", 10)}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN))
+def test_cuda_path_against_committed_golden_vectors(name):
+    """The CUDA path against the committed fixtures of tests/golden/ (oracle-generated, see make_golden.py): bit-exact with
+    the strict library (UPWELLING: 1e-12 relative, its ANA_VMIX evaluates exp() on the device), and with the production
+    library <= 1e-8 relative on zeta/ubar/vbar/u/v, 1e-12 on tracers and rho, 1e-7 on the diagnosed omega."""
+    case, nsteps = GOLDEN[name]
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    app, kw = CASES[case] if case in CASES else (orc.APP_UPWELLING, {})
+    for strict in (True, False):
+        o, t = make_pair(app, strict=strict, **kw)
+        for _ in range(nsteps):
+            o.step(1)                                         # the oracle only supplies the (time-dependent) wind stress here
+            t.set("sustr", o.field("sustr")); t.set("svstr", o.field("svstr"))
+            t.main3d(1)
+        for n in g.files:
+            a, b = g[n], t.get(n)
+            err = float(np.max(np.abs(a - b))) / max(float(np.max(np.abs(a))), 1e-300)
+            if strict and case != "upwelling":
+                assert np.array_equal(a, b), (name, n, err)
+            else:
+                tol = 1e-12 if (strict or n.startswith("t") or n == "rho") else (1e-7 if n == "W" else 1e-8)
+                assert err <= tol, (name, n, err, tol)
+        t.close()

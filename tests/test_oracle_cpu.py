@@ -206,3 +206,16 @@ def test_cabi_rejects_bad_config_and_has_no_cpu_fallback():
     import torch
     if not torch.cuda.is_available():
         assert _lib.load().roms_b200_create(ctypes.byref(cfg), ctypes.byref(h)) == 8  # no device -> fatal, never a CPU path
+
+
+@pytest.mark.parametrize("name,app,kw,nsteps", [("seamount_6steps", orc.APP_SEAMOUNT, {}, 6),
+                                                ("benchmark_64x32x10_6steps", orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10), 6)])
+def test_oracle_regression_golden_vectors(name, app, kw, nsteps):
+    """Self-generated regression vectors (tests/golden/make_golden.py, marked oracle_generated there): the state the GPU
+    parity tests must reproduce; here they pin the oracle itself against accidental edits."""
+    g = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    o = orc.Oracle(app, **kw)
+    o.run_phase("set_data"); o.run_phase("ini")
+    o.step(nsteps)
+    for n in g.files:
+        assert np.array_equal(o.field(n), g[n]), n
