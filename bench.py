@@ -275,7 +275,16 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "roofline_step": {"b_alg_bytes_per_gp_step": balg, "achieved_gbs": step_gbs, "frac": step_gbs / (peak * world)},
             "phase_ms": prof}
-    if rank == 0 and not a.no_cpu:
+    if dist is not None:
+        # a neighbour that never delivered its halo (NVLink peer path: the spin gives up after ~3 s) invalidates the run
+        import torch
+        bad = torch.tensor([int(t.L.roms_b200_peer_error(t.h))], device="cuda")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            sys.stderr.write("bench.py: a halo exchange timed out; results are invalid, no line printed\n")
+            dist.destroy_process_group()
+            return 1
+    if rank == 0 and world == 1 and not a.no_cpu:
         try:
             nth = min(ncores, 32)
             cv, csec, tiles = cpu_run((Lm, Mm, N), 2, 1, nth)
