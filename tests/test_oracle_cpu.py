@@ -219,3 +219,117 @@ def test_oracle_regression_golden_vectors(name, app, kw, nsteps):
     o.step(nsteps)
     for n in g.files:
         assert np.array_equal(o.field(n), g[n]), n
+
+
+@pytest.mark.parametrize("H", [25.0, 50.0])
+def test_physics_kat_shallow_water_wave_speed(H):
+    """Analytical known answer that does not come from the restatement itself: on a flat bottom without rotation and
+    stratification, a small free-surface bump splits into two pulses that travel at c = sqrt(g*H).  This exercises the whole
+    barotropic engine (step2d predictor/corrector, set_weights filter centred on the baroclinic step, 2-D/3-D coupling,
+    set_zeta): the right-going pulse of the fast-time-averaged free surface must advance c*dt per baroclinic step."""
+    o = orc.Oracle(orc.APP_UPWELLING)
+    o.run_phase("set_data")
+    o.field("h")[...] = H
+    o.field("f")[...] = 0.0; o.field("fomn")[...] = 0.0
+    for n in ("t1_0", "t2_0"):
+        o.field(n)[...] = 14.0
+    o.run_phase("ini")
+    x = np.arange(-2, 44)                                   # xi index of the array columns (LBi = -2)
+    bump = 0.01 * np.exp(-((x - 20.5) / 2.5) ** 2)
+    for n in ("zeta1", "zeta2", "zeta3", "Zt_avg1"):
+        o.field(n)[0, :, :] = bump[None, :]
+    cen = []
+    for _ in range(2):
+        o.step(1)
+        o.field("sustr")[...] = 0.0                          # no wind
+        z = o.field("Zt_avg1")[0, 40, 3:44]
+        r = np.clip(z[20:], 0.0, None)
+        cen.append(float((r * np.arange(20, 41)).sum() / r.sum()))
+    dx = 1.0 / o.field("pm")[0, 40, 20]
+    c = (cen[1] - cen[0]) * dx / o.opt("dt")
+    assert abs(c / np.sqrt(o.opt("g") * H) - 1.0) < 0.02, (c, np.sqrt(o.opt("g") * H))
+    assert np.max(np.abs(o.field("vbar1"))) < 1e-12          # the problem stays one-dimensional
+
+
+def test_physics_kat_vertical_diffusion_decay():
+    """Analytical known answer for the implicit vertical-diffusion solve (pre_step3d + step3d_t, SPLINES_VDIFF): at rest
+    over a flat bottom with constant Akt and no-flux boundaries, the mode cos(pi (z+H)/H) decays as exp(-Akt (pi/H)^2 t)."""
+    o = orc.Oracle(orc.APP_SEAMOUNT)
+    o.run_phase("set_data")
+    H, K, nsteps = 1000.0, 1.0, 50
+    o.field("h")[...] = H
+    o.run_phase("ini")
+    zr = o.field("z_r")
+    o.field("Akt_0")[...] = K
+    for n in ("t1_0", "t2_0"):
+        o.field(n)[...] = 10.0 + np.cos(np.pi * (zr + H) / H)
+    for _ in range(nsteps):
+        o.step(1)
+    assert np.max(np.abs(o.field("u1"))) == 0.0 and np.max(np.abs(o.field("v1"))) == 0.0       # horizontally uniform: stays at rest
+    newest = "t%d_0" % o.indices()["nnew"]                   # time level written by the last step
+    mode = np.cos(np.pi * (zr[:, 10, 10] + H) / H)
+    amp = float(np.dot(o.field(newest)[:, 10, 10] - 10.0, mode) / np.dot(mode, mode))
+    exact = float(np.exp(-K * (np.pi / H) ** 2 * nsteps * o.opt("dt")))
+    assert abs((1.0 - amp) / (1.0 - exact) - 1.0) < 0.05, (amp, exact)      # 13 stretched levels: 2 % measured
+
+
+def test_physics_kat_tracer_translation():
+    """Analytical known answer for the tracer advection path (pre_step3d predictor + step3d_t corrector, U3 / C4): in a
+    uniform barotropic current U over a flat bottom a tracer anomaly translates by U*t; its centroid is conserved exactly by
+    a flux-form scheme, so the bar is tight."""
+    o = orc.Oracle(orc.APP_UPWELLING)
+    o.run_phase("set_data")
+    o.field("h")[...] = 100.0
+    o.field("f")[...] = 0.0; o.field("fomn")[...] = 0.0
+    for n in ("t1_0", "t2_0"):
+        o.field(n)[...] = 14.0
+    U, nsteps = 0.5, 20
+    x = np.arange(-2, 44)
+    S = 35.0 + np.exp(-((x - 15.5) / 3.0) ** 2)
+    for n in ("t1_1", "t2_1"):
+        o.field(n)[...] = S[None, None, :]
+    for n in ("u1", "u2", "ubar1", "ubar2", "ubar3"):
+        o.field(n)[...] = U
+    o.run_phase("ini")
+
+    def centroid(name):
+        a = o.field(name)[8, 40, 3:44] - 35.0
+        return float((a * np.arange(41)).sum() / a.sum())
+    c0 = centroid("t1_1")
+    for _ in range(nsteps):
+        o.step(1)
+    newest = "t%d_1" % o.indices()["nnew"]
+    dx = 1.0 / o.field("pm")[0, 40, 20]
+    moved = (centroid(newest) - c0) * dx
+    assert abs(moved / (U * nsteps * o.opt("dt")) - 1.0) < 2e-3, moved
+
+
+def test_physics_kat_geostrophic_balance():
+    """Analytical known answer for the Coriolis / pressure-gradient pair (rhs3d :473-507, step2d :944-1019, :1291-1300): a
+    uniform along-channel current U over a flat bottom is steady when the free surface slopes across the channel by
+    d(zeta)/dy = -f U / g.  With the slope the cross-channel velocity stays ~40 times smaller than without it."""
+    def run(with_slope):
+        o = orc.Oracle(orc.APP_UPWELLING)
+        o.run_phase("set_data")
+        U = 0.1
+        o.field("h")[...] = 100.0
+        o.field("rdrag")[...] = 0.0
+        for n in ("t1_0", "t2_0"):
+            o.field(n)[...] = 14.0
+        if with_slope:
+            f0 = float(o.field("f")[0, 40, 20]); dy = 1.0 / float(o.field("pn")[0, 40, 20])
+            y = (np.arange(0, 82) - 0.5) * dy
+            zeta = -f0 * U / o.opt("g") * (y - y.mean())
+            for n in ("zeta1", "zeta2", "zeta3", "Zt_avg1"):
+                o.field(n)[0, :, :] = zeta[:, None]
+        for n in ("u1", "u2", "ubar1", "ubar2", "ubar3"):
+            o.field(n)[...] = U
+        o.run_phase("ini")
+        for _ in range(10):
+            o.step(1)
+        nn = o.indices()["nnew"]
+        return float(np.abs(o.field("v%d" % nn)[:, 2:80, 3:44]).max()), float(np.abs(o.field("u%d" % nn)[:, 2:80, 3:44] - U).max())
+    v_bal, du_bal = run(True)
+    v_free, _ = run(False)
+    assert v_bal < 3e-4 and du_bal < 2e-3, (v_bal, du_bal)      # measured 1.1e-4, 7.9e-4 (the wind ramp of ana_smflux acts on u)
+    assert v_free > 10.0 * v_bal, (v_free, v_bal)               # measured 4.0e-3
