@@ -333,3 +333,62 @@ def test_physics_kat_geostrophic_balance():
     v_free, _ = run(False)
     assert v_bal < 3e-4 and du_bal < 2e-3, (v_bal, du_bal)      # measured 1.1e-4, 7.9e-4 (the wind ramp of ana_smflux acts on u)
     assert v_free > 10.0 * v_bal, (v_free, v_bal)               # measured 4.0e-3
+
+
+def _cos_mode_setup(o):
+    dy = 1.0 / float(o.field("pn")[0, 40, 20])
+    y = (np.arange(0, 82) - 0.5) * dy
+    L = 80 * dy
+    return y, L, np.cos(np.pi * y / L)                        # zero normal derivative at both closed walls
+
+
+def test_physics_kat_horizontal_viscosity_decay():
+    """Analytical known answer for harmonic viscosity (uv3dmix2_s + the viscous terms of step2d, which must agree or the
+    2-D/3-D coupling would tear them apart): a cross-channel shear u = A cos(pi y/L) between free-slip walls decays as
+    exp(-visc2 (pi/L)^2 t)."""
+    o = orc.Oracle(orc.APP_UPWELLING)
+    o.run_phase("set_data")
+    A, nu, nsteps = 0.1, 1.0e4, 10
+    o.field("h")[...] = 100.0
+    o.field("rdrag")[...] = 0.0
+    o.field("f")[...] = 0.0; o.field("fomn")[...] = 0.0
+    o.field("visc2_r")[...] = nu; o.field("visc2_p")[...] = nu
+    for n in ("t1_0", "t2_0"):
+        o.field(n)[...] = 14.0
+    y, L, mode = _cos_mode_setup(o)
+    for n in ("u1", "u2"):
+        o.field(n)[...] = (A * mode)[None, :, None]
+    for n in ("ubar1", "ubar2", "ubar3"):
+        o.field(n)[0, :, :] = (A * mode)[:, None]
+    o.run_phase("ini")
+    for _ in range(nsteps):
+        o.step(1)
+    nn = o.indices()["nnew"]
+    m = mode[1:81]
+    amp3 = float(np.dot(o.field("u%d" % nn)[8, 1:81, 20], m) / np.dot(m, m)) / A
+    amp2 = float(np.dot(o.field("ubar1")[0, 1:81, 20], m) / np.dot(m, m)) / A
+    exact = float(np.exp(-nu * (np.pi / L) ** 2 * nsteps * o.opt("dt")))
+    assert abs((1 - amp3) / (1 - exact) - 1) < 0.01 and abs(amp2 - amp3) < 1e-12, (amp3, amp2, exact)
+
+
+def test_physics_kat_horizontal_diffusion_decay():
+    """Same for the tracer mixing along s-surfaces (t3dmix2_s): S = 35 + cos(pi y/L) decays as exp(-tnu2 (pi/L)^2 t)."""
+    o = orc.Oracle(orc.APP_UPWELLING)
+    o.run_phase("set_data")
+    kap, nsteps = 1.0e4, 10
+    o.field("h")[...] = 100.0
+    o.field("f")[...] = 0.0; o.field("fomn")[...] = 0.0
+    o.field("diff2_1")[...] = kap
+    for n in ("t1_0", "t2_0"):
+        o.field(n)[...] = 14.0
+    y, L, mode = _cos_mode_setup(o)
+    for n in ("t1_1", "t2_1"):
+        o.field(n)[...] = (35.0 + mode)[None, :, None]
+    o.run_phase("ini")
+    for _ in range(nsteps):
+        o.step(1)
+    nn = o.indices()["nnew"]
+    m = mode[1:81]
+    amp = float(np.dot(o.field("t%d_1" % nn)[8, 1:81, 20] - 35.0, m) / np.dot(m, m))
+    exact = float(np.exp(-kap * (np.pi / L) ** 2 * nsteps * o.opt("dt")))
+    assert abs((1 - amp) / (1 - exact) - 1) < 0.01, (amp, exact)
