@@ -411,8 +411,8 @@ def test_physics_kat_baroclinic_pressure_gradient_shear():
     o.run_phase("ini")
     o.step(1)
     u = o.field("u%d" % o.indices()["nnew"]); zr = o.field("z_r")
-    col = 3 + 10                                             # u point i = 10 at x = (i-1)*dx
-    rho_x = -o.opt("R0") * o.opt("Tcoef") * B * k * np.cos(k * (10 - 1.0) * dx)
+    col = 13                                                 # array column of u point i = col - 2 = 11, at x = (i-1)*dx
+    rho_x = -o.opt("R0") * o.opt("Tcoef") * B * k * np.cos(k * (col - 2 - 1.0) * dx)
     k1, k2 = 3, 12
     z1 = 0.5 * (zr[k1, 40, col] + zr[k1, 40, col - 1]); z2 = 0.5 * (zr[k2, 40, col] + zr[k2, 40, col - 1])
     shear = float(u[k2, 40, col] - u[k1, 40, col])
