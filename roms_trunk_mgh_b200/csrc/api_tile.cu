@@ -147,10 +147,14 @@ const RoutineArgs kRoutineArgs[] = {
 
 /* "in:<names>;out:<names>" of a routine (see kRoutineArgs), or NULL for an unknown phase. */
 const char* roms_b200_routine_args(int phase) {
-  static std::string buf[32];
-  for (const RoutineArgs& r : kRoutineArgs)
-    if (r.phase == phase) { buf[phase & 31] = std::string("in:") + r.in + ";out:" + r.out; return buf[phase & 31].c_str(); }
-  return nullptr;
+  // built once (thread-safe static initialisation): the returned pointers stay valid for the life of the library
+  static const std::vector<std::string> table = [] {
+    std::vector<std::string> t(32);
+    for (const RoutineArgs& r : kRoutineArgs) t[r.phase & 31] = std::string("in:") + r.in + ";out:" + r.out;
+    return t;
+  }();
+  if (phase < 0 || phase >= 32 || table[phase].empty()) return nullptr;
+  return table[phase].c_str();
 }
 
 /* Run ONE routine on whole Fortran arrays in host memory.  mode[i]: 1 = input, 2 = output (its current content is uploaded
