@@ -58,3 +58,57 @@ def test_ring_exchange_gloo(world, Lm, Mm):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, True) for r in range(world)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Model of the halo exchange fused into the step2d kernel (csrc/dev.cuh Xchg, csrc/k_step2d.cu): every sub-step kernel k of
+# a tile PULLS, per CTA (row block rb), the rows rb-1..rb+1 its two neighbours pushed in their kernel k-1 (slot (k-1) % S of
+# the own mailbox, tag k-1), and PUSHES its own rows with tag k into slot k % S of both neighbours' mailboxes.  The only
+# ordering the hardware gives is: a tile's kernel k+1 starts after ALL CTAs of its kernel k have finished; CTAs of a kernel
+# and different tiles progress in any interleaving.  The model replays random interleavings and checks that a pull never
+# finds a LATER epoch in its slot (data overwritten before it was consumed) and that the ring never deadlocks.
+def _simulate_fused_exchange(world, K, R, S, seed):
+    import random
+    rnd = random.Random(seed)
+    # box[r][slot][half][rb] = tag; half 0: written by the west neighbour, 1: by the east neighbour
+    box = [[[[0] * R for _ in range(2)] for _ in range(S)] for _ in range(world)]
+    kern = [1] * world                                  # current kernel of each tile
+    state = [{rb: 0 for rb in range(R)} for _ in range(world)]     # per CTA: 0 = must pull, 1 = must push, (absent) = done
+    while True:
+        if all(k > K for k in kern):
+            return "ok"
+        moves = [(r, rb) for r in range(world) if kern[r] <= K for rb in state[r]]
+        rnd.shuffle(moves)
+        progressed = False
+        for r, rb in moves:
+            k = kern[r]
+            if state[r][rb] == 0:
+                if k >= 2:
+                    need = [b for b in (rb - 1, rb, rb + 1) if 0 <= b < R]
+                    tags = [box[r][(k - 1) % S][half][b] for half in (0, 1) for b in need]
+                    if any(t > k - 1 for t in tags):
+                        return "overwritten"
+                    if any(t < k - 1 for t in tags):
+                        continue                         # not delivered yet: this CTA spins
+                state[r][rb] = 1
+            else:
+                east, west = (r + 1) % world, (r - 1) % world
+                box[east][k % S][0][rb] = k              # my eastern columns -> east neighbour's "from the west" half
+                box[west][k % S][1][rb] = k
+                del state[r][rb]
+                if not state[r]:
+                    kern[r] += 1
+                    state[r] = {b: 0 for b in range(R)}
+            progressed = True
+            break
+        if not progressed:
+            return "deadlock"
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_fused_exchange_protocol_model(world):
+    for seed in range(150):
+        assert _simulate_fused_exchange(world, K=9, R=5, S=4, seed=seed) == "ok"      # XSLOTS = 4 (the library's value)
+        assert _simulate_fused_exchange(world, K=9, R=5, S=2, seed=seed) == "ok"      # two slots are already enough
+    # the model is able to see the hazard: with a single slot some interleaving overwrites unconsumed data
+    assert any(_simulate_fused_exchange(world, K=9, R=5, S=1, seed=seed) == "overwritten" for seed in range(150))
