@@ -418,3 +418,23 @@ def test_physics_kat_baroclinic_pressure_gradient_shear():
     shear = float(u[k2, 40, col] - u[k1, 40, col])
     exact = float((o.opt("g") / o.opt("rho0")) * rho_x * (z2 - z1) * o.opt("dt"))
     assert abs(shear / exact - 1.0) < 0.01, (shear, exact)   # measured 0.17 %
+
+
+def test_bench_accounting_and_reference_arm():
+    """bench.py host logic: the algorithmic-bytes figure of the roofline and the reference arm
+    (`--impl reference`: the oracle timed on the host cores, same metric / JSON keys as the GPU arm; needs no GPU)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    sys.path.insert(0, root)
+    import bench
+    balg, s2d = bench.b_alg_bytes(30, 29)
+    assert s2d == 29 * 44 + 16 + 29 * 41 and abs(balg - 1525.6) < 1e-9
+    assert abs(bench.b_alg_bytes(30, 29, curvgrid=False, nonlin_eos=False)[0] - 8.0 * (105 + 2365 / 30.0)) < 1e-9     # 1471 B
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--grid", "benchmark1", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "grid-point-steps/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
