@@ -6,11 +6,17 @@ Metric (BASELINE.json): grid-point-steps/s = Lm*Mm*N*steps / seconds on a synthe
   e2e   : the same metric through the host-facing call roms_b200_step_forced (H2D of the step's surface forcing from
           pinned memory, the step, D2H of the diag scalars) -- host wall clock around the calls
   roofline     : dominant kernel, algorithmic bytes per launch / CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : the C++ oracle (-O3 -march=native, one tile per host thread) on a bounded sample of the same workload
+  cpu_baseline : the C++ oracle (one tile per host thread) on a bounded sample of the same workload
+  state_digest : sha256 of the owned points of the prognostic fields after spinup + warmup + steps, gathered in global
+                 order -- identical at every GPU count (the reference's tiling-invariance criterion, verify.sh:985-1045)
+  phase_ms     : per-phase device time taken INSIDE the captured step graph (roms_b200_profile_enable(2)), so it describes
+                 the timed configuration at every N and sums to the step
 `--impl reference` times the CPU restatement of the reference (the Fortran reference cannot be built here: no Fortran
-compiler, no NetCDF) with all host threads and prints the same line with "impl": "reference".
+compiler, no NetCDF) with all host threads, on the same grid, spin-up, warm-up and step count, and prints the same line
+with "impl": "reference".
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -26,12 +32,23 @@ GRIDS = {"benchmark1": (512, 64, 30), "benchmark2": (1024, 128, 30), "benchmark3
          "b3tile8x2": (512, 256, 30),
          # ... and this one the 512x256 tile of 4 GPUs
          "b3tile4x2": (1024, 256, 30)}
+# weak scaling: BENCHMARK1/2/3 grow x4 in points per step; grid run at N GPUs
+WEAK = {1: "benchmark1", 2: "benchmark2", 4: "benchmark2", 8: "benchmark3"}
 METRIC = "grid-point-steps/sec (3D baroclinic)"
+DIGEST_FIELDS = ["zeta1", "zeta2", "ubar1", "ubar2", "vbar1", "vbar2", "u1", "u2", "v1", "v2", "t1_0", "t2_0", "t1_1", "t2_1"]
+HISTORY_FIELDS = ["zeta1", "ubar1", "vbar1", "u1", "v1", "t1_0", "t1_1", "rho", "W"]     # what a history record holds (wrt_his.F)
 
 
-def b_alg_bytes(N, nfast, curvgrid=True, nonlin_eos=True, wvelocity=True):
+def workload(grid, Lm, Mm, N, ndtfast=20, nfast=29, mix_geo=False):
+    """The workload string both arms print (config.workload)."""
+    mix = "TS_DIF2 MIX_GEO_TS" if mix_geo else "TS_DIF2 MIX_S_TS"
+    return (f"{grid.upper()} {Lm}x{Mm}x{N}, NT=2, reduced physics set (nonlinear EOS, DJ_GRADPS, U3/C4, UV_VIS2, {mix}, UV_QDRAG, CURVGRID), "
+            f"ndtfast={ndtfast}, nfast={nfast}")
+
+
+def b_alg_bytes(N, nfast, curvgrid=True, nonlin_eos=True, wvelocity=True, mix_geo=False):
     """Algorithmic bytes per grid-point-step (SURVEY.md section 8d / BASELINE.md): 8*(U3D + S2D/N)."""
-    u3d = 98 + (7 if wvelocity else 0) + (3 if nonlin_eos else 0)
+    u3d = 98 + (7 if wvelocity else 0) + (3 if nonlin_eos else 0) + (1 if mix_geo else 0)
     per_pred, per_corr = 42 + (2 if curvgrid else 0), 39 + (2 if curvgrid else 0)
     s2d = nfast * per_pred + 16 + nfast * per_corr
     return 8.0 * (u3d + s2d / N), s2d
@@ -110,27 +127,109 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
-def cpu_run(grid, steps, warmup, nthreads, kind="fast"):
-    """Time the CPU restatement (oracle/) on the host cores: one tile per thread, barrier per phase."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc
-    Lm, Mm, N = grid
-    ni = max(1, min(nthreads, Lm // 16))
-    nj = 1
-    # factor threads into NtileI x NtileJ (reference OpenMP mode: NtileI*NtileJ = threads)
-    best = (ni, 1)
+def cpu_tiles(nthreads, Lm, Mm):
+    """Factor the host threads into NtileI x NtileJ (reference OpenMP mode: NtileI*NtileJ = threads), NtileI >= NtileJ."""
+    best = (max(1, min(nthreads, Lm // 16)), 1)
     for a in range(1, nthreads + 1):
         if nthreads % a == 0:
             b = nthreads // a
             if a >= b and Lm // a >= 8 and Mm // b >= 8:
                 best = (a, b)
                 break
-    ni, nj = best
-    o = orc.Oracle(orc.APP_BENCHMARK, Lm=Lm, Mm=Mm, N=N, NtileI=ni, NtileJ=nj, kind=kind)
+    return best
+
+
+def cpu_run(grid, steps, warmup, nthreads, spinup=0, kinds=("fast", "fastmath")):
+    """Time the CPU restatement (oracle/) on the host cores: one tile per thread, barrier per phase.  Two timing builds
+    (-O3 -march=native, and the same plus the reference's own -ffast-math, Compilers/Linux-gfortran.mk:98-99) are probed on
+    two steps each; the faster one runs the sample.  Returns (gp-steps/s, seconds, tiles, build kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    Lm, Mm, N = grid
+    ni, nj = cpu_tiles(nthreads, Lm, Mm)
+    models, probe = {}, {}
+    for k in kinds:
+        try:
+            models[k] = orc.Oracle(orc.APP_BENCHMARK, Lm=Lm, Mm=Mm, N=N, NtileI=ni, NtileJ=nj, kind=k)
+            models[k].step(1, nthreads)
+            probe[k] = models[k].timed_steps(2, nthreads)
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"bench.py: oracle build '{k}' unavailable: {e}\n")
+    kind = min(probe, key=probe.get)
+    o = models[kind]
+    for k in list(models):
+        if k != kind:
+            del models[k]
+    done = 3                                     # steps the probe already advanced the model
+    if spinup > done:
+        o.step(spinup - done, nthreads)
     if warmup:
         o.step(warmup, nthreads)
     sec = o.timed_steps(steps, nthreads)
-    return Lm * Mm * N * steps / sec, sec, (ni, nj)
+    return Lm * Mm * N * steps / sec, sec, (ni, nj), kind, probe
+
+
+def cpu_flags(kind):
+    return "-O3 -march=native" + (" -ffast-math" if kind == "fastmath" else "")
+
+
+def gather_global(t, dist, name, rank, world, allb):
+    """Owned columns of field `name` of every tile, concatenated along xi on rank 0 (None elsewhere)."""
+    import numpy as np
+    a = t.get(name)
+    b = allb[rank]
+    lo = b["Istr"] - b["LBi"]
+    own = np.ascontiguousarray(a[..., lo:lo + b["Iend"] - b["Istr"] + 1])
+    if dist is None:
+        return own
+    import torch
+    w = max(bb["Iend"] - bb["Istr"] + 1 for bb in allb)
+    pad = torch.zeros(own.shape[:-1] + (w,), dtype=torch.float64, device="cuda")
+    pad[..., :own.shape[-1]] = torch.from_numpy(own).cuda()
+    bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, bufs, dst=0)
+    if rank != 0:
+        return None
+    return np.concatenate([bufs[r][..., :allb[r]["Iend"] - allb[r]["Istr"] + 1].cpu().numpy() for r in range(world)], axis=-1)
+
+
+def state_digest(t, dist, rank, world, Lm, Mm):
+    from roms_trunk_mgh_b200 import _lib
+    allb = [_lib.bounds(Lm, Mm, world, 1, r, distribute=world > 1) for r in range(world)]
+    h = hashlib.sha256()
+    for n in DIGEST_FIELDS:
+        G = gather_global(t, dist, n, rank, world, allb)
+        if rank == 0:
+            assert G.shape[-1] == Lm, (n, G.shape)
+            h.update(n.encode()); h.update(G.tobytes())
+    return h.hexdigest() if rank == 0 else None
+
+
+def make_ring_tile(synth, grid, rank, world, local, dist, **overrides):
+    Lm, Mm, N = grid
+    t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, NtileI=world, tile=rank, device=local, **overrides)
+    xchg = "none (single tile, periodic images written by the producing kernel)"
+    if world > 1:
+        from roms_trunk_mgh_b200 import multigpu
+        multigpu.attach(t, dist, rank, world)
+        xchg = ("nvlink-peer-mailbox+edge-first-overlap+step2d-exchange-fused-into-kernel" if t.peer else "nccl-send-recv+edge-first-overlap")
+        for ph in ("set_depth", "set_massflux", "omega", "rho_eos"):      # start-up phases again, now with live ghosts
+            t.run_phase(ph)
+    return t, xchg
+
+
+def timed_steps(t, dist, steps):
+    """`steps` resident steps bracketed by barrier + synchronize; device time (CUDA events on the library stream), max over ranks."""
+    if dist is not None:
+        dist.barrier()
+    t.sync()
+    t.main3d(steps, sync=True)
+    ms = t.last_step_ms()
+    if dist is not None:
+        dist.barrier()
+        import torch
+        tt = torch.tensor([ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+    return ms
 
 
 def main():
@@ -142,6 +241,7 @@ def main():
     ap.add_argument("--grid", default="benchmark3")
     ap.add_argument("--spinup", type=int, default=20, help="untimed steps before warm-up so that all upstream branches are live")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the MIX_GEO_TS row, the weak-scaling row and the history-write timing")
     a = ap.parse_args()
     # keep stdout clean for the single JSON line: libraries (NCCL's version banner, ...) that print to fd 1 go to stderr
     sys.stdout.flush()
@@ -161,14 +261,16 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        nth = min(ncores, 32)
-        steps = max(1, min(a.steps, 3)); warm = min(W, 1)
-        val, sec, tiles = cpu_run((Lm, Mm, N), steps, warm, nth)
-        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "grid-point-steps/s", "n_gpus": a.gpus, "steps": steps, "warmup": warm,
-                "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": {"workload": f"{a.grid.upper()} {Lm}x{Mm}x{N}, reduced physics set", "tiles": f"{tiles[0]}x{tiles[1]}"},
-                "cpu_baseline": {"value": val, "unit": "grid-point-steps/s", "cores": nth, "kind": "port",
-                                 "sample": f"{steps} steps after {warm} warm-up on the full {a.grid.upper()} grid, {tiles[0]}x{tiles[1]} tiles on {nth} threads"},
+        nth = ncores
+        val, sec, tiles, kind, probe = cpu_run((Lm, Mm, N), a.steps, W, nth, spinup=a.spinup)
+        sample = (f"{a.steps} steps after {a.spinup} spin-up + {W} warm-up steps on the full {a.grid.upper()} grid, {tiles[0]}x{tiles[1]} tiles on {nth} host "
+                  f"threads; C++ restatement of the Fortran (scratch arrays heap-allocated per call), g++ {cpu_flags(kind)} "
+                  f"(2-step probe: " + ", ".join(f"{k} {v / 2:.2f} s/step" for k, v in probe.items()) + ")")
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "grid-point-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": W,
+                "ms_per_step": 1e3 * sec / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": workload(a.grid, Lm, Mm, N), "spinup_steps": a.spinup},
+                "cpu_tiles": f"{tiles[0]}x{tiles[1]}",
+                "cpu_baseline": {"value": val, "unit": "grid-point-steps/s", "cores": nth, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": "grid-point-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return 0
@@ -182,36 +284,24 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl")
     NtileI = world
-    xchg = "none (single tile, periodic images written by the producing kernel)"
-    t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, NtileI=NtileI, tile=rank, device=local)
+    t, xchg = make_ring_tile(synth, (Lm, Mm, N), rank, world, local, dist)
     nfast = synth.set_weights(t.cfg.ndtfast)[0]
-    if world > 1:
-        from roms_trunk_mgh_b200 import multigpu
-        multigpu.attach(t, dist, rank, world)
-        xchg = ("nvlink-peer-mailbox" if t.peer else "nccl-send-recv") + ("" if os.environ.get("ROMS_B200_NO_OVERLAP") == "1" else "+edge-first-overlap")
-        if t.peer and os.environ.get("ROMS_B200_FUSED_XCHG", "2") != "0":
-            xchg += "+step2d-exchange-fused-into-kernel"
-        for ph in ("set_depth", "set_massflux", "omega", "rho_eos"):      # start-up phases again, now with live ghosts
-            t.run_phase(ph)
     t.main3d(a.spinup)
     t.main3d(W)
+
+    clk = ClockSampler(local); clk.start()
+    l0 = t.launch_count()
+    ms = timed_steps(t, dist, a.steps)
+    launches = t.launch_count() - l0
+    clocks = clk.stop()
+    value = Lm * Mm * N * a.steps / (ms * 1e-3)
+
+    # ---- digest of the prognostic state after spinup + warmup + steps (before anything else touches the state)
+    digest = state_digest(t, dist, rank, world, Lm, Mm)
 
     def barrier():
         if dist is not None:
             dist.barrier()
-
-    clk = ClockSampler(local); clk.start()
-    barrier(); t.sync()
-    l0 = t.launch_count()
-    t.main3d(a.steps, sync=True)
-    ms = t.last_step_ms()
-    barrier()
-    launches = t.launch_count() - l0
-    clocks = clk.stop()
-    if dist is not None:
-        import torch
-        tt = torch.tensor([ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
-    value = Lm * Mm * N * a.steps / (ms * 1e-3)
 
     # ---- e2e: host forcing in, diag scalars out, every step
     g = t.synth["grid"]; b = t.synth["bounds"]
@@ -230,12 +320,30 @@ def main():
         tt = torch.tensor([e2e_sec], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); e2e_sec = float(tt.item())
     e2e_val = Lm * Mm * N * ke / e2e_sec
 
-    # ---- per-phase device times (CUDA events on the library's stream) -> dominant kernel roofline
-    t.profile(True)
-    t.main3d(3)
+    # ---- what one history record costs (wrt_his.F writes every NHIS steps; the fields come back with roms_b200_get_field)
+    hist = None
+    if not a.no_extras:
+        barrier(); t.sync(); t0 = time.perf_counter()
+        nbytes = 0
+        for n in HISTORY_FIELDS:
+            nbytes += t.get(n).nbytes
+        hist = {"fields": HISTORY_FIELDS, "bytes": int(nbytes), "ms": 1e3 * (time.perf_counter() - t0),
+                "note": "roms_b200_get_field into pageable numpy arrays, per tile; amortised over NHIS steps (BENCHMARK: NHIS = NTIMES)"}
+
+    # ---- per-phase device times taken inside the captured step graph -> dominant kernel roofline
+    NP = 4
+    t.profile(2)
+    t.main3d(2)                               # both time-level parities get their (marked) graph
+    t.profile(2)                              # reset the accumulators
+    t.main3d(NP)
     prof, _ = t.profile_get()
-    t.profile(False)
-    prof = {k: v / 3.0 for k, v in prof.items()}
+    t.profile(0)
+    prof = {k: v / NP for k, v in prof.items()}
+    if dist is not None:                      # max over ranks, phase by phase
+        import torch
+        keys = sorted(prof)
+        tt = torch.tensor([prof[k] for k in keys], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        prof = dict(zip(keys, [float(x) for x in tt.tolist()]))
     peak, peak_kind = measured_peak()
     balg, s2d = b_alg_bytes(N, nfast, curvgrid=bool(t.cfg.curvgrid), nonlin_eos=bool(t.cfg.nonlin_eos), wvelocity=bool(t.cfg.wvelocity_every_step))
     npts2 = (Lm // NtileI) * Mm
@@ -246,39 +354,68 @@ def main():
     roof = None
     if dom:
         if dom == "step2d_loop":
-            bytes_per_launch = 8.0 * s2d * npts2 / (2 * nfast + 1)
-            dur = prof[dom] * 1e-3 / (2 * nfast + 1)
+            nl = 2 * nfast + 1
+            bytes_per_launch = 8.0 * s2d * npts2 / nl
+            dur = prof[dom] * 1e-3 / nl
             kname = "k_step2d"
         else:
             bytes_per_launch = 8.0 * units3.get(dom, 5) * npts2 * N
             dur = prof[dom] * 1e-3
             kname = dom
         ach = bytes_per_launch / dur / 1e9
-        traffic = None
-        try:   # DRAM bytes per launch from the committed ncu --set full capture (profiles/), single-GPU full-size tile only
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic, tsrc = None, None
+        try:   # DRAM bytes per launch: not measurable in-process; the committed ncu --set full capture of this build (profiles/)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             if world == 1 and a.grid == "benchmark3" and kname in tj:
-                traffic = tj[kname]["dram_bytes_per_launch"]
+                traffic = tj[kname]["dram_bytes_per_launch"]; tsrc = tj[kname].get("source")
         except Exception:
             traffic = None
         roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": dur * 1e3, "share_of_step": prof[dom] / max(sum(prof.values()), 1e-30)}
+                "traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": dur * 1e3,
+                "launches_per_step": (2 * nfast + 1) if dom == "step2d_loop" else 1,
+                "share_of_step": prof[dom] / max(sum(prof.values()), 1e-30)}
     step_gbs = balg * value / 1e9
     line = {"metric": METRIC, "value": value, "unit": "grid-point-steps/s", "n_gpus": world, "steps": a.steps, "warmup": W,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{a.grid.upper()} {Lm}x{Mm}x{N}, NT=2, reduced physics set (nonlinear EOS, DJ_GRADPS, U3/C4, UV_VIS2, TS_DIF2 MIX_S_TS, "
-                                   f"UV_QDRAG, CURVGRID), ndtfast={t.cfg.ndtfast}, nfast={nfast}", "tiles": f"{NtileI}x1", "halo_exchange": xchg,
-                       "launch": "stream" if os.environ.get("ROMS_B200_NO_GRAPH") == "1" else "cuda-graph per step",
-                       "l2": "working set per step (~3.5 GB) exceeds L2 (126 MB); no explicit flush", "spinup_steps": a.spinup},
+            "config": {"workload": workload(a.grid, Lm, Mm, N, t.cfg.ndtfast, nfast), "spinup_steps": a.spinup},
+            "tiles": f"{NtileI}x1", "halo_exchange": xchg, "launch": "cuda-graph per step",
+            "l2": "working set per step (~3.5 GB) exceeds L2 (126 MB); no explicit flush",
             "e2e": {"value": e2e_val, "unit": "grid-point-steps/s", "h2d_bytes_per_step": int(3 * sustr.size * 8), "d2h_bytes_per_step": 12 * 8,
                     "steps": ke},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "roofline_step": {"b_alg_bytes_per_gp_step": balg, "achieved_gbs": step_gbs, "frac": step_gbs / (peak * world)},
-            "phase_ms": prof}
+            "phase_ms": prof, "phase_ms_sum": sum(prof.values()), "phase_ms_mode": "events inside the captured step graph, main stream, max over ranks",
+            "state_digest": digest, "state_digest_steps": a.spinup + W + a.steps, "history_write": hist}
+    perr = int(t.L.roms_b200_peer_error(t.h))
+    t.close()
+
+    # ---- extra rows: MIX_GEO_TS (SURVEY.md section 8d "second row") and weak scaling (section 8e)
+    if not a.no_extras and a.grid == "benchmark3":
+        try:
+            tg, _ = make_ring_tile(synth, (Lm, Mm, N), rank, world, local, dist, mix_geo_ts=1)
+            tg.main3d(6)
+            msg = timed_steps(tg, dist, 6)
+            bg, _ = b_alg_bytes(N, nfast, mix_geo=True)
+            line["mix_geo_ts_row"] = {"ms_per_step": msg / 6, "value": Lm * Mm * N * 6 / (msg * 1e-3), "steps": 6, "spinup_steps": 6,
+                                      "roofline_step_frac": bg * (Lm * Mm * N * 6 / (msg * 1e-3)) / 1e9 / (peak * world)}
+            perr |= int(tg.L.roms_b200_peer_error(tg.h))
+            tg.close()
+            wg = WEAK.get(world)
+            if wg:
+                wl = GRIDS[wg]
+                tw, _ = make_ring_tile(synth, wl, rank, world, local, dist)
+                tw.main3d(10)
+                msw = timed_steps(tw, dist, 10)
+                line["weak_scaling_row"] = {"grid": wg, "n_gpus": world, "ms_per_step": msw / 10, "value": wl[0] * wl[1] * wl[2] * 10 / (msw * 1e-3), "steps": 10,
+                                            "note": "BENCHMARK1 on 1, BENCHMARK2 on 2 and 4, BENCHMARK3 on 8 GPUs (x4 points per grid)"}
+                perr |= int(tw.L.roms_b200_peer_error(tw.h))
+                tw.close()
+        except Exception as e:  # noqa: BLE001
+            line["extras_error"] = str(e)
     if dist is not None:
-        # a neighbour that never delivered its halo (NVLink peer path: the spin gives up after ~3 s) invalidates the run
+        # a neighbour that never delivered its halo invalidates the run
         import torch
-        bad = torch.tensor([int(t.L.roms_b200_peer_error(t.h))], device="cuda")
+        bad = torch.tensor([perr], device="cuda")
         dist.all_reduce(bad, op=dist.ReduceOp.MAX)
         if int(bad.item()):
             sys.stderr.write("bench.py: a halo exchange timed out; results are invalid, no line printed\n")
@@ -286,10 +423,10 @@ def main():
             return 1
     if rank == 0 and world == 1 and not a.no_cpu:
         try:
-            nth = min(ncores, 32)
-            cv, csec, tiles = cpu_run((Lm, Mm, N), 2, 1, nth)
-            line["cpu_baseline"] = {"value": cv, "unit": "grid-point-steps/s", "cores": nth, "kind": "port",
-                                    "sample": f"2 steps after 1 warm-up on the full {a.grid.upper()} grid, {tiles[0]}x{tiles[1]} tiles on {nth} host threads"}
+            cv, csec, tiles, kind, probe = cpu_run((Lm, Mm, N), 4, 1, ncores, spinup=0)
+            line["cpu_baseline"] = {"value": cv, "unit": "grid-point-steps/s", "cores": ncores, "kind": "port",
+                                    "sample": f"4 steps after 4 warm-up steps on the full {a.grid.upper()} grid, {tiles[0]}x{tiles[1]} tiles on {ncores} host threads, "
+                                              f"g++ {cpu_flags(kind)} (the faster of the two timing builds)"}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "grid-point-steps/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:

@@ -14,7 +14,8 @@
  *      3-D  A(LBi:UBi, LBj:UBj, 1:N|0:N)   n = ni*nj*nk      (one time level / one tracer per call)
  *    host pointers are never retained after the call returns.
  *  - return value = ROMS exit_flag codes (ROMS/Modules/mod_scalars.F:523-532): 0 NoError, 1 blow-up, 2 input error,
- *    5 configuration error, 8 fatal algorithm error (CUDA / NCCL failure).  The Fortran shim assigns it to exit_flag.
+ *    5 configuration error, 8 fatal algorithm error (CUDA / NCCL failure, or a halo exchange whose neighbour never
+ *    delivered: sticky, every later synchronising call returns 8 too).  The Fortran shim assigns it to exit_flag.
  *  - the library is re-entrant per handle; one handle == one (ng,tile) == one GPU.
  *  - there is NO CPU fallback: without a CUDA device every compute entry point returns 8.
  */
@@ -81,7 +82,10 @@ int roms_b200_array_bounds(roms_b200_handle h, int* out4);
  * "u<1-2>","v<1-2>","t<1-3>_<itrc>","ru<1-2>","rv<1-2>","rho","pden","W","wvel"; depths "Hz","z_r","z_w","Huon","Hvom";
  * coupling (mod_coupling.F) "Zt_avg1","DU_avg1","DU_avg2","DV_avg1","DV_avg2","rufrc","rvfrc","rhoA","rhoS";
  * forces (mod_forces.F) "sustr","svstr","bustr","bvstr","stflx_<itrc>","btflx_<itrc>","stflux_<itrc>","btflux_<itrc>".
- * <itrc> is 0-based.  n = number of doubles in the whole Fortran array (checked). */
+ * <itrc> is 0-based.  n = number of doubles in the whole Fortran array (checked).
+ * With a ring attached (roms_b200_attach_nccl) roms_b200_set_field and roms_b200_step_forced are COLLECTIVE: every
+ * upload is followed by the halo exchange of that field (mp_exchange2d/3d), so all tiles must upload the same fields in
+ * the same order -- as the reference's distributed build does when every rank runs the same set_data / get_data. */
 int roms_b200_set_field(roms_b200_handle h, const char* name, const double* host, size_t n);
 int roms_b200_get_field(roms_b200_handle h, const char* name, double* host, size_t n);
 /* s-coordinate vectors (mod_scalars.F SCALARS%): which = 0 sc_r, 1 Cs_r, 2 sc_w, 3 Cs_w; n = N+1 values indexed by k */
@@ -114,6 +118,16 @@ int roms_b200_run_phase(roms_b200_handle h, int phase);
  * enqueueing; roms_b200_sync waits.  Forcing (sustr, svstr, stflux, btflux) is whatever was last uploaded. */
 int roms_b200_main3d_step(roms_b200_handle h, int nsteps);
 int roms_b200_sync(roms_b200_handle h);
+/* Run-time switches of a handle (set before stepping; the captured time-step graphs are dropped):
+ *   "cuda_graphs"      1 (default) replay one CUDA graph per baroclinic step, 0 plain stream launches
+ *   "step2d_exchange"  how the xi-halo of the barotropic sub-steps travels on the NVLink peer path (before attach only):
+ *                      2 (default) inside the step2d kernels with edge-first split launches, 1 inside the kernels with one
+ *                      launch per sub-step, 0 stand-alone exchange kernels
+ *   "overlap"          1 (default) edge-first two-stream overlap of halo exchanges with interior compute (before attach only)
+ *   "halo_timeout_s"   seconds a kernel waits for a neighbour's halo before it gives up and raises exit_flag 8
+ *                      (default 30; <= 0 waits for ever)
+ * Unknown key: 2; a value that cannot be applied in the handle's state: 5. */
+int roms_b200_set_option(roms_b200_handle h, const char* key, double value);
 /* One step the way main3d sees it from the host: H2D of this step's surface forcing (the set_data products
  * sustr(LBi:UBi,LBj:UBj), svstr, and optionally stflux for each tracer; NULL keeps the resident value), the step,
  * then D2H of the diag scalars.  out12 = avgke, avgpe, avgkp, volume, max_speed, maxCu, maxCv, maxCw,
@@ -131,6 +145,9 @@ int roms_b200_unregister_host(roms_b200_handle h, void* p);
 /* timing helpers for bench.py: elapsed device ms between two internal CUDA events bracketing the last
  * roms_b200_main3d_step call; per-phase accumulated device ms since the last reset (wclock regions, timers.F). */
 int roms_b200_last_step_ms(roms_b200_handle h, float* ms);
+/* on = 1: every phase bracketed by events and synchronised (plain stream launches); on = 2: events between consecutive
+ * phases recorded inside the captured CUDA graph of the step -- the split of the configuration that is actually timed
+ * (the phase times add up to the step); 0: off.  Phase ids index ms_by_phase32. */
 int roms_b200_profile_enable(roms_b200_handle h, int on);
 int roms_b200_profile_get(roms_b200_handle h, double* ms_by_phase32, long long* launches);
 long long roms_b200_launch_count(roms_b200_handle h);
@@ -151,6 +168,9 @@ int roms_b200_peer_export(roms_b200_handle h, char* out64);
 int roms_b200_peer_attach(roms_b200_handle h, const char* west64, const char* east64);
 int roms_b200_peer_enable(roms_b200_handle h, int on);
 int roms_b200_peer_error(roms_b200_handle h);
+/* Test hook: raises the sticky device error word exactly as a timed-out halo wait does (mp_exchange.F:1698-1705 sets
+ * exit_flag and returns; here roms_b200_sync / run_phase / step_forced / diag / get_field return 8 from then on). */
+int roms_b200_peer_error_inject(roms_b200_handle h);
 
 /* ---- per-routine host-pointer form (mirrors the _tile argument lists; used by the parity tests) ---------------- */
 /* roms_b200_tile_t carries what tile.h/set_bounds.h give a _tile routine. */

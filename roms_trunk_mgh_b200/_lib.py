@@ -42,7 +42,8 @@ EXPORTS = ["roms_b200_default_config", "roms_b200_bounds", "roms_b200_bounds_nam
            "roms_b200_set_indices", "roms_b200_get_indices", "roms_b200_run_phase", "roms_b200_main3d_step", "roms_b200_sync",
            "roms_b200_step_forced", "roms_b200_diag", "roms_b200_register_host", "roms_b200_unregister_host", "roms_b200_last_step_ms", "roms_b200_profile_enable", "roms_b200_profile_get",
            "roms_b200_launch_count", "roms_b200_attach_nccl", "roms_b200_nccl_unique_id", "roms_b200_nccl_init_rank",
-           "roms_b200_peer_export", "roms_b200_peer_attach", "roms_b200_peer_enable", "roms_b200_peer_error",
+           "roms_b200_peer_export", "roms_b200_peer_attach", "roms_b200_peer_enable", "roms_b200_peer_error", "roms_b200_peer_error_inject",
+           "roms_b200_set_option",
            "roms_b200_rho_eos_tile", "roms_b200_prsgrd_tile", "roms_b200_set_massflux_tile", "roms_b200_omega_tile",
            "roms_b200_set_depth_tile", "roms_b200_routine_tile", "roms_b200_routine_args", "roms_b200_field_levels"]
 
@@ -99,6 +100,8 @@ def load(strict=False):
     L.roms_b200_peer_attach.argtypes = [H, C.c_char_p, C.c_char_p]
     L.roms_b200_peer_enable.argtypes = [H, C.c_int]
     L.roms_b200_peer_error.argtypes = [H]
+    L.roms_b200_peer_error_inject.argtypes = [H]
+    L.roms_b200_set_option.argtypes = [H, C.c_char_p, C.c_double]
     TP = C.POINTER(TileArgs)
     L.roms_b200_rho_eos_tile.argtypes = [TP] + [DP] * 9
     L.roms_b200_prsgrd_tile.argtypes = [TP] + [DP] * 8

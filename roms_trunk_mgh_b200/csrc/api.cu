@@ -84,25 +84,12 @@ void make_bounds(int Lm, int Mm, int NtileI, int NtileJ, int tile, bool distribu
 
 namespace {
 
-// 2-D fields every step2d call reads or writes and that change during the barotropic loop
-bool is_hot2d(const std::string& n) {
-  static const char* k[] = {"zeta1", "zeta2", "zeta3", "ubar1", "ubar2", "ubar3", "vbar1", "vbar2", "vbar3", "rzeta1", "rzeta2", "rubar1", "rubar2",
-                            "rvbar1", "rvbar2", "Zt_avg1", "DU_avg1", "DU_avg2", "DV_avg1", "DV_avg2"};
-  for (const char* s : k) if (n == s) return true;
-  return false;
-}
-constexpr int NHOT2D = 20;
-
 int alloc_field(roms_b200_state* h, const std::string& name, double** slot, int LBk, int nk) {
   const size_t n = (size_t)h->par.PL * nk;
   double* base = nullptr;
   const size_t bytes = ((n * sizeof(double) + 255) / 256) * 256;
-  if (nk == 1 && h->hot_arena && is_hot2d(name) && h->hot_used + bytes <= h->hot_cap) {
-    base = (double*)(h->hot_arena + h->hot_used); h->hot_used += bytes;
-  } else {
-    CK(cudaMalloc(&base, n * sizeof(double)));
-    h->allocs.push_back(base);
-  }
+  CK(cudaMalloc(&base, bytes));
+  h->allocs.push_back(base);
   CK(cudaMemsetAsync(base, 0, n * sizeof(double), h->stream));
   // element (i,j,k) lives at base[(i-LBi+ioff) + (j-LBj)*P + (k-LBk)*PL]
   *slot = base + h->ioff - h->LBi_dev - (ptrdiff_t)h->b.LBj * h->par.P - (ptrdiff_t)LBk * h->par.PL;
@@ -121,13 +108,33 @@ void fill_par(roms_b200_state* h) {
   p.w1_m1 = W1(h->iif - 1); p.w2_0 = W2(h->iif); p.w2_p1 = W2(h->iif + 1);
 }
 
+// profile = 2: mark the start of `phase` (or, with phase < 0, the end of the step) on the main stream
+void mark_phase(roms_b200_state* h, int phase) {
+  if (h->profile != 2 || h->n_ev_ph >= 40) return;
+  const int q = h->n_ev_ph++;
+  if (!h->ev_ph[q]) cudaEventCreate(&h->ev_ph[q]);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(h->stream, &cs);
+  cudaEventRecordWithFlags(h->ev_ph[q], h->stream, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+  h->ev_ph_phase[q] = phase;
+}
+// profile = 2: after the step has completed, charge the interval between consecutive marks to the phase that started it
+void collect_marks(roms_b200_state* h) {
+  for (int q = 0; q + 1 < h->n_ev_ph; ++q) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_ph[q], h->ev_ph[q + 1]) == cudaSuccess && h->ev_ph_phase[q] >= 0) h->phase_ms[h->ev_ph_phase[q] & 31] += ms;
+  }
+  cudaGetLastError();
+}
+
 struct PhaseTimer {
   roms_b200_state* h; int phase; cudaEvent_t a = nullptr, b = nullptr;
   PhaseTimer(roms_b200_state* h_, int ph) : h(h_), phase(ph) {
-    if (h->profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, h->stream); }
+    if (h->profile == 1) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, h->stream); }
+    else if (h->profile == 2 && h->in_step) mark_phase(h, ph);
   }
   ~PhaseTimer() {
-    if (h->profile) {
+    if (h->profile == 1) {
       cudaEventRecord(b, h->stream); cudaEventSynchronize(b);
       float ms = 0; cudaEventElapsedTime(&ms, a, b); h->phase_ms[phase & 31] += ms;
       cudaEventDestroy(a); cudaEventDestroy(b);
@@ -210,22 +217,7 @@ int launch_with_halo(roms_b200_state* h, int phase, F fn, bool in_kernel_exchang
   return rc;
 }
 
-// L2 residency of the barotropic state (ROMS_B200_L2PERSIST=<MB>, 0 = off): while the step2d loop runs, accesses to the hot
-// arena are marked persisting so the time-varying 2-D fields are served from L2 between sub-steps instead of being evicted by
-// the streamed static metric arrays.
-void l2_window(roms_b200_state* h, cudaStream_t s, bool on) {
-  if (!h->l2_window_bytes || !s) return;
-  cudaStreamAttrValue a;
-  std::memset(&a, 0, sizeof(a));
-  a.accessPolicyWindow.base_ptr = h->hot_arena;
-  a.accessPolicyWindow.num_bytes = on ? h->l2_window_bytes : 0;
-  a.accessPolicyWindow.hitRatio = on ? h->l2_hit : 0.f;
-  a.accessPolicyWindow.hitProp = on ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
-  a.accessPolicyWindow.missProp = on ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
-  cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a);
-}
-
-bool fused_tmix(const roms_b200_state* h) { return h->in_step && h->fuse_tmix && !h->cfg.mix_geo_ts; }
+bool fused_tmix(const roms_b200_state* h) { return h->in_step && !h->cfg.mix_geo_ts; }
 
 int run_phase_async(roms_b200_state* h, int phase) {
   fill_par(h);
@@ -312,47 +304,16 @@ int run_phase_async(roms_b200_state* h, int phase) {
         }
         if (h->iif < h->nfast + 1) { if (sub_step()) return FatalError; }
       }
-      l2_window(h, h->stream, false); l2_window(h, h->comm_stream, false);
       break;
     }
     default: return ConfigError;
   }
   if (rc) return FatalError;
   if (phase == ROMS_B200_DIAG && h->halo) { if (halo_reduce_diag(h)) return FatalError; }
-  if (h->profile) join_halo(h);      // per-phase timing: charge the exposed part of the exchange to its phase
+  if (h->profile == 1) join_halo(h); // per-phase timing: charge the exposed part of the exchange to its phase
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { std::fprintf(stderr, "roms_b200: launch error in phase %d: %s\n", phase, cudaGetErrorString(e)); return FatalError; }
   return NoError;
-}
-
-// Stream attributes are meant to be inherited by captured kernel nodes; if this driver did not do so, give every kernel
-// node of the step the window explicitly (kernels outside the barotropic loop hardly touch the arena).
-void apply_l2_window_to_graph(roms_b200_state* h, cudaGraph_t graph) {
-  size_t n = 0;
-  if (cudaGraphGetNodes(graph, nullptr, &n) != cudaSuccess || n == 0) { cudaGetLastError(); return; }
-  std::vector<cudaGraphNode_t> nodes(n);
-  if (cudaGraphGetNodes(graph, nodes.data(), &n) != cudaSuccess) { cudaGetLastError(); return; }
-  size_t have = 0, kernels = 0;
-  for (cudaGraphNode_t nd : nodes) {
-    cudaGraphNodeType t;
-    if (cudaGraphNodeGetType(nd, &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
-    ++kernels;
-    cudaKernelNodeAttrValue v; std::memset(&v, 0, sizeof(v));
-    if (cudaGraphKernelNodeGetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &v) == cudaSuccess && v.accessPolicyWindow.num_bytes > 0) ++have;
-  }
-  cudaGetLastError();
-  static bool said = false;
-  if (!said) { std::fprintf(stderr, "roms_b200: graph capture: %zu of %zu kernel nodes inherited the L2 window\n", have, kernels); said = true; }
-  if (have > 0) return;
-  cudaKernelNodeAttrValue v; std::memset(&v, 0, sizeof(v));
-  v.accessPolicyWindow.base_ptr = h->hot_arena; v.accessPolicyWindow.num_bytes = h->l2_window_bytes; v.accessPolicyWindow.hitRatio = h->l2_hit;
-  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  for (cudaGraphNode_t nd : nodes) {
-    cudaGraphNodeType t;
-    if (cudaGraphNodeGetType(nd, &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
-    cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &v);
-  }
-  cudaGetLastError();
 }
 
 // main3d.F:189-917 for one step (without the first-step ini_zeta/ini_fields block and without get_data/output)
@@ -381,6 +342,7 @@ int step_phases_body(roms_b200_state* h, bool with_diag) {
                              ROMS_B200_STEP2D_LOOP, ROMS_B200_SET_DEPTH, ROMS_B200_STEP3D_UV, ROMS_B200_OMEGA2, ROMS_B200_STEP3D_T};
   for (int ph : seq3) { int rc = run_phase_async(h, ph); if (rc) return rc; }
   join_halo(h);                      // the step ends with both streams joined (also required to end a graph capture)
+  mark_phase(h, -1);
   return NoError;
 }
 
@@ -392,8 +354,8 @@ int one_step(roms_b200_state* h, bool with_diag) {
   h->nstp = 1 + ((h->iic - h->ntstart) % 2); h->nnew = 3 - h->nstp; h->nrhs = h->nstp;
   h->tdays = h->time / 86400.0;
   const bool steady = h->iic >= h->ntfirst + 2 && h->predictor == 0;
-  if (h->use_graphs && steady && !h->profile) {
-    const int key = h->nstp | (h->indx1 << 2) | ((with_diag ? 1 : 0) << 4);
+  if (h->use_graphs && steady && h->profile != 1) {
+    const int key = h->nstp | (h->indx1 << 2) | ((with_diag ? 1 : 0) << 4) | ((h->profile == 2 ? 1 : 0) << 5);
     auto it = h->graphs.find(key);
     StepGraph* g = (it == h->graphs.end()) ? nullptr : (StepGraph*)it->second;
     if (!g) {
@@ -401,9 +363,9 @@ int one_step(roms_b200_state* h, bool with_diag) {
       const long long l0 = h->launches;
       cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
       bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+      h->n_ev_ph = 0;
       int rc = ok ? step_phases(h, with_diag) : FatalError;
       if (ok) ok = cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && graph != nullptr;
-      if (ok && rc == NoError && h->l2_window_bytes) apply_l2_window_to_graph(h, graph);
       if (ok && rc == NoError) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
       if (graph) cudaGraphDestroy(graph);
       if (!ok || rc != NoError) {
@@ -417,7 +379,7 @@ int one_step(roms_b200_state* h, bool with_diag) {
         h->iic += 1; h->time += h->cfg.dt;
         return NoError;
       }
-      g = new StepGraph{exec, h->indx1, h->iif, h->kstp, h->krhs, h->knew, h->predictor, h->launches - l0};
+      g = new StepGraph{exec, h->indx1, h->iif, h->kstp, h->krhs, h->knew, h->predictor, h->launches - l0, h->n_ev_ph};
       h->graphs[key] = g;
       h->launches = l0;
     }
@@ -425,9 +387,12 @@ int one_step(roms_b200_state* h, bool with_diag) {
     h->indx1 = g->indx1; h->iif = g->iif; h->kstp = g->kstp; h->krhs = g->krhs; h->knew = g->knew; h->predictor = g->predictor;
     h->launches += g->launches;
     h->iic += 1; h->time += h->cfg.dt;
+    if (h->profile == 2) { h->n_ev_ph = g->n_marks; CK(cudaStreamSynchronize(h->stream)); collect_marks(h); }
     return NoError;
   }
+  h->n_ev_ph = 0;
   const int rc = step_phases(h, with_diag);
+  if (h->profile == 2 && !rc) { CK(cudaStreamSynchronize(h->stream)); collect_marks(h); }
   if (rc) return rc;
   h->iic += 1; h->time += h->cfg.dt;
   return NoError;
@@ -440,9 +405,18 @@ bool is_registered(roms_b200_state* h, const void* p, size_t bytes) {
   return false;
 }
 
+// Wait for the stream and read the sticky device error word back with it.  A halo wait that gave up (dev.cuh ll_wait) left
+// garbage in ghost columns: exit_flag becomes 8 and stays 8 (mod_scalars.F:523-532 "fatal algorithm error"), which is what a
+// Fortran host polling FoundError(exit_flag, NoError, ...) after each call needs in order to stop.
+int sync_and_check(roms_b200_state* h) {
+  CK(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return rbi::check_device_error(h);
+}
+
 int finish_diag(roms_b200_state* h, double* out12) {
   CK(cudaMemcpyAsync(h->h_diag_out, h->d_diag_out, 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  { const int rc = sync_and_check(h); if (rc) return rc; }
   const double* d = h->h_diag_out;
   const double vol = d[2];
   out12[0] = d[0] / vol; out12[1] = d[1] / vol; out12[2] = out12[0] + out12[1]; out12[3] = vol;
@@ -455,6 +429,16 @@ int finish_diag(roms_b200_state* h, double* out12) {
 }
 
 }  // namespace
+
+namespace rbi {
+int check_device_error(roms_b200_state* h) {
+  if (h->h_err && *h->h_err != 0ULL) {
+    if (h->exit_flag != FatalError) std::fprintf(stderr, "roms_b200: tile %d: a halo exchange timed out waiting for a neighbour; the state is invalid (exit_flag 8)\n", h->cfg.tile);
+    h->exit_flag = FatalError;
+  }
+  return h->exit_flag == FatalError ? (int)FatalError : (int)NoError;
+}
+}  // namespace rbi
 
 extern "C" {
 
@@ -515,6 +499,15 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   }
   CK(cudaSetDevice(cfg->device));
   roms_b200_state* h = new roms_b200_state();
+#define CKD(call)                                                                                        \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      std::fprintf(stderr, "roms_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      roms_b200_destroy(h);                                                                              \
+      return FatalError;                                                                                 \
+    }                                                                                                    \
+  } while (0)
   h->cfg = *cfg;
   make_bounds(cfg->Lm, cfg->Mm, cfg->NtileI, cfg->NtileJ, cfg->tile, cfg->NtileI > 1, h->b);
   const Bounds& b = h->b;
@@ -540,36 +533,12 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   for (int it = 0; it < MAXNT; ++it) p.Akt_bak[it] = cfg->Akt_bak[it];
   h->dtfast = cfg->dt / (double)cfg->ndtfast;
   std::memset(h->phase_ms, 0, sizeof(h->phase_ms));
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  { const char* ng = std::getenv("ROMS_B200_NO_GRAPH"); h->use_graphs = !(ng && ng[0] == '1'); }
-  { const char* e = std::getenv("ROMS_B200_FUSE_TMIX"); h->fuse_tmix = !(e && e[0] == '0'); }
-  { const char* e = std::getenv("ROMS_B200_FUSED_XCHG"); h->fused_mode = e ? std::atoi(e) : 2; }
-  CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+  CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CKD(cudaEventCreate(&h->ev0)); CKD(cudaEventCreate(&h->ev1));
   Flds& f = h->fl;
   std::memset(&f, 0, sizeof(f));
   const int N = cfg->N;
   int rc = 0;
-  {
-    const char* e = std::getenv("ROMS_B200_L2PERSIST");
-    const long want_mb = e ? std::atol(e) : 0;
-    if (want_mb > 0) {
-      const size_t per = (((size_t)p.PL * sizeof(double) + 255) / 256) * 256;
-      h->hot_cap = per * NHOT2D;
-      if (cudaMalloc(&h->hot_arena, h->hot_cap) == cudaSuccess) {
-        h->allocs.push_back(h->hot_arena);
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg->device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cfg->device);
-        size_t setaside = std::min((size_t)want_mb << 20, (size_t)max_persist);
-        if (setaside > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside) == cudaSuccess) {
-          h->l2_window_bytes = std::min(h->hot_cap, (size_t)max_window);
-          h->l2_hit = (float)std::min(1.0, (double)setaside / (double)h->l2_window_bytes);
-        } else cudaGetLastError();
-        std::fprintf(stderr, "roms_b200: L2 persistence: arena %.1f MB, set-aside %.1f MB (device max %.1f MB), window %.1f MB, hitRatio %.2f\n",
-                     h->hot_cap / 1048576.0, setaside / 1048576.0, max_persist / 1048576.0, h->l2_window_bytes / 1048576.0, h->l2_hit);
-      } else { cudaGetLastError(); h->hot_arena = nullptr; h->hot_cap = 0; }
-    }
-  }
 #define A2(name) rc |= alloc_field(h, #name, &f.name, 0, 1)
 #define A3(name, k0, nk) rc |= alloc_field(h, #name, &f.name, k0, nk)
   A2(h); A2(f); A2(pm); A2(pn); A2(om_r); A2(on_r); A2(om_u); A2(on_u); A2(om_v); A2(on_v); A2(om_p); A2(on_p); A2(omn); A2(fomn);
@@ -606,16 +575,22 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   }
   if (rc) { roms_b200_destroy(h); return FatalError; }
   double* sc = nullptr;
-  CK(cudaMalloc(&sc, 4 * (MAXN + 1) * sizeof(double)));
-  CK(cudaMemsetAsync(sc, 0, 4 * (MAXN + 1) * sizeof(double), h->stream));
+  CKD(cudaMalloc(&sc, 4 * (MAXN + 1) * sizeof(double)));
+  CKD(cudaMemsetAsync(sc, 0, 4 * (MAXN + 1) * sizeof(double), h->stream));
   h->allocs.push_back(sc);
   f.sc_r = sc; f.Cs_r = sc + (MAXN + 1); f.sc_w = sc + 2 * (MAXN + 1); f.Cs_w = sc + 3 * (MAXN + 1);
-  CK(cudaMalloc(&h->d_diag_partial, (size_t)diag_partial_doubles(p) * sizeof(double)));
+  CKD(cudaMalloc(&h->d_diag_partial, (size_t)diag_partial_doubles(p) * sizeof(double)));
   h->allocs.push_back(h->d_diag_partial);
-  CK(cudaMalloc(&h->d_diag_out, 16 * sizeof(double)));
+  CKD(cudaMalloc(&h->d_diag_out, 16 * sizeof(double)));
   h->allocs.push_back(h->d_diag_out);
-  CK(cudaMallocHost(&h->h_diag_out, 16 * sizeof(double)));
-  CK(cudaStreamSynchronize(h->stream));
+  CKD(cudaMallocHost(&h->h_diag_out, 16 * sizeof(double)));
+  CKD(cudaMalloc(&h->d_err, 64));
+  h->allocs.push_back(h->d_err);
+  CKD(cudaMemsetAsync(h->d_err, 0, 64, h->stream));
+  CKD(cudaMallocHost(&h->h_err, 64));
+  std::memset(h->h_err, 0, 64);
+  CKD(cudaStreamSynchronize(h->stream));
+#undef CKD
   *out = h;
   return NoError;
 }
@@ -629,9 +604,11 @@ int roms_b200_destroy(roms_b200_handle h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_forcing); cudaEventDestroy(h->ev_step_in); }
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_diag_out) cudaFreeHost(h->h_diag_out);
+  if (h->h_err) cudaFreeHost(h->h_err);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   for (auto& r : h->host_pinned) cudaHostUnregister(r.first);
   h->host_pinned.clear();
+  for (cudaEvent_t e : h->ev_ph) if (e) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -658,7 +635,7 @@ static int xfer(roms_b200_handle h, const char* name, double* host, size_t n, bo
   if (up) CK(cudaMemcpy2DAsync(dev, dp, host, sp, sp, (size_t)h->nj * fi.nk, cudaMemcpyHostToDevice, h->stream));
   else CK(cudaMemcpy2DAsync(host, sp, dev, dp, sp, (size_t)h->nj * fi.nk, cudaMemcpyDeviceToHost, h->stream));
   if (up && h->halo) { if (halo_exchange(h, {std::string(name)}, h->stream)) return FatalError; }
-  CK(cudaStreamSynchronize(h->stream));
+  { const int rc = sync_and_check(h); if (rc) return rc; }
   if (up && std::strncmp(name, "diff2_", 6) == 0) {
     bool z = true;
     for (size_t q = 0; q < n; ++q) if (host[q] != 0.0) { z = false; break; }
@@ -713,13 +690,13 @@ int roms_b200_run_phase(roms_b200_handle h, int phase) {
   int rc = run_phase_async(h, phase);
   join_halo(h);
   if (rc) return rc;
-  CK(cudaStreamSynchronize(h->stream));
-  return NoError;
+  return sync_and_check(h);
 }
 
 int roms_b200_main3d_step(roms_b200_handle h, int nsteps) {
   if (!h || nsteps < 0) return InputError;
   if (h->nfast < 1) { std::fprintf(stderr, "roms_b200: set_weights must be called before stepping\n"); return ConfigError; }
+  if (h->exit_flag == FatalError) return FatalError;
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaEventRecord(h->ev0, h->stream));
   for (int s = 0; s < nsteps; ++s) { int rc = one_step(h, false); if (rc) return rc; }
@@ -730,6 +707,28 @@ int roms_b200_main3d_step(roms_b200_handle h, int nsteps) {
 int roms_b200_sync(roms_b200_handle h) {
   if (!h) return InputError;
   CK(cudaSetDevice(h->cfg.device));
+  return sync_and_check(h);
+}
+
+int roms_b200_set_option(roms_b200_handle h, const char* key, double value) {
+  if (!h || !key) return InputError;
+  const std::string k(key);
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (k == "cuda_graphs") h->use_graphs = value != 0.0;
+  else if (k == "step2d_exchange") { const int m = (int)value; if (m < 0 || m > 2 || h->halo) return ConfigError; h->fused_mode = m; }
+  else if (k == "overlap") { if (h->halo) return ConfigError; h->opt_overlap = value != 0.0; }
+  else if (k == "halo_timeout_s") h->halo_timeout_s = value;
+  else return InputError;
+  drop_graphs(h);
+  return NoError;
+}
+
+int roms_b200_peer_error_inject(roms_b200_handle h) {
+  if (!h || !h->d_err) return InputError;
+  CK(cudaSetDevice(h->cfg.device));
+  const unsigned long long one = 1ULL;
+  CK(cudaMemcpyAsync(h->d_err, &one, sizeof(one), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return NoError;
 }
@@ -752,6 +751,7 @@ int roms_b200_diag(roms_b200_handle h, double* out12) {
 int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double* svstr, const double* stflux_temp, size_t n2d, double* out12) {
   if (!h || !out12) return InputError;
   if (h->nfast < 1) return ConfigError;
+  if (h->exit_flag == FatalError) return FatalError;
   CK(cudaSetDevice(h->cfg.device));
   const size_t want = (size_t)h->ni * h->nj;
   if ((sustr || svstr || stflux_temp) && n2d != want) return InputError;
@@ -824,6 +824,7 @@ int roms_b200_unregister_host(roms_b200_handle h, void* p) {
 
 int roms_b200_profile_enable(roms_b200_handle h, int on) {
   if (!h) return InputError;
+  if (on < 0 || on > 2) return InputError;
   h->profile = on; std::memset(h->phase_ms, 0, sizeof(h->phase_ms));
   return NoError;
 }

@@ -25,6 +25,7 @@ struct NcclApi {
   int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -39,10 +40,10 @@ static NcclApi& nccl() {
   if (!a.lib) { std::fprintf(stderr, "roms_b200: cannot load NCCL (%s)\n", dlerror()); return a; }
 #define SYM(field, name) *(void**)(&a.field) = dlsym(a.lib, name)
   SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
-  SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(AllReduce, "ncclAllReduce"); SYM(GroupStart, "ncclGroupStart");
+  SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(AllReduce, "ncclAllReduce"); SYM(AllGather, "ncclAllGather"); SYM(GroupStart, "ncclGroupStart");
   SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
-  a.ok = a.GetUniqueId && a.CommInitRank && a.Send && a.Recv && a.AllReduce && a.GroupStart && a.GroupEnd;
+  a.ok = a.GetUniqueId && a.CommInitRank && a.Send && a.Recv && a.AllReduce && a.AllGather && a.GroupStart && a.GroupEnd;
   return a;
 }
 
@@ -65,6 +66,7 @@ struct Halo {
   // (dev.cuh Xchg, k_step2d.cu); off2 = its offset in doubles, identical on every rank
   size_t off2 = 0;
   bool fused_on = false;
+  double* diag_all = nullptr;                                                      // 16 doubles per tile (halo_reduce_diag)
 };
 
 constexpr int BOX_HDR = 64;                       // header doubles: [2] epoch [4] block counter [6] error
@@ -101,7 +103,7 @@ __device__ __forceinline__ double* field_elem(const FieldTab& t, int plane, int 
 // I send after my epoch-e kernel (including its unpack) has completed.  (ll_store / ll_load: dev.cuh.)
 using rb::ll_load; using rb::ll_store;
 __global__ void __launch_bounds__(256) k_halo_xchg(FieldTab t, int P, int PL, int nj, int Istr, int Iend, int totE, int totW, size_t cap,
-                                                   unsigned long long* hdr, double* box, double* boxE, double* boxW) {
+                                                   unsigned long long* hdr, double* box, double* boxE, double* boxW, unsigned long long* err, long long timeout_ns) {
   const unsigned long long e = hdr[2] + 1;                  // epoch of this exchange (bumped by the last CTA below)
   const unsigned tag = (unsigned)e;
   const size_t base = BOX_HDR + (e & 1) * box_slot(cap);
@@ -117,11 +119,7 @@ __global__ void __launch_bounds__(256) k_halo_xchg(FieldTab t, int P, int PL, in
   if (east || west) {
     const double* line = box + (east ? slotW : slotE);
     double v;
-    const long long t0 = clock64();
-    while (!ll_load(line, tag, v)) {
-      if (clock64() - t0 > (5LL << 30)) { hdr[6] = 1; break; }        // ~3 s: give up instead of hanging the GPU (host reports it)
-      __nanosleep(20);
-    }
+    rb::ll_wait(line, tag, v, timeout_ns, err);
     if (east) *field_elem(t, plane, j, Istr - NW + c, P, PL) = v;     // from the west neighbour
     else *field_elem(t, plane, j, Iend + 1 + c, P, PL) = v;           // from the east neighbour
   }
@@ -135,8 +133,6 @@ __global__ void __launch_bounds__(256) k_halo_xchg(FieldTab t, int P, int PL, in
 int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names, cudaStream_t s) {
   Halo* H = h->halo;
   if (!H || names.empty()) return 0;
-  static const int dbg_mode = [] { const char* e = std::getenv("ROMS_B200_XCHG_DEBUG"); return e ? std::atoi(e) : 0; }();   // timing experiments only
-  if (dbg_mode == 2) return 0;
   NcclApi& N = nccl();
   FieldTab t; t.n = 0; int planes = 0;
   for (const std::string& nm : names) {
@@ -150,7 +146,8 @@ int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names, cud
   if (H->peer_on && need <= H->box_cap) {
     const int totE = (int)need * NW, totW = (int)need * NE, tot = totE + totW;
     unsigned long long* hdr = (unsigned long long*)H->box;
-    k_halo_xchg<<<(tot + 255) / 256, 256, 0, s>>>(t, P, PL, nj, h->b.Istr, h->b.Iend, totE, totW, H->box_cap, hdr, H->box, H->boxE, H->boxW);
+    k_halo_xchg<<<(tot + 255) / 256, 256, 0, s>>>(t, P, PL, nj, h->b.Istr, h->b.Iend, totE, totW, H->box_cap, hdr, H->box, H->boxE, H->boxW, h->d_err,
+                                                   (long long)(h->halo_timeout_s * 1e9));
     h->launches += 1;
     return cudaGetLastError() == cudaSuccess ? 0 : 8;
   }
@@ -167,14 +164,12 @@ int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names, cud
   k_pack<<<(totE + 255) / 256, 256, 0, s>>>(t, P, PL, nj, Iend - NW + 1, NW, totE, H->sendE, 0);
   k_pack<<<(totW + 255) / 256, 256, 0, s>>>(t, P, PL, nj, Istr, NE, totW, H->sendW, 0);
   int rc = 0;
-  if (dbg_mode != 1) {
   rc |= N.GroupStart();
   rc |= N.Send(H->sendE, (size_t)totE, ncclFloat64, H->east, H->comm, s);
   rc |= N.Recv(H->recvW, (size_t)totE, ncclFloat64, H->west, H->comm, s);
   rc |= N.Send(H->sendW, (size_t)totW, ncclFloat64, H->west, H->comm, s);
   rc |= N.Recv(H->recvE, (size_t)totW, ncclFloat64, H->east, H->comm, s);
   rc |= N.GroupEnd();
-  }
   if (rc) { std::fprintf(stderr, "roms_b200: NCCL error in halo_exchange\n"); return 8; }
   k_pack<<<(totE + 255) / 256, 256, 0, s>>>(t, P, PL, nj, Istr - NW, NW, totE, H->recvW, 1);
   k_pack<<<(totW + 255) / 256, 256, 0, s>>>(t, P, PL, nj, Iend + 1, NE, totW, H->recvE, 1);
@@ -188,19 +183,38 @@ bool fused_xchg_fill(roms_b200_state* h, rb::Xchg& x) {
   if (!H || !H->peer_on || !H->fused_on || !H->off2) return false;
   std::memset(&x, 0, sizeof(x));
   x.Istr = h->b.Istr; x.Iend = h->b.Iend; x.nj = h->nj;
+  x.err = h->d_err; x.timeout_ns = (long long)(h->halo_timeout_s * 1e9);
   x.box = H->box + H->off2; x.boxE = H->boxE + H->off2; x.boxW = H->boxW + H->off2;
   return true;
+}
+
+// Cross-tile reduction of the diag scalars.  diag.F reports the Courant components AT the location of the largest
+// Courant number (:388-404, a MAXLOC-style reduction across tiles in the distributed build), so the tiles' 16-double
+// records are gathered and reduced by one thread in tile order: sums ke, pe, volume in ascending tile number (deterministic),
+// (maxC, Cu, Cv, Cw) from the tile that owns the largest C (lowest tile on ties), plain maxima for the rest.
+__global__ void k_diag_ring_final(const double* __restrict__ all, int nranks, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double ke = 0.0, pe = 0.0, vol = 0.0, mC = 0.0, mCu = 0.0, mCv = 0.0, mCw = 0.0;
+  double mx[6] = {0.0, -1.0e37, 0.0, 0.0, 0.0, 0.0};           // max speed, max rho, umax, vmax, ubarmax, vbarmax ([7..12])
+  for (int r = 0; r < nranks; ++r) {
+    const double* d = all + 16 * r;
+    vol = vol + d[2]; pe = pe + d[1]; ke = ke + d[0];
+    if (d[3] > mC) { mC = d[3]; mCu = d[4]; mCv = d[5]; mCw = d[6]; }
+    for (int q = 0; q < 6; ++q) mx[q] = rb::dmax(mx[q], d[7 + q]);
+  }
+  out[0] = ke; out[1] = pe; out[2] = vol; out[3] = mC; out[4] = mCu; out[5] = mCv; out[6] = mCw;
+  for (int q = 0; q < 6; ++q) out[7 + q] = mx[q];
 }
 
 int halo_reduce_diag(roms_b200_state* h) {
   Halo* H = h->halo;
   if (!H) return 0;
   NcclApi& N = nccl();
-  int rc = N.GroupStart();
-  rc |= N.AllReduce(h->d_diag_out, h->d_diag_out, 3, ncclFloat64, ncclSum, H->comm, h->stream);
-  rc |= N.AllReduce(h->d_diag_out + 3, h->d_diag_out + 3, 10, ncclFloat64, ncclMax, H->comm, h->stream);
-  rc |= N.GroupEnd();
-  return rc ? 8 : 0;
+  if (!H->diag_all && cudaMalloc(&H->diag_all, (size_t)16 * H->nranks * sizeof(double)) != cudaSuccess) return 8;
+  if (N.AllGather(h->d_diag_out, H->diag_all, 16, ncclFloat64, H->comm, h->stream)) return 8;
+  k_diag_ring_final<<<1, 32, 0, h->stream>>>(H->diag_all, H->nranks, h->d_diag_out);
+  h->launches += 1;
+  return cudaGetLastError() == cudaSuccess ? 0 : 8;
 }
 
 void drop_graphs(roms_b200_state* h) {
@@ -215,6 +229,7 @@ void halo_destroy(roms_b200_state* h) {
   if (H->mapW) cudaIpcCloseMemHandle(H->mapW);
   if (H->mapE && H->mapE != H->mapW) cudaIpcCloseMemHandle(H->mapE);
   if (H->box) cudaFree(H->box);
+  if (H->diag_all) cudaFree(H->diag_all);
   if (H->own_comm && H->comm && nccl().CommDestroy) nccl().CommDestroy(H->comm);
   delete H;
   h->halo = nullptr;
@@ -266,8 +281,7 @@ int roms_b200_attach_nccl(roms_b200_handle h, void* nccl_comm, int rank, int nra
     cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming);
   }
-  const char* no = std::getenv("ROMS_B200_NO_OVERLAP");
-  h->overlap = !(no && no[0] == '1');
+  h->overlap = h->opt_overlap;
   std::vector<std::string> batch;
   for (auto& kv : h->reg) {
     if (kv.first == "P3") continue;
@@ -321,17 +335,18 @@ int roms_b200_peer_enable(roms_b200_handle h, int on) {
   cudaStreamSynchronize(h->stream);
   drop_graphs(h);
   H->peer_on = on != 0;
-  { const char* e = std::getenv("ROMS_B200_FUSED_XCHG"); H->fused_on = H->peer_on && !(e && e[0] == '0'); }
+  H->fused_on = H->peer_on && h->fused_mode != 0;
   return 0;
 }
 
-// 1 if a peer exchange timed out waiting for a neighbour (results are then invalid), else 0
+// 1 if a peer exchange timed out waiting for a neighbour (results are then invalid; every synchronising entry point
+// also returns 8 from then on), else 0
 int roms_b200_peer_error(roms_b200_handle h) {
-  if (!h || !h->halo || !h->halo->box) return 0;
-  unsigned long long w = 0, w2 = 0;
-  cudaMemcpy(&w, (unsigned long long*)h->halo->box + 6, sizeof(w), cudaMemcpyDeviceToHost);
-  if (h->halo->off2) cudaMemcpy(&w2, (unsigned long long*)(h->halo->box + h->halo->off2) + 2, sizeof(w2), cudaMemcpyDeviceToHost);
-  return (w | w2) != 0;
+  if (!h || !h->d_err) return 0;
+  unsigned long long w = 0;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return 1;
+  cudaMemcpy(&w, h->d_err, sizeof(w), cudaMemcpyDeviceToHost);
+  return w != 0;
 }
 
 }  // extern "C"

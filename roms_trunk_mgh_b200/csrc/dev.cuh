@@ -181,6 +181,8 @@ __device__ __forceinline__ void sweep_levels_deep(int N, Load load, Body body) {
 // only relies on 8-byte store atomicity), so no fences or separate flags are needed.  XSLOTS epochs are kept apart.
 constexpr int XNW = 3, XNE = 2, XF = 4, XSLOTS = 4, XHDR = 16;     // XHDR doubles of header: [0] epoch, [1] CTA counter, [2] error
 struct Xchg {
+  unsigned long long* err;         // sticky device error word of the tile (state.h d_err): set when a wait gives up
+  long long timeout_ns;            // how long a pull waits for the neighbour (<= 0: for ever)
   int send, recv;                  // push this sub-step's edge columns / first pull the previous sub-step's
   int nsend, nrecv;                // number of fields (3: zeta, ubar, vbar; 4: + rzeta)
   int Istr, Iend, nj;              // tile bounds (a split launch may cover only part of them), rows per column
@@ -203,6 +205,21 @@ __device__ __forceinline__ bool ll_load(const double* line, unsigned tag, double
   asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(line) : "memory");
   v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
   return t0 == tag && t1 == tag;
+}
+
+// Wall-clock nanoseconds (independent of the SM clock): bounds the halo waits.
+__device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// Spin until the line carries `tag`.  A neighbour that never delivers (a rank that died, a host that stopped stepping) ends
+// the wait after timeout_ns: the sticky error word is set -- every host synchronisation point of the library turns it into
+// exit_flag 8 -- and the value is whatever the line held.  false: timed out.
+__device__ __forceinline__ bool ll_wait(const double* line, unsigned tag, double& v, long long timeout_ns, unsigned long long* err) {
+  if (ll_load(line, tag, v)) return true;
+  const long long t0 = gtime_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int q = 0; q < 64; ++q) { if (ll_load(line, tag, v)) return true; __nanosleep(20); }
+    if (timeout_ns > 0 && gtime_ns() - t0 > timeout_ns) { *err = 1ULL; return false; }
+  }
 }
 
 // Function attributes (opt-in dynamic shared memory) are per device: launch wrappers remember what they set per device, so

@@ -16,6 +16,7 @@
 // of the kernel, those of stage 3 before the barrier that ends stage 2 -- and the CTA has enough threads (NTH) to cover the
 // (TX+1)x(TY+1) flux regions in a single pass.  On a ring of tiles the xi-halo exchange of the sub-step is part of this
 // kernel (template XCH, dev.cuh Xchg).
+#include <cstdio>
 #include <cstring>
 #include "dev.cuh"
 #include "kernels.h"
@@ -122,11 +123,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
         if (j >= 0 && j <= Mm + 1) {
           const double* line = slot + (w ? xline_w(x.nj, fld, j, c) : xline_e(x.nj, fld, j, c));
           double v;
-          const long long t0 = clock64();
-          while (!ll_load(line, tag, v)) {
-            if (clock64() - t0 > (5LL << 30)) { ((unsigned long long*)x.box)[2] = 1; break; }   // ~3 s: give up, the host reports it
-            __nanosleep(20);
-          }
+          ll_wait(line, tag, v, x.timeout_ns, x.err);
           x.recvf[fld][j * P + (w ? x.Istr - XNW + c : x.Iend + 1 + c)] = v;
         }
       }
@@ -524,15 +521,19 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
   }
 }
 
-// the default step2d kernel (launch_step2d in k_step2d_m.cu dispatches; ROMS_B200_STEP2D=march selects the marching variant)
-void launch_step2d_tile(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x) {
+void launch_step2d(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x) {
   dim3 g((xspan(p) + TX - 1) / TX, (p.Mm + TY - 1) / TY);
   const size_t smem = (size_t)SMEM_DOUBLES * sizeof(double);
   static bool done[MAXDEV] = {false};
   bool& once = done[cur_dev()];
   if (!once) {
-    cudaFuncSetAttribute(k_step2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_step2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // 59.6 KB of dynamic shared memory is above the 48 KB default: without the opt-in the launch fails
+    const cudaError_t e1 = cudaFuncSetAttribute(k_step2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const cudaError_t e2 = cudaFuncSetAttribute(k_step2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      std::fprintf(stderr, "roms_b200: cannot opt in to %zu bytes of shared memory for k_step2d: %s\n", smem, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      return;      // the sticky CUDA error is picked up by the caller's cudaGetLastError (run_phase_async -> exit_flag 8)
+    }
     once = true;
   }
   Xchg none;

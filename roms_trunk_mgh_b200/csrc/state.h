@@ -34,10 +34,6 @@ struct roms_b200_state {
   int LBi_dev, ni_dev;    // device arrays carry 3 west ghost columns on every tile (the fused step2d kernel needs Drhs(i-3))
   std::map<std::string, rbi::FieldInfo> reg;
   std::vector<void*> allocs;
-  // time-varying 2-D fields of the barotropic sub-steps live in one arena so that an L2 access-policy window can keep them
-  // resident across the 59 step2d launches of a baroclinic step (api.cu l2_window)
-  char* hot_arena = nullptr; size_t hot_cap = 0, hot_used = 0;
-  size_t l2_window_bytes = 0; float l2_hit = 0.f;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // stepping state (mod_stepping.F)
@@ -46,6 +42,10 @@ struct roms_b200_state {
   int nfast = 0;
   std::vector<double> w1, w2;
   double dtfast = 0.0;
+  // Sticky device error word (allocated with the state; [0] != 0: a halo wait of a peer-memory exchange gave up, so ghost
+  // columns hold garbage).  Every host synchronisation point reads it back and turns it into exit_flag 8 (check_device_error).
+  unsigned long long* d_err = nullptr; unsigned long long* h_err = nullptr;
+  double halo_timeout_s = 30.0;     // how long a kernel waits for a neighbour's halo before it gives up (roms_b200_set_option)
   // diag
   double* d_diag_partial = nullptr; double* d_diag_out = nullptr; double* h_diag_out = nullptr;
   double* h_pinned = nullptr; size_t pinned_n = 0; double* d_stage = nullptr;
@@ -53,18 +53,22 @@ struct roms_b200_state {
   // step_forced: this step's surface forcing is uploaded on its own stream while the first phases of the step (which do not
   // read it) already run; the step waits for ev_forcing just before set_vbc
   cudaStream_t copy_stream = nullptr; cudaEvent_t ev_forcing = nullptr, ev_step_in = nullptr;
-  // profiling
+  // profiling.  profile = 1: every phase bracketed by CUDA events and synchronised (plain stream launches, halos joined per
+  // phase); profile = 2: one event between consecutive phases on the main stream, recorded INSIDE the captured step graph
+  // (external event-record nodes), so the split describes the configuration that is actually timed and the phase times
+  // add up to the step time by construction.
   int profile = 0; double phase_ms[32]; long long launches = 0;
+  cudaEvent_t ev_ph[40] = {}; int ev_ph_phase[40] = {}; int n_ev_ph = 0;
   bool all_diff2_zero = true;
   // multi-GPU: ring context, and the second (high-priority) stream on which halo exchanges run while the tile interior is
   // being computed on `stream` (api.cu launch_with_halo)
   rbi::Halo* halo = nullptr;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_edge = nullptr, ev_halo = nullptr, ev_main = nullptr;
-  int overlap = 0;
+  int overlap = 0;        // edge-first two-stream schedule active (set at attach from opt_overlap)
+  int opt_overlap = 1;    // roms_b200_set_option("overlap")
   bool edge_pending = false, halo_pending = false;   // main stream has not yet waited for the latest ev_edge / ev_halo
   // CUDA graphs of whole time steps, keyed by the stepping state at the start of the step (api.cu one_step)
-  int fuse_tmix = 1;      // whole-step path: t3dmix2_s folded into pre_step3d_t (ROMS_B200_FUSE_TMIX=0 keeps the separate kernel)
   int fused_mode = 2;     // step2d halo exchange inside the kernels: 0 off, 1 one launch per sub-step, 2 edge / interior split launches
   bool in_step = false;   // inside step_phases (cross-routine fusions are only legal there: run_phase keeps routine granularity)
   int use_graphs = 1;
@@ -73,12 +77,14 @@ struct roms_b200_state {
 
 namespace rbi {
 // One captured time step (CUDA graph) and the host-side stepping state it leaves behind.
-struct StepGraph { cudaGraphExec_t exec; int indx1, iif, kstp, krhs, knew, predictor; long long launches; };
+struct StepGraph { cudaGraphExec_t exec; int indx1, iif, kstp, krhs, knew, predictor; long long launches; int n_marks; };
 }  // namespace rbi
 
 namespace rbi {
 // Halo exchange of the named fields along the xi ring (mp_exchange2d/3d/4d semantics); no-op without an attached comm.
 int halo_exchange(roms_b200_state* h, const std::vector<std::string>& names, cudaStream_t s);
+// read the sticky device error word back (after the stream has been synchronised): 0, or 8 with exit_flag set
+int check_device_error(roms_b200_state* h);
 // mailboxes of the exchange fused into the step2d kernel (false: not available, use halo_exchange)
 bool fused_xchg_fill(roms_b200_state* h, rb::Xchg& x);
 // cross-tile reduction of the 16-double diag buffer: [0..2] sum, [3..12] max

@@ -6,7 +6,6 @@ the communicator to a Tile, (c) scatters / gathers whole global arrays for set-u
 numpy model of the ring exchange that the CPU (gloo) tests run.
 """
 import ctypes as C
-import os
 
 import numpy as np
 
@@ -33,7 +32,7 @@ def broadcast_bytes(dist, payload, src=0):
 
 def attach(tile, dist, rank, world, peer=True):
     """Create the NCCL ring communicator for `tile` (rank == tile index) and fill all ghost columns; then, unless
-    peer=False or ROMS_B200_NO_PEER=1, move the exchanges to the NVLink peer path.  Collective."""
+    peer=False, move the exchanges to the NVLink peer path.  Collective."""
     L = tile.L
     idbuf = C.create_string_buffer(128)
     if rank == 0:
@@ -50,7 +49,7 @@ def attach(tile, dist, rank, world, peer=True):
         raise RuntimeError(f"roms_b200_attach_nccl -> {rc}")
     tile._nccl_comm = comm
     tile.peer = False
-    if peer and os.environ.get("ROMS_B200_NO_PEER") != "1":
+    if peer:
         tile.peer = enable_peer(tile, dist, rank, world)
     return comm
 

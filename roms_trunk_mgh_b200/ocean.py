@@ -108,6 +108,10 @@ class Tile:
         if sync:
             self.sync()
 
+    def set_option(self, key, value):
+        """roms_b200_set_option: "cuda_graphs", "step2d_exchange", "overlap", "halo_timeout_s"."""
+        self._ck(f"set_option({key})", self.L.roms_b200_set_option(self.h, key.encode(), float(value)))
+
     def sync(self):
         self._ck("sync", self.L.roms_b200_sync(self.h))
 

@@ -1,7 +1,7 @@
-"""Run by test_gpu_parity.py in a subprocess with kernel-selection environment variables set (they are read once per
-process): steps a strict-build tile and the oracle side by side and demands bit-exact fields; prints a digest of the state.
+"""Run by test_gpu_parity.py in a subprocess: steps a strict-build tile and the oracle side by side with the given
+roms_b200_set_option switches and demands bit-exact fields; prints a digest of the state.
 
-    ROMS_B200_STEP2D=march python tests/gpu_variant_check.py benchmark30 6
+    python tests/gpu_variant_check.py benchmark30 6 cuda_graphs=0
 """
 import hashlib
 import os
@@ -22,8 +22,11 @@ def main():
     case, nsteps = sys.argv[1], int(sys.argv[2])
     app, kw = CASES[case]
     o, t = make_pair(app, strict=True, **kw)
+    opts = dict(a.split("=") for a in sys.argv[3:])
+    for k, v in opts.items():
+        t.set_option(k, float(v))
     o.step(nsteps)
-    t.main3d(nsteps)                      # steps >= 3 replay the captured CUDA graph unless ROMS_B200_NO_GRAPH=1
+    t.main3d(nsteps)                      # steps >= 3 replay the captured CUDA graph unless cuda_graphs=0
     names = all_names(int(o.opt("NT")))
     bad = compare(o, t, names, exact=True)
     h = hashlib.sha256()
@@ -33,7 +36,7 @@ def main():
     if bad:
         print("MISMATCH", bad[:4])
         sys.exit(1)
-    print("VARIANT_OK", case, nsteps, {k: os.environ[k] for k in os.environ if k.startswith("ROMS_B200_")})
+    print("VARIANT_OK", case, nsteps, opts)
 
 
 if __name__ == "__main__":

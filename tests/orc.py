@@ -26,9 +26,23 @@ BOUND_NAMES = ["tile", "Itile", "Jtile", "LBi", "UBi", "LBj", "UBj", "IminS", "I
 _libs = {}
 
 
+def cpu_tag():
+    """Short hash of this host's CPU feature flags: names the -march=native builds, so that a library built on another
+    host (the build container vs. the GPU box) is rebuilt here instead of dying with an illegal instruction."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as fh:
+            flags = next((ln for ln in fh if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return "_" + hashlib.sha1(flags.encode()).hexdigest()[:8]
+
+
 def build(kind="parity"):
-    target = {"parity": "_build/liboracle.so", "fast": "_build/liboracle_fast.so", "chk": "_build/liboracle_chk.so"}[kind]
-    subprocess.run(["make", "-s", "-C", ORACLE_DIR, target], check=True)
+    tag = cpu_tag()
+    target = {"parity": "_build/liboracle.so", "fast": f"_build/liboracle_fast{tag}.so", "fastmath": f"_build/liboracle_fastmath{tag}.so",
+              "chk": "_build/liboracle_chk.so"}[kind]
+    subprocess.run(["make", "-s", f"-j{min(os.cpu_count() or 1, 12)}", "-C", ORACLE_DIR, f"TAG={tag}", target], check=True)
     return os.path.join(ORACLE_DIR, target)
 
 

@@ -270,6 +270,45 @@ def test_full_size_benchmark1_properties_and_parity():
     tt.close()
 
 
+def _oracle_threads():
+    return min(os.cpu_count() or 1, 32)
+
+
+@pytest.mark.parametrize("grid", [(1024, 128, 30), (2048, 256, 30)], ids=["benchmark2", "benchmark3"])
+def test_full_size_benchmark2_and_3_parity(grid):
+    """BENCHMARK2 and BENCHMARK3 at FULL size against the oracle (host threads, one tile each): 2 spin-up steps on the
+    oracle, state copied to the device, then 2 more steps on both; production-build tolerance (1e-8 on zeta/u/v, 1e-12 on
+    tracers) on every owned point and ghost."""
+    Lm, Mm, N = grid
+    nth = _oracle_threads()
+    o = orc.Oracle(orc.APP_BENCHMARK, Lm=Lm, Mm=Mm, N=N, NtileI=nth, NtileJ=1)
+    o.run_phase("set_data"); o.run_phase("ini")
+    o.step(2, nth)
+    t = Tile(cfg_from_oracle(o), strict=False)
+    copy_state(o, t)
+    o.step(2, nth); t.main3d(2)
+    assert not compare(o, t, ["zeta1", "zeta2", "u1", "u2", "v1", "v2", "ubar1", "vbar1", "ubar2", "vbar2"], exact=False, rtol=1e-8)
+    assert not compare(o, t, ["t1_0", "t2_0", "t1_1", "t2_1", "rho"], exact=False, rtol=1e-12)
+    assert t.indices()["iic"] == o.indices()["iic"] and t.indices()["exit_flag"] == 0
+    t.close()
+
+
+def test_bench_workload_parity_synth_make_tile():
+    """The bench workload exactly as bench.py builds it -- synth.make_tile(APP_BENCHMARK, 2048, 256, 30), graph-replayed
+    steps -- against the oracle started from its own (independent) set-up: 5 steps, so the Euler / AB2 / AB3 start-up
+    branches and two graph replays are covered.  The two set-ups (numpy vs C++ libm) agree to 2e-13
+    (test_oracle_cpu.py::test_synth_matches_oracle_setup), hence 1e-11 instead of 1e-12 on the tracers."""
+    nth = _oracle_threads()
+    Lm, Mm, N = 2048, 256, 30
+    t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N)
+    o = orc.Oracle(orc.APP_BENCHMARK, Lm=Lm, Mm=Mm, N=N, NtileI=nth, NtileJ=1)
+    o.run_phase("set_data"); o.run_phase("ini")
+    o.step(5, nth); t.main3d(5)
+    assert not compare(o, t, ["zeta1", "zeta2", "u1", "u2", "v1", "v2", "ubar1", "vbar1"], exact=False, rtol=1e-8)
+    assert not compare(o, t, ["t1_0", "t2_0", "t1_1", "t2_1", "rho"], exact=False, rtol=1e-11)
+    t.close()
+
+
 def test_full_size_benchmark3_smoke():
     """BENCHMARK3 (2048x256x30), the bench workload: runs, conserves volume, stays finite, images consistent."""
     t = synth.make_tile(synth.APP_BENCHMARK, 2048, 256, 30)
@@ -283,24 +322,44 @@ def test_full_size_benchmark3_smoke():
     t.close()
 
 
-def _variant(case, nsteps, **env):
+def _variant(case, nsteps, **opts):
     import subprocess
     import sys
-    e = dict(os.environ); e.update(env)
-    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_variant_check.py"), case, str(nsteps)],
-                       env=e, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_variant_check.py"), case, str(nsteps)]
+                       + [f"{k}={v}" for k, v in opts.items()], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "VARIANT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     return [ln.split()[1] for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
 
 
 @pytest.mark.parametrize("case", ["seamount", "benchmark30", "wide"])
-def test_kernel_and_launch_variants_are_bit_exact(case):
-    """The row-marching step2d kernel (k_step2d_m.cu, both CTA widths) and plain stream launches (no CUDA graph) give the
-    same bits as the default path (tile kernel, graph replay) and as the oracle."""
+def test_launch_variants_are_bit_exact(case):
+    """Plain stream launches (roms_b200_set_option cuda_graphs = 0) give the same bits as the default path (CUDA-graph replay)
+    and as the oracle."""
     ref = _variant(case, 6)
-    assert _variant(case, 6, ROMS_B200_STEP2D="march") == ref
-    assert _variant(case, 6, ROMS_B200_STEP2D="march", ROMS_B200_S2M_TX="64", ROMS_B200_S2M_JL="5") == ref
-    assert _variant(case, 6, ROMS_B200_NO_GRAPH="1") == ref
+    assert _variant(case, 6, cuda_graphs=0) == ref
+
+
+def test_halo_timeout_raises_exit_flag_8():
+    """A halo wait that gives up sets the sticky device error word (dev.cuh ll_wait); every synchronising entry point then
+    returns exit_flag 8 (mod_scalars.F:523-532) so that a host polling exit_flag stops instead of stepping on garbage ghosts.
+    roms_b200_peer_error_inject raises the word exactly as the kernels do."""
+    t = synth.make_tile(synth.APP_SEAMOUNT)
+    L = t.L
+    t.main3d(1)
+    assert L.roms_b200_sync(t.h) == 0 and L.roms_b200_peer_error(t.h) == 0
+    assert L.roms_b200_set_option(t.h, b"halo_timeout_s", 2.0) == 0 and L.roms_b200_set_option(t.h, b"nonsense", 1.0) == 2
+    assert L.roms_b200_peer_error_inject(t.h) == 0
+    assert L.roms_b200_peer_error(t.h) == 1
+    assert L.roms_b200_sync(t.h) == 8
+    assert t.indices()["exit_flag"] == 8
+    out = (C.c_double * 12)()
+    z = np.zeros((t.nj, t.ni))
+    assert L.roms_b200_diag(t.h, out) == 8
+    assert L.roms_b200_run_phase(t.h, _lib.PHASES["set_massflux"]) == 8
+    assert L.roms_b200_main3d_step(t.h, 1) == 8
+    assert L.roms_b200_step_forced(t.h, z.ctypes.data_as(_lib.DP), None, None, z.size, out) == 8
+    assert L.roms_b200_get_field(t.h, b"zeta1", z.ctypes.data_as(_lib.DP), z.size) == 8
+    t.close()
 
 
 def test_step_forced_from_registered_host_memory():
@@ -336,7 +395,8 @@ def test_tiling_invariance_across_gpus(mode):
     """The reference's own acceptance criterion (ROMS/Bin/verify.sh:985-1045): results do not depend on the tiling.  With more
     than one GPU on the box, step a BENCHMARK-shaped grid as an NtileI x 1 ring (one process per GPU, NVLink halo
     exchange) and demand BITWISE agreement with the single-tile run, for the three step2d exchange modes
-    (ROMS_B200_FUSED_XCHG = 2: fused into the kernel with split launches, 1: fused single launch, 0: stand-alone kernels)."""
+    (roms_b200_set_option step2d_exchange = 2: fused into the kernel with split launches, 1: fused single launch, 0: stand-alone
+    kernels).  mgpu_check.py also compares the diag scalars (maxima identical, sums to 1e-13)."""
     n = _ngpus()
     if n < 2:
         pytest.skip("needs at least two GPUs on the box (tests/mgpu_check.py under torchrun)")
@@ -344,10 +404,9 @@ def test_tiling_invariance_across_gpus(mode):
     import sys
     world = 4 if n >= 4 else 2
     here = os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, ROMS_B200_FUSED_XCHG=mode)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(here, "mgpu_check.py"), "512", "64", "30", "6"]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+           "--master-port", "29533", os.path.join(here, "mgpu_check.py"), "512", "64", "30", "6", f"step2d_exchange={mode}"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "BITWISE-IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 

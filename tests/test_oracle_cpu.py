@@ -431,10 +431,12 @@ def test_bench_accounting_and_reference_arm():
     balg, s2d = bench.b_alg_bytes(30, 29)
     assert s2d == 29 * 44 + 16 + 29 * 41 and abs(balg - 1525.6) < 1e-9
     assert abs(bench.b_alg_bytes(30, 29, curvgrid=False, nonlin_eos=False)[0] - 8.0 * (105 + 2365 / 30.0)) < 1e-9     # 1471 B
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--grid", "benchmark1", "--steps", "1", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--grid", "benchmark1", "--steps", "2", "--warmup", "3", "--spinup", "4"],
+                       capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-1000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "grid-point-steps/s" and line["value"] > 0 and line["higher_is_better"] is True
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["steps"] == 2 and line["warmup"] == 3 and line["config"]["spinup_steps"] == 4        # the driver's --steps / --warmup are honoured
+    assert line["config"]["workload"] == bench.workload("benchmark1", 512, 64, 30)                   # the string the GPU arm prints
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
