@@ -123,6 +123,8 @@ int roms_b200_sync(roms_b200_handle h);
  *   "step2d_exchange"  how the xi-halo of the barotropic sub-steps travels on the NVLink peer path (before attach only):
  *                      2 (default) inside the step2d kernels with edge-first split launches, 1 inside the kernels with one
  *                      launch per sub-step, 0 stand-alone exchange kernels
+ *   "step2d_loop_kernel" 1 (default) run LOOP_2D (main3d.F:592-700) as one persistent kernel whenever all CTAs of the tile
+ *                      can be resident at once (small tiles: BENCHMARK3 on 8 GPUs, BENCHMARK1 on one), 0 one launch per call
  *   "overlap"          1 (default) edge-first two-stream overlap of halo exchanges with interior compute (before attach only)
  *   "halo_timeout_s"   seconds a kernel waits for a neighbour's halo before it gives up and raises exit_flag 8
  *                      (default 30; <= 0 waits for ever)

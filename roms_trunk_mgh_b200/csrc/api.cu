@@ -219,6 +219,82 @@ int launch_with_halo(roms_b200_state* h, int phase, F fn, bool in_kernel_exchang
 
 bool fused_tmix(const roms_b200_state* h) { return h->in_step && !h->cfg.mix_geo_ts; }
 
+// The 2-D time-index machine of LOOP_2D (main3d.F:592-700) for one call sequence that starts from (indx1, predictor = 0):
+// fn(call number) is invoked once per step2d call with h->iif/kstp/krhs/knew/predictor set for it.
+template <class F>
+int loop2d_machine(roms_b200_state* h, F fn) {
+  for (int my_iif = 1; my_iif <= h->nfast + 1; ++my_iif) {
+    const int next_indx1 = 3 - h->indx1;
+    if (!h->predictor && my_iif <= h->nfast + 1) {
+      h->predictor = 1; h->iif = my_iif;
+      h->kstp = (h->iif == 1) ? h->indx1 : 3 - h->indx1;
+      h->knew = 3; h->krhs = h->indx1;
+    }
+    if (my_iif <= h->nfast + 1) { if (fn()) return FatalError; }
+    if (h->predictor) {
+      h->predictor = 0; h->knew = next_indx1; h->kstp = 3 - h->knew; h->krhs = 3;
+      if (h->iif < h->nfast + 1) h->indx1 = next_indx1;
+    }
+    if (h->iif < h->nfast + 1) { if (fn()) return FatalError; }
+  }
+  return NoError;
+}
+
+// Call tables of the persistent loop kernel for a loop that starts with indx1 = 1 and 2 (k_step2d_loop.cu).  Built outside
+// any graph capture (roms_b200_set_weights); with_ring: the fused halo exchange pushes in calls 1..2*nfast and pulls in calls
+// 2..2*nfast+1.
+int build_loop_tables(roms_b200_state* h) {
+  const int ncall = 2 * h->nfast + 1;
+  const int s_indx1 = h->indx1, s_iif = h->iif, s_kstp = h->kstp, s_krhs = h->krhs, s_knew = h->knew, s_pred = h->predictor;
+  for (int start = 1; start <= 2; ++start) {
+    std::vector<LoopStep> tab;
+    h->indx1 = start; h->predictor = 0;
+    loop2d_machine(h, [&]() {
+      fill_par(h);
+      const Par& p = h->par;
+      LoopStep st;
+      std::memset(&st, 0, sizeof(st));
+      st.iif = p.iif; st.kstp = p.kstp; st.krhs = p.krhs; st.knew = p.knew; st.ptsk = p.ptsk; st.predictor = p.predictor;
+      st.w1_m1 = p.w1_m1; st.w2_0 = p.w2_0; st.w2_p1 = p.w2_p1;
+      const int c = (int)tab.size() + 1;
+      st.send = c <= ncall - 1; st.recv = c >= 2;
+      if (c >= 2) { const LoopStep& pr = tab.back(); st.nrecv = pr.predictor ? 4 : 3; st.rk = pr.knew; st.rr = pr.krhs; }
+      tab.push_back(st);
+      return 0;
+    });
+    if ((int)tab.size() != ncall) return FatalError;
+    if (h->d_loop_tab[start]) { cudaFree(h->d_loop_tab[start]); h->d_loop_tab[start] = nullptr; }
+    CK(cudaMalloc(&h->d_loop_tab[start], ncall * sizeof(LoopStep)));
+    CK(cudaMemcpy(h->d_loop_tab[start], tab.data(), ncall * sizeof(LoopStep), cudaMemcpyHostToDevice));
+  }
+  h->indx1 = s_indx1; h->iif = s_iif; h->kstp = s_kstp; h->krhs = s_krhs; h->knew = s_knew; h->predictor = s_pred;
+  return NoError;
+}
+
+// LOOP_2D as one persistent kernel when every CTA of the tile can be resident at once.  Returns -1 when not applicable.
+int try_step2d_loop_kernel(roms_b200_state* h) {
+  if (!h->loop_kernel || h->predictor != 0 || h->indx1 < 1 || h->indx1 > 2 || !h->d_loop_tab[h->indx1] || !h->d_loop_flags) return -1;
+  fill_par(h);
+  // every tile of a ring must take the same decision (the tail of the exchange protocol differs): decide on the widest tile
+  Par widest = h->par;
+  widest.Iend = widest.Istr + (h->cfg.Lm + h->cfg.NtileI - 1) / h->cfg.NtileI - 1;
+  const int nctas = step2d_loop_ctas(widest);
+  if (nctas <= 0 || nctas > 4096) return -1;
+  Xchg x;
+  std::memset(&x, 0, sizeof(x));
+  if (h->halo && !fused_xchg_fill(h, x)) return -1;          // a ring without the NVLink peer path: per-call launches + NCCL
+  join_halo(h);
+  if (h->edge_pending) { cudaStreamWaitEvent(h->stream, h->ev_edge, 0); h->edge_pending = false; }
+  LoopCtl ctl;
+  ctl.steps = h->d_loop_tab[h->indx1]; ctl.ncall = 2 * h->nfast + 1; ctl.nsend = h->halo ? 2 * h->nfast : 0;
+  ctl.flags = h->d_loop_flags; ctl.base = h->d_loop_base; ctl.err = h->d_err; ctl.timeout_ns = (long long)(h->halo_timeout_s * 1e9);
+  if (!launch_step2d_loop(h->par, h->fl, h->stream, h->halo ? &x : nullptr, ctl)) { cudaGetLastError(); return -1; }
+  h->launches += 1;
+  loop2d_machine(h, []() { return 0; });                     // leave the host's copy of the index machine where the loop ends
+  if (h->halo) { if (halo_exchange(h, {"Zt_avg1", "DU_avg1", "DV_avg1"}, h->stream)) return FatalError; }   // step2d_LF_AM3.h:714
+  return NoError;
+}
+
 int run_phase_async(roms_b200_state* h, int phase) {
   fill_par(h);
   const Par& p = h->par; const Flds& f = h->fl; cudaStream_t s = h->stream;
@@ -258,6 +334,7 @@ int run_phase_async(roms_b200_state* h, int phase) {
     case ROMS_B200_DIAG: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_diag(q, f, h->d_diag_partial, h->d_diag_out, h->knew, st); }); h->launches += 3; break;
     case ROMS_B200_STEP2D_LOOP: {
       // main3d.F:592-700
+      { const int lk = try_step2d_loop_kernel(h); if (lk >= 0) { rc = lk; break; } }
       // Sub-step calls are numbered c = 1 .. 2*nfast+1.  On the NVLink peer path the xi-halo of calls 1 .. 2*nfast-1 travels
       // inside the kernels themselves (push at the end of call c, pull at the start of call c+1: dev.cuh Xchg); the last
       // corrector and the averaging-only call keep the stand-alone exchange so that the 3-D kernels find complete ghosts.
@@ -290,20 +367,7 @@ int run_phase_async(roms_b200_state* h, int phase) {
         }
         return launch_with_halo(h, ROMS_B200_STEP2D, [&](const Par& q, cudaStream_t st) { launch_step2d(q, f, st, x.recv ? &x : nullptr); });
       };
-      for (int my_iif = 1; my_iif <= h->nfast + 1; ++my_iif) {
-        const int next_indx1 = 3 - h->indx1;
-        if (!h->predictor && my_iif <= h->nfast + 1) {
-          h->predictor = 1; h->iif = my_iif;
-          h->kstp = (h->iif == 1) ? h->indx1 : 3 - h->indx1;
-          h->knew = 3; h->krhs = h->indx1;
-        }
-        if (my_iif <= h->nfast + 1) { if (sub_step()) return FatalError; }
-        if (h->predictor) {
-          h->predictor = 0; h->knew = next_indx1; h->kstp = 3 - h->knew; h->krhs = 3;
-          if (h->iif < h->nfast + 1) h->indx1 = next_indx1;
-        }
-        if (h->iif < h->nfast + 1) { if (sub_step()) return FatalError; }
-      }
+      if (loop2d_machine(h, sub_step)) return FatalError;
       break;
     }
     default: return ConfigError;
@@ -587,6 +651,12 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   CKD(cudaMalloc(&h->d_err, 64));
   h->allocs.push_back(h->d_err);
   CKD(cudaMemsetAsync(h->d_err, 0, 64, h->stream));
+  CKD(cudaMalloc(&h->d_loop_flags, 4096 * sizeof(unsigned long long)));
+  h->allocs.push_back(h->d_loop_flags);
+  CKD(cudaMemsetAsync(h->d_loop_flags, 0, 4096 * sizeof(unsigned long long), h->stream));
+  CKD(cudaMalloc(&h->d_loop_base, 64));
+  h->allocs.push_back(h->d_loop_base);
+  CKD(cudaMemsetAsync(h->d_loop_base, 0, 64, h->stream));
   CKD(cudaMallocHost(&h->h_err, 64));
   std::memset(h->h_err, 0, 64);
   CKD(cudaStreamSynchronize(h->stream));
@@ -603,6 +673,7 @@ int roms_b200_destroy(roms_b200_handle h) {
   halo_destroy(h);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_forcing); cudaEventDestroy(h->ev_step_in); }
   for (void* p : h->allocs) cudaFree(p);
+  for (LoopStep* t : h->d_loop_tab) if (t) cudaFree(t);
   if (h->h_diag_out) cudaFreeHost(h->h_diag_out);
   if (h->h_err) cudaFreeHost(h->h_err);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -667,7 +738,9 @@ int roms_b200_set_weights(roms_b200_handle h, int nfast, const double* w1, const
   if (!h || !w1 || !w2 || nfast < 1 || n < nfast + 2) return InputError;
   h->nfast = nfast; h->w1.assign(w1, w1 + n); h->w2.assign(w2, w2 + n);
   drop_graphs(h);
-  return NoError;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  return build_loop_tables(h);
 }
 
 int roms_b200_set_indices(roms_b200_handle h, const int* v, const double* tm) {
@@ -719,6 +792,7 @@ int roms_b200_set_option(roms_b200_handle h, const char* key, double value) {
   else if (k == "step2d_exchange") { const int m = (int)value; if (m < 0 || m > 2 || h->halo) return ConfigError; h->fused_mode = m; }
   else if (k == "overlap") { if (h->halo) return ConfigError; h->opt_overlap = value != 0.0; }
   else if (k == "halo_timeout_s") h->halo_timeout_s = value;
+  else if (k == "step2d_loop_kernel") h->loop_kernel = value != 0.0;
   else return InputError;
   drop_graphs(h);
   return NoError;

@@ -222,6 +222,21 @@ __device__ __forceinline__ bool ll_wait(const double* line, unsigned tag, double
   }
 }
 
+// ---- the whole barotropic loop as one persistent kernel (k_step2d_loop.cu) -----------------------------------------
+// One entry per step2d call of LOOP_2D (main3d.F:592-700): the 2-D time indices of the call, its filter weights, and what the
+// fused halo exchange does in it (rk / rr: time levels of zeta/ubar/vbar and rzeta whose ghost columns the pull fills).
+struct LoopStep {
+  int iif, kstp, krhs, knew, ptsk, predictor;
+  int send, recv, nrecv, rk, rr, pad_;
+  double w1_m1, w2_0, w2_p1;
+};
+struct LoopCtl {
+  const LoopStep* steps; int ncall, nsend;
+  unsigned long long* flags;       // one completion counter per CTA
+  unsigned long long* base;        // [0] flag value of "call 0" of this launch (advanced by the kernel), [1] CTAs finished
+  unsigned long long* err; long long timeout_ns;
+};
+
 // Function attributes (opt-in dynamic shared memory) are per device: launch wrappers remember what they set per device, so
 // a process that drives several tiles on several GPUs (one handle each) gets them on every one.
 constexpr int MAXDEV = 64;

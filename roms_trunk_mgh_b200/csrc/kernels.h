@@ -20,6 +20,9 @@ void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s);
 void launch_uv3dmix2(const Par& p, const Flds& f, cudaStream_t s);
 // x != nullptr: this sub-step also pulls / pushes its xi-halo through NVLink peer memory (dev.cuh Xchg)
 void launch_step2d(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x = nullptr);
+// The whole LOOP_2D in one cooperative launch (k_step2d_loop.cu); false / 0: the tile is too large for it
+bool launch_step2d_loop(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x, const LoopCtl& ctl);
+int step2d_loop_ctas(const Par& p);
 void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s);
 void launch_step3d_t(const Par& p, const Flds& f, cudaStream_t s);
 // diag: partial[] must hold 16 doubles per block row; out16 on device

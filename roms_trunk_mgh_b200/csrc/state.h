@@ -68,6 +68,11 @@ struct roms_b200_state {
   int overlap = 0;        // edge-first two-stream schedule active (set at attach from opt_overlap)
   int opt_overlap = 1;    // roms_b200_set_option("overlap")
   bool edge_pending = false, halo_pending = false;   // main stream has not yet waited for the latest ev_edge / ev_halo
+  // persistent barotropic-loop kernel (k_step2d_loop.cu): per-CTA completion flags, flag base, and the call tables for a loop
+  // that starts with indx1 = 1 / 2 (built by roms_b200_set_weights; nullptr: per-call launches)
+  unsigned long long* d_loop_flags = nullptr; unsigned long long* d_loop_base = nullptr;
+  rb::LoopStep* d_loop_tab[3] = {nullptr, nullptr, nullptr};
+  int loop_kernel = 1;    // roms_b200_set_option("step2d_loop_kernel")
   // CUDA graphs of whole time steps, keyed by the stepping state at the start of the step (api.cu one_step)
   int fused_mode = 2;     // step2d halo exchange inside the kernels: 0 off, 1 one launch per sub-step, 2 edge / interior split launches
   bool in_step = false;   // inside step_phases (cross-routine fusions are only legal there: run_phase keeps routine granularity)

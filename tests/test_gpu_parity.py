@@ -337,6 +337,9 @@ def test_launch_variants_are_bit_exact(case):
     and as the oracle."""
     ref = _variant(case, 6)
     assert _variant(case, 6, cuda_graphs=0) == ref
+    # LOOP_2D as one persistent kernel (the default on these small grids) against one k_step2d launch per call
+    assert _variant(case, 6, step2d_loop_kernel=0) == ref
+    assert _variant(case, 6, step2d_loop_kernel=0, cuda_graphs=0) == ref
 
 
 def test_halo_timeout_raises_exit_flag_8():
@@ -390,13 +393,14 @@ def _ngpus():
         return 0
 
 
-@pytest.mark.parametrize("mode", ["2", "1", "0"])
+@pytest.mark.parametrize("mode", ["2", "1", "0", "2 step2d_loop_kernel=0", "1 step2d_loop_kernel=0"])
 def test_tiling_invariance_across_gpus(mode):
     """The reference's own acceptance criterion (ROMS/Bin/verify.sh:985-1045): results do not depend on the tiling.  With more
     than one GPU on the box, step a BENCHMARK-shaped grid as an NtileI x 1 ring (one process per GPU, NVLink halo
     exchange) and demand BITWISE agreement with the single-tile run, for the three step2d exchange modes
     (roms_b200_set_option step2d_exchange = 2: fused into the kernel with split launches, 1: fused single launch, 0: stand-alone
-    kernels).  mgpu_check.py also compares the diag scalars (maxima identical, sums to 1e-13)."""
+    kernels); with the exchange fused, LOOP_2D runs as one persistent kernel per tile unless step2d_loop_kernel=0.
+    mgpu_check.py also compares the diag scalars (maxima identical, sums to 1e-13)."""
     n = _ngpus()
     if n < 2:
         pytest.skip("needs at least two GPUs on the box (tests/mgpu_check.py under torchrun)")
@@ -405,7 +409,7 @@ def test_tiling_invariance_across_gpus(mode):
     world = 4 if n >= 4 else 2
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(here, "mgpu_check.py"), "512", "64", "30", "6", f"step2d_exchange={mode}"]
+           "--master-port", "29533", os.path.join(here, "mgpu_check.py"), "512", "64", "30", "6"] + ("step2d_exchange=" + mode).split()
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "BITWISE-IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
