@@ -208,6 +208,9 @@ def state_digest(t, dist, rank, world, Lm, Mm):
 def make_ring_tile(synth, grid, rank, world, local, dist, **overrides):
     Lm, Mm, N = grid
     t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, NtileI=world, tile=rank, device=local, **overrides)
+    for kv in os.environ.get("ROMS_B200_BENCH_OPTS", "").split():          # tuning aid (tools/): roms_b200_set_option switches
+        k, v = kv.split("=")
+        t.set_option(k, float(v))
     xchg = "none (single tile, periodic images written by the producing kernel)"
     if world > 1:
         from roms_trunk_mgh_b200 import multigpu

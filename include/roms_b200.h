@@ -125,6 +125,9 @@ int roms_b200_sync(roms_b200_handle h);
  *                      launch per sub-step, 0 stand-alone exchange kernels
  *   "step2d_loop_kernel" 1 (default) run LOOP_2D (main3d.F:592-700) as one persistent kernel whenever all CTAs of the tile
  *                      can be resident at once (small tiles: BENCHMARK3 on 8 GPUs, BENCHMARK1 on one), 0 one launch per call
+ *   "fuse_phases"      1 (default) roms_b200_main3d_step / step_forced fuse routines that share operands (t3dmix2_s into
+ *                      pre_step3d's tracer pass), 0 one kernel group per
+ *                      routine as roms_b200_run_phase always does; the strict build gives the same bits either way
  *   "overlap"          1 (default) edge-first two-stream overlap of halo exchanges with interior compute (before attach only)
  *   "halo_timeout_s"   seconds a kernel waits for a neighbour's halo before it gives up and raises exit_flag 8
  *                      (default 30; <= 0 waits for ever)

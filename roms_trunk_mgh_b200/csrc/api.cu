@@ -217,7 +217,7 @@ int launch_with_halo(roms_b200_state* h, int phase, F fn, bool in_kernel_exchang
   return rc;
 }
 
-bool fused_tmix(const roms_b200_state* h) { return h->in_step && !h->cfg.mix_geo_ts; }
+bool fused_tmix(const roms_b200_state* h) { return h->in_step && h->fuse_phases && !h->cfg.mix_geo_ts; }
 
 // The 2-D time-index machine of LOOP_2D (main3d.F:592-700) for one call sequence that starts from (indx1, predictor = 0):
 // fn(call number) is invoked once per step2d call with h->iif/kstp/krhs/knew/predictor set for it.
@@ -302,7 +302,8 @@ int run_phase_async(roms_b200_state* h, int phase) {
   int rc = NoError;
   switch (phase) {
     case ROMS_B200_SET_DATA: break;
-    case ROMS_B200_SET_MASSFLUX: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_massflux(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_SET_MASSFLUX:
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_massflux(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_RHO_EOS: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_rho_eos(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_SET_VBC: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_vbc(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_ANA_VMIX:
@@ -310,7 +311,8 @@ int run_phase_async(roms_b200_state* h, int phase) {
       break;
     case ROMS_B200_OMEGA: case ROMS_B200_OMEGA2:
       rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_omega(q, f, st); }); h->launches += 1; break;
-    case ROMS_B200_WVELOCITY: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_wvelocity(q, f, h->nstp, st); }); h->launches += 1; break;
+    case ROMS_B200_WVELOCITY:
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_wvelocity(q, f, h->nstp, st); }); h->launches += 1; break;
     case ROMS_B200_SET_ZETA: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_zeta(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_PRE_STEP3D:
       h->par.fuse_tmix = fused_tmix(h) ? 1 : 0;
@@ -793,6 +795,7 @@ int roms_b200_set_option(roms_b200_handle h, const char* key, double value) {
   else if (k == "overlap") { if (h->halo) return ConfigError; h->opt_overlap = value != 0.0; }
   else if (k == "halo_timeout_s") h->halo_timeout_s = value;
   else if (k == "step2d_loop_kernel") h->loop_kernel = value != 0.0;
+  else if (k == "fuse_phases") h->fuse_phases = value != 0.0;
   else return InputError;
   drop_graphs(h);
   return NoError;

@@ -25,17 +25,27 @@
 namespace rb {
 
 namespace loopk {
-constexpr int TX = 32, TY = 16;          // output tile of one CTA
-constexpr int NTH = 640;                 // >= (TX+1)*(TY+1) = 561 and >= TX*TY + 64
+#ifndef LK_TY
+#define LK_TY 8
+#endif
+#ifndef LK_NTH
+#define LK_NTH (LK_TY == 8 ? 320 : 640)
+#endif
+#ifndef LK_MINB
+#define LK_MINB (LK_TY == 8 ? 2 : 1)
+#endif
+constexpr int TX = 32, TY = LK_TY;       // output tile of one CTA
+constexpr int NTH = LK_NTH;              // >= (TX+1)*(TY+1) and >= TX*TY + 64
 constexpr int HL = 3, HH = 2;
 constexpr int SW = TX + HL + HH, SH = TY + HL + HH;      // staged inputs, origin (i0-3, j0-3): 37 x 21
 constexpr int ZW = TX + 1, ZH = TY + 1;                  // rho region, origin (i0-1, j0-1), and psi region, origin (i0, j0): 33 x 17
 constexpr int MW = TX + 4, MH = TY + 4;                  // pm / pn with one more ring, origin (i0-2, j0-2): 36 x 20
 constexpr int NS = SW * SH, NZ = ZW * ZH, NM = MW * MH, NO = TX * TY;
-// work: sD sU sV sDU sDV (NS) + 17 flux regions (NZ); static: h on_u om_v (NS), pm pn (NM), 10 rho-point + 5 psi-point (NZ), rufrc rvfrc (NO)
-constexpr int SMEM_DOUBLES = 5 * NS + 17 * NZ + 3 * NS + 2 * NM + 15 * NZ + 2 * NO;
+// work: sD sU sV sDU sDV (NS) + 17 flux regions (NZ); static: h on_u om_v (NS), pm pn (NM), 10 rho-point + 5 psi-point (NZ).
+// 32 x 8 tiles: 113.7 KB, so that two CTAs share an SM (one computes while the other waits for its neighbours or for L2).
+constexpr int SMEM_DOUBLES = 5 * NS + 17 * NZ + 3 * NS + 2 * NM + 15 * NZ;
 static_assert(TX == 32 && TX * ZH + ZH <= NTH && NS <= 2 * NTH && TX * TY + 64 <= NTH && NM <= 2 * NTH, "tile / thread-count mismatch");
-static_assert((size_t)SMEM_DOUBLES * 8 + 64 <= 232448, "shared memory budget of one SM");
+static_assert(((size_t)SMEM_DOUBLES * 8 + 1024 + 64) * LK_MINB <= 233472, "shared memory budget of one SM");
 }  // namespace loopk
 
 using namespace loopk;
@@ -52,7 +62,7 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 __device__ __forceinline__ double ldv(const double* a) { return __ldcg(a); }
 
 template <bool XCH>
-__global__ void __launch_bounds__(NTH, 1) k_step2d_loop(Par p, Flds f, Xchg x, LoopCtl ctl) {
+__global__ void __launch_bounds__(NTH, LK_MINB) k_step2d_loop(Par p, Flds f, Xchg x, LoopCtl ctl) {
   extern __shared__ double smem[];
   double* sD = smem; double* sU = sD + NS; double* sV = sU + NS; double* sDU = sV + NS; double* sDV = sDU + NS;
   double* sDnew = sDV + NS; double* sZw = sDnew + NZ; double* sG = sZw + NZ; double* sG2 = sG + NZ; double* sGSA = sG2 + NZ;
@@ -65,7 +75,6 @@ __global__ void __launch_bounds__(NTH, 1) k_step2d_loop(Par p, Flds f, Xchg x, L
   double* cRS = cPN + NM; double* cRA = cRS + NZ; double* cFOMN = cRA + NZ; double* cVISR = cFOMN + NZ; double* cPMONR = cVISR + NZ;
   double* cPNOMR = cPMONR + NZ; double* cONR = cPNOMR + NZ; double* cOMR = cONR + NZ; double* cDNDX = cOMR + NZ; double* cDMDE = cDNDX + NZ;
   double* cVISP = cDMDE + NZ; double* cPMONP = cVISP + NZ; double* cPNOMP = cPMONP + NZ; double* cOMP = cPNOMP + NZ; double* cONP = cOMP + NZ;
-  double* cRUF = cONP + NZ; double* cRVF = cRUF + NO;
   __shared__ unsigned long long s_base, s_epoch;
 
   const int tid = threadIdx.x;
@@ -119,12 +128,6 @@ __global__ void __launch_bounds__(NTH, 1) k_step2d_loop(Par p, Flds f, Xchg x, L
       cOMP[tid] = ok ? __ldg(f.om_p + q) : 0.0; cONP[tid] = ok ? __ldg(f.on_p + q) : 0.0;
     }
   }
-  if (tid < NO) {
-    const int i = i0 + (tid % TX), j = j0 + (tid / TX);
-    const bool ok = i <= p.Iend && j <= Mm;
-    const int q = j * P + i;
-    cRUF[tid] = ok ? __ldg(f.rufrc + q) : 0.0; cRVF[tid] = ok ? __ldg(f.rvfrc + q) : 0.0;
-  }
 
   // ---- fixed thread maps (the same for every call)
   // stage 2: warps 0..ZH-1 take one region row each, the first ZH lanes of warp ZH take the 33rd column
@@ -162,6 +165,9 @@ __global__ void __launch_bounds__(NTH, 1) k_step2d_loop(Par p, Flds f, Xchg x, L
   const int p0 = ty * ZW + tx, pE = p0 + 1, pN = p0 + ZW;
   // fast-time averages of this thread's point: registers for the whole loop (the first call initialises them, :614-682)
   double av_zt = 0.0, av_du1 = 0.0, av_du2 = 0.0, av_dv1 = 0.0, av_dv2 = 0.0;
+  // 3-D forcing of this thread's u / v point: read once, replaced by the first call (:1884-2065)
+  double rufrc_o = 0.0, rvfrc_o = 0.0;
+  if (live && j3 >= 1 && j3 <= Mm) { rufrc_o = __ldg(f.rufrc + o); rvfrc_o = __ldg(f.rvfrc + o); }
 
   // neighbours whose completion flags order the calls (periodic wrap only when this tile owns the whole xi range)
   int nb_id = -1;
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(NTH, 1) k_step2d_loop(Par p, Flds f, Xchg x, L
           for (;;) {
             bool done = false;
 #pragma unroll 1
-            for (int q = 0; q < 32 && !done; ++q) { done = ld_acquire_u64(fl) >= want; if (!done) __nanosleep(20); }
+            for (int q = 0; q < 64 && !done; ++q) done = ld_acquire_u64(fl) >= want;
             if (done) break;
             if (*(volatile unsigned long long*)ctl.err != 0ULL) break;                    // another wait already gave up
             if (ctl.timeout_ns > 0 && gtime_ns() - t0 > ctl.timeout_ns) { *ctl.err = 2ULL; break; }
@@ -471,7 +477,6 @@ __global__ void __launch_bounds__(NTH, 1) k_step2d_loop(Par p, Flds f, Xchg x, L
         const double rA0 = cRA[z0], rAW = cRA[zW], rAS = cRA[zS];
         const double pm0 = cPM[m3], pmW = cPM[m3 - 1], pmS = cPM[m3S], pn0 = cPN[m3], pnW = cPN[m3 - 1], pnS = cPN[m3S];
         const double onu = cONU[a3], omv = cOMV[a3];
-        const int oo = ty * TX + tx;
         // ---- u-point (i,j)
         {
           const double cff1 = 0.5 * p.g, cff2 = 1.0 / 3.0;
@@ -494,14 +499,13 @@ __global__ void __launch_bounds__(NTH, 1) k_step2d_loop(Par p, Flds f, Xchg x, L
             rhs_u = rhs_u + fc;
           }
           // coupling with the 3-D equations (:1884-2065)
-          const double rufrc_o = cRUF[oo];
           if (FIRST && PRED) {
             const double rf = rufrc_o - rhs_u;
             if (p.istart == 0) rhs_u = rhs_u + rf;
             else if (p.istart == 1) rhs_u = rhs_u + 1.5 * rf - 0.5 * ru_n;
             else rhs_u = rhs_u + (23.0 / 12.0) * rf - (16.0 / 12.0) * ru_n + (5.0 / 12.0) * ru_so;
             f.rufrc[o] = rf;
-            cRUF[oo] = rf;
+            rufrc_o = rf;
             f.ru[p.nstp][o] = rf;
           } else {
             rhs_u = rhs_u + rufrc_o;
@@ -547,14 +551,13 @@ __global__ void __launch_bounds__(NTH, 1) k_step2d_loop(Par p, Flds f, Xchg x, L
             const double fc = a1 - a2;
             rhs_v = rhs_v + fc;
           }
-          const double rvfrc_o = cRVF[oo];
           if (FIRST && PRED) {
             const double rf = rvfrc_o - rhs_v;
             if (p.istart == 0) rhs_v = rhs_v + rf;
             else if (p.istart == 1) rhs_v = rhs_v + 1.5 * rf - 0.5 * rv_n;
             else rhs_v = rhs_v + (23.0 / 12.0) * rf - (16.0 / 12.0) * rv_n + (5.0 / 12.0) * rv_so;
             f.rvfrc[o] = rf;
-            cRVF[oo] = rf;
+            rvfrc_o = rf;
             f.rv[p.nstp][o] = rf;
           } else {
             rhs_v = rhs_v + rvfrc_o;
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(NTH, 1) k_step2d_loop(Par p, Flds f, Xchg x, L
     }
     // ---- publish: every store of this call is visible before the flag
     __syncthreads();
-    if (tid == 0) { __threadfence(); st_release_u64(ctl.flags + (bx + nbx * by), base + (unsigned long long)c); }
+    if (tid == 0) st_release_u64(ctl.flags + (bx + nbx * by), base + (unsigned long long)c);   // release: cumulative over the barrier
   }
   // ---- the CTA that finishes last advances the flag base and the exchange epoch for the next launch
   if (tid == 0) {

@@ -13,7 +13,7 @@ for name in sys.argv[2:]:
     env = dict(os.environ)
     if name != "base":
         env["ROMS_B200_LIB"] = os.path.join(ROOT, "roms_trunk_mgh_b200", "lib", "var", f"libroms_b200_{name}.so")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "10", "--warmup", "3", "--no-cpu"], env=env, capture_output=True, text=True)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "10", "--warmup", "3", "--no-cpu", "--no-extras"], env=env, capture_output=True, text=True)
     try:
         d = json.loads(r.stdout.strip().splitlines()[-1])
         print(name, f"step {d['ms_per_step']:.3f} ms |", " ".join(f"{k}={d['phase_ms'][k]:.3f}" for k in phases), flush=True)
