@@ -30,6 +30,8 @@ sys.path.insert(0, ROOT)
 GRIDS = {"benchmark1": (512, 64, 30), "benchmark2": (1024, 128, 30), "benchmark3": (2048, 256, 30),
          # tuning aid: on 2 GPUs this gives every rank the 256x256 tile BENCHMARK3 has on 8 GPUs
          "b3tile8x2": (512, 256, 30),
+         # ... the same 256x256 tile as a periodic single-GPU domain (no ring): kernel tuning at the 8-GPU tile size
+         "b3tile8": (256, 256, 30),
          # ... and this one the 512x256 tile of 4 GPUs
          "b3tile4x2": (1024, 256, 30)}
 # weak scaling: BENCHMARK1/2/3 grow x4 in points per step; grid run at N GPUs

@@ -801,6 +801,15 @@ int roms_b200_set_option(roms_b200_handle h, const char* key, double value) {
   return NoError;
 }
 
+#ifdef LK_TRACE
+// tuning aid (variant builds only, not declared in the header): the trace words of k_step2d_loop
+int roms_b200_debug_loop_trace(roms_b200_handle h, unsigned long long* out64) {
+  if (!h || !out64) return InputError;
+  CK(cudaMemcpy(out64, h->d_loop_flags + 2048, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return NoError;
+}
+#endif
+
 int roms_b200_peer_error_inject(roms_b200_handle h) {
   if (!h || !h->d_err) return InputError;
   CK(cudaSetDevice(h->cfg.device));

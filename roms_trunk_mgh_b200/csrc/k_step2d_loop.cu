@@ -61,6 +61,13 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 // time-varying field written by other CTAs during this kernel: L2 is the point of coherence
 __device__ __forceinline__ double ldv(const double* a) { return __ldcg(a); }
 
+#ifdef LK_TRACE
+// tuning aid (tools/variant.py -DLK_TRACE): wall-clock stamps of one CTA at the stage boundaries of calls 20..27
+#define TRACE(slot) do { if (tid == 0 && bx == (int)gridDim.x / 2 && by == (int)gridDim.y / 2 && c >= 20 && c < 28) ctl.flags[2048 + (c - 20) * 8 + (slot)] = (unsigned long long)gtime_ns(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 template <bool XCH>
 __global__ void __launch_bounds__(NTH, LK_MINB) k_step2d_loop(Par p, Flds f, Xchg x, LoopCtl ctl) {
   extern __shared__ double smem[];
@@ -193,6 +200,7 @@ __global__ void __launch_bounds__(NTH, LK_MINB) k_step2d_loop(Par p, Flds f, Xch
     const double* zr = f.zeta[st.krhs];
     const double* zs = f.zeta[st.kstp];
 
+    TRACE(0);
     // ---- order: every neighbour has finished call c-1
     if (c > 1) {
       if (nb_id >= 0) {
@@ -251,6 +259,7 @@ __global__ void __launch_bounds__(NTH, LK_MINB) k_step2d_loop(Par p, Flds f, Xch
     };
     const bool xsend = XCH && st.send;
 
+    TRACE(1);
     // ---- time-varying operands of stages 0 and 2a, requested together
     const bool okA = active && okA0;
     double zs_q = 0.0, zr_q = 0.0, rz_s = 0.0, rz_p = 0.0;
@@ -279,6 +288,7 @@ __global__ void __launch_bounds__(NTH, LK_MINB) k_step2d_loop(Par p, Flds f, Xch
         if (s < NS) { sD[s] = ok[r] ? (zv[r] + cH[s]) : 0.0; sU[s] = ok[r] ? uv[r] : 0.0; sV[s] = ok[r] ? vv[r] : 0.0; }
       }
       __syncthreads();
+      TRACE(2);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int s = tid + r * NTH;
@@ -302,6 +312,7 @@ __global__ void __launch_bounds__(NTH, LK_MINB) k_step2d_loop(Par p, Flds f, Xch
     }
     __syncthreads();
 
+    TRACE(3);
 #define D_(di, dj) sD[c0 + (dj) * SW + (di)]
 #define U_(di, dj) sU[c0 + (dj) * SW + (di)]
 #define V_(di, dj) sV[c0 + (dj) * SW + (di)]
@@ -439,6 +450,7 @@ __global__ void __launch_bounds__(NTH, LK_MINB) k_step2d_loop(Par p, Flds f, Xch
       }
     }
     __syncthreads();
+    TRACE(4);
     if (live) {
       // fast-time averages (:614-682); rows 0..Mm+1 for Zt/DU, rows 1..Mm+1 for DV.  Kept in registers, stored by the last call.
       {
@@ -584,8 +596,11 @@ __global__ void __launch_bounds__(NTH, LK_MINB) k_step2d_loop(Par p, Flds f, Xch
       }
     }
     // ---- publish: every store of this call is visible before the flag
+    TRACE(5);
     __syncthreads();
+    TRACE(6);
     if (tid == 0) st_release_u64(ctl.flags + (bx + nbx * by), base + (unsigned long long)c);   // release: cumulative over the barrier
+    TRACE(7);
   }
   // ---- the CTA that finishes last advances the flag base and the exchange epoch for the next launch
   if (tid == 0) {

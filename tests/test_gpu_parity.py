@@ -340,6 +340,8 @@ def test_launch_variants_are_bit_exact(case):
     # LOOP_2D as one persistent kernel (the default on these small grids) against one k_step2d launch per call
     assert _variant(case, 6, step2d_loop_kernel=0) == ref
     assert _variant(case, 6, step2d_loop_kernel=0, cuda_graphs=0) == ref
+    # one kernel group per routine (as roms_b200_run_phase does) against the fused whole-step schedule
+    assert _variant(case, 6, fuse_phases=0) == ref
 
 
 def test_halo_timeout_raises_exit_flag_8():
