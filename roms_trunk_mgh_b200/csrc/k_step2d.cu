@@ -245,10 +245,12 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
     {
       const int i = i0 - 1 + za, j = j0 - 1 + zb;
       const int c0 = (zb + HL - 1) * SW + (za + HL - 1);               // staged index of (i,j)
-      double Dnew = 0.0, zwrk = 0.0, gz = 0.0, gz2 = 0.0, gsa = 0.0;
-      double a_ufx = 0.0, a_vfe = 0.0, c_ufx = 0.0, c_vfe = 0.0, k_ufx = 0.0, k_vfe = 0.0, v_ufx = 0.0, v_vfe = 0.0;
-      if (okA) {
-        const int q = qA;
+      // Straight-line arithmetic for every thread of the region (invalid points compute on in-bounds dummy operands and are
+      // zeroed at the end): one basic block, so the independent flux chains below overlap in the FP64 pipe instead of
+      // running one after the other behind a branch.
+      double Dnew, zwrk, gz, gz2, gsa;
+      double a_ufx, a_vfe, c_ufx, c_vfe, k_ufx = 0.0, k_vfe = 0.0, v_ufx, v_vfe;
+      {
         // new free surface (:770-851)
         const double dd = (DU_(0, 0) - DU_(1, 0)) + (DV_(0, 0) - DV_(0, 1));
         double zeta_new;
@@ -270,7 +272,9 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
         gz = (1000.0 / p.rho0 + rS) * zwrk;
         gz2 = gz * zwrk;
         gsa = zwrk * (rS - rA);
-        if (za >= 1 && zb >= 1) {                                      // own points of this tile
+        if (okA && za >= 1 && zb >= 1) {                                 // own points of this tile
+          const int q = qA;
+          (void)q;
           st_r_grad(f.zeta[p.knew], j * P, i, j, zeta_new, p);
           if (PRED) st_w(f.rzeta[p.krhs], j * P, i, dd, p);
           if (XCH && x.send && (i >= x.Iend - (XNW - 1) || i <= x.Istr + (XNE - 1))) {
@@ -311,16 +315,18 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
           v_ufx = onr * onr * cr; v_vfe = omr * omr * cr;
         }
       }
-      sDnew[zi] = Dnew; sZw[zi] = zwrk; sG[zi] = gz; sG2[zi] = gz2; sGSA[zi] = gsa;
-      aUFx[zi] = a_ufx; aVFe[zi] = a_vfe; cUFx[zi] = c_ufx; cVFe[zi] = c_vfe; kUFx[zi] = k_ufx; kVFe[zi] = k_vfe; vUFx[zi] = v_ufx; vVFe[zi] = v_vfe;
+      sDnew[zi] = okA ? Dnew : 0.0; sZw[zi] = okA ? zwrk : 0.0; sG[zi] = okA ? gz : 0.0; sG2[zi] = okA ? gz2 : 0.0; sGSA[zi] = okA ? gsa : 0.0;
+      aUFx[zi] = okA ? a_ufx : 0.0; aVFe[zi] = okA ? a_vfe : 0.0; cUFx[zi] = okA ? c_ufx : 0.0; cVFe[zi] = okA ? c_vfe : 0.0;
+      kUFx[zi] = okA ? k_ufx : 0.0; kVFe[zi] = okA ? k_vfe : 0.0; vUFx[zi] = okA ? v_ufx : 0.0; vVFe[zi] = okA ? v_vfe : 0.0;
     }
     // ---- stage 2b: psi-point fluxes at (i0+za, j0+zb)
     {
       const int i = i0 + za, j = j0 + zb;
       const int c0 = (zb + HL) * SW + (za + HL);
-      double a_ufe = 0.0, a_vfx = 0.0, v_ufe = 0.0, v_vfx = 0.0;
-      if (j >= 1 && j <= Mm + 1 && i <= p.Iend + 1) {
-        const int q = j * P + i;
+      const bool okB = j >= 1 && j <= Mm + 1 && i <= p.Iend + 1;
+      const int q = okB ? j * P + i : (j0 + 1) * P + i0 + 1;             // dummy: a point of this tile that has all four neighbours
+      double a_ufe, a_vfx, v_ufe, v_vfx;
+      {
         const double visc_q = lds_(f.visc2_p + q), pmon_q = lds_(f.pmon_p + q), pnom_q = lds_(f.pnom_p + q), omp = lds_(f.om_p + q), onp = lds_(f.on_p + q);
         const double pn_q = lds_(pn + q), pnS = lds_(pn + q - P), pnW = lds_(pn + q - 1), pnSW = lds_(pn + q - P - 1);
         const double pm_q = lds_(pm + q), pmS = lds_(pm + q - P), pmW = lds_(pm + q - 1), pmSW = lds_(pm + q - P - 1);
@@ -330,8 +336,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
           a_ufe = 0.25 * (U_(0, 0) + U_(0, -1) - c6 * (GYU(0, d0) + GYU(0, dm))) * (DV_(0, 0) + DV_(-1, 0) - c6 * (GXDV(0, 0) + GXDV(-1, 0)));
         }
         // advective VFx at psi(i,j), j = 2..Mm (:1213-1222)
-        if (j >= 2 && j <= Mm)
-          a_vfx = 0.25 * (V_(0, 0) + V_(-1, 0) - c6 * (GXV(0, 0) + GXV(-1, 0))) * (DU_(0, 0) + DU_(0, -1) - c6 * (GYDU(0, 0) + GYDU(0, -1)));
+        a_vfx = 0.25 * (V_(0, 0) + V_(-1, 0) - c6 * (GXV(0, 0) + GXV(-1, 0))) * (DU_(0, 0) + DU_(0, -1) - c6 * (GYDU(0, 0) + GYDU(0, -1)));
         // viscous stress at psi(i,j) (:1394-1430)
         {
           const double Dp = 0.25 * (D_(0, 0) + D_(-1, 0) + D_(0, -1) + D_(-1, -1));
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
           v_ufe = omp * omp * cp; v_vfx = onp * onp * cp;
         }
       }
-      aUFe[zi] = a_ufe; aVFx[zi] = a_vfx; vUFe[zi] = v_ufe; vVFx[zi] = v_vfx;
+      aUFe[zi] = okB ? a_ufe : 0.0; aVFx[zi] = (okB && j >= 2 && j <= Mm) ? a_vfx : 0.0; vUFe[zi] = okB ? v_ufe : 0.0; vVFx[zi] = okB ? v_vfx : 0.0;
     }
   }
   // ---- stage 3: one thread per rho point of the tile (+ one warp each for wall rows 0 and Mm+1).  None of its global
@@ -417,104 +422,93 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
   const int z0 = (ty + 1) * ZW + (tx + 1), zW = z0 - 1, zS = z0 - ZW;   // rho-region indices of (i,j), (i-1,j), (i,j-1)
   const int p0 = ty * ZW + tx, pE = p0 + 1, pN = p0 + ZW;               // psi-region indices of (i,j), (i+1,j), (i,j+1)
 
-  // ---- u-point (i,j)
+  // ---- u-point (i,j) and v-point (i,j): the arithmetic of both first, as one basic block (two independent dependency chains
+  // that overlap in the FP64 pipe), the stores afterwards; the v results of row 1 (the wall) are computed and dropped
+  const double cff1 = 0.5 * p.g, cff2 = 1.0 / 3.0;
+  double rhs_u = cff1 * onu *
+                 ((hW + h0) * (sG[zW] - sG[z0]) +
+                  (hW - h0) * (sGSA[zW] + sGSA[z0] + cff2 * (rAW - rA0) * (sZw[zW] - sZw[z0])) +
+                  (sG2[zW] - sG2[z0]));
+  double rhs_v = cff1 * omv *
+                 ((hS + h0) * (sG[zS] - sG[z0]) +
+                  (hS - h0) * (sGSA[zS] + sGSA[z0] + cff2 * (rAS - rA0) * (sZw[zS] - sZw[z0])) +
+                  (sG2[zS] - sG2[z0]));
   {
-    const double cff1 = 0.5 * p.g, cff2 = 1.0 / 3.0;
-    double rhs_u = cff1 * onu *
-                   ((hW + h0) * (sG[zW] - sG[z0]) +
-                    (hW - h0) * (sGSA[zW] + sGSA[z0] + cff2 * (rAW - rA0) * (sZw[zW] - sZw[z0])) +
-                    (sG2[zW] - sG2[z0]));
-    {
-      const double a1 = aUFx[z0] - aUFx[zW];
-      const double a2 = aUFe[pN] - aUFe[p0];
-      const double fc = a1 + a2;
-      rhs_u = rhs_u - fc;
+    const double a1 = aUFx[z0] - aUFx[zW];
+    const double a2 = aUFe[pN] - aUFe[p0];
+    const double fc = a1 + a2;
+    rhs_u = rhs_u - fc;
+  }
+  {
+    const double a1 = aVFx[pE] - aVFx[p0];
+    const double a2 = aVFe[z0] - aVFe[zS];
+    const double fc = a1 + a2;
+    rhs_v = rhs_v - fc;
+  }
+  rhs_u = rhs_u + 0.5 * (cUFx[z0] + cUFx[zW]);
+  rhs_v = rhs_v - 0.5 * (cVFe[z0] + cVFe[zS]);
+  if (p.curvgrid) {
+    rhs_u = rhs_u + 0.5 * (kUFx[z0] + kUFx[zW]);
+    rhs_v = rhs_v - 0.5 * (kVFe[z0] + kVFe[zS]);
+  }
+  {
+    const double a1 = 0.5 * (pnW + pn0) * (vUFx[z0] - vUFx[zW]);
+    const double a2 = 0.5 * (pmW + pm0) * (vUFe[pN] - vUFe[p0]);
+    const double fc = a1 + a2;
+    rhs_u = rhs_u + fc;
+  }
+  {
+    const double a1 = 0.5 * (pnS + pn0) * (vVFx[pE] - vVFx[p0]);
+    const double a2 = 0.5 * (pmS + pm0) * (vVFe[z0] - vVFe[zS]);
+    const double fc = a1 - a2;
+    rhs_v = rhs_v + fc;
+  }
+  // coupling with the 3-D equations (:1884-2065); level k = 0 planes of ru carry the AB3 history of the 2-D forcing
+  double rf_u = 0.0, rf_v = 0.0;
+  if (FIRST && PRED) {
+    rf_u = rufrc_o - rhs_u;
+    rf_v = rvfrc_o - rhs_v;
+    if (p.istart == 0) { rhs_u = rhs_u + rf_u; rhs_v = rhs_v + rf_v; }
+    else if (p.istart == 1) { rhs_u = rhs_u + 1.5 * rf_u - 0.5 * ru_n; rhs_v = rhs_v + 1.5 * rf_v - 0.5 * rv_n; }
+    else {
+      rhs_u = rhs_u + (23.0 / 12.0) * rf_u - (16.0 / 12.0) * ru_n + (5.0 / 12.0) * ru_so;
+      rhs_v = rhs_v + (23.0 / 12.0) * rf_v - (16.0 / 12.0) * rv_n + (5.0 / 12.0) * rv_so;
     }
-    rhs_u = rhs_u + 0.5 * (cUFx[z0] + cUFx[zW]);
-    if (p.curvgrid) rhs_u = rhs_u + 0.5 * (kUFx[z0] + kUFx[zW]);
-    {
-      const double a1 = 0.5 * (pnW + pn0) * (vUFx[z0] - vUFx[zW]);
-      const double a2 = 0.5 * (pmW + pm0) * (vUFe[pN] - vUFe[p0]);
-      const double fc = a1 + a2;
-      rhs_u = rhs_u + fc;
-    }
-    // coupling with the 3-D equations (:1884-2065); level k = 0 planes of ru carry the AB3 history of the 2-D forcing
-    if (FIRST && PRED) {
-      const double rf = rufrc_o - rhs_u;
-      if (p.istart == 0) rhs_u = rhs_u + rf;
-      else if (p.istart == 1) rhs_u = rhs_u + 1.5 * rf - 0.5 * ru_n;
-      else rhs_u = rhs_u + (23.0 / 12.0) * rf - (16.0 / 12.0) * ru_n + (5.0 / 12.0) * ru_so;
-      f.rufrc[o] = rf;
-      f.ru[p.nstp][o] = rf;
-    } else {
-      rhs_u = rhs_u + rufrc_o;
-    }
-    // time stepping (:2098-2255), rhs history (:2420-2430), BCs (:2451-2460), periodic images (:2509-2524)
-    const double Dstp = (zs0 + h0) + (zsW + hW);
-    const double cff = (pm0 + pmW) * (pn0 + pnW);
-    const double fc = 1.0 / (sDnew[z0] + sDnew[zW]);
-    double x;
+  } else {
+    rhs_u = rhs_u + rufrc_o;
+    rhs_v = rhs_v + rvfrc_o;
+  }
+  // time stepping (:2098-2255)
+  double xu, xv;
+  {
+    const double Dstp_u = (zs0 + h0) + (zsW + hW), Dstp_v = (zs0 + h0) + (zsS + hS);
+    const double cff_u = (pm0 + pmW) * (pn0 + pnW), cff_v = (pm0 + pmS) * (pn0 + pnS);
+    const double fc_u = 1.0 / (sDnew[z0] + sDnew[zW]), fc_v = 1.0 / (sDnew[z0] + sDnew[zS]);
     if (FIRST || PRED) {
       const double c1 = FIRST ? 0.5 * p.dtfast : p.dtfast;
-      x = (us * Dstp + cff * c1 * rhs_u) * fc;
+      xu = (us * Dstp_u + cff_u * c1 * rhs_u) * fc_u;
+      xv = (vs * Dstp_v + cff_v * c1 * rhs_v) * fc_v;
     } else {
       const double c1 = 0.5 * p.dtfast * 5.0 / 12.0, c2 = 0.5 * p.dtfast * 8.0 / 12.0, c3 = 0.5 * p.dtfast * 1.0 / 12.0;
-      x = (us * Dstp + cff * (c1 * rhs_u + c2 * rub_s - c3 * rub_p)) * fc;
-    }
-    st_u_closed(f.ubar[p.knew], j * P, i, j, x, p);
-    if (PRED) f.rubar[p.krhs][o] = rhs_u;
-    if (XCH && xc.send && (i >= xc.Iend - (XNW - 1) || i <= xc.Istr + (XNE - 1))) {
-      push(1, i, j, x);
-      if (j == 1) push(1, i, 0, p.gamma2 * x);
-      if (j == Mm) push(1, i, Mm + 1, p.gamma2 * x);
+      xu = (us * Dstp_u + cff_u * (c1 * rhs_u + c2 * rub_s - c3 * rub_p)) * fc_u;
+      xv = (vs * Dstp_v + cff_v * (c1 * rhs_v + c2 * rvb_s - c3 * rvb_p)) * fc_v;
     }
   }
-  // ---- v-point (i,j)
+  // ---- stores: rhs history (:2420-2430), BCs (:2451-2460), periodic images (:2509-2524)
+  if (FIRST && PRED) { f.rufrc[o] = rf_u; f.ru[p.nstp][o] = rf_u; }
+  st_u_closed(f.ubar[p.knew], j * P, i, j, xu, p);
+  if (PRED) f.rubar[p.krhs][o] = rhs_u;
+  if (XCH && xc.send && (i >= xc.Iend - (XNW - 1) || i <= xc.Istr + (XNE - 1))) {
+    push(1, i, j, xu);
+    if (j == 1) push(1, i, 0, p.gamma2 * xu);
+    if (j == Mm) push(1, i, Mm + 1, p.gamma2 * xu);
+  }
   if (dov) {
-    const double cff1 = 0.5 * p.g, cff2 = 1.0 / 3.0;
-    double rhs_v = cff1 * omv *
-                   ((hS + h0) * (sG[zS] - sG[z0]) +
-                    (hS - h0) * (sGSA[zS] + sGSA[z0] + cff2 * (rAS - rA0) * (sZw[zS] - sZw[z0])) +
-                    (sG2[zS] - sG2[z0]));
-    {
-      const double a1 = aVFx[pE] - aVFx[p0];
-      const double a2 = aVFe[z0] - aVFe[zS];
-      const double fc = a1 + a2;
-      rhs_v = rhs_v - fc;
-    }
-    rhs_v = rhs_v - 0.5 * (cVFe[z0] + cVFe[zS]);
-    if (p.curvgrid) rhs_v = rhs_v - 0.5 * (kVFe[z0] + kVFe[zS]);
-    {
-      const double a1 = 0.5 * (pnS + pn0) * (vVFx[pE] - vVFx[p0]);
-      const double a2 = 0.5 * (pmS + pm0) * (vVFe[z0] - vVFe[zS]);
-      const double fc = a1 - a2;
-      rhs_v = rhs_v + fc;
-    }
-    if (FIRST && PRED) {
-      const double rf = rvfrc_o - rhs_v;
-      if (p.istart == 0) rhs_v = rhs_v + rf;
-      else if (p.istart == 1) rhs_v = rhs_v + 1.5 * rf - 0.5 * rv_n;
-      else rhs_v = rhs_v + (23.0 / 12.0) * rf - (16.0 / 12.0) * rv_n + (5.0 / 12.0) * rv_so;
-      f.rvfrc[o] = rf;
-      f.rv[p.nstp][o] = rf;
-    } else {
-      rhs_v = rhs_v + rvfrc_o;
-    }
-    const double Dstp = (zs0 + h0) + (zsS + hS);
-    const double cff = (pm0 + pmS) * (pn0 + pnS);
-    const double fc = 1.0 / (sDnew[z0] + sDnew[zS]);
-    double x;
-    if (FIRST || PRED) {
-      const double c1 = FIRST ? 0.5 * p.dtfast : p.dtfast;
-      x = (vs * Dstp + cff * c1 * rhs_v) * fc;
-    } else {
-      const double c1 = 0.5 * p.dtfast * 5.0 / 12.0, c2 = 0.5 * p.dtfast * 8.0 / 12.0, c3 = 0.5 * p.dtfast * 1.0 / 12.0;
-      x = (vs * Dstp + cff * (c1 * rhs_v + c2 * rvb_s - c3 * rvb_p)) * fc;
-    }
-    st_v_closed(f.vbar[p.knew], j * P, i, j, x, p);
+    if (FIRST && PRED) { f.rvfrc[o] = rf_v; f.rv[p.nstp][o] = rf_v; }
+    st_v_closed(f.vbar[p.knew], j * P, i, j, xv, p);
     if (PRED) f.rvbar[p.krhs][o] = rhs_v;
     if (XCH && xc.send && (i >= xc.Iend - (XNW - 1) || i <= xc.Istr + (XNE - 1))) {
-      push(2, i, j, x);
+      push(2, i, j, xv);
       if (j == 2) { push(2, i, 1, 0.0); push(2, i, 0, f.vbar[p.knew][i]); }   // row 1 is the wall (v = 0); row 0 is never written
       if (j == Mm) push(2, i, Mm + 1, 0.0);
     }
