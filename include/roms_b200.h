@@ -38,7 +38,9 @@ enum { ROMS_B200_VADV_C4 = 0, ROMS_B200_VADV_A4 = 1, ROMS_B200_VADV_C2 = 2 };
 /* Live cpp switches (ROMS/Include/{upwelling,seamount,benchmark}.h) + roms_*.in keywords for this path. */
 typedef struct roms_b200_config {
   int Lm, Mm, N, NT;            /* mod_param.F: interior points, levels, tracers                                  */
-  int NtileI, NtileJ, tile;     /* domain partition and this handle's tile (get_bounds.F:933-1007)                 */
+  int NtileI, NtileJ, tile;     /* domain partition and this handle's tile (get_bounds.F:933-1007).  A handle owns the whole
+                                   xi-column of tiles that contains `tile` (all Jtile): the eta partition only splits loop
+                                   ranges, results do not depend on it.  The per-routine _tile forms need NtileJ == 1.   */
   int ndtfast;                  /* NDTFAST; nfast and weights are uploaded with roms_b200_set_weights              */
   double dt;                    /* DT (s)                                                                          */
   int nonlin_eos;               /* NONLIN_EOS (rho_eos.F:111) else linear EOS (rho_eos.F:576)                      */

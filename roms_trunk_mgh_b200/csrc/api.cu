@@ -554,10 +554,7 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   if (!cfg || !out) return InputError;
   *out = nullptr;
   if (cfg->N < 4 || cfg->N > MAXN || cfg->NT < 1 || cfg->NT > MAXNT || cfg->Lm < 8 || cfg->Mm < 4) return ConfigError;
-  if (cfg->NtileJ != 1 || cfg->NtileI < 1 || cfg->tile < 0 || cfg->tile >= cfg->NtileI) {
-    std::fprintf(stderr, "roms_b200: only NtileI x 1 partitions are supported (NtileJ must be 1)\n");
-    return ConfigError;
-  }
+  if (cfg->NtileI < 1 || cfg->NtileJ < 1 || cfg->tile < 0 || cfg->tile >= cfg->NtileI * cfg->NtileJ) return ConfigError;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
     std::fprintf(stderr, "roms_b200: no CUDA device; this library has no CPU fallback\n");
@@ -575,7 +572,12 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
     }                                                                                                    \
   } while (0)
   h->cfg = *cfg;
-  make_bounds(cfg->Lm, cfg->Mm, cfg->NtileI, cfg->NtileJ, cfg->tile, cfg->NtileI > 1, h->b);
+  // NtileI x NtileJ partitions (get_bounds.F:985-1004; the shipped roms_benchmark3.in is 2 x 2): a handle owns a whole xi-COLUMN
+  // of tiles, i.e. tiles Itile + Jtile*NtileI for every Jtile.  The partition only distributes loop ranges -- results do not
+  // depend on it (ROMS/Bin/verify.sh:985-1045) -- so the device treats the column as one tile; any tile number of the column
+  // selects it.  (A distributed-memory host that splits eta between ranks is not supported: its arrays hold only a J sub-range.)
+  h->itile = cfg->tile % cfg->NtileI;
+  make_bounds(cfg->Lm, cfg->Mm, cfg->NtileI, 1, h->itile, cfg->NtileI > 1, h->b);
   const Bounds& b = h->b;
   h->ni = b.UBi - b.LBi + 1; h->nj = b.UBj - b.LBj + 1;
   h->LBi_dev = b.Istr - 3;                       // == b.LBi on the western tile; one extra ghost column elsewhere

@@ -265,7 +265,7 @@ int roms_b200_nccl_init_rank(const char* id128, int rank, int nranks, void** com
 // Attach the ring communicator and fill every ghost column of every field (call after the uploads).  Collective.
 int roms_b200_attach_nccl(roms_b200_handle h, void* nccl_comm, int rank, int nranks) {
   if (!h || !nccl_comm) return 2;
-  if (nranks != h->cfg.NtileI || rank != h->cfg.tile) { std::fprintf(stderr, "roms_b200: rank/tile mismatch in attach_nccl\n"); return 5; }
+  if (nranks != h->cfg.NtileI || rank != h->itile) { std::fprintf(stderr, "roms_b200: rank/tile mismatch in attach_nccl\n"); return 5; }
   if (!nccl().ok) return 8;
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return 8;
   Halo* H = new Halo();

@@ -15,6 +15,9 @@ struct Tmp {
   int rc = 0;
   explicit Tmp(const roms_b200_tile_t* b) {
     if (!b) { rc = 2; return; }
+    // a _tile call computes the whole xi-column of tiles; with NtileJ > 1 a host would call it once per Jtile and the
+    // read-modify-write routines would be applied NtileJ times: the per-routine form needs NtileJ == 1
+    if (b->cfg.NtileJ != 1) { rc = 5; return; }
     rc = roms_b200_create(&b->cfg, &h);
     if (rc) return;
     int ab[4];

@@ -217,6 +217,28 @@ def test_generic_routine_tile_every_phase(case):
                 assert np.array_equal(a, o.field(n)), (ph, n)
 
 
+def test_ntilej_partition_is_accepted_and_tiling_invariant():
+    """The shipped roms_benchmark3.in partitions the domain 2 x 2 (NtileI = NtileJ = 2).  The eta partition only splits loop
+    ranges, so a handle takes the whole xi-column of tiles; the result must be bit-identical to the oracle run with the same
+    2 x 2 tiling (and hence, by the oracle's own tiling-invariance test, to the 1 x 1 run)."""
+    kw = dict(Lm=64, Mm=32, N=10)
+    o = orc.Oracle(orc.APP_BENCHMARK, NtileI=1, NtileJ=2, **kw)
+    o.run_phase("set_data"); o.run_phase("ini")
+    cfg = cfg_from_oracle(o)
+    cfg.NtileI, cfg.NtileJ, cfg.tile = 1, 2, 1                      # tile 1 = (Itile 0, Jtile 1): selects xi-column 0
+    t = Tile(cfg, strict=True)
+    assert (t.LBi, t.UBi, t.LBj, t.UBj) == (-2, 66, 0, 33)
+    copy_state(o, t)
+    o.step(4, 2); t.main3d(4)
+    assert not compare(o, t, all_names(2), exact=True)
+    t.close()
+    L = _lib.load(True)
+    ta = _lib.TileArgs(cfg=cfg, iic=1, ntfirst=1, nstp=1, nnew=2, nrhs=1, iif=1, kstp=1, krhs=1, knew=1, predictor=0)
+    z = np.zeros_like(o.field("W"))
+    P = lambda a: a.ctypes.data_as(_lib.DP)  # noqa: E731
+    assert L.roms_b200_omega_tile(C.byref(ta), P(o.field("Huon")), P(o.field("Hvom")), P(o.field("z_w")), P(z)) == 5   # per-routine form: NtileJ == 1 only
+
+
 def test_error_behaviour():
     """exit_flag convention (mod_scalars.F:523-532): input errors 2, configuration 5; blow-up 1 from diag."""
     t = synth.make_tile(synth.APP_SEAMOUNT)

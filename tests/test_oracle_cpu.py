@@ -199,9 +199,11 @@ def test_cabi_bounds_match_oracle():
 def test_cabi_rejects_bad_config_and_has_no_cpu_fallback():
     from roms_trunk_mgh_b200 import _lib
     cfg = _lib.default_config(0)
-    cfg.NtileJ = 2
+    cfg.NtileJ = 2; cfg.tile = 2                                                       # tile index beyond NtileI*NtileJ
     h = ctypes.c_void_p()
     assert _lib.load().roms_b200_create(ctypes.byref(cfg), ctypes.byref(h)) == 5      # configuration error
+    cfg.NtileJ = 0; cfg.tile = 0
+    assert _lib.load().roms_b200_create(ctypes.byref(cfg), ctypes.byref(h)) == 5
     cfg = _lib.default_config(0)
     import torch
     if not torch.cuda.is_available():
