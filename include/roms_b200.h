@@ -112,7 +112,8 @@ enum {
   ROMS_B200_STEP2D = 13,       /* step2d_LF_AM3.h:137    */  ROMS_B200_SET_DEPTH = 14,   /* set_depth.F:82         */
   ROMS_B200_STEP3D_UV = 15,    /* step3d_uv.F:111        */  ROMS_B200_OMEGA2 = 16,      /* main3d.F:789           */
   ROMS_B200_STEP3D_T = 17,     /* step3d_t.F:108         */  ROMS_B200_DIAG = 18,        /* diag.F:80              */
-  ROMS_B200_SET_DATA = 19,     /* (host forcing; no-op)  */  ROMS_B200_STEP2D_LOOP = 20  /* main3d.F:592-700       */
+  ROMS_B200_SET_DATA = 19,     /* (host forcing; no-op)  */  ROMS_B200_STEP2D_LOOP = 20, /* main3d.F:592-700       */
+  ROMS_B200_SET_AVG = 22       /* set_avg.F:128          */
 };
 int roms_b200_run_phase(roms_b200_handle h, int phase);
 
@@ -120,6 +121,12 @@ int roms_b200_run_phase(roms_b200_handle h, int phase);
  * enqueueing; roms_b200_sync waits.  Forcing (sustr, svstr, stflux, btflux) is whatever was last uploaded. */
 int roms_b200_main3d_step(roms_b200_handle h, int nsteps);
 int roms_b200_sync(roms_b200_handle h);
+/* AVERAGES (ROMS/Nonlinear/set_avg.F, called from main3d.F:494 right after set_zeta): time averages of the chain's state
+ * variables over windows of nAVG steps starting after step ntsAVG (roms_*.in NAVG, NTSAVG; nAVG = 0 switches them off),
+ * accumulated on the device by every step.  The averages are fields like any other (roms_b200_get_field): "avgzeta", "avgu2d",
+ * "avgv2d" (2-D), "avgu3d", "avgv3d", "avgrho", "avgt_<itrc>" (1:N), "avgw3d" = W*pm*pn, "avgwvel" (0:N); a window's averages are
+ * complete after the step with MOD(iic-1, nAVG) == 0, which is when the reference writes them (wrt_avg). */
+int roms_b200_set_avg(roms_b200_handle h, int nAVG, int ntsAVG);
 /* Run-time switches of a handle (set before stepping; the captured time-step graphs are dropped):
  *   "cuda_graphs"      1 (default) replay one CUDA graph per baroclinic step, 0 plain stream launches
  *   "step2d_exchange"  how the xi-halo of the barotropic sub-steps travels on the NVLink peer path (before attach only):

@@ -144,6 +144,7 @@ void run_phase(Model& m, int phase, int nthreads) {
     case PH_OMEGA: case PH_OMEGA2: for_tiles(m, nthreads, [&](const Bnd& b) { omega(m, b); }); break;
     case PH_WVELOCITY: for_tiles(m, nthreads, [&](const Bnd& b) { wvelocity(m, b, m.nstp); }); break;
     case PH_SET_ZETA: for_tiles(m, nthreads, [&](const Bnd& b) { set_zeta(m, b); }); break;
+    case PH_SET_AVG: for_tiles(m, nthreads, [&](const Bnd& b) { set_avg(m, b); }); break;
     case PH_PRE_STEP3D: for_tiles(m, nthreads, [&](const Bnd& b) { pre_step3d(m, b); }); break;
     case PH_PRSGRD: for_tiles(m, nthreads, [&](const Bnd& b) { prsgrd(m, b); }); break;
     case PH_T3DMIX: for_tiles(m, nthreads, [&](const Bnd& b) { t3dmix2(m, b); }); break;
@@ -181,7 +182,7 @@ void main3d_step(Model& m, int nthreads) {
     omega(m, b);
     if (m.c.wvelocity_every_step) wvelocity(m, b, m.nstp);
   });
-  run_phase(m, PH_SET_ZETA, nthreads);                                               // :489
+  for_tiles(m, nthreads, [&](const Bnd& b) { set_zeta(m, b); set_avg(m, b); });      // :489-495
   for_tiles(m, nthreads, [&](const Bnd& b) {                                         // :563 -> rhs3d.F:74-159
     pre_step3d(m, b); prsgrd(m, b); t3dmix2(m, b); rhs3d(m, b); uv3dmix2(m, b);
   });

@@ -147,6 +147,7 @@ struct Cfg {
   int Vtransform = 2, Vstretching = 4;
   double lambda = 1.0;            // mod_scalars.F (implicit vertical diffusion weight)
   int itemp = 1, isalt = 2;       // tracer indices (1-based)
+  int nAVG = 0, ntsAVG = 1;       // AVERAGES: window length in steps (0: off) and starting step (roms_*.in NAVG, NTSAVG)
 };
 
 Cfg make_cfg(int app, int Lm = 0, int Mm = 0, int N = 0);   // defaults from roms_<app>.in (Lm=0 -> shipped sizes)
@@ -180,6 +181,9 @@ struct Model {
   F3 ru[3], rv[3];                              // [1..2], k=0..N
   F3 rho, pden, Hz, z_r, Huon, Hvom;            // k=1..N
   F3 W, wvel, z_w, Akv; F3 Akt[2];              // k=0..N
+  // ---- time-averaged fields (mod_average.F; set_avg.cpp)
+  F2 avgzeta, avgu2d, avgv2d; F3 avgu3d, avgv3d, avgrho, avgt[2];   // k=1..N
+  F3 avgw3d, avgwvel;                                               // k=0..N
   // ---- time stepping (mod_stepping.F:64-72; initial.F:126-170)
   int iic = 0, ntstart = 1, ntfirst = 1, ntend = 0;
   int nstp = 1, nnew = 1, nrhs = 1;
@@ -208,6 +212,7 @@ void ana_vmix(Model& m, const Bnd& b);        // ROMS/Functionals/ana_vmix.h
 void ini_zeta(Model& m, const Bnd& b);        // ROMS/Nonlinear/ini_fields.F:836-1137
 void ini_fields(Model& m, const Bnd& b);      // ROMS/Nonlinear/ini_fields.F:106-777
 void initialize(Model& m);                    // initial.F call order
+void set_avg(Model& m, const Bnd& b);         // ROMS/Nonlinear/set_avg.F
 
 // ---- periodic exchanges / boundary conditions
 void exchange_r2d(const Model& m, const Bnd& b, F2 A);
@@ -255,7 +260,7 @@ void eos_point(double Tt, double Ts, double Tp, double* den, double* den1, doubl
 enum Phase {
   PH_SET_MASSFLUX = 1, PH_RHO_EOS = 2, PH_SET_VBC = 3, PH_ANA_VMIX = 4, PH_OMEGA = 5, PH_WVELOCITY = 6, PH_SET_ZETA = 7,
   PH_PRE_STEP3D = 8, PH_PRSGRD = 9, PH_T3DMIX = 10, PH_RHS3D = 11, PH_UV3DMIX = 12, PH_STEP2D = 13, PH_SET_DEPTH = 14,
-  PH_STEP3D_UV = 15, PH_OMEGA2 = 16, PH_STEP3D_T = 17, PH_DIAG = 18, PH_SET_DATA = 19, PH_STEP2D_LOOP = 20, PH_INI = 21
+  PH_STEP3D_UV = 15, PH_OMEGA2 = 16, PH_STEP3D_T = 17, PH_DIAG = 18, PH_SET_DATA = 19, PH_STEP2D_LOOP = 20, PH_INI = 21, PH_SET_AVG = 22
 };
 void run_phase(Model& m, int phase, int nthreads);
 void main3d_step(Model& m, int nthreads);    // one baroclinic step (main3d.F:189-917)

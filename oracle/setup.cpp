@@ -156,6 +156,9 @@ void Model::allocate() {
   rho = new3(1, N); pden = new3(1, N); Hz = new3(1, N); z_r = new3(1, N); Huon = new3(1, N); Hvom = new3(1, N);
   W = new3(0, N); wvel = new3(0, N); z_w = new3(0, N); Akv = new3(0, N);
   for (int it = 0; it < c.NT; ++it) Akt[it] = new3(0, N);
+  avgzeta = new2(); avgu2d = new2(); avgv2d = new2(); avgu3d = new3(1, N); avgv3d = new3(1, N); avgrho = new3(1, N);
+  avgw3d = new3(0, N); avgwvel = new3(0, N);
+  for (int it = 0; it < c.NT; ++it) avgt[it] = new3(1, N);
   sc_r.assign(N + 1, 0.0); Cs_r.assign(N + 1, 0.0); sc_w.assign(N + 1, 0.0); Cs_w.assign(N + 1, 0.0);
   // mod_mixing.F:1422-1443: Akv/Akt background at k=1..N-1, IniVal at k=0,N
   for (int k = 1; k <= N - 1; ++k)

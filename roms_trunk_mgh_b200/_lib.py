@@ -32,7 +32,7 @@ class TileArgs(C.Structure):
 
 PHASES = dict(set_massflux=1, rho_eos=2, set_vbc=3, ana_vmix=4, omega=5, wvelocity=6, set_zeta=7, pre_step3d=8, prsgrd=9,
               t3dmix=10, rhs3d=11, uv3dmix=12, step2d=13, set_depth=14, step3d_uv=15, omega2=16, step3d_t=17, diag=18,
-              set_data=19, step2d_loop=20)
+              set_data=19, step2d_loop=20, set_avg=22)
 INDEX_NAMES = ["iic", "ntstart", "ntfirst", "nstp", "nnew", "nrhs", "iif", "indx1", "kstp", "krhs", "knew", "PREDICTOR", "exit_flag"]
 DIAG_NAMES = ["avgke", "avgpe", "avgkp", "volume", "max_speed", "maxCu", "maxCv", "maxCw", "ubarmax", "vbarmax", "umax", "vmax"]
 
@@ -43,7 +43,7 @@ EXPORTS = ["roms_b200_default_config", "roms_b200_bounds", "roms_b200_bounds_nam
            "roms_b200_step_forced", "roms_b200_diag", "roms_b200_register_host", "roms_b200_unregister_host", "roms_b200_last_step_ms", "roms_b200_profile_enable", "roms_b200_profile_get",
            "roms_b200_launch_count", "roms_b200_attach_nccl", "roms_b200_nccl_unique_id", "roms_b200_nccl_init_rank",
            "roms_b200_peer_export", "roms_b200_peer_attach", "roms_b200_peer_enable", "roms_b200_peer_error", "roms_b200_peer_error_inject",
-           "roms_b200_set_option",
+           "roms_b200_set_option", "roms_b200_set_avg",
            "roms_b200_rho_eos_tile", "roms_b200_prsgrd_tile", "roms_b200_set_massflux_tile", "roms_b200_omega_tile",
            "roms_b200_set_depth_tile", "roms_b200_routine_tile", "roms_b200_routine_args", "roms_b200_field_levels"]
 
@@ -102,6 +102,7 @@ def load(strict=False):
     L.roms_b200_peer_error.argtypes = [H]
     L.roms_b200_peer_error_inject.argtypes = [H]
     L.roms_b200_set_option.argtypes = [H, C.c_char_p, C.c_double]
+    L.roms_b200_set_avg.argtypes = [H, C.c_int, C.c_int]
     TP = C.POINTER(TileArgs)
     L.roms_b200_rho_eos_tile.argtypes = [TP] + [DP] * 9
     L.roms_b200_prsgrd_tile.argtypes = [TP] + [DP] * 8

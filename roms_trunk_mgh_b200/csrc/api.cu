@@ -127,6 +127,17 @@ void collect_marks(roms_b200_state* h) {
   cudaGetLastError();
 }
 
+// set_avg.F:237-240 / :1264 / :2298-2301 for the step about to run: bit 0 initialise, bit 1 accumulate, bit 2 normalise
+int avg_mode(const roms_b200_state* h) {
+  if (h->navg <= 0) return 0;
+  const int iic = h->iic, n = h->navg, s0 = h->ntsavg;
+  int m = 0;
+  if ((iic > s0 && (iic - 1) % n == 1) || (iic >= s0 && n == 1)) m |= 1;
+  else if (iic > s0) m |= 2;
+  if ((iic > s0 && (iic - 1) % n == 0) || (iic >= s0 && n == 1)) m |= 4;
+  return m;
+}
+
 struct PhaseTimer {
   roms_b200_state* h; int phase; cudaEvent_t a = nullptr, b = nullptr;
   PhaseTimer(roms_b200_state* h_, int ph) : h(h_), phase(ph) {
@@ -164,6 +175,12 @@ std::vector<std::string> halo_fields(roms_b200_state* h, int phase) {
       else v = {"zeta" + kn, "ubar" + kn, "vbar" + kn};
       break;
     case ROMS_B200_SET_DEPTH: v = {"z_w", "z_r", "Hz"}; break;                      // set_depth.F:269-279
+    case ROMS_B200_SET_AVG:                                                         // set_avg.F:2347-2598 (when the window closes)
+      if (avg_mode(h) & 4) {
+        v = {"avgzeta", "avgu2d", "avgv2d", "avgu3d", "avgv3d", "avgrho", "avgw3d", "avgwvel"};
+        for (int it = 0; it < h->cfg.NT; ++it) v.push_back("avgt_" + std::to_string(it));
+      }
+      break;
     case ROMS_B200_STEP3D_UV: v = {"u" + nn, "v" + nn, "Huon", "Hvom", "ubar1", "ubar2", "vbar1", "vbar2"}; break;   // step3d_uv.F:1464-1471
     case ROMS_B200_STEP3D_T: T(h->nnew); break;                                     // step3d_t.F:1626
     default: break;
@@ -331,6 +348,14 @@ int run_phase_async(roms_b200_state* h, int phase) {
     case ROMS_B200_UV3DMIX: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_uv3dmix2(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_STEP2D: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_step2d(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_SET_DEPTH: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_depth(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_SET_AVG: {
+      const int m = avg_mode(h);
+      if (!m) break;
+      // KOUT = kstp, NOUT = nrhs (globaldefs.h:504-508)
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) {
+        launch_set_avg(q, f, (m & 1) ? 0 : 1, (m & 4) ? 1 : 0, 1.0 / (double)h->navg, h->kstp, h->nrhs, st); });
+      h->launches += 1; break;
+    }
     case ROMS_B200_STEP3D_UV: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_step3d_uv(q, f, st); }); h->launches += 2; break;
     case ROMS_B200_STEP3D_T: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_step3d_t(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_DIAG: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_diag(q, f, h->d_diag_partial, h->d_diag_out, h->knew, st); }); h->launches += 3; break;
@@ -404,7 +429,7 @@ int step_phases_body(roms_b200_state* h, bool with_diag) {
   static const int seq2[] = {ROMS_B200_SET_VBC, ROMS_B200_ANA_VMIX, ROMS_B200_OMEGA};
   for (int ph : seq2) { int rc = run_phase_async(h, ph); if (rc) return rc; }
   if (h->cfg.wvelocity_every_step) { int rc = run_phase_async(h, ROMS_B200_WVELOCITY); if (rc) return rc; }
-  static const int seq3[] = {ROMS_B200_SET_ZETA,  ROMS_B200_PRE_STEP3D, ROMS_B200_PRSGRD,    ROMS_B200_T3DMIX,   ROMS_B200_RHS3D, ROMS_B200_UV3DMIX,
+  static const int seq3[] = {ROMS_B200_SET_ZETA,  ROMS_B200_SET_AVG, ROMS_B200_PRE_STEP3D, ROMS_B200_PRSGRD,    ROMS_B200_T3DMIX,   ROMS_B200_RHS3D, ROMS_B200_UV3DMIX,
                              ROMS_B200_STEP2D_LOOP, ROMS_B200_SET_DEPTH, ROMS_B200_STEP3D_UV, ROMS_B200_OMEGA2, ROMS_B200_STEP3D_T};
   for (int ph : seq3) { int rc = run_phase_async(h, ph); if (rc) return rc; }
   join_halo(h);                      // the step ends with both streams joined (also required to end a graph capture)
@@ -421,7 +446,7 @@ int one_step(roms_b200_state* h, bool with_diag) {
   h->tdays = h->time / 86400.0;
   const bool steady = h->iic >= h->ntfirst + 2 && h->predictor == 0;
   if (h->use_graphs && steady && h->profile != 1) {
-    const int key = h->nstp | (h->indx1 << 2) | ((with_diag ? 1 : 0) << 4) | ((h->profile == 2 ? 1 : 0) << 5);
+    const int key = h->nstp | (h->indx1 << 2) | ((with_diag ? 1 : 0) << 4) | ((h->profile == 2 ? 1 : 0) << 5) | (avg_mode(h) << 6);
     auto it = h->graphs.find(key);
     StepGraph* g = (it == h->graphs.end()) ? nullptr : (StepGraph*)it->second;
     if (!g) {
@@ -785,6 +810,25 @@ int roms_b200_sync(roms_b200_handle h) {
   if (!h) return InputError;
   CK(cudaSetDevice(h->cfg.device));
   return sync_and_check(h);
+}
+
+int roms_b200_set_avg(roms_b200_handle h, int nAVG, int ntsAVG) {
+  if (!h || nAVG < 0) return InputError;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
+  if (nAVG > 0 && !h->fl.avgzeta) {
+    Flds& f = h->fl; const int N = h->cfg.N;
+    int rc = 0;
+    rc |= alloc_field(h, "avgzeta", &f.avgzeta, 0, 1); rc |= alloc_field(h, "avgu2d", &f.avgu2d, 0, 1); rc |= alloc_field(h, "avgv2d", &f.avgv2d, 0, 1);
+    rc |= alloc_field(h, "avgu3d", &f.avgu3d, 1, N); rc |= alloc_field(h, "avgv3d", &f.avgv3d, 1, N); rc |= alloc_field(h, "avgrho", &f.avgrho, 1, N);
+    rc |= alloc_field(h, "avgw3d", &f.avgw3d, 0, N + 1); rc |= alloc_field(h, "avgwvel", &f.avgwvel, 0, N + 1);
+    for (int it = 0; it < h->cfg.NT; ++it) rc |= alloc_field(h, "avgt_" + std::to_string(it), &f.avgt[it], 1, N);
+    if (rc) return FatalError;
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  h->navg = nAVG; h->ntsavg = ntsAVG;
+  return NoError;
 }
 
 int roms_b200_set_option(roms_b200_handle h, const char* key, double value) {

@@ -57,6 +57,9 @@ struct Flds {
   double* Akt[MAXNT];
   // scratch
   double* P3;                      // prsgrd32 pressure (1:N)
+  // time-averaged fields (mod_average.F; allocated by roms_b200_set_avg)
+  double *avgzeta, *avgu2d, *avgv2d, *avgu3d, *avgv3d, *avgrho, *avgw3d, *avgwvel;
+  double* avgt[MAXNT];
   // 1-D (device)
   double *sc_r, *Cs_r, *sc_w, *Cs_w;
 };

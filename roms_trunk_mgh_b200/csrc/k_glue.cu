@@ -298,6 +298,34 @@ __global__ void __launch_bounds__(256) k_ana_vmix(Par p, Flds f) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// set_avg_tile (ROMS/Nonlinear/set_avg.F:237-2600, AVERAGES) for the state variables of the chain: the window's first call
+// copies (:280-426), the others add (:1308-1454), and the call that closes the window scales the sums by 1/nAVG and refreshes
+// the periodic images (:2327-2598).  One thread per (i,j,k); level k = 0 also handles the 2-D fields.
+__global__ void __launch_bounds__(256) k_set_avg(Par p, Flds f, int mode, int norm, double fac, int Kout, int Nout) {
+  const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;          // JstrR..JendR = 0..Mm+1
+  const int k = blockIdx.z;                                     // 0..N
+  if (i > p.Iend || j > p.Mm + 1) return;
+  const int o2 = j * p.P, o = o2 + k * p.PL;
+  auto put = [&](double* A, int off, double x) {
+    double v = (mode == 0) ? x : A[off + i] + x;
+    if (norm) { v = fac * v; st_w(A, off, i, v, p); } else A[off + i] = v;
+  };
+  if (k == 0) {
+    put(f.avgzeta, o2, f.zeta[Kout][o2 + i]);
+    put(f.avgu2d, o2, f.ubar[Kout][o2 + i]);
+    if (j >= 1) put(f.avgv2d, o2, f.vbar[Kout][o2 + i]);
+  } else {
+    put(f.avgu3d, o, f.u[Nout][o + i]);
+    if (j >= 1) put(f.avgv3d, o, f.v[Nout][o + i]);
+    put(f.avgrho, o, f.rho[o + i]);
+    for (int it = 0; it < p.NT; ++it) put(f.avgt[it], o, f.t[Nout][it][o + i]);
+  }
+  put(f.avgw3d, o, f.W[o + i] * f.pm[o2 + i] * f.pn[o2 + i]);
+  put(f.avgwvel, o, f.wvel[o + i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 static inline dim3 g2(const Par& p, dim3 b, int nj, int nz = 1) {
   return dim3((xspan(p) + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz);
 }
@@ -314,6 +342,10 @@ void launch_wvelocity(const Par& p, const Flds& f, int Ninp, cudaStream_t s) {
   dim3 b(64, 2);
   if (p.N == 30) k_wvelocity<30><<<g2(p, b, p.Mm), b, 0, s>>>(p, f, Ninp);
   else k_wvelocity<0><<<g2(p, b, p.Mm), b, 0, s>>>(p, f, Ninp);
+}
+void launch_set_avg(const Par& p, const Flds& f, int mode, int norm, double fac, int Kout, int Nout, cudaStream_t s) {
+  dim3 b(64, 4);
+  k_set_avg<<<g2(p, b, p.Mm + 2, p.N + 1), b, 0, s>>>(p, f, mode, norm, fac, Kout, Nout);
 }
 void launch_set_zeta(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_zeta<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
 void launch_set_depth(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_depth<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }

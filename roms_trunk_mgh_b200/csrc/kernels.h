@@ -23,6 +23,8 @@ void launch_step2d(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x = 
 // The whole LOOP_2D in one cooperative launch (k_step2d_loop.cu); false / 0: the tile is too large for it
 bool launch_step2d_loop(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x, const LoopCtl& ctl);
 int step2d_loop_ctas(const Par& p);
+// set_avg_tile (set_avg.F): mode 0 initialise, 1 accumulate; norm: scale by fac and fill the periodic images
+void launch_set_avg(const Par& p, const Flds& f, int mode, int norm, double fac, int Kout, int Nout, cudaStream_t s);
 void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s);
 void launch_step3d_t(const Par& p, const Flds& f, cudaStream_t s);
 // diag: partial[] must hold 16 doubles per block row; out16 on device

@@ -47,6 +47,8 @@ struct roms_b200_state {
   // columns hold garbage).  Every host synchronisation point reads it back and turns it into exit_flag 8 (check_device_error).
   unsigned long long* d_err = nullptr; unsigned long long* h_err = nullptr;
   double halo_timeout_s = 30.0;     // how long a kernel waits for a neighbour's halo before it gives up (roms_b200_set_option)
+  // AVERAGES (set_avg.F): window length in steps (0: off) and first step, roms_b200_set_avg
+  int navg = 0, ntsavg = 1;
   // diag
   double* d_diag_partial = nullptr; double* d_diag_out = nullptr; double* h_diag_out = nullptr;
   double* h_pinned = nullptr; size_t pinned_n = 0; double* d_stage = nullptr;

@@ -65,6 +65,12 @@ class Tile:
             for n in n3:
                 wlev = n in ("W", "wvel", "z_w", "Akv", "ru1", "ru2", "rv1", "rv2") or n.startswith("Akt_")
                 self._nk[n] = self.N + 1 if wlev else self.N
+            for n in ("avgzeta", "avgu2d", "avgv2d"):
+                self._nk[n] = 1
+            for n in ["avgu3d", "avgv3d", "avgrho"] + [f"avgt_{it}" for it in range(self.NT)]:
+                self._nk[n] = self.N
+            for n in ("avgw3d", "avgwvel"):
+                self._nk[n] = self.N + 1
         return self._nk[name]
 
     def set(self, name, arr):
@@ -107,6 +113,10 @@ class Tile:
         self._ck("main3d_step", self.L.roms_b200_main3d_step(self.h, int(nsteps)))
         if sync:
             self.sync()
+
+    def set_avg(self, nAVG, ntsAVG=1):
+        """AVERAGES (set_avg.F): accumulate time averages over windows of nAVG steps on the device (0: off)."""
+        self._ck("set_avg", self.L.roms_b200_set_avg(self.h, int(nAVG), int(ntsAVG)))
 
     def set_option(self, key, value):
         """roms_b200_set_option: "cuda_graphs", "step2d_exchange", "overlap", "halo_timeout_s"."""

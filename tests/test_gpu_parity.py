@@ -239,6 +239,54 @@ def test_ntilej_partition_is_accepted_and_tiling_invariant():
     assert L.roms_b200_omega_tile(C.byref(ta), P(o.field("Huon")), P(o.field("Hvom")), P(o.field("z_w")), P(z)) == 5   # per-routine form: NtileJ == 1 only
 
 
+AVG_NAMES = ["avgzeta", "avgu2d", "avgv2d", "avgu3d", "avgv3d", "avgrho", "avgw3d", "avgwvel", "avgt_0", "avgt_1"]
+
+
+@pytest.mark.parametrize("navg,ntsavg", [(3, 1), (1, 1), (4, 3)])
+def test_set_avg_time_averages_bit_exact(navg, ntsavg):
+    """AVERAGES (set_avg.F, main3d.F:494): the device accumulates the time averages of the chain's state variables inside every
+    step; after each of 9 steps (three windows of 3, captured-graph replays included) they equal the oracle's bit for bit."""
+    kw = dict(Lm=64, Mm=32, N=10)
+    o = orc.Oracle(orc.APP_BENCHMARK, nAVG=navg, ntsAVG=ntsavg, **kw)
+    o.run_phase("set_data"); o.run_phase("ini")
+    t = Tile(cfg_from_oracle(o), strict=True)
+    copy_state(o, t)
+    t.set_avg(navg, ntsavg)
+    for s in range(9):
+        o.step(1); t.main3d(1)
+        for n in AVG_NAMES:
+            assert np.array_equal(o.field(n), t.get(n)), (s, n)
+    assert not compare(o, t, all_names(2), exact=True)
+    t.close()
+
+
+def test_perfect_restart_is_bit_exact():
+    """PERFECT_RESTART (wrt_rst.F:37-156 writes every time level of the prognostic and right-hand-side fields): a run that is
+    stopped after 5 steps, downloaded field by field, uploaded into a NEW handle and continued for 4 steps ends bit-identical to
+    the uninterrupted 9-step run -- i.e. roms_b200_get_field / set_field expose the complete state of the path."""
+    app, kw = CASES["benchmark"]
+    o, a = make_pair(app, strict=True, **kw)
+    a.main3d(9)
+    o2, b = make_pair(app, strict=True, **kw)
+    b.main3d(5)
+    names = all_names(2)
+    saved = {n: b.get(n) for n in names}
+    idx = b.indices()
+    b.close()
+    c = Tile(cfg_from_oracle(o2), strict=True)
+    for n in names:
+        c.set(n, saved[n])
+    N, nd = int(o2.opt("N")), int(o2.opt("ndtfast"))
+    c.set_scoord(o2.vector(0, N + 1), o2.vector(1, N + 1), o2.vector(2, N + 1), o2.vector(3, N + 1))
+    c.set_weights(int(o2.opt("nfast")), o2.vector(4, 2 * nd + 2), o2.vector(5, 2 * nd + 2))
+    c.set_indices(idx)
+    c.main3d(4)
+    for n in names:
+        assert np.array_equal(a.get(n), c.get(n)), n
+    assert a.indices() == c.indices()
+    a.close(); c.close()
+
+
 def test_error_behaviour():
     """exit_flag convention (mod_scalars.F:523-532): input errors 2, configuration 5; blow-up 1 from diag."""
     t = synth.make_tile(synth.APP_SEAMOUNT)
