@@ -60,6 +60,13 @@ typedef struct roms_b200_config {
   double hc;                    /* s-coordinate critical depth (set_scoord.F:170-178)                              */
   int itemp, isalt;             /* 1-based tracer indices                                                          */
   int device;                   /* CUDA device ordinal                                                             */
+  /* Optional terms INSIDE the routines of the chain that the shipped BENCHMARK cpp set (ROMS/Include/benchmark.h) switches
+   * on.  Their inputs come from parameterisations that stay on the host (bulk_flux.F, lmd_vmix.F) and are uploaded like any
+   * field: "srflx" (FORCES%srflx), "Jwtype" (MIXING%Jwtype), "ghats_<itrc>" (MIXING%ghats, 0:N).                            */
+  int bv_frequency;             /* BV_FREQUENCY: rho_eos also returns "bvf" (0:N) (rho_eos.F:402-418 / :751-758)      */
+  int eos_tderivative;          /* LMD_SKPP || BULK_FLUXES: rho_eos also returns "alpha", "beta" (:420-462 / :760-773) */
+  int solar_source;             /* SOLAR_SOURCE: shortwave penetration in pre_step3d (:312-333, :866-883; lmd_swfrac.F) */
+  int lmd_nonlocal;             /* LMD_NONLOCAL: KPP nonlocal transport in pre_step3d (:850-865)                       */
 } roms_b200_config;
 
 /* Fills *cfg with the shipped defaults of roms_<app>.in (Lm,Mm,N = 0 keeps the shipped grid size). */

@@ -16,14 +16,14 @@ bool lookup(Model& m, const std::string& name, double** p, int dims[6]) {
   static const char* n2[] = {"h", "f", "pm", "pn", "om_r", "on_r", "om_u", "on_u", "om_v", "on_v", "om_p", "on_p", "omn", "fomn", "pmon_r", "pnom_r",
                              "pmon_u", "pnom_u", "pmon_v", "pnom_v", "pmon_p", "pnom_p", "dndx", "dmde", "rdrag", "rdrag2", "visc2_r", "visc2_p",
                              "Zt_avg1", "DU_avg1", "DU_avg2", "DV_avg1", "DV_avg2", "rufrc", "rvfrc", "rhoA", "rhoS", "sustr", "svstr", "bustr", "bvstr",
-                             "avgzeta", "avgu2d", "avgv2d"};
+                             "avgzeta", "avgu2d", "avgv2d", "alpha", "beta", "srflx", "Jwtype"};
   F2* a2[] = {&m.h, &m.f, &m.pm, &m.pn, &m.om_r, &m.on_r, &m.om_u, &m.on_u, &m.om_v, &m.on_v, &m.om_p, &m.on_p, &m.omn, &m.fomn, &m.pmon_r, &m.pnom_r,
               &m.pmon_u, &m.pnom_u, &m.pmon_v, &m.pnom_v, &m.pmon_p, &m.pnom_p, &m.dndx, &m.dmde, &m.rdrag, &m.rdrag2, &m.visc2_r, &m.visc2_p,
               &m.Zt_avg1, &m.DU_avg1, &m.DU_avg2, &m.DV_avg1, &m.DV_avg2, &m.rufrc, &m.rvfrc, &m.rhoA, &m.rhoS, &m.sustr, &m.svstr, &m.bustr, &m.bvstr,
-              &m.avgzeta, &m.avgu2d, &m.avgv2d};
+              &m.avgzeta, &m.avgu2d, &m.avgv2d, &m.alpha, &m.beta, &m.srflx, &m.Jwtype};
   for (size_t i = 0; i < sizeof(n2) / sizeof(n2[0]); ++i) if (name == n2[i]) return set2(*a2[i]);
-  static const char* n3[] = {"rho", "pden", "Hz", "z_r", "Huon", "Hvom", "W", "wvel", "z_w", "Akv", "avgu3d", "avgv3d", "avgrho", "avgw3d", "avgwvel"};
-  F3* a3[] = {&m.rho, &m.pden, &m.Hz, &m.z_r, &m.Huon, &m.Hvom, &m.W, &m.wvel, &m.z_w, &m.Akv, &m.avgu3d, &m.avgv3d, &m.avgrho, &m.avgw3d, &m.avgwvel};
+  static const char* n3[] = {"rho", "pden", "Hz", "z_r", "Huon", "Hvom", "W", "wvel", "z_w", "Akv", "avgu3d", "avgv3d", "avgrho", "avgw3d", "avgwvel", "bvf"};
+  F3* a3[] = {&m.rho, &m.pden, &m.Hz, &m.z_r, &m.Huon, &m.Hvom, &m.W, &m.wvel, &m.z_w, &m.Akv, &m.avgu3d, &m.avgv3d, &m.avgrho, &m.avgw3d, &m.avgwvel, &m.bvf};
   for (size_t i = 0; i < sizeof(n3) / sizeof(n3[0]); ++i) if (name == n3[i]) return set3(*a3[i]);
   // indexed names: zeta1..3, ubar1..3, vbar1..3, rzeta1..2, rubar1..2, rvbar1..2, u1..2, v1..2, ru1..2, rv1..2,
   // t<tl>_<itrc>, Akt_<itrc>, diff2_<itrc>, stflx_<itrc>, btflx_<itrc>, stflux_<itrc>, btflux_<itrc>
@@ -55,6 +55,7 @@ bool lookup(Model& m, const std::string& name, double** p, int dims[6]) {
   int it;
   if ((it = trc("Akt_")) >= 0) return set3(m.Akt[it]);
   if ((it = trc("avgt_")) >= 0) return set3(m.avgt[it]);
+  if ((it = trc("ghats_")) >= 0) return set3(m.ghats[it]);
   if ((it = trc("diff2_")) >= 0) return set2(m.diff2[it]);
   if ((it = trc("stflx_")) >= 0) return set2(m.stflx[it]);
   if ((it = trc("btflx_")) >= 0) return set2(m.btflx[it]);
@@ -85,6 +86,8 @@ int orc_set_option(void* hp, const char* key, double val) {
   else if (k == "tnu2") { c.tnu2[0] = c.tnu2[1] = val; } else if (k == "gamma2") c.gamma2 = val;
   else if (k == "Akv_bak") c.Akv_bak = val; else if (k == "Akt_bak") { c.Akt_bak[0] = c.Akt_bak[1] = val; }
   else if (k == "rdrg") c.rdrg = val; else if (k == "rdrg2") c.rdrg2 = val;
+  else if (k == "bv_frequency") c.bv_frequency = (int)val; else if (k == "eos_tderivative") c.eos_tderivative = (int)val;
+  else if (k == "solar_source") c.solar_source = (int)val; else if (k == "lmd_nonlocal") c.lmd_nonlocal = (int)val;
   else if (k == "nAVG") c.nAVG = (int)val; else if (k == "ntsAVG") c.ntsAVG = (int)val;
   else return 1;
   return 0;
@@ -100,6 +103,8 @@ double orc_get_option(void* hp, const char* key) {
   if (k == "R0") return c.R0; if (k == "T0") return c.T0; if (k == "S0") return c.S0; if (k == "Tcoef") return c.Tcoef; if (k == "Scoef") return c.Scoef;
   if (k == "theta_s") return c.theta_s; if (k == "theta_b") return c.theta_b; if (k == "Tcline") return c.Tcline; if (k == "lambda") return c.lambda;
   if (k == "nfast") return m.nfast; if (k == "dtfast") return m.dtfast; if (k == "hc") return m.hc; if (k == "wvelocity_every_step") return c.wvelocity_every_step;
+  if (k == "bv_frequency") return c.bv_frequency; if (k == "eos_tderivative") return c.eos_tderivative;
+  if (k == "solar_source") return c.solar_source; if (k == "lmd_nonlocal") return c.lmd_nonlocal;
   if (k == "app") return c.app; if (k == "nAVG") return c.nAVG; if (k == "ntsAVG") return c.ntsAVG;
   return -1.0e300;
 }

@@ -36,7 +36,10 @@ const double W00 = +4.8314e-04;
 
 // ROMS/Nonlinear/rho_eos.F:259-343 for one point (Tt,Ts already clipped by the caller as in :259-261).
 // den = in-situ density (kg/m3, NOT anomaly), den1 = density at the surface pressure, bulk = secant bulk modulus.
-void eos_point(double Tt, double Ts, double Tp, double* den, double* den1, double* bulk) {
+// extra: [0..2] bulk0, bulk1, bulk2 (BV_FREQUENCY :402-418), [3..6] Dden1DS, Dden1DT, DbulkDS, DbulkDT (:290-294, :330-335)
+void eos_point_x(double Tt, double Ts, double Tp, double* den, double* den1, double* bulk, double* extra);
+void eos_point(double Tt, double Ts, double Tp, double* den, double* den1, double* bulk) { eos_point_x(Tt, Ts, Tp, den, den1, bulk, nullptr); }
+void eos_point_x(double Tt, double Ts, double Tp, double* den, double* den1, double* bulk, double* extra) {
   using namespace eos;
   double C[10];
   double sqrtTs = std::sqrt(Ts);
@@ -58,6 +61,24 @@ void eos_point(double Tt, double Ts, double Tp, double* den, double* den1, doubl
   double bk = bulk0 - Tp * (bulk1 - Tp * bulk2);
   double cff = 1.0 / (bk + Tpr10);
   *den1 = d1; *bulk = bk; *den = d1 * bk * cff;
+  if (extra) {
+    double dCdT[10];
+    dCdT[0] = Q01 + Tt * (2.0 * Q02 + Tt * (3.0 * Q03 + Tt * (4.0 * Q04 + Tt * 5.0 * Q05)));      // :279-282
+    dCdT[1] = U01 + Tt * (2.0 * U02 + Tt * (3.0 * U03 + Tt * 4.0 * U04));
+    dCdT[2] = V01 + Tt * 2.0 * V02;
+    dCdT[3] = A01 + Tt * (2.0 * A02 + Tt * (3.0 * A03 + Tt * 4.0 * A04));                         // :313-319
+    dCdT[4] = B01 + Tt * (2.0 * B02 + Tt * 3.0 * B03);
+    dCdT[5] = D01 + Tt * 2.0 * D02;
+    dCdT[6] = E01 + Tt * (2.0 * E02 + Tt * 3.0 * E03);
+    dCdT[7] = F01 + Tt * 2.0 * F02;
+    dCdT[8] = G02 + Tt * 2.0 * G03;
+    dCdT[9] = H01 + Tt * 2.0 * H02;
+    extra[0] = bulk0; extra[1] = bulk1; extra[2] = bulk2;
+    extra[3] = C[1] + 1.5 * C[2] * sqrtTs + 2.0 * W00 * Ts;                                       // Dden1DS :293
+    extra[4] = dCdT[0] + Ts * (dCdT[1] + sqrtTs * dCdT[2]);                                       // Dden1DT :294
+    extra[5] = C[4] + sqrtTs * 1.5 * C[5] - Tp * (C[7] + sqrtTs * 1.5 * G00 - Tp * C[9]);        // DbulkDS :335-336
+    extra[6] = dCdT[3] + Ts * (dCdT[4] + sqrtTs * dCdT[5]) - Tp * (dCdT[6] + Ts * dCdT[7] - Tp * (dCdT[8] + Ts * dCdT[9]));   // DbulkDT :337-339
+  }
 }
 
 // ROMS/Nonlinear/rho_eos.F: nonlinear :252-483 (+ exchanges :489-526), linear :696-799 (+ :805-842)
@@ -67,6 +88,9 @@ void rho_eos(Model& m, const Bnd& b) {
   F3 T = m.t[nrhs][c.itemp - 1];
   F3 S = (c.salinity && c.NT >= 2) ? m.t[nrhs][c.isalt - 1] : F3();
   SK den(IminS, ImaxS, 1, N), den1(IminS, ImaxS, 1, N);
+  SK bulk(IminS, ImaxS, 1, N), bulk0(IminS, ImaxS, 1, N), bulk1(IminS, ImaxS, 1, N), bulk2(IminS, ImaxS, 1, N);
+  SK Dden1DS(IminS, ImaxS, 1, N), Dden1DT(IminS, ImaxS, 1, N), DbulkDS(IminS, ImaxS, 1, N), DbulkDT(IminS, ImaxS, 1, N);
+  const bool extras = c.bv_frequency || c.eos_tderivative;
   for (int j = JstrT; j <= JendT; ++j) {
     if (c.nonlin_eos) {
       for (int k = 1; k <= N; ++k)
@@ -74,10 +98,14 @@ void rho_eos(Model& m, const Bnd& b) {
           double Tt = std::max(-2.0, T(i, j, k));
           double Ts = c.salinity ? std::max(0.0, S(i, j, k)) : 0.0;
           double Tp = m.z_r(i, j, k);
-          double d, d1, bk;
-          eos_point(Tt, Ts, Tp, &d, &d1, &bk);
+          double d, d1, bk, ex[7];
+          eos_point_x(Tt, Ts, Tp, &d, &d1, &bk, extras ? ex : nullptr);
           den1(i, k) = d1;
           den(i, k) = d - 1000.0;
+          if (extras) {
+            bulk(i, k) = bk; bulk0(i, k) = ex[0]; bulk1(i, k) = ex[1]; bulk2(i, k) = ex[2];
+            Dden1DS(i, k) = ex[3]; Dden1DT(i, k) = ex[4]; DbulkDS(i, k) = ex[5]; DbulkDT(i, k) = ex[6];
+          }
         }
     } else {
       for (int k = 1; k <= N; ++k)
@@ -106,6 +134,46 @@ void rho_eos(Model& m, const Bnd& b) {
       m.rhoA(i, j) = cff2 * cff1 * m.rhoA(i, j);
       m.rhoS(i, j) = 2.0 * cff1 * cff1 * cff2 * m.rhoS(i, j);
     }
+    if (c.bv_frequency) {
+      if (c.nonlin_eos) {                                                               // :402-418
+        for (int k = 1; k <= N - 1; ++k)
+          for (int i = IstrT; i <= IendT; ++i) {
+            const double zw = m.z_w(i, j, k);
+            double bulk_up = bulk0(i, k + 1) - zw * (bulk1(i, k + 1) - bulk2(i, k + 1) * zw);
+            double bulk_dn = bulk0(i, k) - zw * (bulk1(i, k) - bulk2(i, k) * zw);
+            double cff1 = 1.0 / (bulk_up + 0.1 * zw);
+            double cff2 = 1.0 / (bulk_dn + 0.1 * zw);
+            double den_up = cff1 * (den1(i, k + 1) * bulk_up);
+            double den_dn = cff2 * (den1(i, k) * bulk_dn);
+            m.bvf(i, j, k) = -c.g * (den_up - den_dn) / (0.5 * (den_up + den_dn) * (m.z_r(i, j, k + 1) - m.z_r(i, j, k)));
+          }
+        for (int i = IstrT; i <= IendT; ++i) { m.bvf(i, j, 0) = 0.0; m.bvf(i, j, N) = 0.0; }
+      } else {                                                                          // :751-758
+        const double gorho0 = c.g / c.rho0;
+        for (int k = 1; k <= N - 1; ++k)
+          for (int i = IstrT; i <= IendT; ++i)
+            m.bvf(i, j, k) = -gorho0 * (den(i, k + 1) - den(i, k)) / (m.z_r(i, j, k + 1) - m.z_r(i, j, k));
+      }
+    }
+    if (c.eos_tderivative) {
+      if (c.nonlin_eos) {                                                               // :440-462 (no LMD_DDMIX: k = N only)
+        for (int i = IstrT; i <= IendT; ++i) {
+          const int k = N;
+          double Tpr10 = 0.1 * m.z_r(i, j, k);
+          double cff = bulk(i, k) + Tpr10;
+          double cff1 = Tpr10 * den1(i, k);
+          double cff2 = bulk(i, k) * cff;
+          double wrk = (den(i, k) + 1000.0) * cff * cff;
+          double Tcof = -(DbulkDT(i, k) * cff1 + Dden1DT(i, k) * cff2);
+          double Scof = (DbulkDS(i, k) * cff1 + Dden1DS(i, k) * cff2);
+          double cf = 1.0 / wrk;
+          m.alpha(i, j) = cf * Tcof;
+          m.beta(i, j) = cf * Scof;
+        }
+      } else {                                                                          // :766-773
+        for (int i = IstrT; i <= IendT; ++i) { m.alpha(i, j) = std::fabs(c.Tcoef); m.beta(i, j) = c.salinity ? std::fabs(c.Scoef) : 0.0; }
+      }
+    }
     for (int k = 1; k <= N; ++k)
       for (int i = IstrT; i <= IendT; ++i) {
         m.rho(i, j, k) = den(i, k);
@@ -114,6 +182,8 @@ void rho_eos(Model& m, const Bnd& b) {
   }
   exchange_r3d(m, b, m.rho); exchange_r3d(m, b, m.pden);
   exchange_r2d(m, b, m.rhoA); exchange_r2d(m, b, m.rhoS);
+  if (c.bv_frequency) exchange_w3d(m, b, m.bvf);                                        // :499-503
+  if (c.eos_tderivative) { exchange_r2d(m, b, m.alpha); exchange_r2d(m, b, m.beta); }    // :512-517
 }
 
 // ROMS/Nonlinear/set_vbc.F: tracer fluxes :278-283, :340-355; quadratic drag :591-624; linear drag :629-652; BCs :657-662

@@ -141,6 +141,23 @@ void pre_step3d(Model& m, const Bnd& b) {
           double cff = 1.0 / (z_r(i, j, k + 1) - z_r(i, j, k));
           FC(i, k) = cff3 * cff * Akt(i, j, k) * (tst(i, j, k + 1) - tst(i, j, k));
         }
+      if (c.lmd_nonlocal && itrc < (c.salinity ? 2 : 1)) {                 // :850-865 (active tracers, itrc <= NAT)
+        for (int k = 1; k <= N - 1; ++k)
+          for (int i = Istr; i <= Iend; ++i) FC(i, k) = FC(i, k) - dt * Akt(i, j, k) * m.ghats[itrc](i, j, k);
+      }
+      if (c.solar_source && itrc == c.itemp - 1) {                         // :312-333 + lmd_swfrac.F:66-80 (Zscale = -1), :866-883
+        static const double lmd_mu1[9] = {0.35, 0.6, 1.0, 1.5, 1.4, 0.42, 0.37, 0.33, 0.00468592};      // mod_scalars.F:1502-1512
+        static const double lmd_mu2[9] = {23.0, 20.0, 17.0, 14.0, 7.9, 5.13, 3.54, 2.34, 1.51};
+        static const double lmd_r1[9] = {0.58, 0.62, 0.67, 0.77, 0.78, 0.57, 0.57, 0.57, 0.55};
+        for (int k = 1; k <= N - 1; ++k)
+          for (int i = Istr; i <= Iend; ++i) {
+            const double Z = m.z_w(i, j, N) - m.z_w(i, j, k);
+            const int Jindex = (int)m.Jwtype(i, j);
+            const double fac1 = -1.0 / lmd_mu1[Jindex - 1], fac2 = -1.0 / lmd_mu2[Jindex - 1], fac3 = lmd_r1[Jindex - 1];
+            const double swdk = std::exp(Z * fac1) * fac3 + std::exp(Z * fac2) * (1.0 - fac3);
+            FC(i, k) = FC(i, k) + dt * m.srflx(i, j) * swdk;
+          }
+      }
       for (int i = Istr; i <= Iend; ++i) { FC(i, 0) = dt * m.btflx[itrc](i, j); FC(i, N) = dt * m.stflx[itrc](i, j); }
       for (int k = 1; k <= N; ++k)
         for (int i = Istr; i <= Iend; ++i) {

@@ -147,6 +147,12 @@ struct Cfg {
   int Vtransform = 2, Vstretching = 4;
   double lambda = 1.0;            // mod_scalars.F (implicit vertical diffusion weight)
   int itemp = 1, isalt = 2;       // tracer indices (1-based)
+  // optional terms INSIDE the routines of the chain that the shipped BENCHMARK cpp set switches on (benchmark.h); their
+  // inputs (srflx, ghats from bulk_flux / lmd_skpp) are supplied by the host
+  int bv_frequency = 0;           // BV_FREQUENCY: rho_eos also returns bvf (rho_eos.F:402-418 / :751-758)
+  int eos_tderivative = 0;        // LMD_SKPP || BULK_FLUXES: rho_eos also returns alpha, beta (:420-462 / :760-773)
+  int solar_source = 0;           // SOLAR_SOURCE: shortwave penetration in pre_step3d (:312-333, :866-883), lmd_swfrac.F
+  int lmd_nonlocal = 0;           // LMD_NONLOCAL: KPP nonlocal transport in pre_step3d (:850-865)
   int nAVG = 0, ntsAVG = 1;       // AVERAGES: window length in steps (0: off) and starting step (roms_*.in NAVG, NTSAVG)
 };
 
@@ -181,6 +187,8 @@ struct Model {
   F3 ru[3], rv[3];                              // [1..2], k=0..N
   F3 rho, pden, Hz, z_r, Huon, Hvom;            // k=1..N
   F3 W, wvel, z_w, Akv; F3 Akt[2];              // k=0..N
+  F3 bvf; F2 alpha, beta;                       // rho_eos optional outputs (bvf k=0..N)
+  F2 srflx, Jwtype; F3 ghats[2];                // mod_forces.F srflx; mod_mixing.F Jwtype, ghats (k=0..N)
   // ---- time-averaged fields (mod_average.F; set_avg.cpp)
   F2 avgzeta, avgu2d, avgv2d; F3 avgu3d, avgv3d, avgrho, avgt[2];   // k=1..N
   F3 avgw3d, avgwvel;                                               // k=0..N

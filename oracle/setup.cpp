@@ -156,6 +156,9 @@ void Model::allocate() {
   rho = new3(1, N); pden = new3(1, N); Hz = new3(1, N); z_r = new3(1, N); Huon = new3(1, N); Hvom = new3(1, N);
   W = new3(0, N); wvel = new3(0, N); z_w = new3(0, N); Akv = new3(0, N);
   for (int it = 0; it < c.NT; ++it) Akt[it] = new3(0, N);
+  bvf = new3(0, N); alpha = new2(); beta = new2(); srflx = new2(); Jwtype = new2();
+  for (int it = 0; it < c.NT; ++it) ghats[it] = new3(0, N);
+  for (int j = LBj; j <= UBj; ++j) for (int i = LBi; i <= UBi; ++i) Jwtype(i, j) = 1.0;      // roms_benchmark1.in WTYPE == 1
   avgzeta = new2(); avgu2d = new2(); avgv2d = new2(); avgu3d = new3(1, N); avgv3d = new3(1, N); avgrho = new3(1, N);
   avgw3d = new3(0, N); avgwvel = new3(0, N);
   for (int it = 0; it < c.NT; ++it) avgt[it] = new3(1, N);

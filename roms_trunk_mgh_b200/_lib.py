@@ -21,6 +21,7 @@ class Config(C.Structure):
         ("Akt_bak", C.c_double * 2), ("Akv_bak", C.c_double),
         ("gamma2", C.c_double), ("lambda_", C.c_double), ("hc", C.c_double),
         ("itemp", C.c_int), ("isalt", C.c_int), ("device", C.c_int),
+        ("bv_frequency", C.c_int), ("eos_tderivative", C.c_int), ("solar_source", C.c_int), ("lmd_nonlocal", C.c_int),
     ]
 
 

@@ -86,11 +86,17 @@ namespace {
 
 int alloc_field(roms_b200_state* h, const std::string& name, double** slot, int LBk, int nk) {
   const size_t n = (size_t)h->par.PL * nk;
-  double* base = nullptr;
-  const size_t bytes = ((n * sizeof(double) + 255) / 256) * 256;
-  CK(cudaMalloc(&base, bytes));
-  h->allocs.push_back(base);
-  CK(cudaMemsetAsync(base, 0, n * sizeof(double), h->stream));
+  // Two zeroed guard rows on either side of every field.  Stencil kernels load the operands of clamped neighbours
+  // unconditionally (the values are then discarded), so a row just outside rows LBj..UBj of the first / last plane must be
+  // addressable whatever the surrounding address space looks like -- an address just before a cudaMalloc block is only
+  // mapped by accident (a BENCHMARK3 run faulted in k_uv3dmix2 when the preceding block had been freed).
+  const size_t guard = ((size_t)2 * h->par.P + 31) / 32 * 32;
+  double* raw = nullptr;
+  const size_t bytes = (((n + 2 * guard) * sizeof(double) + 255) / 256) * 256;
+  CK(cudaMalloc(&raw, bytes));
+  h->allocs.push_back(raw);
+  CK(cudaMemsetAsync(raw, 0, (n + 2 * guard) * sizeof(double), h->stream));
+  double* base = raw + guard;
   // element (i,j,k) lives at base[(i-LBi+ioff) + (j-LBj)*P + (k-LBk)*PL]
   *slot = base + h->ioff - h->LBi_dev - (ptrdiff_t)h->b.LBj * h->par.P - (ptrdiff_t)LBk * h->par.PL;
   h->reg[name] = FieldInfo{slot, LBk, nk, base};
@@ -160,7 +166,11 @@ std::vector<std::string> halo_fields(roms_b200_state* h, int phase) {
   const std::string nn = std::to_string(h->nnew), kn = std::to_string(h->knew), kr = std::to_string(h->krhs);
   switch (phase) {
     case ROMS_B200_SET_MASSFLUX: v = {"Huon", "Hvom"}; break;                       // set_massflux.F:177
-    case ROMS_B200_RHO_EOS: v = {"rho", "pden", "rhoA", "rhoS"}; break;             // rho_eos.F:530-553
+    case ROMS_B200_RHO_EOS:                                                         // rho_eos.F:489-526
+      v = {"rho", "pden", "rhoA", "rhoS"};
+      if (h->cfg.bv_frequency) v.push_back("bvf");
+      if (h->cfg.eos_tderivative) { v.push_back("alpha"); v.push_back("beta"); }
+      break;
     case ROMS_B200_SET_VBC: v = {"bustr", "bvstr"}; break;                          // set_vbc.F:664
     case ROMS_B200_ANA_VMIX:
       if (h->cfg.ana_vmix) { v = {"Akv"}; for (int it = 0; it < h->cfg.NT; ++it) v.push_back("Akt_" + std::to_string(it)); }
@@ -621,6 +631,7 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   p.gap_at = 0x7fffffff; p.gap_len = 0;
   p.nonlin_eos = cfg->nonlin_eos; p.curvgrid = cfg->curvgrid; p.uv_qdrag = cfg->uv_qdrag; p.salinity = cfg->salinity;
   p.hadv = cfg->hadv; p.vadv = cfg->vadv; p.itemp = cfg->itemp; p.isalt = cfg->isalt;
+  p.bv_frequency = cfg->bv_frequency; p.eos_tderivative = cfg->eos_tderivative; p.solar_source = cfg->solar_source; p.lmd_nonlocal = cfg->lmd_nonlocal;
   p.dt = cfg->dt; p.g = cfg->g; p.rho0 = cfg->rho0; p.R0 = cfg->R0; p.T0 = cfg->T0; p.S0 = cfg->S0; p.Tcoef = cfg->Tcoef; p.Scoef = cfg->Scoef;
   p.gamma2 = cfg->gamma2; p.lambda = cfg->lambda; p.hc = cfg->hc; p.Akv_bak = cfg->Akv_bak;
   for (int it = 0; it < MAXNT; ++it) p.Akt_bak[it] = cfg->Akt_bak[it];
@@ -666,6 +677,10 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
     rc |= alloc_field(h, "stflux_" + s, &f.stflux[it], 0, 1);
     rc |= alloc_field(h, "btflux_" + s, &f.btflux[it], 0, 1);
   }
+  if (cfg->bv_frequency) rc |= alloc_field(h, "bvf", &f.bvf, 0, N + 1);
+  if (cfg->eos_tderivative) { rc |= alloc_field(h, "alpha", &f.alpha, 0, 1); rc |= alloc_field(h, "beta", &f.beta, 0, 1); }
+  if (cfg->solar_source) { rc |= alloc_field(h, "srflx", &f.srflx, 0, 1); rc |= alloc_field(h, "Jwtype", &f.Jwtype, 0, 1); }
+  if (cfg->lmd_nonlocal) for (int it = 0; it < cfg->NT; ++it) rc |= alloc_field(h, "ghats_" + std::to_string(it), &f.ghats[it], 0, N + 1);
   if (rc) { roms_b200_destroy(h); return FatalError; }
   double* sc = nullptr;
   CKD(cudaMalloc(&sc, 4 * (MAXN + 1) * sizeof(double)));

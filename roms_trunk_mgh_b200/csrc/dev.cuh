@@ -33,6 +33,7 @@ struct Par {
   int iif, kstp, krhs, knew, ptsk, predictor, nfast;
   // options
   int nonlin_eos, curvgrid, uv_qdrag, salinity, hadv, vadv, itemp, isalt;
+  int bv_frequency, eos_tderivative, solar_source, lmd_nonlocal;   // optional terms of rho_eos / pre_step3d (roms_b200_config)
   int fuse_tmix;                  // pre_step3d_t also applies t3dmix2_s (whole-step path only; 0 for single-phase calls)
   // scalars
   double dt, dtfast, g, rho0, R0, T0, S0, Tcoef, Scoef, gamma2, lambda, hc;
@@ -57,6 +58,9 @@ struct Flds {
   double* Akt[MAXNT];
   // scratch
   double* P3;                      // prsgrd32 pressure (1:N)
+  // optional: rho_eos outputs bvf (0:N), alpha, beta; pre_step3d inputs srflx, Jwtype, ghats (0:N)
+  double *bvf, *alpha, *beta, *srflx, *Jwtype;
+  double* ghats[MAXNT];
   // time-averaged fields (mod_average.F; allocated by roms_b200_set_avg)
   double *avgzeta, *avgu2d, *avgv2d, *avgu3d, *avgv3d, *avgrho, *avgw3d, *avgwvel;
   double* avgt[MAXNT];

@@ -28,7 +28,10 @@ __global__ void __launch_bounds__(256) k_set_massflux(Par p, Flds f) {
 // ---------------------------------------------------------------------------------------------------------------
 // rho_eos_tile: nonlinear (ROMS/Nonlinear/rho_eos.F:252-483, coefficients mod_eoscoef.F:24-64) and linear (:696-799).
 // One thread per column, top-down so that the VAR_RHO_2D integrals rhoA/rhoS accumulate in registers.
-__device__ __forceinline__ void eos_nl(double Tt, double Ts, double Tp, double& den, double& den1) {
+// X: also return what BV_FREQUENCY (:402-418) and the expansion coefficients (:290-294, :330-339, :440-462) need
+struct EosX { double bulk, bulk0, bulk1, bulk2, Dden1DS, Dden1DT, DbulkDS, DbulkDT; };
+template <bool X>
+__device__ __forceinline__ void eos_nl(double Tt, double Ts, double Tp, double& den, double& den1, EosX* x = nullptr) {
   const double A00 = +1.909256e+04, A01 = +2.098925e+02, A02 = -3.041638e+00, A03 = -1.852732e-03, A04 = -1.361629e-05;
   const double B00 = +1.044077e+02, B01 = -6.500517e+00, B02 = +1.553190e-01, B03 = +2.326469e-04;
   const double D00 = -5.587545e+00, D01 = +7.390729e-01, D02 = -1.909078e-02;
@@ -59,8 +62,26 @@ __device__ __forceinline__ void eos_nl(double Tt, double Ts, double Tp, double& 
   const double bulk = bulk0 - Tp * (bulk1 - Tp * bulk2);
   const double cff = 1.0 / (bulk + Tpr10);
   den = den1 * bulk * cff;
+  if (X) {
+    const double dC0 = Q01 + Tt * (2.0 * Q02 + Tt * (3.0 * Q03 + Tt * (4.0 * Q04 + Tt * 5.0 * Q05)));
+    const double dC1 = U01 + Tt * (2.0 * U02 + Tt * (3.0 * U03 + Tt * 4.0 * U04));
+    const double dC2 = V01 + Tt * 2.0 * V02;
+    const double dC3 = A01 + Tt * (2.0 * A02 + Tt * (3.0 * A03 + Tt * 4.0 * A04));
+    const double dC4 = B01 + Tt * (2.0 * B02 + Tt * 3.0 * B03);
+    const double dC5 = D01 + Tt * 2.0 * D02;
+    const double dC6 = E01 + Tt * (2.0 * E02 + Tt * 3.0 * E03);
+    const double dC7 = F01 + Tt * 2.0 * F02;
+    const double dC8 = G02 + Tt * 2.0 * G03;
+    const double dC9 = H01 + Tt * 2.0 * H02;
+    x->bulk = bulk; x->bulk0 = bulk0; x->bulk1 = bulk1; x->bulk2 = bulk2;
+    x->Dden1DS = C1 + 1.5 * C2 * sqrtTs + 2.0 * W00 * Ts;
+    x->Dden1DT = dC0 + Ts * (dC1 + sqrtTs * dC2);
+    x->DbulkDS = C4 + sqrtTs * 1.5 * C5 - Tp * (C7 + sqrtTs * 1.5 * G00 - Tp * C9);
+    x->DbulkDT = dC3 + Ts * (dC4 + sqrtTs * dC5) - Tp * (dC6 + Ts * dC7 - Tp * (dC8 + Ts * dC9));
+  }
 }
 
+template <bool X>     // X: with the optional outputs bvf / alpha, beta (BV_FREQUENCY; LMD_SKPP || BULK_FLUXES)
 __global__ void __launch_bounds__(256) k_rho_eos(Par p, Flds f) {
   const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;          // JstrT..JendT = 0..Mm+1
@@ -70,22 +91,56 @@ __global__ void __launch_bounds__(256) k_rho_eos(Par p, Flds f) {
   const double* __restrict__ S = (p.salinity && p.NT >= 2) ? f.t[p.nrhs][p.isalt - 1] : nullptr;
   const double* __restrict__ Hz = f.Hz;
   double rhoA = 0.0, rhoS = 0.0;
+  EosX up; double den1_up = 0.0, den_up_lin = 0.0, zr_up = 0.0;      // level k+1 of the downward march (bvf at W-point k)
   for (int k = p.N; k >= 1; --k) {
     const int o = o2 + k * p.PL;
     double den, pd;
+    EosX cur; double d1c = 0.0;
+    const double zr = f.z_r[o + i];
     if (p.nonlin_eos) {
       const double Tt = dmax(-2.0, T[o + i]);
       const double Ts = S ? dmax(0.0, S[o + i]) : 0.0;
       double d, d1;
-      eos_nl(Tt, Ts, f.z_r[o + i], d, d1);
+      eos_nl<X>(Tt, Ts, zr, d, d1, &cur);
       den = d - 1000.0;
       pd = d1 - 1000.0;
+      d1c = d1;
+      if (X && p.eos_tderivative && k == p.N) {                            // :440-462 (no LMD_DDMIX: level N only)
+        const double Tpr10 = 0.1 * zr;
+        const double cff = cur.bulk + Tpr10;
+        const double cff1 = Tpr10 * d1;
+        const double cff2 = cur.bulk * cff;
+        const double wrk = (den + 1000.0) * cff * cff;
+        const double Tcof = -(cur.DbulkDT * cff1 + cur.Dden1DT * cff2);
+        const double Scof = (cur.DbulkDS * cff1 + cur.Dden1DS * cff2);
+        const double cf = 1.0 / wrk;
+        st_w(f.alpha, o2, i, cf * Tcof, p);
+        st_w(f.beta, o2, i, cf * Scof, p);
+      }
     } else {
       double r = p.R0 - p.R0 * p.Tcoef * (T[o + i] - p.T0);
       if (S) r = r + p.R0 * p.Scoef * (S[o + i] - p.S0);
       r = r - 1000.0;
       den = r; pd = r;
     }
+    if (X && p.bv_frequency && k < p.N) {                                    // bvf at W-point k from levels k+1 (up) and k (dn)
+      double bv;
+      if (p.nonlin_eos) {                                                    // :402-418
+        const double zw = f.z_w[o + i];
+        const double bulk_up = up.bulk0 - zw * (up.bulk1 - up.bulk2 * zw);
+        const double bulk_dn = cur.bulk0 - zw * (cur.bulk1 - cur.bulk2 * zw);
+        const double cff1 = 1.0 / (bulk_up + 0.1 * zw);
+        const double cff2 = 1.0 / (bulk_dn + 0.1 * zw);
+        const double den_up = cff1 * (den1_up * bulk_up);
+        const double den_dn = cff2 * (d1c * bulk_dn);
+        bv = -p.g * (den_up - den_dn) / (0.5 * (den_up + den_dn) * (zr_up - zr));
+      } else {                                                               // :751-758
+        const double gorho0 = p.g / p.rho0;
+        bv = -gorho0 * (den_up_lin - den) / (zr_up - zr);
+      }
+      st_w(f.bvf, o, i, bv, p);
+    }
+    if (X) { up = cur; den1_up = d1c; den_up_lin = den; zr_up = zr; }
     st_w(f.rho, o, i, den, p);
     st_w(f.pden, o, i, pd, p);
     const double hz = Hz[o + i];
@@ -97,6 +152,13 @@ __global__ void __launch_bounds__(256) k_rho_eos(Par p, Flds f) {
   const double cff1 = 1.0 / (f.z_w[o2 + p.N * p.PL + i] - f.z_w[o2 + i]);
   st_w(f.rhoA, o2, i, cff2 * cff1 * rhoA, p);
   st_w(f.rhoS, o2, i, 2.0 * cff1 * cff1 * cff2 * rhoS, p);
+  if (X) {
+    if (p.bv_frequency && p.nonlin_eos) { st_w(f.bvf, o2, i, 0.0, p); st_w(f.bvf, o2 + p.N * p.PL, i, 0.0, p); }   // :414-417
+    if (p.eos_tderivative && !p.nonlin_eos) {                                // :766-773
+      st_w(f.alpha, o2, i, fabs(p.Tcoef), p);
+      st_w(f.beta, o2, i, S ? fabs(p.Scoef) : 0.0, p);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -331,7 +393,11 @@ static inline dim3 g2(const Par& p, dim3 b, int nj, int nz = 1) {
 }
 
 void launch_set_massflux(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_massflux<<<g2(p, b, p.Mm + 2, p.N), b, 0, s>>>(p, f); }
-void launch_rho_eos(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_rho_eos<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
+void launch_rho_eos(const Par& p, const Flds& f, cudaStream_t s) {
+  dim3 b(64, 4);
+  if (p.bv_frequency || p.eos_tderivative) k_rho_eos<true><<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f);
+  else k_rho_eos<false><<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f);
+}
 void launch_set_vbc(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_vbc<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
 void launch_omega(const Par& p, const Flds& f, cudaStream_t s) {
   dim3 b(64, 2);

@@ -12,7 +12,11 @@ namespace rb {
 // MIXS: also apply t3dmix2_s (ROMS/Nonlinear/t3dmix2_s.h:198-301) to t(nnew) in the same pass -- its operands t(nrhs = nstp) at
 // i+-1, j+-1 are already in registers for the advective fluxes, only the four Hz neighbours are extra loads -- so the separate
 // kernel (7 units of traffic) disappears from the time step.  The additions happen in the reference's order.
-template <int HADV, int VADV, bool MIXS>
+// Jerlov water types (mod_scalars.F:1502-1512): reciprocal absorption coefficients and band-1 fraction
+__constant__ double c_lmd_mu1[9] = {0.35, 0.6, 1.0, 1.5, 1.4, 0.42, 0.37, 0.33, 0.00468592};
+__constant__ double c_lmd_mu2[9] = {23.0, 20.0, 17.0, 14.0, 7.9, 5.13, 3.54, 2.34, 1.51};
+__constant__ double c_lmd_r1[9] = {0.58, 0.62, 0.67, 0.77, 0.78, 0.57, 0.57, 0.57, 0.55};
+template <int HADV, int VADV, bool MIXS, bool SRC>     // SRC: with the KPP nonlocal / shortwave source terms of the vertical flux
 #ifndef PRT_PP
 #define PRT_PP false
 #endif
@@ -80,6 +84,18 @@ __global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
     return L;
   };
   const double cff3 = p.dt * (1.0 - p.lambda);
+  // optional terms of the vertical flux FC (benchmark.h): KPP nonlocal transport of the active tracers (:850-865) and, for
+  // temperature, the penetrating shortwave radiation (:312-333 with lmd_swfrac.F:66-80, Zscale = -1; :866-883)
+  const bool nonloc = SRC && p.lmd_nonlocal && itrc < (p.salinity ? 2 : 1);
+  const bool solar = SRC && p.solar_source && itrc == p.itemp - 1;
+  const double* __restrict__ ghats = nonloc ? f.ghats[itrc] : nullptr;
+  double sw_fac1 = 0.0, sw_fac2 = 0.0, sw_fac3 = 0.0, sw_srflx = 0.0, sw_zwN = 0.0;
+  if (solar) {
+    int J = (int)f.Jwtype[o2 + i];
+    J = (J < 1) ? 1 : (J > 9 ? 9 : J);
+    sw_fac1 = -1.0 / c_lmd_mu1[J - 1]; sw_fac2 = -1.0 / c_lmd_mu2[J - 1]; sw_fac3 = c_lmd_r1[J - 1];
+    sw_srflx = f.srflx[o2 + i]; sw_zwN = f.z_w[o2 + N * p.PL + i];
+  }
   double FCm = 0.0;                                   // advective FC(k-1)
   double FDm = p.dt * f.btflx[itrc][o2 + i];          // diffusive FC(k-1), FC(0) = dt*btflx
   double Wm = W[o2 + i];                              // W(k-1)
@@ -103,6 +119,12 @@ __global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
     if (k < N) {
       const double c = 1.0 / (cur.zr1 - zrk);
       FDk = cff3 * c * cur.akt * (tkp1 - tk);
+      if (SRC && nonloc) FDk = FDk - p.dt * cur.akt * ghats[o + i];
+      if (SRC && solar) {
+        const double Z = sw_zwN - f.z_w[o + i];
+        const double swdk = exp(Z * sw_fac1) * sw_fac3 + exp(Z * sw_fac2) * (1.0 - sw_fac3);
+        FDk = FDk + p.dt * sw_srflx * swdk;
+      }
     } else {
       FDk = p.dt * f.stflx[itrc][o2 + i];
     }
@@ -427,25 +449,29 @@ __global__ void __launch_bounds__(128) k_t3dmix2_s(Par p, Flds f) {
 // ---------------------------------------------------------------------------------------------------------------
 static inline dim3 g2(const Par& p, dim3 b, int ni, int nj, int nz = 1) { return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz); }
 
-template <int H>
+template <int H, bool SRC>
 static void launch_pre_t_v(const Par& p, const Flds& f, cudaStream_t s) {
   dim3 b(64, 2); dim3 g = g2(p, b, xspan(p), p.Mm);
   g.x *= p.NT;
   if (p.fuse_tmix) {
-    if (p.vadv == 0) k_pre_step3d_t<H, 0, true><<<g, b, 0, s>>>(p, f);
-    else if (p.vadv == 1) k_pre_step3d_t<H, 1, true><<<g, b, 0, s>>>(p, f);
-    else k_pre_step3d_t<H, 2, true><<<g, b, 0, s>>>(p, f);
+    if (p.vadv == 0) k_pre_step3d_t<H, 0, true, SRC><<<g, b, 0, s>>>(p, f);
+    else if (p.vadv == 1) k_pre_step3d_t<H, 1, true, SRC><<<g, b, 0, s>>>(p, f);
+    else k_pre_step3d_t<H, 2, true, SRC><<<g, b, 0, s>>>(p, f);
     return;
   }
-  if (p.vadv == 0) k_pre_step3d_t<H, 0, false><<<g, b, 0, s>>>(p, f);
-  else if (p.vadv == 1) k_pre_step3d_t<H, 1, false><<<g, b, 0, s>>>(p, f);
-  else k_pre_step3d_t<H, 2, false><<<g, b, 0, s>>>(p, f);
+  if (p.vadv == 0) k_pre_step3d_t<H, 0, false, SRC><<<g, b, 0, s>>>(p, f);
+  else if (p.vadv == 1) k_pre_step3d_t<H, 1, false, SRC><<<g, b, 0, s>>>(p, f);
+  else k_pre_step3d_t<H, 2, false, SRC><<<g, b, 0, s>>>(p, f);
+}
+template <int H>
+static void launch_pre_t_h(const Par& p, const Flds& f, cudaStream_t s) {
+  if (p.solar_source || p.lmd_nonlocal) launch_pre_t_v<H, true>(p, f, s); else launch_pre_t_v<H, false>(p, f, s);
 }
 void launch_pre_step3d_t(const Par& p, const Flds& f, cudaStream_t s) {
-  if (p.hadv == 0) launch_pre_t_v<0>(p, f, s);
-  else if (p.hadv == 1) launch_pre_t_v<1>(p, f, s);
-  else if (p.hadv == 2) launch_pre_t_v<2>(p, f, s);
-  else launch_pre_t_v<3>(p, f, s);
+  if (p.hadv == 0) launch_pre_t_h<0>(p, f, s);
+  else if (p.hadv == 1) launch_pre_t_h<1>(p, f, s);
+  else if (p.hadv == 2) launch_pre_t_h<2>(p, f, s);
+  else launch_pre_t_h<3>(p, f, s);
 }
 void launch_pre_step3d_uv(const Par& p, const Flds& f, cudaStream_t s) {
   dim3 b(64, 2);

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(128, UVM_MINB) k_uv3dmix2(Par p, Flds f) {
   auto p2 = [&](int c) -> P2 {
     return P2{f.pmon_p[c], f.pnom_p[c], pn[c - P] + pn[c], pn[c - P - 1] + pn[c - 1], pm[c - 1] + pm[c], pm[c - P - 1] + pm[c - P]};
   };
-  const R2 R0 = r2(o2), RW = r2(o2 - 1), RS = r2(o2 - P);
+  const R2 R0 = r2(o2), RW = r2(o2 - 1), RS = r2(dov ? o2 - P : o2);      // (the southern cell's factors read row j-2: only where v exists)
   const P2 Q0 = p2(o2), QN = p2(o2 + P), QE = p2(o2 + 1);
   auto rho_cff = [](const R2& m, double hz, double uE, double u0, double vN, double v0) -> double {
     return hz * 0.5 * (m.pmon * (m.pnE * uE - m.pnW * u0) - m.pnom * (m.pmN * vN - m.pmS * v0));

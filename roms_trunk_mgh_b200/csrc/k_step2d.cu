@@ -63,6 +63,13 @@ __device__ __forceinline__ double lds_pol(const double* a, unsigned long long po
 #else
 #define lds_(a) (*(a))
 #endif
+// Time-varying 2-D fields.  In the exchange instance the ghost columns of these arrays are written by this very kernel (the pull
+// below, through x.recvf) before they are read, so the reads must neither be declared __restrict__ / const (eligible for the
+// read-only ld.global.nc path) nor be served from a stale L1 line: they go to L2 (ld.global.cg).  The single-tile instance
+// keeps the plain cached loads.
+template <bool XCH>
+__device__ __forceinline__ double ldt(const double* a) { return XCH ? __ldcg(a) : *a; }
+
 template <bool XCH>      // XCH: with the fused halo exchange (multi-GPU peer path); the single-tile instance carries none of it
 __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x) {
 #if S2D_EVICT
@@ -95,8 +102,8 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
   const bool FIRST = (p.iif == 1);
   const bool active = (p.iif <= p.nfast);                              // :755 (the nfast+1-th call only averages)
   const double* __restrict__ h = f.h;
-  const double* __restrict__ zr = f.zeta[p.krhs];
-  const double* __restrict__ zs = f.zeta[p.kstp];
+  const double* zr = f.zeta[p.krhs];
+  const double* zs = f.zeta[p.kstp];
   const double* __restrict__ pm = f.pm;
   const double* __restrict__ pn = f.pn;
 
@@ -146,12 +153,12 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
   // stage 0, so that the CTA pays one DRAM latency for both.
   const bool okA = active && tid < TX * ZH + ZH && (j0 - 1 + zb) >= 1 && (j0 - 1 + zb) <= Mm && (i0 - 1 + za) <= p.Iend;
   const int qA = okA ? (j0 - 1 + zb) * P + (i0 - 1 + za) : (j0 * P + i0);
-  const double zs_q = zs[qA], zr_q = zr[qA], pm_q = lds_(pm + qA), pn_q = lds_(pn + qA), h_q = lds_(h + qA), rS = lds_(f.rhoS + qA), rA = lds_(f.rhoA + qA);
+  const double zs_q = ldt<XCH>(zs + qA), zr_q = ldt<XCH>(zr + qA), pm_q = lds_(pm + qA), pn_q = lds_(pn + qA), h_q = lds_(h + qA), rS = lds_(f.rhoS + qA), rA = lds_(f.rhoA + qA);
   const double fomn_q = lds_(f.fomn + qA), visc_q = lds_(f.visc2_r + qA), pmon_q = lds_(f.pmon_r + qA), pnom_q = lds_(f.pnom_r + qA);
   const double pnE_a = lds_(pn + qA + 1), pnW_a = lds_(pn + qA - 1), pmN_a = lds_(pm + qA + P), pmS_a = lds_(pm + qA - P), onr = lds_(f.on_r + qA), omr = lds_(f.om_r + qA);
   double dndx_q = 0.0, dmde_q = 0.0, rz_s = 0.0, rz_p = 0.0;
   if (p.curvgrid) { dndx_q = lds_(f.dndx + qA); dmde_q = lds_(f.dmde + qA); }
-  if (!FIRST && !PRED) { rz_s = f.rzeta[p.kstp][qA]; rz_p = f.rzeta[p.ptsk][qA]; }
+  if (!FIRST && !PRED) { rz_s = ldt<XCH>(f.rzeta[p.kstp] + qA); rz_p = ldt<XCH>(f.rzeta[p.ptsk] + qA); }
 #if S2D_PF
   // L2 prefetch of the operands of stages 2b and 3 (18 arrays x TY rows x two 128-byte lines, one request per thread): no
   // register cost, and the loads issued two barriers later find their lines in L2.
@@ -172,8 +179,8 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
 #endif
   // ---- stages 0/1: Drhs, ubar, vbar, DUon, DVom on the staged region (two items per thread, loads first)
   {
-    const double* __restrict__ ur = f.ubar[p.krhs];
-    const double* __restrict__ vr = f.vbar[p.krhs];
+    const double* ur = f.ubar[p.krhs];
+    const double* vr = f.vbar[p.krhs];
     double zv[2], hv[2], uv[2], vv[2], onu[2], omv[2];
     bool ok[2];
 #pragma unroll
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
       const int i = i0 - HL + a, j = j0 - HL + b;
       ok[r] = (s < NS) && i >= p.LBi && i <= p.UBi && j >= 0 && j <= Mm + 1;
       const int q = ok[r] ? (j * P + i) : (j0 * P + i0);               // safe dummy address
-      zv[r] = zr[q]; hv[r] = lds_(h + q); uv[r] = ur[q]; vv[r] = vr[q]; onu[r] = lds_(f.on_u + q); omv[r] = lds_(f.om_v + q);
+      zv[r] = ldt<XCH>(zr + q); hv[r] = lds_(h + q); uv[r] = ldt<XCH>(ur + q); vv[r] = ldt<XCH>(vr + q); onu[r] = lds_(f.on_u + q); omv[r] = lds_(f.om_v + q);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
   const bool dov = inner && (j >= p.JstrV);
   const int oS = (j >= 1) ? o - P : o;                                  // row j-1 (clamped so the loads stay in bounds)
   // all global operands of this stage, issued back to back
-  const double zr_o = zr[o];
+  const double zr_o = ldt<XCH>(zr + o);
   const double av_du2 = f.DU_avg2[o], av_dv2 = f.DV_avg2[o];
   double av_zt = 0.0, av_du1 = 0.0, av_dv1 = 0.0;
   if (PRED && !FIRST) { av_zt = f.Zt_avg1[o]; av_du1 = f.DU_avg1[o]; av_dv1 = f.DV_avg1[o]; }
@@ -381,7 +388,7 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
   const double rA0 = lds_(f.rhoA + o), rAW = lds_(f.rhoA + o - 1), rAS = lds_(f.rhoA + oS);
   const double pm0 = lds_(pm + o), pmW = lds_(pm + o - 1), pmS = lds_(pm + oS), pn0 = lds_(pn + o), pnW = lds_(pn + o - 1), pnS = lds_(pn + oS);
   const double onu = lds_(f.on_u + o), omv = lds_(f.om_v + o);
-  const double zs0 = zs[o], zsW = zs[o - 1], zsS = zs[oS];
+  const double zs0 = ldt<XCH>(zs + o), zsW = ldt<XCH>(zs + o - 1), zsS = ldt<XCH>(zs + oS);
   const double us = f.ubar[p.kstp][o], vs = f.vbar[p.kstp][o];
   const double rufrc_o = lds_(f.rufrc + o), rvfrc_o = lds_(f.rvfrc + o);
   double rub_s = 0.0, rub_p = 0.0, rvb_s = 0.0, rvb_p = 0.0, ru_n = 0.0, ru_so = 0.0, rv_n = 0.0, rv_so = 0.0;

@@ -58,19 +58,13 @@ class Tile:
 
     # ---- data movement -------------------------------------------------------------------------------------
     def nk_of(self, name):
-        """Number of vertical planes of a field: 1 (2-D), N (rho/u/v levels) or N+1 (W levels 0:N)."""
+        """Number of vertical planes of a field: 1 (2-D), N (rho/u/v levels) or N+1 (W levels 0:N) -- roms_b200_field_levels."""
         if not hasattr(self, "_nk"):
-            n2, n3 = field_names(self.NT)
-            self._nk = {n: 1 for n in n2}
-            for n in n3:
-                wlev = n in ("W", "wvel", "z_w", "Akv", "ru1", "ru2", "rv1", "rv2") or n.startswith("Akt_")
-                self._nk[n] = self.N + 1 if wlev else self.N
-            for n in ("avgzeta", "avgu2d", "avgv2d"):
-                self._nk[n] = 1
-            for n in ["avgu3d", "avgv3d", "avgrho"] + [f"avgt_{it}" for it in range(self.NT)]:
-                self._nk[n] = self.N
-            for n in ("avgw3d", "avgwvel"):
-                self._nk[n] = self.N + 1
+            self._nk = {}
+        if name not in self._nk:
+            lbk, nk = C.c_int(), C.c_int()
+            self._ck(f"field_levels({name})", self.L.roms_b200_field_levels(self.h, name.encode(), C.byref(lbk), C.byref(nk)))
+            self._nk[name] = nk.value
         return self._nk[name]
 
     def set(self, name, arr):

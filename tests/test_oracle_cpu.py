@@ -422,6 +422,31 @@ def test_physics_kat_baroclinic_pressure_gradient_shear():
     assert abs(shear / exact - 1.0) < 0.01, (shear, exact)   # measured 0.17 %
 
 
+def test_oracle_eos_derived_quantities():
+    """rho_eos.F:402-462: with the nonlinear EOS the Brunt-Vaisala frequency of the stably stratified BENCHMARK initial state is
+    positive and of oceanic magnitude, and alpha, beta agree with centred finite differences of the oracle's own in-situ density
+    at the surface level (a check of the derivative polynomials against the polynomial itself); the linear EOS returns
+    |Tcoef|, |Scoef| and the textbook N^2 = -g/rho0 drho/dz."""
+    o = orc.Oracle(orc.APP_BENCHMARK, Lm=32, Mm=16, N=10, bv_frequency=1, eos_tderivative=1)
+    o.run_phase("set_data"); o.run_phase("ini"); o.run_phase("rho_eos")
+    bvf = o.field("bvf")[1:-1, 1:-1, 3:35]
+    assert bvf.min() > 0 and 1e-7 < bvf.max() < 1e-3
+    al, be = o.field("alpha")[0, 8, 10], o.field("beta")[0, 8, 10]
+    T, S, z = o.field("t1_0")[-1, 8, 10], o.field("t1_1")[-1, 8, 10], o.field("z_r")[-1, 8, 10]
+    dT, dS = 1e-4, 1e-4
+    r0 = orc.eos_point(T, S, z)[0]
+    a_fd = -(orc.eos_point(T + dT, S, z)[0] - orc.eos_point(T - dT, S, z)[0]) / (2 * dT) / r0
+    b_fd = (orc.eos_point(T, S + dS, z)[0] - orc.eos_point(T, S - dS, z)[0]) / (2 * dS) / r0
+    assert abs(al / a_fd - 1) < 1e-6 and abs(be / b_fd - 1) < 1e-6, (al, a_fd, be, b_fd)
+    ol = orc.Oracle(orc.APP_BENCHMARK, Lm=32, Mm=16, N=10, nonlin_eos=0, bv_frequency=1, eos_tderivative=1)
+    ol.run_phase("set_data"); ol.run_phase("ini"); ol.run_phase("rho_eos")
+    assert ol.field("alpha")[0, 8, 10] == abs(ol.opt("Tcoef")) and ol.field("beta")[0, 8, 10] == abs(ol.opt("Scoef"))
+    rho, zr = ol.field("rho"), ol.field("z_r")
+    k = 5
+    n2 = -ol.opt("g") / ol.opt("rho0") * (rho[k, 8, 10] - rho[k - 1, 8, 10]) / (zr[k, 8, 10] - zr[k - 1, 8, 10])
+    assert abs(ol.field("bvf")[k, 8, 10] / n2 - 1) < 1e-12
+
+
 def test_oracle_set_avg_windows():
     """set_avg.F restatement: with nAVG = 3 the average that closes at step 3k+1 equals the mean of the three zeta(kstp) fields
     the calls of that window saw; a constant tracer averages to itself; nAVG = 1 reproduces the instantaneous field."""
