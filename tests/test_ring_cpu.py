@@ -112,3 +112,72 @@ def test_fused_exchange_protocol_model(world):
         assert _simulate_fused_exchange(world, K=9, R=5, S=2, seed=seed) == "ok"      # two slots are already enough
     # the model is able to see the hazard: with a single slot some interleaving overwrites unconsumed data
     assert any(_simulate_fused_exchange(world, K=9, R=5, S=1, seed=seed) == "overwritten" for seed in range(150))
+
+
+# ---- model of the persistent barotropic-loop kernel's ordering (csrc/k_step2d_loop.cu) ------------------------------------
+def _simulate_loop_kernel(nbx, nby, nfast, seed, wait_for_neighbours=True):
+    """CTAs of a nbx x nby grid each own one tile for the whole LOOP_2D.  Call c of a CTA READS, at its start, levels krhs(c) and
+    kstp(c) of zeta/ubar/vbar on its own tile and on its 8 neighbours (halo), and WRITES level knew(c) of its own tile at its
+    end.  The kernel's rule: a CTA starts call c once every neighbour has published call c-1.  The model runs the CTAs under a
+    random scheduler (reads and writes of one call are separate events), tags every tile/level with the call that wrote it,
+    and checks that each read sees exactly the version a sequential run sees (RAW) -- which also fails if a neighbour has
+    already overwritten the level with a later call (WAR)."""
+    rng = random.Random(seed)
+    # the 2-D time indices of LOOP_2D (main3d.F:592-700), starting with indx1 = 1
+    calls, indx1, pred = [], 1, False
+    for my_iif in range(1, nfast + 2):
+        nxt = 3 - indx1
+        if not pred:
+            pred, iif = True, my_iif
+            kstp, knew, krhs = (indx1 if iif == 1 else 3 - indx1), 3, indx1
+        calls.append((krhs, kstp, knew))
+        if pred:
+            pred, knew = False, nxt
+            kstp, krhs = 3 - knew, 3
+            if iif < nfast + 1:
+                indx1 = nxt
+        if iif < nfast + 1:
+            calls.append((krhs, kstp, knew))
+    ncall = len(calls)
+    tiles = [(x, y) for y in range(nby) for x in range(nbx)]
+    nbrs = {t: [((t[0] + dx) % nbx, t[1] + dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1)
+                if 0 <= t[1] + dy < nby and ((t[0] + dx) % nbx, t[1] + dy) != t] for t in tiles}
+    # sequential reference: version of (tile, level) seen by call c = last call < c that wrote that level (0 = initial state)
+    expect, last = [], {1: 0, 2: 0, 3: 0}
+    for c, (krhs, kstp, knew) in enumerate(calls, start=1):
+        expect.append((last[krhs], last[kstp]))
+        last[knew] = c
+    ver = {t: {1: 0, 2: 0, 3: 0} for t in tiles}
+    done = {t: 0 for t in tiles}                  # published completion flag
+    phase = {t: "idle" for t in tiles}            # idle -> read done ("busy") -> written + published
+    cur = {t: 1 for t in tiles}
+    while any(cur[t] <= ncall for t in tiles):
+        ready = [t for t in tiles if cur[t] <= ncall and
+                 (phase[t] == "busy" or not wait_for_neighbours or all(done[n] >= cur[t] - 1 for n in nbrs[t]))]
+        if not ready:
+            return "deadlock"
+        t = rng.choice(ready)
+        c = cur[t]
+        krhs, kstp, knew = calls[c - 1]
+        if phase[t] == "idle":
+            for n in nbrs[t] + [t]:
+                if (ver[n][krhs], ver[n][kstp]) != expect[c - 1]:
+                    return "stale-or-overwritten"
+            phase[t] = "busy"
+        else:
+            ver[t][knew] = c
+            done[t] = c
+            cur[t] += 1
+            phase[t] = "idle"
+    return "ok"
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 2), (4, 3), (8, 4)])
+def test_loop_kernel_neighbour_flag_ordering_model(shape):
+    import random as _r
+    globals()["random"] = _r
+    for seed in range(60):
+        assert _simulate_loop_kernel(shape[0], shape[1], nfast=6, seed=seed) == "ok"
+    if shape != (1, 1):
+        # the model sees the hazards: without the neighbour wait some interleaving reads a stale or already overwritten level
+        assert any(_simulate_loop_kernel(shape[0], shape[1], nfast=6, seed=seed, wait_for_neighbours=False) != "ok" for seed in range(60))
