@@ -84,8 +84,10 @@ void make_bounds(int Lm, int Mm, int NtileI, int NtileJ, int tile, bool distribu
 
 namespace {
 
-int alloc_field(roms_b200_state* h, const std::string& name, double** slot, int LBk, int nk) {
-  const size_t n = (size_t)h->par.PL * nk;
+// Device storage of one registered field (guard rows included); sets *fi.slot.
+int materialize(roms_b200_state* h, FieldInfo& fi) {
+  if (fi.base) return NoError;
+  const size_t n = (size_t)h->par.PL * fi.nk;
   // Two zeroed guard rows on either side of every field.  Stencil kernels load the operands of clamped neighbours
   // unconditionally (the values are then discarded), so a row just outside rows LBj..UBj of the first / last plane must be
   // addressable whatever the surrounding address space looks like -- an address just before a cudaMalloc block is only
@@ -96,10 +98,20 @@ int alloc_field(roms_b200_state* h, const std::string& name, double** slot, int 
   CK(cudaMalloc(&raw, bytes));
   h->allocs.push_back(raw);
   CK(cudaMemsetAsync(raw, 0, (n + 2 * guard) * sizeof(double), h->stream));
-  double* base = raw + guard;
+  fi.base = raw + guard;
   // element (i,j,k) lives at base[(i-LBi+ioff) + (j-LBj)*P + (k-LBk)*PL]
-  *slot = base + h->ioff - h->LBi_dev - (ptrdiff_t)h->b.LBj * h->par.P - (ptrdiff_t)LBk * h->par.PL;
-  h->reg[name] = FieldInfo{slot, LBk, nk, base};
+  *fi.slot = fi.base + h->ioff - h->LBi_dev - (ptrdiff_t)h->b.LBj * h->par.P - (ptrdiff_t)fi.LBk * h->par.PL;
+  return NoError;
+}
+
+// Register a field.  Normally its storage is allocated at once; a handle created for ONE per-routine call (api_tile.cu) is
+// `lazy`: a field gets storage when the caller hands it over (roms_b200_set_field) -- a routine's published argument list is
+// everything it touches -- so a _tile call on BENCHMARK3 allocates the routine's 5-50 arrays instead of the whole 5 GB state.
+int alloc_field(roms_b200_state* h, const std::string& name, double** slot, int LBk, int nk) {
+  *slot = nullptr;
+  FieldInfo fi{slot, LBk, nk, nullptr};
+  if (!h->lazy || name == "P3") { const int rc = materialize(h, fi); if (rc) return rc; }
+  h->reg[name] = fi;
   return NoError;
 }
 
@@ -322,7 +334,22 @@ int try_step2d_loop_kernel(roms_b200_state* h) {
   return NoError;
 }
 
+// Lazy handles (per-routine calls): the optional arrays of a routine that the caller did not hand over still need storage --
+// rho_eos writes bvf / alpha / beta, pre_step3d reads srflx / Jwtype / ghats (zeros: no shortwave, no nonlocal transport).
+int ensure_optional(roms_b200_state* h, int phase) {
+  if (!h->lazy) return NoError;
+  std::vector<std::string> names;
+  if (phase == ROMS_B200_RHO_EOS) names = {"bvf", "alpha", "beta"};
+  else if (phase == ROMS_B200_PRE_STEP3D) { names = {"srflx", "Jwtype"}; for (int it = 0; it < h->cfg.NT; ++it) names.push_back("ghats_" + std::to_string(it)); }
+  for (const std::string& n : names) {
+    auto it = h->reg.find(n);
+    if (it != h->reg.end()) { const int rc = materialize(h, it->second); if (rc) return rc; }
+  }
+  return NoError;
+}
+
 int run_phase_async(roms_b200_state* h, int phase) {
+  { const int rc = ensure_optional(h, phase); if (rc) return rc; }
   fill_par(h);
   const Par& p = h->par; const Flds& f = h->fl; cudaStream_t s = h->stream;
   PhaseTimer pt(h, phase);
@@ -585,7 +612,11 @@ int roms_b200_bounds(int Lm, int Mm, int NtileI, int NtileJ, int tile, int distr
   return NoError;
 }
 
-int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
+static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool lazy);
+int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) { return create_impl(cfg, out, false); }
+// internal (api_tile.cu): a handle whose fields get device storage when they are first uploaded
+int roms_b200_create_lazy_(const roms_b200_config* cfg, roms_b200_handle* out) { return create_impl(cfg, out, true); }
+static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool lazy) {
   if (!cfg || !out) return InputError;
   *out = nullptr;
   if (cfg->N < 4 || cfg->N > MAXN || cfg->NT < 1 || cfg->NT > MAXNT || cfg->Lm < 8 || cfg->Mm < 4) return ConfigError;
@@ -597,6 +628,7 @@ int roms_b200_create(const roms_b200_config* cfg, roms_b200_handle* out) {
   }
   CK(cudaSetDevice(cfg->device));
   roms_b200_state* h = new roms_b200_state();
+  h->lazy = lazy;
 #define CKD(call)                                                                                        \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \
@@ -741,10 +773,11 @@ static int xfer(roms_b200_handle h, const char* name, double* host, size_t n, bo
   if (!h || !name || !host) return InputError;
   auto it = h->reg.find(name);
   if (it == h->reg.end()) { std::fprintf(stderr, "roms_b200: unknown field '%s'\n", name); return InputError; }
-  const FieldInfo& fi = it->second;
+  FieldInfo& fi = it->second;
   const size_t want = (size_t)h->ni * h->nj * fi.nk;
   if (n != want) { std::fprintf(stderr, "roms_b200: field '%s' expects %zu doubles, got %zu\n", name, want, n); return InputError; }
   CK(cudaSetDevice(h->cfg.device));
+  if (!fi.base) { if (!up) return InputError; const int rc = materialize(h, fi); if (rc) return rc; }   // lazy handle: first hand-over
   double* dev = fi.base + h->ioff + (h->b.LBi - h->LBi_dev);
   const size_t dp = (size_t)h->par.P * sizeof(double), sp = (size_t)h->ni * sizeof(double);
   if (up) CK(cudaMemcpy2DAsync(dev, dp, host, sp, sp, (size_t)h->nj * fi.nk, cudaMemcpyHostToDevice, h->stream));

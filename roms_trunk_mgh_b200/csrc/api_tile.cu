@@ -6,6 +6,8 @@
 #include <vector>
 #include "../../include/roms_b200.h"
 
+extern "C" int roms_b200_create_lazy_(const roms_b200_config* cfg, roms_b200_handle* out);   // api.cu
+
 namespace {
 
 struct Tmp {
@@ -18,7 +20,7 @@ struct Tmp {
     // a _tile call computes the whole xi-column of tiles; with NtileJ > 1 a host would call it once per Jtile and the
     // read-modify-write routines would be applied NtileJ times: the per-routine form needs NtileJ == 1
     if (b->cfg.NtileJ != 1) { rc = 5; return; }
-    rc = roms_b200_create(&b->cfg, &h);
+    rc = roms_b200_create_lazy_(&b->cfg, &h);          // only the arrays handed over get device storage
     if (rc) return;
     int ab[4];
     roms_b200_array_bounds(h, ab);
@@ -48,6 +50,7 @@ int roms_b200_rho_eos_tile(const roms_b200_tile_t* b, const double* Hz, const do
   T.up("Hz", Hz, N); T.up("z_r", z_r, N); T.up("z_w", z_w, N + 1);
   T.up("t" + tl + "_" + std::to_string(b->cfg.itemp - 1), t, N);
   if (s && b->cfg.NT >= 2) T.up("t" + tl + "_" + std::to_string(b->cfg.isalt - 1), s, N);
+  T.up("rhoA", rhoA, 1); T.up("rhoS", rhoS, 1); T.up("pden", pden, N); T.up("rho", rho, N);     // untouched elements are preserved
   T.run(ROMS_B200_RHO_EOS);
   T.down("rhoA", rhoA, 1); T.down("rhoS", rhoS, 1); T.down("pden", pden, N); T.down("rho", rho, N);
   return T.rc;

@@ -30,6 +30,7 @@ struct roms_b200_state {
   rbi::Bounds b;          // the reference's bounds of this tile (host-facing array extents LBi:UBi, LBj:UBj)
   rb::Par par;
   rb::Flds fl;
+  bool lazy = false;      // fields get device storage on their first upload (per-routine _tile calls, api_tile.cu)
   int itile = 0;          // the xi-column of tiles this handle owns (cfg.tile % cfg.NtileI)
   int ni, nj, ioff;       // host array extents; device origin shift
   int LBi_dev, ni_dev;    // device arrays carry 3 west ghost columns on every tile (the fused step2d kernel needs Drhs(i-3))
