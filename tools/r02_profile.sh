@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round-2 evidence run on one B200: plain bench first (must exit 0), then the ncu passes of B200_PROFILING.md.
 set -x
+python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -2 gpurun_out/r02_pytest_gpu.log
 python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err || exit 1
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err
 B="python bench.py --steps 2 --warmup 3 --spinup 2 --no-cpu --no-extras"
