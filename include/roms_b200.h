@@ -67,6 +67,14 @@ typedef struct roms_b200_config {
   int eos_tderivative;          /* LMD_SKPP || BULK_FLUXES: rho_eos also returns "alpha", "beta" (:420-462 / :760-773) */
   int solar_source;             /* SOLAR_SOURCE: shortwave penetration in pre_step3d (:312-333, :866-883; lmd_swfrac.F) */
   int lmd_nonlocal;             /* LMD_NONLOCAL: KPP nonlocal transport in pre_step3d (:850-865)                       */
+  /* The parameterisations themselves, on the device (main3d.F:384-390, :467).  bulk_fluxes: the host uploads the atmosphere
+   * "Uwind","Vwind","Tair","Pair","Hair","rain","cloud","srflx" (FORCES, bulk_flux.F:100-125) and ROMS_B200_BULK_FLUX returns
+   * "lrflx","lhflx","shflx","stflux_<itemp-1>","sustr","svstr".  lmd_mixing: ROMS_B200_LMD_VMIX (lmd_vmix.F with LMD_RIMIX,
+   * LMD_CONVEC, LMD_SKPP, LMD_NONLOCAL, RI_SPLINES) returns "Akv","Akt_<itrc>","ghats_<itrc>","hsbl","ksbl" (ksbl as whole
+   * doubles; the reference holds INTEGERs); it needs bv_frequency, eos_tderivative, solar_source and lmd_nonlocal set.        */
+  int bulk_fluxes;              /* BULK_FLUXES + LONGWAVE (bulk_flux.F:381-948)                                        */
+  int lmd_mixing;               /* LMD_MIXING (lmd_vmix.F:100-659, lmd_skpp.F:246-923, lmd_swfrac.F)                   */
+  double blk_ZQ, blk_ZT, blk_ZW;/* BLK_ZQ, BLK_ZT, BLK_ZW (m): heights of the humidity / temperature / wind data       */
 } roms_b200_config;
 
 /* Fills *cfg with the shipped defaults of roms_<app>.in (Lm,Mm,N = 0 keeps the shipped grid size). */
@@ -120,7 +128,9 @@ enum {
   ROMS_B200_STEP3D_UV = 15,    /* step3d_uv.F:111        */  ROMS_B200_OMEGA2 = 16,      /* main3d.F:789           */
   ROMS_B200_STEP3D_T = 17,     /* step3d_t.F:108         */  ROMS_B200_DIAG = 18,        /* diag.F:80              */
   ROMS_B200_SET_DATA = 19,     /* (host forcing; no-op)  */  ROMS_B200_STEP2D_LOOP = 20, /* main3d.F:592-700       */
-  ROMS_B200_SET_AVG = 22       /* set_avg.F:128          */
+  ROMS_B200_SET_AVG = 22,      /* set_avg.F:128          */
+  ROMS_B200_BULK_FLUX = 23,    /* bulk_flux.F:59         */
+  ROMS_B200_LMD_VMIX = 24      /* lmd_vmix.F:33 (lmd_vmix_tile, lmd_skpp, lmd_finish) */
 };
 int roms_b200_run_phase(roms_b200_handle h, int phase);
 

@@ -16,11 +16,13 @@ bool lookup(Model& m, const std::string& name, double** p, int dims[6]) {
   static const char* n2[] = {"h", "f", "pm", "pn", "om_r", "on_r", "om_u", "on_u", "om_v", "on_v", "om_p", "on_p", "omn", "fomn", "pmon_r", "pnom_r",
                              "pmon_u", "pnom_u", "pmon_v", "pnom_v", "pmon_p", "pnom_p", "dndx", "dmde", "rdrag", "rdrag2", "visc2_r", "visc2_p",
                              "Zt_avg1", "DU_avg1", "DU_avg2", "DV_avg1", "DV_avg2", "rufrc", "rvfrc", "rhoA", "rhoS", "sustr", "svstr", "bustr", "bvstr",
-                             "avgzeta", "avgu2d", "avgv2d", "alpha", "beta", "srflx", "Jwtype"};
+                             "avgzeta", "avgu2d", "avgv2d", "alpha", "beta", "srflx", "Jwtype",
+                             "Uwind", "Vwind", "Tair", "Pair", "Hair", "rain", "cloud", "lrflx", "lhflx", "shflx", "hsbl", "ksbl", "latr", "lonr"};
   F2* a2[] = {&m.h, &m.f, &m.pm, &m.pn, &m.om_r, &m.on_r, &m.om_u, &m.on_u, &m.om_v, &m.on_v, &m.om_p, &m.on_p, &m.omn, &m.fomn, &m.pmon_r, &m.pnom_r,
               &m.pmon_u, &m.pnom_u, &m.pmon_v, &m.pnom_v, &m.pmon_p, &m.pnom_p, &m.dndx, &m.dmde, &m.rdrag, &m.rdrag2, &m.visc2_r, &m.visc2_p,
               &m.Zt_avg1, &m.DU_avg1, &m.DU_avg2, &m.DV_avg1, &m.DV_avg2, &m.rufrc, &m.rvfrc, &m.rhoA, &m.rhoS, &m.sustr, &m.svstr, &m.bustr, &m.bvstr,
-              &m.avgzeta, &m.avgu2d, &m.avgv2d, &m.alpha, &m.beta, &m.srflx, &m.Jwtype};
+              &m.avgzeta, &m.avgu2d, &m.avgv2d, &m.alpha, &m.beta, &m.srflx, &m.Jwtype,
+              &m.Uwind, &m.Vwind, &m.Tair, &m.Pair, &m.Hair, &m.rain, &m.cloud, &m.lrflx, &m.lhflx, &m.shflx, &m.hsbl, &m.ksbl, &m.latr, &m.lonr};
   for (size_t i = 0; i < sizeof(n2) / sizeof(n2[0]); ++i) if (name == n2[i]) return set2(*a2[i]);
   static const char* n3[] = {"rho", "pden", "Hz", "z_r", "Huon", "Hvom", "W", "wvel", "z_w", "Akv", "avgu3d", "avgv3d", "avgrho", "avgw3d", "avgwvel", "bvf"};
   F3* a3[] = {&m.rho, &m.pden, &m.Hz, &m.z_r, &m.Huon, &m.Hvom, &m.W, &m.wvel, &m.z_w, &m.Akv, &m.avgu3d, &m.avgv3d, &m.avgrho, &m.avgw3d, &m.avgwvel, &m.bvf};
@@ -89,6 +91,7 @@ int orc_set_option(void* hp, const char* key, double val) {
   else if (k == "bv_frequency") c.bv_frequency = (int)val; else if (k == "eos_tderivative") c.eos_tderivative = (int)val;
   else if (k == "solar_source") c.solar_source = (int)val; else if (k == "lmd_nonlocal") c.lmd_nonlocal = (int)val;
   else if (k == "nAVG") c.nAVG = (int)val; else if (k == "ntsAVG") c.ntsAVG = (int)val;
+  else if (k == "bulk_fluxes") c.bulk_fluxes = (int)val; else if (k == "lmd_mixing") c.lmd_mixing = (int)val;
   else return 1;
   return 0;
 }
@@ -105,6 +108,8 @@ double orc_get_option(void* hp, const char* key) {
   if (k == "nfast") return m.nfast; if (k == "dtfast") return m.dtfast; if (k == "hc") return m.hc; if (k == "wvelocity_every_step") return c.wvelocity_every_step;
   if (k == "bv_frequency") return c.bv_frequency; if (k == "eos_tderivative") return c.eos_tderivative;
   if (k == "solar_source") return c.solar_source; if (k == "lmd_nonlocal") return c.lmd_nonlocal;
+  if (k == "bulk_fluxes") return c.bulk_fluxes; if (k == "lmd_mixing") return c.lmd_mixing;
+  if (k == "blk_ZQ") return c.blk_ZQ; if (k == "blk_ZT") return c.blk_ZT; if (k == "blk_ZW") return c.blk_ZW;
   if (k == "app") return c.app; if (k == "nAVG") return c.nAVG; if (k == "ntsAVG") return c.ntsAVG;
   return -1.0e300;
 }

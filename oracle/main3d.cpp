@@ -134,8 +134,14 @@ static void step2d_loop(Model& m, int nthreads) {
 void run_phase(Model& m, int phase, int nthreads) {
   switch (phase) {
     case PH_SET_DATA:
-      for_tiles(m, nthreads, [&](const Bnd& b) { ana_smflux(m, b); ana_stflux_btflux(m, b); });
+      // set_data.F: with BULK_FLUXES the atmosphere replaces ana_smflux and the heat part of ana_stflux (:406-412, :552-564)
+      for_tiles(m, nthreads, [&](const Bnd& b) {
+        if (m.c.bulk_fluxes) ana_atmosphere(m, b); else ana_smflux(m, b);
+        ana_stflux_btflux(m, b);
+      });
       break;
+    case PH_BULK_FLUX: if (m.c.bulk_fluxes) for_tiles(m, nthreads, [&](const Bnd& b) { bulk_flux(m, b); }); break;
+    case PH_LMD_VMIX: if (m.c.lmd_mixing) for_tiles(m, nthreads, [&](const Bnd& b) { lmd_vmix(m, b); }); break;
     case PH_SET_MASSFLUX: for_tiles(m, nthreads, [&](const Bnd& b) { set_massflux(m, b); }); break;
     case PH_RHO_EOS: for_tiles(m, nthreads, [&](const Bnd& b) { rho_eos(m, b); }); break;
     case PH_DIAG: diag(m); break;
@@ -176,9 +182,11 @@ void main3d_step(Model& m, int nthreads) {
   }
   for_tiles(m, nthreads, [&](const Bnd& b) { set_massflux(m, b); rho_eos(m, b); });   // :307-309
   run_phase(m, PH_DIAG, nthreads);                                                   // :314
+  run_phase(m, PH_BULK_FLUX, nthreads);                                              // :384-390
   run_phase(m, PH_SET_VBC, nthreads);                                                // :394
   for_tiles(m, nthreads, [&](const Bnd& b) {                                         // :465-475
     if (m.c.ana_vmix) ana_vmix(m, b);
+    else if (m.c.lmd_mixing) lmd_vmix(m, b);
     omega(m, b);
     if (m.c.wvelocity_every_step) wvelocity(m, b, m.nstp);
   });

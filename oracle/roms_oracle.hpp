@@ -153,6 +153,10 @@ struct Cfg {
   int eos_tderivative = 0;        // LMD_SKPP || BULK_FLUXES: rho_eos also returns alpha, beta (:420-462 / :760-773)
   int solar_source = 0;           // SOLAR_SOURCE: shortwave penetration in pre_step3d (:312-333, :866-883), lmd_swfrac.F
   int lmd_nonlocal = 0;           // LMD_NONLOCAL: KPP nonlocal transport in pre_step3d (:850-865)
+  // the forcing / mixing physics of the shipped BENCHMARK set (physics.cpp)
+  int bulk_fluxes = 0;            // BULK_FLUXES: bulk_flux computes stflux(itemp), sustr, svstr from the atmosphere (main3d.F:384-390)
+  int lmd_mixing = 0;             // LMD_MIXING (+LMD_RIMIX, LMD_CONVEC, LMD_SKPP, LMD_NONLOCAL, RI_SPLINES): lmd_vmix (main3d.F:467)
+  double blk_ZQ = 10.0, blk_ZT = 10.0, blk_ZW = 10.0;   // roms_benchmark1.in BLK_ZQ, BLK_ZT, BLK_ZW
   int nAVG = 0, ntsAVG = 1;       // AVERAGES: window length in steps (0: off) and starting step (roms_*.in NAVG, NTSAVG)
 };
 
@@ -189,6 +193,8 @@ struct Model {
   F3 W, wvel, z_w, Akv; F3 Akt[2];              // k=0..N
   F3 bvf; F2 alpha, beta;                       // rho_eos optional outputs (bvf k=0..N)
   F2 srflx, Jwtype; F3 ghats[2];                // mod_forces.F srflx; mod_mixing.F Jwtype, ghats (k=0..N)
+  F2 Uwind, Vwind, Tair, Pair, Hair, rain, cloud, lrflx, lhflx, shflx;   // mod_forces.F (BULK_FLUXES)
+  F2 hsbl, ksbl;                                // mod_mixing.F (LMD_SKPP); ksbl is INTEGER in the reference, kept as whole doubles
   // ---- time-averaged fields (mod_average.F; set_avg.cpp)
   F2 avgzeta, avgu2d, avgv2d; F3 avgu3d, avgv3d, avgrho, avgt[2];   // k=1..N
   F3 avgw3d, avgwvel;                                               // k=0..N
@@ -221,6 +227,9 @@ void ini_zeta(Model& m, const Bnd& b);        // ROMS/Nonlinear/ini_fields.F:836
 void ini_fields(Model& m, const Bnd& b);      // ROMS/Nonlinear/ini_fields.F:106-777
 void initialize(Model& m);                    // initial.F call order
 void set_avg(Model& m, const Bnd& b);         // ROMS/Nonlinear/set_avg.F
+void ana_atmosphere(Model& m, const Bnd& b);  // set_data.F:197-394 -> ana_cloud/tair/humid/srflux/winds/rain/pair (BENCHMARK)
+void bulk_flux(Model& m, const Bnd& b);       // ROMS/Nonlinear/bulk_flux.F
+void lmd_vmix(Model& m, const Bnd& b);        // ROMS/Nonlinear/lmd_vmix.F, lmd_skpp.F, lmd_swfrac.F
 
 // ---- periodic exchanges / boundary conditions
 void exchange_r2d(const Model& m, const Bnd& b, F2 A);
@@ -268,7 +277,8 @@ void eos_point(double Tt, double Ts, double Tp, double* den, double* den1, doubl
 enum Phase {
   PH_SET_MASSFLUX = 1, PH_RHO_EOS = 2, PH_SET_VBC = 3, PH_ANA_VMIX = 4, PH_OMEGA = 5, PH_WVELOCITY = 6, PH_SET_ZETA = 7,
   PH_PRE_STEP3D = 8, PH_PRSGRD = 9, PH_T3DMIX = 10, PH_RHS3D = 11, PH_UV3DMIX = 12, PH_STEP2D = 13, PH_SET_DEPTH = 14,
-  PH_STEP3D_UV = 15, PH_OMEGA2 = 16, PH_STEP3D_T = 17, PH_DIAG = 18, PH_SET_DATA = 19, PH_STEP2D_LOOP = 20, PH_INI = 21, PH_SET_AVG = 22
+  PH_STEP3D_UV = 15, PH_OMEGA2 = 16, PH_STEP3D_T = 17, PH_DIAG = 18, PH_SET_DATA = 19, PH_STEP2D_LOOP = 20, PH_INI = 21, PH_SET_AVG = 22,
+  PH_BULK_FLUX = 23, PH_LMD_VMIX = 24
 };
 void run_phase(Model& m, int phase, int nthreads);
 void main3d_step(Model& m, int nthreads);    // one baroclinic step (main3d.F:189-917)

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "lib", "obj")
-SOURCES = ["api.cu", "api_tile.cu", "api_nccl.cu", "k_glue.cu", "k_pre.cu", "k_rhs.cu", "k_step3d.cu", "k_step2d.cu", "k_step2d_loop.cu", "k_diag.cu", "k_mixgeo.cu"]
+SOURCES = ["api.cu", "api_tile.cu", "api_nccl.cu", "k_glue.cu", "k_pre.cu", "k_rhs.cu", "k_step3d.cu", "k_step2d.cu", "k_step2d_loop.cu", "k_diag.cu", "k_mixgeo.cu", "k_physics.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

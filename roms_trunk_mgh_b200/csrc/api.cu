@@ -110,7 +110,7 @@ int materialize(roms_b200_state* h, FieldInfo& fi) {
 int alloc_field(roms_b200_state* h, const std::string& name, double** slot, int LBk, int nk) {
   *slot = nullptr;
   FieldInfo fi{slot, LBk, nk, nullptr};
-  if (!h->lazy || name == "P3") { const int rc = materialize(h, fi); if (rc) return rc; }
+  if (!h->lazy || name == "P3" || name == "Taux" || name == "Tauy") { const int rc = materialize(h, fi); if (rc) return rc; }
   h->reg[name] = fi;
   return NoError;
 }
@@ -184,6 +184,12 @@ std::vector<std::string> halo_fields(roms_b200_state* h, int phase) {
       if (h->cfg.eos_tderivative) { v.push_back("alpha"); v.push_back("beta"); }
       break;
     case ROMS_B200_SET_VBC: v = {"bustr", "bvstr"}; break;                          // set_vbc.F:664
+    case ROMS_B200_BULK_FLUX:                                                       // bulk_flux.F:949-960
+      if (h->cfg.bulk_fluxes) v = {"lrflx", "lhflx", "shflx", "stflux_" + std::to_string(h->cfg.itemp - 1), "sustr", "svstr"};
+      break;
+    case ROMS_B200_LMD_VMIX:                                                        // lmd_skpp.F:641-647, lmd_vmix.F:644-655
+      if (h->cfg.lmd_mixing) { v = {"hsbl", "Akv"}; for (int it = 0; it < (h->cfg.salinity ? 2 : 1); ++it) v.push_back("Akt_" + std::to_string(it)); }
+      break;
     case ROMS_B200_ANA_VMIX:
       if (h->cfg.ana_vmix) { v = {"Akv"}; for (int it = 0; it < h->cfg.NT; ++it) v.push_back("Akt_" + std::to_string(it)); }
       break;
@@ -340,6 +346,8 @@ int ensure_optional(roms_b200_state* h, int phase) {
   if (!h->lazy) return NoError;
   std::vector<std::string> names;
   if (phase == ROMS_B200_RHO_EOS) names = {"bvf", "alpha", "beta"};
+  else if (phase == ROMS_B200_BULK_FLUX) names = {"lrflx", "lhflx", "shflx", "sustr", "svstr", "stflux_" + std::to_string(h->cfg.itemp - 1)};
+  else if (phase == ROMS_B200_LMD_VMIX) { names = {"hsbl", "ksbl", "Akv"}; for (int it = 0; it < h->cfg.NT; ++it) { names.push_back("ghats_" + std::to_string(it)); names.push_back("Akt_" + std::to_string(it)); } }
   else if (phase == ROMS_B200_PRE_STEP3D) { names = {"srflx", "Jwtype"}; for (int it = 0; it < h->cfg.NT; ++it) names.push_back("ghats_" + std::to_string(it)); }
   for (const std::string& n : names) {
     auto it = h->reg.find(n);
@@ -363,6 +371,16 @@ int run_phase_async(roms_b200_state* h, int phase) {
     case ROMS_B200_ANA_VMIX:
       if (h->cfg.ana_vmix) { rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_ana_vmix(q, f, st); }); h->launches += 1; }
       break;
+    case ROMS_B200_BULK_FLUX:
+      if (!h->cfg.bulk_fluxes) return ConfigError;
+      // the stresses at u / v points need the rho-point values of the neighbouring column: one launch over the whole tile
+      launch_full(h, [&](const Par& q, cudaStream_t st) { launch_bulk_flux(q, f, st); });
+      if (h->halo) rc = halo_exchange(h, halo_fields(h, phase), h->stream);
+      h->launches += 2; break;
+    case ROMS_B200_LMD_VMIX:
+      if (!h->cfg.lmd_mixing) return ConfigError;
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_lmd_vmix(q, f, st); });
+      h->launches += (p.Iend == p.Lm) ? 2 : 1; break;
     case ROMS_B200_OMEGA: case ROMS_B200_OMEGA2:
       rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_omega(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_WVELOCITY:
@@ -463,8 +481,10 @@ int step_phases_body(roms_b200_state* h, bool with_diag) {
     cudaStreamIsCapturing(h->stream, &cs);
     cudaStreamWaitEvent(h->stream, h->ev_forcing, cs == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : 0);
   }
-  static const int seq2[] = {ROMS_B200_SET_VBC, ROMS_B200_ANA_VMIX, ROMS_B200_OMEGA};
-  for (int ph : seq2) { int rc = run_phase_async(h, ph); if (rc) return rc; }
+  if (h->cfg.bulk_fluxes) { int rc = run_phase_async(h, ROMS_B200_BULK_FLUX); if (rc) return rc; }      // main3d.F:384-390
+  { int rc = run_phase_async(h, ROMS_B200_SET_VBC); if (rc) return rc; }
+  { int rc = run_phase_async(h, h->cfg.lmd_mixing && !h->cfg.ana_vmix ? ROMS_B200_LMD_VMIX : ROMS_B200_ANA_VMIX); if (rc) return rc; }   // :464-470
+  { int rc = run_phase_async(h, ROMS_B200_OMEGA); if (rc) return rc; }
   if (h->cfg.wvelocity_every_step) { int rc = run_phase_async(h, ROMS_B200_WVELOCITY); if (rc) return rc; }
   static const int seq3[] = {ROMS_B200_SET_ZETA,  ROMS_B200_SET_AVG, ROMS_B200_PRE_STEP3D, ROMS_B200_PRSGRD,    ROMS_B200_T3DMIX,   ROMS_B200_RHS3D, ROMS_B200_UV3DMIX,
                              ROMS_B200_STEP2D_LOOP, ROMS_B200_SET_DEPTH, ROMS_B200_STEP3D_UV, ROMS_B200_OMEGA2, ROMS_B200_STEP3D_T};
@@ -621,6 +641,8 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   *out = nullptr;
   if (cfg->N < 4 || cfg->N > MAXN || cfg->NT < 1 || cfg->NT > MAXNT || cfg->Lm < 8 || cfg->Mm < 4) return ConfigError;
   if (cfg->NtileI < 1 || cfg->NtileJ < 1 || cfg->tile < 0 || cfg->tile >= cfg->NtileI * cfg->NtileJ) return ConfigError;
+  // lmd_skpp reads bvf, alpha / beta, srflx and writes ghats: the switches that provide those arrays must be on with it
+  if (cfg->lmd_mixing && !(cfg->bv_frequency && cfg->eos_tderivative && cfg->solar_source && cfg->lmd_nonlocal)) return ConfigError;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
     std::fprintf(stderr, "roms_b200: no CUDA device; this library has no CPU fallback\n");
@@ -664,6 +686,8 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   p.nonlin_eos = cfg->nonlin_eos; p.curvgrid = cfg->curvgrid; p.uv_qdrag = cfg->uv_qdrag; p.salinity = cfg->salinity;
   p.hadv = cfg->hadv; p.vadv = cfg->vadv; p.itemp = cfg->itemp; p.isalt = cfg->isalt;
   p.bv_frequency = cfg->bv_frequency; p.eos_tderivative = cfg->eos_tderivative; p.solar_source = cfg->solar_source; p.lmd_nonlocal = cfg->lmd_nonlocal;
+  p.bulk_fluxes = cfg->bulk_fluxes; p.lmd_mixing = cfg->lmd_mixing;
+  p.blk_ZQ = cfg->blk_ZQ > 0.0 ? cfg->blk_ZQ : 10.0; p.blk_ZT = cfg->blk_ZT > 0.0 ? cfg->blk_ZT : 10.0; p.blk_ZW = cfg->blk_ZW > 0.0 ? cfg->blk_ZW : 10.0;
   p.dt = cfg->dt; p.g = cfg->g; p.rho0 = cfg->rho0; p.R0 = cfg->R0; p.T0 = cfg->T0; p.S0 = cfg->S0; p.Tcoef = cfg->Tcoef; p.Scoef = cfg->Scoef;
   p.gamma2 = cfg->gamma2; p.lambda = cfg->lambda; p.hc = cfg->hc; p.Akv_bak = cfg->Akv_bak;
   for (int it = 0; it < MAXNT; ++it) p.Akt_bak[it] = cfg->Akt_bak[it];
@@ -711,7 +735,14 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   }
   if (cfg->bv_frequency) rc |= alloc_field(h, "bvf", &f.bvf, 0, N + 1);
   if (cfg->eos_tderivative) { rc |= alloc_field(h, "alpha", &f.alpha, 0, 1); rc |= alloc_field(h, "beta", &f.beta, 0, 1); }
-  if (cfg->solar_source) { rc |= alloc_field(h, "srflx", &f.srflx, 0, 1); rc |= alloc_field(h, "Jwtype", &f.Jwtype, 0, 1); }
+  if (cfg->solar_source || cfg->bulk_fluxes) rc |= alloc_field(h, "srflx", &f.srflx, 0, 1);
+  if (cfg->solar_source) rc |= alloc_field(h, "Jwtype", &f.Jwtype, 0, 1);
+  if (cfg->bulk_fluxes) {
+#define A2(name) rc |= alloc_field(h, #name, &f.name, 0, 1)
+    A2(Uwind); A2(Vwind); A2(Tair); A2(Pair); A2(Hair); A2(rain); A2(cloud); A2(lrflx); A2(lhflx); A2(shflx); A2(Taux); A2(Tauy);
+#undef A2
+  }
+  if (cfg->lmd_mixing) { rc |= alloc_field(h, "hsbl", &f.hsbl, 0, 1); rc |= alloc_field(h, "ksbl", &f.ksbl, 0, 1); }
   if (cfg->lmd_nonlocal) for (int it = 0; it < cfg->NT; ++it) rc |= alloc_field(h, "ghats_" + std::to_string(it), &f.ghats[it], 0, N + 1);
   if (rc) { roms_b200_destroy(h); return FatalError; }
   double* sc = nullptr;

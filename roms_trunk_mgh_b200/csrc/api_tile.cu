@@ -148,6 +148,10 @@ const RoutineArgs kRoutineArgs[] = {
      "u1,u2,v1,v2,Huon,Hvom,ubar1,ubar2,vbar1,vbar2"},
     {ROMS_B200_OMEGA2, "Huon,Hvom,z_w", "W"},
     {ROMS_B200_STEP3D_T, "Hz,Huon,Hvom,W,Akt_*,pm,pn,t1_*,t2_*,t3_*", "t1_*,t2_*"},
+    // cfg.bulk_fluxes / cfg.lmd_mixing (with the switches lmd_mixing needs) must be set in roms_b200_tile_t.cfg for these two
+    {ROMS_B200_BULK_FLUX, "t1_*,t2_*,Uwind,Vwind,Tair,Pair,Hair,rain,cloud,srflx", "lrflx,lhflx,shflx,stflux_*,sustr,svstr"},
+    {ROMS_B200_LMD_VMIX, "f,Hz,z_w,u1,u2,v1,v2,pden,bvf,alpha,beta,srflx,Jwtype,stflx_*,sustr,svstr,bustr,bvstr,hsbl,Akv,Akt_*",
+     "Akv,Akt_*,ghats_*,hsbl,ksbl"},
 };
 }  // namespace
 

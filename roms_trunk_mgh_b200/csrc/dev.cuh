@@ -34,11 +34,13 @@ struct Par {
   // options
   int nonlin_eos, curvgrid, uv_qdrag, salinity, hadv, vadv, itemp, isalt;
   int bv_frequency, eos_tderivative, solar_source, lmd_nonlocal;   // optional terms of rho_eos / pre_step3d (roms_b200_config)
+  int bulk_fluxes, lmd_mixing;    // BULK_FLUXES / LMD_MIXING phases are part of the step (k_physics.cu)
   int fuse_tmix;                  // pre_step3d_t also applies t3dmix2_s (whole-step path only; 0 for single-phase calls)
   // scalars
   double dt, dtfast, g, rho0, R0, T0, S0, Tcoef, Scoef, gamma2, lambda, hc;
   double Akv_bak, Akt_bak[MAXNT];
   double w1_m1, w2_0, w2_p1;      // weight(1,iif-1), weight(2,iif), weight(2,iif+1) for the current step2d call
+  double blk_ZQ, blk_ZT, blk_ZW;  // heights (m) of the atmospheric humidity / temperature / wind data (bulk_flux.F)
 };
 
 // Field table (all pointers pre-offset; [0] slots of time-indexed arrays are unused so Fortran indices apply)
@@ -61,6 +63,8 @@ struct Flds {
   // optional: rho_eos outputs bvf (0:N), alpha, beta; pre_step3d inputs srflx, Jwtype, ghats (0:N)
   double *bvf, *alpha, *beta, *srflx, *Jwtype;
   double* ghats[MAXNT];
+  // optional: atmosphere read by bulk_flux, its flux outputs, wind stress scratch at rho points; KPP boundary layer depth / index
+  double *Uwind, *Vwind, *Tair, *Pair, *Hair, *rain, *cloud, *lrflx, *lhflx, *shflx, *Taux, *Tauy, *hsbl, *ksbl;
   // time-averaged fields (mod_average.F; allocated by roms_b200_set_avg)
   double *avgzeta, *avgu2d, *avgv2d, *avgu3d, *avgv3d, *avgrho, *avgw3d, *avgwvel;
   double* avgt[MAXNT];

@@ -167,6 +167,8 @@ class Tile:
     def rho_eos(self): self.run_phase("rho_eos")
     def set_vbc(self): self.run_phase("set_vbc")
     def ana_vmix(self): self.run_phase("ana_vmix")
+    def bulk_flux(self): self.run_phase("bulk_flux")
+    def lmd_vmix(self): self.run_phase("lmd_vmix")
     def omega(self): self.run_phase("omega")
     def wvelocity(self): self.run_phase("wvelocity")
     def set_zeta(self): self.run_phase("set_zeta")

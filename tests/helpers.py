@@ -6,7 +6,7 @@ from roms_trunk_mgh_b200 import _lib
 from roms_trunk_mgh_b200.ocean import Tile, field_names
 
 APP_OPTS = ["nonlin_eos", "dj_gradps", "curvgrid", "mix_geo_ts", "uv_qdrag", "hadv", "vadv", "ana_vmix", "wvelocity_every_step",
-            "bv_frequency", "eos_tderivative", "solar_source", "lmd_nonlocal"]
+            "bv_frequency", "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing"]
 
 
 def cfg_from_oracle(o, device=0):
@@ -22,15 +22,32 @@ def cfg_from_oracle(o, device=0):
     cfg.R0 = o.opt("R0"); cfg.T0 = o.opt("T0"); cfg.S0 = o.opt("S0"); cfg.Tcoef = o.opt("Tcoef"); cfg.Scoef = o.opt("Scoef")
     cfg.Akt_bak[0] = cfg.Akt_bak[1] = o.opt("Akt_bak"); cfg.Akv_bak = o.opt("Akv_bak")
     cfg.gamma2 = o.opt("gamma2"); cfg.lambda_ = o.opt("lambda"); cfg.hc = o.opt("hc")
+    cfg.blk_ZQ = o.opt("blk_ZQ"); cfg.blk_ZT = o.opt("blk_ZT"); cfg.blk_ZW = o.opt("blk_ZW")
     cfg.device = device
     return cfg
+
+
+ATMOSPHERE = ["Uwind", "Vwind", "Tair", "Pair", "Hair", "rain", "cloud", "srflx"]      # what the host hands bulk_flux (FORCES)
+
+
+def optional_names(o):
+    """Names of the arrays that exist only when a cpp switch of the BENCHMARK set is on (include/roms_b200.h)."""
+    NT = int(o.opt("NT"))
+    v = []
+    if o.opt("bv_frequency"): v += ["bvf"]
+    if o.opt("eos_tderivative"): v += ["alpha", "beta"]
+    if o.opt("solar_source"): v += ["srflx", "Jwtype"]
+    if o.opt("lmd_nonlocal"): v += [f"ghats_{it}" for it in range(NT)]
+    if o.opt("bulk_fluxes"): v += [n for n in ATMOSPHERE if n not in v] + ["lrflx", "lhflx", "shflx"]
+    if o.opt("lmd_mixing"): v += ["hsbl", "ksbl"]
+    return v
 
 
 def copy_state(o, t):
     """Upload every field, vector and index of oracle `o` into device tile `t`."""
     NT = int(o.opt("NT")); N = int(o.opt("N"))
     n2, n3 = field_names(NT)
-    for n in n2 + n3:
+    for n in n2 + n3 + optional_names(o):
         t.set(n, o.field(n))
     t.set_scoord(o.vector(0, N + 1), o.vector(1, N + 1), o.vector(2, N + 1), o.vector(3, N + 1))
     nd = int(o.opt("ndtfast"))

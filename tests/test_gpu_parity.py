@@ -38,7 +38,10 @@ def begin_step(o, t):
     d["tdays"] = d["time"] / 86400.0
     o.set_indices(d)
     o.run_phase("set_data")
-    t.set("sustr", o.field("sustr")); t.set("svstr", o.field("svstr"))
+    if o.opt("bulk_fluxes"):
+        t.set("srflx", o.field("srflx"))           # the only time-dependent member of the analytical atmosphere (ana_srflux.h)
+    else:
+        t.set("sustr", o.field("sustr")); t.set("svstr", o.field("svstr"))
     t.set_indices(o.indices())
 
 
@@ -281,6 +284,70 @@ def test_benchmark_cpp_terms_inside_the_chain(nonlin):
     for ph in ("set_data", "set_massflux", "rho_eos", "set_vbc", "ana_vmix", "omega", "wvelocity", "set_zeta", "pre_step3d"):
         o2.run_phase(ph)
     assert not np.array_equal(o2.field(f"t{nn}_0"), o.field(f"t{nn}_0"))
+    t.close()
+
+
+FULL_BENCHMARK = dict(bv_frequency=1, eos_tderivative=1, solar_source=1, lmd_nonlocal=1, bulk_fluxes=1, lmd_mixing=1)
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(a))), 1e-300))
+
+
+@pytest.mark.parametrize("spinup", [0, 6])
+def test_bulk_flux_and_lmd_vmix_phase_parity(spinup):
+    """bulk_flux (bulk_flux.F:381-948, COARE 3.0 + LONGWAVE) and lmd_vmix (lmd_vmix.F, lmd_skpp.F, lmd_swfrac.F: LMD_RIMIX,
+    LMD_CONVEC, LMD_SKPP, LMD_NONLOCAL, RI_SPLINES) on the device against the oracle, one phase at a time, on the BENCHMARK
+    channel with the analytical atmosphere of ana_winds / tair / pair / humid / rain / cloud / srflux.  Both routines evaluate
+    pow / exp / log / atan, whose device versions differ from glibc's in the last bits: fluxes and coefficients are held to
+    1e-11 relative, the integer boundary-layer index ksbl exactly."""
+    o = orc.Oracle(orc.APP_BENCHMARK, Lm=64, Mm=48, N=30, **FULL_BENCHMARK)
+    o.run_phase("set_data"); o.run_phase("ini")
+    if spinup:
+        o.step(spinup)
+    t = Tile(cfg_from_oracle(o), strict=True)
+    copy_state(o, t)
+    begin_step(o, t)
+    for ph in ("set_massflux", "rho_eos", "bulk_flux"):
+        o.run_phase(ph); t.run_phase(ph)
+    for n in ("lrflx", "lhflx", "shflx", "stflux_0", "sustr", "svstr"):
+        a, b = o.field(n), t.get(n)
+        assert np.abs(a).max() > 0 or n == "svstr", n
+        assert _rel(a, b) <= 1e-11, (n, _rel(a, b))
+    assert np.abs(o.field("sustr")).max() > 1e-4                 # ~0.5 N/m2 under the 15 m/s jet
+    # continue from identical inputs so that lmd_vmix is tested on its own
+    for n in ("lrflx", "lhflx", "shflx", "stflux_0", "sustr", "svstr"):
+        t.set(n, o.field(n))
+    for ph in ("set_vbc", "lmd_vmix"):
+        o.run_phase(ph); t.run_phase(ph)
+    assert np.array_equal(o.field("ksbl"), t.get("ksbl"))
+    for n in ("hsbl", "Akv", "Akt_0", "Akt_1", "ghats_0", "ghats_1"):
+        a, b = o.field(n), t.get(n)
+        assert _rel(a, b) <= 1e-11, (n, _rel(a, b))
+    if spinup:
+        assert o.field("hsbl")[0, 1:-1, 3:-3].min() < -10.0 and o.field("Akv").max() > 1e-3     # a live boundary layer
+        assert len(np.unique(o.field("ksbl")[0, 1:-1, 3:-3])) > 1
+    t.close()
+
+
+def test_full_benchmark_physics_multistep():
+    """The shipped BENCHMARK cpp set end to end (benchmark.h: BULK_FLUXES, LMD_MIXING + SKPP + NONLOCAL, SOLAR_SOURCE, MIX_GEO_TS
+    off here): 12 steps on the device, the host refreshing only the shortwave flux, against the oracle's main3d_step."""
+    o = orc.Oracle(orc.APP_BENCHMARK, Lm=64, Mm=48, N=30, **FULL_BENCHMARK)
+    o.run_phase("set_data"); o.run_phase("ini")
+    t = Tile(cfg_from_oracle(o), strict=True)
+    copy_state(o, t)
+    for s in range(12):
+        begin_step(o, t)
+        o.step(1)
+        t.main3d(1)
+    nn = o.indices()["nnew"]
+    worst = {}
+    for n in ("zeta1", f"u{nn}", f"v{nn}", f"t{nn}_0", f"t{nn}_1", "Akv", "Akt_0", "hsbl", "sustr", "stflux_0"):
+        worst[n] = _rel(o.field(n), t.get(n))
+    assert max(worst.values()) <= 1e-9, worst
+    assert np.array_equal(o.field("ksbl"), t.get("ksbl"))
+    assert t.diag()["avgke"] > 0
     t.close()
 
 
