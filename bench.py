@@ -48,9 +48,11 @@ def workload(grid, Lm, Mm, N, ndtfast=20, nfast=29, mix_geo=False):
             f"ndtfast={ndtfast}, nfast={nfast}")
 
 
-def b_alg_bytes(N, nfast, curvgrid=True, nonlin_eos=True, wvelocity=True, mix_geo=False):
-    """Algorithmic bytes per grid-point-step (SURVEY.md section 8d / BASELINE.md): 8*(U3D + S2D/N)."""
-    u3d = 98 + (7 if wvelocity else 0) + (3 if nonlin_eos else 0) + (1 if mix_geo else 0)
+def b_alg_bytes(N, nfast, curvgrid=True, nonlin_eos=True, wvelocity=True, mix_geo=False, full_physics=False):
+    """Algorithmic bytes per grid-point-step (SURVEY.md section 8d / BASELINE.md): 8*(U3D + S2D/N).
+    full_physics (the shipped benchmark.h set): lmd_vmix reads Hz, u, v, pden, bvf, z_w and writes Akv, Akt x2, ghats x2 (11 units),
+    rho_eos also writes bvf (1), pre_step3d also reads ghats x2 and z_w (3); bulk_flux is 2-D only."""
+    u3d = 98 + (7 if wvelocity else 0) + (3 if nonlin_eos else 0) + (1 if mix_geo else 0) + (15 if full_physics else 0)
     per_pred, per_corr = 42 + (2 if curvgrid else 0), 39 + (2 if curvgrid else 0)
     s2d = nfast * per_pred + 16 + nfast * per_corr
     return 8.0 * (u3d + s2d / N), s2d
@@ -405,6 +407,32 @@ def main():
                                       "roofline_step_frac": bg * (Lm * Mm * N * 6 / (msg * 1e-3)) / 1e9 / (peak * world)}
             perr |= int(tg.L.roms_b200_peer_error(tg.h))
             tg.close()
+            # the shipped benchmark.h cpp set: + BULK_FLUXES, LMD_MIXING/SKPP/NONLOCAL, SOLAR_SOURCE, BV_FREQUENCY, MIX_GEO_TS
+            tf, _ = make_ring_tile(synth, (Lm, Mm, N), rank, world, local, dist, **synth.FULL_BENCHMARK)
+            gsy = tf.synth["grid"]; bsy = tf.synth["bounds"]
+            tf.main3d(10)
+            msf = timed_steps(tf, dist, 6)
+            bf, _ = b_alg_bytes(N, nfast, mix_geo=True, full_physics=True)
+            vf = Lm * Mm * N * 6 / (msf * 1e-3)
+            tf.profile(2); tf.main3d(2); tf.profile(2); tf.main3d(2)
+            pf, _ = tf.profile_get(); tf.profile(0)
+            # e2e: the atmosphere of this model time H2D (8 arrays), the step with bulk_flux + lmd_vmix on the device, diag D2H
+            atm = {n: np.ascontiguousarray(synth.tile_slice(v, Lm, bsy)) for n, v in synth.atmosphere_at(gsy, tf.cfg, tf.indices()["tdays"]).items()}
+            for _ in range(3):
+                tf.step_fields(atm)
+            barrier(); tf.sync(); t0 = time.perf_counter()
+            for _ in range(6):
+                tf.step_fields(atm)
+            tf.sync(); barrier(); fsec = time.perf_counter() - t0
+            line["full_benchmark_row"] = {
+                "workload": "the shipped ROMS/Include/benchmark.h cpp set: reduced set + BULK_FLUXES (COARE 3.0, LONGWAVE), LMD_MIXING (RIMIX, CONVEC, SKPP, "
+                            "NONLOCAL, RI_SPLINES), SOLAR_SOURCE, BV_FREQUENCY, MIX_GEO_TS; analytical atmosphere (ana_winds/tair/pair/humid/rain/cloud/srflux)",
+                "ms_per_step": msf / 6, "value": vf, "steps": 6, "spinup_steps": 10, "b_alg_bytes_per_gp_step": bf,
+                "roofline_step_frac": bf * vf / 1e9 / (peak * world),
+                "phase_ms": {k: v / 2 for k, v in pf.items() if k in ("bulk_flux", "lmd_vmix", "t3dmix", "rho_eos", "pre_step3d")},
+                "e2e": {"value": Lm * Mm * N * 6 / fsec, "h2d_bytes_per_step": int(sum(v.nbytes for v in atm.values())), "d2h_bytes_per_step": 96, "steps": 6}}
+            perr |= int(tf.L.roms_b200_peer_error(tf.h))
+            tf.close()
             wg = WEAK.get(world)
             if wg:
                 wl = GRIDS[wg]

@@ -98,7 +98,9 @@ int roms_b200_array_bounds(roms_b200_handle h, int* out4);
  * "Akt_<itrc>"; ocean (mod_ocean.F) "zeta<1-3>","ubar<1-3>","vbar<1-3>","rzeta<1-2>","rubar<1-2>","rvbar<1-2>",
  * "u<1-2>","v<1-2>","t<1-3>_<itrc>","ru<1-2>","rv<1-2>","rho","pden","W","wvel"; depths "Hz","z_r","z_w","Huon","Hvom";
  * coupling (mod_coupling.F) "Zt_avg1","DU_avg1","DU_avg2","DV_avg1","DV_avg2","rufrc","rvfrc","rhoA","rhoS";
- * forces (mod_forces.F) "sustr","svstr","bustr","bvstr","stflx_<itrc>","btflx_<itrc>","stflux_<itrc>","btflux_<itrc>".
+ * forces (mod_forces.F) "sustr","svstr","bustr","bvstr","stflx_<itrc>","btflx_<itrc>","stflux_<itrc>","btflux_<itrc>";
+ * with the switches of roms_b200_config that create them: "bvf","alpha","beta","srflx","Jwtype","ghats_<itrc>","Uwind","Vwind",
+ * "Tair","Pair","Hair","rain","cloud","lrflx","lhflx","shflx","hsbl","ksbl".
  * <itrc> is 0-based.  n = number of doubles in the whole Fortran array (checked).
  * With a ring attached (roms_b200_attach_nccl) roms_b200_set_field and roms_b200_step_forced are COLLECTIVE: every
  * upload is followed by the halo exchange of that field (mp_exchange2d/3d), so all tiles must upload the same fields in
@@ -164,6 +166,11 @@ int roms_b200_set_option(roms_b200_handle h, const char* key, double value);
  * then D2H of the diag scalars.  out12 = avgke, avgpe, avgkp, volume, max_speed, maxCu, maxCv, maxCw,
  * ubarmax, vbarmax, umax, vmax (diag.F:293-437, ana_diag.h:116-142).  Synchronous. */
 int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double* svstr, const double* stflux_temp,
+                          size_t n2d, double* out12);
+/* The same with any set of 2-D forcing arrays, by name -- with cfg.bulk_fluxes the set_data products are the atmosphere
+ * ("Uwind","Vwind","Tair","Pair","Hair","rain","cloud","srflx") instead of the stresses.  arrays[i] == NULL keeps the
+ * resident value of names[i]; nfields <= 16.  Collective with a ring attached, like roms_b200_set_field. */
+int roms_b200_step_fields(roms_b200_handle h, int nfields, const char* const* names, const double* const* arrays,
                           size_t n2d, double* out12);
 int roms_b200_diag(roms_b200_handle h, double* out12);
 /* Pin a caller-owned host range (cudaHostRegister) so that roms_b200_step_forced copies from it directly instead of

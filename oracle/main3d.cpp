@@ -141,7 +141,12 @@ void run_phase(Model& m, int phase, int nthreads) {
       });
       break;
     case PH_BULK_FLUX: if (m.c.bulk_fluxes) for_tiles(m, nthreads, [&](const Bnd& b) { bulk_flux(m, b); }); break;
-    case PH_LMD_VMIX: if (m.c.lmd_mixing) for_tiles(m, nthreads, [&](const Bnd& b) { lmd_vmix(m, b); }); break;
+    case PH_LMD_VMIX:
+      if (m.c.lmd_mixing) {
+        for_tiles(m, nthreads, [&](const Bnd& b) { lmd_vmix(m, b); });
+        for_tiles(m, nthreads, [&](const Bnd& b) { lmd_vmix_bc(m, b); });
+      }
+      break;
     case PH_SET_MASSFLUX: for_tiles(m, nthreads, [&](const Bnd& b) { set_massflux(m, b); }); break;
     case PH_RHO_EOS: for_tiles(m, nthreads, [&](const Bnd& b) { rho_eos(m, b); }); break;
     case PH_DIAG: diag(m); break;
@@ -184,9 +189,9 @@ void main3d_step(Model& m, int nthreads) {
   run_phase(m, PH_DIAG, nthreads);                                                   // :314
   run_phase(m, PH_BULK_FLUX, nthreads);                                              // :384-390
   run_phase(m, PH_SET_VBC, nthreads);                                                // :394
+  if (!m.c.ana_vmix) run_phase(m, PH_LMD_VMIX, nthreads);                            // :467
   for_tiles(m, nthreads, [&](const Bnd& b) {                                         // :465-475
     if (m.c.ana_vmix) ana_vmix(m, b);
-    else if (m.c.lmd_mixing) lmd_vmix(m, b);
     omega(m, b);
     if (m.c.wvelocity_every_step) wvelocity(m, b, m.nstp);
   });

@@ -564,15 +564,22 @@ static void lmd_finish(Model& m, const Bnd& b) {
       m.Akv(Iend + 1, Jend + 1, k) = 0.5 * (m.Akv(Iend, Jend + 1, k) + m.Akv(Iend + 1, Jend, k));
     }
   }
-  bc_w3d(m, b, m.Akv);
-  for (int it = 0; it < NAT; ++it) bc_w3d(m, b, m.Akt[it]);
 }
 
-// lmd_vmix (lmd_vmix.F:33-96): interior scheme, surface boundary layer, convective adjustment + boundary conditions
+// lmd_vmix (lmd_vmix.F:33-96): interior scheme, surface boundary layer, convective adjustment + boundary copies ...
 void lmd_vmix(Model& m, const Bnd& b) {
   lmd_vmix_interior(m, b);
   lmd_skpp(m, b);
   lmd_finish(m, b);
+}
+// ... and the end of lmd_finish_tile (lmd_vmix.F:636-655): bc_w3d = closed-wall copies + periodic / halo exchange.  A separate
+// stage, run after every tile has done lmd_vmix: the western-edge copy of one tile and the periodic copy of the eastern tile
+// write the same ghost column (0), and step3d_uv reads it, so in the reference's shared-memory mode the result depends on the
+// order of the tiles; the serial and the distributed-memory runs have the exchange last, which is what this ordering gives.
+void lmd_vmix_bc(Model& m, const Bnd& b) {
+  const int NAT = m.c.salinity ? 2 : 1;
+  bc_w3d(m, b, m.Akv);
+  for (int it = 0; it < NAT; ++it) bc_w3d(m, b, m.Akt[it]);
 }
 
 }  // namespace orc

@@ -230,6 +230,7 @@ void set_avg(Model& m, const Bnd& b);         // ROMS/Nonlinear/set_avg.F
 void ana_atmosphere(Model& m, const Bnd& b);  // set_data.F:197-394 -> ana_cloud/tair/humid/srflux/winds/rain/pair (BENCHMARK)
 void bulk_flux(Model& m, const Bnd& b);       // ROMS/Nonlinear/bulk_flux.F
 void lmd_vmix(Model& m, const Bnd& b);        // ROMS/Nonlinear/lmd_vmix.F, lmd_skpp.F, lmd_swfrac.F
+void lmd_vmix_bc(Model& m, const Bnd& b);     // ... its closing bc_w3d / exchange (second stage, see physics.cpp)
 
 // ---- periodic exchanges / boundary conditions
 void exchange_r2d(const Model& m, const Bnd& b, F2 A);

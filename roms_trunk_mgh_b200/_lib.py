@@ -42,7 +42,7 @@ DIAG_NAMES = ["avgke", "avgpe", "avgkp", "volume", "max_speed", "maxCu", "maxCv"
 EXPORTS = ["roms_b200_default_config", "roms_b200_bounds", "roms_b200_bounds_names", "roms_b200_create", "roms_b200_destroy",
            "roms_b200_array_bounds", "roms_b200_set_field", "roms_b200_get_field", "roms_b200_set_scoord", "roms_b200_set_weights",
            "roms_b200_set_indices", "roms_b200_get_indices", "roms_b200_run_phase", "roms_b200_main3d_step", "roms_b200_sync",
-           "roms_b200_step_forced", "roms_b200_diag", "roms_b200_register_host", "roms_b200_unregister_host", "roms_b200_last_step_ms", "roms_b200_profile_enable", "roms_b200_profile_get",
+           "roms_b200_step_forced", "roms_b200_step_fields", "roms_b200_diag", "roms_b200_register_host", "roms_b200_unregister_host", "roms_b200_last_step_ms", "roms_b200_profile_enable", "roms_b200_profile_get",
            "roms_b200_launch_count", "roms_b200_attach_nccl", "roms_b200_nccl_unique_id", "roms_b200_nccl_init_rank",
            "roms_b200_peer_export", "roms_b200_peer_attach", "roms_b200_peer_enable", "roms_b200_peer_error", "roms_b200_peer_error_inject",
            "roms_b200_set_option", "roms_b200_set_avg",
@@ -87,6 +87,7 @@ def load(strict=False):
     L.roms_b200_main3d_step.argtypes = [H, C.c_int]
     L.roms_b200_sync.argtypes = [H]
     L.roms_b200_step_forced.argtypes = [H, DP, DP, DP, C.c_size_t, DP]
+    L.roms_b200_step_fields.argtypes = [H, C.c_int, C.POINTER(C.c_char_p), C.POINTER(DP), C.c_size_t, DP]
     L.roms_b200_diag.argtypes = [H, DP]
     L.roms_b200_register_host.argtypes = [H, C.c_void_p, C.c_size_t]
     L.roms_b200_unregister_host.argtypes = [H, C.c_void_p]

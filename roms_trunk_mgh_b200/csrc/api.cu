@@ -959,25 +959,33 @@ int roms_b200_diag(roms_b200_handle h, double* out12) {
   return finish_diag(h, out12);
 }
 
-int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double* svstr, const double* stflux_temp, size_t n2d, double* out12) {
-  if (!h || !out12) return InputError;
+// One step the way main3d sees it from the host: nf 2-D forcing arrays by name H2D, the step, the diag scalars D2H.
+static int step_with_uploads(roms_b200_handle h, int nf, const char* const* nm, const double* const* src, size_t n2d, double* out12) {
+  if (!h || !out12 || nf < 0 || nf > 16) return InputError;
   if (h->nfast < 1) return ConfigError;
   if (h->exit_flag == FatalError) return FatalError;
   CK(cudaSetDevice(h->cfg.device));
   const size_t want = (size_t)h->ni * h->nj;
-  if ((sustr || svstr || stflux_temp) && n2d != want) return InputError;
-  if (!h->h_pinned) {
-    CK(cudaMallocHost(&h->h_pinned, 3 * want * sizeof(double))); h->pinned_n = want;
-    CK(cudaMalloc(&h->d_stage, 3 * want * sizeof(double))); h->allocs.push_back(h->d_stage);
+  bool any = false;
+  for (int q = 0; q < nf; ++q) {
+    if (!src[q]) continue;
+    any = true;
+    auto it = h->reg.find(nm[q]);
+    if (it == h->reg.end() || it->second.nk != 1 || !it->second.base) { std::fprintf(stderr, "roms_b200: '%s' is not a 2-D field of this handle\n", nm[q]); return InputError; }
+  }
+  if (any && n2d != want) return InputError;
+  if (!h->h_pinned || h->pinned_n < (size_t)nf * want) {
+    if (h->h_pinned) { CK(cudaStreamSynchronize(h->stream)); if (h->copy_stream) CK(cudaStreamSynchronize(h->copy_stream)); CK(cudaFreeHost(h->h_pinned)); h->h_pinned = nullptr; }
+    const size_t cap = (size_t)std::max(nf, 3) * want;
+    CK(cudaMallocHost(&h->h_pinned, cap * sizeof(double))); h->pinned_n = cap;
+    CK(cudaMalloc(&h->d_stage, cap * sizeof(double))); h->allocs.push_back(h->d_stage);
   }
   const size_t dp = (size_t)h->par.P * sizeof(double), sp = (size_t)h->ni * sizeof(double);
-  const double* src[3] = {sustr, svstr, stflux_temp};
-  const char* nm[3] = {"sustr", "svstr", "stflux_0"};
   // single tile: upload on the copy stream, overlapped with set_massflux / rho_eos / diag of this step (step_phases_body waits
-  // for ev_forcing before set_vbc).  With a ring attached the uploaded fields also need a halo exchange: keep them on the
-  // compute stream.
+  // for ev_forcing before bulk_flux / set_vbc).  With a ring attached the uploaded fields also need a halo exchange: keep them on
+  // the compute stream.
   cudaStream_t cps = h->stream;
-  if (!h->halo && (sustr || svstr || stflux_temp)) {
+  if (!h->halo && any) {
     if (!h->copy_stream) {
       CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&h->ev_forcing, cudaEventDisableTiming));
@@ -988,7 +996,7 @@ int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double*
     CK(cudaEventRecord(h->ev_step_in, h->stream));          // earlier asynchronous steps may still read the forcing arrays
     CK(cudaStreamWaitEvent(cps, h->ev_step_in, 0));
   }
-  for (int q = 0; q < 3; ++q) {
+  for (int q = 0; q < nf; ++q) {
     if (!src[q]) continue;
     const double* stage = src[q];
     if (!is_registered(h, src[q], want * sizeof(double))) {         // pageable caller memory: stage through the pinned buffer
@@ -1004,12 +1012,26 @@ int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double*
   if (cps != h->stream) CK(cudaEventRecord(h->ev_forcing, cps));
   if (h->halo) {
     std::vector<std::string> up;
-    for (int q = 0; q < 3; ++q) if (src[q]) up.push_back(nm[q]);
+    for (int q = 0; q < nf; ++q) if (src[q]) up.push_back(nm[q]);
     if (halo_exchange(h, up, h->stream)) return FatalError;
   }
   int rc = one_step(h, true);
   if (rc) return rc;
   return finish_diag(h, out12);
+}
+
+int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double* svstr, const double* stflux_temp, size_t n2d, double* out12) {
+  if (!h) return InputError;
+  const std::string st = "stflux_" + std::to_string(h->cfg.itemp - 1);
+  const char* nm[3] = {"sustr", "svstr", st.c_str()};
+  const double* src[3] = {sustr, svstr, stflux_temp};
+  return step_with_uploads(h, 3, nm, src, n2d, out12);
+}
+
+int roms_b200_step_fields(roms_b200_handle h, int nfields, const char* const* names, const double* const* arrays, size_t n2d, double* out12) {
+  if (!h || (nfields > 0 && (!names || !arrays))) return InputError;
+  for (int q = 0; q < nfields; ++q) if (!names[q]) return InputError;
+  return step_with_uploads(h, nfields, names, arrays, n2d, out12);
 }
 
 int roms_b200_register_host(roms_b200_handle h, void* p, size_t bytes) {

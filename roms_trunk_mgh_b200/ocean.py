@@ -134,6 +134,18 @@ class Tile:
             raise RomsB200Error("step_forced", rc)
         return dict(zip(DIAG_NAMES, list(out))), rc
 
+    def step_fields(self, fields):
+        """step_forced with any set of 2-D forcing arrays by name (roms_b200_step_fields), e.g. the atmosphere bulk_flux reads."""
+        names = list(fields)
+        arrs = [np.ascontiguousarray(fields[n], dtype=np.float64) for n in names]
+        cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        cp = (_lib.DP * len(names))(*[_dp(a) for a in arrs])
+        out = (C.c_double * 12)()
+        rc = self.L.roms_b200_step_fields(self.h, len(names), cn, cp, self.ni * self.nj, out)
+        if rc not in (0, 1):
+            raise RomsB200Error("step_fields", rc)
+        return dict(zip(DIAG_NAMES, list(out))), rc
+
     def register_host(self, *arrays):
         """Pin caller-owned forcing arrays (they must outlive the Tile or be released with unregister_host): step_forced
         then copies from them directly.  Mirrors what a Fortran host does once for FORCES(ng)%sustr, %svstr, %stflux."""

@@ -242,6 +242,11 @@ def build(app, Lm=0, Mm=0, N=0, **overrides):
     # ---- surface momentum stress at t = 0 (ana_smflux.h); see `sustr_at`
     F["sustr"] = sustr_at(app, g, cfg, 0.0)
     F["svstr"] = g.zeros()
+    if cfg.bulk_fluxes:
+        F.update(atmosphere_at(g, cfg, 0.0))                   # bulk_flux replaces the analytical stress / heat flux
+    if cfg.solar_source:
+        F["Jwtype"] = 1.0 * ones                                 # roms_benchmark1.in WTYPE == 1
+        F.setdefault("srflx", g.zeros())
     nfast, w1, w2 = set_weights(cfg.ndtfast)
     return cfg, F, (sc_r, Cs_r, sc_w, Cs_w), (nfast, w1, w2)
 
@@ -258,6 +263,42 @@ def sustr_at(app, g, cfg, tdays):
     if app == APP_BENCHMARK:
         return (0.1 / cfg.rho0 * np.sin(PI * (g.J - 0.5) / g.Mm)) * ones
     return 0.0 * ones
+
+
+ATMOSPHERE = ["Uwind", "Vwind", "Tair", "Pair", "Hair", "rain", "cloud", "srflx"]
+# the shipped benchmark.h set on top of the reduced one: BULK_FLUXES, LMD_MIXING (+SKPP, NONLOCAL, RIMIX, CONVEC, RI_SPLINES),
+# SOLAR_SOURCE, BV_FREQUENCY, MIX_GEO_TS
+FULL_BENCHMARK = dict(bv_frequency=1, eos_tderivative=1, solar_source=1, lmd_nonlocal=1, bulk_fluxes=1, lmd_mixing=1, mix_geo_ts=1)
+
+
+def atmosphere_at(g, cfg, tdays):
+    """The BENCHMARK analytical atmosphere set_data.F hands bulk_flux (global 2-D arrays, periodic images included):
+    ana_winds.h (15 m/s Gaussian jet at 60S), ana_tair.h (4 degC), ana_pair.h (1025 mb), ana_humid.h (0.8), ana_rain.h (0),
+    ana_cloud.h (0.6) and ana_srflux.h with ALBEDO (Zillman / Laevastu; day of year and hour from the model clock,
+    dateclock.F caldate with TIME_REF = 0, DSTART = 0)."""
+    Lm, Mm = g.Lm, g.Mm
+    ones = np.ones((g.nj, g.ni))
+    dx, dy = 360.0 / Lm, 20.0 / Mm
+    latr = (-70.0 + dy * (g.J - 0.5)) * ones
+    lonr = (dx * (g.I - 0.5)) * ones
+    A = dict(Tair=4.0 * ones, Pair=1025.0 * ones, Hair=0.8 * ones, rain=0.0 * ones, cloud=0.6 * ones, Vwind=0.0 * ones)
+    cff = 0.2 * (60.0 + latr)
+    A["Uwind"] = 15.0 * np.exp(-cff * cff)
+    whole = math.floor(tdays); frac = abs(tdays - whole)
+    yday = float(1 + int(whole) % 365) + frac; hour = 24.0 * frac
+    Dangle = 23.44 * math.cos((172.0 - yday) * 2.0 * PI / 365.2425) * DEG2RAD
+    Hangle = (12.0 - hour) * PI / 12.0
+    Rsolar = 1353.0 / (cfg.rho0 * 3985.0)                              # Csolar / (rho0*Cp), mod_scalars.F:431-432
+    LatRad = latr * DEG2RAD
+    zenith = np.sin(LatRad) * math.sin(Dangle) + np.cos(LatRad) * math.cos(Dangle) * np.cos(Hangle - lonr * DEG2RAD)
+    e_sat = 10.0 ** ((0.7859 + 0.03477 * A["Tair"]) / (1.0 + 0.00412 * A["Tair"]))
+    vap_p = e_sat * A["Hair"]
+    zz = np.maximum(zenith, 0.0)
+    sr = Rsolar * zz * zz * (1.0 - 0.6 * A["cloud"] ** 3) / ((zz + 2.7) * vap_p * 1.0e-3 + 1.085 * zz + 0.1)
+    A["srflx"] = (1.0 - 0.06) * np.where(zenith > 0.0, sr, 0.0)
+    for a in A.values():
+        g.exchange(a)
+    return A
 
 
 def tile_slice(a, Lm, bounds):

@@ -89,8 +89,8 @@ def test_driver_patch_names_existing_call_sites():
     """fortran/patches/b200_drivers.patch only adds lines, one CALL b200_routine per driver of the chain."""
     p = open(os.path.join(ROOT, "fortran", "patches", "b200_drivers.patch")).read()
     files = re.findall(r"^\+\+\+ b/(\S+)", p, re.M)
-    assert len(files) == 18 and len(set(files)) == 18
-    assert len(re.findall(r"^\+\s+CALL b200_routine \(ng, tile, B200_\w+\)", p, re.M)) == 18
+    assert len(files) == 20 and len(set(files)) == 20                 # the 18 drivers of the chain + bulk_flux.F, lmd_vmix.F
+    assert len(re.findall(r"^\+\s+CALL b200_routine \(ng, tile, B200_\w+\)", p, re.M)) == 20
     assert not re.findall(r"^-(?!--)", p, re.M)                        # nothing of the reference is removed
     ref = "/root/reference"
     if os.path.isdir(ref):                                             # not on the GPU box
