@@ -29,8 +29,9 @@ __global__ void __launch_bounds__(256) k_set_massflux(Par p, Flds f) {
 // rho_eos_tile: nonlinear (ROMS/Nonlinear/rho_eos.F:252-483, coefficients mod_eoscoef.F:24-64) and linear (:696-799).
 // One thread per column, top-down so that the VAR_RHO_2D integrals rhoA/rhoS accumulate in registers.
 // X: also return what BV_FREQUENCY (:402-418) and the expansion coefficients (:290-294, :330-339, :440-462) need
+// X = 1: the bulk-modulus terms bvf needs; X = 2: also the temperature / salinity derivatives (needed at level N only)
 struct EosX { double bulk, bulk0, bulk1, bulk2, Dden1DS, Dden1DT, DbulkDS, DbulkDT; };
-template <bool X>
+template <int X>
 __device__ __forceinline__ void eos_nl(double Tt, double Ts, double Tp, double& den, double& den1, EosX* x = nullptr) {
   const double A00 = +1.909256e+04, A01 = +2.098925e+02, A02 = -3.041638e+00, A03 = -1.852732e-03, A04 = -1.361629e-05;
   const double B00 = +1.044077e+02, B01 = -6.500517e+00, B02 = +1.553190e-01, B03 = +2.326469e-04;
@@ -62,7 +63,8 @@ __device__ __forceinline__ void eos_nl(double Tt, double Ts, double Tp, double& 
   const double bulk = bulk0 - Tp * (bulk1 - Tp * bulk2);
   const double cff = 1.0 / (bulk + Tpr10);
   den = den1 * bulk * cff;
-  if (X) {
+  if (X >= 1) { x->bulk = bulk; x->bulk0 = bulk0; x->bulk1 = bulk1; x->bulk2 = bulk2; }
+  if (X >= 2) {
     const double dC0 = Q01 + Tt * (2.0 * Q02 + Tt * (3.0 * Q03 + Tt * (4.0 * Q04 + Tt * 5.0 * Q05)));
     const double dC1 = U01 + Tt * (2.0 * U02 + Tt * (3.0 * U03 + Tt * 4.0 * U04));
     const double dC2 = V01 + Tt * 2.0 * V02;
@@ -73,7 +75,6 @@ __device__ __forceinline__ void eos_nl(double Tt, double Ts, double Tp, double& 
     const double dC7 = F01 + Tt * 2.0 * F02;
     const double dC8 = G02 + Tt * 2.0 * G03;
     const double dC9 = H01 + Tt * 2.0 * H02;
-    x->bulk = bulk; x->bulk0 = bulk0; x->bulk1 = bulk1; x->bulk2 = bulk2;
     x->Dden1DS = C1 + 1.5 * C2 * sqrtTs + 2.0 * W00 * Ts;
     x->Dden1DT = dC0 + Ts * (dC1 + sqrtTs * dC2);
     x->DbulkDS = C4 + sqrtTs * 1.5 * C5 - Tp * (C7 + sqrtTs * 1.5 * G00 - Tp * C9);
@@ -81,6 +82,9 @@ __device__ __forceinline__ void eos_nl(double Tt, double Ts, double Tp, double& 
   }
 }
 
+#ifndef EOS_PF
+#define EOS_PF 4          // L2 prefetch distance (levels) of k_rho_eos<true>
+#endif
 template <bool X>     // X: with the optional outputs bvf / alpha, beta (BV_FREQUENCY; LMD_SKPP || BULK_FLUXES)
 __global__ void __launch_bounds__(256) k_rho_eos(Par p, Flds f) {
   const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
@@ -94,6 +98,10 @@ __global__ void __launch_bounds__(256) k_rho_eos(Par p, Flds f) {
   EosX up; double den1_up = 0.0, den_up_lin = 0.0, zr_up = 0.0;      // level k+1 of the downward march (bvf at W-point k)
   for (int k = p.N; k >= 1; --k) {
     const int o = o2 + k * p.PL;
+    if (X) {               // the variant with bvf runs at half the occupancy of the plain one: start the fetch of lower levels early
+      pf_dn<EOS_PF>(T, o + i, k, p.PL); pf_dn<EOS_PF>(f.z_r, o + i, k, p.PL); pf_dn<EOS_PF>(Hz, o + i, k, p.PL); pf_dn<EOS_PF>(f.z_w, o + i, k, p.PL);
+      if (S) pf_dn<EOS_PF>(S, o + i, k, p.PL);
+    }
     double den, pd;
     EosX cur; double d1c = 0.0;
     const double zr = f.z_r[o + i];
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(256) k_rho_eos(Par p, Flds f) {
       const double Tt = dmax(-2.0, T[o + i]);
       const double Ts = S ? dmax(0.0, S[o + i]) : 0.0;
       double d, d1;
-      eos_nl<X>(Tt, Ts, zr, d, d1, &cur);
+      eos_nl<X ? 2 : 0>(Tt, Ts, zr, d, d1, &cur);
       den = d - 1000.0;
       pd = d1 - 1000.0;
       d1c = d1;

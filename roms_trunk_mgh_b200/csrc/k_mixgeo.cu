@@ -7,6 +7,9 @@
 
 namespace rb {
 
+#ifndef GEO_PF
+#define GEO_PF 4          // L2 prefetch distance (levels)
+#endif
 __global__ void __launch_bounds__(128) k_t3dmix2_geo(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -36,6 +39,8 @@ __global__ void __launch_bounds__(128) k_t3dmix2_geo(Par p, Flds f) {
   for (int k = 0; k <= N; ++k) {
     if (k < N) {
       const int o = o2 + (k + 1) * p.PL;
+      // start the DRAM fetch of the rows a few levels up (the neighbouring rows j-1, j+1 are fetched by their own threads)
+      pf_up<GEO_PF>(tr, o, k + 1, N, p.PL); pf_up<GEO_PF>(z_r, o, k + 1, N, p.PL); pf_up<GEO_PF>(Hz, o, k + 1, N, p.PL); pf_up<GEO_PF>(tn, o, k + 1, N, p.PL);
 #pragma unroll
       for (int c = 0; c < 5; ++c) { tk1[c] = tr[o + off[c]]; zk1[c] = z_r[o + off[c]]; }
       dZdx_c[0] = cxa * (zk1[0] - zk1[1]); dTdx_c[0] = cxa * (tk1[0] - tk1[1]);

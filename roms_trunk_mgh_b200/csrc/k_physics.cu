@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(128) k_bulk_flux(Par p, Flds f) {
   // first guesses, :616-624
   Wstar = delW * vonKar / (log(blk_ZW / Zo10) - bulk_psiu(blk_ZW / L10));
   double Tstar = -(delT - delTc) * vonKar / (log(blk_ZT / ZoT10) - bulk_psit(blk_ZT / L10));
+  // blk_ZQ == blk_ZT (the usual case, roms_benchmark1.in): the humidity terms repeat the temperature ones bit for bit
+  const bool zq_is_zt = (blk_ZQ == blk_ZT);
   double Qstar = -(delQ - delQc) * vonKar / (log(blk_ZQ / ZoT10) - bulk_psit(blk_ZQ / L10));
   // Charnock, :629-637
   double charn;
@@ -134,10 +136,12 @@ __global__ void __launch_bounds__(128) k_bulk_flux(Par p, Flds f) {
     const double L = blk_ZW / (ZoL + eps);
     const double Wpsi = bulk_psiu(ZoL);
     const double Tpsi = bulk_psit(blk_ZT / L);
-    const double Qpsi = bulk_psit(blk_ZQ / L);
+    const double Qpsi = zq_is_zt ? Tpsi : bulk_psit(blk_ZQ / L);
     Wstar = dmax(eps, delW * vonKar / (log(blk_ZW / ZoW) - Wpsi));
-    Tstar = -(delT - delTc) * vonKar / (log(blk_ZT / ZoT) - Tpsi);
-    Qstar = -(delQ - delQc) * vonKar / (log(blk_ZQ / ZoQ) - Qpsi);
+    const double lT = log(blk_ZT / ZoT);
+    const double lQ = zq_is_zt ? lT : log(blk_ZQ / ZoQ);                  // ZoT == ZoQ (:668)
+    Tstar = -(delT - delTc) * vonKar / (lT - Tpsi);
+    Qstar = -(delQ - delQc) * vonKar / (lQ - Qpsi);
     const double Bf = -g / TairK * Wstar * (Tstar + 0.61 * TairK * Qstar);
     if (Bf > 0.0) Wgus = blk_beta * pow(Bf * blk_Zabl, r3);
     else Wgus = 0.2;
@@ -204,11 +208,40 @@ __device__ __forceinline__ void lmd_wscale(double Ustar, double sigma, double Bf
 
 // lmd_vmix: lmd_vmix_tile (lmd_vmix.F:182-347), lmd_skpp_tile (lmd_skpp.F:246-923) and lmd_finish_tile (lmd_vmix.F:508-659) in one
 // pass, one thread per column.  The parabolic splines of the shear (dU, dV) are the same in lmd_vmix_tile and lmd_skpp_tile and are
-// built once; the interior coefficients live in thread-local columns until the boundary-layer values replace them above ksbl, so
-// Akv / Akt are written once.  The column Iend-1 copy of the eastern edge (lmd_vmix.F:568-575) is k_lmd_east.
-// NC > 0: N is the compile-time constant NC (thread-local columns sized for it).
+// built once.  Only the four spline columns live in thread-local memory: the shortwave fraction / buoyancy flux of a level and the
+// interior coefficients are evaluated where they are used (the boundary layer needs them at a few levels near the surface), so
+// Akv / Akt are written once and nothing else is staged.  The column Iend-1 copy of the eastern edge (lmd_vmix.F:568-575) is
+// k_lmd_east.  NC > 0: N is the compile-time constant NC (thread-local columns sized for it).
+#ifndef LMD_MINB
+#define LMD_MINB 4
+#endif
+#ifndef LMD_PF
+#define LMD_PF 6          // L2 prefetch distance (levels) of the upward spline sweep
+#endif
+struct LmdCol {           // per-column constants of the shortwave / buoyancy profile
+  double zwN, Bo, Bosol, fac1, fac2, fac3;
+};
+// lmd_swfrac.F:66-80 (Zscale = -1) and the total buoyancy flux (lmd_skpp.F:312-316) at depth Z below the surface
+__device__ __forceinline__ double lmd_swdk(const LmdCol& c, double Z) { return exp(Z * c.fac1) * c.fac3 + exp(Z * c.fac2) * (1.0 - c.fac3); }
+__device__ __forceinline__ double lmd_bflux(const LmdCol& c, double swdk) { return (c.Bo + c.Bosol * (1.0 - swdk)); }
+// interior coefficients of one level (lmd_vmix.F:230-234, :309-347): Richardson-number mixing + internal waves
+__device__ __forceinline__ void lmd_interior(double bv, double dUk, double dVk, double& av, double& at) {
+  const double e14 = 1.0e-14;
+  double shear2 = dUk * dUk + dVk * dVk;
+  const double Rig = bv / (shear2 + e14);
+  double cff = dmin(1.0, dmax(0.0, Rig) / lmd_Ri0);
+  double nu_sx = 1.0 - cff * cff;
+  nu_sx = nu_sx * nu_sx * nu_sx;
+  shear2 = bv / (Rig + e14);
+  cff = shear2 * shear2 / (shear2 * shear2 + 16.0e-10);
+  nu_sx = cff * nu_sx;
+  cff = 1.0 / sqrt(dmax(bv, 1.0e-7));
+  av = 1.0e-6 * cff + lmd_nu0m * nu_sx;
+  at = 1.0e-7 * cff + lmd_nu0s * nu_sx;
+}
+
 template <int NC>
-__global__ void __launch_bounds__(128) k_lmd_vmix(Par p, Flds f) {
+__global__ void __launch_bounds__(128, LMD_MINB) k_lmd_vmix(Par p, Flds f) {
   constexpr int NA = (NC > 0 ? NC : MAXN) + 1;
   const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -223,11 +256,13 @@ __global__ void __launch_bounds__(128) k_lmd_vmix(Par p, Flds f) {
   const double* __restrict__ bvf = f.bvf;
   const double* __restrict__ u = f.u[p.nstp];
   const double* __restrict__ v = f.v[p.nstp];
-  double FC[NA], dR[NA], dU[NA], dV[NA], Bfl[NA], sw[NA], Av[NA], At[NA];
+  double FC[NA], dR[NA], dU[NA], dV[NA];
   const double g = p.g, gorho0 = p.g / p.rho0, eps = 1.0e-10;
   const double lmd_Cg = lmd_Cstar * vonKar * pow(lmd_cs * vonKar * lmd_epsilon, 1.0 / 3.0);      // mod_scalars.F:4330
   const double Vtc = lmd_Cv * sqrt(-lmd_betaT) / (sqrt(lmd_cs * lmd_epsilon) * lmd_Ric * vonKar * vonKar);
-  const double zwN = z_w[q + N * PL];
+  LmdCol c;
+  c.zwN = z_w[q + N * PL];
+  const double zwN = c.zwN;
   const double stT = f.stflx[it_T][q], stS = salt ? f.stflx[it_S][q] : 0.0, sr = f.srflx[q], al = f.alpha[q];
   // lmd_skpp.F:256-290
   double sl_dpth = lmd_epsilon * (zwN - f.hsbl[q]);
@@ -236,59 +271,44 @@ __global__ void __launch_bounds__(128) k_lmd_vmix(Par p, Flds f) {
     const double a = 0.5 * (f.sustr[q] + f.sustr[q + 1]), b = 0.5 * (f.svstr[q] + f.svstr[q + P]);
     Ustar = sqrt(sqrt(a * a + b * b));
   }
-  double Bo;
-  if (salt) Bo = g * (al * (stT - sr) - f.beta[q] * stS);
-  else Bo = g * al * (stT - sr);
-  const double Bosol = g * al * sr;
-  // lmd_swfrac.F:66-80 (Zscale = -1) at every W level; total buoyancy flux and the start of ghats (lmd_skpp.F:302-328)
-  int J = (int)f.Jwtype[q];
-  J = (J < 1) ? 1 : (J > 9 ? 9 : J);
-  const double fac1 = -1.0 / k_lmd_mu1[J - 1], fac2 = -1.0 / k_lmd_mu2[J - 1], fac3 = k_lmd_r1[J - 1];
-  for (int k = 0; k <= N; ++k) {
-    const double Z = zwN - z_w[q + k * PL];
-    const double s = exp(Z * fac1) * fac3 + exp(Z * fac2) * (1.0 - fac3);
-    sw[k] = s;
-    Bfl[k] = (Bo + Bosol * (1.0 - s));
+  if (salt) c.Bo = g * (al * (stT - sr) - f.beta[q] * stS);
+  else c.Bo = g * al * (stT - sr);
+  c.Bosol = g * al * sr;
+  {
+    int J = (int)f.Jwtype[q];
+    J = (J < 1) ? 1 : (J > 9 ? 9 : J);
+    c.fac1 = -1.0 / k_lmd_mu1[J - 1]; c.fac2 = -1.0 / k_lmd_mu2[J - 1]; c.fac3 = k_lmd_r1[J - 1];
   }
-  // parabolic splines of pden, u, v at W points (lmd_skpp.F:342-377 == lmd_vmix.F:196-229 for dU, dV)
+  // parabolic splines of pden, u, v at W points, upward sweep (lmd_skpp.F:342-364 == lmd_vmix.F:196-216 for dU, dV); the operands
+  // of level k+2 are requested while level k is computed
   FC[0] = 0.0; dR[0] = 0.0; dU[0] = 0.0; dV[0] = 0.0;
   {
-    double hzk = Hz[q + PL], pdk = pden[q + PL];
-    double uk = u[q + PL], uek = u[q + 1 + PL], vk = v[q + PL], vnk = v[q + P + PL];
+    struct Lv { double hz, pd, u0, u1, v0, v1; };
+    auto ld = [&](int k) -> Lv {
+      const int o = q + k * PL;
+      pf_up<LMD_PF>(Hz, o, k, N, PL); pf_up<LMD_PF>(pden, o, k, N, PL); pf_up<LMD_PF>(u, o, k, N, PL); pf_up<LMD_PF>(v, o, k, N, PL);
+      return Lv{Hz[o], pden[o], u[o], u[o + 1], v[o], v[o + P]};
+    };
+    Lv a = ld(1), b = ld(2), n2 = b;
+#pragma unroll 2
     for (int k = 1; k <= N - 1; ++k) {
-      const int o = q + (k + 1) * PL;
-      const double hz1 = Hz[o], pd1 = pden[o], u1 = u[o], ue1 = u[o + 1], v1 = v[o], vn1 = v[o + P];
-      const double cff = 1.0 / (2.0 * hz1 + hzk * (2.0 - FC[k - 1]));
-      FC[k] = cff * hz1;
-      dR[k] = cff * (6.0 * (pd1 - pdk) - hzk * dR[k - 1]);
-      dU[k] = cff * (3.0 * (u1 - uk + ue1 - uek) - hzk * dU[k - 1]);
-      dV[k] = cff * (3.0 * (v1 - vk + vn1 - vnk) - hzk * dV[k - 1]);
-      hzk = hz1; pdk = pd1; uk = u1; uek = ue1; vk = v1; vnk = vn1;
+      if (k + 2 <= N) n2 = ld(k + 2);
+      const double cff = 1.0 / (2.0 * b.hz + a.hz * (2.0 - FC[k - 1]));
+      FC[k] = cff * b.hz;
+      dR[k] = cff * (6.0 * (b.pd - a.pd) - a.hz * dR[k - 1]);
+      dU[k] = cff * (3.0 * (b.u0 - a.u0 + b.u1 - a.u1) - a.hz * dU[k - 1]);
+      dV[k] = cff * (3.0 * (b.v0 - a.v0 + b.v1 - a.v1) - a.hz * dV[k - 1]);
+      a = b; b = n2;
     }
   }
+  // downward sweep (lmd_skpp.F:365-377) ...
   dR[N] = 0.0; dU[N] = 0.0; dV[N] = 0.0;
   for (int k = N - 1; k >= 1; --k) {
     dR[k] = dR[k] - FC[k] * dR[k + 1];
     dU[k] = dU[k] - FC[k] * dU[k + 1];
     dV[k] = dV[k] - FC[k] * dV[k + 1];
   }
-  // interior coefficients (lmd_vmix.F:230-234, :309-347): Richardson-number mixing + internal waves
-  for (int k = 1; k <= N - 1; ++k) {
-    const double e14 = 1.0e-14;
-    const double bv = bvf[q + k * PL];
-    double shear2 = dU[k] * dU[k] + dV[k] * dV[k];
-    const double Rig = bv / (shear2 + e14);
-    double cff = dmin(1.0, dmax(0.0, Rig) / lmd_Ri0);
-    double nu_sx = 1.0 - cff * cff;
-    nu_sx = nu_sx * nu_sx * nu_sx;
-    shear2 = bv / (Rig + e14);
-    cff = shear2 * shear2 / (shear2 * shear2 + 16.0e-10);
-    nu_sx = cff * nu_sx;
-    cff = 1.0 / sqrt(dmax(bv, 1.0e-7));
-    Av[k] = 1.0e-6 * cff + lmd_nu0m * nu_sx;
-    At[k] = 1.0e-7 * cff + lmd_nu0s * nu_sx;
-  }
-  // bulk Richardson criterion, top down, until FC changes sign (lmd_skpp.F:435-508, SASHA)
+  // ... and the bulk Richardson criterion, top down, until FC changes sign (lmd_skpp.F:435-508, SASHA)
   int ksbl = 1;
   double hsbl = z_w[q + PL];
   {
@@ -302,7 +322,7 @@ __global__ void __launch_bounds__(128) k_lmd_vmix(Par p, Flds f) {
       const int o = q + k * PL;
       const double zwm = z_w[o - PL];
       const double depth = zwN - zwm;
-      const double Bf = Bfl[k - 1];
+      const double Bf = lmd_bflux(c, lmd_swdk(c, depth));
       const double sigma = (Bf < 0.0) ? dmin(sl_dpth, depth) : depth;
       double wm, ws;
       lmd_wscale(Ustar, sigma, Bf, wm, ws);
@@ -325,9 +345,7 @@ __global__ void __launch_bounds__(128) k_lmd_vmix(Par p, Flds f) {
   // limits under stable forcing (lmd_skpp.F:551-589)
   const double zw0 = z_w[q];
   {
-    const double Z = zwN - hsbl;
-    const double s = exp(Z * fac1) * fac3 + exp(Z * fac2) * (1.0 - fac3);
-    const double Bfsfc = (Bo + Bosol * (1.0 - s));
+    const double Bfsfc = lmd_bflux(c, lmd_swdk(c, zwN - hsbl));
     if (Ustar > 0.0 && Bfsfc > 0.0) {
       const double hekman = lmd_cekman * Ustar / dmax(fabs(f.f[q]), eps);
       const double hmonob = lmd_cmonob * Ustar * Ustar * Ustar / dmax(vonKar * Bfsfc, eps);
@@ -342,12 +360,7 @@ __global__ void __launch_bounds__(128) k_lmd_vmix(Par p, Flds f) {
   for (int k = N; k >= 2; --k)
     if (z_w[q + (k - 1) * PL] < hsbl) { ksbl = k; break; }
   // buoyancy flux and velocity scales at hsbl (:666-737)
-  double Bfsfc;
-  {
-    const double Z = zwN - hsbl;
-    const double s = exp(Z * fac1) * fac3 + exp(Z * fac2) * (1.0 - fac3);
-    Bfsfc = (Bo + Bosol * (1.0 - s));
-  }
+  const double Bfsfc = lmd_bflux(c, lmd_swdk(c, zwN - hsbl));
   sl_dpth = lmd_epsilon * (zwN - hsbl);
   double wm, ws;
   {
@@ -366,18 +379,19 @@ __global__ void __launch_bounds__(128) k_lmd_vmix(Par p, Flds f) {
     const double cff_dn = cff * (hsbl - zkm);
     const double cff_up = cff * (zk - hsbl);
     // levels 1..N-1 hold this step's interior values; level N is whatever the array holds (never set by lmd_vmix)
-    const double avk = (k <= N - 1) ? Av[k] : f.Akv[q + k * PL], avm = Av[k - 1];
+    double avk, atk, ask, avm, atm;
+    lmd_interior(bvf[q + (k - 1) * PL], dU[k - 1], dV[k - 1], avm, atm);
+    if (k <= N - 1) { lmd_interior(bvf[q + k * PL], dU[k], dV[k], avk, atk); ask = atk; }
+    else { avk = f.Akv[q + k * PL]; atk = f.Akt[it_T][q + k * PL]; ask = salt ? f.Akt[it_S][q + k * PL] : 0.0; }
     double K_bl = cff_dn * avk + cff_up * avm;
     double dK_bl = cff * (avk - avm);
     Gm1 = K_bl / (zbl * wm + eps);
     dGm1dS = dmin(0.0, -dK_bl / (wm + eps) - K_bl * f1);
-    const double atk = (k <= N - 1) ? At[k] : f.Akt[it_T][q + k * PL], atm = At[k - 1];
     K_bl = cff_dn * atk + cff_up * atm;
     dK_bl = cff * (atk - atm);
     Gt1 = K_bl / (zbl * ws + eps);
     dGt1dS = dmin(0.0, -dK_bl / (ws + eps) - K_bl * f1);
     if (salt) {
-      const double ask = (k <= N - 1) ? At[k] : f.Akt[it_S][q + k * PL];
       K_bl = cff_dn * ask + cff_up * atm;
       dK_bl = cff * (ask - atm);
       Gs1 = K_bl / (zbl * ws + eps);
@@ -404,20 +418,26 @@ __global__ void __launch_bounds__(128) k_lmd_vmix(Par p, Flds f) {
   double* __restrict__ ghS = salt ? f.ghats[it_S] : nullptr;
   for (int k = 0; k <= N; k += N) {                           // levels 0 and N: ghats keeps its first value, Akv / Akt only get the copies
     const int o = o2 + k * PL;
-    const double c0 = 1.0 - (0.5 + copysign(0.5, Bfl[k]));
-    ghT[o + i] = -c0 * (stT - sr + sr * (1.0 - sw[k]));
+    const double swdk = lmd_swdk(c, zwN - z_w[o + i]);
+    const double c0 = 1.0 - (0.5 + copysign(0.5, lmd_bflux(c, swdk)));
+    ghT[o + i] = -c0 * (stT - sr + sr * (1.0 - swdk));
     if (salt) ghS[o + i] = c0 * stS;
     st_r_grad(Akv, o, i, j, Akv[o + i], p);
     st_r_grad(AkT, o, i, j, AkT[o + i], p);
     if (salt) st_r_grad(AkS, o, i, j, AkS[o + i], p);
   }
+#pragma unroll 2
   for (int k = 1; k <= N - 1; ++k) {
     const int o = o2 + k * PL;
-    double av = Av[k], at = At[k], as = At[k];
+    const double bv = bvf[o + i];
+    double av, at;
+    lmd_interior(bv, dU[k], dV[k], av, at);
+    double as = at;
     double gT = 0.0, gS = 0.0;
     if (k > ksbl) {
       const double depth = zwN - z_w[o + i];
-      const double Bf = Bfl[k];
+      const double swdk = lmd_swdk(c, depth);
+      const double Bf = lmd_bflux(c, swdk);
       double sigma = (Bf < 0.0) ? dmin(sl_dpth, depth) : depth;
       lmd_wscale(Ustar, sigma, Bf, wm, ws);
       sigma = depth / (zbl + eps);
@@ -432,12 +452,12 @@ __global__ void __launch_bounds__(128) k_lmd_vmix(Par p, Flds f) {
       }
       const double c0 = 1.0 - (0.5 + copysign(0.5, Bf));
       const double cff = lmd_Cg * c0 / (zbl * ws + eps);
-      gT = cff * (-c0 * (stT - sr + sr * (1.0 - sw[k])));
+      gT = cff * (-c0 * (stT - sr + sr * (1.0 - swdk)));
       gS = cff * (c0 * stS);
     }
     ghT[o + i] = gT;
     if (salt) ghS[o + i] = gS;
-    double cff = dmax(bvf[o + i], lmd_bvfcon);
+    double cff = dmax(bv, lmd_bvfcon);
     cff = dmin(1.0, (lmd_bvfcon - cff) / lmd_bvfcon);
     double nu_sxc = 1.0 - cff * cff;
     nu_sxc = nu_sxc * nu_sxc * nu_sxc;

@@ -70,7 +70,12 @@ __global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
     mN = 0.25 * (d2[q + P] + d0) * f.pnom_v[q + P];
     mcff = p.dt * pm * pn;
   }
-  struct Lvl { AdvIn a; double tnw, hz, W, zr1, akt, tk3, hzW, hzE, hzS, hzN; };
+  // optional terms of the vertical flux FC (benchmark.h): KPP nonlocal transport of the active tracers (:850-865) and, for
+  // temperature, the penetrating shortwave radiation (:312-333 with lmd_swfrac.F:66-80, Zscale = -1; :866-883)
+  const bool nonloc = SRC && p.lmd_nonlocal && itrc < (p.salinity ? 2 : 1);
+  const bool solar = SRC && p.solar_source && itrc == p.itemp - 1;
+  const double* __restrict__ ghats = nonloc ? f.ghats[itrc] : nullptr;
+  struct Lvl { AdvIn a; double tnw, hz, W, zr1, akt, tk3, hzW, hzE, hzS, hzN, gh, zw; };
   auto load_level = [&](int k) -> Lvl {
     const int o = o2 + k * p.PL;
     Lvl L;
@@ -81,14 +86,13 @@ __global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
     if (MIXS) { L.hzW = Hz[o + i - 1]; L.hzE = Hz[o + i + 1]; L.hzS = Hz[o - P + i]; L.hzN = Hz[o + P + i]; }
     L.zr1 = z_r[o + ((k < N) ? p.PL : 0) + i];                   // z_r(k+1) (k = N: unused)
     L.tk3 = tst[o2 + ((k + 2 <= N) ? (k + 2) : N) * p.PL + i];   // t(k+2), clamped
+    if (SRC) {                                                   // operands of the optional flux terms, requested with the rest
+      L.gh = nonloc ? ghats[o + i] : 0.0;
+      L.zw = solar ? f.z_w[o + i] : 0.0;
+    }
     return L;
   };
   const double cff3 = p.dt * (1.0 - p.lambda);
-  // optional terms of the vertical flux FC (benchmark.h): KPP nonlocal transport of the active tracers (:850-865) and, for
-  // temperature, the penetrating shortwave radiation (:312-333 with lmd_swfrac.F:66-80, Zscale = -1; :866-883)
-  const bool nonloc = SRC && p.lmd_nonlocal && itrc < (p.salinity ? 2 : 1);
-  const bool solar = SRC && p.solar_source && itrc == p.itemp - 1;
-  const double* __restrict__ ghats = nonloc ? f.ghats[itrc] : nullptr;
   double sw_fac1 = 0.0, sw_fac2 = 0.0, sw_fac3 = 0.0, sw_srflx = 0.0, sw_zwN = 0.0;
   if (solar) {
     int J = (int)f.Jwtype[o2 + i];
@@ -119,9 +123,9 @@ __global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
     if (k < N) {
       const double c = 1.0 / (cur.zr1 - zrk);
       FDk = cff3 * c * cur.akt * (tkp1 - tk);
-      if (SRC && nonloc) FDk = FDk - p.dt * cur.akt * ghats[o + i];
+      if (SRC && nonloc) FDk = FDk - p.dt * cur.akt * cur.gh;
       if (SRC && solar) {
-        const double Z = sw_zwN - f.z_w[o + i];
+        const double Z = sw_zwN - cur.zw;
         const double swdk = exp(Z * sw_fac1) * sw_fac3 + exp(Z * sw_fac2) * (1.0 - sw_fac3);
         FDk = FDk + p.dt * sw_srflx * swdk;
       }

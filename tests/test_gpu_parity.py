@@ -493,6 +493,31 @@ def test_bench_workload_parity_synth_make_tile():
     t.close()
 
 
+def test_full_benchmark_cpp_set_at_full_size():
+    """The shipped benchmark.h cpp set (synth.FULL_BENCHMARK: + BULK_FLUXES, LMD_MIXING / SKPP / NONLOCAL, SOLAR_SOURCE,
+    BV_FREQUENCY, MIX_GEO_TS) on BENCHMARK3 2048x256x30 exactly as bench.py's full_benchmark_row runs it: production library,
+    graph-replayed steps, the atmosphere of each model time uploaded through roms_b200_step_fields; against the oracle started
+    from its own set-up.  KPP has a discrete boundary-layer index: it must agree in all but a handful of the 524288 columns."""
+    nth = _oracle_threads()
+    Lm, Mm, N = 2048, 256, 30
+    t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, **synth.FULL_BENCHMARK)
+    kw = {k: v for k, v in synth.FULL_BENCHMARK.items()}
+    o = orc.Oracle(orc.APP_BENCHMARK, Lm=Lm, Mm=Mm, N=N, NtileI=nth, NtileJ=1, **kw)
+    o.run_phase("set_data"); o.run_phase("ini")
+    g, b = t.synth["grid"], t.synth["bounds"]
+    for s in range(5):
+        atm = {n: synth.tile_slice(v, Lm, b) for n, v in synth.atmosphere_at(g, t.cfg, t.indices()["time"] / 86400.0).items()}
+        d, rc = t.step_fields(atm)
+        o.step(1, nth)
+        assert rc == 0
+    assert not compare(o, t, ["zeta1", "zeta2", "u1", "u2", "v1", "v2", "ubar1", "vbar1", "sustr", "stflux_0"], exact=False, rtol=1e-8)
+    assert not compare(o, t, ["t1_0", "t2_0", "t1_1", "t2_1", "rho", "hsbl", "Akv", "Akt_0"], exact=False, rtol=1e-9)
+    ka, kb = o.field("ksbl"), t.get("ksbl")
+    assert np.count_nonzero(ka != kb) <= 8, np.count_nonzero(ka != kb)
+    assert d["avgke"] > 0 and len(np.unique(ka[0, 1:-1, 3:-3])) > 1
+    t.close()
+
+
 def test_full_size_benchmark3_smoke():
     """BENCHMARK3 (2048x256x30), the bench workload: runs, conserves volume, stays finite, images consistent."""
     t = synth.make_tile(synth.APP_BENCHMARK, 2048, 256, 30)
