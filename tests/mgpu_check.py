@@ -24,7 +24,9 @@ def main():
     Lm, Mm, N = (int(x) for x in (pos[0:3] if len(pos) >= 3 else (256, 64, 30)))
     nsteps = int(pos[3]) if len(pos) >= 4 else 6
     peer = opts.pop("peer", "1") != "0"
-    t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, NtileI=world, tile=rank, device=local)
+    # physics=full: the shipped benchmark.h cpp set (bulk_flux + lmd_vmix on the device, synth.FULL_BENCHMARK)
+    phys = synth.FULL_BENCHMARK if opts.pop("physics", "reduced") == "full" else {}
+    t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, NtileI=world, tile=rank, device=local, **phys)
     for k, v in opts.items():
         t.set_option(k, float(v))
     multigpu.attach(t, dist, rank, world, peer=peer)
@@ -36,11 +38,13 @@ def main():
     t.main3d(nsteps)
     d = t.diag()
     names = ["zeta1", "zeta2", "ubar1", "vbar1", "u1", "u2", "v1", "v2", "t1_0", "t2_0", "t1_1", "t2_1", "Huon", "Hvom", "W", "rho"]
+    if phys:
+        names += ["Akv", "Akt_0", "Akt_1", "hsbl", "sustr", "svstr", "stflux_0", "lrflx", "lhflx", "shflx", "bvf"]
     allb = [_lib.bounds(Lm, Mm, world, 1, r, distribute=True) for r in range(world)]
     ok = True
     ref = None
     if rank == 0:
-        ref = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, device=local)
+        ref = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, device=local, **phys)
         ref.main3d(nsteps)
     for n in names:
         a = torch.from_numpy(t.get(n)).cuda()
@@ -70,7 +74,7 @@ def main():
                     ok = False; print(f"  diag {k}: {d[k]!r} vs {dr[k]!r}", flush=True)
             elif d[k] != dr[k]:
                 ok = False; print(f"  diag {k}: {d[k]!r} vs {dr[k]!r}", flush=True)
-        print(f"MGPU_CHECK world={world} grid={Lm}x{Mm}x{N} steps={nsteps}:", "BITWISE-IDENTICAL" if ok else "FAILED", flush=True)
+        print(f"MGPU_CHECK world={world} physics={'full' if phys else 'reduced'} grid={Lm}x{Mm}x{N} steps={nsteps}:", "BITWISE-IDENTICAL" if ok else "FAILED", flush=True)
     perr = t.L.roms_b200_peer_error(t.h)
     if perr:
         print(f"rank {rank}: peer exchange timed out", flush=True)
