@@ -45,4 +45,12 @@ for name, (app, kw, nsteps) in GOLD_CASES.items():
     NT = int(o.opt("NT"))
     names = ["zeta1", "ubar1", "vbar1", "u1", "v1", "rho", "W"] + [f"t1_{it}" for it in range(NT)]
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **{n: o.field(n).copy() for n in names})
+# the shipped BENCHMARK cpp set minus MIX_GEO_TS (bulk_flux + lmd_vmix + the in-chain terms) on a small channel: 16 steps, so that
+# the surface boundary layer has started to deepen (ksbl takes two values)
+FULL = dict(bv_frequency=1, eos_tderivative=1, solar_source=1, lmd_nonlocal=1, bulk_fluxes=1, lmd_mixing=1)
+o = orc.Oracle(orc.APP_BENCHMARK, Lm=32, Mm=24, N=30, **FULL)
+o.run_phase("set_data"); o.run_phase("ini")
+o.step(16)
+names = ["zeta1", "ubar1", "u1", "t1_0", "Akv", "Akt_1", "hsbl", "ksbl", "ghats_0", "sustr", "stflux_0", "lhflx", "shflx", "lrflx"]
+np.savez_compressed(os.path.join(HERE, "benchmark_fullphysics_32x24x30_16steps.npz"), **{n: o.field(n).copy() for n in names})
 print("golden fixtures written")

@@ -627,6 +627,30 @@ def test_tiling_invariance_across_gpus(mode):
     assert r.returncode == 0 and "BITWISE-IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_cuda_path_against_the_full_physics_golden_vector():
+    """tests/golden/benchmark_fullphysics_32x24x30_16steps.npz (oracle-generated, make_golden.py): 16 steps of the BENCHMARK set
+    with bulk_flux and lmd_vmix on the device, the host refreshing the shortwave flux; strict and production library within
+    1e-9 (pow / exp / log / atan differ from glibc's in the last bits), the boundary-layer index exactly."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "benchmark_fullphysics_32x24x30_16steps.npz"))
+    for strict in (True, False):
+        o = orc.Oracle(orc.APP_BENCHMARK, Lm=32, Mm=24, N=30, **FULL_BENCHMARK)
+        o.run_phase("set_data"); o.run_phase("ini")
+        t = Tile(cfg_from_oracle(o), strict=strict)
+        copy_state(o, t)
+        for s in range(16):
+            begin_step(o, t)                                  # the oracle only supplies the shortwave flux of this model time
+            o.step(1)
+            t.main3d(1)
+        assert len(np.unique(g["ksbl"][0, 1:-1, 3:-3])) > 1
+        for n in g.files:
+            a, b = g[n], t.get(n)
+            if n == "ksbl":
+                assert np.array_equal(a, b), (strict, n)
+            else:
+                assert _rel(a, b) <= 1e-9, (strict, n, _rel(a, b))
+        t.close()
+
+
 GOLDEN = {"seamount_6steps": ("seamount", 6), "benchmark_64x32x10_6steps": ("benchmark", 6), "upwelling_10steps": ("upwelling", 10)}
 
 

@@ -214,7 +214,10 @@ def test_cabi_rejects_bad_config_and_has_no_cpu_fallback():
 
 
 @pytest.mark.parametrize("name,app,kw,nsteps", [("seamount_6steps", orc.APP_SEAMOUNT, {}, 6),
-                                                ("benchmark_64x32x10_6steps", orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10), 6)])
+                                                ("benchmark_64x32x10_6steps", orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10), 6),
+                                                ("benchmark_fullphysics_32x24x30_16steps", orc.APP_BENCHMARK,
+                                                 dict(Lm=32, Mm=24, N=30, bv_frequency=1, eos_tderivative=1, solar_source=1, lmd_nonlocal=1,
+                                                      bulk_fluxes=1, lmd_mixing=1), 16)])
 def test_oracle_regression_golden_vectors(name, app, kw, nsteps):
     """Self-generated regression vectors (tests/golden/make_golden.py, marked oracle_generated there): the state the GPU
     parity tests must reproduce; here they pin the oracle itself against accidental edits."""
