@@ -33,7 +33,7 @@ typedef struct roms_b200_state* roms_b200_handle;
 enum { ROMS_B200_APP_UPWELLING = 0, ROMS_B200_APP_SEAMOUNT = 1, ROMS_B200_APP_BENCHMARK = 2 };
 /* Hadvection / Vadvection keywords of roms_*.in (ROMS/Modules/mod_param.F:382-394, T_ADV) */
 enum { ROMS_B200_HADV_U3 = 0, ROMS_B200_HADV_A4 = 1, ROMS_B200_HADV_C4 = 2, ROMS_B200_HADV_C2 = 3 };
-enum { ROMS_B200_VADV_C4 = 0, ROMS_B200_VADV_A4 = 1, ROMS_B200_VADV_C2 = 2 };
+enum { ROMS_B200_VADV_C4 = 0, ROMS_B200_VADV_A4 = 1, ROMS_B200_VADV_C2 = 2, ROMS_B200_VADV_SPLINES = 3 };
 
 /* Live cpp switches (ROMS/Include/{upwelling,seamount,benchmark}.h) + roms_*.in keywords for this path. */
 typedef struct roms_b200_config {

@@ -88,7 +88,22 @@ void pre_step3d(Model& m, const Bnd& b) {
   for (int j = Jstr; j <= Jend; ++j) {
     for (int itrc = 0; itrc < NT; ++itrc) {
       F3 tst = m.t[nstp][itrc], t3 = m.t[3][itrc];
-      if (c.vadv == VADV_A4) {                                  // :667-707
+      if (c.vadv == VADV_SPLINES) {                              // :622-665: conservative parabolic splines (NEUMANN, pre_step3d.F:4)
+        for (int i = Istr; i <= Iend; ++i) { FC(i, 0) = 1.5 * tst(i, j, 1); CF(i, 1) = 0.5; }
+        for (int k = 1; k <= N - 1; ++k)
+          for (int i = Istr; i <= Iend; ++i) {
+            const double cff = 1.0 / (2.0 * Hz(i, j, k) + Hz(i, j, k + 1) * (2.0 - CF(i, k)));
+            CF(i, k + 1) = cff * Hz(i, j, k);
+            FC(i, k) = cff * (3.0 * (Hz(i, j, k) * tst(i, j, k + 1) + Hz(i, j, k + 1) * tst(i, j, k)) - Hz(i, j, k + 1) * FC(i, k - 1));
+          }
+        for (int i = Istr; i <= Iend; ++i) FC(i, N) = (3.0 * tst(i, j, N) - FC(i, N - 1)) / (2.0 - CF(i, N));
+        for (int k = N - 1; k >= 0; --k)
+          for (int i = Istr; i <= Iend; ++i) {
+            FC(i, k) = FC(i, k) - CF(i, k + 1) * FC(i, k + 1);
+            FC(i, k + 1) = W(i, j, k + 1) * FC(i, k + 1);
+          }
+        for (int i = Istr; i <= Iend; ++i) { FC(i, N) = 0.0; FC(i, 0) = 0.0; }
+      } else if (c.vadv == VADV_A4) {                                  // :667-707
         for (int k = 1; k <= N - 1; ++k) for (int i = Istr; i <= Iend; ++i) FC(i, k) = tst(i, j, k + 1) - tst(i, j, k);
         for (int i = Istr; i <= Iend; ++i) { FC(i, 0) = FC(i, 1); FC(i, N) = FC(i, N - 1); }
         for (int k = 1; k <= N; ++k)

@@ -115,7 +115,7 @@ struct Bnd {
 // Application identifiers (ROMS/Include/{upwelling,seamount,benchmark}.h)
 enum App { APP_UPWELLING = 0, APP_SEAMOUNT = 1, APP_BENCHMARK = 2 };
 enum HAdv { HADV_U3 = 0, HADV_A4 = 1, HADV_C4 = 2, HADV_C2 = 3 };
-enum VAdv { VADV_C4 = 0, VADV_A4 = 1, VADV_C2 = 2 };
+enum VAdv { VADV_C4 = 0, VADV_A4 = 1, VADV_C2 = 2, VADV_SPLINES = 3 };
 
 // Run configuration = the live cpp switches + roms_*.in keywords of the three applications.
 struct Cfg {

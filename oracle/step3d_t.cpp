@@ -87,7 +87,22 @@ void step3d_t(Model& m, const Bnd& b) {
   for (int itrc = 0; itrc < NT; ++itrc) {
     F3 t3 = m.t[3][itrc], tn = m.t[nnew][itrc];
     for (int j = Jstr; j <= Jend; ++j) {
-      if (c.vadv == VADV_A4) {
+      if (c.vadv == VADV_SPLINES) {                              // step3d_t.F:894-937: conservative parabolic splines (not NEUMANN here)
+        for (int i = Istr; i <= Iend; ++i) { FC(i, 0) = 2.0 * t3(i, j, 1); CF(i, 1) = 1.0; }
+        for (int k = 1; k <= N - 1; ++k)
+          for (int i = Istr; i <= Iend; ++i) {
+            const double cff = 1.0 / (2.0 * Hz(i, j, k) + Hz(i, j, k + 1) * (2.0 - CF(i, k)));
+            CF(i, k + 1) = cff * Hz(i, j, k);
+            FC(i, k) = cff * (3.0 * (Hz(i, j, k) * t3(i, j, k + 1) + Hz(i, j, k + 1) * t3(i, j, k)) - Hz(i, j, k + 1) * FC(i, k - 1));
+          }
+        for (int i = Istr; i <= Iend; ++i) FC(i, N) = (2.0 * t3(i, j, N) - FC(i, N - 1)) / (1.0 - CF(i, N));
+        for (int k = N - 1; k >= 0; --k)
+          for (int i = Istr; i <= Iend; ++i) {
+            FC(i, k) = FC(i, k) - CF(i, k + 1) * FC(i, k + 1);
+            FC(i, k + 1) = W(i, j, k + 1) * FC(i, k + 1);
+          }
+        for (int i = Istr; i <= Iend; ++i) { FC(i, N) = 0.0; FC(i, 0) = 0.0; }
+      } else if (c.vadv == VADV_A4) {
         for (int k = 1; k <= N - 1; ++k) for (int i = Istr; i <= Iend; ++i) FC(i, k) = t3(i, j, k + 1) - t3(i, j, k);
         for (int i = Istr; i <= Iend; ++i) { FC(i, 0) = FC(i, 1); FC(i, N) = FC(i, N - 1); }
         for (int k = 1; k <= N; ++k)

@@ -105,6 +105,8 @@ __device__ __forceinline__ double vflux4(double tkm1, double tk, double tkp1, do
     if (k == 1) return Wk * (0.5 * tk + (7.0 / 12.0) * tkp1 - (1.0 / 12.0) * tkp2);
     if (k == N - 1) return Wk * (0.5 * tkp1 + (7.0 / 12.0) * tk - (1.0 / 12.0) * tkm1);
     return Wk * ((7.0 / 12.0) * (tk + tkp1) - (1.0 / 12.0) * (tkm1 + tkp2));
+  } else if (VADV == 3) {
+    return 0.0;                                   // SPLINES: the flux comes from vspline_flux, not from the rolling window
   } else if (VADV == 1) {
     const double eps = 1.0e-16;
     const double dk = tkp1 - tk;
@@ -118,6 +120,30 @@ __device__ __forceinline__ double vflux4(double tkm1, double tk, double tkp1, do
   } else {
     return Wk * 0.5 * (tk + tkp1);
   }
+}
+
+// SPLINES vertical advection (pre_step3d.F:622-665 with NEUMANN, step3d_t.F:894-937 without): interfacial tracer values from
+// conservative parabolic splines -- a tridiagonal solve along the column -- times W.  FCs / CFs: thread-local columns (0:N);
+// on return FCs(k) is the vertical advective flux through W level k.  q = offset of (i,j) in level 0.
+template <bool NEUMANN>
+__device__ __forceinline__ void vspline_flux(const double* __restrict__ T, const double* __restrict__ Hz, const double* __restrict__ W,
+                                             int q, int N, int PL, double* FCs, double* CFs) {
+  double tk = T[q + PL], hk = Hz[q + PL];
+  FCs[0] = (NEUMANN ? 1.5 : 2.0) * tk;
+  CFs[1] = NEUMANN ? 0.5 : 1.0;
+  for (int k = 1; k <= N - 1; ++k) {
+    const double t1 = T[q + (k + 1) * PL], h1 = Hz[q + (k + 1) * PL];
+    const double cff = 1.0 / (2.0 * hk + h1 * (2.0 - CFs[k]));
+    CFs[k + 1] = cff * hk;
+    FCs[k] = cff * (3.0 * (hk * t1 + h1 * tk) - h1 * FCs[k - 1]);
+    tk = t1; hk = h1;
+  }
+  FCs[N] = ((NEUMANN ? 3.0 : 2.0) * tk - FCs[N - 1]) / ((NEUMANN ? 2.0 : 1.0) - CFs[N]);
+  for (int k = N - 1; k >= 0; --k) {
+    FCs[k] = FCs[k] - CFs[k + 1] * FCs[k + 1];
+    FCs[k + 1] = W[q + (k + 1) * PL] * FCs[k + 1];
+  }
+  FCs[N] = 0.0; FCs[0] = 0.0;
 }
 
 }  // namespace rb

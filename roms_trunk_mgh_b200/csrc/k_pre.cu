@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
     sw_fac1 = -1.0 / c_lmd_mu1[J - 1]; sw_fac2 = -1.0 / c_lmd_mu2[J - 1]; sw_fac3 = c_lmd_r1[J - 1];
     sw_srflx = f.srflx[o2 + i]; sw_zwN = f.z_w[o2 + N * p.PL + i];
   }
+  double FCs[VADV == 3 ? MAXN + 1 : 1], CFs[VADV == 3 ? MAXN + 1 : 1];
+  if (VADV == 3) vspline_flux<true>(tst, Hz, W, o2 + i, N, p.PL, FCs, CFs);       // SPLINES (NEUMANN: pre_step3d.F:4)
   double FCm = 0.0;                                   // advective FC(k-1)
   double FDm = p.dt * f.btflx[itrc][o2 + i];          // diffusive FC(k-1), FC(0) = dt*btflx
   double Wm = W[o2 + i];                              // W(k-1)
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
     const double div = FXip - FXi + FEjp - FEj;
     double t3v = hz * (cff1h * tk + cff2h * cur.tnw) - cff * pm * pn * div;
     const double Wk = cur.W;
-    const double FCk = (k < N) ? vflux4<VADV>(tkm1, tk, tkp1, tkp2, k, N, Wk) : 0.0;
+    const double FCk = (VADV == 3) ? FCs[VADV == 3 ? k : 0] : ((k < N) ? vflux4<VADV>(tkm1, tk, tkp1, tkp2, k, N, Wk) : 0.0);
     const double DC = 1.0 / (hz - cff * pm * pn * (cur.a.hu1 - cur.a.hu0 + cur.a.hv1 - cur.a.hv0 + (Wk - Wm)));
     const double cff1 = cff * pm * pn;
     t3v = DC * (t3v - cff1 * (FCk - FCm));
@@ -460,12 +462,14 @@ static void launch_pre_t_v(const Par& p, const Flds& f, cudaStream_t s) {
   if (p.fuse_tmix) {
     if (p.vadv == 0) k_pre_step3d_t<H, 0, true, SRC><<<g, b, 0, s>>>(p, f);
     else if (p.vadv == 1) k_pre_step3d_t<H, 1, true, SRC><<<g, b, 0, s>>>(p, f);
-    else k_pre_step3d_t<H, 2, true, SRC><<<g, b, 0, s>>>(p, f);
+    else if (p.vadv == 2) k_pre_step3d_t<H, 2, true, SRC><<<g, b, 0, s>>>(p, f);
+    else k_pre_step3d_t<H, 3, true, SRC><<<g, b, 0, s>>>(p, f);
     return;
   }
   if (p.vadv == 0) k_pre_step3d_t<H, 0, false, SRC><<<g, b, 0, s>>>(p, f);
   else if (p.vadv == 1) k_pre_step3d_t<H, 1, false, SRC><<<g, b, 0, s>>>(p, f);
-  else k_pre_step3d_t<H, 2, false, SRC><<<g, b, 0, s>>>(p, f);
+  else if (p.vadv == 2) k_pre_step3d_t<H, 2, false, SRC><<<g, b, 0, s>>>(p, f);
+  else k_pre_step3d_t<H, 3, false, SRC><<<g, b, 0, s>>>(p, f);
 }
 template <int H>
 static void launch_pre_t_h(const Par& p, const Flds& f, cudaStream_t s) {

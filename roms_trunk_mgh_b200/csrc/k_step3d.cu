@@ -306,6 +306,8 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
     L.tk3 = t3[o2 + ((k + 2 <= N) ? (k + 2) : N) * PL + i];                // t(k+2), clamped
     return L;
   };
+  double FCs[VADV == 3 ? MAXN + 1 : 1], CFs[VADV == 3 ? MAXN + 1 : 1];
+  if (VADV == 3) vspline_flux<false>(t3, Hz, W, o2 + i, N, PL, FCs, CFs);         // SPLINES (step3d_t.F:894-937)
   double AKm = Akt[o2 + i], AKmm = 0.0, AKN;
   {
     double tkm1 = t3[o2 + PL + i], tk = tkm1, tkp1 = t3[o2 + 2 * PL + i], tkp2 = t3[o2 + 3 * PL + i];
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
       const double c3 = c1 + c2;
       double tv = cur.tn - c3;
       // vertical (:1189-1207)
-      const double FCk = (k < N) ? vflux4<VADV>(tkm1, tk, tkp1, tkp2, k, N, cur.W) : 0.0;
+      const double FCk = (VADV == 3) ? FCs[VADV == 3 ? k : 0] : ((k < N) ? vflux4<VADV>(tkm1, tk, tkp1, tkp2, k, N, cur.W) : 0.0);
       const double cv = cffh * (FCk - FCm);
       tv = tv - cv;
       tv = tv * ok;
@@ -430,7 +432,8 @@ template <int H>
 static void launch_s3t_v(const Par& p, const Flds& f, cudaStream_t s) {
   if (p.vadv == 0) launch_s3t<H, 0>(p, f, s);
   else if (p.vadv == 1) launch_s3t<H, 1>(p, f, s);
-  else launch_s3t<H, 2>(p, f, s);
+  else if (p.vadv == 2) launch_s3t<H, 2>(p, f, s);
+  else launch_s3t<H, 3>(p, f, s);
 }
 void launch_step3d_t(const Par& p, const Flds& f, cudaStream_t s) {
   if (p.hadv == 0) launch_s3t_v<0>(p, f, s);

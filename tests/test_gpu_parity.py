@@ -28,6 +28,7 @@ CASES = {
     "benchmark30": (orc.APP_BENCHMARK, dict(Lm=96, Mm=40, N=30)),                    # compile-time-N fast paths
     "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, mix_geo_ts=1)),    # MIX_GEO_TS with tnu2 = 500
     "benchmark_p31": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, dj_gradps=0, nonlin_eos=0)),   # prsgrd31 + linear EOS
+    "benchmark_splines": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, vadv=3)),      # Vadvection = SPLINES (tridiagonal solve per column)
     "ragged": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7)),                          # sizes that are no multiple of any tile
 }
 

@@ -600,3 +600,21 @@ def test_synth_atmosphere_matches_the_oracle():
             ref = o.field(n)[0]
             assert np.max(np.abs(A[n] - ref)) <= 1e-13 * max(np.max(np.abs(ref)), 1e-300), (n, tdays)
     assert o.field("srflx").max() > 1e-4
+
+
+def test_splines_vertical_advection_properties():
+    """Vadvection = SPLINES (pre_step3d.F:622-665, step3d_t.F:894-937): a constant tracer stays constant (the spline of a constant
+    is that constant and the flux divergence cancels against the pseudo-compressible divide), volume is conserved, and the
+    solution stays close to the CENTERED4 one (both are fourth-order in the interior)."""
+    runs = {}
+    for vadv in (0, 3):
+        o = orc.Oracle(orc.APP_BENCHMARK, Lm=48, Mm=32, N=20, vadv=vadv, kind="chk")
+        o.run_phase("set_data"); o.run_phase("ini")
+        v0 = o.diag()["volume"]
+        o.step(30)
+        d = o.diag()
+        assert abs(d["volume"] - v0) <= 1e-12 * v0 and o.indices()["exit_flag"] == 0
+        assert np.max(np.abs(o.field("t1_1")[:, 1:-1, 3:-3] - 35.0)) < 1e-11
+        runs[vadv] = o.field("t1_0").copy()
+    dT = np.max(np.abs(runs[0] - runs[3]))
+    assert 0.0 < dT < 1e-4, dT
