@@ -41,8 +41,17 @@ DIGEST_FIELDS = ["zeta1", "zeta2", "ubar1", "ubar2", "vbar1", "vbar2", "u1", "u2
 HISTORY_FIELDS = ["zeta1", "ubar1", "vbar1", "u1", "v1", "t1_0", "t1_1", "rho", "W"]     # what a history record holds (wrt_his.F)
 
 
-def workload(grid, Lm, Mm, N, ndtfast=20, nfast=29, mix_geo=False):
+# The shipped ROMS/Include/benchmark.h cpp set on top of the reduced one (oracle option names == roms_b200_config members):
+# BULK_FLUXES (+LONGWAVE), LMD_MIXING (+RIMIX, CONVEC, SKPP, NONLOCAL, RI_SPLINES), SOLAR_SOURCE, BV_FREQUENCY, MIX_GEO_TS
+FULL_BENCHMARK = dict(bv_frequency=1, eos_tderivative=1, solar_source=1, lmd_nonlocal=1, bulk_fluxes=1, lmd_mixing=1, mix_geo_ts=1)
+
+
+def workload(grid, Lm, Mm, N, ndtfast=20, nfast=29, mix_geo=False, physics="full"):
     """The workload string both arms print (config.workload)."""
+    if physics == "full":
+        return (f"{grid.upper()} {Lm}x{Mm}x{N}, NT=2, the shipped benchmark.h cpp set (NONLIN_EOS, DJ_GRADPS, U3/C4, UV_VIS2, TS_DIF2 MIX_GEO_TS, UV_QDRAG, "
+                f"CURVGRID, SOLAR_SOURCE, BULK_FLUXES+LONGWAVE, LMD_MIXING+RIMIX+CONVEC+SKPP+NONLOCAL+RI_SPLINES; analytical atmosphere), "
+                f"ndtfast={ndtfast}, nfast={nfast}")
     mix = "TS_DIF2 MIX_GEO_TS" if mix_geo else "TS_DIF2 MIX_S_TS"
     return (f"{grid.upper()} {Lm}x{Mm}x{N}, NT=2, reduced physics set (nonlinear EOS, DJ_GRADPS, U3/C4, UV_VIS2, {mix}, UV_QDRAG, CURVGRID), "
             f"ndtfast={ndtfast}, nfast={nfast}")
@@ -143,7 +152,7 @@ def cpu_tiles(nthreads, Lm, Mm):
     return best
 
 
-def cpu_run(grid, steps, warmup, nthreads, spinup=0, kinds=("fast", "fastmath")):
+def cpu_run(grid, steps, warmup, nthreads, spinup=0, kinds=("fast", "fastmath"), physics="full"):
     """Time the CPU restatement (oracle/) on the host cores: one tile per thread, barrier per phase.  Two timing builds
     (-O3 -march=native, and the same plus the reference's own -ffast-math, Compilers/Linux-gfortran.mk:98-99) are probed on
     two steps each; the faster one runs the sample.  Returns (gp-steps/s, seconds, tiles, build kind)."""
@@ -154,7 +163,7 @@ def cpu_run(grid, steps, warmup, nthreads, spinup=0, kinds=("fast", "fastmath"))
     models, probe = {}, {}
     for k in kinds:
         try:
-            models[k] = orc.Oracle(orc.APP_BENCHMARK, Lm=Lm, Mm=Mm, N=N, NtileI=ni, NtileJ=nj, kind=k)
+            models[k] = orc.Oracle(orc.APP_BENCHMARK, Lm=Lm, Mm=Mm, N=N, NtileI=ni, NtileJ=nj, kind=k, **(FULL_BENCHMARK if physics == "full" else {}))
             models[k].step(1, nthreads)
             probe[k] = models[k].timed_steps(2, nthreads)
         except Exception as e:  # noqa: BLE001
@@ -247,6 +256,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--grid", default="benchmark3")
     ap.add_argument("--spinup", type=int, default=20, help="untimed steps before warm-up so that all upstream branches are live")
+    ap.add_argument("--physics", default="full", choices=["full", "reduced"],
+                    help="full: the shipped benchmark.h cpp set (bulk_flux + lmd_vmix on the device); reduced: round 1's set (analytical stress, constant mixing)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the MIX_GEO_TS row, the weak-scaling row and the history-write timing")
     a = ap.parse_args()
@@ -269,13 +280,13 @@ def main():
         if rank != 0:
             return 0
         nth = ncores
-        val, sec, tiles, kind, probe = cpu_run((Lm, Mm, N), a.steps, W, nth, spinup=a.spinup)
+        val, sec, tiles, kind, probe = cpu_run((Lm, Mm, N), a.steps, W, nth, spinup=a.spinup, physics=a.physics)
         sample = (f"{a.steps} steps after {a.spinup} spin-up + {W} warm-up steps on the full {a.grid.upper()} grid, {tiles[0]}x{tiles[1]} tiles on {nth} host "
                   f"threads; C++ restatement of the Fortran (scratch arrays heap-allocated per call), g++ {cpu_flags(kind)} "
                   f"(2-step probe: " + ", ".join(f"{k} {v / 2:.2f} s/step" for k, v in probe.items()) + ")")
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "grid-point-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": W,
                 "ms_per_step": 1e3 * sec / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": {"workload": workload(a.grid, Lm, Mm, N), "spinup_steps": a.spinup},
+                "data": "synthetic", "config": {"workload": workload(a.grid, Lm, Mm, N, physics=a.physics), "spinup_steps": a.spinup, "physics": a.physics},
                 "cpu_tiles": f"{tiles[0]}x{tiles[1]}",
                 "cpu_baseline": {"value": val, "unit": "grid-point-steps/s", "cores": nth, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": "grid-point-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -291,7 +302,10 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl")
     NtileI = world
-    t, xchg = make_ring_tile(synth, (Lm, Mm, N), rank, world, local, dist)
+    full = a.physics == "full"
+    phys = dict(synth.FULL_BENCHMARK) if full else {}
+    assert phys == (FULL_BENCHMARK if full else {})
+    t, xchg = make_ring_tile(synth, (Lm, Mm, N), rank, world, local, dist, **phys)
     nfast = synth.set_weights(t.cfg.ndtfast)[0]
     t.main3d(a.spinup)
     t.main3d(W)
@@ -312,15 +326,24 @@ def main():
 
     # ---- e2e: host forcing in, diag scalars out, every step
     g = t.synth["grid"]; b = t.synth["bounds"]
-    sustr = np.ascontiguousarray(synth.tile_slice(synth.sustr_at(synth.APP_BENCHMARK, g, t.cfg, 0.0), Lm, b), dtype=np.float64)
-    svstr = np.zeros_like(sustr); stf = np.zeros_like(sustr)
     ke = min(a.steps, 10)
-    t.register_host(sustr, svstr, stf)        # what the Fortran host does once for its FORCES(ng) module arrays
+    if full:
+        # the set_data products of the shipped set: the atmosphere bulk_flux reads (8 arrays), as of the current model time
+        atm = {n: np.ascontiguousarray(synth.tile_slice(v, Lm, b), dtype=np.float64) for n, v in synth.atmosphere_at(g, t.cfg, t.indices()["tdays"]).items()}
+        t.register_host(*atm.values())        # what the Fortran host does once for its FORCES(ng) module arrays
+        forced = lambda: t.step_fields(atm)   # noqa: E731
+        h2d = int(sum(v.nbytes for v in atm.values()))
+    else:
+        sustr = np.ascontiguousarray(synth.tile_slice(synth.sustr_at(synth.APP_BENCHMARK, g, t.cfg, 0.0), Lm, b), dtype=np.float64)
+        svstr = np.zeros_like(sustr); stf = np.zeros_like(sustr)
+        t.register_host(sustr, svstr, stf)
+        forced = lambda: t.step_forced(sustr, svstr, stf)   # noqa: E731
+        h2d = int(3 * sustr.size * 8)
     for _ in range(4):                        # untimed: both time-level parities of the with-diag step get their CUDA graph
-        t.step_forced(sustr, svstr, stf)
+        forced()
     barrier(); t.sync(); t0 = time.perf_counter()
     for _ in range(ke):
-        d, rc = t.step_forced(sustr, svstr, stf)
+        d, rc = forced()
     t.sync(); barrier(); e2e_sec = time.perf_counter() - t0
     if dist is not None:
         import torch
@@ -352,11 +375,13 @@ def main():
         tt = torch.tensor([prof[k] for k in keys], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         prof = dict(zip(keys, [float(x) for x in tt.tolist()]))
     peak, peak_kind = measured_peak()
-    balg, s2d = b_alg_bytes(N, nfast, curvgrid=bool(t.cfg.curvgrid), nonlin_eos=bool(t.cfg.nonlin_eos), wvelocity=bool(t.cfg.wvelocity_every_step))
+    balg, s2d = b_alg_bytes(N, nfast, curvgrid=bool(t.cfg.curvgrid), nonlin_eos=bool(t.cfg.nonlin_eos), wvelocity=bool(t.cfg.wvelocity_every_step),
+                            mix_geo=full, full_physics=full)
     npts2 = (Lm // NtileI) * Mm
     # units (whole 3-D arrays, or 2-D arrays for step2d) touched per launch group, SURVEY.md section 8a
-    units3 = {"pre_step3d": 24, "rhs3d": 10, "step3d_t": 12, "step3d_uv": 12, "prsgrd": 5, "t3dmix": 7, "uv3dmix": 7, "wvelocity": 7,
-              "set_massflux": 5, "rho_eos": 8 if t.cfg.nonlin_eos else 5, "omega": 4, "omega2": 4, "set_depth": 3}
+    units3 = {"pre_step3d": 24 + (3 if full else 0), "rhs3d": 10, "step3d_t": 12, "step3d_uv": 12, "prsgrd": 5, "t3dmix": 8 if full else 7, "uv3dmix": 7,
+              "wvelocity": 7, "set_massflux": 5, "rho_eos": (8 if t.cfg.nonlin_eos else 5) + (1 if full else 0), "omega": 4, "omega2": 4, "set_depth": 3,
+              "lmd_vmix": 11}
     dom = max(prof, key=prof.get) if prof else None
     roof = None
     if dom:
@@ -384,11 +409,11 @@ def main():
     step_gbs = balg * value / 1e9
     line = {"metric": METRIC, "value": value, "unit": "grid-point-steps/s", "n_gpus": world, "steps": a.steps, "warmup": W,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload(a.grid, Lm, Mm, N, t.cfg.ndtfast, nfast), "spinup_steps": a.spinup},
+            "config": {"workload": workload(a.grid, Lm, Mm, N, t.cfg.ndtfast, nfast, physics=a.physics), "spinup_steps": a.spinup, "physics": a.physics},
             "tiles": f"{NtileI}x1", "halo_exchange": xchg, "launch": "cuda-graph per step",
             "l2": "working set per step (~3.5 GB) exceeds L2 (126 MB); no explicit flush",
-            "e2e": {"value": e2e_val, "unit": "grid-point-steps/s", "h2d_bytes_per_step": int(3 * sustr.size * 8), "d2h_bytes_per_step": 12 * 8,
-                    "steps": ke},
+            "e2e": {"value": e2e_val, "unit": "grid-point-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12 * 8, "steps": ke,
+                    "api": "roms_b200_step_fields (atmosphere: 8 arrays)" if full else "roms_b200_step_forced (sustr, svstr, stflux)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "roofline_step": {"b_alg_bytes_per_gp_step": balg, "achieved_gbs": step_gbs, "frac": step_gbs / (peak * world)},
             "phase_ms": prof, "phase_ms_sum": sum(prof.values()), "phase_ms_mode": "events inside the captured step graph, main stream, max over ranks",
@@ -396,47 +421,32 @@ def main():
     perr = int(t.L.roms_b200_peer_error(t.h))
     t.close()
 
-    # ---- extra rows: MIX_GEO_TS (SURVEY.md section 8d "second row") and weak scaling (section 8e)
+    # ---- extra rows: the other physics set (continuity with round 1 / SURVEY.md section 8d "second row") and weak scaling (8e)
     if not a.no_extras and a.grid == "benchmark3":
         try:
-            tg, _ = make_ring_tile(synth, (Lm, Mm, N), rank, world, local, dist, mix_geo_ts=1)
-            tg.main3d(6)
-            msg = timed_steps(tg, dist, 6)
-            bg, _ = b_alg_bytes(N, nfast, mix_geo=True)
-            line["mix_geo_ts_row"] = {"ms_per_step": msg / 6, "value": Lm * Mm * N * 6 / (msg * 1e-3), "steps": 6, "spinup_steps": 6,
-                                      "roofline_step_frac": bg * (Lm * Mm * N * 6 / (msg * 1e-3)) / 1e9 / (peak * world)}
+            if full:
+                # round 1's reduced set (analytical stress, constant vertical mixing, MIX_S_TS fused into pre_step3d)
+                tg, _ = make_ring_tile(synth, (Lm, Mm, N), rank, world, local, dist)
+                tg.main3d(10)
+                msg = timed_steps(tg, dist, 10)
+                bg, _ = b_alg_bytes(N, nfast)
+                vg = Lm * Mm * N * 10 / (msg * 1e-3)
+                line["reduced_physics_row"] = {"workload": workload(a.grid, Lm, Mm, N, t.cfg.ndtfast, nfast, physics="reduced"), "ms_per_step": msg / 10, "value": vg,
+                                               "steps": 10, "spinup_steps": 10, "b_alg_bytes_per_gp_step": bg, "roofline_step_frac": bg * vg / 1e9 / (peak * world)}
+            else:
+                tg, _ = make_ring_tile(synth, (Lm, Mm, N), rank, world, local, dist, **synth.FULL_BENCHMARK)
+                tg.main3d(10)
+                msg = timed_steps(tg, dist, 6)
+                bg, _ = b_alg_bytes(N, nfast, mix_geo=True, full_physics=True)
+                vg = Lm * Mm * N * 6 / (msg * 1e-3)
+                line["full_benchmark_row"] = {"workload": workload(a.grid, Lm, Mm, N, t.cfg.ndtfast, nfast, physics="full"), "ms_per_step": msg / 6, "value": vg,
+                                              "steps": 6, "spinup_steps": 10, "b_alg_bytes_per_gp_step": bg, "roofline_step_frac": bg * vg / 1e9 / (peak * world)}
             perr |= int(tg.L.roms_b200_peer_error(tg.h))
             tg.close()
-            # the shipped benchmark.h cpp set: + BULK_FLUXES, LMD_MIXING/SKPP/NONLOCAL, SOLAR_SOURCE, BV_FREQUENCY, MIX_GEO_TS
-            tf, _ = make_ring_tile(synth, (Lm, Mm, N), rank, world, local, dist, **synth.FULL_BENCHMARK)
-            gsy = tf.synth["grid"]; bsy = tf.synth["bounds"]
-            tf.main3d(10)
-            msf = timed_steps(tf, dist, 6)
-            bf, _ = b_alg_bytes(N, nfast, mix_geo=True, full_physics=True)
-            vf = Lm * Mm * N * 6 / (msf * 1e-3)
-            tf.profile(2); tf.main3d(2); tf.profile(2); tf.main3d(2)
-            pf, _ = tf.profile_get(); tf.profile(0)
-            # e2e: the atmosphere of this model time H2D (8 arrays), the step with bulk_flux + lmd_vmix on the device, diag D2H
-            atm = {n: np.ascontiguousarray(synth.tile_slice(v, Lm, bsy)) for n, v in synth.atmosphere_at(gsy, tf.cfg, tf.indices()["tdays"]).items()}
-            for _ in range(3):
-                tf.step_fields(atm)
-            barrier(); tf.sync(); t0 = time.perf_counter()
-            for _ in range(6):
-                tf.step_fields(atm)
-            tf.sync(); barrier(); fsec = time.perf_counter() - t0
-            line["full_benchmark_row"] = {
-                "workload": "the shipped ROMS/Include/benchmark.h cpp set: reduced set + BULK_FLUXES (COARE 3.0, LONGWAVE), LMD_MIXING (RIMIX, CONVEC, SKPP, "
-                            "NONLOCAL, RI_SPLINES), SOLAR_SOURCE, BV_FREQUENCY, MIX_GEO_TS; analytical atmosphere (ana_winds/tair/pair/humid/rain/cloud/srflux)",
-                "ms_per_step": msf / 6, "value": vf, "steps": 6, "spinup_steps": 10, "b_alg_bytes_per_gp_step": bf,
-                "roofline_step_frac": bf * vf / 1e9 / (peak * world),
-                "phase_ms": {k: v / 2 for k, v in pf.items() if k in ("bulk_flux", "lmd_vmix", "t3dmix", "rho_eos", "pre_step3d")},
-                "e2e": {"value": Lm * Mm * N * 6 / fsec, "h2d_bytes_per_step": int(sum(v.nbytes for v in atm.values())), "d2h_bytes_per_step": 96, "steps": 6}}
-            perr |= int(tf.L.roms_b200_peer_error(tf.h))
-            tf.close()
             wg = WEAK.get(world)
             if wg:
                 wl = GRIDS[wg]
-                tw, _ = make_ring_tile(synth, wl, rank, world, local, dist)
+                tw, _ = make_ring_tile(synth, wl, rank, world, local, dist, **phys)
                 tw.main3d(10)
                 msw = timed_steps(tw, dist, 10)
                 line["weak_scaling_row"] = {"grid": wg, "n_gpus": world, "ms_per_step": msw / 10, "value": wl[0] * wl[1] * wl[2] * 10 / (msw * 1e-3), "steps": 10,
@@ -456,7 +466,7 @@ def main():
             return 1
     if rank == 0 and world == 1 and not a.no_cpu:
         try:
-            cv, csec, tiles, kind, probe = cpu_run((Lm, Mm, N), 4, 1, ncores, spinup=0)
+            cv, csec, tiles, kind, probe = cpu_run((Lm, Mm, N), 4, 1, ncores, spinup=0, physics=a.physics)
             line["cpu_baseline"] = {"value": cv, "unit": "grid-point-steps/s", "cores": ncores, "kind": "port",
                                     "sample": f"4 steps after 4 warm-up steps on the full {a.grid.upper()} grid, {tiles[0]}x{tiles[1]} tiles on {ncores} host threads, "
                                               f"g++ {cpu_flags(kind)} (the faster of the two timing builds)"}

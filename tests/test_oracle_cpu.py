@@ -495,6 +495,9 @@ def test_bench_accounting_and_reference_arm():
     balg, s2d = bench.b_alg_bytes(30, 29)
     assert s2d == 29 * 44 + 16 + 29 * 41 and abs(balg - 1525.6) < 1e-9
     assert abs(bench.b_alg_bytes(30, 29, curvgrid=False, nonlin_eos=False)[0] - 8.0 * (105 + 2365 / 30.0)) < 1e-9     # 1471 B
+    assert abs(bench.b_alg_bytes(30, 29, mix_geo=True, full_physics=True)[0] - 8.0 * (124 + 2481 / 30.0)) < 1e-9      # the shipped cpp set: 1653.6 B
+    from roms_trunk_mgh_b200 import synth
+    assert bench.FULL_BENCHMARK == synth.FULL_BENCHMARK
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--grid", "benchmark1", "--steps", "2", "--warmup", "3", "--spinup", "4"],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-1000:]
@@ -502,6 +505,7 @@ def test_bench_accounting_and_reference_arm():
     assert line["impl"] == "reference" and line["unit"] == "grid-point-steps/s" and line["value"] > 0 and line["higher_is_better"] is True
     assert line["steps"] == 2 and line["warmup"] == 3 and line["config"]["spinup_steps"] == 4        # the driver's --steps / --warmup are honoured
     assert line["config"]["workload"] == bench.workload("benchmark1", 512, 64, 30)                   # the string the GPU arm prints
+    assert line["config"]["physics"] == "full" and "BULK_FLUXES" in line["config"]["workload"]       # default: the shipped benchmark.h set
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
 
