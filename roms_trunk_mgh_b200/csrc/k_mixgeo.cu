@@ -10,7 +10,10 @@ namespace rb {
 #ifndef GEO_PF
 #define GEO_PF 4          // L2 prefetch distance (levels)
 #endif
-__global__ void __launch_bounds__(128) k_t3dmix2_geo(Par p, Flds f) {
+#ifndef GEO_MINB
+#define GEO_MINB 4          // 128 registers: the allocation the kernel had before the bound was made explicit; 5 and 6 are slower
+#endif
+__global__ void __launch_bounds__(128, GEO_MINB) k_t3dmix2_geo(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   const int itrc = blockIdx.z;

@@ -213,7 +213,7 @@ __device__ __forceinline__ void lmd_wscale(double Ustar, double sigma, double Bf
 // Akv / Akt are written once and nothing else is staged.  The column Iend-1 copy of the eastern edge (lmd_vmix.F:568-575) is
 // k_lmd_east.  NC > 0: N is the compile-time constant NC (thread-local columns sized for it).
 #ifndef LMD_MINB
-#define LMD_MINB 4
+#define LMD_MINB 5          // 0.64 ms (3: 0.77, 4: 0.67, 6: 0.66)
 #endif
 #ifndef LMD_PF
 #define LMD_PF 6          // L2 prefetch distance (levels) of the upward spline sweep

@@ -35,7 +35,9 @@ template <int HADV, int VADV, bool MIXS, bool SRC>     // SRC: with the KPP nonl
 #ifndef PRU_PF
 #define PRU_PF 4          // same for k_pre_step3d_uv
 #endif
-__global__ void __launch_bounds__(128, PRT_MINB) k_pre_step3d_t(Par p, Flds f) {
+// without the fused t3dmix2_s the kernel fits 128 registers: 4 CTAs per SM (0.86 -> 0.80 ms for pre_step3d on BENCHMARK3 with the
+// shipped cpp set); with it (156 registers) the cap costs more in spills than the extra CTA brings (profiles/README.md)
+__global__ void __launch_bounds__(128, MIXS ? PRT_MINB : PRT_MINB + 1) k_pre_step3d_t(Par p, Flds f) {
   // the tracer index is the fastest grid dimension: the CTAs of all tracers of one tile run back to back, so the shared
   // operands (Huon, Hvom, W, Hz, z_r) of the second tracer come from L2
   const int itrc = blockIdx.x % p.NT;
