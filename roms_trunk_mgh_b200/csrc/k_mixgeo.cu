@@ -99,10 +99,10 @@ __global__ void __launch_bounds__(128, GEO_MINB) k_t3dmix2_geo(Par p, Flds f) {
 // from the tile.  Against the column kernel above: 1.3 instead of 5 divisions and 4-7 instead of 16 global loads per point and
 // level.  Expressions and their order are unchanged (bit-identical results).
 #ifndef GEO_TY
-#define GEO_TY 8
+#define GEO_TY 4           // 32x4 columns per CTA, 4 CTAs per SM: 0.49 ms (32x8 with 2: 0.53, with 3: 1.21; 32x16: 0.60)
 #endif
 #ifndef GEO_TMINB
-#define GEO_TMINB 2
+#define GEO_TMINB 4
 #endif
 constexpr int GT_X = 32, GT_Y = GEO_TY, GT_SW = GT_X + 2, GT_SH = GT_Y + 2, GT_NH = 2 * GT_X + 2 * GT_Y;
 static_assert(GT_NH <= GT_X * GT_Y, "one rim cell per thread");
