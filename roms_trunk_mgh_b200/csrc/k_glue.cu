@@ -86,10 +86,10 @@ __device__ __forceinline__ void eos_nl(double Tt, double Ts, double Tp, double& 
 #define EOS_PF 4          // L2 prefetch distance (levels) of k_rho_eos<true>
 #endif
 #ifndef EOS_MINB
-#define EOS_MINB 4          // 64 registers: rho_eos<true> 0.35 -> 0.32 ms (3: 0.35, unbounded: 0.45)
+#define EOS_MINB 4          // 64 registers: rho_eos<true> 0.35 -> 0.32 ms (3: 0.35, unbounded: 0.45); the plain kernel keeps its 40 (6 CTAs per SM)
 #endif
 template <bool X>     // X: with the optional outputs bvf / alpha, beta (BV_FREQUENCY; LMD_SKPP || BULK_FLUXES)
-__global__ void __launch_bounds__(256, EOS_MINB) k_rho_eos(Par p, Flds f) {
+__global__ void __launch_bounds__(256, X ? EOS_MINB : 6) k_rho_eos(Par p, Flds f) {
   const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;          // JstrT..JendT = 0..Mm+1
   if (i > p.Iend || j > p.Mm + 1) return;
