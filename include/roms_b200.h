@@ -247,7 +247,10 @@ int roms_b200_set_depth_tile(const roms_b200_tile_t* b, const double* h, const d
 int roms_b200_routine_tile(const roms_b200_tile_t* b, int phase, int nargs, const char* const* names, double* const* arrays,
                            const int* mode, const double* scoord4, int nfast, const double* weight1, const double* weight2,
                            int nweight);
-/* "in:<comma-separated names>;out:<names>" a routine needs (`*` = one entry per tracer), NULL for an unknown phase */
+/* "in:<comma-separated names>;out:<names>" a routine needs, NULL for an unknown phase.  `*` = one entry per tracer.  A leading
+ * `?` marks an argument only the optional terms of the routine touch (bvf / alpha / beta of rho_eos; z_w, srflx, Jwtype, ghats of
+ * pre_step3d with SOLAR_SOURCE / LMD_NONLOCAL): pass it (without the `?`) when the configuration has the array, leave it out
+ * otherwise -- an optional input that is left out reads as zero, an optional output that is left out is discarded. */
 const char* roms_b200_routine_args(int phase);
 /* vertical extent of a named field: first level (0 or 1) and number of planes (1, N or N+1) */
 int roms_b200_field_levels(roms_b200_handle h, const char* name, int* LBk, int* nk);

@@ -348,7 +348,7 @@ int ensure_optional(roms_b200_state* h, int phase) {
   if (phase == ROMS_B200_RHO_EOS) names = {"bvf", "alpha", "beta"};
   else if (phase == ROMS_B200_BULK_FLUX) names = {"lrflx", "lhflx", "shflx", "sustr", "svstr", "stflux_" + std::to_string(h->cfg.itemp - 1)};
   else if (phase == ROMS_B200_LMD_VMIX) { names = {"hsbl", "ksbl", "Akv"}; for (int it = 0; it < h->cfg.NT; ++it) { names.push_back("ghats_" + std::to_string(it)); names.push_back("Akt_" + std::to_string(it)); } }
-  else if (phase == ROMS_B200_PRE_STEP3D) { names = {"srflx", "Jwtype"}; for (int it = 0; it < h->cfg.NT; ++it) names.push_back("ghats_" + std::to_string(it)); }
+  else if (phase == ROMS_B200_PRE_STEP3D) { names = {"srflx", "Jwtype", "z_w"}; for (int it = 0; it < h->cfg.NT; ++it) names.push_back("ghats_" + std::to_string(it)); }
   for (const std::string& n : names) {
     auto it = h->reg.find(n);
     if (it != h->reg.end()) { const int rc = materialize(h, it->second); if (rc) return rc; }

@@ -119,17 +119,20 @@ int roms_b200_set_depth_tile(const roms_b200_tile_t* b, const double* h, const d
 namespace {
 struct RoutineArgs { int phase; const char* in; const char* out; };
 // 3-D time levels: both levels of u, v, ru, rv and all three of t are listed (which of them a call reads is decided by
-// nstp/nnew/nrhs in roms_b200_tile_t); `*` = one entry per tracer.
+// nstp/nnew/nrhs in roms_b200_tile_t); `*` = one entry per tracer; a leading `?` marks an argument that only the optional terms
+// of the routine touch (BV_FREQUENCY / expansion coefficients in rho_eos, SOLAR_SOURCE / LMD_NONLOCAL in pre_step3d): pass it
+// when the configuration has the array (roms_b200_config switches), leave it out otherwise.
 const RoutineArgs kRoutineArgs[] = {
     {ROMS_B200_SET_MASSFLUX, "u1,u2,v1,v2,Hz,on_u,om_v", "Huon,Hvom"},
-    {ROMS_B200_RHO_EOS, "t1_*,t2_*,z_r,z_w,Hz", "rho,pden,rhoA,rhoS"},
+    {ROMS_B200_RHO_EOS, "t1_*,t2_*,z_r,z_w,Hz", "rho,pden,rhoA,rhoS,?bvf,?alpha,?beta"},
     {ROMS_B200_SET_VBC, "u1,u2,v1,v2,t1_*,t2_*,rdrag,rdrag2,stflux_*,btflux_*", "bustr,bvstr,stflx_*,btflx_*"},
     {ROMS_B200_ANA_VMIX, "z_w", "Akv,Akt_*"},
     {ROMS_B200_OMEGA, "Huon,Hvom,z_w", "W"},
     {ROMS_B200_WVELOCITY, "u1,u2,v1,v2,z_r,z_w,W,DU_avg1,DV_avg1,pm,pn", "wvel"},
     {ROMS_B200_SET_ZETA, "Zt_avg1", "zeta1,zeta2"},
     {ROMS_B200_PRE_STEP3D,
-     "Hz,Huon,Hvom,W,z_r,Akv,Akt_*,pm,pn,stflx_*,btflx_*,sustr,svstr,bustr,bvstr,ru1,ru2,rv1,rv2,u1,u2,v1,v2,t1_*,t2_*",
+     "Hz,Huon,Hvom,W,z_r,Akv,Akt_*,pm,pn,stflx_*,btflx_*,sustr,svstr,bustr,bvstr,ru1,ru2,rv1,rv2,u1,u2,v1,v2,t1_*,t2_*,"
+     "?z_w,?srflx,?Jwtype,?ghats_*",
      "t3_*,t1_*,t2_*,u1,u2,v1,v2"},
     {ROMS_B200_PRSGRD, "Hz,z_r,z_w,rho,on_u,om_v", "ru1,ru2,rv1,rv2"},
     {ROMS_B200_T3DMIX, "Hz,z_r,pm,pn,on_u,om_v,pmon_u,pnom_v,diff2_*,t1_*,t2_*", "t1_*,t2_*"},

@@ -96,11 +96,14 @@ static int routine(int phase) {
     while (*p && *p != ',' && *p != ';') tok[l++] = *p++;
     tok[l] = 0;
     if (*p == ',') ++p;
+    const int optional = (tok[0] == '?');           /* present only with the cpp switch that creates the array */
+    if (optional) memmove(tok, tok + 1, strlen(tok));
     char* star = strchr(tok, '*');
     for (int it = 0; it < (star ? cfg.NT : 1); ++it) {
       char one[24];
       strcpy(one, tok);
       if (star) one[star - tok] = (char)('0' + it);
+      if (optional && !find(one)) continue;
       int j = 0;
       while (j < nargs && strcmp(names[j], one) != 0) ++j;
       if (j == nargs) { strcpy(names[nargs], one); cn[nargs] = names[nargs]; arrs[nargs] = need(one)->data; mode[nargs] = 0; ++nargs; }
@@ -131,8 +134,10 @@ static int main3d_by_routine(void) {
   tdays = time_s / 86400.0;
   CHECK(routine(ROMS_B200_SET_MASSFLUX));                                  /* :307 */
   CHECK(routine(ROMS_B200_RHO_EOS));
+  if (cfg.bulk_fluxes) CHECK(routine(ROMS_B200_BULK_FLUX));                /* :384-390 */
   CHECK(routine(ROMS_B200_SET_VBC));                                       /* :429 */
-  if (cfg.ana_vmix) CHECK(routine(ROMS_B200_ANA_VMIX));
+  if (cfg.ana_vmix) CHECK(routine(ROMS_B200_ANA_VMIX));                    /* :464-470 */
+  else if (cfg.lmd_mixing) CHECK(routine(ROMS_B200_LMD_VMIX));
   CHECK(routine(ROMS_B200_OMEGA));                                         /* :474 */
   if (cfg.wvelocity_every_step) CHECK(routine(ROMS_B200_WVELOCITY));
   CHECK(routine(ROMS_B200_SET_ZETA));                                      /* :531 */

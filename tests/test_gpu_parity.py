@@ -146,10 +146,15 @@ def test_host_pointer_tile_entry_points():
     assert b["Istr"] == 1
 
 
-def _expand(names, NT):
+def _expand(names, NT, have=None):
+    """Names of a roms_b200_routine_args list; `?name` entries (optional terms) only if `have` says the array exists."""
     out = []
     for n in names.split(","):
-        out += [n.replace("*", str(it)) for it in range(NT)] if "*" in n else [n]
+        opt = n.startswith("?")
+        n = n.lstrip("?")
+        for m in ([n.replace("*", str(it)) for it in range(NT)] if "*" in n else [n]):
+            if not opt or (have is not None and have(m)):
+                out.append(m)
     return out
 
 
@@ -219,6 +224,46 @@ def test_generic_routine_tile_every_phase(case):
                 assert np.allclose(a, o.field(n), rtol=1e-13, atol=0), (ph, n)
             else:
                 assert np.array_equal(a, o.field(n)), (ph, n)
+
+
+def test_routine_tile_bulk_flux_and_lmd_vmix_by_name():
+    """The per-routine host-pointer form for the two parameterisations (what `CALL b200_routine(ng, tile, B200_BULK_FLUX /
+    B200_LMD_VMIX)` of the Fortran patch reaches): a fresh device state receives ONLY the arrays roms_b200_routine_args lists,
+    so agreement with the oracle also proves the published argument lists complete.  1e-11 relative (pow / exp / log / atan),
+    the boundary-layer index exactly."""
+    o = orc.Oracle(orc.APP_BENCHMARK, Lm=64, Mm=48, N=30, **FULL_BENCHMARK)
+    o.run_phase("set_data"); o.run_phase("ini")
+    o.step(7)
+    L = _lib.load(True)
+    cfg = cfg_from_oracle(o)
+    NT = int(o.opt("NT"))
+    d = o.indices()
+    d["nstp"] = 1 + ((d["iic"] - d["ntstart"]) % 2); d["nnew"] = 3 - d["nstp"]; d["nrhs"] = d["nstp"]; d["tdays"] = d["time"] / 86400.0
+    o.set_indices(d)
+    for ph in ("set_data", "set_massflux", "rho_eos"):
+        o.run_phase(ph)
+    for ph, after in (("bulk_flux", ("set_vbc",)), ("lmd_vmix", ())):
+        spec = L.roms_b200_routine_args(_lib.PHASES[ph]).decode()
+        ins, outs = [_expand(x.split(":")[1], NT, lambda m: True) for x in spec.split(";")]
+        names = list(dict.fromkeys(ins + outs))
+        arrs = [o.field(n).copy() for n in names]
+        mode = [(1 if n in ins else 0) | (2 if n in outs else 0) for n in names]
+        ta = _lib.TileArgs(cfg=cfg, iic=d["iic"], ntfirst=d["ntfirst"], nstp=d["nstp"], nnew=d["nnew"], nrhs=d["nrhs"], iif=1, kstp=1, krhs=1, knew=1, predictor=0)
+        cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        ca = (_lib.DP * len(names))(*[a.ctypes.data_as(_lib.DP) for a in arrs])
+        cm = (C.c_int * len(names))(*mode)
+        rc = L.roms_b200_routine_tile(C.byref(ta), _lib.PHASES[ph], len(names), cn, ca, cm, None, 0, None, None, 0)
+        assert rc == 0, (ph, rc)
+        o.run_phase(ph)
+        for n, a in zip(names, arrs):
+            if n not in outs:
+                continue
+            if n == "ksbl":
+                assert np.array_equal(a, o.field(n)), (ph, n)
+            else:
+                assert _rel(o.field(n), a) <= 1e-11, (ph, n, _rel(o.field(n), a))
+        for q in after:
+            o.run_phase(q)
 
 
 def test_ntilej_partition_is_accepted_and_tiling_invariant():
