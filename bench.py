@@ -67,6 +67,27 @@ def b_alg_bytes(N, nfast, curvgrid=True, nonlin_eos=True, wvelocity=True, mix_ge
     return 8.0 * (u3d + s2d / N), s2d
 
 
+# wclock_on / wclock_off region of each phase (the ids a -DPROFILE build of the reference reports, ROMS/Utility/timers.F with the
+# names of ROMS/Modules/mod_strings.F:162-222): phase_wclock maps this bench's phase_ms onto that table.  wvelocity and ana_vmix
+# carry no region of their own (they fall into the caller's "residual"); t3dmix is 24 with MIX_S_TS, 25 with MIX_GEO_TS.
+WCLOCK = {"set_data": 4, "set_avg": 5, "set_vbc": 6, "diag": 7, "step2d_loop": 9, "set_zeta": 12, "set_depth": 12, "set_massflux": 12, "omega": 13,
+          "omega2": 13, "rho_eos": 14, "bulk_flux": 17, "lmd_vmix": 18, "rhs3d": 21, "pre_step3d": 22, "prsgrd": 23, "t3dmix": 24, "uv3dmix": 30,
+          "step3d_uv": 34, "step3d_t": 35}
+
+
+def wclock_ms(prof, mix_geo):
+    """phase_ms summed per timers.F region id."""
+    out = {}
+    for k, v in prof.items():
+        r = WCLOCK.get(k)
+        if r is None:
+            continue
+        if k == "t3dmix" and mix_geo:
+            r = 25
+        out[str(r)] = out.get(str(r), 0.0) + v
+    return dict(sorted(out.items(), key=lambda kv: int(kv[0])))
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -416,7 +437,7 @@ def main():
                     "api": "roms_b200_step_fields (atmosphere: 8 arrays)" if full else "roms_b200_step_forced (sustr, svstr, stflux)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "roofline_step": {"b_alg_bytes_per_gp_step": balg, "achieved_gbs": step_gbs, "frac": step_gbs / (peak * world)},
-            "phase_ms": prof, "phase_ms_sum": sum(prof.values()), "phase_ms_mode": "events inside the captured step graph, main stream, max over ranks",
+            "phase_ms": prof, "phase_ms_sum": sum(prof.values()), "phase_ms_by_wclock_region": wclock_ms(prof, full), "phase_ms_mode": "events inside the captured step graph, main stream, max over ranks",
             "state_digest": digest, "state_digest_steps": a.spinup + W + a.steps, "history_write": hist}
     perr = int(t.L.roms_b200_peer_error(t.h))
     t.close()
