@@ -102,9 +102,11 @@ int roms_b200_array_bounds(roms_b200_handle h, int* out4);
  * with the switches of roms_b200_config that create them: "bvf","alpha","beta","srflx","Jwtype","ghats_<itrc>","Uwind","Vwind",
  * "Tair","Pair","Hair","rain","cloud","lrflx","lhflx","shflx","hsbl","ksbl".
  * <itrc> is 0-based.  n = number of doubles in the whole Fortran array (checked).
- * With a ring attached (roms_b200_attach_nccl) roms_b200_set_field and roms_b200_step_forced are COLLECTIVE: every
- * upload is followed by the halo exchange of that field (mp_exchange2d/3d), so all tiles must upload the same fields in
- * the same order -- as the reference's distributed build does when every rank runs the same set_data / get_data. */
+ * With a ring attached (roms_b200_attach_nccl) roms_b200_set_field is COLLECTIVE: every upload is followed by the halo
+ * exchange of that field (mp_exchange2d/3d), so all tiles must upload the same fields in the same order -- as the
+ * reference's distributed build does when every rank runs the same set_data / get_data.  roms_b200_step_forced /
+ * roms_b200_step_fields upload WITHOUT an exchange: the surface forcing arrays must carry valid ghost columns (LBi:UBi), as
+ * they do in the reference after set_data; the step itself is collective. */
 int roms_b200_set_field(roms_b200_handle h, const char* name, const double* host, size_t n);
 int roms_b200_get_field(roms_b200_handle h, const char* name, double* host, size_t n);
 /* s-coordinate vectors (mod_scalars.F SCALARS%): which = 0 sc_r, 1 Cs_r, 2 sc_w, 3 Cs_w; n = N+1 values indexed by k */
@@ -169,7 +171,7 @@ int roms_b200_step_forced(roms_b200_handle h, const double* sustr, const double*
                           size_t n2d, double* out12);
 /* The same with any set of 2-D forcing arrays, by name -- with cfg.bulk_fluxes the set_data products are the atmosphere
  * ("Uwind","Vwind","Tair","Pair","Hair","rain","cloud","srflx") instead of the stresses.  arrays[i] == NULL keeps the
- * resident value of names[i]; nfields <= 16.  Collective with a ring attached, like roms_b200_set_field. */
+ * resident value of names[i]; nfields <= 16. */
 int roms_b200_step_fields(roms_b200_handle h, int nfields, const char* const* names, const double* const* arrays,
                           size_t n2d, double* out12);
 int roms_b200_diag(roms_b200_handle h, double* out12);

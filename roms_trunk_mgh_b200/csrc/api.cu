@@ -981,11 +981,10 @@ static int step_with_uploads(roms_b200_handle h, int nf, const char* const* nm, 
     CK(cudaMalloc(&h->d_stage, cap * sizeof(double))); h->allocs.push_back(h->d_stage);
   }
   const size_t dp = (size_t)h->par.P * sizeof(double), sp = (size_t)h->ni * sizeof(double);
-  // single tile: upload on the copy stream, overlapped with set_massflux / rho_eos / diag of this step (step_phases_body waits
-  // for ev_forcing before bulk_flux / set_vbc).  With a ring attached the uploaded fields also need a halo exchange: keep them on
-  // the compute stream.
+  // upload on the copy stream, overlapped with set_massflux / rho_eos / diag of this step (step_phases_body waits for ev_forcing
+  // before bulk_flux / set_vbc)
   cudaStream_t cps = h->stream;
-  if (!h->halo && any) {
+  if (any) {
     if (!h->copy_stream) {
       CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&h->ev_forcing, cudaEventDisableTiming));
@@ -1010,11 +1009,10 @@ static int step_with_uploads(roms_b200_handle h, int nf, const char* const* nm, 
     CK(cudaMemcpy2DAsync(dev, dp, h->d_stage + q * want, sp, sp, (size_t)h->nj, cudaMemcpyDeviceToDevice, cps));
   }
   if (cps != h->stream) CK(cudaEventRecord(h->ev_forcing, cps));
-  if (h->halo) {
-    std::vector<std::string> up;
-    for (int q = 0; q < nf; ++q) if (src[q]) up.push_back(nm[q]);
-    if (halo_exchange(h, up, h->stream)) return FatalError;
-  }
+  // No halo exchange here, also in a ring: the host's arrays span LBi:UBi, i.e. they carry their two ghost columns (the
+  // reference's set_data ends with mp_exchange2d), and no routine of the path reads a surface forcing field further out than
+  // one column (sustr(i+1) / bustr(i+1) in lmd_skpp, the atmosphere at Istr-1 in bulk_flux).  The device's third western ghost
+  // column, which only the 3-column exchanges of the advected state fill, is never read for these fields.
   int rc = one_step(h, true);
   if (rc) return rc;
   return finish_diag(h, out12);

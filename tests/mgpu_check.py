@@ -24,6 +24,7 @@ def main():
     Lm, Mm, N = (int(x) for x in (pos[0:3] if len(pos) >= 3 else (256, 64, 30)))
     nsteps = int(pos[3]) if len(pos) >= 4 else 6
     peer = opts.pop("peer", "1") != "0"
+    opts_e2e = opts.pop("e2e", "0") != "0"     # step through roms_b200_step_fields / step_forced (uploads without halo exchange)
     # physics=full: the shipped benchmark.h cpp set (bulk_flux + lmd_vmix on the device, synth.FULL_BENCHMARK)
     phys = synth.FULL_BENCHMARK if opts.pop("physics", "reduced") == "full" else {}
     t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, NtileI=world, tile=rank, device=local, **phys)
@@ -35,7 +36,23 @@ def main():
     # redo the start-up phases now that ghosts can be exchanged (make_tile ran them before the ring existed)
     for ph in ("set_depth", "set_massflux", "omega", "rho_eos"):
         t.run_phase(ph)
-    t.main3d(nsteps)
+    e2e = opts_e2e
+
+    def advance(tt, n):
+        """n steps: resident, or (e2e=1) through the forced-step API with this tile's slice of the forcing uploaded every step"""
+        if not e2e:
+            tt.main3d(n)
+            return
+        g, b = tt.synth["grid"], tt.synth["bounds"]
+        for _ in range(n):
+            if phys:
+                atm = {k: synth.tile_slice(v, Lm, b) for k, v in synth.atmosphere_at(g, tt.cfg, tt.indices()["time"] / 86400.0).items()}
+                tt.step_fields(atm)
+            else:
+                su = synth.tile_slice(synth.sustr_at(synth.APP_BENCHMARK, g, tt.cfg, 0.0), Lm, b)
+                tt.step_forced(su, np.zeros_like(su), np.zeros_like(su))
+
+    advance(t, nsteps)
     d = t.diag()
     names = ["zeta1", "zeta2", "ubar1", "vbar1", "u1", "u2", "v1", "v2", "t1_0", "t2_0", "t1_1", "t2_1", "Huon", "Hvom", "W", "rho"]
     if phys:
@@ -45,7 +62,7 @@ def main():
     ref = None
     if rank == 0:
         ref = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, device=local, **phys)
-        ref.main3d(nsteps)
+        advance(ref, nsteps)
     for n in names:
         a = torch.from_numpy(t.get(n)).cuda()
         # gather variable-width tiles: pad to the widest
@@ -74,7 +91,7 @@ def main():
                     ok = False; print(f"  diag {k}: {d[k]!r} vs {dr[k]!r}", flush=True)
             elif d[k] != dr[k]:
                 ok = False; print(f"  diag {k}: {d[k]!r} vs {dr[k]!r}", flush=True)
-        print(f"MGPU_CHECK world={world} physics={'full' if phys else 'reduced'} grid={Lm}x{Mm}x{N} steps={nsteps}:", "BITWISE-IDENTICAL" if ok else "FAILED", flush=True)
+        print(f"MGPU_CHECK world={world} e2e={int(e2e)} physics={'full' if phys else 'reduced'} grid={Lm}x{Mm}x{N} steps={nsteps}:", "BITWISE-IDENTICAL" if ok else "FAILED", flush=True)
     perr = t.L.roms_b200_peer_error(t.h)
     if perr:
         print(f"rank {rank}: peer exchange timed out", flush=True)
