@@ -158,6 +158,10 @@ int roms_b200_set_avg(roms_b200_handle h, int nAVG, int ntsAVG);
  *   "fuse_phases"      1 (default) roms_b200_main3d_step / step_forced fuse routines that share operands (t3dmix2_s into
  *                      pre_step3d's tracer pass), 0 one kernel group per
  *                      routine as roms_b200_run_phase always does; the strict build gives the same bits either way
+ *   "ghost_compute"    1 (default) in a ring, bulk_flux and set_vbc compute their ghost columns (inputs are valid there) instead
+ *                      of exchanging them; 0 exchange after every phase as the reference's mp_exchange calls do.  Same bits
+ *                      either way on every column a routine reads; with 1 the outermost ghost column of bustr, bvstr, sustr
+ *                      may be stale (nothing reads it)
  *   "overlap"          1 (default) edge-first two-stream overlap of halo exchanges with interior compute (before attach only)
  *   "halo_timeout_s"   seconds a kernel waits for a neighbour's halo before it gives up and raises exit_flag 8
  *                      (default 30; <= 0 waits for ever)

@@ -262,6 +262,24 @@ int launch_with_halo(roms_b200_state* h, int phase, F fn, bool in_kernel_exchang
   return rc;
 }
 
+// Ring tiles: a phase whose output at a ghost column only depends on inputs that are valid there can compute its ghost columns
+// itself (gw columns west of Istr, ge east of Iend) instead of exchanging them -- the same expressions on bitwise identical
+// inputs give the neighbour's bits.  Used for the two 2-D phases whose exchange is not hidden behind interior work: bulk_flux
+// (0.059 -> 0.037 ms on a 256-column tile) and set_vbc (0.017 -> 0.010).  For the 3-D phases (set_massflux, rho_eos, omega,
+// set_depth: measured) the edge-first overlap already hides the exchange, and a whole-tile launch that has to wait for the
+// previous phase's exchange is slower.  Valid input ranges: the device keeps three ghost columns west (the eastward exchanges
+// move three) and two east of the tile.
+template <class F>
+int launch_ghosts(roms_b200_state* h, int gw, int ge, F fn) {
+  join_halo(h);
+  if (h->edge_pending) { cudaStreamWaitEvent(h->stream, h->ev_edge, 0); h->edge_pending = false; }
+  Par q = h->par;
+  q.Istr -= gw; q.Iend += ge;
+  fn(q, h->stream);
+  return NoError;
+}
+bool ghost_compute(const roms_b200_state* h) { return h->halo && h->ghost_compute; }
+
 bool fused_tmix(const roms_b200_state* h) { return h->in_step && h->fuse_phases && !h->cfg.mix_geo_ts; }
 
 // The 2-D time-index machine of LOOP_2D (main3d.F:592-700) for one call sequence that starts from (indx1, predictor = 0):
@@ -364,28 +382,41 @@ int run_phase_async(roms_b200_state* h, int phase) {
   int rc = NoError;
   switch (phase) {
     case ROMS_B200_SET_DATA: break;
-    case ROMS_B200_SET_MASSFLUX:
-      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_massflux(q, f, st); }); h->launches += 1; break;
-    case ROMS_B200_RHO_EOS: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_rho_eos(q, f, st); }); h->launches += 1; break;
-    case ROMS_B200_SET_VBC: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_vbc(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_SET_MASSFLUX:                                                    // Huon(i) needs Hz(i-1)
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_massflux(q, f, st); });
+      h->launches += 1; break;
+    case ROMS_B200_RHO_EOS:                                                         // column-local
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_rho_eos(q, f, st); });
+      h->launches += 1; break;
+    case ROMS_B200_SET_VBC:                                                         // bustr(i) needs v(i-1), bvstr(i) needs u(i+1)
+      if (ghost_compute(h)) rc = launch_ghosts(h, 2, 1, [&](const Par& q, cudaStream_t st) { launch_set_vbc(q, f, st); });
+      else rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_vbc(q, f, st); });
+      h->launches += 1; break;
     case ROMS_B200_ANA_VMIX:
       if (h->cfg.ana_vmix) { rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_ana_vmix(q, f, st); }); h->launches += 1; }
       break;
     case ROMS_B200_BULK_FLUX:
       if (!h->cfg.bulk_fluxes) return ConfigError;
       // the stresses at u / v points need the rho-point values of the neighbouring column: one launch over the whole tile
-      launch_full(h, [&](const Par& q, cudaStream_t st) { launch_bulk_flux(q, f, st); });
-      if (h->halo) rc = halo_exchange(h, halo_fields(h, phase), h->stream);
+      // in a ring the fluxes of the ghost columns are computed locally: rho points Istr-2 .. Iend+2, stresses Istr-1 .. Iend+2
+      if (ghost_compute(h)) rc = launch_ghosts(h, 1, 2, [&](const Par& q, cudaStream_t st) { launch_bulk_flux(q, f, st); });
+      else {
+        launch_full(h, [&](const Par& q, cudaStream_t st) { launch_bulk_flux(q, f, st); });
+        if (h->halo) rc = halo_exchange(h, halo_fields(h, phase), h->stream);
+      }
       h->launches += 2; break;
     case ROMS_B200_LMD_VMIX:
       if (!h->cfg.lmd_mixing) return ConfigError;
       rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_lmd_vmix(q, f, st); });
       h->launches += (p.Iend == p.Lm) ? 2 : 1; break;
-    case ROMS_B200_OMEGA: case ROMS_B200_OMEGA2:
-      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_omega(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_OMEGA: case ROMS_B200_OMEGA2:                                    // W(i) needs Huon(i+1); read at i-2 .. i+1 (rhs3d)
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_omega(q, f, st); });
+      h->launches += 1; break;
     case ROMS_B200_WVELOCITY:
       rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_wvelocity(q, f, h->nstp, st); }); h->launches += 1; break;
-    case ROMS_B200_SET_ZETA: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_zeta(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_SET_ZETA:
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_zeta(q, f, st); });
+      h->launches += 1; break;
     case ROMS_B200_PRE_STEP3D:
       h->par.fuse_tmix = fused_tmix(h) ? 1 : 0;
       rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_pre_step3d_t(q, f, st); });
@@ -402,7 +433,9 @@ int run_phase_async(roms_b200_state* h, int phase) {
     case ROMS_B200_RHS3D: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_rhs3d(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_UV3DMIX: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_uv3dmix2(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_STEP2D: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_step2d(q, f, st); }); h->launches += 1; break;
-    case ROMS_B200_SET_DEPTH: rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_depth(q, f, st); }); h->launches += 1; break;
+    case ROMS_B200_SET_DEPTH:                                                       // column-local
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_set_depth(q, f, st); });
+      h->launches += 1; break;
     case ROMS_B200_SET_AVG: {
       const int m = avg_mode(h);
       if (!m) break;
@@ -921,6 +954,7 @@ int roms_b200_set_option(roms_b200_handle h, const char* key, double value) {
   else if (k == "halo_timeout_s") h->halo_timeout_s = value;
   else if (k == "step2d_loop_kernel") h->loop_kernel = value != 0.0;
   else if (k == "fuse_phases") h->fuse_phases = value != 0.0;
+  else if (k == "ghost_compute") h->ghost_compute = value != 0.0;
   else return InputError;
   drop_graphs(h);
   return NoError;

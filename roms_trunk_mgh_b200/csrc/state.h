@@ -78,6 +78,7 @@ struct roms_b200_state {
   rb::LoopStep* d_loop_tab[3] = {nullptr, nullptr, nullptr};
   int loop_kernel = 1;    // roms_b200_set_option("step2d_loop_kernel")
   int fuse_phases = 1;    // roms_b200_set_option("fuse_phases"): cross-routine fusions of the whole-step path
+  bool ghost_compute = true;   // roms_b200_set_option("ghost_compute"): ring tiles compute the ghost columns of the cheap phases (api.cu launch_ghosts)
   // CUDA graphs of whole time steps, keyed by the stepping state at the start of the step (api.cu one_step)
   int fused_mode = 2;     // step2d halo exchange inside the kernels: 0 off, 1 one launch per sub-step, 2 edge / interior split launches
   bool in_step = false;   // inside step_phases (cross-routine fusions are only legal there: run_phase keeps routine granularity)

@@ -650,7 +650,7 @@ def _ngpus():
         return 0
 
 
-@pytest.mark.parametrize("mode", ["2", "1", "0", "2 step2d_loop_kernel=0", "1 step2d_loop_kernel=0", "2 physics=full", "0 physics=full peer=0", "2 physics=full e2e=1"])
+@pytest.mark.parametrize("mode", ["2", "1", "0", "2 step2d_loop_kernel=0", "1 step2d_loop_kernel=0", "2 physics=full", "0 physics=full peer=0", "2 physics=full e2e=1", "2 physics=full ghost_compute=0"])
 def test_tiling_invariance_across_gpus(mode):
     """The reference's own acceptance criterion (ROMS/Bin/verify.sh:985-1045): results do not depend on the tiling.  With more
     than one GPU on the box, step a BENCHMARK-shaped grid as an NtileI x 1 ring (one process per GPU, NVLink halo
@@ -660,7 +660,8 @@ def test_tiling_invariance_across_gpus(mode):
     mgpu_check.py also compares the diag scalars (maxima identical, sums to 1e-13).  physics=full: the shipped benchmark.h cpp
     set, i.e. bulk_flux and lmd_vmix on every tile (with the column Lm-1 copy of lmd_finish on the eastern one) -- Akv, Akt, hsbl and
     the surface fluxes are compared as well; peer=0: NCCL send/recv instead of the NVLink mailboxes; e2e=1: every step through
-    roms_b200_step_fields, each tile uploading its slice of the atmosphere (no halo exchange of the uploads)."""
+    roms_b200_step_fields, each tile uploading its slice of the atmosphere (no halo exchange of the uploads); ghost_compute=0:
+    bulk_flux and set_vbc exchange their outputs instead of computing their ghost columns."""
     n = _ngpus()
     if n < 2:
         pytest.skip("needs at least two GPUs on the box (tests/mgpu_check.py under torchrun)")
