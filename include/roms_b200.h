@@ -47,7 +47,8 @@ typedef struct roms_b200_config {
   int dj_gradps;                /* DJ_GRADPS -> prsgrd32.h, else prsgrd31.h (prsgrd.F:16-26)                       */
   int curvgrid;                 /* CURVGRID terms (rhs3d.F:515-564, step2d_LF_AM3.h:1333-1382)                     */
   int mix_geo_ts;               /* MIX_GEO_TS -> t3dmix2_geo.h, else MIX_S_TS -> t3dmix2_s.h                       */
-  int uv_qdrag;                 /* UV_QDRAG (set_vbc.F:591-624) else UV_LDRAG (set_vbc.F:629-652)                  */
+  int uv_qdrag;                 /* bottom stress: 0 UV_LDRAG (set_vbc.F:629-652), 1 UV_QDRAG (:591-624), 2 UV_LOGDRAG (:541-586,
+                                   roughness length "ZoBot" = GRID%ZoBot uploaded by the host)                          */
   int salinity;                 /* SALINITY                                                                        */
   int ana_vmix;                 /* ANA_VMIX, UPWELLING profile (ana_vmix.h:200-208,327-337), refreshed every step  */
   int wvelocity_every_step;     /* main3d.F:475                                                                    */
@@ -94,7 +95,7 @@ int roms_b200_array_bounds(roms_b200_handle h, int* out4);
 
 /* Field transfer by name.  Names follow the reference's module members: grid (mod_grid.F) "h","f","pm","pn","om_r",
  * "on_r","om_u","on_u","om_v","on_v","om_p","on_p","omn","fomn","pmon_r","pnom_r","pmon_u","pnom_u","pmon_v","pnom_v",
- * "pmon_p","pnom_p","dndx","dmde","rdrag","rdrag2"; mixing (mod_mixing.F) "visc2_r","visc2_p","diff2_<itrc>","Akv",
+ * "pmon_p","pnom_p","dndx","dmde","rdrag","rdrag2" ("ZoBot" with UV_LOGDRAG); mixing (mod_mixing.F) "visc2_r","visc2_p","diff2_<itrc>","Akv",
  * "Akt_<itrc>"; ocean (mod_ocean.F) "zeta<1-3>","ubar<1-3>","vbar<1-3>","rzeta<1-2>","rubar<1-2>","rvbar<1-2>",
  * "u<1-2>","v<1-2>","t<1-3>_<itrc>","ru<1-2>","rv<1-2>","rho","pden","W","wvel"; depths "Hz","z_r","z_w","Huon","Hvom";
  * coupling (mod_coupling.F) "Zt_avg1","DU_avg1","DU_avg2","DV_avg1","DV_avg2","rufrc","rvfrc","rhoA","rhoS";

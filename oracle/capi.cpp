@@ -14,12 +14,12 @@ bool lookup(Model& m, const std::string& name, double** p, int dims[6]) {
   auto set2 = [&](F2 a) { *p = a.p; dims[0] = a.LBi; dims[1] = a.UBi - a.LBi + 1; dims[2] = a.LBj; dims[3] = a.UBj - a.LBj + 1; dims[4] = 0; dims[5] = 1; return true; };
   auto set3 = [&](F3 a) { *p = a.p; dims[0] = a.LBi; dims[1] = a.UBi - a.LBi + 1; dims[2] = a.LBj; dims[3] = a.UBj - a.LBj + 1; dims[4] = a.LBk; dims[5] = a.UBk - a.LBk + 1; return true; };
   static const char* n2[] = {"h", "f", "pm", "pn", "om_r", "on_r", "om_u", "on_u", "om_v", "on_v", "om_p", "on_p", "omn", "fomn", "pmon_r", "pnom_r",
-                             "pmon_u", "pnom_u", "pmon_v", "pnom_v", "pmon_p", "pnom_p", "dndx", "dmde", "rdrag", "rdrag2", "visc2_r", "visc2_p",
+                             "pmon_u", "pnom_u", "pmon_v", "pnom_v", "pmon_p", "pnom_p", "dndx", "dmde", "rdrag", "rdrag2", "ZoBot", "visc2_r", "visc2_p",
                              "Zt_avg1", "DU_avg1", "DU_avg2", "DV_avg1", "DV_avg2", "rufrc", "rvfrc", "rhoA", "rhoS", "sustr", "svstr", "bustr", "bvstr",
                              "avgzeta", "avgu2d", "avgv2d", "alpha", "beta", "srflx", "Jwtype",
                              "Uwind", "Vwind", "Tair", "Pair", "Hair", "rain", "cloud", "lrflx", "lhflx", "shflx", "hsbl", "ksbl", "latr", "lonr"};
   F2* a2[] = {&m.h, &m.f, &m.pm, &m.pn, &m.om_r, &m.on_r, &m.om_u, &m.on_u, &m.om_v, &m.on_v, &m.om_p, &m.on_p, &m.omn, &m.fomn, &m.pmon_r, &m.pnom_r,
-              &m.pmon_u, &m.pnom_u, &m.pmon_v, &m.pnom_v, &m.pmon_p, &m.pnom_p, &m.dndx, &m.dmde, &m.rdrag, &m.rdrag2, &m.visc2_r, &m.visc2_p,
+              &m.pmon_u, &m.pnom_u, &m.pmon_v, &m.pnom_v, &m.pmon_p, &m.pnom_p, &m.dndx, &m.dmde, &m.rdrag, &m.rdrag2, &m.ZoBot, &m.visc2_r, &m.visc2_p,
               &m.Zt_avg1, &m.DU_avg1, &m.DU_avg2, &m.DV_avg1, &m.DV_avg2, &m.rufrc, &m.rvfrc, &m.rhoA, &m.rhoS, &m.sustr, &m.svstr, &m.bustr, &m.bvstr,
               &m.avgzeta, &m.avgu2d, &m.avgv2d, &m.alpha, &m.beta, &m.srflx, &m.Jwtype,
               &m.Uwind, &m.Vwind, &m.Tair, &m.Pair, &m.Hair, &m.rain, &m.cloud, &m.lrflx, &m.lhflx, &m.shflx, &m.hsbl, &m.ksbl, &m.latr, &m.lonr};
@@ -87,7 +87,7 @@ int orc_set_option(void* hp, const char* key, double val) {
   else if (k == "dt") c.dt = val; else if (k == "ndtfast") c.ndtfast = (int)val; else if (k == "visc2") c.visc2 = val;
   else if (k == "tnu2") { c.tnu2[0] = c.tnu2[1] = val; } else if (k == "gamma2") c.gamma2 = val;
   else if (k == "Akv_bak") c.Akv_bak = val; else if (k == "Akt_bak") { c.Akt_bak[0] = c.Akt_bak[1] = val; }
-  else if (k == "rdrg") c.rdrg = val; else if (k == "rdrg2") c.rdrg2 = val;
+  else if (k == "rdrg") c.rdrg = val; else if (k == "rdrg2") c.rdrg2 = val; else if (k == "Zob") c.Zob = val;
   else if (k == "bv_frequency") c.bv_frequency = (int)val; else if (k == "eos_tderivative") c.eos_tderivative = (int)val;
   else if (k == "solar_source") c.solar_source = (int)val; else if (k == "lmd_nonlocal") c.lmd_nonlocal = (int)val;
   else if (k == "nAVG") c.nAVG = (int)val; else if (k == "ntsAVG") c.ntsAVG = (int)val;

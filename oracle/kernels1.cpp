@@ -203,7 +203,28 @@ void set_vbc(Model& m, const Bnd& b) {
         m.btflx[is](i, j) = m.btflx[is](i, j) * S(i, j, 1);
       }
   }
-  if (c.uv_qdrag) {
+  if (c.uv_qdrag == 2) {                                          // UV_LOGDRAG, set_vbc.F:541-586 (no LIMIT_BSTRESS)
+    const double vonKar = 0.41, Cdb_min = 0.000001, Cdb_max = 0.5;  // mod_scalars.F:444, :747-748
+    S2 wrk(IminS, ImaxS, JminS, JmaxS);
+    for (int j = JstrV - 1; j <= Jend; ++j)
+      for (int i = IstrU - 1; i <= Iend; ++i) {
+        const double cff1 = 1.0 / std::log((m.z_r(i, j, 1) - m.z_w(i, j, 0)) / m.ZoBot(i, j));
+        const double cff2 = vonKar * vonKar * cff1 * cff1;
+        wrk(i, j) = std::min(Cdb_max, std::max(Cdb_min, cff2));
+      }
+    for (int j = Jstr; j <= Jend; ++j)
+      for (int i = IstrU; i <= Iend; ++i) {
+        const double cff1 = 0.25 * (v(i, j, 1) + v(i, j + 1, 1) + v(i - 1, j, 1) + v(i - 1, j + 1, 1));
+        const double cff2 = std::sqrt(u(i, j, 1) * u(i, j, 1) + cff1 * cff1);
+        m.bustr(i, j) = 0.5 * (wrk(i - 1, j) + wrk(i, j)) * u(i, j, 1) * cff2;
+      }
+    for (int j = JstrV; j <= Jend; ++j)
+      for (int i = Istr; i <= Iend; ++i) {
+        const double cff1 = 0.25 * (u(i, j, 1) + u(i + 1, j, 1) + u(i, j - 1, 1) + u(i + 1, j - 1, 1));
+        const double cff2 = std::sqrt(cff1 * cff1 + v(i, j, 1) * v(i, j, 1));
+        m.bvstr(i, j) = 0.5 * (wrk(i, j - 1) + wrk(i, j)) * v(i, j, 1) * cff2;
+      }
+  } else if (c.uv_qdrag) {
     for (int j = Jstr; j <= Jend; ++j)
       for (int i = IstrU; i <= Iend; ++i) {
         double cff1 = 0.25 * (v(i, j, 1) + v(i, j + 1, 1) + v(i - 1, j, 1) + v(i - 1, j + 1, 1));

@@ -131,7 +131,8 @@ struct Cfg {
   int curvgrid = 0;               // CURVGRID
   int spherical = 0;              // SPHERICAL (set-up only)
   int mix_geo_ts = 0;             // MIX_GEO_TS (else MIX_S_TS)
-  int uv_qdrag = 0;               // UV_QDRAG (else UV_LDRAG)
+  int uv_qdrag = 0;               // 0 UV_LDRAG, 1 UV_QDRAG, 2 UV_LOGDRAG (set_vbc.F:541-652)
+  double Zob = 0.02;              // bottom roughness (m), roms_*.in Zob -> GRID%ZoBot (mod_grid.F:1256)
   int salinity = 1;               // SALINITY
   int ana_vmix = 0;               // ANA_VMIX (UPWELLING profile)
   int wvelocity_every_step = 1;   // main3d.F:475
@@ -178,7 +179,7 @@ struct Model {
   std::vector<std::vector<double>> pool;
   // ---- 2-D grid (mod_grid.F)
   F2 h, f, pm, pn, om_r, on_r, om_u, on_u, om_v, on_v, om_p, on_p, omn, fomn, pmon_r, pnom_r, pmon_u, pnom_u,
-      pmon_v, pnom_v, pmon_p, pnom_p, dndx, dmde, xr, yr, latr, lonr, rdrag, rdrag2;
+      pmon_v, pnom_v, pmon_p, pnom_p, dndx, dmde, xr, yr, latr, lonr, rdrag, rdrag2, ZoBot;
   F2 visc2_r, visc2_p; F2 diff2[2];             // mod_mixing.F
   // ---- 2-D state (mod_ocean.F, mod_coupling.F, mod_forces.F)
   F2 zeta[4], ubar[4], vbar[4];                 // [1..3]

@@ -145,7 +145,7 @@ void Model::allocate() {
   const int N = c.N;
   pool.clear(); pool.reserve(400);
   F2* g2[] = {&h, &f, &pm, &pn, &om_r, &on_r, &om_u, &on_u, &om_v, &on_v, &om_p, &on_p, &omn, &fomn, &pmon_r, &pnom_r,
-              &pmon_u, &pnom_u, &pmon_v, &pnom_v, &pmon_p, &pnom_p, &dndx, &dmde, &xr, &yr, &latr, &lonr, &rdrag, &rdrag2,
+              &pmon_u, &pnom_u, &pmon_v, &pnom_v, &pmon_p, &pnom_p, &dndx, &dmde, &xr, &yr, &latr, &lonr, &rdrag, &rdrag2, &ZoBot,
               &visc2_r, &visc2_p, &diff2[0], &diff2[1], &Zt_avg1, &DU_avg1, &DU_avg2, &DV_avg1, &DV_avg2, &rufrc, &rvfrc,
               &rhoA, &rhoS, &sustr, &svstr, &bustr, &bvstr, &stflx[0], &stflx[1], &btflx[0], &btflx[1], &stflux[0], &stflux[1], &btflux[0], &btflux[1]};
   for (F2* p_ : g2) *p_ = new2();
@@ -174,7 +174,8 @@ void Model::allocate() {
   // mod_grid.F:1257-1261
   for (int j = LBj; j <= UBj; ++j)
     for (int i = LBi; i <= UBi; ++i) {
-      if (c.uv_qdrag) rdrag2(i, j) = c.rdrg2; else rdrag(i, j) = c.rdrg;
+      if (c.uv_qdrag == 1) rdrag2(i, j) = c.rdrg2; else if (c.uv_qdrag == 0) rdrag(i, j) = c.rdrg;
+      ZoBot(i, j) = c.Zob;                                        // mod_grid.F:1256
     }
 }
 

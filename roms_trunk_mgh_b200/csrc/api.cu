@@ -364,6 +364,7 @@ int ensure_optional(roms_b200_state* h, int phase) {
   if (!h->lazy) return NoError;
   std::vector<std::string> names;
   if (phase == ROMS_B200_RHO_EOS) names = {"bvf", "alpha", "beta"};
+  else if (phase == ROMS_B200_SET_VBC && h->cfg.uv_qdrag == 2) names = {"ZoBot", "z_r", "z_w"};
   else if (phase == ROMS_B200_BULK_FLUX) names = {"lrflx", "lhflx", "shflx", "sustr", "svstr", "stflux_" + std::to_string(h->cfg.itemp - 1)};
   else if (phase == ROMS_B200_LMD_VMIX) { names = {"hsbl", "ksbl", "Akv"}; for (int it = 0; it < h->cfg.NT; ++it) { names.push_back("ghats_" + std::to_string(it)); names.push_back("Akt_" + std::to_string(it)); } }
   else if (phase == ROMS_B200_PRE_STEP3D) { names = {"srflx", "Jwtype", "z_w"}; for (int it = 0; it < h->cfg.NT; ++it) names.push_back("ghats_" + std::to_string(it)); }
@@ -674,6 +675,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   *out = nullptr;
   if (cfg->N < 4 || cfg->N > MAXN || cfg->NT < 1 || cfg->NT > MAXNT || cfg->Lm < 8 || cfg->Mm < 4) return ConfigError;
   if (cfg->NtileI < 1 || cfg->NtileJ < 1 || cfg->tile < 0 || cfg->tile >= cfg->NtileI * cfg->NtileJ) return ConfigError;
+  if (cfg->uv_qdrag < 0 || cfg->uv_qdrag > 2) return ConfigError;
   // lmd_skpp reads bvf, alpha / beta, srflx and writes ghats: the switches that provide those arrays must be on with it
   if (cfg->lmd_mixing && !(cfg->bv_frequency && cfg->eos_tderivative && cfg->solar_source && cfg->lmd_nonlocal)) return ConfigError;
   int ndev = 0;
@@ -766,6 +768,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
     rc |= alloc_field(h, "stflux_" + s, &f.stflux[it], 0, 1);
     rc |= alloc_field(h, "btflux_" + s, &f.btflux[it], 0, 1);
   }
+  if (cfg->uv_qdrag == 2) rc |= alloc_field(h, "ZoBot", &f.ZoBot, 0, 1);
   if (cfg->bv_frequency) rc |= alloc_field(h, "bvf", &f.bvf, 0, N + 1);
   if (cfg->eos_tderivative) { rc |= alloc_field(h, "alpha", &f.alpha, 0, 1); rc |= alloc_field(h, "beta", &f.beta, 0, 1); }
   if (cfg->solar_source || cfg->bulk_fluxes) rc |= alloc_field(h, "srflx", &f.srflx, 0, 1);

@@ -47,7 +47,7 @@ struct Par {
 struct Flds {
   // grid
   double *h, *f, *pm, *pn, *om_r, *on_r, *om_u, *on_u, *om_v, *on_v, *om_p, *on_p, *omn, *fomn, *pmon_r, *pnom_r, *pmon_u, *pnom_u,
-      *pmon_v, *pnom_v, *pmon_p, *pnom_p, *dndx, *dmde, *rdrag, *rdrag2, *visc2_r, *visc2_p;
+      *pmon_v, *pnom_v, *pmon_p, *pnom_p, *dndx, *dmde, *rdrag, *rdrag2, *visc2_r, *visc2_p, *ZoBot;
   double* diff2[MAXNT];
   // 2-D state
   double *zeta[4], *ubar[4], *vbar[4], *rzeta[3], *rubar[3], *rvbar[3];

@@ -173,7 +173,13 @@ __global__ void __launch_bounds__(256, X ? EOS_MINB : 6) k_rho_eos(Par p, Flds f
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// set_vbc_tile (ROMS/Nonlinear/set_vbc.F:278-283, :340-355, :591-624 quadratic, :629-652 linear, BCs :657-662)
+// UV_LOGDRAG drag coefficient of a cell (set_vbc.F:545-551; vonKar, Cdb_min, Cdb_max: mod_scalars.F:444, :747-748)
+__device__ __forceinline__ double logdrag_cd(const Flds& f, int q1, int q0, int q2d) {
+  const double cff1 = 1.0 / log((f.z_r[q1] - f.z_w[q0]) / f.ZoBot[q2d]);
+  const double cff2 = 0.41 * 0.41 * cff1 * cff1;
+  return dmin(0.5, dmax(0.000001, cff2));
+}
+// set_vbc_tile (ROMS/Nonlinear/set_vbc.F:278-283, :340-355, :541-586 logarithmic, :591-624 quadratic, :629-652 linear, BCs :657-662)
 __global__ void __launch_bounds__(256) k_set_vbc(Par p, Flds f) {
   const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;          // 0..Mm+1
@@ -195,7 +201,12 @@ __global__ void __launch_bounds__(256) k_set_vbc(Par p, Flds f) {
   const double* __restrict__ v = f.v[p.nrhs];
   if (j >= 1 && j <= p.Mm) {
     double bu;
-    if (p.uv_qdrag) {
+    if (p.uv_qdrag == 2) {
+      const double cff1 = 0.25 * (v[o1 + i] + v[o1 + p.P + i] + v[o1 + i - 1] + v[o1 + p.P + i - 1]);
+      const double uu = u[o1 + i];
+      const double cff2 = sqrt(uu * uu + cff1 * cff1);
+      bu = 0.5 * (logdrag_cd(f, o1 + i - 1, o2 + i - 1, o2 + i - 1) + logdrag_cd(f, o1 + i, o2 + i, o2 + i)) * uu * cff2;
+    } else if (p.uv_qdrag) {
       const double cff1 = 0.25 * (v[o1 + i] + v[o1 + p.P + i] + v[o1 + i - 1] + v[o1 + p.P + i - 1]);
       const double uu = u[o1 + i];
       const double cff2 = sqrt(uu * uu + cff1 * cff1);
@@ -207,7 +218,12 @@ __global__ void __launch_bounds__(256) k_set_vbc(Par p, Flds f) {
   }
   if (j >= 2 && j <= p.Mm) {
     double bv;
-    if (p.uv_qdrag) {
+    if (p.uv_qdrag == 2) {
+      const double cff1 = 0.25 * (u[o1 + i] + u[o1 + i + 1] + u[o1 - p.P + i] + u[o1 - p.P + i + 1]);
+      const double vv = v[o1 + i];
+      const double cff2 = sqrt(cff1 * cff1 + vv * vv);
+      bv = 0.5 * (logdrag_cd(f, o1 - p.P + i, o2 - p.P + i, o2 - p.P + i) + logdrag_cd(f, o1 + i, o2 + i, o2 + i)) * vv * cff2;
+    } else if (p.uv_qdrag) {
       const double cff1 = 0.25 * (u[o1 + i] + u[o1 + i + 1] + u[o1 - p.P + i] + u[o1 - p.P + i + 1]);
       const double vv = v[o1 + i];
       const double cff2 = sqrt(cff1 * cff1 + vv * vv);

@@ -199,8 +199,10 @@ def build(app, Lm=0, Mm=0, N=0, **overrides):
     F["visc2_r"] = par["visc2"] * ones; F["visc2_p"] = par["visc2"] * ones
     for it in range(NT):
         F[f"diff2_{it}"] = par["tnu2"] * ones
-    F["rdrag"] = (0.0 if cfg.uv_qdrag else par["rdrg"]) * ones
-    F["rdrag2"] = (par["rdrg2"] if cfg.uv_qdrag else 0.0) * ones
+    F["rdrag"] = (par["rdrg"] if cfg.uv_qdrag == 0 else 0.0) * ones
+    F["rdrag2"] = (par["rdrg2"] if cfg.uv_qdrag == 1 else 0.0) * ones
+    if cfg.uv_qdrag == 2:
+        F["ZoBot"] = 0.02 * ones                               # UV_LOGDRAG: roms_*.in Zob = 0.02 m
     # ---- s-coordinate and depths at rest (set_depth.F:210-246, Zt_avg1 = 0)
     sc_r, Cs_r, sc_w, Cs_w = set_scoord(N, par["theta_s"], par["theta_b"])
     hc = par["Tcline"]

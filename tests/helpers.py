@@ -34,6 +34,7 @@ def optional_names(o):
     """Names of the arrays that exist only when a cpp switch of the BENCHMARK set is on (include/roms_b200.h)."""
     NT = int(o.opt("NT"))
     v = []
+    if o.opt("uv_qdrag") == 2: v += ["ZoBot"]
     if o.opt("bv_frequency"): v += ["bvf"]
     if o.opt("eos_tderivative"): v += ["alpha", "beta"]
     if o.opt("solar_source"): v += ["srflx", "Jwtype"]

@@ -29,6 +29,7 @@ CASES = {
     "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, mix_geo_ts=1)),    # MIX_GEO_TS with tnu2 = 500
     "benchmark_p31": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, dj_gradps=0, nonlin_eos=0)),   # prsgrd31 + linear EOS
     "benchmark_splines": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, vadv=3)),      # Vadvection = SPLINES (tridiagonal solve per column)
+    "benchmark_logdrag": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, uv_qdrag=2)),   # UV_LOGDRAG (device log(): see test_uv_logdrag)
     "ragged": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7)),                          # sizes that are no multiple of any tile
 }
 
@@ -52,7 +53,31 @@ def test_native_library_is_loaded():
     assert "libroms_b200.so" in maps and "libroms_b200_strict.so" in maps
 
 
-@pytest.mark.parametrize("case", list(CASES))
+def test_uv_logdrag():
+    """UV_LOGDRAG (set_vbc.F:541-586): the drag coefficient is vonKar^2 / log(dz/ZoBot)^2 clipped to [Cdb_min, Cdb_max]; the device
+    log() differs from glibc's in the last bit, so bustr / bvstr are held to 1e-14 and the state after 6 steps to 1e-12."""
+    app, kw = CASES["benchmark_logdrag"]
+    o, t = make_pair(app, strict=True, spinup=2, **kw)
+    begin_step(o, t)
+    for ph in ("set_massflux", "rho_eos", "set_vbc"):
+        o.run_phase(ph); t.run_phase(ph)
+    for n in ("bustr", "bvstr"):
+        a, b = o.field(n), t.get(n)
+        assert np.abs(a).max() > 0 and np.max(np.abs(a - b)) <= 1e-14 * np.abs(a).max(), n
+    o2, t2 = make_pair(app, strict=True, **kw)
+    for _ in range(6):
+        o2.step(1); t2.main3d(1)
+    assert not compare(o2, t2, ["zeta1", "u1", "u2", "v1", "v2", "t1_0", "t2_0", "bustr", "bvstr"], exact=False, rtol=1e-12)
+    # the coefficient is live: the quadratic law with rdrg2 gives another stress
+    o3, _t3 = make_pair(orc.APP_BENCHMARK, strict=True, spinup=2, Lm=64, Mm=32, N=10)
+    _t3.close()
+    d = o3.indices(); d["nstp"] = 1 + ((d["iic"] - d["ntstart"]) % 2); d["nnew"] = 3 - d["nstp"]; d["nrhs"] = d["nstp"]; o3.set_indices(d)
+    o3.run_phase("set_vbc")
+    assert not np.array_equal(o3.field("bustr"), o.field("bustr"))
+    t.close(); t2.close()
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c != "benchmark_logdrag"])
 @pytest.mark.parametrize("spinup", [0, 1, 3])      # iic == ntfirst (Euler), ntfirst+1 (AB2), later (AB3) start-up branches
 def test_strict_bit_exact_every_phase(case, spinup):
     app, kw = CASES[case]

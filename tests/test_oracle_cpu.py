@@ -170,7 +170,7 @@ def test_cabi_routine_args_name_known_fields():
     L = _lib.load(False)
     n2, n3 = field_names(2)
     # + the arrays that exist only with the BENCHMARK cpp switches on (include/roms_b200.h, roms_b200_config)
-    optional = ["bvf", "alpha", "beta", "srflx", "Jwtype", "ghats_0", "ghats_1", "Uwind", "Vwind", "Tair", "Pair", "Hair", "rain", "cloud",
+    optional = ["ZoBot", "bvf", "alpha", "beta", "srflx", "Jwtype", "ghats_0", "ghats_1", "Uwind", "Vwind", "Tair", "Pair", "Hair", "rain", "cloud",
                 "lrflx", "lhflx", "shflx", "hsbl", "ksbl"]
     known = set(n2 + n3 + optional)
     for name, ph in _lib.PHASES.items():
