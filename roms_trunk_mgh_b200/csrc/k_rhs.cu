@@ -11,7 +11,8 @@ __device__ __forceinline__ double d2y(const double* __restrict__ A, int o, int P
 
 // ROMS/Nonlinear/rhs3d.F:174-1671.  (A variant that gave the xi- and eta-momentum equations of a column to two threads of the
 // same CTA -- half the live operands, 122 registers, twice the resident warps -- was exact but slower, 0.65 vs 0.56 ms: the
-// kernel is bound by L1 / issue throughput, and the split adds ~10% loads.  profiles/README.md.)
+// kernel is bound by L1 / issue throughput, and the split adds ~10% loads.  A shared-memory tiled form that evaluates every face
+// flux once -- tools/variants/k_rhs3d_tiled.cuh -- is exact too and also slower, 0.546 vs 0.517 ms.  profiles/README.md.)
 #ifndef RHS_MINB
 #define RHS_MINB 2
 #endif
