@@ -163,6 +163,7 @@ void orc_bounds(int Lm, int Mm, int NtileI, int NtileJ, int tile, int distribute
   std::memcpy(out, v, sizeof(v));
 }
 
+void orc_physics_point(int which, const double* in, double* out) { physics_point(which, in, out); }
 void orc_eos_point(double Tt, double Ts, double Tp, double* out3) { eos_point(Tt, Ts, Tp, &out3[0], &out3[1], &out3[2]); }
 
 // set_weights stand-alone: returns nfast; chk[5] = FORMAT 40 integrals; w1,w2 sized 2*ndtfast+2

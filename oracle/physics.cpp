@@ -566,6 +566,13 @@ static void lmd_finish(Model& m, const Bnd& b) {
   }
 }
 
+// point functions for the known-answer tests (tests/test_oracle_cpu.py)
+void physics_point(int which, const double* in, double* out) {
+  if (which == 0) { out[0] = bulk_psiu(in[0]); out[1] = bulk_psit(in[0]); }                                 // stability functions at Z/L
+  else if (which == 1) out[0] = lmd_swfrac(-1.0, in[0], (int)in[1]);                                       // shortwave fraction at depth Z
+  else if (which == 2) lmd_wscale(in[0], in[1], in[2], out[0], out[1]);                                    // wm, ws (Ustar, sigma, Bflux)
+}
+
 // lmd_vmix (lmd_vmix.F:33-96): interior scheme, surface boundary layer, convective adjustment + boundary copies ...
 void lmd_vmix(Model& m, const Bnd& b) {
   lmd_vmix_interior(m, b);

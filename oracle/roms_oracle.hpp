@@ -231,6 +231,7 @@ void set_avg(Model& m, const Bnd& b);         // ROMS/Nonlinear/set_avg.F
 void ana_atmosphere(Model& m, const Bnd& b);  // set_data.F:197-394 -> ana_cloud/tair/humid/srflux/winds/rain/pair (BENCHMARK)
 void bulk_flux(Model& m, const Bnd& b);       // ROMS/Nonlinear/bulk_flux.F
 void lmd_vmix(Model& m, const Bnd& b);        // ROMS/Nonlinear/lmd_vmix.F, lmd_skpp.F, lmd_swfrac.F
+void physics_point(int which, const double* in, double* out);   // bulk_psiu/psit, lmd_swfrac, KPP velocity scales at a point
 void lmd_vmix_bc(Model& m, const Bnd& b);     // ... its closing bc_w3d / exchange (second stage, see physics.cpp)
 
 // ---- periodic exchanges / boundary conditions

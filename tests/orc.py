@@ -66,6 +66,7 @@ def lib(kind="parity"):
     L.orc_diag.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.orc_bounds.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_int)]
     L.orc_eos_point.argtypes = [C.c_double] * 3 + [C.POINTER(C.c_double)]
+    L.orc_physics_point.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.orc_set_weights.restype = C.c_int
     L.orc_set_weights.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.orc_timed_steps.restype = C.c_double
@@ -156,6 +157,14 @@ def eos_point(T, S, z, kind="parity"):
     out = (C.c_double * 3)()
     lib(kind).orc_eos_point(T, S, z, out)
     return out[0], out[1], out[2]
+
+
+def physics_point(which, *args, kind="parity"):
+    """which = 0: (bulk_psiu, bulk_psit)(Z/L); 1: lmd_swfrac(depth Z >= 0, Jerlov type); 2: (wm, ws)(Ustar, sigma, Bflux)."""
+    a = (C.c_double * 4)(*[float(x) for x in args] + [0.0] * (4 - len(args)))
+    out = (C.c_double * 2)()
+    lib(kind).orc_physics_point(which, a, out)
+    return out[0], out[1]
 
 
 def set_weights(ndtfast, dt=1.0, kind="parity"):

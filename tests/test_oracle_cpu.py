@@ -622,3 +622,40 @@ def test_splines_vertical_advection_properties():
         runs[vadv] = o.field("t1_0").copy()
     dT = np.max(np.abs(runs[0] - runs[3]))
     assert 0.0 < dT < 1e-4, dT
+
+
+def test_physics_point_functions_known_answers():
+    """Analytical anchors of the parameterisations' point functions (they do not come from the restatement itself):
+    * bulk_psiu / bulk_psit (bulk_flux.F:950-1066) vanish at neutral stratification from both sides, are positive when unstable
+      and negative when stable, and the stable branch tends to the Beljaars-Holtslag form -(1 + z/L) - 8.525 for large z/L;
+    * lmd_swfrac (lmd_swfrac.F:66-80) is 1 at the surface, decreases monotonically, and at depth the slowly decaying band is left:
+      (1 - r1) exp(-z / mu2);
+    * the KPP velocity scales (lmd_skpp.F:454-476) are vonKar*Ustar at neutral forcing, smaller under stable and larger under
+      unstable forcing, ws >= wm when unstable, and follow the 1/3-power convective limit vonKar*(cs*vonKar*sigma*|B|)^(1/3) for
+      Ustar -> 0."""
+    vonKar = 0.41
+    for s in (1e-9, -1e-9):
+        pu, pt = orc.physics_point(0, s)
+        assert abs(pu) < 1e-2 and abs(pt) < 1e-2                      # the stable form is -(1 + ZoL - 9.520 + 8.525) = -0.005 at 0
+    pu, pt = orc.physics_point(0, -1.0)
+    assert pu > 0.5 and pt > 0.5
+    pu, pt = orc.physics_point(0, +1.0)
+    assert pu < -1.0 and pt < -1.0
+    pu, _ = orc.physics_point(0, 500.0)
+    assert abs(pu + (1.0 + 500.0 + 8.525)) < 1e-6                       # exp(-min(50, 0.35 z/L)) has killed the middle term
+    assert orc.physics_point(1, 0.0, 1)[0] == 1.0
+    prev = 1.0
+    for z in (0.5, 2.0, 10.0, 50.0, 200.0):
+        f = orc.physics_point(1, z, 1)[0]
+        assert 0.0 < f < prev
+        prev = f
+    assert abs(orc.physics_point(1, 200.0, 1)[0] - (1.0 - 0.58) * np.exp(-200.0 / 23.0)) < 1e-12   # Jerlov type I: r1 = 0.58, mu2 = 23 m
+    us = 0.01
+    wm, ws = orc.physics_point(2, us, 5.0, 0.0)
+    assert abs(wm - vonKar * us) < 1e-15 and ws == wm
+    wm_s, ws_s = orc.physics_point(2, us, 5.0, +1e-7)
+    wm_u, ws_u = orc.physics_point(2, us, 5.0, -1e-7)
+    assert wm_s < wm < wm_u and ws_s < ws < ws_u and ws_u >= wm_u
+    wm_c, ws_c = orc.physics_point(2, 1e-12, 5.0, -1e-7)
+    assert abs(ws_c - vonKar * (98.96 * vonKar * 5.0 * 1e-7) ** (1.0 / 3.0)) < 1e-9 * ws_c
+    assert abs(wm_c - vonKar * (8.36 * vonKar * 5.0 * 1e-7) ** (1.0 / 3.0)) < 1e-9 * wm_c
