@@ -76,6 +76,7 @@ typedef struct roms_b200_config {
   int bulk_fluxes;              /* BULK_FLUXES + LONGWAVE (bulk_flux.F:381-948)                                        */
   int lmd_mixing;               /* LMD_MIXING (lmd_vmix.F:100-659, lmd_skpp.F:246-923, lmd_swfrac.F)                   */
   double blk_ZQ, blk_ZT, blk_ZW;/* BLK_ZQ, BLK_ZT, BLK_ZW (m): heights of the humidity / temperature / wind data       */
+  int bvf_mixing;               /* BVF_MIXING (bvf_mix.F:92-127; main3d.F:468-469): Akv, Akt from "bvf"; needs bv_frequency   */
 } roms_b200_config;
 
 /* Fills *cfg with the shipped defaults of roms_<app>.in (Lm,Mm,N = 0 keeps the shipped grid size). */
@@ -135,7 +136,8 @@ enum {
   ROMS_B200_SET_DATA = 19,     /* (host forcing; no-op)  */  ROMS_B200_STEP2D_LOOP = 20, /* main3d.F:592-700       */
   ROMS_B200_SET_AVG = 22,      /* set_avg.F:128          */
   ROMS_B200_BULK_FLUX = 23,    /* bulk_flux.F:59         */
-  ROMS_B200_LMD_VMIX = 24      /* lmd_vmix.F:33 (lmd_vmix_tile, lmd_skpp, lmd_finish) */
+  ROMS_B200_LMD_VMIX = 24,     /* lmd_vmix.F:33 (lmd_vmix_tile, lmd_skpp, lmd_finish) */
+  ROMS_B200_BVF_MIX = 25       /* bvf_mix.F:27           */
 };
 int roms_b200_run_phase(roms_b200_handle h, int phase);
 

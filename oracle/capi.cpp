@@ -91,6 +91,7 @@ int orc_set_option(void* hp, const char* key, double val) {
   else if (k == "bv_frequency") c.bv_frequency = (int)val; else if (k == "eos_tderivative") c.eos_tderivative = (int)val;
   else if (k == "solar_source") c.solar_source = (int)val; else if (k == "lmd_nonlocal") c.lmd_nonlocal = (int)val;
   else if (k == "nAVG") c.nAVG = (int)val; else if (k == "ntsAVG") c.ntsAVG = (int)val;
+  else if (k == "bvf_mixing") c.bvf_mixing = (int)val;
   else if (k == "bulk_fluxes") c.bulk_fluxes = (int)val; else if (k == "lmd_mixing") c.lmd_mixing = (int)val;
   else return 1;
   return 0;
@@ -108,6 +109,7 @@ double orc_get_option(void* hp, const char* key) {
   if (k == "nfast") return m.nfast; if (k == "dtfast") return m.dtfast; if (k == "hc") return m.hc; if (k == "wvelocity_every_step") return c.wvelocity_every_step;
   if (k == "bv_frequency") return c.bv_frequency; if (k == "eos_tderivative") return c.eos_tderivative;
   if (k == "solar_source") return c.solar_source; if (k == "lmd_nonlocal") return c.lmd_nonlocal;
+  if (k == "bvf_mixing") return c.bvf_mixing;
   if (k == "bulk_fluxes") return c.bulk_fluxes; if (k == "lmd_mixing") return c.lmd_mixing;
   if (k == "blk_ZQ") return c.blk_ZQ; if (k == "blk_ZT") return c.blk_ZT; if (k == "blk_ZW") return c.blk_ZW;
   if (k == "app") return c.app; if (k == "nAVG") return c.nAVG; if (k == "ntsAVG") return c.ntsAVG;

@@ -141,6 +141,7 @@ void run_phase(Model& m, int phase, int nthreads) {
       });
       break;
     case PH_BULK_FLUX: if (m.c.bulk_fluxes) for_tiles(m, nthreads, [&](const Bnd& b) { bulk_flux(m, b); }); break;
+    case PH_BVF_MIX: if (m.c.bvf_mixing) for_tiles(m, nthreads, [&](const Bnd& b) { bvf_mix(m, b); }); break;
     case PH_LMD_VMIX:
       if (m.c.lmd_mixing) {
         for_tiles(m, nthreads, [&](const Bnd& b) { lmd_vmix(m, b); });
@@ -189,7 +190,7 @@ void main3d_step(Model& m, int nthreads) {
   run_phase(m, PH_DIAG, nthreads);                                                   // :314
   run_phase(m, PH_BULK_FLUX, nthreads);                                              // :384-390
   run_phase(m, PH_SET_VBC, nthreads);                                                // :394
-  if (!m.c.ana_vmix) run_phase(m, PH_LMD_VMIX, nthreads);                            // :467
+  if (!m.c.ana_vmix) { if (m.c.lmd_mixing) run_phase(m, PH_LMD_VMIX, nthreads); else run_phase(m, PH_BVF_MIX, nthreads); }   // :467-469
   for_tiles(m, nthreads, [&](const Bnd& b) {                                         // :465-475
     if (m.c.ana_vmix) ana_vmix(m, b);
     omega(m, b);

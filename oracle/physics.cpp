@@ -566,6 +566,34 @@ static void lmd_finish(Model& m, const Bnd& b) {
   }
 }
 
+// bvf_mix_tile (bvf_mix.F:92-127; constants mod_scalars.F:1793-1796): diffusivity ~ 1/N, convective value where unstable
+void bvf_mix(Model& m, const Bnd& b) {
+  const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
+  const int N = c.N, itemp = c.itemp - 1, isalt = c.isalt - 1;
+  const double bvf_numax = 4.0e-4, bvf_numin = 3.0e-5, bvf_nu0 = 1.0e-7, bvf_nu0c = 1.0;
+  for (int k = 1; k <= N - 1; ++k)
+    for (int j = Jstr; j <= Jend; ++j)
+      for (int i = Istr; i <= Iend; ++i) {
+        m.Akv(i, j, k) = c.Akv_bak;
+        if (m.bvf(i, j, k) < 0.0) {
+          m.Akv(i, j, k) = bvf_nu0c;
+          m.Akt[itemp](i, j, k) = bvf_nu0c;
+          if (c.salinity) m.Akt[isalt](i, j, k) = bvf_nu0c;
+        } else if (m.bvf(i, j, k) == 0.0) {
+          m.Akv(i, j, k) = c.Akv_bak;
+          m.Akt[itemp](i, j, k) = c.Akt_bak[itemp];
+          if (c.salinity) m.Akt[isalt](i, j, k) = c.Akt_bak[isalt];
+        } else {
+          const double cff = bvf_nu0 / std::sqrt(m.bvf(i, j, k));
+          m.Akt[itemp](i, j, k) = std::min(bvf_numax, std::max(bvf_numin, cff));
+          m.Akv(i, j, k) = m.Akt[itemp](i, j, k);
+          if (c.salinity) m.Akt[isalt](i, j, k) = m.Akt[itemp](i, j, k);
+        }
+      }
+  exchange_w3d(m, b, m.Akv);
+  for (int it = 0; it < (c.salinity ? 2 : 1); ++it) exchange_w3d(m, b, m.Akt[it]);
+}
+
 // point functions for the known-answer tests (tests/test_oracle_cpu.py)
 void physics_point(int which, const double* in, double* out) {
   if (which == 0) { out[0] = bulk_psiu(in[0]); out[1] = bulk_psit(in[0]); }                                 // stability functions at Z/L

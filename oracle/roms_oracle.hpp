@@ -156,6 +156,7 @@ struct Cfg {
   int lmd_nonlocal = 0;           // LMD_NONLOCAL: KPP nonlocal transport in pre_step3d (:850-865)
   // the forcing / mixing physics of the shipped BENCHMARK set (physics.cpp)
   int bulk_fluxes = 0;            // BULK_FLUXES: bulk_flux computes stflux(itemp), sustr, svstr from the atmosphere (main3d.F:384-390)
+  int bvf_mixing = 0;             // BVF_MIXING: Akv, Akt from the Brunt-Vaisala frequency (bvf_mix.F; needs bv_frequency; main3d.F:468-469)
   int lmd_mixing = 0;             // LMD_MIXING (+LMD_RIMIX, LMD_CONVEC, LMD_SKPP, LMD_NONLOCAL, RI_SPLINES): lmd_vmix (main3d.F:467)
   double blk_ZQ = 10.0, blk_ZT = 10.0, blk_ZW = 10.0;   // roms_benchmark1.in BLK_ZQ, BLK_ZT, BLK_ZW
   int nAVG = 0, ntsAVG = 1;       // AVERAGES: window length in steps (0: off) and starting step (roms_*.in NAVG, NTSAVG)
@@ -230,6 +231,7 @@ void initialize(Model& m);                    // initial.F call order
 void set_avg(Model& m, const Bnd& b);         // ROMS/Nonlinear/set_avg.F
 void ana_atmosphere(Model& m, const Bnd& b);  // set_data.F:197-394 -> ana_cloud/tair/humid/srflux/winds/rain/pair (BENCHMARK)
 void bulk_flux(Model& m, const Bnd& b);       // ROMS/Nonlinear/bulk_flux.F
+void bvf_mix(Model& m, const Bnd& b);         // ROMS/Nonlinear/bvf_mix.F
 void lmd_vmix(Model& m, const Bnd& b);        // ROMS/Nonlinear/lmd_vmix.F, lmd_skpp.F, lmd_swfrac.F
 void physics_point(int which, const double* in, double* out);   // bulk_psiu/psit, lmd_swfrac, KPP velocity scales at a point
 void lmd_vmix_bc(Model& m, const Bnd& b);     // ... its closing bc_w3d / exchange (second stage, see physics.cpp)
@@ -281,7 +283,7 @@ enum Phase {
   PH_SET_MASSFLUX = 1, PH_RHO_EOS = 2, PH_SET_VBC = 3, PH_ANA_VMIX = 4, PH_OMEGA = 5, PH_WVELOCITY = 6, PH_SET_ZETA = 7,
   PH_PRE_STEP3D = 8, PH_PRSGRD = 9, PH_T3DMIX = 10, PH_RHS3D = 11, PH_UV3DMIX = 12, PH_STEP2D = 13, PH_SET_DEPTH = 14,
   PH_STEP3D_UV = 15, PH_OMEGA2 = 16, PH_STEP3D_T = 17, PH_DIAG = 18, PH_SET_DATA = 19, PH_STEP2D_LOOP = 20, PH_INI = 21, PH_SET_AVG = 22,
-  PH_BULK_FLUX = 23, PH_LMD_VMIX = 24
+  PH_BULK_FLUX = 23, PH_LMD_VMIX = 24, PH_BVF_MIX = 25
 };
 void run_phase(Model& m, int phase, int nthreads);
 void main3d_step(Model& m, int nthreads);    // one baroclinic step (main3d.F:189-917)

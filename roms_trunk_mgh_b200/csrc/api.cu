@@ -187,6 +187,9 @@ std::vector<std::string> halo_fields(roms_b200_state* h, int phase) {
     case ROMS_B200_BULK_FLUX:                                                       // bulk_flux.F:949-960
       if (h->cfg.bulk_fluxes) v = {"lrflx", "lhflx", "shflx", "stflux_" + std::to_string(h->cfg.itemp - 1), "sustr", "svstr"};
       break;
+    case ROMS_B200_BVF_MIX:                                                         // bvf_mix.F:133-160
+      if (h->cfg.bvf_mixing) { v = {"Akv"}; for (int it = 0; it < (h->cfg.salinity ? 2 : 1); ++it) v.push_back("Akt_" + std::to_string(it)); }
+      break;
     case ROMS_B200_LMD_VMIX:                                                        // lmd_skpp.F:641-647, lmd_vmix.F:644-655
       if (h->cfg.lmd_mixing) { v = {"hsbl", "Akv"}; for (int it = 0; it < (h->cfg.salinity ? 2 : 1); ++it) v.push_back("Akt_" + std::to_string(it)); }
       break;
@@ -406,6 +409,10 @@ int run_phase_async(roms_b200_state* h, int phase) {
         if (h->halo) rc = halo_exchange(h, halo_fields(h, phase), h->stream);
       }
       h->launches += 2; break;
+    case ROMS_B200_BVF_MIX:
+      if (!h->cfg.bvf_mixing) return ConfigError;
+      rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_bvf_mix(q, f, st); });
+      h->launches += 1; break;
     case ROMS_B200_LMD_VMIX:
       if (!h->cfg.lmd_mixing) return ConfigError;
       rc = launch_with_halo(h, phase, [&](const Par& q, cudaStream_t st) { launch_lmd_vmix(q, f, st); });
@@ -517,7 +524,10 @@ int step_phases_body(roms_b200_state* h, bool with_diag) {
   }
   if (h->cfg.bulk_fluxes) { int rc = run_phase_async(h, ROMS_B200_BULK_FLUX); if (rc) return rc; }      // main3d.F:384-390
   { int rc = run_phase_async(h, ROMS_B200_SET_VBC); if (rc) return rc; }
-  { int rc = run_phase_async(h, h->cfg.lmd_mixing && !h->cfg.ana_vmix ? ROMS_B200_LMD_VMIX : ROMS_B200_ANA_VMIX); if (rc) return rc; }   // :464-470
+  {                                                                                  // :464-470: ANA_VMIX, else LMD_MIXING, else BVF_MIXING
+    const int ph = h->cfg.ana_vmix ? ROMS_B200_ANA_VMIX : h->cfg.lmd_mixing ? ROMS_B200_LMD_VMIX : h->cfg.bvf_mixing ? ROMS_B200_BVF_MIX : ROMS_B200_ANA_VMIX;
+    int rc = run_phase_async(h, ph); if (rc) return rc;
+  }
   { int rc = run_phase_async(h, ROMS_B200_OMEGA); if (rc) return rc; }
   if (h->cfg.wvelocity_every_step) { int rc = run_phase_async(h, ROMS_B200_WVELOCITY); if (rc) return rc; }
   static const int seq3[] = {ROMS_B200_SET_ZETA,  ROMS_B200_SET_AVG, ROMS_B200_PRE_STEP3D, ROMS_B200_PRSGRD,    ROMS_B200_T3DMIX,   ROMS_B200_RHS3D, ROMS_B200_UV3DMIX,
@@ -678,6 +688,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   if (cfg->uv_qdrag < 0 || cfg->uv_qdrag > 2) return ConfigError;
   // lmd_skpp reads bvf, alpha / beta, srflx and writes ghats: the switches that provide those arrays must be on with it
   if (cfg->lmd_mixing && !(cfg->bv_frequency && cfg->eos_tderivative && cfg->solar_source && cfg->lmd_nonlocal)) return ConfigError;
+  if (cfg->bvf_mixing && !cfg->bv_frequency) return ConfigError;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
     std::fprintf(stderr, "roms_b200: no CUDA device; this library has no CPU fallback\n");

@@ -155,6 +155,7 @@ const RoutineArgs kRoutineArgs[] = {
     {ROMS_B200_BULK_FLUX, "t1_*,t2_*,Uwind,Vwind,Tair,Pair,Hair,rain,cloud,srflx", "lrflx,lhflx,shflx,stflux_*,sustr,svstr"},
     {ROMS_B200_LMD_VMIX, "f,Hz,z_w,u1,u2,v1,v2,pden,bvf,alpha,beta,srflx,Jwtype,stflx_*,sustr,svstr,bustr,bvstr,hsbl,Akv,Akt_*",
      "Akv,Akt_*,ghats_*,hsbl,ksbl"},
+    {ROMS_B200_BVF_MIX, "bvf", "Akv,Akt_*"},
 };
 }  // namespace
 

@@ -386,6 +386,29 @@ __global__ void __launch_bounds__(256) k_ana_vmix(Par p, Flds f) {
   if (p.salinity && p.NT >= 2) st_w(f.Akt[p.isalt - 1], o, i, p.Akt_bak[p.isalt - 1], p);
 }
 
+// bvf_mix_tile (ROMS/Nonlinear/bvf_mix.F:92-127; constants mod_scalars.F:1793-1796) + periodic images (:133-143)
+__global__ void __launch_bounds__(256) k_bvf_mix(Par p, Flds f) {
+  const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
+  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = 1 + blockIdx.z;
+  if (i > p.Iend || j > p.Mm) return;
+  const int o = j * p.P + k * p.PL;
+  const double bvf_numax = 4.0e-4, bvf_numin = 3.0e-5, bvf_nu0 = 1.0e-7, bvf_nu0c = 1.0;
+  const double bv = f.bvf[o + i];
+  const int it = p.itemp - 1, is = p.isalt - 1;
+  double av, at, as;
+  if (bv < 0.0) { av = bvf_nu0c; at = bvf_nu0c; as = bvf_nu0c; }
+  else if (bv == 0.0) { av = p.Akv_bak; at = p.Akt_bak[it]; as = p.salinity ? p.Akt_bak[is] : 0.0; }
+  else {
+    const double cff = bvf_nu0 / sqrt(bv);
+    at = dmin(bvf_numax, dmax(bvf_numin, cff));
+    av = at; as = at;
+  }
+  st_w(f.Akv, o, i, av, p);
+  st_w(f.Akt[it], o, i, at, p);
+  if (p.salinity && p.NT >= 2) st_w(f.Akt[is], o, i, as, p);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // set_avg_tile (ROMS/Nonlinear/set_avg.F:237-2600, AVERAGES) for the state variables of the chain: the window's first call
 // copies (:280-426), the others add (:1308-1454), and the call that closes the window scales the sums by 1/nAVG and refreshes
@@ -442,6 +465,7 @@ void launch_set_avg(const Par& p, const Flds& f, int mode, int norm, double fac,
 }
 void launch_set_zeta(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_zeta<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
 void launch_set_depth(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_depth<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
+void launch_bvf_mix(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_bvf_mix<<<g2(p, b, p.Mm, p.N - 1), b, 0, s>>>(p, f); }
 void launch_ana_vmix(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_ana_vmix<<<g2(p, b, p.Mm + 2, p.N - 1), b, 0, s>>>(p, f); }
 
 }  // namespace rb

@@ -11,6 +11,7 @@ void launch_wvelocity(const Par& p, const Flds& f, int Ninp, cudaStream_t s);
 void launch_set_zeta(const Par& p, const Flds& f, cudaStream_t s);
 void launch_set_depth(const Par& p, const Flds& f, cudaStream_t s);
 void launch_ana_vmix(const Par& p, const Flds& f, cudaStream_t s);
+void launch_bvf_mix(const Par& p, const Flds& f, cudaStream_t s);         // bvf_mix.F
 void launch_bulk_flux(const Par& p, const Flds& f, cudaStream_t s);       // bulk_flux.F (whole tile only: not split-launch aware)
 void launch_lmd_vmix(const Par& p, const Flds& f, cudaStream_t s);        // lmd_vmix.F + lmd_skpp.F (split-launch aware)
 void launch_pre_step3d_t(const Par& p, const Flds& f, cudaStream_t s);    // tracer predictor (halo-exchanged: split-launch aware)

@@ -181,6 +181,7 @@ class Tile:
     def ana_vmix(self): self.run_phase("ana_vmix")
     def bulk_flux(self): self.run_phase("bulk_flux")
     def lmd_vmix(self): self.run_phase("lmd_vmix")
+    def bvf_mix(self): self.run_phase("bvf_mix")
     def omega(self): self.run_phase("omega")
     def wvelocity(self): self.run_phase("wvelocity")
     def set_zeta(self): self.run_phase("set_zeta")

@@ -138,6 +138,7 @@ static int main3d_by_routine(void) {
   CHECK(routine(ROMS_B200_SET_VBC));                                       /* :429 */
   if (cfg.ana_vmix) CHECK(routine(ROMS_B200_ANA_VMIX));                    /* :464-470 */
   else if (cfg.lmd_mixing) CHECK(routine(ROMS_B200_LMD_VMIX));
+  else if (cfg.bvf_mixing) CHECK(routine(ROMS_B200_BVF_MIX));
   CHECK(routine(ROMS_B200_OMEGA));                                         /* :474 */
   if (cfg.wvelocity_every_step) CHECK(routine(ROMS_B200_WVELOCITY));
   CHECK(routine(ROMS_B200_SET_ZETA));                                      /* :531 */
@@ -198,7 +199,7 @@ static void print_layout(void) {
   OFFC(rho0); OFFC(g); OFFC(R0); OFFC(T0); OFFC(S0); OFFC(Tcoef); OFFC(Scoef); OFFC(Akt_bak); OFFC(Akv_bak); OFFC(gamma2); OFFC(lambda);
   OFFC(hc); OFFC(itemp); OFFC(isalt); OFFC(device);
   OFFC(bv_frequency); OFFC(eos_tderivative); OFFC(solar_source); OFFC(lmd_nonlocal);
-  OFFC(bulk_fluxes); OFFC(lmd_mixing); OFFC(blk_ZQ); OFFC(blk_ZT); OFFC(blk_ZW);
+  OFFC(bulk_fluxes); OFFC(lmd_mixing); OFFC(blk_ZQ); OFFC(blk_ZT); OFFC(blk_ZW); OFFC(bvf_mixing);
   OFFT(cfg); OFFT(iic); OFFT(ntfirst); OFFT(nstp); OFFT(nnew); OFFT(nrhs); OFFT(iif); OFFT(kstp); OFFT(krhs); OFFT(knew); OFFT(predictor);
 }
 

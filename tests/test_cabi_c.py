@@ -74,7 +74,7 @@ def test_fortran_shim_is_consistent_with_the_header():
     # the by-name vocabulary of b200_loc covers every field name the routines ask for
     cases = set(re.findall(r"CASE \('(\w+)'\)", src))
     L = _lib.load(True)
-    for ph in list(range(1, 18)) + [23, 24]:
+    for ph in list(range(1, 18)) + [23, 24, 25]:
         spec = L.roms_b200_routine_args(ph)
         if not spec:
             continue

@@ -53,6 +53,25 @@ def test_native_library_is_loaded():
     assert "libroms_b200.so" in maps and "libroms_b200_strict.so" in maps
 
 
+def test_bvf_mixing_bit_exact():
+    """BVF_MIXING (bvf_mix.F; main3d.F:468-469): vertical mixing coefficients from the Brunt-Vaisala frequency rho_eos returns.
+    Only + - * / sqrt: bit-exact with the strict library, phase by phase and over 6 steps; by name through the routine form too."""
+    kw = dict(Lm=64, Mm=32, N=10, bv_frequency=1, bvf_mixing=1)
+    o, t = make_pair(orc.APP_BENCHMARK, strict=True, spinup=2, **kw)
+    begin_step(o, t)
+    for ph in ("set_massflux", "rho_eos", "set_vbc", "bvf_mix"):
+        o.run_phase(ph); t.run_phase(ph)
+    for n in ("bvf", "Akv", "Akt_0", "Akt_1"):
+        assert np.array_equal(o.field(n), t.get(n)), n
+    a = o.field("Akt_0")[1:10, 1:-1, 3:-3]
+    assert a.min() >= 3.0e-5 and a.max() <= 4.0e-4 and a.max() > a.min()        # the clipped 1/N law is live
+    o2, t2 = make_pair(orc.APP_BENCHMARK, strict=True, **kw)
+    for _ in range(6):
+        o2.step(1); t2.main3d(1)
+    assert not compare(o2, t2, all_names(2) + ["bvf"], exact=True)
+    t.close(); t2.close()
+
+
 def test_uv_logdrag():
     """UV_LOGDRAG (set_vbc.F:541-586): the drag coefficient is vonKar^2 / log(dz/ZoBot)^2 clipped to [Cdb_min, Cdb_max]; the device
     log() differs from glibc's in the last bit, so bustr / bvstr are held to 1e-14 and the state after 6 steps to 1e-12."""
