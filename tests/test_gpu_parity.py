@@ -608,6 +608,31 @@ def test_full_benchmark_cpp_set_at_full_size():
     t.close()
 
 
+def test_full_benchmark_cpp_set_long_run_properties():
+    """BENCHMARK1 (512x64x30) with the shipped cpp set for 600 steps (25 model hours: the sun sets and rises over part of the
+    channel): the step must stay finite and within the reference's blow-up limits, conserve volume, keep the boundary layer
+    inside the water column and salinity constant (no freshwater flux), and develop the wind-driven flow."""
+    t = synth.make_tile(synth.APP_BENCHMARK, 512, 64, 30, **synth.FULL_BENCHMARK)
+    g, b = t.synth["grid"], t.synth["bounds"]
+    d0 = t.diag()
+    for s in range(12):
+        atm = {n: synth.tile_slice(v, 512, b) for n, v in synth.atmosphere_at(g, t.cfg, t.indices()["time"] / 86400.0).items()}
+        for n in ("srflx",):
+            t.set(n, atm[n])                                   # the shortwave flux of this model time, refreshed every 50 steps
+        t.main3d(50)
+    d1 = t.diag()
+    assert t.indices()["exit_flag"] == 0 and t.indices()["iic"] == 601
+    assert np.isfinite(d1["avgke"]) and d1["avgke"] > 10.0 * max(d0["avgke"], 1e-12) and d1["max_speed"] < 2.0
+    assert abs(d1["volume"] - d0["volume"]) <= 1e-11 * d0["volume"]
+    hs, zw = t.get("hsbl")[0, 1:-1, 3:-3], t.get("z_w")[:, 1:-1, 3:-3]
+    assert np.all(hs <= zw[30] + 1e-2) and np.all(hs >= zw[0] - 1e-2) and hs.min() < -20.0
+    for n in ("Akv", "Akt_0", "u1", "t1_0"):
+        assert np.all(np.isfinite(t.get(n))), n
+    assert np.max(np.abs(t.get("t1_1")[:, 1:-1, 3:-3] - 35.0)) < 1e-9
+    assert t.get("Akv").max() > 1e-2
+    t.close()
+
+
 def test_full_size_benchmark3_smoke():
     """BENCHMARK3 (2048x256x30), the bench workload: runs, conserves volume, stays finite, images consistent."""
     t = synth.make_tile(synth.APP_BENCHMARK, 2048, 256, 30)
