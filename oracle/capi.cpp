@@ -59,6 +59,7 @@ bool lookup(Model& m, const std::string& name, double** p, int dims[6]) {
   if ((it = trc("avgt_")) >= 0) return set3(m.avgt[it]);
   if ((it = trc("ghats_")) >= 0) return set3(m.ghats[it]);
   if ((it = trc("diff2_")) >= 0) return set2(m.diff2[it]);
+  if ((it = trc("diff4_")) >= 0) return set2(m.diff4[it]);
   if ((it = trc("stflx_")) >= 0) return set2(m.stflx[it]);
   if ((it = trc("btflx_")) >= 0) return set2(m.btflx[it]);
   if ((it = trc("stflux_")) >= 0) return set2(m.stflux[it]);
@@ -92,6 +93,8 @@ int orc_set_option(void* hp, const char* key, double val) {
   else if (k == "solar_source") c.solar_source = (int)val; else if (k == "lmd_nonlocal") c.lmd_nonlocal = (int)val;
   else if (k == "nAVG") c.nAVG = (int)val; else if (k == "ntsAVG") c.ntsAVG = (int)val;
   else if (k == "bvf_mixing") c.bvf_mixing = (int)val;
+  else if (k == "uv_adv") c.uv_adv = (int)val; else if (k == "ts_dif4") c.ts_dif4 = (int)val;
+  else if (k == "tnu4") { c.tnu4[0] = c.tnu4[1] = val; }
   else if (k == "bulk_fluxes") c.bulk_fluxes = (int)val; else if (k == "lmd_mixing") c.lmd_mixing = (int)val;
   else return 1;
   return 0;
@@ -109,7 +112,8 @@ double orc_get_option(void* hp, const char* key) {
   if (k == "nfast") return m.nfast; if (k == "dtfast") return m.dtfast; if (k == "hc") return m.hc; if (k == "wvelocity_every_step") return c.wvelocity_every_step;
   if (k == "bv_frequency") return c.bv_frequency; if (k == "eos_tderivative") return c.eos_tderivative;
   if (k == "solar_source") return c.solar_source; if (k == "lmd_nonlocal") return c.lmd_nonlocal;
-  if (k == "bvf_mixing") return c.bvf_mixing;
+  if (k == "bvf_mixing") return c.bvf_mixing; if (k == "itemp") return c.itemp; if (k == "isalt") return c.isalt;
+  if (k == "uv_adv") return c.uv_adv; if (k == "ts_dif4") return c.ts_dif4; if (k == "tnu4") return c.tnu4[0];
   if (k == "bulk_fluxes") return c.bulk_fluxes; if (k == "lmd_mixing") return c.lmd_mixing;
   if (k == "blk_ZQ") return c.blk_ZQ; if (k == "blk_ZT") return c.blk_ZT; if (k == "blk_ZW") return c.blk_ZW;
   if (k == "app") return c.app; if (k == "nAVG") return c.nAVG; if (k == "ntsAVG") return c.ntsAVG;

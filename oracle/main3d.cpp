@@ -159,7 +159,7 @@ void run_phase(Model& m, int phase, int nthreads) {
     case PH_SET_AVG: for_tiles(m, nthreads, [&](const Bnd& b) { set_avg(m, b); }); break;
     case PH_PRE_STEP3D: for_tiles(m, nthreads, [&](const Bnd& b) { pre_step3d(m, b); }); break;
     case PH_PRSGRD: for_tiles(m, nthreads, [&](const Bnd& b) { prsgrd(m, b); }); break;
-    case PH_T3DMIX: for_tiles(m, nthreads, [&](const Bnd& b) { t3dmix2(m, b); }); break;
+    case PH_T3DMIX: for_tiles(m, nthreads, [&](const Bnd& b) { t3dmix2(m, b); if (m.c.ts_dif4) t3dmix4(m, b); }); break;   // rhs3d.F:81-97
     case PH_RHS3D: for_tiles(m, nthreads, [&](const Bnd& b) { rhs3d(m, b); }); break;
     case PH_UV3DMIX: for_tiles(m, nthreads, [&](const Bnd& b) { uv3dmix2(m, b); }); break;
     case PH_STEP2D: for_tiles(m, nthreads, [&](const Bnd& b) { step2d(m, b); }); break;
@@ -198,7 +198,7 @@ void main3d_step(Model& m, int nthreads) {
   });
   for_tiles(m, nthreads, [&](const Bnd& b) { set_zeta(m, b); set_avg(m, b); });      // :489-495
   for_tiles(m, nthreads, [&](const Bnd& b) {                                         // :563 -> rhs3d.F:74-159
-    pre_step3d(m, b); prsgrd(m, b); t3dmix2(m, b); rhs3d(m, b); uv3dmix2(m, b);
+    pre_step3d(m, b); prsgrd(m, b); t3dmix2(m, b); if (m.c.ts_dif4) t3dmix4(m, b); rhs3d(m, b); uv3dmix2(m, b);
   });
   step2d_loop(m, nthreads);                                                          // :592-700
   run_phase(m, PH_SET_DEPTH, nthreads);                                              // :736

@@ -1,6 +1,6 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see roms_oracle.hpp).
 // Harmonic horizontal mixing: ROMS/Nonlinear/t3dmix2_s.h:198-301, t3dmix2_geo.h:219-419 (dispatch t3dmix.F),
-// ROMS/Nonlinear/uv3dmix2_s.h:239-330 (dispatch uv3dmix.F).
+// ROMS/Nonlinear/uv3dmix2_s.h:239-330 (dispatch uv3dmix.F); biharmonic tracer mixing along s-surfaces t3dmix4_s.h:215-476.
 #include "roms_oracle.hpp"
 
 namespace orc {
@@ -113,6 +113,62 @@ static void t3dmix2_geo(Model& m, const Bnd& b) {
       }
     }
   }
+}
+
+// t3dmix4_s_tile (ROMS/Nonlinear/t3dmix4_s.h:215-476; TS_DIF4 + MIX_S_TS; diff4 = SQRT(ABS(tnu4)), read_phypar.F:6905): the
+// harmonic operator applied twice.  EW periodic, NS closed walls (LapT = 0 outside a closed wall, :352-376).
+static void t3dmix4_s(Model& m, const Bnd& b) {
+  const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
+  const int N = c.N; const double dt = c.dt;
+  F3& Hz = m.Hz; F2 &pm = m.pm, &pn = m.pn;
+  S2 FE(IminS, ImaxS, JminS, JmaxS), FX(IminS, ImaxS, JminS, JmaxS), LapT(IminS, ImaxS, JminS, JmaxS);
+  const int Imin = Istr - 1, Imax = Iend + 1;                                   // :221-227 (EWperiodic)
+  const int Jmin = std::max(Jstr - 1, 1), Jmax = std::min(Jend + 1, c.Mm);      // :228-234
+  for (int itrc = 0; itrc < c.NT; ++itrc) {
+    F3 tr = m.t[m.nrhs][itrc], tn = m.t[m.nnew][itrc]; F2 diff4 = m.diff4[itrc];
+    for (int k = 1; k <= N; ++k) {
+      for (int j = Jmin; j <= Jmax; ++j)                                        // :243-291
+        for (int i = Imin; i <= Imax + 1; ++i) {
+          double cff = 0.25 * (diff4(i, j) + diff4(i - 1, j)) * m.pmon_u(i, j);
+          FX(i, j) = cff * (Hz(i, j, k) + Hz(i - 1, j, k)) * (tr(i, j, k) - tr(i - 1, j, k));
+        }
+      for (int j = Jmin; j <= Jmax + 1; ++j)                                    // :292-340
+        for (int i = Imin; i <= Imax; ++i) {
+          double cff = 0.25 * (diff4(i, j) + diff4(i, j - 1)) * m.pnom_v(i, j);
+          FE(i, j) = cff * (Hz(i, j, k) + Hz(i, j - 1, k)) * (tr(i, j, k) - tr(i, j - 1, k));
+        }
+      for (int j = Jmin; j <= Jmax; ++j)                                        // :341-348
+        for (int i = Imin; i <= Imax; ++i) {
+          double cff = 1.0 / Hz(i, j, k);
+          LapT(i, j) = pm(i, j) * pn(i, j) * cff * (FX(i + 1, j) - FX(i, j) + FE(i, j + 1) - FE(i, j));
+        }
+      if (b.Southern_Edge) for (int i = Imin; i <= Imax; ++i) LapT(i, Jstr - 1) = 0.0;   // :378-390 (closed)
+      if (b.Northern_Edge) for (int i = Imin; i <= Imax; ++i) LapT(i, Jend + 1) = 0.0;   // :392-404
+      for (int j = Jstr; j <= Jend; ++j)                                        // :410-435
+        for (int i = Istr; i <= Iend + 1; ++i) {
+          double cff = 0.25 * (diff4(i, j) + diff4(i - 1, j)) * m.pmon_u(i, j);
+          FX(i, j) = cff * (Hz(i, j, k) + Hz(i - 1, j, k)) * (LapT(i, j) - LapT(i - 1, j));
+        }
+      for (int j = Jstr; j <= Jend + 1; ++j)                                    // :436-461
+        for (int i = Istr; i <= Iend; ++i) {
+          double cff = 0.25 * (diff4(i, j) + diff4(i, j - 1)) * m.pnom_v(i, j);
+          FE(i, j) = cff * (Hz(i, j, k) + Hz(i, j - 1, k)) * (LapT(i, j) - LapT(i, j - 1));
+        }
+      for (int j = Jstr; j <= Jend; ++j)                                        // :465-471
+        for (int i = Istr; i <= Iend; ++i) {
+          double cff = dt * pm(i, j) * pn(i, j);
+          double cff1 = cff * (FX(i + 1, j) - FX(i, j));
+          double cff2 = cff * (FE(i, j + 1) - FE(i, j));
+          double cff3 = cff1 + cff2;
+          tn(i, j, k) = tn(i, j, k) - cff3;
+        }
+    }
+  }
+}
+
+void t3dmix4(Model& m, const Bnd& b) {
+  if (m.c.mix_geo_ts) { std::fprintf(stderr, "oracle: t3dmix4_geo.h is not restated (TS_DIF4 needs MIX_S_TS)\n"); std::abort(); }
+  t3dmix4_s(m, b);
 }
 
 void t3dmix2(Model& m, const Bnd& b) {

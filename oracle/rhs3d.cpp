@@ -1,7 +1,8 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see roms_oracle.hpp).
 // ROMS/Nonlinear/rhs3d.F:174-1671 (rhs3d_tile): Coriolis :473-507, curvilinear :515-564, third-order upstream
 // horizontal advection (default branch) :658-983, fourth-order centred vertical advection :1177-1265 / :1434-1522,
-// column sums -> rufrc,rvfrc :1534-1667.
+// column sums -> rufrc,rvfrc :1534-1667.  uv_adv = 1 (UV_C4ADVECTION): fourth-order centred horizontal fluxes :685-705,
+// :761-781, :829-849, :902-921 and the 9/32, 1/32 vertical flux :1108-1175 / :1362-1429.
 #include "roms_oracle.hpp"
 
 namespace orc {
@@ -10,6 +11,7 @@ void rhs3d(Model& m, const Bnd& b) {
   const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
   const int N = c.N;
   const double Gadv = -0.25;                                         // rhs3d.F:299
+  const bool c4 = (c.uv_adv == 1);                                   // UV_C4ADVECTION
   F3 &Hz = m.Hz, &Huon = m.Huon, &Hvom = m.Hvom, &W = m.W;
   F3 u = m.u[m.nrhs], v = m.v[m.nrhs], ru = m.ru[m.nrhs], rv = m.rv[m.nrhs];
   SK FC(IminS, ImaxS, 0, N);
@@ -53,6 +55,13 @@ void rhs3d(Model& m, const Bnd& b) {
         Huxx(i, j) = Huon(i - 1, j, k) - 2.0 * Huon(i, j, k) + Huon(i + 1, j, k);
       }
     // (:669-684 closed E/W wall copies: not live, EW periodic)
+    if (c4) {                                                                                         // :685-705
+      const double cff = 1.0 / 6.0;
+      for (int j = Jstr; j <= Jend; ++j)
+        for (int i = IstrU - 1; i <= Iend; ++i)
+          UFx(i, j) = 0.25 * (u(i, j, k) + u(i + 1, j, k) - cff * (uxx(i, j) + uxx(i + 1, j))) *
+                      (Huon(i, j, k) + Huon(i + 1, j, k) - cff * (Huxx(i, j) + Huxx(i + 1, j)));
+    } else
     for (int j = Jstr; j <= Jend; ++j)
       for (int i = IstrU - 1; i <= Iend; ++i) {
         double cff1 = u(i, j, k) + u(i + 1, j, k);
@@ -65,6 +74,13 @@ void rhs3d(Model& m, const Bnd& b) {
     if (b.Northern_Edge) for (int i = IstrU; i <= Iend; ++i) uee(i, Jend + 1) = uee(i, Jend);     // :749-755
     for (int j = Jstr; j <= Jend + 1; ++j)
       for (int i = IstrU - 1; i <= Iend; ++i) Hvxx(i, j) = Hvom(i - 1, j, k) - 2.0 * Hvom(i, j, k) + Hvom(i + 1, j, k);
+    if (c4) {                                                                                         // :761-781
+      const double cff = 1.0 / 6.0;
+      for (int j = Jstr; j <= Jend + 1; ++j)
+        for (int i = IstrU; i <= Iend; ++i)
+          UFe(i, j) = 0.25 * (u(i, j, k) + u(i, j - 1, k) - cff * (uee(i, j) + uee(i, j - 1))) *
+                      (Hvom(i, j, k) + Hvom(i - 1, j, k) - cff * (Hvxx(i, j) + Hvxx(i - 1, j)));
+    } else
     for (int j = Jstr; j <= Jend + 1; ++j)
       for (int i = IstrU; i <= Iend; ++i) {
         double cff1 = u(i, j, k) + u(i, j - 1, k);
@@ -76,6 +92,13 @@ void rhs3d(Model& m, const Bnd& b) {
       for (int i = Istrm1; i <= Iendp1; ++i) vxx(i, j) = v(i - 1, j, k) - 2.0 * v(i, j, k) + v(i + 1, j, k);
     for (int j = JstrV - 1; j <= Jend; ++j)
       for (int i = Istr; i <= Iend + 1; ++i) Huee(i, j) = Huon(i, j - 1, k) - 2.0 * Huon(i, j, k) + Huon(i, j + 1, k);
+    if (c4) {                                                                                         // :829-849
+      const double cff = 1.0 / 6.0;
+      for (int j = JstrV; j <= Jend; ++j)
+        for (int i = Istr; i <= Iend + 1; ++i)
+          VFx(i, j) = 0.25 * (v(i, j, k) + v(i - 1, j, k) - cff * (vxx(i, j) + vxx(i - 1, j))) *
+                      (Huon(i, j, k) + Huon(i, j - 1, k) - cff * (Huee(i, j) + Huee(i, j - 1)));
+    } else
     for (int j = JstrV; j <= Jend; ++j)
       for (int i = Istr; i <= Iend + 1; ++i) {
         double cff1 = v(i, j, k) + v(i - 1, j, k);
@@ -90,6 +113,13 @@ void rhs3d(Model& m, const Bnd& b) {
       }
     if (b.Southern_Edge) for (int i = Istr; i <= Iend; ++i) { vee(i, Jstr) = vee(i, Jstr + 1); Hvee(i, Jstr) = Hvee(i, Jstr + 1); }   // :886-893
     if (b.Northern_Edge) for (int i = Istr; i <= Iend; ++i) { vee(i, Jend + 1) = vee(i, Jend); Hvee(i, Jend + 1) = Hvee(i, Jend); }   // :894-901
+    if (c4) {                                                                                         // :902-921
+      const double cff = 1.0 / 6.0;
+      for (int j = JstrV - 1; j <= Jend; ++j)
+        for (int i = Istr; i <= Iend; ++i)
+          VFe(i, j) = 0.25 * (v(i, j, k) + v(i, j + 1, k) - cff * (vee(i, j) + vee(i, j + 1))) *
+                      (Hvom(i, j, k) + Hvom(i, j + 1, k) - cff * (Hvee(i, j) + Hvee(i, j + 1)));
+    } else
     for (int j = JstrV - 1; j <= Jend; ++j)
       for (int i = Istr; i <= Iend; ++i) {
         double cff1 = v(i, j, k) + v(i, j + 1, k);
@@ -114,7 +144,20 @@ void rhs3d(Model& m, const Bnd& b) {
 
   // ---- vertical advection + column sums
   for (int j = Jstr; j <= Jend; ++j) {
-    {
+    if (c4) {                                                                                         // :1108-1175
+      const double cff1 = 9.0 / 32.0, cff2 = 1.0 / 32.0;
+      for (int k = 2; k <= N - 2; ++k)
+        for (int i = IstrU; i <= Iend; ++i)
+          FC(i, k) = (cff1 * (u(i, j, k) + u(i, j, k + 1)) - cff2 * (u(i, j, k - 1) + u(i, j, k + 2))) * (W(i, j, k) + W(i - 1, j, k));
+      for (int i = IstrU; i <= Iend; ++i) {
+        FC(i, N) = 0.0;
+        FC(i, N - 1) = (cff1 * (u(i, j, N - 1) + u(i, j, N)) - cff2 * (u(i, j, N - 2) + u(i, j, N))) * (W(i, j, N - 1) + W(i - 1, j, N - 1));
+        FC(i, 1) = (cff1 * (u(i, j, 1) + u(i, j, 2)) - cff2 * (u(i, j, 1) + u(i, j, 3))) * (W(i, j, 1) + W(i - 1, j, 1));
+        FC(i, 0) = 0.0;
+      }
+      for (int k = 1; k <= N; ++k)
+        for (int i = IstrU; i <= Iend; ++i) { double cff = FC(i, k) - FC(i, k - 1); ru(i, j, k) = ru(i, j, k) - cff; }
+    } else {
       const double cff1 = 9.0 / 16.0, cff2 = 1.0 / 16.0;
       for (int k = 2; k <= N - 2; ++k)
         for (int i = IstrU; i <= Iend; ++i)
@@ -131,7 +174,20 @@ void rhs3d(Model& m, const Bnd& b) {
       for (int k = 1; k <= N; ++k)
         for (int i = IstrU; i <= Iend; ++i) { double cff = FC(i, k) - FC(i, k - 1); ru(i, j, k) = ru(i, j, k) - cff; }
     }
-    if (j >= JstrV) {
+    if (j >= JstrV && c4) {                                                                           // :1362-1429
+      const double cff1 = 9.0 / 32.0, cff2 = 1.0 / 32.0;
+      for (int k = 2; k <= N - 2; ++k)
+        for (int i = Istr; i <= Iend; ++i)
+          FC(i, k) = (cff1 * (v(i, j, k) + v(i, j, k + 1)) - cff2 * (v(i, j, k - 1) + v(i, j, k + 2))) * (W(i, j, k) + W(i, j - 1, k));
+      for (int i = Istr; i <= Iend; ++i) {
+        FC(i, N) = 0.0;
+        FC(i, N - 1) = (cff1 * (v(i, j, N - 1) + v(i, j, N)) - cff2 * (v(i, j, N - 2) + v(i, j, N))) * (W(i, j, N - 1) + W(i, j - 1, N - 1));
+        FC(i, 1) = (cff1 * (v(i, j, 1) + v(i, j, 2)) - cff2 * (v(i, j, 1) + v(i, j, 3))) * (W(i, j, 1) + W(i, j - 1, 1));
+        FC(i, 0) = 0.0;
+      }
+      for (int k = 1; k <= N; ++k)
+        for (int i = Istr; i <= Iend; ++i) { double cff = FC(i, k) - FC(i, k - 1); rv(i, j, k) = rv(i, j, k) - cff; }
+    } else if (j >= JstrV) {
       const double cff1 = 9.0 / 16.0, cff2 = 1.0 / 16.0;
       for (int k = 2; k <= N - 2; ++k)
         for (int i = Istr; i <= Iend; ++i)

@@ -137,10 +137,13 @@ struct Cfg {
   int ana_vmix = 0;               // ANA_VMIX (UPWELLING profile)
   int wvelocity_every_step = 1;   // main3d.F:475
   int hadv = HADV_U3, vadv = VADV_C4;
+  int uv_adv = 0;                 // momentum advection: 0 default (U3 horizontal, C4 vertical), 1 UV_C4ADVECTION (rhs3d.F:685-921, :1108-1175)
+  int ts_dif4 = 0;                // TS_DIF4 (+ MIX_S_TS): t3dmix4_s.h after t3dmix2 (rhs3d.F:81-97)
   // physical parameters
   double rho0 = 1025.0, g = 9.81;
   double R0 = 1027.0, T0 = 14.0, S0 = 35.0, Tcoef = 1.7e-4, Scoef = 0.0;
   double tnu2[2] = {0.0, 0.0}; double visc2 = 5.0;
+  double tnu4[2] = {0.0, 0.0};    // TNU4 (m4/s); diff4 holds SQRT(ABS(tnu4)) (read_phypar.F:6905)
   double Akt_bak[2] = {1e-6, 1e-6}; double Akv_bak = 1e-5;
   double rdrg = 3e-4, rdrg2 = 3e-3;
   double gamma2 = 1.0;
@@ -181,7 +184,7 @@ struct Model {
   // ---- 2-D grid (mod_grid.F)
   F2 h, f, pm, pn, om_r, on_r, om_u, on_u, om_v, on_v, om_p, on_p, omn, fomn, pmon_r, pnom_r, pmon_u, pnom_u,
       pmon_v, pnom_v, pmon_p, pnom_p, dndx, dmde, xr, yr, latr, lonr, rdrag, rdrag2, ZoBot;
-  F2 visc2_r, visc2_p; F2 diff2[2];             // mod_mixing.F
+  F2 visc2_r, visc2_p; F2 diff2[2]; F2 diff4[2]; // mod_mixing.F
   // ---- 2-D state (mod_ocean.F, mod_coupling.F, mod_forces.F)
   F2 zeta[4], ubar[4], vbar[4];                 // [1..3]
   F2 rzeta[3], rubar[3], rvbar[3];              // [1..2]
@@ -267,6 +270,7 @@ void set_zeta(Model& m, const Bnd& b);
 void pre_step3d(Model& m, const Bnd& b);
 void prsgrd(Model& m, const Bnd& b);
 void t3dmix2(Model& m, const Bnd& b);
+void t3dmix4(Model& m, const Bnd& b);         // ROMS/Nonlinear/t3dmix4_s.h (TS_DIF4)
 void rhs3d(Model& m, const Bnd& b);       // rhs3d_tile only
 void uv3dmix2(Model& m, const Bnd& b);
 void step2d(Model& m, const Bnd& b);

@@ -146,7 +146,7 @@ void Model::allocate() {
   pool.clear(); pool.reserve(400);
   F2* g2[] = {&h, &f, &pm, &pn, &om_r, &on_r, &om_u, &on_u, &om_v, &on_v, &om_p, &on_p, &omn, &fomn, &pmon_r, &pnom_r,
               &pmon_u, &pnom_u, &pmon_v, &pnom_v, &pmon_p, &pnom_p, &dndx, &dmde, &xr, &yr, &latr, &lonr, &rdrag, &rdrag2, &ZoBot,
-              &visc2_r, &visc2_p, &diff2[0], &diff2[1], &Zt_avg1, &DU_avg1, &DU_avg2, &DV_avg1, &DV_avg2, &rufrc, &rvfrc,
+              &visc2_r, &visc2_p, &diff2[0], &diff2[1], &diff4[0], &diff4[1], &Zt_avg1, &DU_avg1, &DU_avg2, &DV_avg1, &DV_avg2, &rufrc, &rvfrc,
               &rhoA, &rhoS, &sustr, &svstr, &bustr, &bvstr, &stflx[0], &stflx[1], &btflx[0], &btflx[1], &stflux[0], &stflux[1], &btflux[0], &btflux[1]};
   for (F2* p_ : g2) *p_ = new2();
   for (int k = 1; k <= 3; ++k) { zeta[k] = new2(); ubar[k] = new2(); vbar[k] = new2(); }
@@ -395,7 +395,7 @@ void ini_hmixcoef(Model& m, const Bnd& b) {
   for (int j = m.LBj; j <= m.UBj; ++j)
     for (int i = m.LBi; i <= m.UBi; ++i) {
       m.visc2_p(i, j) = m.c.visc2; m.visc2_r(i, j) = m.c.visc2;
-      for (int it = 0; it < m.c.NT; ++it) m.diff2[it](i, j) = m.c.tnu2[it];
+      for (int it = 0; it < m.c.NT; ++it) { m.diff2[it](i, j) = m.c.tnu2[it]; m.diff4[it](i, j) = std::sqrt(std::fabs(m.c.tnu4[it])); }   // :293; read_phypar.F:6905
     }
 }
 

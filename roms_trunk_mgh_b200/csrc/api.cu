@@ -433,10 +433,14 @@ int run_phase_async(roms_b200_state* h, int phase) {
       h->launches += 2; break;
     case ROMS_B200_PRSGRD: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_prsgrd(q, f, h->cfg.dj_gradps, st); }); h->launches += h->cfg.dj_gradps ? 2 : 1; break;
     case ROMS_B200_T3DMIX:
-      if (fused_tmix(h)) break;                                                     // already applied by pre_step3d_t
+      if (fused_tmix(h)) {                                                          // t3dmix2_s already applied by pre_step3d_t
+        if (h->cfg.ts_dif4) { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix4_s(q, f, st); }); h->launches += 1; }
+        break;
+      }
       if (h->cfg.mix_geo_ts) {
         if (!h->all_diff2_zero) { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix2_geo(q, f, st); }); h->launches += 1; }   // diff2 == 0: exact no-op
       } else { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix2_s(q, f, st); }); h->launches += 1; }
+      if (h->cfg.ts_dif4) { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix4_s(q, f, st); }); h->launches += 1; }   // rhs3d.F:90-97
       break;
     case ROMS_B200_RHS3D: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_rhs3d(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_UV3DMIX: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_uv3dmix2(q, f, st); }); h->launches += 1; break;
@@ -689,6 +693,8 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   // lmd_skpp reads bvf, alpha / beta, srflx and writes ghats: the switches that provide those arrays must be on with it
   if (cfg->lmd_mixing && !(cfg->bv_frequency && cfg->eos_tderivative && cfg->solar_source && cfg->lmd_nonlocal)) return ConfigError;
   if (cfg->bvf_mixing && !cfg->bv_frequency) return ConfigError;
+  if (cfg->uv_adv < 0 || cfg->uv_adv > 1) return ConfigError;
+  if (cfg->ts_dif4 && cfg->mix_geo_ts) return ConfigError;                          // t3dmix4_geo.h is not built
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
     std::fprintf(stderr, "roms_b200: no CUDA device; this library has no CPU fallback\n");
@@ -732,7 +738,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   p.nonlin_eos = cfg->nonlin_eos; p.curvgrid = cfg->curvgrid; p.uv_qdrag = cfg->uv_qdrag; p.salinity = cfg->salinity;
   p.hadv = cfg->hadv; p.vadv = cfg->vadv; p.itemp = cfg->itemp; p.isalt = cfg->isalt;
   p.bv_frequency = cfg->bv_frequency; p.eos_tderivative = cfg->eos_tderivative; p.solar_source = cfg->solar_source; p.lmd_nonlocal = cfg->lmd_nonlocal;
-  p.bulk_fluxes = cfg->bulk_fluxes; p.lmd_mixing = cfg->lmd_mixing;
+  p.bulk_fluxes = cfg->bulk_fluxes; p.lmd_mixing = cfg->lmd_mixing; p.uv_adv = cfg->uv_adv; p.pad_ = 0;
   p.blk_ZQ = cfg->blk_ZQ > 0.0 ? cfg->blk_ZQ : 10.0; p.blk_ZT = cfg->blk_ZT > 0.0 ? cfg->blk_ZT : 10.0; p.blk_ZW = cfg->blk_ZW > 0.0 ? cfg->blk_ZW : 10.0;
   p.dt = cfg->dt; p.g = cfg->g; p.rho0 = cfg->rho0; p.R0 = cfg->R0; p.T0 = cfg->T0; p.S0 = cfg->S0; p.Tcoef = cfg->Tcoef; p.Scoef = cfg->Scoef;
   p.gamma2 = cfg->gamma2; p.lambda = cfg->lambda; p.hc = cfg->hc; p.Akv_bak = cfg->Akv_bak;
@@ -774,6 +780,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
     for (int k = 1; k <= 3; ++k) rc |= alloc_field(h, "t" + std::to_string(k) + "_" + s, &f.t[k][it], 1, N);
     rc |= alloc_field(h, "Akt_" + s, &f.Akt[it], 0, N + 1);
     rc |= alloc_field(h, "diff2_" + s, &f.diff2[it], 0, 1);
+    if (cfg->ts_dif4) rc |= alloc_field(h, "diff4_" + s, &f.diff4[it], 0, 1);
     rc |= alloc_field(h, "stflx_" + s, &f.stflx[it], 0, 1);
     rc |= alloc_field(h, "btflx_" + s, &f.btflx[it], 0, 1);
     rc |= alloc_field(h, "stflux_" + s, &f.stflux[it], 0, 1);

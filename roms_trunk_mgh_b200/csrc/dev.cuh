@@ -41,6 +41,8 @@ struct Par {
   double Akv_bak, Akt_bak[MAXNT];
   double w1_m1, w2_0, w2_p1;      // weight(1,iif-1), weight(2,iif), weight(2,iif+1) for the current step2d call
   double blk_ZQ, blk_ZT, blk_ZW;  // heights (m) of the atmospheric humidity / temperature / wind data (bulk_flux.F)
+  int uv_adv;                     // rhs3d momentum advection: 0 default (U3 / C4), 1 UV_C4ADVECTION
+  int pad_;
 };
 
 // Field table (all pointers pre-offset; [0] slots of time-indexed arrays are unused so Fortran indices apply)
@@ -70,6 +72,8 @@ struct Flds {
   double* avgt[MAXNT];
   // 1-D (device)
   double *sc_r, *Cs_r, *sc_w, *Cs_w;
+  // TS_DIF4: MIXING%diff4 = SQRT(ABS(tnu4)) (t3dmix4_s.h)
+  double* diff4[MAXNT];
 };
 
 constexpr int EDGE_W = 64;        // width of the tile edges computed ahead of the halo exchange (multiple of every CTA width)

@@ -455,6 +455,61 @@ __global__ void __launch_bounds__(128) k_t3dmix2_s(Par p, Flds f) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// t3dmix4_s_tile (ROMS/Nonlinear/t3dmix4_s.h:215-476; TS_DIF4 + MIX_S_TS): biharmonic mixing of tracers along s-surfaces, the
+// harmonic operator applied twice with diff4 = SQRT(ABS(tnu4)).  No vertical coupling: one thread per (i,j,k).  The reference
+// keeps LapT in a private 2-D scratch array; here a thread evaluates LapT at its own cell and at its four neighbours (each from
+// that cell's four face fluxes, the expressions of :243-348 verbatim, so the five values are bit-identical to the scratch array's)
+// and applies the second operator (:410-471) in registers: t(nrhs) and Hz are read on a 13-point diamond that the L1 serves, no
+// scratch traffic.  LapT = 0 outside the closed southern / northern walls (:378-404); EW periodic (ghost columns of t(nrhs), Hz).
+__device__ __forceinline__ double lapT4(const Par& p, const Flds& f, const double* __restrict__ tr, const double* __restrict__ d4,
+                                        int i, int j, int ok) {
+  if (j < 1 || j > p.Mm) return 0.0;
+  const int P = p.P, o2 = j * P + i, o = o2 + ok;
+  const double* __restrict__ Hz = f.Hz;
+  const double h0 = Hz[o], t0 = tr[o], d0 = d4[o2];
+  double cff = 0.25 * (d0 + d4[o2 - 1]) * f.pmon_u[o2];
+  const double FX0 = cff * (h0 + Hz[o - 1]) * (t0 - tr[o - 1]);
+  cff = 0.25 * (d4[o2 + 1] + d0) * f.pmon_u[o2 + 1];
+  const double FX1 = cff * (Hz[o + 1] + h0) * (tr[o + 1] - t0);
+  cff = 0.25 * (d0 + d4[o2 - P]) * f.pnom_v[o2];
+  const double FE0 = cff * (h0 + Hz[o - P]) * (t0 - tr[o - P]);
+  cff = 0.25 * (d4[o2 + P] + d0) * f.pnom_v[o2 + P];
+  const double FE1 = cff * (Hz[o + P] + h0) * (tr[o + P] - t0);
+  cff = 1.0 / h0;
+  return f.pm[o2] * f.pn[o2] * cff * (FX1 - FX0 + FE1 - FE0);
+}
+__global__ void __launch_bounds__(128) k_t3dmix4_s(Par p, Flds f) {
+  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = 1 + blockIdx.z;
+  if (i > p.Iend || j > p.Mm) return;
+  const int P = p.P, ok = k * p.PL, o2 = j * P + i, o = o2 + ok;
+  const double* __restrict__ Hz = f.Hz;
+  const double h0 = Hz[o], hW = Hz[o - 1], hE = Hz[o + 1], hS = Hz[o - P], hN = Hz[o + P];
+  const double dtmn = p.dt * f.pm[o2] * f.pn[o2];
+  for (int it = 0; it < p.NT; ++it) {
+    const double* __restrict__ tr = f.t[p.nrhs][it];
+    const double* __restrict__ d4 = f.diff4[it];
+    double* __restrict__ tn = f.t[p.nnew][it];
+    const double L0 = lapT4(p, f, tr, d4, i, j, ok), LW = lapT4(p, f, tr, d4, i - 1, j, ok), LE = lapT4(p, f, tr, d4, i + 1, j, ok);
+    const double LS = lapT4(p, f, tr, d4, i, j - 1, ok), LN = lapT4(p, f, tr, d4, i, j + 1, ok);
+    const double d0 = d4[o2];
+    double cff = 0.25 * (d0 + d4[o2 - 1]) * f.pmon_u[o2];
+    const double FX0 = cff * (h0 + hW) * (L0 - LW);
+    cff = 0.25 * (d4[o2 + 1] + d0) * f.pmon_u[o2 + 1];
+    const double FX1 = cff * (hE + h0) * (LE - L0);
+    cff = 0.25 * (d0 + d4[o2 - P]) * f.pnom_v[o2];
+    const double FE0 = cff * (h0 + hS) * (L0 - LS);
+    cff = 0.25 * (d4[o2 + P] + d0) * f.pnom_v[o2 + P];
+    const double FE1 = cff * (hN + h0) * (LN - L0);
+    const double cff1 = dtmn * (FX1 - FX0);
+    const double cff2 = dtmn * (FE1 - FE0);
+    const double cff3 = cff1 + cff2;
+    tn[o] = tn[o] - cff3;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 static inline dim3 g2(const Par& p, dim3 b, int ni, int nj, int nz = 1) { return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz); }
 
 template <int H, bool SRC>
@@ -497,6 +552,10 @@ void launch_prsgrd(const Par& p, const Flds& f, int dj_gradps, cudaStream_t s) {
     dim3 b(64, 2);
     k_prsgrd31<<<g2(p, b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
   }
+}
+void launch_t3dmix4_s(const Par& p, const Flds& f, cudaStream_t s) {
+  dim3 b(64, 2);
+  k_t3dmix4_s<<<g2(p, b, p.Iend - p.Istr + 1, p.Mm, p.N), b, 0, s>>>(p, f);
 }
 void launch_t3dmix2_s(const Par& p, const Flds& f, cudaStream_t s) {
   dim3 b(64, 2); dim3 g = g2(p, b, p.Iend - p.Istr + 1, p.Mm);

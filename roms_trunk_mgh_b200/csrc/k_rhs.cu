@@ -28,12 +28,15 @@ __device__ __forceinline__ double d2y(const double* __restrict__ A, int o, int P
 #ifndef UVM_PF
 #define UVM_PF 4          // same for k_uv3dmix2
 #endif
+// UADV: 0 the default branch (third-order upstream horizontal :706-730 ..., fourth-order centred vertical :1177-1255); 1
+// UV_C4ADVECTION (fourth-order centred horizontal :685-705, :761-781, :829-849, :902-921; vertical 9/32, 1/32 :1108-1175, :1362-1429).
+template <int UADV>
 __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > p.Iend || j > p.Mm) return;
   const int N = p.N, P = p.P, Mm = p.Mm, o2 = j * P;
-  const double Gadv = -0.25;
+  const double Gadv = -0.25, C6 = 1.0 / 6.0;
   const double* __restrict__ u = f.u[p.nrhs];
   const double* __restrict__ v = f.v[p.nrhs];
   const double* __restrict__ Hz = f.Hz;
@@ -111,24 +114,36 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
       // UFx(i,j) at rho(i,j) and UFx(i-1,j)
       double c1 = u0 + uE;
       double c = (c1 > 0.0) ? uxx0 : uxxE;
-      const double UFx0 = 0.25 * (c1 + Gadv * c) * (Hu0 + HuE + Gadv * 0.5 * (Hxx0 + HxxE));
-      c1 = uW + u0;
-      c = (c1 > 0.0) ? uxxW : uxx0;
-      const double UFxW = 0.25 * (c1 + Gadv * c) * (HuW + Hu0 + Gadv * 0.5 * (HxxW + Hxx0));
+      double UFx0, UFxW;
+      if (UADV == 1) {
+        UFx0 = 0.25 * (u0 + uE - C6 * (uxx0 + uxxE)) * (Hu0 + HuE - C6 * (Hxx0 + HxxE));
+        UFxW = 0.25 * (uW + u0 - C6 * (uxxW + uxx0)) * (HuW + Hu0 - C6 * (HxxW + Hxx0));
+      } else {
+        UFx0 = 0.25 * (c1 + Gadv * c) * (Hu0 + HuE + Gadv * 0.5 * (Hxx0 + HxxE));
+        c1 = uW + u0;
+        c = (c1 > 0.0) ? uxxW : uxx0;
+        UFxW = 0.25 * (c1 + Gadv * c) * (HuW + Hu0 + Gadv * 0.5 * (HxxW + Hxx0));
+      }
       // UFe(i,j) and UFe(i,j+1) at psi points; uee(i,0) = uee(i,1), uee(i,Mm+1) = uee(i,Mm)
       const double uee_j = uS - 2.0 * u0 + uN;
       const double uee_jm1 = (j > 1) ? (uS2 - 2.0 * uS + u0) : uee_j;
       const double uee_jp1 = (j < Mm) ? (u0 - 2.0 * uN + uN2) : uee_j;
       const double Hvxx0 = HvW - 2.0 * Hv0 + HvE, HvxxW = HvW2 - 2.0 * HvW + Hv0;
       const double HvxxN = HvNW - 2.0 * HvN + HvNE, HvxxNW = HvNW2 - 2.0 * HvNW + HvN;
-      c1 = u0 + uS;
-      double c2 = Hv0 + HvW;
-      c = (c2 > 0.0) ? uee_jm1 : uee_j;
-      const double UFe0 = 0.25 * (c1 + Gadv * c) * (c2 + Gadv * 0.5 * (Hvxx0 + HvxxW));
-      c1 = uN + u0;
-      c2 = HvN + HvNW;
-      c = (c2 > 0.0) ? uee_j : uee_jp1;
-      const double UFeN = 0.25 * (c1 + Gadv * c) * (c2 + Gadv * 0.5 * (HvxxN + HvxxNW));
+      double UFe0, UFeN;
+      if (UADV == 1) {
+        UFe0 = 0.25 * (u0 + uS - C6 * (uee_j + uee_jm1)) * (Hv0 + HvW - C6 * (Hvxx0 + HvxxW));
+        UFeN = 0.25 * (uN + u0 - C6 * (uee_jp1 + uee_j)) * (HvN + HvNW - C6 * (HvxxN + HvxxNW));
+      } else {
+        c1 = u0 + uS;
+        double c2 = Hv0 + HvW;
+        c = (c2 > 0.0) ? uee_jm1 : uee_j;
+        UFe0 = 0.25 * (c1 + Gadv * c) * (c2 + Gadv * 0.5 * (Hvxx0 + HvxxW));
+        c1 = uN + u0;
+        c2 = HvN + HvNW;
+        c = (c2 > 0.0) ? uee_j : uee_jp1;
+        UFeN = 0.25 * (c1 + Gadv * c) * (c2 + Gadv * 0.5 * (HvxxN + HvxxNW));
+      }
       const double a1 = UFx0 - UFxW;
       const double a2 = UFeN - UFe0;
       rux = rux - (a1 + a2);
@@ -139,40 +154,54 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
       const double Huee0 = HuS - 2.0 * Hu0 + HuN, HueeS = HuS2 - 2.0 * HuS + Hu0;
       const double HueeE = HuSE - 2.0 * HuE + HuNE, HueeSE = HuES2 - 2.0 * HuSE + HuE;
       // VFx(i,j), VFx(i+1,j) at psi points
-      double c1 = v0 + vW;
-      double c2 = Hu0 + HuS;
-      double c = (c2 > 0.0) ? vxxW : vxx0;
-      const double VFx0 = 0.25 * (c1 + Gadv * c) * (c2 + Gadv * 0.5 * (Huee0 + HueeS));
-      c1 = vE + v0;
-      c2 = HuE + HuSE;
-      c = (c2 > 0.0) ? vxx0 : vxxE;
-      const double VFxE = 0.25 * (c1 + Gadv * c) * (c2 + Gadv * 0.5 * (HueeE + HueeSE));
+      double c1, c2, c, VFx0, VFxE;
+      if (UADV == 1) {
+        VFx0 = 0.25 * (v0 + vW - C6 * (vxx0 + vxxW)) * (Hu0 + HuS - C6 * (Huee0 + HueeS));
+        VFxE = 0.25 * (vE + v0 - C6 * (vxxE + vxx0)) * (HuE + HuSE - C6 * (HueeE + HueeSE));
+      } else {
+        c1 = v0 + vW;
+        c2 = Hu0 + HuS;
+        c = (c2 > 0.0) ? vxxW : vxx0;
+        VFx0 = 0.25 * (c1 + Gadv * c) * (c2 + Gadv * 0.5 * (Huee0 + HueeS));
+        c1 = vE + v0;
+        c2 = HuE + HuSE;
+        c = (c2 > 0.0) ? vxx0 : vxxE;
+        VFxE = 0.25 * (c1 + Gadv * c) * (c2 + Gadv * 0.5 * (HueeE + HueeSE));
+      }
       // VFe(i,j), VFe(i,j-1) at rho points; vee/Hvee rows 2..Mm with copies (1)=(2), (Mm+1)=(Mm)
       const double vee_j = vS - 2.0 * v0 + vN, Hvee_j = HvS - 2.0 * Hv0 + HvN;
       const double vee_jp = (j < Mm) ? (v0 - 2.0 * vN + vN2) : vee_j, Hvee_jp = (j < Mm) ? (Hv0 - 2.0 * HvN + HvN2) : Hvee_j;
       const double vee_jm = (j > 2) ? (vS2 - 2.0 * vS + v0) : vee_j, Hvee_jm = (j > 2) ? (HvS2 - 2.0 * HvS + Hv0) : Hvee_j;
-      c1 = v0 + vN;
-      c = (c1 > 0.0) ? vee_j : vee_jp;
-      const double VFe0 = 0.25 * (c1 + Gadv * c) * (Hv0 + HvN + Gadv * 0.5 * (Hvee_j + Hvee_jp));
-      c1 = vS + v0;
-      c = (c1 > 0.0) ? vee_jm : vee_j;
-      const double VFeS = 0.25 * (c1 + Gadv * c) * (HvS + Hv0 + Gadv * 0.5 * (Hvee_jm + Hvee_j));
+      double VFe0, VFeS;
+      if (UADV == 1) {
+        VFe0 = 0.25 * (v0 + vN - C6 * (vee_j + vee_jp)) * (Hv0 + HvN - C6 * (Hvee_j + Hvee_jp));
+        VFeS = 0.25 * (vS + v0 - C6 * (vee_jm + vee_j)) * (HvS + Hv0 - C6 * (Hvee_jm + Hvee_j));
+      } else {
+        c1 = v0 + vN;
+        c = (c1 > 0.0) ? vee_j : vee_jp;
+        VFe0 = 0.25 * (c1 + Gadv * c) * (Hv0 + HvN + Gadv * 0.5 * (Hvee_j + Hvee_jp));
+        c1 = vS + v0;
+        c = (c1 > 0.0) ? vee_jm : vee_j;
+        VFeS = 0.25 * (c1 + Gadv * c) * (HvS + Hv0 + Gadv * 0.5 * (Hvee_jm + Hvee_j));
+      }
       const double a1 = VFxE - VFx0;
       const double a2 = VFe0 - VFeS;
       rvx = rvx - (a1 + a2);
     }
     // ---- vertical advection (rhs3d.F:1177-1265, :1434-1522): FC(k) through the top of level k
     {
-      const double c1 = 9.0 / 16.0, c2 = 1.0 / 16.0;
+      const double c1 = (UADV == 1) ? 9.0 / 32.0 : 9.0 / 16.0, c2 = (UADV == 1) ? 1.0 / 32.0 : 1.0 / 16.0;
       double FCu = 0.0, FCv = 0.0;
       if (k < N) {
         const double ukm = (k > 1) ? uDn : u0;
         const double ukpp = (k + 2 <= N) ? uUp2 : uUp;
-        FCu = (c1 * (u0 + uUp) - c2 * (ukm + ukpp)) * (c1 * (W0 + WW) - c2 * (WE + WW2));
+        if (UADV == 1) FCu = (c1 * (u0 + uUp) - c2 * (ukm + ukpp)) * (W0 + WW);
+        else FCu = (c1 * (u0 + uUp) - c2 * (ukm + ukpp)) * (c1 * (W0 + WW) - c2 * (WE + WW2));
         if (dov) {
           const double vkm = (k > 1) ? vDn : v0;
           const double vkpp = (k + 2 <= N) ? vUp2 : vUp;
-          FCv = (c1 * (v0 + vUp) - c2 * (vkm + vkpp)) * (c1 * (W0 + WS) - c2 * (WN + WS2));
+          if (UADV == 1) FCv = (c1 * (v0 + vUp) - c2 * (vkm + vkpp)) * (W0 + WS);
+          else FCv = (c1 * (v0 + vUp) - c2 * (vkm + vkpp)) * (c1 * (W0 + WS) - c2 * (WN + WS2));
         }
       }
       rux = rux - (FCu - FCu_m);
@@ -294,7 +323,11 @@ __global__ void __launch_bounds__(128, UVM_MINB) k_uv3dmix2(Par p, Flds f) {
 }
 
 static inline dim3 g2(dim3 b, int ni, int nj, int nz = 1) { return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz); }
-void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(RHS_BX, 128 / RHS_BX); k_rhs3d<<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f); }
+void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s) {
+  dim3 b(RHS_BX, 128 / RHS_BX);
+  if (p.uv_adv == 1) k_rhs3d<1><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
+  else k_rhs3d<0><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
+}
 void launch_uv3dmix2(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(UVM_BX, 128 / UVM_BX); k_uv3dmix2<<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f); }
 
 }  // namespace rb

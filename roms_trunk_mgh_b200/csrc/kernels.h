@@ -19,6 +19,7 @@ void launch_pre_step3d_uv(const Par& p, const Flds& f, cudaStream_t s);   // mom
 void launch_prsgrd(const Par& p, const Flds& f, int dj_gradps, cudaStream_t s);
 void launch_t3dmix2_s(const Par& p, const Flds& f, cudaStream_t s);
 void launch_t3dmix2_geo(const Par& p, const Flds& f, cudaStream_t s);
+void launch_t3dmix4_s(const Par& p, const Flds& f, cudaStream_t s);       // t3dmix4_s.h (TS_DIF4)
 void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s);
 void launch_uv3dmix2(const Par& p, const Flds& f, cudaStream_t s);
 // x != nullptr: this sub-step also pulls / pushes its xi-halo through NVLink peer memory (dev.cuh Xchg)

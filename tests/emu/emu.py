@@ -1,0 +1,68 @@
+"""TEST INFRASTRUCTURE: ctypes front end of tests/emu (host emulation of the barrier-free CUDA kernels)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DP = C.POINTER(C.c_double)
+EMULATED = {"set_massflux": 1, "rho_eos": 2, "set_vbc": 3, "ana_vmix": 4, "omega": 5, "wvelocity": 6, "set_zeta": 7, "pre_step3d": 8,
+            "prsgrd": 9, "t3dmix": 10, "rhs3d": 11, "uv3dmix": 12, "set_depth": 14, "omega2": 16, "bvf_mix": 25}
+IOPT = ["Lm", "Mm", "N", "NT", "nonlin_eos", "curvgrid", "uv_qdrag", "salinity", "hadv", "vadv", "itemp", "isalt", "bv_frequency",
+        "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "uv_adv", "ts_dif4", "dj_gradps", "mix_geo_ts",
+        "ana_vmix", "ndtfast"]
+DOPT = ["dt", "g", "rho0", "R0", "T0", "S0", "Tcoef", "Scoef", "gamma2", "lambda", "hc", "Akv_bak", "Akt_bak", "Akt_bak", "blk_ZQ", "blk_ZT", "blk_ZW"]
+_L = None
+
+
+def lib():
+    global _L
+    if _L is None:
+        subprocess.run(["make", "-s", "-C", HERE], check=True)
+        _L = C.CDLL(os.path.join(HERE, "_build", "libemu.so"))
+        _L.emu_create.restype = C.c_void_p
+        _L.emu_create.argtypes = [C.POINTER(C.c_int), DP]
+        _L.emu_destroy.argtypes = [C.c_void_p]
+        _L.emu_xfer.argtypes = [C.c_void_p, C.c_char_p, DP, C.c_int]
+        _L.emu_levels.argtypes = [C.c_void_p, C.c_char_p]
+        _L.emu_scoord.argtypes = [C.c_void_p, C.c_int, DP, C.c_int]
+        _L.emu_indices.argtypes = [C.c_void_p] + [C.c_int] * 4
+        _L.emu_run.argtypes = [C.c_void_p, C.c_int]
+    return _L
+
+
+class EmuTile:
+    """The kernels of one tile run thread by thread on the host, configured from an oracle instance."""
+
+    def __init__(self, o):
+        self.L = lib()
+        io = (C.c_int * len(IOPT))(*[int(o.opt(k)) for k in IOPT])
+        dv = (C.c_double * len(DOPT))(*[float(o.opt(k)) for k in DOPT])
+        self.h = C.c_void_p(self.L.emu_create(io, dv))
+        self.N, self.Lm, self.Mm = int(o.opt("N")), int(o.opt("Lm")), int(o.opt("Mm"))
+        for w in range(4):
+            v = np.ascontiguousarray(o.vector(w, self.N + 1))
+            self.L.emu_scoord(self.h, w, v.ctypes.data_as(DP), v.size)
+
+    def close(self):
+        if self.h:
+            self.L.emu_destroy(self.h); self.h = None
+
+    def set(self, name, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        assert a.shape == (self.L.emu_levels(self.h, name.encode()), self.Mm + 2, self.Lm + 5), (name, a.shape)
+        assert self.L.emu_xfer(self.h, name.encode(), a.ctypes.data_as(DP), 1) == 0, name
+
+    def get(self, name):
+        out = np.empty((self.L.emu_levels(self.h, name.encode()), self.Mm + 2, self.Lm + 5))
+        assert self.L.emu_xfer(self.h, name.encode(), out.ctypes.data_as(DP), 0) == 0, name
+        return out
+
+    def set_indices(self, d):
+        istart = 0 if d["iic"] == d["ntfirst"] else (1 if d["iic"] == d["ntfirst"] + 1 else 2)
+        self.L.emu_indices(self.h, d["nstp"], d["nnew"], d["nrhs"], istart)
+
+    def run_phase(self, name):
+        rc = self.L.emu_run(self.h, EMULATED[name])
+        assert rc == 0, (name, rc)

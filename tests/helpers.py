@@ -6,7 +6,7 @@ from roms_trunk_mgh_b200 import _lib
 from roms_trunk_mgh_b200.ocean import Tile, field_names
 
 APP_OPTS = ["nonlin_eos", "dj_gradps", "curvgrid", "mix_geo_ts", "uv_qdrag", "hadv", "vadv", "ana_vmix", "wvelocity_every_step",
-            "bv_frequency", "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "bvf_mixing"]
+            "bv_frequency", "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "bvf_mixing", "uv_adv", "ts_dif4"]
 
 
 def cfg_from_oracle(o, device=0):
@@ -41,6 +41,7 @@ def optional_names(o):
     if o.opt("lmd_nonlocal"): v += [f"ghats_{it}" for it in range(NT)]
     if o.opt("bulk_fluxes"): v += [n for n in ATMOSPHERE if n not in v] + ["lrflx", "lhflx", "shflx"]
     if o.opt("lmd_mixing"): v += ["hsbl", "ksbl"]
+    if o.opt("ts_dif4"): v += [f"diff4_{it}" for it in range(NT)]
     return v
 
 

@@ -679,3 +679,95 @@ def test_bvf_mixing_properties():
     o2.step(10, 4)
     for n in ("zeta1", "u1", "t1_0", "Akv", "Akt_1"):
         assert np.array_equal(o.field(n), o2.field(n)), n
+
+
+# ---- SURVEY 8(f)-3 variants: TS_DIF4 + MIX_S_TS (t3dmix4_s.h) and UV_C4ADVECTION (rhs3d.F) -----------------------------------------
+def _wave(o, name, m):
+    """sin(2 pi m i / Lm) along xi on every row / level of field `name`, ghost columns included (periodic by construction)."""
+    a = o.field(name)
+    LBi = o.origin(name)[0]
+    i = np.arange(a.shape[2]) + LBi
+    a[:] = np.sin(2.0 * np.pi * m * i / int(o.opt("Lm")))[None, None, :]
+    return a
+
+
+def test_t3dmix4_s_known_answer():
+    """t3dmix4_s.h on a uniform grid with Hz = 1 and a tracer that is a sine in xi: the two passes give
+    -dt * tnu4 * (2 - 2 cos th)^2 / dx^4 * t away from the walls; next to a closed wall LapT = 0 outside (t3dmix4_s.h:378-404)
+    leaves the extra term -dt * tnu4 * (2 - 2 cos th) / (dx^2 dy^2) * t.  Pins the 0.25*(d+d), SQRT(ABS(tnu4)) and sign conventions."""
+    Lm, Mm, N, m, tnu4 = 40, 24, 6, 3, 2.5e8
+    o = orc.Oracle(orc.APP_UPWELLING, Lm=Lm, Mm=Mm, N=N, kind="chk", ts_dif4=1, tnu4=tnu4)
+    o.run_phase("set_data"); o.run_phase("ini")
+    d = o.indices(); d["nstp"] = 1; d["nnew"] = 2; d["nrhs"] = 1; o.set_indices(d)
+    assert np.all(o.field("diff4_0") == np.sqrt(tnu4)) and np.all(o.field("diff2_0") == 0.0)
+    o.field("Hz")[:] = 1.0
+    tr = _wave(o, "t1_0", m).copy(); _wave(o, "t1_1", m)
+    o.field("t2_0")[:] = 0.0; o.field("t2_1")[:] = 0.0
+    o.run_phase("t3dmix")
+    pm, pn = o.field("pm")[0, 3, 5], o.field("pn")[0, 3, 5]
+    assert np.all(o.field("pm") == pm) and np.all(o.field("pn") == pn)
+    dt, th = o.opt("dt"), 2.0 * np.pi * m / Lm
+    lam = 2.0 - 2.0 * np.cos(th)
+    LBi, LBj, _ = o.origin("t2_0")
+    got = o.field("t2_0")
+    I = slice(1 - LBi, Lm + 1 - LBi)
+    want = -dt * tnu4 * lam * lam * pm ** 4 * tr[:, :, I]
+    scale = np.abs(want).max()
+    assert scale > 1e-3
+    assert np.abs(got[:, 2 - LBj:Mm - LBj, I] - want[:, 2 - LBj:Mm - LBj, :]).max() < 1e-11 * scale
+    wall = want - dt * tnu4 * lam * pm * pm * pn * pn * tr[:, :, I]
+    for j in (1, Mm):
+        assert np.abs(got[:, j - LBj, I] - wall[:, j - LBj, :]).max() < 1e-11 * scale
+    assert np.array_equal(o.field("t2_1"), o.field("t2_0"))               # same operands for both tracers
+
+
+def test_uv_c4advection_known_answers():
+    """rhs3d.F with UV_C4ADVECTION: (1) u a sine in xi, constant Huon = H, nothing else: ru = -0.5 H (1 + (2 - 2 cos th) / 6)
+    (u(i+1) - u(i-1)) -- pins 0.25 and the 1/6 curvature weights of :685-705; (2) u linear in k, uniform W = w, no horizontal
+    transport: the 9/32, 1/32 vertical flux (:1108-1175) is exact for a linear profile, ru = -w a per level away from the ends."""
+    Lm, Mm, N, m = 40, 24, 12, 2
+    o = orc.Oracle(orc.APP_UPWELLING, Lm=Lm, Mm=Mm, N=N, kind="chk", uv_adv=1)
+    o.run_phase("set_data"); o.run_phase("ini")
+    d = o.indices(); d["nstp"] = 1; d["nnew"] = 2; d["nrhs"] = 1; o.set_indices(d)
+    for n in ("fomn", "v1", "Hvom", "W", "ru1", "rv1", "sustr", "svstr", "bustr", "bvstr"):
+        o.field(n)[:] = 0.0
+    H = 3.0e4
+    o.field("Huon")[:] = H
+    u = _wave(o, "u1", m).copy()
+    o.run_phase("rhs3d")
+    LBi, LBj, _ = o.origin("ru1")
+    th = 2.0 * np.pi * m / Lm
+    I = np.arange(1, Lm + 1) - LBi
+    want = -0.5 * H * (1.0 + (2.0 - 2.0 * np.cos(th)) / 6.0) * (u[:, :, I + 1] - u[:, :, I - 1])
+    got = o.field("ru1")[1:, :, :][:, :, I]                                 # ru holds levels 0:N
+    rows = slice(2 - LBj, Mm - LBj)                                         # away from the walls (uee copies)
+    assert np.abs(got[:, rows] - want[:, rows]).max() < 1e-12 * np.abs(want).max()
+    assert np.all(o.field("rv1")[1:, 2 - LBj:Mm + 1 - LBj, :][:, :, I] == 0.0)
+    # (2) vertical
+    for n in ("Huon", "ru1", "rv1"):
+        o.field(n)[:] = 0.0
+    a, w = 0.01, 2.5
+    o.field("u1")[:] = (a * np.arange(1, N + 1))[:, None, None]
+    o.field("W")[:] = w
+    o.run_phase("rhs3d")
+    got = o.field("ru1")[1:, :, :][:, rows][:, :, I]
+    # FC(k) = (u(k) + u(k+1)) / 2 * 2w / 2 ... = w (u(k) + u(k+1)) / 2 for a linear profile; ru(k) = -(FC(k) - FC(k-1)) = -w a
+    assert np.abs(got[2:N - 2] + w * a).max() < 1e-14
+    # k = N: FC(N) = 0, FC(N-1) = (9/32 (u(N-1) + u(N)) - 1/32 (u(N-2) + u(N))) 2w
+    fcn1 = (9.0 / 32.0 * (a * (N - 1) + a * N) - 1.0 / 32.0 * (a * (N - 2) + a * N)) * 2.0 * w
+    assert np.abs(got[N - 1] - fcn1).max() < 1e-13
+
+
+def test_variants_tiling_invariance_and_effect():
+    """Both variants are tiling-invariant (verify.sh criterion) on 2 x 2 tiles and change the answer with respect to the default branches."""
+    base = dict(Lm=48, Mm=32, N=10)
+    ref = orc.Oracle(orc.APP_BENCHMARK, kind="chk", **base); ref.run_phase("set_data"); ref.run_phase("ini"); ref.step(10)
+    for kw in (dict(uv_adv=1), dict(ts_dif4=1, tnu4=1.0e15), dict(uv_adv=1, ts_dif4=1, tnu4=1.0e15)):
+        a = orc.Oracle(orc.APP_BENCHMARK, kind="chk", **base, **kw); a.run_phase("set_data"); a.run_phase("ini"); a.step(10)
+        b = orc.Oracle(orc.APP_BENCHMARK, NtileI=2, NtileJ=2, kind="chk", **base, **kw); b.run_phase("set_data"); b.run_phase("ini"); b.step(10, 4)
+        for n in ("zeta1", "u1", "v1", "t1_0", "t1_1", "ru1", "rufrc"):
+            assert np.array_equal(a.field(n), b.field(n)), (kw, n)
+            assert np.isfinite(a.field(n)).all()
+        changed = "u1" if "uv_adv" in kw else "t1_0"
+        assert not np.array_equal(a.field(changed), ref.field(changed)), kw
+        assert abs(a.diag()["volume"] / ref.diag()["volume"] - 1.0) < 1e-12
