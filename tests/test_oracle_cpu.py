@@ -171,7 +171,7 @@ def test_cabi_routine_args_name_known_fields():
     n2, n3 = field_names(2)
     # + the arrays that exist only with the BENCHMARK cpp switches on (include/roms_b200.h, roms_b200_config)
     optional = ["ZoBot", "bvf", "alpha", "beta", "srflx", "Jwtype", "ghats_0", "ghats_1", "Uwind", "Vwind", "Tair", "Pair", "Hair", "rain", "cloud",
-                "lrflx", "lhflx", "shflx", "hsbl", "ksbl"]
+                "lrflx", "lhflx", "shflx", "hsbl", "ksbl", "diff4_0", "diff4_1"]
     known = set(n2 + n3 + optional)
     for name, ph in _lib.PHASES.items():
         spec = L.roms_b200_routine_args(ph)
