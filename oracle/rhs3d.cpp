@@ -12,6 +12,8 @@ void rhs3d(Model& m, const Bnd& b) {
   const int N = c.N;
   const double Gadv = -0.25;                                         // rhs3d.F:299
   const bool c4 = (c.uv_adv == 1);                                   // UV_C4ADVECTION
+  const bool sadv = (c.uv_adv == 2);                                 // UV_SADVECTION (horizontal: the default branch)
+  SK CF(IminS, ImaxS, 0, N), DC(IminS, ImaxS, 0, N);
   F3 &Hz = m.Hz, &Huon = m.Huon, &Hvom = m.Hvom, &W = m.W;
   F3 u = m.u[m.nrhs], v = m.v[m.nrhs], ru = m.ru[m.nrhs], rv = m.rv[m.nrhs];
   SK FC(IminS, ImaxS, 0, N);
@@ -144,7 +146,30 @@ void rhs3d(Model& m, const Bnd& b) {
 
   // ---- vertical advection + column sums
   for (int j = Jstr; j <= Jend; ++j) {
-    if (c4) {                                                                                         // :1108-1175
+    if (sadv) {                                                                                       // :1016-1078: parabolic splines
+      const double cff1 = 9.0 / 16.0, cff2 = 1.0 / 16.0;
+      for (int k = 1; k <= N; ++k)
+        for (int i = IstrU; i <= Iend; ++i)
+          DC(i, k) = cff1 * (Hz(i, j, k) + Hz(i - 1, j, k)) - cff2 * (Hz(i + 1, j, k) + Hz(i - 2, j, k));
+      for (int i = IstrU; i <= Iend; ++i) { FC(i, 0) = 0.0; CF(i, 0) = 0.0; }
+      for (int k = 1; k <= N - 1; ++k)
+        for (int i = IstrU; i <= Iend; ++i) {
+          double cff = 1.0 / (2.0 * DC(i, k + 1) + DC(i, k) * (2.0 - FC(i, k - 1)));
+          FC(i, k) = cff * DC(i, k + 1);
+          CF(i, k) = cff * (6.0 * (u(i, j, k + 1) - u(i, j, k)) - DC(i, k) * CF(i, k - 1));
+        }
+      for (int i = IstrU; i <= Iend; ++i) CF(i, N) = 0.0;
+      for (int k = N - 1; k >= 1; --k)
+        for (int i = IstrU; i <= Iend; ++i) CF(i, k) = CF(i, k) - FC(i, k) * CF(i, k + 1);
+      const double cff3 = 1.0 / 3.0, cff4 = 1.0 / 6.0;
+      for (int k = 1; k <= N - 1; ++k)
+        for (int i = IstrU; i <= Iend; ++i)
+          FC(i, k) = (cff1 * (W(i, j, k) + W(i - 1, j, k)) - cff2 * (W(i + 1, j, k) + W(i - 2, j, k))) *
+                     (u(i, j, k) + DC(i, k) * (cff3 * CF(i, k) + cff4 * CF(i, k - 1)));
+      for (int i = IstrU; i <= Iend; ++i) { FC(i, N) = 0.0; FC(i, 0) = 0.0; }
+      for (int k = 1; k <= N; ++k)
+        for (int i = IstrU; i <= Iend; ++i) { double cff = FC(i, k) - FC(i, k - 1); ru(i, j, k) = ru(i, j, k) - cff; }
+    } else if (c4) {                                                                                  // :1108-1175
       const double cff1 = 9.0 / 32.0, cff2 = 1.0 / 32.0;
       for (int k = 2; k <= N - 2; ++k)
         for (int i = IstrU; i <= Iend; ++i)
@@ -174,7 +199,30 @@ void rhs3d(Model& m, const Bnd& b) {
       for (int k = 1; k <= N; ++k)
         for (int i = IstrU; i <= Iend; ++i) { double cff = FC(i, k) - FC(i, k - 1); ru(i, j, k) = ru(i, j, k) - cff; }
     }
-    if (j >= JstrV && c4) {                                                                           // :1362-1429
+    if (j >= JstrV && sadv) {                                                                         // :1267-1329
+      const double cff1 = 9.0 / 16.0, cff2 = 1.0 / 16.0;
+      for (int k = 1; k <= N; ++k)
+        for (int i = Istr; i <= Iend; ++i)
+          DC(i, k) = (cff1 * (Hz(i, j, k) + Hz(i, j - 1, k)) - cff2 * (Hz(i, j + 1, k) + Hz(i, j - 2, k)));
+      for (int i = Istr; i <= Iend; ++i) { FC(i, 0) = 0.0; CF(i, 0) = 0.0; }
+      for (int k = 1; k <= N - 1; ++k)
+        for (int i = Istr; i <= Iend; ++i) {
+          double cff = 1.0 / (2.0 * DC(i, k + 1) + DC(i, k) * (2.0 - FC(i, k - 1)));
+          FC(i, k) = cff * DC(i, k + 1);
+          CF(i, k) = cff * (6.0 * (v(i, j, k + 1) - v(i, j, k)) - DC(i, k) * CF(i, k - 1));
+        }
+      for (int i = Istr; i <= Iend; ++i) CF(i, N) = 0.0;
+      for (int k = N - 1; k >= 1; --k)
+        for (int i = Istr; i <= Iend; ++i) CF(i, k) = CF(i, k) - FC(i, k) * CF(i, k + 1);
+      const double cff3 = 1.0 / 3.0, cff4 = 1.0 / 6.0;
+      for (int k = 1; k <= N - 1; ++k)
+        for (int i = Istr; i <= Iend; ++i)
+          FC(i, k) = (cff1 * (W(i, j, k) + W(i, j - 1, k)) - cff2 * (W(i, j + 1, k) + W(i, j - 2, k))) *
+                     (v(i, j, k) + DC(i, k) * (cff3 * CF(i, k) + cff4 * CF(i, k - 1)));
+      for (int i = Istr; i <= Iend; ++i) { FC(i, N) = 0.0; FC(i, 0) = 0.0; }
+      for (int k = 1; k <= N; ++k)
+        for (int i = Istr; i <= Iend; ++i) { double cff = FC(i, k) - FC(i, k - 1); rv(i, j, k) = rv(i, j, k) - cff; }
+    } else if (j >= JstrV && c4) {                                                                    // :1362-1429
       const double cff1 = 9.0 / 32.0, cff2 = 1.0 / 32.0;
       for (int k = 2; k <= N - 2; ++k)
         for (int i = Istr; i <= Iend; ++i)

@@ -693,7 +693,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   // lmd_skpp reads bvf, alpha / beta, srflx and writes ghats: the switches that provide those arrays must be on with it
   if (cfg->lmd_mixing && !(cfg->bv_frequency && cfg->eos_tderivative && cfg->solar_source && cfg->lmd_nonlocal)) return ConfigError;
   if (cfg->bvf_mixing && !cfg->bv_frequency) return ConfigError;
-  if (cfg->uv_adv < 0 || cfg->uv_adv > 1) return ConfigError;
+  if (cfg->uv_adv < 0 || cfg->uv_adv > 2) return ConfigError;
   if (cfg->ts_dif4 && cfg->mix_geo_ts) return ConfigError;                          // t3dmix4_geo.h is not built
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {

@@ -29,7 +29,8 @@ __device__ __forceinline__ double d2y(const double* __restrict__ A, int o, int P
 #define UVM_PF 4          // same for k_uv3dmix2
 #endif
 // UADV: 0 the default branch (third-order upstream horizontal :706-730 ..., fourth-order centred vertical :1177-1255); 1
-// UV_C4ADVECTION (fourth-order centred horizontal :685-705, :761-781, :829-849, :902-921; vertical 9/32, 1/32 :1108-1175, :1362-1429).
+// UV_C4ADVECTION (fourth-order centred horizontal :685-705, :761-781, :829-849, :902-921; vertical 9/32, 1/32 :1108-1175, :1362-1429);
+// 2 UV_SADVECTION (the default horizontal branch; conservative parabolic splines in the vertical :1016-1078, :1267-1329).
 template <int UADV>
 __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,6 +58,42 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
   // :886-901) and keep every load in bounds so that all operands of a level can be fetched unconditionally.
   const int S2 = (j >= 2) ? -2 * P : -P, N2 = (j + 2 <= Mm + 1) ? 2 * P : P;
   double FCu_m = 0.0, FCv_m = 0.0, rufrc = 0.0, rvfrc = 0.0;
+  // UV_SADVECTION (rhs3d.F:1016-1051, :1267-1302): the spline derivatives CF(0:N) of the u and v columns, by the reference's own
+  // forward elimination / back substitution, before the level sweep (thread-local columns)
+  double CFu[UADV == 2 ? MAXN + 1 : 1], CFv[UADV == 2 ? MAXN + 1 : 1];
+  if (UADV == 2) {
+    const double s1 = 9.0 / 16.0, s2 = 1.0 / 16.0;
+    double FCs[MAXN + 1];
+    const int ob = o2 + i;
+    {
+      FCs[0] = 0.0; CFu[0] = 0.0;
+      double dck = s1 * (Hz[ob + p.PL] + Hz[ob + p.PL - 1]) - s2 * (Hz[ob + p.PL + 1] + Hz[ob + p.PL - 2]);
+      for (int k = 1; k <= N - 1; ++k) {
+        const int o1 = ob + (k + 1) * p.PL;
+        const double dck1 = s1 * (Hz[o1] + Hz[o1 - 1]) - s2 * (Hz[o1 + 1] + Hz[o1 - 2]);
+        const double cff = 1.0 / (2.0 * dck1 + dck * (2.0 - FCs[k - 1]));
+        FCs[k] = cff * dck1;
+        CFu[k] = cff * (6.0 * (u[o1] - u[o1 - p.PL]) - dck * CFu[k - 1]);
+        dck = dck1;
+      }
+      CFu[N] = 0.0;
+      for (int k = N - 1; k >= 1; --k) CFu[k] = CFu[k] - FCs[k] * CFu[k + 1];
+    }
+    if (dov) {
+      FCs[0] = 0.0; CFv[0] = 0.0;
+      double dck = (s1 * (Hz[ob + p.PL] + Hz[ob + p.PL - P]) - s2 * (Hz[ob + p.PL + P] + Hz[ob + p.PL - 2 * P]));
+      for (int k = 1; k <= N - 1; ++k) {
+        const int o1 = ob + (k + 1) * p.PL;
+        const double dck1 = (s1 * (Hz[o1] + Hz[o1 - P]) - s2 * (Hz[o1 + P] + Hz[o1 - 2 * P]));
+        const double cff = 1.0 / (2.0 * dck1 + dck * (2.0 - FCs[k - 1]));
+        FCs[k] = cff * dck1;
+        CFv[k] = cff * (6.0 * (v[o1] - v[o1 - p.PL]) - dck * CFv[k - 1]);
+        dck = dck1;
+      }
+      CFv[N] = 0.0;
+      for (int k = N - 1; k >= 1; --k) CFv[k] = CFv[k] - FCs[k] * CFv[k + 1];
+    }
+  }
   for (int k = 1; k <= N; ++k) {
     const int o = o2 + k * p.PL + i;                     // includes i
     const int oU = (k < N) ? o + p.PL : o, oUU = (k + 2 <= N) ? o + 2 * p.PL : oU, oD = (k > 1) ? o - p.PL : o;
@@ -196,11 +233,19 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
         const double ukm = (k > 1) ? uDn : u0;
         const double ukpp = (k + 2 <= N) ? uUp2 : uUp;
         if (UADV == 1) FCu = (c1 * (u0 + uUp) - c2 * (ukm + ukpp)) * (W0 + WW);
+        else if (UADV == 2) {                                               // rhs3d.F:1052-1069
+          const double DCk = c1 * (hz0 + hzW) - c2 * (Hz[o + 1] + Hz[o - 2]);
+          FCu = (c1 * (W0 + WW) - c2 * (WE + WW2)) * (u0 + DCk * ((1.0 / 3.0) * CFu[k] + (1.0 / 6.0) * CFu[k - 1]));
+        }
         else FCu = (c1 * (u0 + uUp) - c2 * (ukm + ukpp)) * (c1 * (W0 + WW) - c2 * (WE + WW2));
         if (dov) {
           const double vkm = (k > 1) ? vDn : v0;
           const double vkpp = (k + 2 <= N) ? vUp2 : vUp;
           if (UADV == 1) FCv = (c1 * (v0 + vUp) - c2 * (vkm + vkpp)) * (W0 + WS);
+          else if (UADV == 2) {                                             // rhs3d.F:1303-1320
+            const double DCk = (c1 * (hz0 + hzS) - c2 * (Hz[o + P] + Hz[o - 2 * P]));
+            FCv = (c1 * (W0 + WS) - c2 * (WN + WS2)) * (v0 + DCk * ((1.0 / 3.0) * CFv[k] + (1.0 / 6.0) * CFv[k - 1]));
+          }
           else FCv = (c1 * (v0 + vUp) - c2 * (vkm + vkpp)) * (c1 * (W0 + WS) - c2 * (WN + WS2));
         }
       }
@@ -326,6 +371,7 @@ static inline dim3 g2(dim3 b, int ni, int nj, int nz = 1) { return dim3((ni + b.
 void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s) {
   dim3 b(RHS_BX, 128 / RHS_BX);
   if (p.uv_adv == 1) k_rhs3d<1><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
+  else if (p.uv_adv == 2) k_rhs3d<2><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
   else k_rhs3d<0><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
 }
 void launch_uv3dmix2(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(UVM_BX, 128 / UVM_BX); k_uv3dmix2<<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f); }

@@ -28,6 +28,8 @@ CASES = {
     "benchmark_bvf": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, bv_frequency=1, bvf_mixing=1)),
     "uv_c4": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, uv_adv=1)),
     "uv_c4_seamount": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, uv_adv=1)),
+    "uv_sadv": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, uv_adv=2)),
+    "uv_sadv_seamount": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, uv_adv=2)),
     "ts_dif4": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, ts_dif4=1, tnu4=1.0e15)),
     "ts_dif4_upwelling": (orc.APP_UPWELLING, dict(Lm=20, Mm=24, N=8, ts_dif4=1, tnu4=4.0e8)),
     "both_n30": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=30, uv_adv=1, ts_dif4=1, tnu4=1.0e15)),

@@ -771,3 +771,32 @@ def test_variants_tiling_invariance_and_effect():
         changed = "u1" if "uv_adv" in kw else "t1_0"
         assert not np.array_equal(a.field(changed), ref.field(changed)), kw
         assert abs(a.diag()["volume"] / ref.diag()["volume"] - 1.0) < 1e-12
+
+
+def test_uv_sadvection_known_answer_and_tiling():
+    """rhs3d.F with UV_SADVECTION: for u linear in k over uniform layers the parabolic-spline derivative is a / Hz away from the
+    ends (the end conditions CF(0) = CF(N) = 0 decay like (2 - sqrt 3)^n), so the flux is w (u(k) + u(k+1)) / 2 and ru = -w a
+    at mid-depth; the run is tiling-invariant and differs from the default C4 branch."""
+    Lm, Mm, N = 24, 16, 40
+    o = orc.Oracle(orc.APP_UPWELLING, Lm=Lm, Mm=Mm, N=N, kind="chk", uv_adv=2)
+    o.run_phase("set_data"); o.run_phase("ini")
+    d = o.indices(); d["nstp"] = 1; d["nnew"] = 2; d["nrhs"] = 1; o.set_indices(d)
+    for n in ("fomn", "v1", "Huon", "Hvom", "ru1", "rv1", "sustr", "svstr", "bustr", "bvstr"):
+        o.field(n)[:] = 0.0
+    a, w, H = 0.01, 2.5, 3.7
+    o.field("Hz")[:] = H
+    o.field("u1")[:] = (a * np.arange(1, N + 1))[:, None, None]
+    o.field("W")[:] = w
+    o.run_phase("rhs3d")
+    LBi, LBj, _ = o.origin("ru1")
+    got = o.field("ru1")[1:, 2 - LBj:Mm - LBj, 1 - LBi:Lm + 1 - LBi]
+    mid = got[N // 2 - 3:N // 2 + 3]
+    assert np.abs(mid + w * a).max() < 1e-9 * w * a
+    assert np.abs(got[0] + w * a).max() > 1e-3 * w * a                   # the end condition is felt at the bottom level
+    base = dict(Lm=48, Mm=32, N=10, uv_adv=2)
+    x = orc.Oracle(orc.APP_BENCHMARK, kind="chk", **base); x.run_phase("set_data"); x.run_phase("ini"); x.step(10)
+    y = orc.Oracle(orc.APP_BENCHMARK, NtileI=2, NtileJ=2, kind="chk", **base); y.run_phase("set_data"); y.run_phase("ini"); y.step(10, 4)
+    z = orc.Oracle(orc.APP_BENCHMARK, kind="chk", Lm=48, Mm=32, N=10); z.run_phase("set_data"); z.run_phase("ini"); z.step(10)
+    for n in ("zeta1", "u1", "v1", "t1_0", "ru1", "rufrc"):
+        assert np.array_equal(x.field(n), y.field(n)), n
+    assert not np.array_equal(x.field("u1"), z.field("u1"))
