@@ -11,6 +11,10 @@
 #include "cuda_runtime.h"
 thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
+EmuBlockBarrier emu_block_barrier;
+void __syncthreads() { emu_block_barrier.wait(); }
+double* emu_dynsmem() { static std::vector<double> buf(64 * 1024); return buf.data(); }      // 512 KB >= any CTA's dynamic shared memory
+unsigned long long atomicAdd(unsigned long long* a, unsigned long long v) { static std::mutex m; std::lock_guard<std::mutex> g(m); const unsigned long long o = *a; *a = o + v; return o; }
 #include "kernels.h"
 
 using namespace rb;
@@ -108,6 +112,12 @@ void emu_scoord(void* h, int which, const double* v, int n) {
   double* d = which == 0 ? e->f.sc_r : which == 1 ? e->f.Cs_r : which == 2 ? e->f.sc_w : e->f.Cs_w;
   std::memcpy(d, v, sizeof(double) * n);
 }
+// the 2-D indices of one step2d call (main3d.F:599-661) and its filter weights weight(1,iif-1), weight(2,iif), weight(2,iif+1)
+void emu_indices2d(void* h, int iif, int kstp, int krhs, int knew, int predictor, int nfast, double w1_m1, double w2_0, double w2_p1) {
+  Par& p = ((Emu*)h)->p;
+  p.iif = iif; p.kstp = kstp; p.krhs = krhs; p.knew = knew; p.ptsk = 3 - kstp; p.predictor = predictor; p.nfast = nfast;
+  p.w1_m1 = w1_m1; p.w2_0 = w2_0; p.w2_p1 = w2_p1;
+}
 void emu_indices(void* h, int nstp, int nnew, int nrhs, int istart) { Par& p = ((Emu*)h)->p; p.nstp = nstp; p.nnew = nnew; p.nrhs = nrhs; p.istart = istart; }
 
 // one phase, as csrc/api.cu run_phase_async issues it for a single tile (phase numbers of include/roms_b200.h)
@@ -126,13 +136,15 @@ int emu_run(void* h, int phase) {
     case 8: launch_pre_step3d_t(p, f, s); launch_pre_step3d_uv(p, f, s); break;
     case 9: launch_prsgrd(p, f, e->dj_gradps, s); break;
     case 10:
-      if (e->mix_geo_ts) return 5;                                   // k_t3dmix2_geo_tiled uses shared memory: not emulated
-      launch_t3dmix2_s(p, f, s);
+      if (e->mix_geo_ts) launch_t3dmix2_geo(p, f, s); else launch_t3dmix2_s(p, f, s);
       if (e->ts_dif4) launch_t3dmix4_s(p, f, s);
       break;
     case 11: launch_rhs3d(p, f, s); break;
     case 12: launch_uv3dmix2(p, f, s); break;
+    case 13: launch_step2d(p, f, s, nullptr); break;
     case 14: launch_set_depth(p, f, s); break;
+    case 15: launch_step3d_uv(p, f, s); break;
+    case 17: launch_step3d_t(p, f, s); break;
     case 25: launch_bvf_mix(p, f, s); break;
     default: return 5;
   }

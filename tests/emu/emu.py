@@ -8,7 +8,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 DP = C.POINTER(C.c_double)
 EMULATED = {"set_massflux": 1, "rho_eos": 2, "set_vbc": 3, "ana_vmix": 4, "omega": 5, "wvelocity": 6, "set_zeta": 7, "pre_step3d": 8,
-            "prsgrd": 9, "t3dmix": 10, "rhs3d": 11, "uv3dmix": 12, "set_depth": 14, "omega2": 16, "bvf_mix": 25}
+            "prsgrd": 9, "t3dmix": 10, "rhs3d": 11, "uv3dmix": 12, "step2d": 13, "set_depth": 14, "step3d_uv": 15, "omega2": 16, "step3d_t": 17,
+            "bvf_mix": 25}
 IOPT = ["Lm", "Mm", "N", "NT", "nonlin_eos", "curvgrid", "uv_qdrag", "salinity", "hadv", "vadv", "itemp", "isalt", "bv_frequency",
         "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "uv_adv", "ts_dif4", "dj_gradps", "mix_geo_ts",
         "ana_vmix", "ndtfast"]
@@ -28,6 +29,7 @@ def lib():
         _L.emu_levels.argtypes = [C.c_void_p, C.c_char_p]
         _L.emu_scoord.argtypes = [C.c_void_p, C.c_int, DP, C.c_int]
         _L.emu_indices.argtypes = [C.c_void_p] + [C.c_int] * 4
+        _L.emu_indices2d.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_double] * 3
         _L.emu_run.argtypes = [C.c_void_p, C.c_int]
     return _L
 
@@ -41,6 +43,8 @@ class EmuTile:
         dv = (C.c_double * len(DOPT))(*[float(o.opt(k)) for k in DOPT])
         self.h = C.c_void_p(self.L.emu_create(io, dv))
         self.N, self.Lm, self.Mm = int(o.opt("N")), int(o.opt("Lm")), int(o.opt("Mm"))
+        nd = int(o.opt("ndtfast"))
+        self.nfast, self.w1, self.w2 = int(o.opt("nfast")), o.vector(4, 2 * nd + 2), o.vector(5, 2 * nd + 2)
         for w in range(4):
             v = np.ascontiguousarray(o.vector(w, self.N + 1))
             self.L.emu_scoord(self.h, w, v.ctypes.data_as(DP), v.size)
@@ -62,6 +66,9 @@ class EmuTile:
     def set_indices(self, d):
         istart = 0 if d["iic"] == d["ntfirst"] else (1 if d["iic"] == d["ntfirst"] + 1 else 2)
         self.L.emu_indices(self.h, d["nstp"], d["nnew"], d["nrhs"], istart)
+        iif = d["iif"]
+        w = lambda a, i: float(a[i]) if 0 <= i < len(a) else 0.0
+        self.L.emu_indices2d(self.h, iif, d["kstp"], d["krhs"], d["knew"], d["PREDICTOR"], self.nfast, w(self.w1, iif - 1), w(self.w2, iif), w(self.w2, iif + 1))
 
     def run_phase(self, name):
         rc = self.L.emu_run(self.h, EMULATED[name])

@@ -1,10 +1,12 @@
-"""CPU check of the CUDA kernels' SOURCE (no GPU needed): tests/emu compiles the unmodified text of the barrier-free kernels
-(csrc/k_glue.cu, k_pre.cu, k_rhs.cu: set_massflux, rho_eos, set_vbc, ana_vmix, omega, wvelocity, set_zeta, pre_step3d, prsgrd31/32,
-t3dmix2_s, t3dmix4_s, rhs3d, uv3dmix2, set_depth, bvf_mix) for the host and runs every thread of every launch in turn.  Built like
-the oracle's parity build (-O2 -ffp-contract=off), each phase must reproduce the oracle BIT FOR BIT from the oracle's own inputs:
-loop ranges, wall / periodic-image handling, upstream selects and operation order of the kernel text are pinned without a device.
-What it cannot see: kernels with shared memory / barriers (step2d, step3d_uv, step3d_t, t3dmix2_geo, diag, lmd_vmix's east column),
-device libm, races.  The -m gpu tests remain the parity tests proper."""
+"""CPU check of the CUDA kernels' SOURCE (no GPU needed): tests/emu compiles the unmodified text of the kernels of the chain
+(csrc/k_glue.cu, k_pre.cu, k_rhs.cu, k_step3d.cu, k_mixgeo.cu, k_step2d.cu: set_massflux, rho_eos, set_vbc, ana_vmix, omega,
+wvelocity, set_zeta, pre_step3d, prsgrd31/32, t3dmix2_s, t3dmix2_geo, t3dmix4_s, rhs3d, uv3dmix2, step2d, set_depth, step3d_uv,
+step3d_t, bvf_mix) for the host and runs every thread of every launch -- in turn, or as a pool of host threads with a real barrier
+for the kernels that call __syncthreads().  Built like the oracle's parity build (-O2 -ffp-contract=off), each phase must reproduce
+the oracle BIT FOR BIT from the oracle's own inputs: loop ranges, wall / periodic-image handling, upstream selects, shared-memory
+tile indexing and the operation order of the kernel text are pinned without a device.  What it cannot see: the cooperative loop
+kernel (k_step2d_loop), diag (warp shuffles), the multi-GPU exchange, device libm, data races.  The -m gpu tests remain the parity
+tests proper."""
 import os
 import sys
 
@@ -26,6 +28,9 @@ CASES = {
     "benchmark_p31": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, dj_gradps=0, nonlin_eos=0)),
     "benchmark_splines": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, vadv=3)),
     "benchmark_bvf": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, bv_frequency=1, bvf_mixing=1)),
+    "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, mix_geo_ts=1)),
+    "benchmark_a4": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, hadv=1, vadv=1)),
+    "benchmark_c2": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, hadv=3, vadv=2)),
     "uv_c4": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, uv_adv=1)),
     "uv_c4_seamount": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, uv_adv=1)),
     "uv_sadv": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, uv_adv=2)),
@@ -55,19 +60,63 @@ def test_kernel_source_bit_exact_against_oracle(case, spinup):
     if o.opt("bvf_mixing"):
         phases[phases.index("ana_vmix")] = "bvf_mix"
     ran = 0
+
+    AVG = ("Zt_avg1", "DU_avg1", "DV_avg1", "DU_avg2", "DV_avg2")
+
+    def both(ph, interior_avg=False):
+        for n in names:                                       # the oracle's state BEFORE the phase: every phase is checked on its own
+            t.set(n, o.field(n))
+        t.set_indices(o.indices())
+        o.run_phase(ph); t.run_phase(ph)
+        for n in names:
+            a, b = o.field(n), t.get(n)
+            if interior_avg and n in AVG:
+                # the fast-time averages are only accumulated point by point during the loop: the kernel fills their periodic images in
+                # the last call of the loop (where every consumer finds them), the oracle after every call -- compare i = 1..Lm
+                a, b = a[:, :, 3:-2], b[:, :, 3:-2]
+            if not np.array_equal(a, b):
+                dif = np.abs(a - b)
+                raise AssertionError(f"{case} spinup={spinup} phase {ph} {o.indices()} field {n}: {np.count_nonzero(dif > 0)} points differ, max {np.nanmax(dif)}")
+
     for ph in phases:
-        if ph in EMULATED and not (ph == "t3dmix" and o.opt("mix_geo_ts")):
-            for n in names:                                   # the oracle's state BEFORE the phase: every phase is checked on its own
-                t.set(n, o.field(n))
-            t.set_indices(o.indices())
-            o.run_phase(ph); t.run_phase(ph)
-            for n in names:
-                a, b = o.field(n), t.get(n)
-                if not np.array_equal(a, b):
-                    dif = np.abs(a - b)
-                    raise AssertionError(f"{case} spinup={spinup} phase {ph} field {n}: {np.count_nonzero(dif > 0)} points differ, max {np.nanmax(dif)}")
-            ran += 1
+        if ph == "step2d_loop":
+            # LOOP_2D (main3d.F:592-700) call by call through the oracle's step2d; the first five calls and the last three (the
+            # final corrector and the averaging-only call iif = nfast + 1) also run in the emulation
+            twin = None
+            if spinup == 0:
+                twin = orc.Oracle(app, **kw); twin.run_phase("set_data"); twin.run_phase("ini"); twin.set_indices(o.indices())
+                for n in names:
+                    twin.field(n)[:] = o.field(n)
+                twin.run_phase("step2d_loop")
+            nfast, call, ncall = int(o.opt("nfast")), 0, 2 * int(o.opt("nfast")) + 1
+            d = o.indices(); d["PREDICTOR"] = 0
+
+            def sub():
+                nonlocal call, ran
+                call += 1
+                o.set_indices(d)
+                if call <= 5 or call >= ncall - 2:
+                    both("step2d", interior_avg=(call < ncall)); ran += 1
+                else:
+                    o.run_phase("step2d")
+            for my_iif in range(1, nfast + 2):                # csrc/api.cu loop2d_machine
+                nxt = 3 - d["indx1"]
+                d["PREDICTOR"] = 1; d["iif"] = my_iif
+                d["kstp"] = d["indx1"] if my_iif == 1 else 3 - d["indx1"]; d["knew"] = 3; d["krhs"] = d["indx1"]
+                sub()
+                d["PREDICTOR"] = 0; d["knew"] = nxt; d["kstp"] = 3 - nxt; d["krhs"] = 3
+                if my_iif < nfast + 1:
+                    d["indx1"] = nxt
+                    sub()
+            o.set_indices(d)
+            assert call == ncall
+            if twin is not None:                              # the Python call sequence above IS the oracle's LOOP_2D
+                assert twin.indices() == o.indices()
+                for n in names:
+                    assert np.array_equal(twin.field(n), o.field(n)), n
+        elif ph in EMULATED:
+            both(ph); ran += 1
         else:
             o.run_phase(ph)
-    assert ran >= 13
+    assert ran >= 24
     t.close()
