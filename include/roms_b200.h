@@ -80,7 +80,9 @@ typedef struct roms_b200_config {
   int uv_adv;                   /* momentum advection in rhs3d: 0 the default branch (third-order upstream horizontal, fourth-order
                                    centred vertical), 1 UV_C4ADVECTION (rhs3d.F:685-705, :761-781, :829-849, :902-921, :1108-1175,
                                    :1362-1429; step2d keeps its fourth-order centred default, step2d_LF_AM3.h:1065), 2 UV_SADVECTION
-                                   (default horizontal branch, parabolic splines in the vertical: rhs3d.F:1016-1078, :1267-1329)   */
+                                   (default horizontal branch, parabolic splines in the vertical: rhs3d.F:1016-1078, :1267-1329),
+                                   3 UV_C2ADVECTION (second-order centred in rhs3d.F:605-657, :1079-1107, :1330-1361 AND in step2d,
+                                   step2d_LF_AM3.h:1026-1080; LOOP_2D then runs as per-call kernels)                                */
   int ts_dif4;                  /* TS_DIF4 + MIX_S_TS: biharmonic tracer mixing along s-surfaces (t3dmix4_s.h:215-476), run by
                                    ROMS_B200_T3DMIX after the harmonic operator (rhs3d.F:81-97); field "diff4_<itrc>" =
                                    MIXING%diff4 = SQRT(ABS(tnu4)) (read_phypar.F:6905); not with mix_geo_ts                   */

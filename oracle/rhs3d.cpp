@@ -12,6 +12,7 @@ void rhs3d(Model& m, const Bnd& b) {
   const int N = c.N;
   const double Gadv = -0.25;                                         // rhs3d.F:299
   const bool c4 = (c.uv_adv == 1);                                   // UV_C4ADVECTION
+  const bool c2 = (c.uv_adv == 3);                                   // UV_C2ADVECTION
   const bool sadv = (c.uv_adv == 2);                                 // UV_SADVECTION (horizontal: the default branch)
   SK CF(IminS, ImaxS, 0, N), DC(IminS, ImaxS, 0, N);
   F3 &Hz = m.Hz, &Huon = m.Huon, &Hvom = m.Hvom, &W = m.W;
@@ -50,6 +51,16 @@ void rhs3d(Model& m, const Bnd& b) {
       for (int j = JstrV; j <= Jend; ++j)
         for (int i = Istr; i <= Iend; ++i) { double cff1 = 0.5 * (VFe(i, j) + VFe(i, j - 1)); rv(i, j, k) = rv(i, j, k) - cff1; }
     }
+    if (c2) {                                                                                         // :605-657
+      for (int j = Jstr; j <= Jend; ++j)
+        for (int i = IstrU - 1; i <= Iend; ++i) UFx(i, j) = 0.25 * (u(i, j, k) + u(i + 1, j, k)) * (Huon(i, j, k) + Huon(i + 1, j, k));
+      for (int j = Jstr; j <= Jend + 1; ++j)
+        for (int i = IstrU; i <= Iend; ++i) UFe(i, j) = 0.25 * (u(i, j - 1, k) + u(i, j, k)) * (Hvom(i - 1, j, k) + Hvom(i, j, k));
+      for (int j = JstrV; j <= Jend; ++j)
+        for (int i = Istr; i <= Iend + 1; ++i) VFx(i, j) = 0.25 * (v(i - 1, j, k) + v(i, j, k)) * (Huon(i, j - 1, k) + Huon(i, j, k));
+      for (int j = JstrV - 1; j <= Jend; ++j)
+        for (int i = Istr; i <= Iend; ++i) VFe(i, j) = 0.25 * (v(i, j, k) + v(i, j + 1, k)) * (Hvom(i, j, k) + Hvom(i, j + 1, k));
+    } else {
     // ---- UV_ADV, third-order upstream :658-983
     for (int j = Jstr; j <= Jend; ++j)
       for (int i = IstrUm1; i <= Iendp1; ++i) {
@@ -128,6 +139,7 @@ void rhs3d(Model& m, const Bnd& b) {
         double cff = (cff1 > 0.0) ? vee(i, j) : vee(i, j + 1);
         VFe(i, j) = 0.25 * (cff1 + Gadv * cff) * (Hvom(i, j, k) + Hvom(i, j + 1, k) + Gadv * 0.5 * (Hvee(i, j) + Hvee(i, j + 1)));
       }
+    }
     for (int j = Jstr; j <= Jend; ++j)
       for (int i = IstrU; i <= Iend; ++i) {
         double cff1 = UFx(i, j) - UFx(i - 1, j);
@@ -146,7 +158,13 @@ void rhs3d(Model& m, const Bnd& b) {
 
   // ---- vertical advection + column sums
   for (int j = Jstr; j <= Jend; ++j) {
-    if (sadv) {                                                                                       // :1016-1078: parabolic splines
+    if (c2) {                                                                                         // :1079-1107
+      for (int k = 1; k <= N - 1; ++k)
+        for (int i = IstrU; i <= Iend; ++i) FC(i, k) = 0.25 * (u(i, j, k) + u(i, j, k + 1)) * (W(i, j, k) + W(i - 1, j, k));
+      for (int i = IstrU; i <= Iend; ++i) { FC(i, 0) = 0.0; FC(i, N) = 0.0; }
+      for (int k = 1; k <= N; ++k)
+        for (int i = IstrU; i <= Iend; ++i) { double cff = FC(i, k) - FC(i, k - 1); ru(i, j, k) = ru(i, j, k) - cff; }
+    } else if (sadv) {                                                                                // :1016-1078: parabolic splines
       const double cff1 = 9.0 / 16.0, cff2 = 1.0 / 16.0;
       for (int k = 1; k <= N; ++k)
         for (int i = IstrU; i <= Iend; ++i)
@@ -199,7 +217,13 @@ void rhs3d(Model& m, const Bnd& b) {
       for (int k = 1; k <= N; ++k)
         for (int i = IstrU; i <= Iend; ++i) { double cff = FC(i, k) - FC(i, k - 1); ru(i, j, k) = ru(i, j, k) - cff; }
     }
-    if (j >= JstrV && sadv) {                                                                         // :1267-1329
+    if (j >= JstrV && c2) {                                                                           // :1330-1361
+      for (int k = 1; k <= N - 1; ++k)
+        for (int i = Istr; i <= Iend; ++i) FC(i, k) = 0.25 * (v(i, j, k) + v(i, j, k + 1)) * (W(i, j, k) + W(i, j - 1, k));
+      for (int i = Istr; i <= Iend; ++i) { FC(i, 0) = 0.0; FC(i, N) = 0.0; }
+      for (int k = 1; k <= N; ++k)
+        for (int i = Istr; i <= Iend; ++i) { double cff = FC(i, k) - FC(i, k - 1); rv(i, j, k) = rv(i, j, k) - cff; }
+    } else if (j >= JstrV && sadv) {                                                                  // :1267-1329
       const double cff1 = 9.0 / 16.0, cff2 = 1.0 / 16.0;
       for (int k = 1; k <= N; ++k)
         for (int i = Istr; i <= Iend; ++i)

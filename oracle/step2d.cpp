@@ -148,6 +148,16 @@ void step2d(Model& m, const Bnd& b) {
     }
   }
 
+  if (c.uv_adv == 3) {                                                  // UV_C2ADVECTION :1026-1080
+    for (int j = Jstr; j <= Jend; ++j)
+      for (int i = IstrU - 1; i <= Iend; ++i) UFx(i, j) = 0.25 * (DUon(i, j) + DUon(i + 1, j)) * (ubar_r(i, j) + ubar_r(i + 1, j));
+    for (int j = Jstr; j <= Jend + 1; ++j)
+      for (int i = IstrU; i <= Iend; ++i) UFe(i, j) = 0.25 * (DVom(i, j) + DVom(i - 1, j)) * (ubar_r(i, j) + ubar_r(i, j - 1));
+    for (int j = JstrV; j <= Jend; ++j)
+      for (int i = Istr; i <= Iend + 1; ++i) VFx(i, j) = 0.25 * (DUon(i, j) + DUon(i, j - 1)) * (vbar_r(i, j) + vbar_r(i - 1, j));
+    for (int j = JstrV - 1; j <= Jend; ++j)
+      for (int i = Istr; i <= Iend; ++i) VFe(i, j) = 0.25 * (DVom(i, j) + DVom(i, j + 1)) * (vbar_r(i, j) + vbar_r(i, j + 1));
+  } else {
   // ---- :1081-1283  UV_ADV, fourth-order centred
   for (int j = Jstr; j <= Jend; ++j)
     for (int i = IstrUm1; i <= Iendp1; ++i) {
@@ -198,6 +208,7 @@ void step2d(Model& m, const Bnd& b) {
       for (int i = Istr; i <= Iend; ++i)
         VFe(i, j) = 0.25 * (vbar_r(i, j) + vbar_r(i, j + 1) - cff * (grad(i, j) + grad(i, j + 1))) *
                     (DVom(i, j) + DVom(i, j + 1) - cff * (Dgrad(i, j) + Dgrad(i, j + 1)));
+  }
   }
   for (int j = Jstr; j <= Jend; ++j)
     for (int i = IstrU; i <= Iend; ++i) {

@@ -339,6 +339,7 @@ int build_loop_tables(roms_b200_state* h) {
 
 // LOOP_2D as one persistent kernel when every CTA of the tile can be resident at once.  Returns -1 when not applicable.
 int try_step2d_loop_kernel(roms_b200_state* h) {
+  if (h->cfg.uv_adv == 3) return -1;                         // UV_C2ADVECTION: per-call kernels (the loop kernel carries the default fluxes only)
   if (!h->loop_kernel || h->predictor != 0 || h->indx1 < 1 || h->indx1 > 2 || !h->d_loop_tab[h->indx1] || !h->d_loop_flags) return -1;
   fill_par(h);
   // every tile of a ring must take the same decision (the tail of the exchange protocol differs): decide on the widest tile
@@ -693,7 +694,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   // lmd_skpp reads bvf, alpha / beta, srflx and writes ghats: the switches that provide those arrays must be on with it
   if (cfg->lmd_mixing && !(cfg->bv_frequency && cfg->eos_tderivative && cfg->solar_source && cfg->lmd_nonlocal)) return ConfigError;
   if (cfg->bvf_mixing && !cfg->bv_frequency) return ConfigError;
-  if (cfg->uv_adv < 0 || cfg->uv_adv > 2) return ConfigError;
+  if (cfg->uv_adv < 0 || cfg->uv_adv > 3) return ConfigError;
   if (cfg->ts_dif4 && cfg->mix_geo_ts) return ConfigError;                          // t3dmix4_geo.h is not built
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {

@@ -30,7 +30,8 @@ __device__ __forceinline__ double d2y(const double* __restrict__ A, int o, int P
 #endif
 // UADV: 0 the default branch (third-order upstream horizontal :706-730 ..., fourth-order centred vertical :1177-1255); 1
 // UV_C4ADVECTION (fourth-order centred horizontal :685-705, :761-781, :829-849, :902-921; vertical 9/32, 1/32 :1108-1175, :1362-1429);
-// 2 UV_SADVECTION (the default horizontal branch; conservative parabolic splines in the vertical :1016-1078, :1267-1329).
+// 2 UV_SADVECTION (the default horizontal branch; conservative parabolic splines in the vertical :1016-1078, :1267-1329);
+// 3 UV_C2ADVECTION (second-order centred: horizontal :605-657, vertical :1079-1107, :1330-1361).
 template <int UADV>
 __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,7 +153,10 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
       double c1 = u0 + uE;
       double c = (c1 > 0.0) ? uxx0 : uxxE;
       double UFx0, UFxW;
-      if (UADV == 1) {
+      if (UADV == 3) {
+        UFx0 = 0.25 * (u0 + uE) * (Hu0 + HuE);
+        UFxW = 0.25 * (uW + u0) * (HuW + Hu0);
+      } else if (UADV == 1) {
         UFx0 = 0.25 * (u0 + uE - C6 * (uxx0 + uxxE)) * (Hu0 + HuE - C6 * (Hxx0 + HxxE));
         UFxW = 0.25 * (uW + u0 - C6 * (uxxW + uxx0)) * (HuW + Hu0 - C6 * (HxxW + Hxx0));
       } else {
@@ -168,7 +172,10 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
       const double Hvxx0 = HvW - 2.0 * Hv0 + HvE, HvxxW = HvW2 - 2.0 * HvW + Hv0;
       const double HvxxN = HvNW - 2.0 * HvN + HvNE, HvxxNW = HvNW2 - 2.0 * HvNW + HvN;
       double UFe0, UFeN;
-      if (UADV == 1) {
+      if (UADV == 3) {
+        UFe0 = 0.25 * (uS + u0) * (HvW + Hv0);
+        UFeN = 0.25 * (u0 + uN) * (HvNW + HvN);
+      } else if (UADV == 1) {
         UFe0 = 0.25 * (u0 + uS - C6 * (uee_j + uee_jm1)) * (Hv0 + HvW - C6 * (Hvxx0 + HvxxW));
         UFeN = 0.25 * (uN + u0 - C6 * (uee_jp1 + uee_j)) * (HvN + HvNW - C6 * (HvxxN + HvxxNW));
       } else {
@@ -192,7 +199,10 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
       const double HueeE = HuSE - 2.0 * HuE + HuNE, HueeSE = HuES2 - 2.0 * HuSE + HuE;
       // VFx(i,j), VFx(i+1,j) at psi points
       double c1, c2, c, VFx0, VFxE;
-      if (UADV == 1) {
+      if (UADV == 3) {
+        VFx0 = 0.25 * (vW + v0) * (HuS + Hu0);
+        VFxE = 0.25 * (v0 + vE) * (HuSE + HuE);
+      } else if (UADV == 1) {
         VFx0 = 0.25 * (v0 + vW - C6 * (vxx0 + vxxW)) * (Hu0 + HuS - C6 * (Huee0 + HueeS));
         VFxE = 0.25 * (vE + v0 - C6 * (vxxE + vxx0)) * (HuE + HuSE - C6 * (HueeE + HueeSE));
       } else {
@@ -210,7 +220,10 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
       const double vee_jp = (j < Mm) ? (v0 - 2.0 * vN + vN2) : vee_j, Hvee_jp = (j < Mm) ? (Hv0 - 2.0 * HvN + HvN2) : Hvee_j;
       const double vee_jm = (j > 2) ? (vS2 - 2.0 * vS + v0) : vee_j, Hvee_jm = (j > 2) ? (HvS2 - 2.0 * HvS + Hv0) : Hvee_j;
       double VFe0, VFeS;
-      if (UADV == 1) {
+      if (UADV == 3) {
+        VFe0 = 0.25 * (v0 + vN) * (Hv0 + HvN);
+        VFeS = 0.25 * (vS + v0) * (HvS + Hv0);
+      } else if (UADV == 1) {
         VFe0 = 0.25 * (v0 + vN - C6 * (vee_j + vee_jp)) * (Hv0 + HvN - C6 * (Hvee_j + Hvee_jp));
         VFeS = 0.25 * (vS + v0 - C6 * (vee_jm + vee_j)) * (HvS + Hv0 - C6 * (Hvee_jm + Hvee_j));
       } else {
@@ -232,7 +245,8 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
       if (k < N) {
         const double ukm = (k > 1) ? uDn : u0;
         const double ukpp = (k + 2 <= N) ? uUp2 : uUp;
-        if (UADV == 1) FCu = (c1 * (u0 + uUp) - c2 * (ukm + ukpp)) * (W0 + WW);
+        if (UADV == 3) FCu = 0.25 * (u0 + uUp) * (W0 + WW);                  // rhs3d.F:1080-1088
+        else if (UADV == 1) FCu = (c1 * (u0 + uUp) - c2 * (ukm + ukpp)) * (W0 + WW);
         else if (UADV == 2) {                                               // rhs3d.F:1052-1069
           const double DCk = c1 * (hz0 + hzW) - c2 * (Hz[o + 1] + Hz[o - 2]);
           FCu = (c1 * (W0 + WW) - c2 * (WE + WW2)) * (u0 + DCk * ((1.0 / 3.0) * CFu[k] + (1.0 / 6.0) * CFu[k - 1]));
@@ -241,7 +255,8 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
         if (dov) {
           const double vkm = (k > 1) ? vDn : v0;
           const double vkpp = (k + 2 <= N) ? vUp2 : vUp;
-          if (UADV == 1) FCv = (c1 * (v0 + vUp) - c2 * (vkm + vkpp)) * (W0 + WS);
+          if (UADV == 3) FCv = 0.25 * (v0 + vUp) * (W0 + WS);                // rhs3d.F:1331-1339
+          else if (UADV == 1) FCv = (c1 * (v0 + vUp) - c2 * (vkm + vkpp)) * (W0 + WS);
           else if (UADV == 2) {                                             // rhs3d.F:1303-1320
             const double DCk = (c1 * (hz0 + hzS) - c2 * (Hz[o + P] + Hz[o - 2 * P]));
             FCv = (c1 * (W0 + WS) - c2 * (WN + WS2)) * (v0 + DCk * ((1.0 / 3.0) * CFv[k] + (1.0 / 6.0) * CFv[k - 1]));
@@ -372,6 +387,7 @@ void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s) {
   dim3 b(RHS_BX, 128 / RHS_BX);
   if (p.uv_adv == 1) k_rhs3d<1><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
   else if (p.uv_adv == 2) k_rhs3d<2><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
+  else if (p.uv_adv == 3) k_rhs3d<3><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
   else k_rhs3d<0><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
 }
 void launch_uv3dmix2(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(UVM_BX, 128 / UVM_BX); k_uv3dmix2<<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f); }

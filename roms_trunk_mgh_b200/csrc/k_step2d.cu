@@ -70,7 +70,8 @@ __device__ __forceinline__ double lds_pol(const double* a, unsigned long long po
 template <bool XCH>
 __device__ __forceinline__ double ldt(const double* a) { return XCH ? __ldcg(a) : *a; }
 
-template <bool XCH>      // XCH: with the fused halo exchange (multi-GPU peer path); the single-tile instance carries none of it
+// C2: UV_C2ADVECTION, second-order centred advective fluxes (step2d_LF_AM3.h:1026-1080) instead of the fourth-order centred default
+template <bool XCH, bool C2 = false>   // XCH: with the fused halo exchange (multi-GPU peer path); the single-tile instance carries none of it
 __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x) {
 #if S2D_EVICT
   const unsigned long long l2pol = evict_first_policy();
@@ -300,9 +301,11 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
           }
         }
         // advective UFx at rho(i,j) (:1104-1112)
-        a_ufx = 0.25 * (U_(0, 0) + U_(1, 0) - c6 * (GXU(0, 0) + GXU(1, 0))) * (DU_(0, 0) + DU_(1, 0) - c6 * (GXDU(0, 0) + GXDU(1, 0)));
+        if (C2) a_ufx = 0.25 * (DU_(0, 0) + DU_(1, 0)) * (U_(0, 0) + U_(1, 0));                         // :1027-1038
+        else a_ufx = 0.25 * (U_(0, 0) + U_(1, 0) - c6 * (GXU(0, 0) + GXU(1, 0))) * (DU_(0, 0) + DU_(1, 0) - c6 * (GXDU(0, 0) + GXDU(1, 0)));
         // advective VFe at rho(i,j) (:1263-1272): grad/Dgrad rows 2..Mm with wall copies (1)=(2), (Mm+1)=(Mm)
-        {
+        if (C2) a_vfe = 0.25 * (DV_(0, 0) + DV_(0, 1)) * (V_(0, 0) + V_(0, 1));                         // :1066-1077
+        else {
           const int da = (j < 2) ? 1 : 0, db = (j + 1 > Mm) ? 0 : 1;
           a_vfe = 0.25 * (V_(0, 0) + V_(0, 1) - c6 * (GYV(0, da) + GYV(0, db))) * (DV_(0, 0) + DV_(0, 1) - c6 * (GYDV(0, da) + GYDV(0, db)));
         }
@@ -342,12 +345,14 @@ __global__ void __launch_bounds__(NTH, S2D_MINB) k_step2d(Par p, Flds f, Xchg x)
         const double pn_q = lds_(pn + q), pnS = lds_(pn + q - P), pnW = lds_(pn + q - 1), pnSW = lds_(pn + q - P - 1);
         const double pm_q = lds_(pm + q), pmS = lds_(pm + q - P), pmW = lds_(pm + q - 1), pmSW = lds_(pm + q - P - 1);
         // advective UFe at psi(i,j) (:1141-1150): grad = d2y(ubar), rows 1..Mm with wall copies (0)=(1), (Mm+1)=(Mm)
-        {
+        if (C2) a_ufe = 0.25 * (DV_(0, 0) + DV_(-1, 0)) * (U_(0, 0) + U_(0, -1));                      // :1040-1051
+        else {
           const int d0 = (j > Mm) ? -1 : 0, dm = (j - 1 < 1) ? 0 : -1;
           a_ufe = 0.25 * (U_(0, 0) + U_(0, -1) - c6 * (GYU(0, d0) + GYU(0, dm))) * (DV_(0, 0) + DV_(-1, 0) - c6 * (GXDV(0, 0) + GXDV(-1, 0)));
         }
         // advective VFx at psi(i,j), j = 2..Mm (:1213-1222)
-        a_vfx = 0.25 * (V_(0, 0) + V_(-1, 0) - c6 * (GXV(0, 0) + GXV(-1, 0))) * (DU_(0, 0) + DU_(0, -1) - c6 * (GYDU(0, 0) + GYDU(0, -1)));
+        if (C2) a_vfx = 0.25 * (DU_(0, 0) + DU_(0, -1)) * (V_(0, 0) + V_(-1, 0));                      // :1053-1064
+        else a_vfx = 0.25 * (V_(0, 0) + V_(-1, 0) - c6 * (GXV(0, 0) + GXV(-1, 0))) * (DU_(0, 0) + DU_(0, -1) - c6 * (GYDU(0, 0) + GYDU(0, -1)));
         // viscous stress at psi(i,j) (:1394-1430)
         {
           const double Dp = 0.25 * (D_(0, 0) + D_(-1, 0) + D_(0, -1) + D_(-1, -1));
@@ -533,8 +538,10 @@ void launch_step2d(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x) {
   bool& once = done[cur_dev()];
   if (!once) {
     // 59.6 KB of dynamic shared memory is above the 48 KB default: without the opt-in the launch fails
-    const cudaError_t e1 = cudaFuncSetAttribute(k_step2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const cudaError_t e2 = cudaFuncSetAttribute(k_step2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e1 = cudaFuncSetAttribute(k_step2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e2 = cudaFuncSetAttribute(k_step2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_step2d<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_step2d<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
       std::fprintf(stderr, "roms_b200: cannot opt in to %zu bytes of shared memory for k_step2d: %s\n", smem, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
       return;      // the sticky CUDA error is picked up by the caller's cudaGetLastError (run_phase_async -> exit_flag 8)
@@ -543,6 +550,11 @@ void launch_step2d(const Par& p, const Flds& f, cudaStream_t s, const Xchg* x) {
   }
   Xchg none;
   std::memset(&none, 0, sizeof(none));
+  if (p.uv_adv == 3) {                                                  // UV_C2ADVECTION
+    if (x && (x->send || x->recv)) k_step2d<true, true><<<g, NTH, smem, s>>>(p, f, *x);
+    else k_step2d<false, true><<<g, NTH, smem, s>>>(p, f, none);
+    return;
+  }
   if (x && (x->send || x->recv)) k_step2d<true><<<g, NTH, smem, s>>>(p, f, *x);
   else k_step2d<false><<<g, NTH, smem, s>>>(p, f, none);
 }

@@ -33,6 +33,8 @@ CASES = {
     "benchmark_c2": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, hadv=3, vadv=2)),
     "uv_c4": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, uv_adv=1)),
     "uv_c4_seamount": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, uv_adv=1)),
+    "uv_c2": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, uv_adv=3)),
+    "uv_c2_seamount": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, uv_adv=3)),
     "uv_sadv": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, uv_adv=2)),
     "uv_sadv_seamount": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, uv_adv=2)),
     "ts_dif4": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, ts_dif4=1, tnu4=1.0e15)),

@@ -800,3 +800,41 @@ def test_uv_sadvection_known_answer_and_tiling():
     for n in ("zeta1", "u1", "v1", "t1_0", "ru1", "rufrc"):
         assert np.array_equal(x.field(n), y.field(n)), n
     assert not np.array_equal(x.field("u1"), z.field("u1"))
+
+
+def test_uv_c2advection_known_answer_and_tiling():
+    """rhs3d.F with UV_C2ADVECTION (:605-657, :1079-1107): u a sine in xi under constant Huon = H gives ru = -0.5 H (u(i+1) - u(i-1));
+    u linear in k under uniform W = w gives FC = 0.25 (u(k) + u(k+1)) 2w, so ru = -(FC(k) - FC(k-1)) = -w a;
+    with step2d's C2 branch (step2d_LF_AM3.h:1026-1080) the run is tiling-invariant and differs from the default."""
+    Lm, Mm, N, m = 40, 24, 12, 2
+    o = orc.Oracle(orc.APP_UPWELLING, Lm=Lm, Mm=Mm, N=N, kind="chk", uv_adv=3)
+    o.run_phase("set_data"); o.run_phase("ini")
+    d = o.indices(); d["nstp"] = 1; d["nnew"] = 2; d["nrhs"] = 1; o.set_indices(d)
+    for n in ("fomn", "v1", "Hvom", "W", "ru1", "rv1", "sustr", "svstr", "bustr", "bvstr"):
+        o.field(n)[:] = 0.0
+    H = 3.0e4
+    o.field("Huon")[:] = H
+    u = _wave(o, "u1", m).copy()
+    o.run_phase("rhs3d")
+    LBi, LBj, _ = o.origin("ru1")
+    I = np.arange(1, Lm + 1) - LBi
+    want = -0.5 * H * (u[:, :, I + 1] - u[:, :, I - 1])
+    got = o.field("ru1")[1:, :, :][:, :, I]
+    rows = slice(1 - LBj, Mm + 1 - LBj)                                     # C2 has no wall copies: every row
+    assert np.abs(got[:, rows] - want[:, rows]).max() < 1e-12 * np.abs(want).max()
+    for n in ("Huon", "ru1", "rv1"):
+        o.field(n)[:] = 0.0
+    a, w = 0.01, 2.5
+    o.field("u1")[:] = (a * np.arange(1, N + 1))[:, None, None]
+    o.field("W")[:] = w
+    o.run_phase("rhs3d")
+    got = o.field("ru1")[1:, :, :][:, rows][:, :, I]
+    assert np.abs(got[1:N - 1] + w * a).max() < 1e-14                      # FC(k) - FC(k-1) = 0.5 w (u(k+1) - u(k-1)) = w a
+    assert np.abs(got[0] - (-0.5 * w * (a * 1 + a * 2))).max() < 1e-14     # FC(0) = 0
+    base = dict(Lm=48, Mm=32, N=10, uv_adv=3)
+    x = orc.Oracle(orc.APP_BENCHMARK, kind="chk", **base); x.run_phase("set_data"); x.run_phase("ini"); x.step(10)
+    y = orc.Oracle(orc.APP_BENCHMARK, NtileI=2, NtileJ=2, kind="chk", **base); y.run_phase("set_data"); y.run_phase("ini"); y.step(10, 4)
+    z = orc.Oracle(orc.APP_BENCHMARK, kind="chk", Lm=48, Mm=32, N=10); z.run_phase("set_data"); z.run_phase("ini"); z.step(10)
+    for n in ("zeta1", "ubar1", "u1", "v1", "t1_0", "ru1", "rufrc"):
+        assert np.array_equal(x.field(n), y.field(n)), n
+    assert not np.array_equal(x.field("u1"), z.field("u1")) and not np.array_equal(x.field("ubar1"), z.field("ubar1"))
