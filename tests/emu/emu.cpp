@@ -145,6 +145,8 @@ int emu_run(void* h, int phase) {
     case 14: launch_set_depth(p, f, s); break;
     case 15: launch_step3d_uv(p, f, s); break;
     case 17: launch_step3d_t(p, f, s); break;
+    case 23: launch_bulk_flux(p, f, s); break;
+    case 24: launch_lmd_vmix(p, f, s); break;
     case 25: launch_bvf_mix(p, f, s); break;
     default: return 5;
   }

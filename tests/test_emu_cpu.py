@@ -31,6 +31,10 @@ CASES = {
     "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, mix_geo_ts=1)),
     "benchmark_a4": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, hadv=1, vadv=1)),
     "benchmark_c2": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, hadv=3, vadv=2)),
+    "benchmark_full": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=30, bv_frequency=1, eos_tderivative=1, solar_source=1, lmd_nonlocal=1,
+                                               bulk_fluxes=1, lmd_mixing=1, mix_geo_ts=1)),      # the shipped benchmark.h cpp set
+    "benchmark_full_n12": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=12, bv_frequency=1, eos_tderivative=1, solar_source=1, lmd_nonlocal=1,
+                                                   bulk_fluxes=1, lmd_mixing=1)),
     "uv_c4": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, uv_adv=1)),
     "uv_c4_seamount": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, uv_adv=1)),
     "uv_c2": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, uv_adv=3)),
@@ -57,10 +61,14 @@ def test_kernel_source_bit_exact_against_oracle(case, spinup):
     o.set_indices(d)
     o.run_phase("set_data")
     t = EmuTile(o)
-    names = all_names(int(o.opt("NT"))) + [n for n in optional_names(o) if n not in ("ksbl",)]
+    names = all_names(int(o.opt("NT"))) + optional_names(o)
     phases = list(STEP_PHASES)
     if o.opt("bvf_mixing"):
         phases[phases.index("ana_vmix")] = "bvf_mix"
+    if o.opt("lmd_mixing"):
+        phases[phases.index("ana_vmix")] = "lmd_vmix"
+    if o.opt("bulk_fluxes"):
+        phases.insert(phases.index("set_vbc"), "bulk_flux")
     ran = 0
 
     AVG = ("Zt_avg1", "DU_avg1", "DV_avg1", "DU_avg2", "DV_avg2")
