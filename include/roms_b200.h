@@ -44,7 +44,8 @@ typedef struct roms_b200_config {
   int ndtfast;                  /* NDTFAST; nfast and weights are uploaded with roms_b200_set_weights              */
   double dt;                    /* DT (s)                                                                          */
   int nonlin_eos;               /* NONLIN_EOS (rho_eos.F:111) else linear EOS (rho_eos.F:576)                      */
-  int dj_gradps;                /* DJ_GRADPS -> prsgrd32.h, else prsgrd31.h (prsgrd.F:16-26)                       */
+  int dj_gradps;                /* pressure-gradient algorithm (prsgrd.F:16-26): 1 DJ_GRADPS -> prsgrd32.h, 0 prsgrd31.h, 2 PJ_GRADP ->
+                                   prsgrd40.h (finite-volume Jacobian), 3 WJ_GRADP -> prsgrd31.h with the weighted Jacobian (:236-254)  */
   int curvgrid;                 /* CURVGRID terms (rhs3d.F:515-564, step2d_LF_AM3.h:1333-1382)                     */
   int mix_geo_ts;               /* MIX_GEO_TS -> t3dmix2_geo.h, else MIX_S_TS -> t3dmix2_s.h                       */
   int uv_qdrag;                 /* bottom stress: 0 UV_LDRAG (set_vbc.F:629-652), 1 UV_QDRAG (:591-624), 2 UV_LOGDRAG (:541-586,

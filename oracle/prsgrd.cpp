@@ -1,6 +1,7 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see roms_oracle.hpp).
 // Baroclinic pressure gradient: ROMS/Nonlinear/prsgrd32.h:106-421 (DJ_GRADPS, spline density Jacobian) and
 // ROMS/Nonlinear/prsgrd31.h:97-362 (standard density Jacobian, RHO_SURF on: globaldefs.h:130).
+// WJ_GRADP variant of prsgrd31 (:236-254, :317-335); ROMS/Nonlinear/prsgrd40.h:176-270 (PJ_GRADP, finite-volume pressure Jacobian).
 // Dispatch: ROMS/Nonlinear/prsgrd.F:16-26.  ru,rv(:,:,1:N,nrhs) are overwritten.
 #include "roms_oracle.hpp"
 
@@ -78,7 +79,7 @@ static void prsgrd32(Model& m, const Bnd& b) {
   }
 }
 
-static void prsgrd31(Model& m, const Bnd& b) {
+static void prsgrd31(Model& m, const Bnd& b, bool wj) {
   const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
   const int N = c.N; const double g = c.g, rho0 = c.rho0;
   F3 &rho = m.rho, &z_r = m.z_r, &z_w = m.z_w, &Hz = m.Hz; F3 ru = m.ru[m.nrhs], rv = m.rv[m.nrhs];
@@ -94,10 +95,22 @@ static void prsgrd31(Model& m, const Bnd& b) {
     }
     for (int k = N - 1; k >= 1; --k)
       for (int i = IstrU; i <= Iend; ++i) {
-        double cff1 = rho(i, j, k + 1) - rho(i - 1, j, k + 1) + rho(i, j, k) - rho(i - 1, j, k);
-        double cff2 = rho(i, j, k + 1) + rho(i - 1, j, k + 1) - rho(i, j, k) - rho(i - 1, j, k);
-        double cff3 = z_r(i, j, k + 1) + z_r(i - 1, j, k + 1) - z_r(i, j, k) - z_r(i - 1, j, k);
-        double cff4 = z_r(i, j, k + 1) - z_r(i - 1, j, k + 1) + z_r(i, j, k) - z_r(i - 1, j, k);
+        double cff1, cff2, cff3, cff4;
+        if (wj) {                                                                   // WJ_GRADP :236-254
+          cff1 = 1.0 / ((z_r(i, j, k + 1) - z_r(i, j, k)) * (z_r(i - 1, j, k + 1) - z_r(i - 1, j, k)));
+          cff2 = z_r(i, j, k) - z_r(i - 1, j, k) + z_r(i, j, k + 1) - z_r(i - 1, j, k + 1);
+          cff3 = z_r(i, j, k + 1) - z_r(i, j, k) - z_r(i - 1, j, k + 1) + z_r(i - 1, j, k);
+          const double gamma = 0.125 * cff1 * cff2 * cff3;
+          cff1 = (1.0 + gamma) * (rho(i, j, k + 1) - rho(i - 1, j, k + 1)) + (1.0 - gamma) * (rho(i, j, k) - rho(i - 1, j, k));
+          cff2 = rho(i, j, k + 1) + rho(i - 1, j, k + 1) - rho(i, j, k) - rho(i - 1, j, k);
+          cff3 = z_r(i, j, k + 1) + z_r(i - 1, j, k + 1) - z_r(i, j, k) - z_r(i - 1, j, k);
+          cff4 = (1.0 + gamma) * (z_r(i, j, k + 1) - z_r(i - 1, j, k + 1)) + (1.0 - gamma) * (z_r(i, j, k) - z_r(i - 1, j, k));
+        } else {
+        cff1 = rho(i, j, k + 1) - rho(i - 1, j, k + 1) + rho(i, j, k) - rho(i - 1, j, k);
+        cff2 = rho(i, j, k + 1) + rho(i - 1, j, k + 1) - rho(i, j, k) - rho(i - 1, j, k);
+        cff3 = z_r(i, j, k + 1) + z_r(i - 1, j, k + 1) - z_r(i, j, k) - z_r(i - 1, j, k);
+        cff4 = z_r(i, j, k + 1) - z_r(i - 1, j, k + 1) + z_r(i, j, k) - z_r(i - 1, j, k);
+        }
         phix[i] = phix[i] + fac3 * (cff1 * cff3 - cff2 * cff4);
         ru(i, j, k) = -0.5 * (Hz(i, j, k) + Hz(i - 1, j, k)) * phix[i] * m.on_u(i, j);
       }
@@ -110,10 +123,22 @@ static void prsgrd31(Model& m, const Bnd& b) {
       }
       for (int k = N - 1; k >= 1; --k)
         for (int i = Istr; i <= Iend; ++i) {
-          double cff1 = rho(i, j, k + 1) - rho(i, j - 1, k + 1) + rho(i, j, k) - rho(i, j - 1, k);
-          double cff2 = rho(i, j, k + 1) + rho(i, j - 1, k + 1) - rho(i, j, k) - rho(i, j - 1, k);
-          double cff3 = z_r(i, j, k + 1) + z_r(i, j - 1, k + 1) - z_r(i, j, k) - z_r(i, j - 1, k);
-          double cff4 = z_r(i, j, k + 1) - z_r(i, j - 1, k + 1) + z_r(i, j, k) - z_r(i, j - 1, k);
+          double cff1, cff2, cff3, cff4;
+          if (wj) {                                                                 // WJ_GRADP :317-335
+            cff1 = 1.0 / ((z_r(i, j, k + 1) - z_r(i, j, k)) * (z_r(i, j - 1, k + 1) - z_r(i, j - 1, k)));
+            cff2 = z_r(i, j, k) - z_r(i, j - 1, k) + z_r(i, j, k + 1) - z_r(i, j - 1, k + 1);
+            cff3 = z_r(i, j, k + 1) - z_r(i, j, k) - z_r(i, j - 1, k + 1) + z_r(i, j - 1, k);
+            const double gamma = 0.125 * cff1 * cff2 * cff3;
+            cff1 = (1.0 + gamma) * (rho(i, j, k + 1) - rho(i, j - 1, k + 1)) + (1.0 - gamma) * (rho(i, j, k) - rho(i, j - 1, k));
+            cff2 = rho(i, j, k + 1) + rho(i, j - 1, k + 1) - rho(i, j, k) - rho(i, j - 1, k);
+            cff3 = z_r(i, j, k + 1) + z_r(i, j - 1, k + 1) - z_r(i, j, k) - z_r(i, j - 1, k);
+            cff4 = (1.0 + gamma) * (z_r(i, j, k + 1) - z_r(i, j - 1, k + 1)) + (1.0 - gamma) * (z_r(i, j, k) - z_r(i, j - 1, k));
+          } else {
+          cff1 = rho(i, j, k + 1) - rho(i, j - 1, k + 1) + rho(i, j, k) - rho(i, j - 1, k);
+          cff2 = rho(i, j, k + 1) + rho(i, j - 1, k + 1) - rho(i, j, k) - rho(i, j - 1, k);
+          cff3 = z_r(i, j, k + 1) + z_r(i, j - 1, k + 1) - z_r(i, j, k) - z_r(i, j - 1, k);
+          cff4 = z_r(i, j, k + 1) - z_r(i, j - 1, k + 1) + z_r(i, j, k) - z_r(i, j - 1, k);
+          }
           phie[i] = phie[i] + fac3 * (cff1 * cff3 - cff2 * cff4);
           rv(i, j, k) = -0.5 * (Hz(i, j, k) + Hz(i, j - 1, k)) * phie[i] * m.om_v(i, j);
         }
@@ -121,8 +146,53 @@ static void prsgrd31(Model& m, const Bnd& b) {
   }
 }
 
+// prsgrd40_tile (ROMS/Nonlinear/prsgrd40.h:176-270; PJ_GRADP): finite-volume pressure Jacobian (Lin, 1997)
+static void prsgrd40(Model& m, const Bnd& b) {
+  const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
+  const int N = c.N; const double g = c.g, rho0 = c.rho0;
+  F3 &rho = m.rho, &z_w = m.z_w, &Hz = m.Hz; F3 ru = m.ru[m.nrhs], rv = m.rv[m.nrhs];
+  SK FC(IminS, ImaxS, 0, N);
+  S3 FX(IminS, ImaxS, JminS, JmaxS, 1, N), P(IminS, ImaxS, JminS, JmaxS, 0, N);
+  for (int j = JstrV - 1; j <= Jend; ++j) {
+    for (int i = IstrU - 1; i <= Iend; ++i) P(i, j, N) = 0.0;
+    for (int k = N; k >= 1; --k)
+      for (int i = IstrU - 1; i <= Iend; ++i) {
+        P(i, j, k - 1) = P(i, j, k) + Hz(i, j, k) * rho(i, j, k);
+        FX(i, j, k) = 0.5 * Hz(i, j, k) * (P(i, j, k) + P(i, j, k - 1));
+      }
+    if (j >= Jstr) {
+      for (int i = IstrU; i <= Iend; ++i) FC(i, N) = 0.0;
+      const double cff = 0.5 * g, cff1 = g / rho0;
+      for (int k = N; k >= 1; --k)
+        for (int i = IstrU; i <= Iend; ++i) {
+          const double dh = z_w(i, j, k - 1) - z_w(i - 1, j, k - 1);
+          FC(i, k - 1) = 0.5 * dh * (P(i, j, k - 1) + P(i - 1, j, k - 1));
+          ru(i, j, k) = (cff * (Hz(i - 1, j, k) + Hz(i, j, k)) * (z_w(i - 1, j, N) - z_w(i, j, N)) +
+                         cff1 * (FX(i - 1, j, k) - FX(i, j, k) + FC(i, k) - FC(i, k - 1))) * m.on_u(i, j);
+        }
+    }
+    if (j >= JstrV) {
+      for (int i = Istr; i <= Iend; ++i) FC(i, N) = 0.0;
+      const double cff = 0.5 * g, cff1 = g / rho0;
+      for (int k = N; k >= 1; --k)
+        for (int i = Istr; i <= Iend; ++i) {
+          const double dh = z_w(i, j, k - 1) - z_w(i, j - 1, k - 1);
+          FC(i, k - 1) = 0.5 * dh * (P(i, j, k - 1) + P(i, j - 1, k - 1));
+          rv(i, j, k) = (cff * (Hz(i, j - 1, k) + Hz(i, j, k)) * (z_w(i, j - 1, N) - z_w(i, j, N)) +
+                         cff1 * (FX(i, j - 1, k) - FX(i, j, k) + FC(i, k) - FC(i, k - 1))) * m.om_v(i, j);
+        }
+    }
+  }
+}
+
+// prsgrd.F:16-26.  dj_gradps: 0 prsgrd31, 1 DJ_GRADPS prsgrd32, 2 PJ_GRADP prsgrd40, 3 WJ_GRADP (prsgrd31 with the weighted Jacobian)
 void prsgrd(Model& m, const Bnd& b) {
-  if (m.c.dj_gradps) prsgrd32(m, b); else prsgrd31(m, b);
+  switch (m.c.dj_gradps) {
+    case 1: prsgrd32(m, b); break;
+    case 2: prsgrd40(m, b); break;
+    case 3: prsgrd31(m, b, true); break;
+    default: prsgrd31(m, b, false);
+  }
 }
 
 }  // namespace orc

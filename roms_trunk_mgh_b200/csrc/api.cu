@@ -432,7 +432,7 @@ int run_phase_async(roms_b200_state* h, int phase) {
       h->par.fuse_tmix = 0;
       launch_full(h, [&](const Par& q, cudaStream_t st) { launch_pre_step3d_uv(q, f, st); });
       h->launches += 2; break;
-    case ROMS_B200_PRSGRD: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_prsgrd(q, f, h->cfg.dj_gradps, st); }); h->launches += h->cfg.dj_gradps ? 2 : 1; break;
+    case ROMS_B200_PRSGRD: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_prsgrd(q, f, h->cfg.dj_gradps, st); }); h->launches += h->cfg.dj_gradps == 1 ? 2 : 1; break;
     case ROMS_B200_T3DMIX:
       if (fused_tmix(h)) {                                                          // t3dmix2_s already applied by pre_step3d_t
         if (h->cfg.ts_dif4) { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix4_s(q, f, st); }); h->launches += 1; }
@@ -695,6 +695,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   if (cfg->lmd_mixing && !(cfg->bv_frequency && cfg->eos_tderivative && cfg->solar_source && cfg->lmd_nonlocal)) return ConfigError;
   if (cfg->bvf_mixing && !cfg->bv_frequency) return ConfigError;
   if (cfg->uv_adv < 0 || cfg->uv_adv > 3) return ConfigError;
+  if (cfg->dj_gradps < 0 || cfg->dj_gradps > 3) return ConfigError;
   if (cfg->ts_dif4 && cfg->mix_geo_ts) return ConfigError;                          // t3dmix4_geo.h is not built
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {

@@ -365,6 +365,8 @@ __global__ void __launch_bounds__(256) k_prsgrd32_R(Par p, Flds f) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // prsgrd31_tile (ROMS/Nonlinear/prsgrd31.h:203-359): standard density Jacobian, RHO_SURF on.  Thread per column.
+// WJ: the weighted Jacobian of Song & Wright (WJ_GRADP, :236-254, :317-335).
+template <bool WJ>
 __global__ void __launch_bounds__(128) k_prsgrd31(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -387,13 +389,69 @@ __global__ void __launch_bounds__(128) k_prsgrd31(Par p, Flds f) {
     R[oN] = -0.5 * (Hz[oN] + Hz[oN - s]) * phi * met;
     for (int k = N - 1; k >= 1; --k) {
       const int o = o2 + k * p.PL + i, ou = o + p.PL;
-      const double c1 = rho[ou] - rho[ou - s] + rho[o] - rho[o - s];
+      double c1, c4;
+      if (WJ) {
+        const double w1 = 1.0 / ((z_r[ou] - z_r[o]) * (z_r[ou - s] - z_r[o - s]));
+        const double w2 = z_r[o] - z_r[o - s] + z_r[ou] - z_r[ou - s];
+        const double w3 = z_r[ou] - z_r[o] - z_r[ou - s] + z_r[o - s];
+        const double gamma = 0.125 * w1 * w2 * w3;
+        c1 = (1.0 + gamma) * (rho[ou] - rho[ou - s]) + (1.0 - gamma) * (rho[o] - rho[o - s]);
+        c4 = (1.0 + gamma) * (z_r[ou] - z_r[ou - s]) + (1.0 - gamma) * (z_r[o] - z_r[o - s]);
+      } else {
+        c1 = rho[ou] - rho[ou - s] + rho[o] - rho[o - s];
+        c4 = z_r[ou] - z_r[ou - s] + z_r[o] - z_r[o - s];
+      }
       const double c2 = rho[ou] + rho[ou - s] - rho[o] - rho[o - s];
       const double c3 = z_r[ou] + z_r[ou - s] - z_r[o] - z_r[o - s];
-      const double c4 = z_r[ou] - z_r[ou - s] + z_r[o] - z_r[o - s];
       phi = phi + fac3 * (c1 * c3 - c2 * c4);
       R[o] = -0.5 * (Hz[o] + Hz[o - s]) * phi * met;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prsgrd40_tile (ROMS/Nonlinear/prsgrd40.h:176-270; PJ_GRADP): finite-volume pressure Jacobian (Lin, 1997).  Thread per column,
+// marching downward: the hydrostatic sums P of the column and of its western and southern neighbours are carried in registers
+// (the reference keeps a private 3-D P; each neighbour sum is re-accumulated by the same expression, so it is bit-identical),
+// with the face integrals FC(k) of the two directions.  No divisions; rho, Hz, z_w are each read once per column they belong to.
+__global__ void __launch_bounds__(128) k_prsgrd40(Par p, Flds f) {
+  const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > p.Iend || j > p.Mm) return;
+  const int N = p.N, P = p.P, o2 = j * P + i;
+  const double* __restrict__ rho = f.rho;
+  const double* __restrict__ z_w = f.z_w;
+  const double* __restrict__ Hz = f.Hz;
+  double* __restrict__ ru = f.ru[p.nrhs];
+  double* __restrict__ rv = f.rv[p.nrhs];
+  const bool dov = (j >= p.JstrV);
+  const double cff = 0.5 * p.g, cff1 = p.g / p.rho0;
+  const double on_u = f.on_u[o2], om_v = f.om_v[o2];
+  const int oN = o2 + N * p.PL;
+  const double dzu = z_w[oN - 1] - z_w[oN], dzv = z_w[oN - P] - z_w[oN];          // z_w(i-1,j,N) - z_w(i,j,N), z_w(i,j-1,N) - z_w(i,j,N)
+  double P0 = 0.0, PW = 0.0, PS = 0.0, FCu = 0.0, FCv = 0.0;
+  for (int k = N; k >= 1; --k) {
+    const int o = o2 + k * p.PL, od = o - p.PL;
+    const double hz0 = Hz[o], hzW = Hz[o - 1];
+    const double P0n = P0 + hz0 * rho[o], PWn = PW + hzW * rho[o - 1];
+    const double FX0 = 0.5 * hz0 * (P0 + P0n), FXW = 0.5 * hzW * (PW + PWn);
+    const double zw0 = z_w[od];
+    {
+      const double dh = zw0 - z_w[od - 1];
+      const double FCn = 0.5 * dh * (P0n + PWn);
+      ru[o] = (cff * (hzW + hz0) * dzu + cff1 * (FXW - FX0 + FCu - FCn)) * on_u;
+      FCu = FCn;
+    }
+    if (dov) {
+      const double hzS = Hz[o - P];
+      const double PSn = PS + hzS * rho[o - P];
+      const double FXS = 0.5 * hzS * (PS + PSn);
+      const double dh = zw0 - z_w[od - P];
+      const double FCn = 0.5 * dh * (P0n + PSn);
+      rv[o] = (cff * (hzS + hz0) * dzv + cff1 * (FXS - FX0 + FCv - FCn)) * om_v;
+      FCv = FCn; PS = PSn;
+    }
+    P0 = P0n; PW = PWn;
   }
 }
 
@@ -543,14 +601,18 @@ void launch_pre_step3d_uv(const Par& p, const Flds& f, cudaStream_t s) {
   k_pre_step3d_uv<<<g2(p, b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
 }
 void launch_prsgrd(const Par& p, const Flds& f, int dj_gradps, cudaStream_t s) {
-  if (dj_gradps) {
+  if (dj_gradps == 2) {                                                  // PJ_GRADP
+    dim3 b(64, 2);
+    k_prsgrd40<<<g2(p, b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
+  } else if (dj_gradps == 1) {
     dim3 b(64, 2);
     k_prsgrd32_P<<<g2(p, b, p.Iend - p.Istr + 2, p.Mm), b, 0, s>>>(p, f);
     dim3 b2(64, 4);
     k_prsgrd32_R<<<g2(p, b2, p.Iend - p.Istr + 1, p.Mm, p.N), b2, 0, s>>>(p, f);
   } else {
     dim3 b(64, 2);
-    k_prsgrd31<<<g2(p, b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
+    if (dj_gradps == 3) k_prsgrd31<true><<<g2(p, b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);     // WJ_GRADP
+    else k_prsgrd31<false><<<g2(p, b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
   }
 }
 void launch_t3dmix4_s(const Par& p, const Flds& f, cudaStream_t s) {

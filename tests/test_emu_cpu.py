@@ -26,6 +26,10 @@ CASES = {
     "upwelling": (orc.APP_UPWELLING, dict(Lm=20, Mm=24, N=8)),
     "benchmark": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7)),
     "benchmark_p31": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, dj_gradps=0, nonlin_eos=0)),
+    "benchmark_p40": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, dj_gradps=2)),                       # PJ_GRADP (prsgrd40.h)
+    "seamount_p40": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, dj_gradps=2)),
+    "benchmark_wj": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, dj_gradps=3)),                        # WJ_GRADP (prsgrd31.h, weighted)
+    "seamount_wj": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, dj_gradps=3)),
     "benchmark_splines": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, vadv=3)),
     "benchmark_bvf": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, bv_frequency=1, bvf_mixing=1)),
     "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, mix_geo_ts=1)),

@@ -838,3 +838,39 @@ def test_uv_c2advection_known_answer_and_tiling():
     for n in ("zeta1", "ubar1", "u1", "v1", "t1_0", "ru1", "rufrc"):
         assert np.array_equal(x.field(n), y.field(n)), n
     assert not np.array_equal(x.field("u1"), z.field("u1")) and not np.array_equal(x.field("ubar1"), z.field("ubar1"))
+
+
+def test_prsgrd_variants_known_answers():
+    """prsgrd.F dispatch (dj_gradps = 0 prsgrd31, 1 prsgrd32, 2 PJ_GRADP prsgrd40, 3 WJ_GRADP) on the SEAMOUNT grid at rest:
+    (1) for rho = a + b z the standard and the weighted density Jacobians cancel below the surface layer (the discrete J(rho, z) of a
+    function of z vanishes term by term: prsgrd31.h:236-262), whatever the slope of the s-surfaces: phix stays at its surface value; (2) for the shipped exponential stratification
+    the spurious force of prsgrd32 is an order of magnitude below that of the three second-order schemes, which differ from one another
+    by less than a factor two;
+    (3) every variant is tiling-invariant over 3 steps."""
+    err = {}
+    for alg in (0, 1, 2, 3):
+        o = orc.Oracle(orc.APP_SEAMOUNT, kind="chk", dj_gradps=alg)
+        o.run_phase("set_data"); o.run_phase("ini")
+        d = o.indices(); d["nstp"] = 1; d["nnew"] = 2; d["nrhs"] = 1; o.set_indices(d)
+        N, Lm, Mm = int(o.opt("N")), int(o.opt("Lm")), int(o.opt("Mm"))
+        LBi, LBj, _ = o.origin("ru1")
+        box = (slice(1, N + 1), slice(2 - LBj, Mm - LBj), slice(1 - LBi, Lm + 1 - LBi))
+        o.run_phase("rho_eos"); o.run_phase("prsgrd")
+        err[alg] = np.abs(o.field("ru1")[box]).max()
+        if alg in (0, 3):
+            o.field("rho")[:] = 3.0 - 2.0e-3 * o.field("z_r")
+            o.run_phase("prsgrd")
+            # ru(k) = -0.5 (Hz(i) + Hz(i-1)) phix(k) on_u: phix keeps its surface value (the top half-layer term) at every level
+            Hz = o.field("Hz"); hzu = Hz + np.roll(Hz, 1, axis=2)
+            phix = o.field("ru1")[1:] / (-0.5 * hzu * o.field("on_u"))
+            I = slice(1 - LBi, Lm + 1 - LBi); J = slice(1 - LBj, Mm + 1 - LBj)
+            drift = np.abs(phix[:, J, I] - phix[N - 1:N, J, I]).max()
+            # each product of the Jacobian is O(fac3 * 1 kg/m3 * 500 m) ~ 1: a drift of 1e-11 is rounding, the surface term is 1e-5
+            assert np.abs(phix[N - 1, J, I]).max() > 1e-6 and drift < 1e-11, (alg, drift)
+    assert 0 < err[1] < 0.1 * min(err[0], err[2], err[3]), err              # the spline Jacobian is an order of magnitude better
+    assert max(err[0], err[2], err[3]) < 2.0 * min(err[0], err[2], err[3]) and len({err[0], err[2], err[3]}) == 3, err
+    for alg in (2, 3):
+        a = orc.Oracle(orc.APP_SEAMOUNT, kind="chk", dj_gradps=alg); a.run_phase("set_data"); a.run_phase("ini"); a.step(3)
+        b = orc.Oracle(orc.APP_SEAMOUNT, NtileI=2, NtileJ=2, kind="chk", dj_gradps=alg); b.run_phase("set_data"); b.run_phase("ini"); b.step(3, 4)
+        for n in ("zeta1", "u1", "v1", "ru1", "rv1", "t1_0"):
+            assert np.array_equal(a.field(n), b.field(n)), (alg, n)

@@ -22,6 +22,10 @@ VARIANTS = {
     "uv_c4_seamount": (orc.APP_SEAMOUNT, dict(uv_adv=1)),                                   # no-slip walls, NT = 1
     "uv_c2": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, uv_adv=3)),                        # UV_C2ADVECTION: rhs3d AND step2d (per-call kernels)
     "uv_c2_seamount": (orc.APP_SEAMOUNT, dict(uv_adv=3)),
+    "p40": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, dj_gradps=2)),                         # PJ_GRADP: prsgrd40.h
+    "p40_seamount": (orc.APP_SEAMOUNT, dict(dj_gradps=2)),
+    "wj": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, dj_gradps=3)),                          # WJ_GRADP: prsgrd31.h, weighted Jacobian
+    "wj_seamount": (orc.APP_SEAMOUNT, dict(dj_gradps=3)),
     "uv_sadv": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, uv_adv=2)),                      # UV_SADVECTION: spline vertical advection
     "uv_sadv_seamount": (orc.APP_SEAMOUNT, dict(uv_adv=2)),
     "ts_dif4": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, ts_dif4=1, tnu4=TNU4)),
@@ -44,7 +48,7 @@ def test_variants_strict_bit_exact_every_phase(case, spinup):
     t.close()
 
 
-@pytest.mark.parametrize("case", ["uv_c4", "uv_c2", "uv_sadv", "ts_dif4", "both_n30"])
+@pytest.mark.parametrize("case", ["uv_c4", "uv_c2", "uv_sadv", "p40", "wj", "ts_dif4", "both_n30"])
 def test_variants_strict_bit_exact_multistep(case):
     """Whole steps (the captured step graph; t3dmix2_s fused into pre_step3d_t with t3dmix4_s behind it)."""
     app, kw = VARIANTS[case]
