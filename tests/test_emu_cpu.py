@@ -134,3 +134,48 @@ def test_kernel_source_bit_exact_against_oracle(case, spinup):
             o.run_phase(ph)
     assert ran >= 24
     t.close()
+
+
+@pytest.mark.parametrize("case", ["seamount", "benchmark", "benchmark_geo", "uv_c2", "ts_dif4", "benchmark_p40"])
+def test_kernel_chain_whole_steps_without_resync(case):
+    """Two whole baroclinic steps with the state kept in the emulated device arrays (no re-upload between phases, LOOP_2D as
+    2 nfast + 1 per-call launches): every ghost row / periodic image / wall value that a later kernel consumes must have been
+    written by the kernel that produces it.  Only the forcing (set_data) comes from the oracle, as in the resident C-ABI form."""
+    app, kw = CASES[case]
+    o = orc.Oracle(app, **kw)
+    o.run_phase("set_data"); o.run_phase("ini")
+    t = EmuTile(o)
+    names = all_names(int(o.opt("NT"))) + optional_names(o)
+    for n in names:
+        t.set(n, o.field(n))
+    nfast = int(o.opt("nfast"))
+    for step in range(2):
+        d = o.indices()
+        d["nstp"] = 1 + ((d["iic"] - d["ntstart"]) % 2); d["nnew"] = 3 - d["nstp"]; d["nrhs"] = d["nstp"]
+        d["tdays"] = d["time"] / 86400.0
+        o.set_indices(d)
+        o.run_phase("set_data")
+        t.set("sustr", o.field("sustr")); t.set("svstr", o.field("svstr"))
+        for ph in STEP_PHASES:
+            if ph == "step2d_loop":
+                e = o.indices(); e["PREDICTOR"] = 0
+                for my_iif in range(1, nfast + 2):            # csrc/api.cu loop2d_machine
+                    nxt = 3 - e["indx1"]
+                    e["PREDICTOR"] = 1; e["iif"] = my_iif
+                    e["kstp"] = e["indx1"] if my_iif == 1 else 3 - e["indx1"]; e["knew"] = 3; e["krhs"] = e["indx1"]
+                    t.set_indices(e); t.run_phase("step2d")
+                    e["PREDICTOR"] = 0; e["knew"] = nxt; e["kstp"] = 3 - nxt; e["krhs"] = 3
+                    if my_iif < nfast + 1:
+                        e["indx1"] = nxt
+                        t.set_indices(e); t.run_phase("step2d")
+                o.run_phase("step2d_loop")
+                assert {k: o.indices()[k] for k in ("indx1", "kstp", "krhs", "knew")} == {k: e[k] for k in ("indx1", "kstp", "krhs", "knew")}
+            else:
+                t.set_indices(o.indices())
+                o.run_phase(ph); t.run_phase(ph)
+        # advance the oracle's clock exactly as main3d does at the end of a step
+        d = o.indices(); d["iic"] += 1; d["time"] += o.opt("dt"); o.set_indices(d)
+        for n in names:
+            a, b = o.field(n), t.get(n)
+            assert np.array_equal(a, b), f"{case} step {step} field {n}: {np.count_nonzero(a != b)} points differ"
+    t.close()
