@@ -84,8 +84,8 @@ typedef struct roms_b200_config {
                                    (default horizontal branch, parabolic splines in the vertical: rhs3d.F:1016-1078, :1267-1329),
                                    3 UV_C2ADVECTION (second-order centred in rhs3d.F:605-657, :1079-1107, :1330-1361 AND in step2d,
                                    step2d_LF_AM3.h:1026-1080; LOOP_2D then runs as per-call kernels)                                */
-  int ts_dif4;                  /* TS_DIF4 + MIX_S_TS: biharmonic tracer mixing along s-surfaces (t3dmix4_s.h:215-476), run by
-                                   ROMS_B200_T3DMIX after the harmonic operator (rhs3d.F:81-97); field "diff4_<itrc>" =
+  int ts_dif4;                  /* TS_DIF4 + MIX_S_TS: biharmonic tracer mixing along s-surfaces (t3dmix4_s.h:215-476), phase
+                                   ROMS_B200_T3DMIX4, after the harmonic operator (rhs3d.F:81-97); field "diff4_<itrc>" =
                                    MIXING%diff4 = SQRT(ABS(tnu4)) (read_phypar.F:6905); not with mix_geo_ts                   */
 } roms_b200_config;
 
@@ -147,7 +147,8 @@ enum {
   ROMS_B200_SET_AVG = 22,      /* set_avg.F:128          */
   ROMS_B200_BULK_FLUX = 23,    /* bulk_flux.F:59         */
   ROMS_B200_LMD_VMIX = 24,     /* lmd_vmix.F:33 (lmd_vmix_tile, lmd_skpp, lmd_finish) */
-  ROMS_B200_BVF_MIX = 25       /* bvf_mix.F:27           */
+  ROMS_B200_BVF_MIX = 25,      /* bvf_mix.F:27           */
+  ROMS_B200_T3DMIX4 = 26       /* t3dmix4_s.h:41 (TS_DIF4 + MIX_S_TS; rhs3d.F:89-97) */
 };
 int roms_b200_run_phase(roms_b200_handle h, int phase);
 

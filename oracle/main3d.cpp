@@ -159,7 +159,8 @@ void run_phase(Model& m, int phase, int nthreads) {
     case PH_SET_AVG: for_tiles(m, nthreads, [&](const Bnd& b) { set_avg(m, b); }); break;
     case PH_PRE_STEP3D: for_tiles(m, nthreads, [&](const Bnd& b) { pre_step3d(m, b); }); break;
     case PH_PRSGRD: for_tiles(m, nthreads, [&](const Bnd& b) { prsgrd(m, b); }); break;
-    case PH_T3DMIX: for_tiles(m, nthreads, [&](const Bnd& b) { t3dmix2(m, b); if (m.c.ts_dif4) t3dmix4(m, b); }); break;   // rhs3d.F:81-97
+    case PH_T3DMIX: for_tiles(m, nthreads, [&](const Bnd& b) { t3dmix2(m, b); }); break;                              // rhs3d.F:81-88
+    case PH_T3DMIX4: if (m.c.ts_dif4) for_tiles(m, nthreads, [&](const Bnd& b) { t3dmix4(m, b); }); break;            // rhs3d.F:89-97
     case PH_RHS3D: for_tiles(m, nthreads, [&](const Bnd& b) { rhs3d(m, b); }); break;
     case PH_UV3DMIX: for_tiles(m, nthreads, [&](const Bnd& b) { uv3dmix2(m, b); }); break;
     case PH_STEP2D: for_tiles(m, nthreads, [&](const Bnd& b) { step2d(m, b); }); break;

@@ -287,7 +287,7 @@ enum Phase {
   PH_SET_MASSFLUX = 1, PH_RHO_EOS = 2, PH_SET_VBC = 3, PH_ANA_VMIX = 4, PH_OMEGA = 5, PH_WVELOCITY = 6, PH_SET_ZETA = 7,
   PH_PRE_STEP3D = 8, PH_PRSGRD = 9, PH_T3DMIX = 10, PH_RHS3D = 11, PH_UV3DMIX = 12, PH_STEP2D = 13, PH_SET_DEPTH = 14,
   PH_STEP3D_UV = 15, PH_OMEGA2 = 16, PH_STEP3D_T = 17, PH_DIAG = 18, PH_SET_DATA = 19, PH_STEP2D_LOOP = 20, PH_INI = 21, PH_SET_AVG = 22,
-  PH_BULK_FLUX = 23, PH_LMD_VMIX = 24, PH_BVF_MIX = 25
+  PH_BULK_FLUX = 23, PH_LMD_VMIX = 24, PH_BVF_MIX = 25, PH_T3DMIX4 = 26
 };
 void run_phase(Model& m, int phase, int nthreads);
 void main3d_step(Model& m, int nthreads);    // one baroclinic step (main3d.F:189-917)

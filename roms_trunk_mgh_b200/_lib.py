@@ -35,7 +35,7 @@ class TileArgs(C.Structure):
 
 PHASES = dict(set_massflux=1, rho_eos=2, set_vbc=3, ana_vmix=4, omega=5, wvelocity=6, set_zeta=7, pre_step3d=8, prsgrd=9,
               t3dmix=10, rhs3d=11, uv3dmix=12, step2d=13, set_depth=14, step3d_uv=15, omega2=16, step3d_t=17, diag=18,
-              set_data=19, step2d_loop=20, set_avg=22, bulk_flux=23, lmd_vmix=24, bvf_mix=25)
+              set_data=19, step2d_loop=20, set_avg=22, bulk_flux=23, lmd_vmix=24, bvf_mix=25, t3dmix4=26)
 INDEX_NAMES = ["iic", "ntstart", "ntfirst", "nstp", "nnew", "nrhs", "iif", "indx1", "kstp", "krhs", "knew", "PREDICTOR", "exit_flag"]
 DIAG_NAMES = ["avgke", "avgpe", "avgkp", "volume", "max_speed", "maxCu", "maxCv", "maxCw", "ubarmax", "vbarmax", "umax", "vmax"]
 

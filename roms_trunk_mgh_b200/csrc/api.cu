@@ -434,14 +434,14 @@ int run_phase_async(roms_b200_state* h, int phase) {
       h->launches += 2; break;
     case ROMS_B200_PRSGRD: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_prsgrd(q, f, h->cfg.dj_gradps, st); }); h->launches += h->cfg.dj_gradps == 1 ? 2 : 1; break;
     case ROMS_B200_T3DMIX:
-      if (fused_tmix(h)) {                                                          // t3dmix2_s already applied by pre_step3d_t
-        if (h->cfg.ts_dif4) { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix4_s(q, f, st); }); h->launches += 1; }
-        break;
-      }
+      if (fused_tmix(h)) break;                                                     // already applied by pre_step3d_t
       if (h->cfg.mix_geo_ts) {
         if (!h->all_diff2_zero) { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix2_geo(q, f, st); }); h->launches += 1; }   // diff2 == 0: exact no-op
       } else { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix2_s(q, f, st); }); h->launches += 1; }
-      if (h->cfg.ts_dif4) { launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix4_s(q, f, st); }); h->launches += 1; }   // rhs3d.F:90-97
+      break;
+    case ROMS_B200_T3DMIX4:                                                         // rhs3d.F:89-97
+      if (!h->cfg.ts_dif4) return ConfigError;
+      launch_full(h, [&](const Par& q, cudaStream_t st) { launch_t3dmix4_s(q, f, st); }); h->launches += 1;
       break;
     case ROMS_B200_RHS3D: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_rhs3d(q, f, st); }); h->launches += 1; break;
     case ROMS_B200_UV3DMIX: launch_full(h, [&](const Par& q, cudaStream_t st) { launch_uv3dmix2(q, f, st); }); h->launches += 1; break;
@@ -537,7 +537,10 @@ int step_phases_body(roms_b200_state* h, bool with_diag) {
   if (h->cfg.wvelocity_every_step) { int rc = run_phase_async(h, ROMS_B200_WVELOCITY); if (rc) return rc; }
   static const int seq3[] = {ROMS_B200_SET_ZETA,  ROMS_B200_SET_AVG, ROMS_B200_PRE_STEP3D, ROMS_B200_PRSGRD,    ROMS_B200_T3DMIX,   ROMS_B200_RHS3D, ROMS_B200_UV3DMIX,
                              ROMS_B200_STEP2D_LOOP, ROMS_B200_SET_DEPTH, ROMS_B200_STEP3D_UV, ROMS_B200_OMEGA2, ROMS_B200_STEP3D_T};
-  for (int ph : seq3) { int rc = run_phase_async(h, ph); if (rc) return rc; }
+  for (int ph : seq3) {
+    int rc = run_phase_async(h, ph); if (rc) return rc;
+    if (ph == ROMS_B200_T3DMIX && h->cfg.ts_dif4) { rc = run_phase_async(h, ROMS_B200_T3DMIX4); if (rc) return rc; }   // rhs3d.F:89-97
+  }
   join_halo(h);                      // the step ends with both streams joined (also required to end a graph capture)
   mark_phase(h, -1);
   return NoError;

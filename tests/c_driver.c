@@ -145,6 +145,7 @@ static int main3d_by_routine(void) {
   CHECK(routine(ROMS_B200_PRE_STEP3D));                                    /* rhs3d.F:25-167 */
   CHECK(routine(ROMS_B200_PRSGRD));
   CHECK(routine(ROMS_B200_T3DMIX));
+  if (cfg.ts_dif4) CHECK(routine(ROMS_B200_T3DMIX4));
   CHECK(routine(ROMS_B200_RHS3D));
   CHECK(routine(ROMS_B200_UV3DMIX));
   for (int my_iif = 1; my_iif <= nfast + 1; ++my_iif) {                    /* LOOP_2D, :592-700 */

@@ -137,8 +137,8 @@ int emu_run(void* h, int phase) {
     case 9: launch_prsgrd(p, f, e->dj_gradps, s); break;
     case 10:
       if (e->mix_geo_ts) launch_t3dmix2_geo(p, f, s); else launch_t3dmix2_s(p, f, s);
-      if (e->ts_dif4) launch_t3dmix4_s(p, f, s);
       break;
+    case 26: launch_t3dmix4_s(p, f, s); break;
     case 11: launch_rhs3d(p, f, s); break;
     case 12: launch_uv3dmix2(p, f, s); break;
     case 13: launch_step2d(p, f, s, nullptr); break;

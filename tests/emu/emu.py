@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DP = C.POINTER(C.c_double)
 EMULATED = {"set_massflux": 1, "rho_eos": 2, "set_vbc": 3, "ana_vmix": 4, "omega": 5, "wvelocity": 6, "set_zeta": 7, "pre_step3d": 8,
             "prsgrd": 9, "t3dmix": 10, "rhs3d": 11, "uv3dmix": 12, "step2d": 13, "set_depth": 14, "step3d_uv": 15, "omega2": 16, "step3d_t": 17,
-            "bulk_flux": 23, "lmd_vmix": 24, "bvf_mix": 25}
+            "bulk_flux": 23, "lmd_vmix": 24, "bvf_mix": 25, "t3dmix4": 26}
 IOPT = ["Lm", "Mm", "N", "NT", "nonlin_eos", "curvgrid", "uv_qdrag", "salinity", "hadv", "vadv", "itemp", "isalt", "bv_frequency",
         "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "uv_adv", "ts_dif4", "dj_gradps", "mix_geo_ts",
         "ana_vmix", "ndtfast"]

@@ -74,7 +74,7 @@ def test_fortran_shim_is_consistent_with_the_header():
     # the by-name vocabulary of b200_loc covers every field name the routines ask for
     cases = set(re.findall(r"CASE \('(\w+)'\)", src))
     L = _lib.load(True)
-    for ph in list(range(1, 18)) + [23, 24, 25]:
+    for ph in list(range(1, 18)) + [23, 24, 25, 26]:
         spec = L.roms_b200_routine_args(ph)
         if not spec:
             continue
@@ -89,8 +89,8 @@ def test_driver_patch_names_existing_call_sites():
     """fortran/patches/b200_drivers.patch only adds lines, one CALL b200_routine per driver of the chain."""
     p = open(os.path.join(ROOT, "fortran", "patches", "b200_drivers.patch")).read()
     files = re.findall(r"^\+\+\+ b/(\S+)", p, re.M)
-    assert len(files) == 20 and len(set(files)) == 20                 # the 18 drivers of the chain + bulk_flux.F, lmd_vmix.F
-    assert len(re.findall(r"^\+\s+CALL b200_routine \(ng, tile, B200_\w+\)", p, re.M)) == 20
+    assert len(files) == 22 and len(set(files)) == 22                 # the 18 drivers of the chain + bulk_flux.F, lmd_vmix.F, t3dmix4_s.h, prsgrd40.h
+    assert len(re.findall(r"^\+\s+CALL b200_routine \(ng, tile, B200_\w+\)", p, re.M)) == 22
     assert not re.findall(r"^-(?!--)", p, re.M)                        # nothing of the reference is removed
     ref = "/root/reference"
     if os.path.isdir(ref):                                             # not on the GPU box

@@ -73,6 +73,8 @@ def test_kernel_source_bit_exact_against_oracle(case, spinup):
         phases[phases.index("ana_vmix")] = "lmd_vmix"
     if o.opt("bulk_fluxes"):
         phases.insert(phases.index("set_vbc"), "bulk_flux")
+    if o.opt("ts_dif4"):
+        phases.insert(phases.index("t3dmix") + 1, "t3dmix4")
     ran = 0
 
     AVG = ("Zt_avg1", "DU_avg1", "DV_avg1", "DU_avg2", "DV_avg2")
@@ -156,7 +158,7 @@ def test_kernel_chain_whole_steps_without_resync(case):
         o.set_indices(d)
         o.run_phase("set_data")
         t.set("sustr", o.field("sustr")); t.set("svstr", o.field("svstr"))
-        for ph in STEP_PHASES:
+        for ph in (STEP_PHASES[:STEP_PHASES.index("t3dmix") + 1] + ["t3dmix4"] * int(o.opt("ts_dif4")) + STEP_PHASES[STEP_PHASES.index("t3dmix") + 1:]):
             if ph == "step2d_loop":
                 e = o.indices(); e["PREDICTOR"] = 0
                 for my_iif in range(1, nfast + 2):            # csrc/api.cu loop2d_machine

@@ -703,7 +703,7 @@ def test_t3dmix4_s_known_answer():
     o.field("Hz")[:] = 1.0
     tr = _wave(o, "t1_0", m).copy(); _wave(o, "t1_1", m)
     o.field("t2_0")[:] = 0.0; o.field("t2_1")[:] = 0.0
-    o.run_phase("t3dmix")
+    o.run_phase("t3dmix"); o.run_phase("t3dmix4")                          # rhs3d.F:81-97: harmonic (tnu2 = 0 here), then biharmonic
     pm, pn = o.field("pm")[0, 3, 5], o.field("pn")[0, 3, 5]
     assert np.all(o.field("pm") == pm) and np.all(o.field("pn") == pn)
     dt, th = o.opt("dt"), 2.0 * np.pi * m / Lm

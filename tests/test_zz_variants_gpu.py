@@ -41,7 +41,8 @@ def test_variants_strict_bit_exact_every_phase(case, spinup):
     o, t = make_pair(app, strict=True, spinup=spinup, **kw)
     names = all_names(int(o.opt("NT")))
     begin_step(o, t)
-    for ph in STEP_PHASES:
+    k = STEP_PHASES.index("t3dmix") + 1
+    for ph in STEP_PHASES[:k] + ["t3dmix4"] * int(o.opt("ts_dif4")) + STEP_PHASES[k:]:       # rhs3d.F:81-97
         o.run_phase(ph); t.run_phase(ph)
         bad = compare(o, t, names, exact=True)
         assert not bad, f"{case} spinup={spinup} phase {ph}: {bad}"
@@ -88,7 +89,7 @@ def test_variants_production_tolerance():
 
 
 def test_ts_dif4_by_routine_and_config_errors():
-    """t3dmix through roms_b200_routine_tile with the optional diff4 arrays passed by name; TS_DIF4 with MIX_GEO_TS (t3dmix4_geo.h is
+    """t3dmix4 through roms_b200_routine_tile (its own routine, as in the reference: rhs3d.F:89-97) with the diff4 arrays passed by name; TS_DIF4 with MIX_GEO_TS (t3dmix4_geo.h is
     not built) and an unknown uv_adv are configuration errors (exit_flag 5)."""
     app, kw = VARIANTS["ts_dif4"]
     o, t = make_pair(app, strict=True, spinup=3, **kw)
@@ -101,10 +102,10 @@ def test_ts_dif4_by_routine_and_config_errors():
     d["tdays"] = d["time"] / 86400.0
     o.set_indices(d)
     o.run_phase("set_data")
-    for ph in ("set_massflux", "rho_eos", "set_vbc", "ana_vmix", "omega", "wvelocity", "set_zeta", "pre_step3d", "prsgrd"):
+    for ph in ("set_massflux", "rho_eos", "set_vbc", "ana_vmix", "omega", "wvelocity", "set_zeta", "pre_step3d", "prsgrd", "t3dmix"):
         o.run_phase(ph)
-    spec = L.roms_b200_routine_args(_lib.PHASES["t3dmix"]).decode()
-    assert "?diff4_*" in spec
+    spec = L.roms_b200_routine_args(_lib.PHASES["t3dmix4"]).decode()
+    assert "diff4_*" in spec
 
     def expand(part):
         out = []
@@ -123,10 +124,10 @@ def test_ts_dif4_by_routine_and_config_errors():
     cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
     ca = (_lib.DP * len(names))(*[a.ctypes.data_as(_lib.DP) for a in arrs])
     cm = (C.c_int * len(names))(*mode)
-    rc = L.roms_b200_routine_tile(C.byref(ta), _lib.PHASES["t3dmix"], len(names), cn, ca, cm, sc.ctypes.data_as(_lib.DP), int(o.opt("nfast")),
+    rc = L.roms_b200_routine_tile(C.byref(ta), _lib.PHASES["t3dmix4"], len(names), cn, ca, cm, sc.ctypes.data_as(_lib.DP), int(o.opt("nfast")),
                                   w1.ctypes.data_as(_lib.DP), w2.ctypes.data_as(_lib.DP), len(w1))
     assert rc == 0
-    o.run_phase("t3dmix")
+    o.run_phase("t3dmix4")
     for n, a in zip(names, arrs):
         if n in outs:
             assert np.array_equal(a, o.field(n)), n
