@@ -127,6 +127,7 @@ class Grid:
 def build(app, Lm=0, Mm=0, N=0, **overrides):
     """Returns (cfg, fields, scoord, (nfast, w1, w2)) for a fresh run at rest (time level 1; ini_fields already applied)."""
     cfg = _lib.default_config(app, Lm, Mm, N)
+    tnu4 = float(overrides.pop("tnu4", 0.0))                  # roms_*.in TNU4 (m4/s): only with ts_dif4
     for k, v in overrides.items():
         setattr(cfg, k, v)
     Lm, Mm, N, NT = cfg.Lm, cfg.Mm, cfg.N, cfg.NT
@@ -199,6 +200,8 @@ def build(app, Lm=0, Mm=0, N=0, **overrides):
     F["visc2_r"] = par["visc2"] * ones; F["visc2_p"] = par["visc2"] * ones
     for it in range(NT):
         F[f"diff2_{it}"] = par["tnu2"] * ones
+        if cfg.ts_dif4:
+            F[f"diff4_{it}"] = math.sqrt(abs(tnu4)) * ones      # ini_hmixcoef.F:293 with read_phypar.F:6905: diff4 = SQRT(ABS(tnu4))
     F["rdrag"] = (par["rdrg"] if cfg.uv_qdrag == 0 else 0.0) * ones
     F["rdrag2"] = (par["rdrg2"] if cfg.uv_qdrag == 1 else 0.0) * ones
     if cfg.uv_qdrag == 2:

@@ -26,7 +26,13 @@ def main():
     peer = opts.pop("peer", "1") != "0"
     opts_e2e = opts.pop("e2e", "0") != "0"     # step through roms_b200_step_fields / step_forced (uploads without halo exchange)
     # physics=full: the shipped benchmark.h cpp set (bulk_flux + lmd_vmix on the device, synth.FULL_BENCHMARK)
-    phys = synth.FULL_BENCHMARK if opts.pop("physics", "reduced") == "full" else {}
+    phys = dict(synth.FULL_BENCHMARK) if opts.pop("physics", "reduced") == "full" else {}
+    # cpp variants of the chain (roms_b200_config members): uv_adv=1|2|3, dj_gradps=0..3, ts_dif4=1 tnu4=..., vadv=3, ...
+    for k in ("uv_adv", "dj_gradps", "ts_dif4", "hadv", "vadv", "uv_qdrag", "mix_geo_ts", "nonlin_eos"):
+        if k in opts:
+            phys[k] = int(opts.pop(k))
+    if "tnu4" in opts:
+        phys["tnu4"] = float(opts.pop("tnu4"))
     t = synth.make_tile(synth.APP_BENCHMARK, Lm, Mm, N, NtileI=world, tile=rank, device=local, **phys)
     for k, v in opts.items():
         t.set_option(k, float(v))

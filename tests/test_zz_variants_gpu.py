@@ -11,7 +11,7 @@ import pytest
 import orc
 from helpers import all_names, cfg_from_oracle, compare, make_pair
 from roms_trunk_mgh_b200 import _lib
-from test_gpu_parity import STEP_PHASES, begin_step
+from test_gpu_parity import STEP_PHASES, begin_step, test_tiling_invariance_across_gpus as _tiling_invariance
 
 pytestmark = pytest.mark.gpu
 
@@ -136,3 +136,12 @@ def test_ts_dif4_by_routine_and_config_errors():
     assert L.roms_b200_create(C.byref(bad), C.byref(h)) == 5
     bad = cfg_from_oracle(o); bad.uv_adv = 7
     assert L.roms_b200_create(C.byref(bad), C.byref(h)) == 5
+
+
+@pytest.mark.parametrize("mode", ["2 uv_adv=3", "1 uv_adv=3 step2d_loop_kernel=0", "0 uv_adv=3 peer=0", "2 uv_adv=1 dj_gradps=2",
+                                  "2 uv_adv=2 dj_gradps=3 ts_dif4=1 tnu4=2e13"])
+def test_variants_tiling_invariance_across_gpus(mode):
+    """The variants on a ring of GPUs (skipped on a one-GPU box): bitwise agreement with the single-tile run, as
+    test_gpu_parity.py::test_tiling_invariance_across_gpus demands of the default branches.  uv_adv=3 runs LOOP_2D through the
+    per-call kernels k_step2d<XCH, C2> with the exchange fused (modes 2, 1) or stand-alone over NCCL (mode 0, peer=0)."""
+    _tiling_invariance(mode)
