@@ -243,6 +243,19 @@ void set_vbc(Model& m, const Bnd& b) {
     for (int j = JstrV; j <= Jend; ++j)
       for (int i = Istr; i <= Iend; ++i) m.bvstr(i, j) = 0.5 * (m.rdrag(i, j - 1) + m.rdrag(i, j)) * v(i, j, 1);
   }
+  if (c.limit_bstress) {                                          // LIMIT_BSTRESS (set_vbc.F:533-540, :562-567, :579-584, :600-605, ...):
+    const double cff = 0.75 / c.dt;                               // the stress may slow the bottom layer down, not reverse it
+    for (int j = Jstr; j <= Jend; ++j)
+      for (int i = IstrU; i <= Iend; ++i) {
+        const double cff3 = cff * 0.5 * (m.Hz(i - 1, j, 1) + m.Hz(i, j, 1));
+        m.bustr(i, j) = std::copysign(1.0, m.bustr(i, j)) * std::min(std::fabs(m.bustr(i, j)), std::fabs(u(i, j, 1)) * cff3);
+      }
+    for (int j = JstrV; j <= Jend; ++j)
+      for (int i = Istr; i <= Iend; ++i) {
+        const double cff3 = cff * 0.5 * (m.Hz(i, j - 1, 1) + m.Hz(i, j, 1));
+        m.bvstr(i, j) = std::copysign(1.0, m.bvstr(i, j)) * std::min(std::fabs(m.bvstr(i, j)), std::fabs(v(i, j, 1)) * cff3);
+      }
+  }
   bc_u2d(m, b, m.bustr); bc_v2d(m, b, m.bvstr);
 }
 

@@ -368,7 +368,7 @@ int ensure_optional(roms_b200_state* h, int phase) {
   if (!h->lazy) return NoError;
   std::vector<std::string> names;
   if (phase == ROMS_B200_RHO_EOS) names = {"bvf", "alpha", "beta"};
-  else if (phase == ROMS_B200_SET_VBC && h->cfg.uv_qdrag == 2) names = {"ZoBot", "z_r", "z_w"};
+  else if (phase == ROMS_B200_SET_VBC) { if (h->cfg.uv_qdrag == 2) names = {"ZoBot", "z_r", "z_w"}; if (h->cfg.limit_bstress) names.push_back("Hz"); }
   else if (phase == ROMS_B200_BULK_FLUX) names = {"lrflx", "lhflx", "shflx", "sustr", "svstr", "stflux_" + std::to_string(h->cfg.itemp - 1)};
   else if (phase == ROMS_B200_LMD_VMIX) { names = {"hsbl", "ksbl", "Akv"}; for (int it = 0; it < h->cfg.NT; ++it) { names.push_back("ghats_" + std::to_string(it)); names.push_back("Akt_" + std::to_string(it)); } }
   else if (phase == ROMS_B200_PRE_STEP3D) { names = {"srflx", "Jwtype", "z_w"}; for (int it = 0; it < h->cfg.NT; ++it) names.push_back("ghats_" + std::to_string(it)); }
@@ -743,7 +743,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   p.nonlin_eos = cfg->nonlin_eos; p.curvgrid = cfg->curvgrid; p.uv_qdrag = cfg->uv_qdrag; p.salinity = cfg->salinity;
   p.hadv = cfg->hadv; p.vadv = cfg->vadv; p.itemp = cfg->itemp; p.isalt = cfg->isalt;
   p.bv_frequency = cfg->bv_frequency; p.eos_tderivative = cfg->eos_tderivative; p.solar_source = cfg->solar_source; p.lmd_nonlocal = cfg->lmd_nonlocal;
-  p.bulk_fluxes = cfg->bulk_fluxes; p.lmd_mixing = cfg->lmd_mixing; p.uv_adv = cfg->uv_adv; p.pad_ = 0;
+  p.bulk_fluxes = cfg->bulk_fluxes; p.lmd_mixing = cfg->lmd_mixing; p.uv_adv = cfg->uv_adv; p.limit_bstress = cfg->limit_bstress;
   p.blk_ZQ = cfg->blk_ZQ > 0.0 ? cfg->blk_ZQ : 10.0; p.blk_ZT = cfg->blk_ZT > 0.0 ? cfg->blk_ZT : 10.0; p.blk_ZW = cfg->blk_ZW > 0.0 ? cfg->blk_ZW : 10.0;
   p.dt = cfg->dt; p.g = cfg->g; p.rho0 = cfg->rho0; p.R0 = cfg->R0; p.T0 = cfg->T0; p.S0 = cfg->S0; p.Tcoef = cfg->Tcoef; p.Scoef = cfg->Scoef;
   p.gamma2 = cfg->gamma2; p.lambda = cfg->lambda; p.hc = cfg->hc; p.Akv_bak = cfg->Akv_bak;

@@ -42,7 +42,7 @@ struct Par {
   double w1_m1, w2_0, w2_p1;      // weight(1,iif-1), weight(2,iif), weight(2,iif+1) for the current step2d call
   double blk_ZQ, blk_ZT, blk_ZW;  // heights (m) of the atmospheric humidity / temperature / wind data (bulk_flux.F)
   int uv_adv;                     // rhs3d momentum advection: 0 default (U3 / C4), 1 UV_C4ADVECTION, 2 UV_SADVECTION, 3 UV_C2ADVECTION (also in step2d)
-  int pad_;
+  int limit_bstress;              // LIMIT_BSTRESS in set_vbc
 };
 
 // Field table (all pointers pre-offset; [0] slots of time-indexed arrays are unused so Fortran indices apply)

@@ -214,6 +214,10 @@ __global__ void __launch_bounds__(256) k_set_vbc(Par p, Flds f) {
     } else {
       bu = 0.5 * (f.rdrag[o2 + i - 1] + f.rdrag[o2 + i]) * u[o1 + i];
     }
+    if (p.limit_bstress) {                                       // set_vbc.F:562-567 / :600-605 / :633-638
+      const double cff3 = (0.75 / p.dt) * 0.5 * (f.Hz[o1 + i - 1] + f.Hz[o1 + i]);
+      bu = copysign(1.0, bu) * dmin(fabs(bu), fabs(u[o1 + i]) * cff3);
+    }
     st_u_closed(f.bustr, o2, i, j, bu, p);
   }
   if (j >= 2 && j <= p.Mm) {
@@ -230,6 +234,10 @@ __global__ void __launch_bounds__(256) k_set_vbc(Par p, Flds f) {
       bv = 0.5 * (f.rdrag2[o2 - p.P + i] + f.rdrag2[o2 + i]) * vv * cff2;
     } else {
       bv = 0.5 * (f.rdrag[o2 - p.P + i] + f.rdrag[o2 + i]) * v[o1 + i];
+    }
+    if (p.limit_bstress) {
+      const double cff3 = (0.75 / p.dt) * 0.5 * (f.Hz[o1 - p.P + i] + f.Hz[o1 + i]);
+      bv = copysign(1.0, bv) * dmin(fabs(bv), fabs(v[o1 + i]) * cff3);
     }
     st_v_closed(f.bvstr, o2, i, j, bv, p);
   }

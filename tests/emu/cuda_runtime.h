@@ -41,7 +41,7 @@ inline double __longlong_as_double(long long v) { double r; __builtin_memcpy(&r,
 inline void __nanosleep(unsigned) {}
 inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 using std::sqrt; using std::exp; using std::log; using std::pow; using std::atan; using std::tanh; using std::fabs; using std::cos; using std::sin;
-using std::fmin; using std::fmax; using std::floor;
+using std::fmin; using std::fmax; using std::floor; using std::copysign;
 // one kernel launch = every thread of every block, in order (valid for kernels without barriers or inter-thread communication)
 template <class F>
 inline void emu_launch(dim3 g, dim3 b, F body) {

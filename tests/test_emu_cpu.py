@@ -30,6 +30,8 @@ CASES = {
     "seamount_p40": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, dj_gradps=2)),
     "benchmark_wj": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, dj_gradps=3)),                        # WJ_GRADP (prsgrd31.h, weighted)
     "seamount_wj": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, dj_gradps=3)),
+    "benchmark_limit": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, limit_bstress=1, uv_qdrag=0, rdrg=5.0)),   # LIMIT_BSTRESS, with a linear drag strong enough to hit the limit
+    "upwelling_limit": (orc.APP_UPWELLING, dict(Lm=20, Mm=24, N=8, limit_bstress=1, rdrg=0.5)),
     "benchmark_splines": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, vadv=3)),
     "benchmark_bvf": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, bv_frequency=1, bvf_mixing=1)),
     "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, mix_geo_ts=1)),

@@ -874,3 +874,29 @@ def test_prsgrd_variants_known_answers():
         b = orc.Oracle(orc.APP_SEAMOUNT, NtileI=2, NtileJ=2, kind="chk", dj_gradps=alg); b.run_phase("set_data"); b.run_phase("ini"); b.step(3, 4)
         for n in ("zeta1", "u1", "v1", "ru1", "rv1", "t1_0"):
             assert np.array_equal(a.field(n), b.field(n)), (alg, n)
+
+
+def test_limit_bstress_known_answer():
+    """LIMIT_BSTRESS (set_vbc.F:533-540): the bottom stress keeps the sign of the bottom velocity and never exceeds
+    0.75 |u(k=1)| Hz_u(k=1) / dt; where the linear drag rdrg |u| is larger than that bound the stress IS the bound, elsewhere it is the
+    drag law's value.  Checked after 8 steps of a BENCHMARK run whose drag coefficient straddles the bound."""
+    kw = dict(Lm=48, Mm=32, N=10, uv_qdrag=0, rdrg=1.2, limit_bstress=1)
+    o = orc.Oracle(orc.APP_BENCHMARK, kind="chk", **kw)
+    o.run_phase("set_data"); o.run_phase("ini"); o.step(8)
+    d = o.indices(); d["nstp"] = 1 + ((d["iic"] - d["ntstart"]) % 2); d["nnew"] = 3 - d["nstp"]; d["nrhs"] = d["nstp"]; o.set_indices(d)
+    o.run_phase("set_vbc")
+    u = o.field(f"u{d['nrhs']}")[0]; Hz = o.field("Hz")[0]; bu = o.field("bustr")[0]
+    LBi, LBj, _ = o.origin("bustr")
+    J = slice(1 - LBj, 32 + 1 - LBj); I = slice(1 - LBi, 48 + 1 - LBi); Im = slice(0 - LBi, 48 - LBi)
+    bound = (0.75 / o.opt("dt")) * 0.5 * (Hz[J, Im] + Hz[J, I]) * np.abs(u[J, I])
+    law = 1.2 * u[J, I]
+    got = bu[J, I]
+    assert np.all(np.abs(got) <= bound * (1 + 1e-15)) and np.all(np.sign(got) == np.sign(u[J, I]))
+    hit = np.abs(law) > bound
+    assert hit.any() and (~hit).any()                                   # the coefficient straddles the bound on this grid
+    assert np.allclose(np.abs(got[hit]), bound[hit], rtol=1e-14, atol=0) and np.array_equal(got[~hit], law[~hit])
+    o2 = orc.Oracle(orc.APP_BENCHMARK, NtileI=2, NtileJ=2, kind="chk", **kw)
+    o2.run_phase("set_data"); o2.run_phase("ini"); o2.step(8, 4)
+    o2.set_indices(d); o2.run_phase("set_vbc")
+    for n in ("bustr", "bvstr", "u1", "zeta1"):
+        assert np.array_equal(o.field(n), o2.field(n)), n

@@ -26,6 +26,7 @@ VARIANTS = {
     "p40_seamount": (orc.APP_SEAMOUNT, dict(dj_gradps=2)),
     "wj": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, dj_gradps=3)),                          # WJ_GRADP: prsgrd31.h, weighted Jacobian
     "wj_seamount": (orc.APP_SEAMOUNT, dict(dj_gradps=3)),
+    "limit_bstress": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, limit_bstress=1, uv_qdrag=0, rdrg=5.0)),   # LIMIT_BSTRESS with a linear drag that hits the limit
     "uv_sadv": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, uv_adv=2)),                      # UV_SADVECTION: spline vertical advection
     "uv_sadv_seamount": (orc.APP_SEAMOUNT, dict(uv_adv=2)),
     "ts_dif4": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, ts_dif4=1, tnu4=TNU4)),
