@@ -42,14 +42,24 @@ void* emu_create(const int* io, const double* dv) {
   std::memset(&p, 0, sizeof(p)); std::memset(&f, 0, sizeof(f));
   p.Lm = io[0]; p.Mm = io[1]; p.N = io[2]; p.NT = io[3];
   const int Lm = p.Lm, Mm = p.Mm, N = p.N;
-  e->LBi = -2; e->LBj = 0; e->ni = Lm + 5; e->nj = Mm + 2;
-  e->ioff = (16 - ((1 - e->LBi) % 16)) % 16;                       // i = Istr on a 128-byte boundary, as on the device
+  // xi-tile `tile` of NtileI (io[25], io[26]; 1, 0 = the whole periodic domain): get_bounds.F tile_bounds_2d as csrc/api.cu make_bounds
+  const int NtileI = io[25] > 0 ? io[25] : 1, tile = io[26];
+  int is = 1, ie = Lm;
+  if (NtileI > 1) {
+    const int chunk = (Lm + NtileI - 1) / NtileI, margin = (NtileI * chunk - Lm) / 2;
+    is = 1 + tile * chunk - margin; ie = is + chunk - 1;
+    if (is < 1) is = 1;
+    if (ie > Lm) ie = Lm;
+  }
+  // device extents of a tile: Istr-3 .. Iend+2 (csrc/api.cu: LBi_dev = Istr - 3, UBi = Iend + Nghost); the single tile -2 .. Lm+2
+  e->LBi = (NtileI > 1) ? is - 3 : -2; e->LBj = 0; e->ni = ((NtileI > 1) ? ie + 2 : Lm + 2) - e->LBi + 1; e->nj = Mm + 2;
+  e->ioff = (16 - ((is - e->LBi) % 16)) % 16;                      // i = Istr on a 128-byte boundary, as on the device
   p.P = ((e->ioff + e->ni + 15) / 16) * 16; p.PL = p.P * (e->nj + 4);
-  p.LBi = e->LBi; p.UBi = Lm + 2; p.LBj = 0; p.UBj = Mm + 1;
-  // get_bounds.F var_bounds for the single tile of an EW-periodic, NS-closed grid (csrc/api.cu make_bounds)
-  p.Istr = 1; p.Iend = Lm; p.Jstr = 1; p.Jend = Mm; p.IstrU = 1; p.JstrV = 2; p.JstrR = 0; p.JendR = Mm + 1;
+  p.LBi = e->LBi; p.UBi = e->LBi + e->ni - 1; p.LBj = 0; p.UBj = Mm + 1;
+  // get_bounds.F var_bounds of an EW-periodic, NS-closed grid: no clipping in xi on any tile, the eta clips of the edge rows
+  p.Istr = is; p.Iend = ie; p.Jstr = 1; p.Jend = Mm; p.IstrU = is; p.JstrV = 2; p.JstrR = 0; p.JendR = Mm + 1;
   p.Jstrm1 = 1; p.Jendp1 = Mm; p.Jendp2 = Mm + 1; p.JstrVm1 = 2; p.JstrVm2 = 1;
-  p.ew_wrap = 1; p.gap_at = 0x7fffffff; p.gap_len = 0;
+  p.ew_wrap = (NtileI == 1) ? 1 : 0; p.gap_at = 0x7fffffff; p.gap_len = 0;
   p.nonlin_eos = io[4]; p.curvgrid = io[5]; p.uv_qdrag = io[6]; p.salinity = io[7]; p.hadv = io[8]; p.vadv = io[9]; p.itemp = io[10]; p.isalt = io[11];
   p.bv_frequency = io[12]; p.eos_tderivative = io[13]; p.solar_source = io[14]; p.lmd_nonlocal = io[15]; p.bulk_fluxes = io[16]; p.lmd_mixing = io[17];
   p.uv_adv = io[18]; e->ts_dif4 = io[19]; e->dj_gradps = io[20]; e->mix_geo_ts = io[21]; e->ana_vmix = io[22];
@@ -106,6 +116,8 @@ int emu_xfer(void* h, const char* name, double* host, int up) {
     }
   return 0;
 }
+// first array column (Fortran index) and number of columns of this tile's arrays
+void emu_extent(void* h, int* out2) { Emu* e = (Emu*)h; out2[0] = e->LBi; out2[1] = e->ni; }
 int emu_levels(void* h, const char* name) { Emu* e = (Emu*)h; auto it = e->reg.find(name); return it == e->reg.end() ? -1 : it->second.nk; }
 void emu_scoord(void* h, int which, const double* v, int n) {
   Emu* e = (Emu*)h;

@@ -183,3 +183,73 @@ def test_kernel_chain_whole_steps_without_resync(case):
             a, b = o.field(n), t.get(n)
             assert np.array_equal(a, b), f"{case} step {step} field {n}: {np.count_nonzero(a != b)} points differ"
     t.close()
+
+
+@pytest.mark.parametrize("case", ["benchmark", "seamount", "benchmark_full_n12", "uv_c2", "uv_sadv", "ts_dif4", "benchmark_p40", "benchmark_wj",
+                                  "benchmark_limit", "benchmark_geo"])
+def test_kernel_source_on_ring_tiles(case):
+    """The same kernels as xi-TILES of a ring (NtileI = 3, uneven widths; ew_wrap = 0, arrays Istr-3 .. Iend+2 as on the device): every
+    tile starts each phase from the oracle's state -- i.e. after a perfect halo exchange -- and must reproduce the oracle's owned
+    columns bit for bit.  This is the tiling-invariance of the kernels' index handling (tile offsets, no periodic self-images, the
+    eastern-edge copy of lmd_finish) checked without GPUs; the exchange itself is what tests/mgpu_check.py checks on a multi-GPU box."""
+    app, kw = CASES[case]
+    o = orc.Oracle(app, **kw)
+    o.run_phase("set_data"); o.run_phase("ini")
+    o.step(2)
+    d = o.indices()
+    d["nstp"] = 1 + ((d["iic"] - d["ntstart"]) % 2); d["nnew"] = 3 - d["nstp"]; d["nrhs"] = d["nstp"]
+    d["tdays"] = d["time"] / 86400.0
+    o.set_indices(d)
+    o.run_phase("set_data")
+    NtileI = 3
+    tiles = [EmuTile(o, NtileI=NtileI, tile=q) for q in range(NtileI)]
+    own = [(t.LBi + 3, t.LBi + t.ni - 3) for t in tiles]                       # Istr, Iend
+    assert own[0][0] == 1 and own[-1][1] == int(o.opt("Lm")) and all(own[q][1] + 1 == own[q + 1][0] for q in range(NtileI - 1))
+    names = all_names(int(o.opt("NT"))) + optional_names(o)
+    phases = list(STEP_PHASES)
+    if o.opt("lmd_mixing"):
+        phases[phases.index("ana_vmix")] = "lmd_vmix"
+    if o.opt("bulk_fluxes"):
+        phases.insert(phases.index("set_vbc"), "bulk_flux")
+    if o.opt("ts_dif4"):
+        phases.insert(phases.index("t3dmix") + 1, "t3dmix4")
+
+    def both(oo, ph):
+        for t in tiles:
+            for n in names:
+                t.set(n, oo.field(n))
+            t.set_indices(oo.indices())
+        oo.run_phase(ph)
+        for q, t in enumerate(tiles):
+            t.run_phase(ph)
+            Istr, Iend = own[q]
+            for n in names:
+                a = oo.field(n)[:, :, Istr + 2:Iend + 3]
+                b = t.get(n)[:, :, Istr - t.LBi:Iend - t.LBi + 1]
+                if not np.array_equal(a, b):
+                    raise AssertionError(f"{case} tile {q} phase {ph} {oo.indices()} field {n}: {np.count_nonzero(a != b)} owned points differ")
+
+    # a twin of the oracle, advanced to the start of LOOP_2D, plays the first four step2d calls with the tiles; the main oracle runs
+    # the whole loop on its own and then the rest of the step with the tiles
+    twin = orc.Oracle(app, **kw)
+    twin.run_phase("set_data"); twin.run_phase("ini"); twin.step(2)
+    twin.set_indices(d); twin.run_phase("set_data")
+    for ph in phases[:phases.index("step2d_loop")]:
+        twin.run_phase(ph)
+    e = twin.indices(); e["PREDICTOR"] = 0
+    for my_iif in (1, 2):
+        nxt = 3 - e["indx1"]
+        e["PREDICTOR"] = 1; e["iif"] = my_iif
+        e["kstp"] = e["indx1"] if my_iif == 1 else 3 - e["indx1"]; e["knew"] = 3; e["krhs"] = e["indx1"]
+        twin.set_indices(e); both(twin, "step2d")
+        e["PREDICTOR"] = 0; e["knew"] = nxt; e["kstp"] = 3 - nxt; e["krhs"] = 3; e["indx1"] = nxt
+        twin.set_indices(e); both(twin, "step2d")
+    ran = 0
+    for ph in phases:
+        if ph in EMULATED:
+            both(o, ph); ran += 1
+        else:
+            o.run_phase(ph)                                                    # step2d_loop
+    assert ran >= 16
+    for t in tiles:
+        t.close()
