@@ -78,6 +78,9 @@ typedef struct roms_b200_config {
   int lmd_mixing;               /* LMD_MIXING (lmd_vmix.F:100-659, lmd_skpp.F:246-923, lmd_swfrac.F)                   */
   double blk_ZQ, blk_ZT, blk_ZW;/* BLK_ZQ, BLK_ZT, BLK_ZW (m): heights of the humidity / temperature / wind data       */
   int bvf_mixing;               /* BVF_MIXING (bvf_mix.F:92-127; main3d.F:468-469): Akv, Akt from "bvf"; needs bv_frequency   */
+  int nospl_vvisc, nospl_vdiff; /* 1: SPLINES_VVISC / SPLINES_VDIFF NOT defined: centred implicit vertical viscosity / diffusion
+                                   (step3d_uv.F:397-462, :730-795; step3d_t.F:1196-1198, :1430-1499) instead of the parabolic splines;
+                                   0 (what upwelling.h, seamount.h and benchmark.h select): the splines                          */
   int limit_bstress;            /* LIMIT_BSTRESS (set_vbc.F:533-540 and the three drag laws): |bustr| <= 0.75 |u(k=1)| Hz(k=1) / dt        */
   int uv_adv;                   /* momentum advection in rhs3d: 0 the default branch (third-order upstream horizontal, fourth-order
                                    centred vertical), 1 UV_C4ADVECTION (rhs3d.F:685-705, :761-781, :829-849, :902-921, :1108-1175,

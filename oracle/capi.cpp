@@ -95,6 +95,7 @@ int orc_set_option(void* hp, const char* key, double val) {
   else if (k == "bvf_mixing") c.bvf_mixing = (int)val;
   else if (k == "uv_adv") c.uv_adv = (int)val; else if (k == "ts_dif4") c.ts_dif4 = (int)val;
   else if (k == "tnu4") { c.tnu4[0] = c.tnu4[1] = val; } else if (k == "limit_bstress") c.limit_bstress = (int)val;
+  else if (k == "nospl_vvisc") c.nospl_vvisc = (int)val; else if (k == "nospl_vdiff") c.nospl_vdiff = (int)val;
   else if (k == "rdrg2") c.rdrg2 = val; else if (k == "rdrg") c.rdrg = val;
   else if (k == "bulk_fluxes") c.bulk_fluxes = (int)val; else if (k == "lmd_mixing") c.lmd_mixing = (int)val;
   else return 1;
@@ -114,6 +115,7 @@ double orc_get_option(void* hp, const char* key) {
   if (k == "bv_frequency") return c.bv_frequency; if (k == "eos_tderivative") return c.eos_tderivative;
   if (k == "solar_source") return c.solar_source; if (k == "lmd_nonlocal") return c.lmd_nonlocal;
   if (k == "bvf_mixing") return c.bvf_mixing; if (k == "itemp") return c.itemp; if (k == "isalt") return c.isalt;
+  if (k == "nospl_vvisc") return c.nospl_vvisc; if (k == "nospl_vdiff") return c.nospl_vdiff;
   if (k == "limit_bstress") return c.limit_bstress; if (k == "rdrg2") return c.rdrg2; if (k == "rdrg") return c.rdrg;
   if (k == "uv_adv") return c.uv_adv; if (k == "ts_dif4") return c.ts_dif4; if (k == "tnu4") return c.tnu4[0];
   if (k == "bulk_fluxes") return c.bulk_fluxes; if (k == "lmd_mixing") return c.lmd_mixing;

@@ -138,6 +138,8 @@ struct Cfg {
   int wvelocity_every_step = 1;   // main3d.F:475
   int hadv = HADV_U3, vadv = VADV_C4;
   int uv_adv = 0;                 // momentum advection: 0 default (U3 horizontal, C4 vertical), 1 UV_C4ADVECTION (rhs3d.F:685-921, :1108-1175), 2 UV_SADVECTION (:1016-1078, :1267-1329), 3 UV_C2ADVECTION (:605-657, :1079-1107; step2d_LF_AM3.h:1026-1080)
+  int nospl_vvisc = 0, nospl_vdiff = 0;   // 1: SPLINES_VVISC / SPLINES_VDIFF UNdefined -> centred implicit vertical viscosity / diffusion
+                                          // (step3d_uv.F:397-462, :730-795; step3d_t.F:1430-1499) instead of the parabolic splines
   int limit_bstress = 0;          // LIMIT_BSTRESS (set_vbc.F:533-540): |bottom stress| <= 0.75 |u| Hz / dt
   int ts_dif4 = 0;                // TS_DIF4 (+ MIX_S_TS): t3dmix4_s.h after t3dmix2 (rhs3d.F:81-97)
   // physical parameters

@@ -9,6 +9,7 @@ namespace orc {
 
 void step3d_t(Model& m, const Bnd& b) {
   const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
+  const bool nospl = c.nospl_vdiff != 0;                          // SPLINES_VDIFF undefined (:1196-1198, :1430-1499)
   const int N = c.N, NT = c.NT, nnew = m.nnew; const double dt = c.dt;
   const double eps = 1.0e-16;
   F3 &Hz = m.Hz, &Huon = m.Huon, &Hvom = m.Hvom, &W = m.W; F2 &pm = m.pm, &pn = m.pn;
@@ -136,7 +137,7 @@ void step3d_t(Model& m, const Bnd& b) {
         for (int i = Istr; i <= Iend; ++i) {
           double cff1 = CF(i, 0) * (FC(i, k) - FC(i, k - 1));
           tn(i, j, k) = tn(i, j, k) - cff1;
-          tn(i, j, k) = tn(i, j, k) * oHz(i, j, k);
+          if (!nospl) tn(i, j, k) = tn(i, j, k) * oHz(i, j, k);           // # ifdef SPLINES_VDIFF (:1196-1198)
         }
     }
   }
@@ -145,6 +146,31 @@ void step3d_t(Model& m, const Bnd& b) {
   for (int j = Jstr; j <= Jend; ++j) {
     for (int itrc = 0; itrc < NT; ++itrc) {
       F3 tn = m.t[nnew][itrc]; F3 Akt = m.Akt[std::min(NT, itrc + 1) - 1];
+      if (nospl) {                                                               // :1430-1499: centred tridiagonal system
+        const double cff = -dt * c.lambda;
+        for (int k = 1; k <= N - 1; ++k)
+          for (int i = Istr; i <= Iend; ++i) {
+            const double cff1 = 1.0 / (m.z_r(i, j, k + 1) - m.z_r(i, j, k));
+            FC(i, k) = cff * cff1 * Akt(i, j, k);
+          }
+        for (int i = Istr; i <= Iend; ++i) { FC(i, 0) = 0.0; FC(i, N) = 0.0; }
+        for (int k = 1; k <= N; ++k)
+          for (int i = Istr; i <= Iend; ++i) { BC(i, k) = Hz(i, j, k) - FC(i, k) - FC(i, k - 1); DC(i, k) = tn(i, j, k); }
+        for (int i = Istr; i <= Iend; ++i) { const double cf = 1.0 / BC(i, 1); CF(i, 1) = cf * FC(i, 1); DC(i, 1) = cf * DC(i, 1); }
+        for (int k = 2; k <= N - 1; ++k)
+          for (int i = Istr; i <= Iend; ++i) {
+            const double cf = 1.0 / (BC(i, k) - FC(i, k - 1) * CF(i, k - 1));
+            CF(i, k) = cf * FC(i, k);
+            DC(i, k) = cf * (DC(i, k) - FC(i, k - 1) * DC(i, k - 1));
+          }
+        for (int i = Istr; i <= Iend; ++i) {
+          DC(i, N) = (DC(i, N) - FC(i, N - 1) * DC(i, N - 1)) / (BC(i, N) - FC(i, N - 1) * CF(i, N - 1));
+          tn(i, j, N) = DC(i, N);
+        }
+        for (int k = N - 1; k >= 1; --k)
+          for (int i = Istr; i <= Iend; ++i) { DC(i, k) = DC(i, k) - CF(i, k) * DC(i, k + 1); tn(i, j, k) = DC(i, k); }
+        continue;
+      }
       double cff1 = 1.0 / 6.0;
       for (int k = 1; k <= N - 1; ++k)
         for (int i = Istr; i <= Iend; ++i) {

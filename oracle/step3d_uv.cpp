@@ -10,6 +10,7 @@ void step3d_uv(Model& m, const Bnd& b) {
   const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
   const int N = c.N, Mm = c.Mm; const double dt = c.dt;
   const int nnew = m.nnew, nrhs = m.nrhs;
+  const bool nospl = c.nospl_vvisc != 0;                          // SPLINES_VVISC undefined: the centred tridiagonal system (:397-462, :730-795)
   F3 &Hz = m.Hz, &Akv = m.Akv, &Huon = m.Huon, &Hvom = m.Hvom; F2 &pm = m.pm, &pn = m.pn;
   F3 u = m.u[nnew], v = m.v[nnew], ru = m.ru[nrhs], rv = m.rv[nrhs];
   SK AK(IminS, ImaxS, 0, N), BC(IminS, ImaxS, 0, N), CF(IminS, ImaxS, 0, N), DC(IminS, ImaxS, 0, N), FC(IminS, ImaxS, 0, N),
@@ -33,9 +34,32 @@ void step3d_uv(Model& m, const Bnd& b) {
     for (int k = 1; k <= N; ++k)
       for (int i = IstrU; i <= Iend; ++i) {
         u(i, j, k) = u(i, j, k) + DC(i, 0) * ru(i, j, k);
-        u(i, j, k) = u(i, j, k) * oHz(i, k);
+        if (!nospl) u(i, j, k) = u(i, j, k) * oHz(i, k);                       // # ifdef SPLINES_VVISC (:319-321)
       }
-    {
+    if (nospl) {                                                                // # else of SPLINES_VVISC, :397-462: centred tridiagonal system
+      const double cff = -c.lambda * dt / 0.5;
+      for (int k = 1; k <= N - 1; ++k)
+        for (int i = IstrU; i <= Iend; ++i) {
+          const double cff1 = 1.0 / (m.z_r(i, j, k + 1) + m.z_r(i - 1, j, k + 1) - m.z_r(i, j, k) - m.z_r(i - 1, j, k));
+          FC(i, k) = cff * cff1 * AK(i, k);
+        }
+      for (int i = IstrU; i <= Iend; ++i) { FC(i, 0) = 0.0; FC(i, N) = 0.0; }
+      for (int k = 1; k <= N; ++k)
+        for (int i = IstrU; i <= Iend; ++i) { DC(i, k) = u(i, j, k); BC(i, k) = Hzk(i, k) - FC(i, k) - FC(i, k - 1); }
+      for (int i = IstrU; i <= Iend; ++i) { const double cf = 1.0 / BC(i, 1); CF(i, 1) = cf * FC(i, 1); DC(i, 1) = cf * DC(i, 1); }
+      for (int k = 2; k <= N - 1; ++k)
+        for (int i = IstrU; i <= Iend; ++i) {
+          const double cf = 1.0 / (BC(i, k) - FC(i, k - 1) * CF(i, k - 1));
+          CF(i, k) = cf * FC(i, k);
+          DC(i, k) = cf * (DC(i, k) - FC(i, k - 1) * DC(i, k - 1));
+        }
+      for (int i = IstrU; i <= Iend; ++i) {
+        DC(i, N) = (DC(i, N) - FC(i, N - 1) * DC(i, N - 1)) / (BC(i, N) - FC(i, N - 1) * CF(i, N - 1));
+        u(i, j, N) = DC(i, N);
+      }
+      for (int k = N - 1; k >= 1; --k)
+        for (int i = IstrU; i <= Iend; ++i) { DC(i, k) = DC(i, k) - CF(i, k) * DC(i, k + 1); u(i, j, k) = DC(i, k); }
+    } else {
       double cff1 = 1.0 / 6.0;
       for (int k = 1; k <= N - 1; ++k)
         for (int i = IstrU; i <= Iend; ++i) {
@@ -82,8 +106,32 @@ void step3d_uv(Model& m, const Bnd& b) {
       for (int k = 1; k <= N; ++k)
         for (int i = Istr; i <= Iend; ++i) {
           v(i, j, k) = v(i, j, k) + DC(i, 0) * rv(i, j, k);
-          v(i, j, k) = v(i, j, k) * oHz(i, k);
+          if (!nospl) v(i, j, k) = v(i, j, k) * oHz(i, k);
         }
+      if (nospl) {                                                              // :730-795
+        const double cff = -c.lambda * dt / 0.5;
+        for (int k = 1; k <= N - 1; ++k)
+          for (int i = Istr; i <= Iend; ++i) {
+            const double cff1 = 1.0 / (m.z_r(i, j, k + 1) + m.z_r(i, j - 1, k + 1) - m.z_r(i, j, k) - m.z_r(i, j - 1, k));
+            FC(i, k) = cff * cff1 * AK(i, k);
+          }
+        for (int i = Istr; i <= Iend; ++i) { FC(i, 0) = 0.0; FC(i, N) = 0.0; }
+        for (int k = 1; k <= N; ++k)
+          for (int i = Istr; i <= Iend; ++i) { DC(i, k) = v(i, j, k); BC(i, k) = Hzk(i, k) - FC(i, k) - FC(i, k - 1); }
+        for (int i = Istr; i <= Iend; ++i) { const double cf = 1.0 / BC(i, 1); CF(i, 1) = cf * FC(i, 1); DC(i, 1) = cf * DC(i, 1); }
+        for (int k = 2; k <= N - 1; ++k)
+          for (int i = Istr; i <= Iend; ++i) {
+            const double cf = 1.0 / (BC(i, k) - FC(i, k - 1) * CF(i, k - 1));
+            CF(i, k) = cf * FC(i, k);
+            DC(i, k) = cf * (DC(i, k) - FC(i, k - 1) * DC(i, k - 1));
+          }
+        for (int i = Istr; i <= Iend; ++i) {
+          DC(i, N) = (DC(i, N) - FC(i, N - 1) * DC(i, N - 1)) / (BC(i, N) - FC(i, N - 1) * CF(i, N - 1));
+          v(i, j, N) = DC(i, N);
+        }
+        for (int k = N - 1; k >= 1; --k)
+          for (int i = Istr; i <= Iend; ++i) { DC(i, k) = DC(i, k) - CF(i, k) * DC(i, k + 1); v(i, j, k) = DC(i, k); }
+      } else {
       double cff1 = 1.0 / 6.0;
       for (int k = 1; k <= N - 1; ++k)
         for (int i = Istr; i <= Iend; ++i) {
@@ -107,6 +155,7 @@ void step3d_uv(Model& m, const Bnd& b) {
           double cff = dt * oHz(i, k) * (DC(i, k) - DC(i, k - 1));
           v(i, j, k) = v(i, j, k) + cff;
         }
+      }
       for (int i = Istr; i <= Iend; ++i) { CF(i, 0) = Hzk(i, 1); DC(i, 0) = v(i, j, 1) * Hzk(i, 1); }
       for (int k = 2; k <= N; ++k)
         for (int i = Istr; i <= Iend; ++i) { CF(i, 0) = CF(i, 0) + Hzk(i, k); DC(i, 0) = DC(i, 0) + v(i, j, k) * Hzk(i, k); }

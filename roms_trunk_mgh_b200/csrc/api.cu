@@ -744,6 +744,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   p.hadv = cfg->hadv; p.vadv = cfg->vadv; p.itemp = cfg->itemp; p.isalt = cfg->isalt;
   p.bv_frequency = cfg->bv_frequency; p.eos_tderivative = cfg->eos_tderivative; p.solar_source = cfg->solar_source; p.lmd_nonlocal = cfg->lmd_nonlocal;
   p.bulk_fluxes = cfg->bulk_fluxes; p.lmd_mixing = cfg->lmd_mixing; p.uv_adv = cfg->uv_adv; p.limit_bstress = cfg->limit_bstress;
+  p.nospl_vvisc = cfg->nospl_vvisc ? 1 : 0; p.nospl_vdiff = cfg->nospl_vdiff ? 1 : 0;
   p.blk_ZQ = cfg->blk_ZQ > 0.0 ? cfg->blk_ZQ : 10.0; p.blk_ZT = cfg->blk_ZT > 0.0 ? cfg->blk_ZT : 10.0; p.blk_ZW = cfg->blk_ZW > 0.0 ? cfg->blk_ZW : 10.0;
   p.dt = cfg->dt; p.g = cfg->g; p.rho0 = cfg->rho0; p.R0 = cfg->R0; p.T0 = cfg->T0; p.S0 = cfg->S0; p.Tcoef = cfg->Tcoef; p.Scoef = cfg->Scoef;
   p.gamma2 = cfg->gamma2; p.lambda = cfg->lambda; p.hc = cfg->hc; p.Akv_bak = cfg->Akv_bak;

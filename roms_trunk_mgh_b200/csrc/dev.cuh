@@ -43,6 +43,7 @@ struct Par {
   double blk_ZQ, blk_ZT, blk_ZW;  // heights (m) of the atmospheric humidity / temperature / wind data (bulk_flux.F)
   int uv_adv;                     // rhs3d momentum advection: 0 default (U3 / C4), 1 UV_C4ADVECTION, 2 UV_SADVECTION, 3 UV_C2ADVECTION (also in step2d)
   int limit_bstress;              // LIMIT_BSTRESS in set_vbc
+  int nospl_vvisc, nospl_vdiff;   // 1: SPLINES_VVISC / SPLINES_VDIFF not defined (centred implicit systems in step3d_uv / step3d_t)
 };
 
 // Field table (all pointers pre-offset; [0] slots of time-indexed arrays are unused so Fortran indices apply)

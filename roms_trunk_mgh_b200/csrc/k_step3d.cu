@@ -77,7 +77,9 @@ __device__ __forceinline__ void spline_forward(double hm, double om, double hk, 
 // step3d_uv_tile (ROMS/Nonlinear/step3d_uv.F:288-950 time step + implicit viscosity + vertical-mean replacement;
 // :956-965 closed-wall BCs; :1002-1432 coupling with DU_avg1/DU_avg2, ubar/vbar reset, corrected Huon/Hvom;
 // :1438-1461 periodic images).  DIR = 0: u-points, DIR = 1: v-points.
-template <int DIR>
+// SPL = false: SPLINES_VVISC not defined -- the centred tridiagonal system of :397-462 / :730-795 (u is NOT divided by Hz first; the
+// matrix carries Hz): the same delayed forward elimination with FC(k) = -lambda dt / 0.5 * AK(k) / (sum of the two columns' dz_r).
+template <int DIR, bool SPL = true>
 __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
@@ -108,27 +110,40 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
 
   // ---- pass 1 (upward): right-hand side x(k) and the forward elimination; loads of level k+1 are issued before level k
   // is computed
-  struct Lvl { double ak0, ak1, h0, h1, x, r; };
+  struct Lvl { double ak0, ak1, h0, h1, x, r, z0, z1; };
+  const double* __restrict__ z_r = f.z_r;
   auto load_level = [&](int k) -> Lvl {
     const int o = o2 + k * PL;
     pf_l2(HUV + o);                                                        // first touched by the coupling pass
     pf_up<S3U_PF>(Akv, o, k, N, PL); pf_up<S3U_PF>(Hz, o, k, N, PL); pf_up<S3U_PF>(X, o, k, N, PL); pf_up<S3U_PF>(R, o, k, N, PL);
-    return Lvl{Akv[o - s], Akv[o], Hz[o - s], Hz[o], X[o], R[o]};
+    return Lvl{Akv[o - s], Akv[o], Hz[o - s], Hz[o], X[o], R[o], SPL ? 0.0 : z_r[o], SPL ? 0.0 : z_r[o - s]};
   };
   double AKm = 0.5 * (Akv[o2 - s] + Akv[o2]), AKmm = 0.0, AKN;
+  double topDC = 0.0;                                                      // !SPL: DC(N) of the centred system
   {
     double hm = 0.0, om = 0.0, xm = 0.0, CFp = 0.0, DCp = 0.0;
+    double zm0 = 0.0, zm1 = 0.0, FCmm = 0.0;                               // !SPL: z_r of level k-1 in the two columns, FC(k-2)
+    const double cffd = -p.lambda * dt / 0.5;
     auto level = [&](const Lvl& cur, const Lvl&, int k) {
       const double AKk = 0.5 * (cur.ak0 + cur.ak1);
       const double hk = 0.5 * (cur.h0 + cur.h1);
       const double ok = 1.0 / hk;
       double xv = cur.x + DC0 * cur.r;
-      xv = xv * ok;
+      if (SPL) xv = xv * ok;
       if (k >= 2) {
-        spline_forward(hm, om, hk, ok, AKmm, AKm, AKk, xv - xm, dt, CFp, DCp);
+        if (SPL) spline_forward(hm, om, hk, ok, AKmm, AKm, AKk, xv - xm, dt, CFp, DCp);
+        else {                                                             // row m = k-1 of the centred system
+          const double cff1 = 1.0 / (cur.z0 + cur.z1 - zm0 - zm1);
+          const double FCm = cffd * cff1 * AKm;
+          const double BCm = hm - FCm - FCmm;
+          const double cf = 1.0 / (BCm - FCmm * CFp);
+          CFp = cf * FCm;
+          DCp = cf * (xm - FCmm * DCp);
+          FCmm = FCm;
+        }
         sA[(k - 2) * TS] = CFp; sB[(k - 2) * TS] = DCp;
       }
-      AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = xv;
+      AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = xv; zm0 = cur.z0; zm1 = cur.z1;
     };
 #if S3U_RING > 0
     // Register-free deep prefetch: every thread copies the six operands of level k + S3U_RING straight into its own slots of a
@@ -152,7 +167,7 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
       for (int k = 1; k <= N; ++k) {
         cp_async_wait<D - 1>();
         const double* r = ring + ((k - 1) % D) * 6 * TS;
-        const Lvl cur{r[0], r[TS], r[2 * TS], r[3 * TS], r[4 * TS], r[5 * TS]};
+        const Lvl cur{r[0], r[TS], r[2 * TS], r[3 * TS], r[4 * TS], r[5 * TS], 0.0, 0.0};
         issue(k + D);
         level(cur, cur, k);
       }
@@ -163,10 +178,19 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
     sweep_levels<S3U_PP>(N, load_level, level);
 #endif
     AKN = AKm;
+    if (!SPL) topDC = (xm - FCmm * DCp) / (hm - FCmm - FCmm * CFp);         // :436-441: BC(N) = Hzk(N) - FC(N) - FC(N-1), FC(N) = 0
   }
   // ---- pass 2 (downward): back substitution fused with the update x(k) += dt*oHz(k)*(AK(k)*DC(k) - AK(k-1)*DC(k-1));
   // x(k) and Hzk(k) replace CF(k), DC(k) in shared memory (both already consumed at level k+1)
-  {
+  if (!SPL) {                                                              // centred system: x(k) = DC(k) - CF(k) x(k+1) (:442-462)
+    double dk = topDC;
+    for (int k = N; k >= 1; --k) {
+      const int o = o2 + k * PL;
+      if (k < N) dk = sB[(k - 1) * TS] - sA[(k - 1) * TS] * dk;
+      sA[(k - 1) * TS] = dk;
+      sB[(k - 1) * TS] = 0.5 * (Hz[o - s] + Hz[o]);
+    }
+  } else {
     double dk = 0.0;                       // DC(N) = 0
     double ak = dk * AKN;
     for (int kt = N; kt >= 1; kt -= CH) {
@@ -271,7 +295,9 @@ __global__ void __launch_bounds__(TS, S3D_MINB) k_step3d_uv(Par p, Flds f) {
 // ---------------------------------------------------------------------------------------------------------------
 // step3d_t_tile (ROMS/Nonlinear/step3d_t.F:388-876 horizontal advection of t(:,:,:,3,:), :883-1210 vertical advection,
 // :1366-1427 implicit diffusion, :1551-1621 t3dbc + periodic images).  One thread per column and tracer.
-template <int HADV, int VADV>
+// SPL = false: SPLINES_VDIFF not defined -- t(nnew) stays in Hz*t units after the advection (:1196-1198) and the centred tridiagonal
+// system of :1430-1499 (matrix Hz(k) - FC(k) - FC(k-1), FC(k) = -lambda dt Akt(k) / (z_r(k+1) - z_r(k))) returns the tracer.
+template <int HADV, int VADV, bool SPL = true>
 __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
@@ -295,7 +321,8 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
   const double cffh = p.dt * pm * pn;
   const double dt = p.dt;
   // ---- pass 1 (upward): t(nnew) - advection, /Hz -> x(k), parked in t(nnew); forward elimination
-  struct Lvl { AdvIn a; double tn, hz, W, akt, tk3; };
+  struct Lvl { AdvIn a; double tn, hz, W, akt, tk3, zr; };
+  const double* __restrict__ z_r = f.z_r;
   auto load_level = [&](int k) -> Lvl {
     const int o = o2 + k * PL;
     Lvl L;
@@ -304,14 +331,18 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
     L.a = adv_load(t3, Huon, Hvom, o, i, j, p);
     L.tn = tn[o + i]; L.hz = Hz[o + i]; L.W = W[o + i]; L.akt = Akt[o + i];
     L.tk3 = t3[o2 + ((k + 2 <= N) ? (k + 2) : N) * PL + i];                // t(k+2), clamped
+    L.zr = SPL ? 0.0 : z_r[o + i];
     return L;
   };
   double FCs[VADV == 3 ? MAXN + 1 : 1], CFs[VADV == 3 ? MAXN + 1 : 1];
   if (VADV == 3) vspline_flux<false>(t3, Hz, W, o2 + i, N, PL, FCs, CFs);         // SPLINES (step3d_t.F:894-937)
   double AKm = Akt[o2 + i], AKmm = 0.0, AKN;
+  double topDC = 0.0;                                                      // !SPL: DC(N) of the centred system
   {
     double tkm1 = t3[o2 + PL + i], tk = tkm1, tkp1 = t3[o2 + 2 * PL + i], tkp2 = t3[o2 + 3 * PL + i];
     double FCm = 0.0, hm = 0.0, om = 0.0, xm = 0.0, CFp = 0.0, DCp = 0.0;
+    double zm = 0.0, FDmm = 0.0;                                           // !SPL: z_r(k-1), FC(k-2) of the diffusion matrix
+    const double cffd = -dt * p.lambda;
     auto level = [&](const Lvl& cur, const Lvl& nxt, int k) {
       const double hk = cur.hz;
       const double ok = 1.0 / hk;
@@ -327,13 +358,22 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
       const double FCk = (VADV == 3) ? FCs[VADV == 3 ? k : 0] : ((k < N) ? vflux4<VADV>(tkm1, tk, tkp1, tkp2, k, N, cur.W) : 0.0);
       const double cv = cffh * (FCk - FCm);
       tv = tv - cv;
-      tv = tv * ok;
-      tn[o2 + k * PL + i] = tv;
+      if (SPL) tv = tv * ok;
+      if (SPL) tn[o2 + k * PL + i] = tv;                                   // (the centred system needs no parked copy)
       if (k >= 2) {
-        spline_forward(hm, om, hk, ok, AKmm, AKm, AKk, tv - xm, dt, CFp, DCp);
+        if (SPL) spline_forward(hm, om, hk, ok, AKmm, AKm, AKk, tv - xm, dt, CFp, DCp);
+        else {                                                             // row m = k-1 (:1431-1461)
+          const double cff1 = 1.0 / (cur.zr - zm);
+          const double FDm = cffd * cff1 * AKm;
+          const double BCm = hm - FDm - FDmm;
+          const double cf = 1.0 / (BCm - FDmm * CFp);
+          CFp = cf * FDm;
+          DCp = cf * (xm - FDmm * DCp);
+          FDmm = FDm;
+        }
         sCF[(k - 2) * TS] = CFp; sDC[(k - 2) * TS] = DCp;
       }
-      AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = tv; FCm = FCk;
+      AKmm = AKm; AKm = AKk; hm = hk; om = ok; xm = tv; FCm = FCk; zm = cur.zr;
       tkm1 = tk; tk = tkp1; tkp1 = tkp2; tkp2 = nxt.tk3;
     };
 #if S3T_RING > 0
@@ -361,7 +401,7 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
         const double* r = ring + ((k - 1) % D) * NF * TS;
         Lvl cur;
         cur.a = AdvIn{r[0], r[TS], r[2 * TS], r[3 * TS], r[4 * TS], r[5 * TS], r[6 * TS], r[7 * TS], r[8 * TS], r[9 * TS], r[10 * TS], r[11 * TS], r[12 * TS]};
-        cur.tn = r[13 * TS]; cur.hz = r[14 * TS]; cur.W = r[15 * TS]; cur.akt = r[16 * TS]; cur.tk3 = r[17 * TS];
+        cur.tn = r[13 * TS]; cur.hz = r[14 * TS]; cur.W = r[15 * TS]; cur.akt = r[16 * TS]; cur.tk3 = r[17 * TS]; cur.zr = 0.0;
         issue(k + D);
         level(cur, cur, k);                                                // only nxt.tk3 is read from the second argument
       }
@@ -370,9 +410,16 @@ __global__ void __launch_bounds__(TS, S3T_MINB) k_step3d_t(Par p, Flds f) {
     sweep_levels<S3T_PP>(N, load_level, level);
 #endif
     AKN = AKm;
+    if (!SPL) topDC = (xm - FDmm * DCp) / (hm - FDmm - FDmm * CFp);         // :1462-1470
   }
   // ---- pass 2 (downward): back substitution + update + t3dbc / periodic images
-  {
+  if (!SPL) {                                                              // :1471-1499: t(k) = DC(k) - CF(k) t(k+1)
+    double dk = topDC;
+    for (int k = N; k >= 1; --k) {
+      if (k < N) dk = sDC[(k - 1) * TS] - sCF[(k - 1) * TS] * dk;
+      st_r_grad(tn, o2 + k * PL, i, j, dk, p);
+    }
+  } else {
     double dk = 0.0;
     double ak = dk * AKN;
     for (int kt = N; kt >= 1; kt -= CHT) {
@@ -415,6 +462,14 @@ void launch_step3d_uv(const Par& p, const Flds& f, cudaStream_t s) {
   size_t& al = allowed[cur_dev()];
   if (sm > al) { allow_smem(k_step3d_uv<0>, sm); allow_smem(k_step3d_uv<1>, sm); al = sm; }
   const int nbx = (xspan(p) + TS - 1) / TS;
+  if (p.nospl_vvisc) {                                                   // SPLINES_VVISC not defined
+    static size_t allowed2[MAXDEV] = {0};
+    size_t& a2 = allowed2[cur_dev()];
+    if (sm > a2) { allow_smem(k_step3d_uv<0, false>, sm); allow_smem(k_step3d_uv<1, false>, sm); a2 = sm; }
+    k_step3d_uv<0, false><<<dim3(nbx, p.Mm), TS, sm, s>>>(p, f);
+    k_step3d_uv<1, false><<<dim3(nbx, p.Mm - 1), TS, sm, s>>>(p, f);
+    return;
+  }
   k_step3d_uv<0><<<dim3(nbx, p.Mm), TS, sm, s>>>(p, f);
   k_step3d_uv<1><<<dim3(nbx, p.Mm - 1), TS, sm, s>>>(p, f);
 }
@@ -424,9 +479,10 @@ static void launch_s3t(const Par& p, const Flds& f, cudaStream_t s) {
   const size_t sm = smem_cols_t(p.N);
   static size_t allowed[MAXDEV] = {0};
   size_t& al = allowed[cur_dev()];
-  if (sm > al) { allow_smem(k_step3d_t<H, V>, sm); al = sm; }
+  if (sm > al) { allow_smem(k_step3d_t<H, V>, sm); allow_smem(k_step3d_t<H, V, false>, sm); al = sm; }
   const int nbx = (xspan(p) + TS - 1) / TS;
-  k_step3d_t<H, V><<<dim3(nbx * p.NT, p.Mm), TS, sm, s>>>(p, f);
+  if (p.nospl_vdiff) k_step3d_t<H, V, false><<<dim3(nbx * p.NT, p.Mm), TS, sm, s>>>(p, f);       // SPLINES_VDIFF not defined
+  else k_step3d_t<H, V><<<dim3(nbx * p.NT, p.Mm), TS, sm, s>>>(p, f);
 }
 template <int H>
 static void launch_s3t_v(const Par& p, const Flds& f, cudaStream_t s) {

@@ -66,7 +66,7 @@ void* emu_create(const int* io, const double* dv) {
   p.dt = dv[0]; p.g = dv[1]; p.rho0 = dv[2]; p.R0 = dv[3]; p.T0 = dv[4]; p.S0 = dv[5]; p.Tcoef = dv[6]; p.Scoef = dv[7];
   p.gamma2 = dv[8]; p.lambda = dv[9]; p.hc = dv[10]; p.Akv_bak = dv[11]; p.Akt_bak[0] = dv[12]; p.Akt_bak[1] = dv[13];
   p.blk_ZQ = dv[14]; p.blk_ZT = dv[15]; p.blk_ZW = dv[16];
-  p.dtfast = p.dt / (double)io[23]; p.limit_bstress = io[24];
+  p.dtfast = p.dt / (double)io[23]; p.limit_bstress = io[24]; p.nospl_vvisc = io[27]; p.nospl_vdiff = io[28];
 #define A2(name) e->add(#name, &f.name, 0, 1)
 #define A3(name, k0, nk) e->add(#name, &f.name, k0, nk)
   A2(h); A2(f); A2(pm); A2(pn); A2(om_r); A2(on_r); A2(om_u); A2(on_u); A2(om_v); A2(on_v); A2(om_p); A2(on_p); A2(omn); A2(fomn);

@@ -32,6 +32,9 @@ CASES = {
     "seamount_wj": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, dj_gradps=3)),
     "benchmark_limit": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, limit_bstress=1, uv_qdrag=0, rdrg=5.0)),   # LIMIT_BSTRESS, with a linear drag strong enough to hit the limit
     "upwelling_limit": (orc.APP_UPWELLING, dict(Lm=20, Mm=24, N=8, limit_bstress=1, rdrg=0.5)),
+    "benchmark_nospl": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, nospl_vvisc=1, nospl_vdiff=1)),     # SPLINES_VVISC / SPLINES_VDIFF undefined
+    "seamount_nospl": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, nospl_vvisc=1, nospl_vdiff=1)),
+    "upwelling_nospl_n30": (orc.APP_UPWELLING, dict(Lm=20, Mm=24, N=30, nospl_vvisc=1, nospl_vdiff=0)),
     "benchmark_splines": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, vadv=3)),
     "benchmark_bvf": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, bv_frequency=1, bvf_mixing=1)),
     "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, mix_geo_ts=1)),

@@ -259,10 +259,12 @@ def test_physics_kat_shallow_water_wave_speed(H):
     assert np.max(np.abs(o.field("vbar1"))) < 1e-12          # the problem stays one-dimensional
 
 
-def test_physics_kat_vertical_diffusion_decay():
-    """Analytical known answer for the implicit vertical-diffusion solve (pre_step3d + step3d_t, SPLINES_VDIFF): at rest
-    over a flat bottom with constant Akt and no-flux boundaries, the mode cos(pi (z+H)/H) decays as exp(-Akt (pi/H)^2 t)."""
-    o = orc.Oracle(orc.APP_SEAMOUNT)
+@pytest.mark.parametrize("nospl", [0, 1])
+def test_physics_kat_vertical_diffusion_decay(nospl):
+    """Analytical known answer for the implicit vertical-diffusion solve (pre_step3d + step3d_t): at rest over a flat bottom with
+    constant Akt and no-flux boundaries, the mode cos(pi (z+H)/H) decays as exp(-Akt (pi/H)^2 t).  nospl = 0: SPLINES_VDIFF
+    (step3d_t.F:1370-1427); 1: the centred tridiagonal system used when SPLINES_VDIFF is not defined (:1430-1499)."""
+    o = orc.Oracle(orc.APP_SEAMOUNT, nospl_vdiff=nospl, nospl_vvisc=nospl)
     o.run_phase("set_data")
     H, K, nsteps = 1000.0, 1.0, 50
     o.field("h")[...] = H

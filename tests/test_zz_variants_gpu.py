@@ -27,6 +27,9 @@ VARIANTS = {
     "wj": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, dj_gradps=3)),                          # WJ_GRADP: prsgrd31.h, weighted Jacobian
     "wj_seamount": (orc.APP_SEAMOUNT, dict(dj_gradps=3)),
     "limit_bstress": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, limit_bstress=1, uv_qdrag=0, rdrg=5.0)),   # LIMIT_BSTRESS with a linear drag that hits the limit
+    "nospl": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, nospl_vvisc=1, nospl_vdiff=1)),       # SPLINES_VVISC / SPLINES_VDIFF undefined
+    "nospl_seamount": (orc.APP_SEAMOUNT, dict(nospl_vvisc=1, nospl_vdiff=1)),
+    "nospl_n30": (orc.APP_BENCHMARK, dict(Lm=96, Mm=40, N=30, nospl_vvisc=0, nospl_vdiff=1, vadv=3)),
     "uv_sadv": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, uv_adv=2)),                      # UV_SADVECTION: spline vertical advection
     "uv_sadv_seamount": (orc.APP_SEAMOUNT, dict(uv_adv=2)),
     "ts_dif4": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, ts_dif4=1, tnu4=TNU4)),
@@ -50,7 +53,7 @@ def test_variants_strict_bit_exact_every_phase(case, spinup):
     t.close()
 
 
-@pytest.mark.parametrize("case", ["uv_c4", "uv_c2", "uv_sadv", "p40", "wj", "ts_dif4", "both_n30"])
+@pytest.mark.parametrize("case", ["uv_c4", "uv_c2", "uv_sadv", "p40", "wj", "ts_dif4", "both_n30", "nospl", "nospl_seamount"])
 def test_variants_strict_bit_exact_multistep(case):
     """Whole steps (the captured step graph; t3dmix2_s fused into pre_step3d_t with t3dmix4_s behind it)."""
     app, kw = VARIANTS[case]
