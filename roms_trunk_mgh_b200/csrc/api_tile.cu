@@ -148,10 +148,10 @@ const RoutineArgs kRoutineArgs[] = {
      "zeta1,zeta2,zeta3,ubar1,ubar2,ubar3,vbar1,vbar2,vbar3,rzeta1,rzeta2,rubar1,rubar2,rvbar1,rvbar2,Zt_avg1,DU_avg1,DU_avg2,"
      "DV_avg1,DV_avg2,rufrc,rvfrc,ru1,ru2,rv1,rv2"},
     {ROMS_B200_SET_DEPTH, "h,Zt_avg1", "z_r,z_w,Hz"},
-    {ROMS_B200_STEP3D_UV, "Akv,Hz,ru1,ru2,rv1,rv2,DU_avg1,DU_avg2,DV_avg1,DV_avg2,pm,pn,on_u,om_v,u1,u2,v1,v2,Huon,Hvom",
+    {ROMS_B200_STEP3D_UV, "Akv,Hz,ru1,ru2,rv1,rv2,DU_avg1,DU_avg2,DV_avg1,DV_avg2,pm,pn,on_u,om_v,u1,u2,v1,v2,Huon,Hvom,?z_r",
      "u1,u2,v1,v2,Huon,Hvom,ubar1,ubar2,vbar1,vbar2"},
     {ROMS_B200_OMEGA2, "Huon,Hvom,z_w", "W"},
-    {ROMS_B200_STEP3D_T, "Hz,Huon,Hvom,W,Akt_*,pm,pn,t1_*,t2_*,t3_*", "t1_*,t2_*"},
+    {ROMS_B200_STEP3D_T, "Hz,Huon,Hvom,W,Akt_*,pm,pn,t1_*,t2_*,t3_*,?z_r", "t1_*,t2_*"},
     // cfg.bulk_fluxes / cfg.lmd_mixing (with the switches lmd_mixing needs) must be set in roms_b200_tile_t.cfg for these two
     {ROMS_B200_BULK_FLUX, "t1_*,t2_*,Uwind,Vwind,Tair,Pair,Hair,rain,cloud,srflx", "lrflx,lhflx,shflx,stflux_*,sustr,svstr"},
     {ROMS_B200_LMD_VMIX, "f,Hz,z_w,u1,u2,v1,v2,pden,bvf,alpha,beta,srflx,Jwtype,stflx_*,sustr,svstr,bustr,bvstr,hsbl,Akv,Akt_*",
