@@ -88,9 +88,13 @@ typedef struct roms_b200_config {
                                    (default horizontal branch, parabolic splines in the vertical: rhs3d.F:1016-1078, :1267-1329),
                                    3 UV_C2ADVECTION (second-order centred in rhs3d.F:605-657, :1079-1107, :1330-1361 AND in step2d,
                                    step2d_LF_AM3.h:1026-1080; LOOP_2D then runs as per-call kernels)                                */
+  int qcorrection;              /* QCORRECTION (set_vbc.F:285-299): stflx(itemp) += dqdt (SST - sst); fields "dqdt", "sst" (FORCES)        */
+  int limit_stflx_cooling;      /* LIMIT_STFLX_COOLING (:301-328): a cooling heat flux is suppressed where SST < -2 degC                       */
+  int scorrection;              /* 1 SCORRECTION, 2 SRELAXATION (:344-351) with Tnudg_salt = Tnudg(isalt) (1/s); field "sss"; Hz is read      */
   int ts_dif4;                  /* TS_DIF4 + MIX_S_TS: biharmonic tracer mixing along s-surfaces (t3dmix4_s.h:215-476), phase
                                    ROMS_B200_T3DMIX4, after the harmonic operator (rhs3d.F:81-97); field "diff4_<itrc>" =
                                    MIXING%diff4 = SQRT(ABS(tnu4)) (read_phypar.F:6905); not with mix_geo_ts                   */
+  double Tnudg_salt;            /* Tnudg(isalt,ng) of SCORRECTION / SRELAXATION, 1/s (roms_*.in TNUDG, converted by read_phypar.F)                 */
 } roms_b200_config;
 
 /* Fills *cfg with the shipped defaults of roms_<app>.in (Lm,Mm,N = 0 keeps the shipped grid size). */

@@ -17,12 +17,12 @@ bool lookup(Model& m, const std::string& name, double** p, int dims[6]) {
                              "pmon_u", "pnom_u", "pmon_v", "pnom_v", "pmon_p", "pnom_p", "dndx", "dmde", "rdrag", "rdrag2", "ZoBot", "visc2_r", "visc2_p",
                              "Zt_avg1", "DU_avg1", "DU_avg2", "DV_avg1", "DV_avg2", "rufrc", "rvfrc", "rhoA", "rhoS", "sustr", "svstr", "bustr", "bvstr",
                              "avgzeta", "avgu2d", "avgv2d", "alpha", "beta", "srflx", "Jwtype",
-                             "Uwind", "Vwind", "Tair", "Pair", "Hair", "rain", "cloud", "lrflx", "lhflx", "shflx", "hsbl", "ksbl", "latr", "lonr"};
+                             "Uwind", "Vwind", "Tair", "Pair", "Hair", "rain", "cloud", "lrflx", "lhflx", "shflx", "hsbl", "ksbl", "latr", "lonr", "sst", "dqdt", "sss"};
   F2* a2[] = {&m.h, &m.f, &m.pm, &m.pn, &m.om_r, &m.on_r, &m.om_u, &m.on_u, &m.om_v, &m.on_v, &m.om_p, &m.on_p, &m.omn, &m.fomn, &m.pmon_r, &m.pnom_r,
               &m.pmon_u, &m.pnom_u, &m.pmon_v, &m.pnom_v, &m.pmon_p, &m.pnom_p, &m.dndx, &m.dmde, &m.rdrag, &m.rdrag2, &m.ZoBot, &m.visc2_r, &m.visc2_p,
               &m.Zt_avg1, &m.DU_avg1, &m.DU_avg2, &m.DV_avg1, &m.DV_avg2, &m.rufrc, &m.rvfrc, &m.rhoA, &m.rhoS, &m.sustr, &m.svstr, &m.bustr, &m.bvstr,
               &m.avgzeta, &m.avgu2d, &m.avgv2d, &m.alpha, &m.beta, &m.srflx, &m.Jwtype,
-              &m.Uwind, &m.Vwind, &m.Tair, &m.Pair, &m.Hair, &m.rain, &m.cloud, &m.lrflx, &m.lhflx, &m.shflx, &m.hsbl, &m.ksbl, &m.latr, &m.lonr};
+              &m.Uwind, &m.Vwind, &m.Tair, &m.Pair, &m.Hair, &m.rain, &m.cloud, &m.lrflx, &m.lhflx, &m.shflx, &m.hsbl, &m.ksbl, &m.latr, &m.lonr, &m.sst, &m.dqdt, &m.sss};
   for (size_t i = 0; i < sizeof(n2) / sizeof(n2[0]); ++i) if (name == n2[i]) return set2(*a2[i]);
   static const char* n3[] = {"rho", "pden", "Hz", "z_r", "Huon", "Hvom", "W", "wvel", "z_w", "Akv", "avgu3d", "avgv3d", "avgrho", "avgw3d", "avgwvel", "bvf"};
   F3* a3[] = {&m.rho, &m.pden, &m.Hz, &m.z_r, &m.Huon, &m.Hvom, &m.W, &m.wvel, &m.z_w, &m.Akv, &m.avgu3d, &m.avgv3d, &m.avgrho, &m.avgw3d, &m.avgwvel, &m.bvf};
@@ -95,6 +95,8 @@ int orc_set_option(void* hp, const char* key, double val) {
   else if (k == "bvf_mixing") c.bvf_mixing = (int)val;
   else if (k == "uv_adv") c.uv_adv = (int)val; else if (k == "ts_dif4") c.ts_dif4 = (int)val;
   else if (k == "tnu4") { c.tnu4[0] = c.tnu4[1] = val; } else if (k == "limit_bstress") c.limit_bstress = (int)val;
+  else if (k == "qcorrection") c.qcorrection = (int)val; else if (k == "limit_stflx_cooling") c.limit_stflx_cooling = (int)val;
+  else if (k == "scorrection") c.scorrection = (int)val; else if (k == "Tnudg_salt") c.Tnudg_salt = val;
   else if (k == "nospl_vvisc") c.nospl_vvisc = (int)val; else if (k == "nospl_vdiff") c.nospl_vdiff = (int)val;
   else if (k == "rdrg2") c.rdrg2 = val; else if (k == "rdrg") c.rdrg = val;
   else if (k == "bulk_fluxes") c.bulk_fluxes = (int)val; else if (k == "lmd_mixing") c.lmd_mixing = (int)val;
@@ -115,6 +117,8 @@ double orc_get_option(void* hp, const char* key) {
   if (k == "bv_frequency") return c.bv_frequency; if (k == "eos_tderivative") return c.eos_tderivative;
   if (k == "solar_source") return c.solar_source; if (k == "lmd_nonlocal") return c.lmd_nonlocal;
   if (k == "bvf_mixing") return c.bvf_mixing; if (k == "itemp") return c.itemp; if (k == "isalt") return c.isalt;
+  if (k == "qcorrection") return c.qcorrection; if (k == "limit_stflx_cooling") return c.limit_stflx_cooling;
+  if (k == "scorrection") return c.scorrection; if (k == "Tnudg_salt") return c.Tnudg_salt;
   if (k == "nospl_vvisc") return c.nospl_vvisc; if (k == "nospl_vdiff") return c.nospl_vdiff;
   if (k == "limit_bstress") return c.limit_bstress; if (k == "rdrg2") return c.rdrg2; if (k == "rdrg") return c.rdrg;
   if (k == "uv_adv") return c.uv_adv; if (k == "ts_dif4") return c.ts_dif4; if (k == "tnu4") return c.tnu4[0];

@@ -194,11 +194,31 @@ void set_vbc(Model& m, const Bnd& b) {
   const int it = c.itemp - 1;
   for (int j = JstrR; j <= JendR; ++j)
     for (int i = IstrR; i <= IendR; ++i) { m.stflx[it](i, j) = m.stflux[it](i, j); m.btflx[it](i, j) = m.btflux[it](i, j); }
+  if (c.qcorrection) {                                            // QCORRECTION :285-299
+    F3 T = m.t[nrhs][it];
+    for (int j = JstrR; j <= JendR; ++j)
+      for (int i = IstrR; i <= IendR; ++i) m.stflx[it](i, j) = m.stflx[it](i, j) + m.dqdt(i, j) * (T(i, j, N) - m.sst(i, j));
+  }
+  if (c.limit_stflx_cooling) {                                    // LIMIT_STFLX_COOLING :301-328
+    F3 T = m.t[nrhs][it];
+    const double cff1 = -2.0;
+    for (int j = JstrR; j <= JendR; ++j)
+      for (int i = IstrR; i <= IendR; ++i) {
+        const double cff2 = m.stflx[it](i, j);
+        const double cff3 = 0.5 * (1.0 + std::copysign(1.0, cff1 - T(i, j, N)));
+        m.stflx[it](i, j) = cff2 - cff3 * 0.5 * (cff2 - std::fabs(cff2));
+      }
+  }
   if (c.salinity && c.NT >= 2) {
     const int is = c.isalt - 1; F3 S = m.t[nrhs][is];
     for (int j = JstrR; j <= JendR; ++j)
       for (int i = IstrR; i <= IendR; ++i) {
         double EmP = m.stflux[is](i, j);
+        if (c.scorrection == 1)                                   // SCORRECTION :344-347
+          m.stflx[is](i, j) = EmP * S(i, j, N) - c.Tnudg_salt * m.Hz(i, j, N) * (S(i, j, N) - m.sss(i, j));
+        else if (c.scorrection == 2)                              // SRELAXATION :348-350
+          m.stflx[is](i, j) = -c.Tnudg_salt * m.Hz(i, j, N) * (S(i, j, N) - m.sss(i, j));
+        else
         m.stflx[is](i, j) = EmP * S(i, j, N);
         m.btflx[is](i, j) = m.btflx[is](i, j) * S(i, j, 1);
       }

@@ -140,6 +140,10 @@ struct Cfg {
   int uv_adv = 0;                 // momentum advection: 0 default (U3 horizontal, C4 vertical), 1 UV_C4ADVECTION (rhs3d.F:685-921, :1108-1175), 2 UV_SADVECTION (:1016-1078, :1267-1329), 3 UV_C2ADVECTION (:605-657, :1079-1107; step2d_LF_AM3.h:1026-1080)
   int nospl_vvisc = 0, nospl_vdiff = 0;   // 1: SPLINES_VVISC / SPLINES_VDIFF UNdefined -> centred implicit vertical viscosity / diffusion
                                           // (step3d_uv.F:397-462, :730-795; step3d_t.F:1430-1499) instead of the parabolic splines
+  int qcorrection = 0;            // QCORRECTION: stflx(itemp) += dqdt (SST - sst) (set_vbc.F:285-299)
+  int limit_stflx_cooling = 0;    // LIMIT_STFLX_COOLING: no further cooling below -2 degC (:301-328)
+  int scorrection = 0;            // 1 SCORRECTION, 2 SRELAXATION (:344-351), with Tnudg(isalt) = Tnudg_salt (1/s)
+  double Tnudg_salt = 0.0;
   int limit_bstress = 0;          // LIMIT_BSTRESS (set_vbc.F:533-540): |bottom stress| <= 0.75 |u| Hz / dt
   int ts_dif4 = 0;                // TS_DIF4 (+ MIX_S_TS): t3dmix4_s.h after t3dmix2 (rhs3d.F:81-97)
   // physical parameters
@@ -202,6 +206,7 @@ struct Model {
   F3 bvf; F2 alpha, beta;                       // rho_eos optional outputs (bvf k=0..N)
   F2 srflx, Jwtype; F3 ghats[2];                // mod_forces.F srflx; mod_mixing.F Jwtype, ghats (k=0..N)
   F2 Uwind, Vwind, Tair, Pair, Hair, rain, cloud, lrflx, lhflx, shflx;   // mod_forces.F (BULK_FLUXES)
+  F2 sst, dqdt, sss;                            // mod_forces.F: QCORRECTION / SCORRECTION / SRELAXATION data
   F2 hsbl, ksbl;                                // mod_mixing.F (LMD_SKPP); ksbl is INTEGER in the reference, kept as whole doubles
   // ---- time-averaged fields (mod_average.F; set_avg.cpp)
   F2 avgzeta, avgu2d, avgv2d; F3 avgu3d, avgv3d, avgrho, avgt[2];   // k=1..N

@@ -158,7 +158,7 @@ void Model::allocate() {
   for (int it = 0; it < c.NT; ++it) Akt[it] = new3(0, N);
   bvf = new3(0, N); alpha = new2(); beta = new2(); srflx = new2(); Jwtype = new2();
   for (int it = 0; it < c.NT; ++it) ghats[it] = new3(0, N);
-  { F2* f2[] = {&Uwind, &Vwind, &Tair, &Pair, &Hair, &rain, &cloud, &lrflx, &lhflx, &shflx, &hsbl, &ksbl}; for (F2* p_ : f2) *p_ = new2(); }   // hsbl: IniVal = 0 (mod_mixing.F:1508)
+  { F2* f2[] = {&Uwind, &Vwind, &Tair, &Pair, &Hair, &rain, &cloud, &lrflx, &lhflx, &shflx, &hsbl, &ksbl, &sst, &dqdt, &sss}; for (F2* p_ : f2) *p_ = new2(); }   // hsbl: IniVal = 0 (mod_mixing.F:1508)
   for (int j = LBj; j <= UBj; ++j) for (int i = LBi; i <= UBi; ++i) Jwtype(i, j) = 1.0;      // roms_benchmark1.in WTYPE == 1
   avgzeta = new2(); avgu2d = new2(); avgv2d = new2(); avgu3d = new3(1, N); avgv3d = new3(1, N); avgrho = new3(1, N);
   avgw3d = new3(0, N); avgwvel = new3(0, N);

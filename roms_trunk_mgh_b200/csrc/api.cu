@@ -368,7 +368,7 @@ int ensure_optional(roms_b200_state* h, int phase) {
   if (!h->lazy) return NoError;
   std::vector<std::string> names;
   if (phase == ROMS_B200_RHO_EOS) names = {"bvf", "alpha", "beta"};
-  else if (phase == ROMS_B200_SET_VBC) { if (h->cfg.uv_qdrag == 2) names = {"ZoBot", "z_r", "z_w"}; if (h->cfg.limit_bstress) names.push_back("Hz"); }
+  else if (phase == ROMS_B200_SET_VBC) { if (h->cfg.uv_qdrag == 2) names = {"ZoBot", "z_r", "z_w"}; if (h->cfg.limit_bstress || h->cfg.scorrection) names.push_back("Hz"); }
   else if (phase == ROMS_B200_BULK_FLUX) names = {"lrflx", "lhflx", "shflx", "sustr", "svstr", "stflux_" + std::to_string(h->cfg.itemp - 1)};
   else if (phase == ROMS_B200_LMD_VMIX) { names = {"hsbl", "ksbl", "Akv"}; for (int it = 0; it < h->cfg.NT; ++it) { names.push_back("ghats_" + std::to_string(it)); names.push_back("Akt_" + std::to_string(it)); } }
   else if (phase == ROMS_B200_PRE_STEP3D) { names = {"srflx", "Jwtype", "z_w"}; for (int it = 0; it < h->cfg.NT; ++it) names.push_back("ghats_" + std::to_string(it)); }
@@ -699,6 +699,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   if (cfg->bvf_mixing && !cfg->bv_frequency) return ConfigError;
   if (cfg->uv_adv < 0 || cfg->uv_adv > 3) return ConfigError;
   if (cfg->dj_gradps < 0 || cfg->dj_gradps > 3) return ConfigError;
+  if (cfg->scorrection < 0 || cfg->scorrection > 2 || (cfg->scorrection && !(cfg->salinity && cfg->NT >= 2))) return ConfigError;
   if (cfg->ts_dif4 && cfg->mix_geo_ts) return ConfigError;                          // t3dmix4_geo.h is not built
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
@@ -745,6 +746,8 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   p.bv_frequency = cfg->bv_frequency; p.eos_tderivative = cfg->eos_tderivative; p.solar_source = cfg->solar_source; p.lmd_nonlocal = cfg->lmd_nonlocal;
   p.bulk_fluxes = cfg->bulk_fluxes; p.lmd_mixing = cfg->lmd_mixing; p.uv_adv = cfg->uv_adv; p.limit_bstress = cfg->limit_bstress;
   p.nospl_vvisc = cfg->nospl_vvisc ? 1 : 0; p.nospl_vdiff = cfg->nospl_vdiff ? 1 : 0;
+  p.qcorrection = cfg->qcorrection ? 1 : 0; p.limit_stflx_cooling = cfg->limit_stflx_cooling ? 1 : 0; p.scorrection = cfg->scorrection;
+  p.pad2_ = 0; p.Tnudg_salt = cfg->Tnudg_salt;
   p.blk_ZQ = cfg->blk_ZQ > 0.0 ? cfg->blk_ZQ : 10.0; p.blk_ZT = cfg->blk_ZT > 0.0 ? cfg->blk_ZT : 10.0; p.blk_ZW = cfg->blk_ZW > 0.0 ? cfg->blk_ZW : 10.0;
   p.dt = cfg->dt; p.g = cfg->g; p.rho0 = cfg->rho0; p.R0 = cfg->R0; p.T0 = cfg->T0; p.S0 = cfg->S0; p.Tcoef = cfg->Tcoef; p.Scoef = cfg->Scoef;
   p.gamma2 = cfg->gamma2; p.lambda = cfg->lambda; p.hc = cfg->hc; p.Akv_bak = cfg->Akv_bak;
@@ -793,6 +796,8 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
     rc |= alloc_field(h, "btflux_" + s, &f.btflux[it], 0, 1);
   }
   if (cfg->uv_qdrag == 2) rc |= alloc_field(h, "ZoBot", &f.ZoBot, 0, 1);
+  if (cfg->qcorrection) { rc |= alloc_field(h, "sst", &f.sst, 0, 1); rc |= alloc_field(h, "dqdt", &f.dqdt, 0, 1); }
+  if (cfg->scorrection) rc |= alloc_field(h, "sss", &f.sss, 0, 1);
   if (cfg->bv_frequency) rc |= alloc_field(h, "bvf", &f.bvf, 0, N + 1);
   if (cfg->eos_tderivative) { rc |= alloc_field(h, "alpha", &f.alpha, 0, 1); rc |= alloc_field(h, "beta", &f.beta, 0, 1); }
   if (cfg->solar_source || cfg->bulk_fluxes) rc |= alloc_field(h, "srflx", &f.srflx, 0, 1);

@@ -125,7 +125,7 @@ struct RoutineArgs { int phase; const char* in; const char* out; };
 const RoutineArgs kRoutineArgs[] = {
     {ROMS_B200_SET_MASSFLUX, "u1,u2,v1,v2,Hz,on_u,om_v", "Huon,Hvom"},
     {ROMS_B200_RHO_EOS, "t1_*,t2_*,z_r,z_w,Hz", "rho,pden,rhoA,rhoS,?bvf,?alpha,?beta"},
-    {ROMS_B200_SET_VBC, "u1,u2,v1,v2,t1_*,t2_*,rdrag,rdrag2,stflux_*,btflux_*,?ZoBot,?z_r,?z_w,?Hz", "bustr,bvstr,stflx_*,btflx_*"},
+    {ROMS_B200_SET_VBC, "u1,u2,v1,v2,t1_*,t2_*,rdrag,rdrag2,stflux_*,btflux_*,?ZoBot,?z_r,?z_w,?Hz,?sst,?dqdt,?sss", "bustr,bvstr,stflx_*,btflx_*"},
     {ROMS_B200_ANA_VMIX, "z_w", "Akv,Akt_*"},
     {ROMS_B200_OMEGA, "Huon,Hvom,z_w", "W"},
     {ROMS_B200_WVELOCITY, "u1,u2,v1,v2,z_r,z_w,W,DU_avg1,DV_avg1,pm,pn", "wvel"},

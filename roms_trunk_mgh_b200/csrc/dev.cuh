@@ -44,6 +44,8 @@ struct Par {
   int uv_adv;                     // rhs3d momentum advection: 0 default (U3 / C4), 1 UV_C4ADVECTION, 2 UV_SADVECTION, 3 UV_C2ADVECTION (also in step2d)
   int limit_bstress;              // LIMIT_BSTRESS in set_vbc
   int nospl_vvisc, nospl_vdiff;   // 1: SPLINES_VVISC / SPLINES_VDIFF not defined (centred implicit systems in step3d_uv / step3d_t)
+  int qcorrection, limit_stflx_cooling, scorrection, pad2_;   // set_vbc surface-flux corrections (set_vbc.F:285-351)
+  double Tnudg_salt;
 };
 
 // Field table (all pointers pre-offset; [0] slots of time-indexed arrays are unused so Fortran indices apply)
@@ -75,6 +77,8 @@ struct Flds {
   double *sc_r, *Cs_r, *sc_w, *Cs_w;
   // TS_DIF4: MIXING%diff4 = SQRT(ABS(tnu4)) (t3dmix4_s.h)
   double* diff4[MAXNT];
+  // QCORRECTION / SCORRECTION / SRELAXATION data (mod_forces.F)
+  double *sst, *dqdt, *sss;
 };
 
 constexpr int EDGE_W = 64;        // width of the tile edges computed ahead of the halo exchange (multiple of every CTA width)

@@ -187,12 +187,22 @@ __global__ void __launch_bounds__(256) k_set_vbc(Par p, Flds f) {
   const int o2 = j * p.P, o1 = o2 + p.PL;                       // k = 1
   {
     const int it = p.itemp - 1;
-    f.stflx[it][o2 + i] = f.stflux[it][o2 + i];
+    double sf = f.stflux[it][o2 + i];
+    if (p.qcorrection) sf = sf + f.dqdt[o2 + i] * (f.t[p.nrhs][it][o2 + p.N * p.PL + i] - f.sst[o2 + i]);       // QCORRECTION :285-299
+    if (p.limit_stflx_cooling) {                                                                             // LIMIT_STFLX_COOLING :301-328
+      const double cff3 = 0.5 * (1.0 + copysign(1.0, -2.0 - f.t[p.nrhs][it][o2 + p.N * p.PL + i]));
+      sf = sf - cff3 * 0.5 * (sf - fabs(sf));
+    }
+    f.stflx[it][o2 + i] = sf;
     f.btflx[it][o2 + i] = f.btflux[it][o2 + i];
     if (p.salinity && p.NT >= 2) {
       const int is = p.isalt - 1;
       const double* __restrict__ S = f.t[p.nrhs][is];
       const double EmP = f.stflux[is][o2 + i];
+      const int oN = o2 + p.N * p.PL + i;
+      if (p.scorrection == 1) f.stflx[is][o2 + i] = EmP * S[oN] - p.Tnudg_salt * f.Hz[oN] * (S[oN] - f.sss[o2 + i]);   // SCORRECTION :344-347
+      else if (p.scorrection == 2) f.stflx[is][o2 + i] = -p.Tnudg_salt * f.Hz[oN] * (S[oN] - f.sss[o2 + i]);           // SRELAXATION :348-350
+      else
       f.stflx[is][o2 + i] = EmP * S[o2 + p.N * p.PL + i];
       f.btflx[is][o2 + i] = f.btflx[is][o2 + i] * S[o1 + i];
     }

@@ -67,13 +67,14 @@ void* emu_create(const int* io, const double* dv) {
   p.gamma2 = dv[8]; p.lambda = dv[9]; p.hc = dv[10]; p.Akv_bak = dv[11]; p.Akt_bak[0] = dv[12]; p.Akt_bak[1] = dv[13];
   p.blk_ZQ = dv[14]; p.blk_ZT = dv[15]; p.blk_ZW = dv[16];
   p.dtfast = p.dt / (double)io[23]; p.limit_bstress = io[24]; p.nospl_vvisc = io[27]; p.nospl_vdiff = io[28];
+  p.qcorrection = io[29]; p.limit_stflx_cooling = io[30]; p.scorrection = io[31]; p.Tnudg_salt = dv[17];
 #define A2(name) e->add(#name, &f.name, 0, 1)
 #define A3(name, k0, nk) e->add(#name, &f.name, k0, nk)
   A2(h); A2(f); A2(pm); A2(pn); A2(om_r); A2(on_r); A2(om_u); A2(on_u); A2(om_v); A2(on_v); A2(om_p); A2(on_p); A2(omn); A2(fomn);
   A2(pmon_r); A2(pnom_r); A2(pmon_u); A2(pnom_u); A2(pmon_v); A2(pnom_v); A2(pmon_p); A2(pnom_p); A2(dndx); A2(dmde); A2(rdrag); A2(rdrag2);
   A2(visc2_r); A2(visc2_p); A2(Zt_avg1); A2(DU_avg1); A2(DU_avg2); A2(DV_avg1); A2(DV_avg2); A2(rufrc); A2(rvfrc); A2(rhoA); A2(rhoS);
   A2(sustr); A2(svstr); A2(bustr); A2(bvstr); A2(ZoBot); A2(alpha); A2(beta); A2(srflx); A2(Jwtype);
-  A2(Uwind); A2(Vwind); A2(Tair); A2(Pair); A2(Hair); A2(rain); A2(cloud); A2(lrflx); A2(lhflx); A2(shflx); A2(Taux); A2(Tauy); A2(hsbl); A2(ksbl);
+  A2(Uwind); A2(Vwind); A2(Tair); A2(Pair); A2(Hair); A2(rain); A2(cloud); A2(lrflx); A2(lhflx); A2(shflx); A2(Taux); A2(Tauy); A2(hsbl); A2(ksbl); A2(sst); A2(dqdt); A2(sss);
   A3(rho, 1, N); A3(pden, 1, N); A3(Hz, 1, N); A3(z_r, 1, N); A3(Huon, 1, N); A3(Hvom, 1, N); A3(W, 0, N + 1); A3(wvel, 0, N + 1);
   A3(z_w, 0, N + 1); A3(Akv, 0, N + 1); A3(P3, 1, N); A3(bvf, 0, N + 1);
 #undef A2

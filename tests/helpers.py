@@ -6,7 +6,7 @@ from roms_trunk_mgh_b200 import _lib
 from roms_trunk_mgh_b200.ocean import Tile, field_names
 
 APP_OPTS = ["nonlin_eos", "dj_gradps", "curvgrid", "mix_geo_ts", "uv_qdrag", "hadv", "vadv", "ana_vmix", "wvelocity_every_step",
-            "bv_frequency", "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "bvf_mixing", "uv_adv", "ts_dif4", "limit_bstress", "nospl_vvisc", "nospl_vdiff"]
+            "bv_frequency", "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "bvf_mixing", "uv_adv", "ts_dif4", "limit_bstress", "nospl_vvisc", "nospl_vdiff", "qcorrection", "limit_stflx_cooling", "scorrection"]
 
 
 def cfg_from_oracle(o, device=0):
@@ -22,6 +22,7 @@ def cfg_from_oracle(o, device=0):
     cfg.R0 = o.opt("R0"); cfg.T0 = o.opt("T0"); cfg.S0 = o.opt("S0"); cfg.Tcoef = o.opt("Tcoef"); cfg.Scoef = o.opt("Scoef")
     cfg.Akt_bak[0] = cfg.Akt_bak[1] = o.opt("Akt_bak"); cfg.Akv_bak = o.opt("Akv_bak")
     cfg.gamma2 = o.opt("gamma2"); cfg.lambda_ = o.opt("lambda"); cfg.hc = o.opt("hc")
+    cfg.Tnudg_salt = o.opt("Tnudg_salt")
     cfg.blk_ZQ = o.opt("blk_ZQ"); cfg.blk_ZT = o.opt("blk_ZT"); cfg.blk_ZW = o.opt("blk_ZW")
     cfg.device = device
     return cfg
@@ -42,6 +43,8 @@ def optional_names(o):
     if o.opt("bulk_fluxes"): v += [n for n in ATMOSPHERE if n not in v] + ["lrflx", "lhflx", "shflx"]
     if o.opt("lmd_mixing"): v += ["hsbl", "ksbl"]
     if o.opt("ts_dif4"): v += [f"diff4_{it}" for it in range(NT)]
+    if o.opt("qcorrection"): v += ["sst", "dqdt"]
+    if o.opt("scorrection"): v += ["sss"]
     return v
 
 
@@ -88,3 +91,19 @@ def compare(o, t, names, exact=True, rtol=0.0, label=""):
 def all_names(NT):
     n2, n3 = field_names(NT)
     return n2 + n3
+
+
+def fill_flux_data(o):
+    """sst, dqdt, sss of set_vbc's QCORRECTION / SCORRECTION / SRELAXATION (host data in a real run): analytical, part below -2 degC."""
+    if o.opt("qcorrection"):
+        a = o.field("sst"); j = np.arange(a.shape[1])[None, :, None]; i = np.arange(a.shape[2])[None, None, :]
+        a[:] = 1.0 + 0.1 * j + 0.01 * i
+        o.field("dqdt")[:] = -40.0 / (1025.0 * 3985.0) * (1.0 + 0.02 * j)
+    if o.opt("scorrection"):
+        a = o.field("sss"); j = np.arange(a.shape[1])[None, :, None]; i = np.arange(a.shape[2])[None, None, :]
+        a[:] = 34.0 + 0.03 * j + 0.002 * i
+    if o.opt("limit_stflx_cooling"):
+        o.field("stflux_0")[:] = -1.0e-5
+        o.field("stflux_0")[0, ::3, :] = 1.0e-5
+        for tl in (1, 2):
+            o.field(f"t{tl}_0")[-1, :, ::2] = -2.5

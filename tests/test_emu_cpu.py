@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 import orc
-from helpers import all_names, optional_names
+from helpers import all_names, fill_flux_data, optional_names
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 from emu import EMULATED, EmuTile  # noqa: E402
@@ -35,6 +35,8 @@ CASES = {
     "benchmark_nospl": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, nospl_vvisc=1, nospl_vdiff=1)),     # SPLINES_VVISC / SPLINES_VDIFF undefined
     "seamount_nospl": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, nospl_vvisc=1, nospl_vdiff=1)),
     "upwelling_nospl_n30": (orc.APP_UPWELLING, dict(Lm=20, Mm=24, N=30, nospl_vvisc=1, nospl_vdiff=0)),
+    "flux_corr": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, qcorrection=1, limit_stflx_cooling=1, scorrection=1, Tnudg_salt=1.0e-6)),
+    "flux_relax": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, scorrection=2, Tnudg_salt=2.0e-7)),
     "benchmark_splines": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, vadv=3)),
     "benchmark_bvf": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, bv_frequency=1, bvf_mixing=1)),
     "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, mix_geo_ts=1)),
@@ -62,6 +64,7 @@ def test_kernel_source_bit_exact_against_oracle(case, spinup):
     app, kw = CASES[case]
     o = orc.Oracle(app, **kw)
     o.run_phase("set_data"); o.run_phase("ini")
+    fill_flux_data(o)
     if spinup:
         o.step(spinup)
     d = o.indices()

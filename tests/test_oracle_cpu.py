@@ -171,7 +171,7 @@ def test_cabi_routine_args_name_known_fields():
     n2, n3 = field_names(2)
     # + the arrays that exist only with the BENCHMARK cpp switches on (include/roms_b200.h, roms_b200_config)
     optional = ["ZoBot", "bvf", "alpha", "beta", "srflx", "Jwtype", "ghats_0", "ghats_1", "Uwind", "Vwind", "Tair", "Pair", "Hair", "rain", "cloud",
-                "lrflx", "lhflx", "shflx", "hsbl", "ksbl", "diff4_0", "diff4_1"]
+                "lrflx", "lhflx", "shflx", "hsbl", "ksbl", "diff4_0", "diff4_1", "sst", "dqdt", "sss"]
     known = set(n2 + n3 + optional)
     for name, ph in _lib.PHASES.items():
         spec = L.roms_b200_routine_args(ph)
@@ -902,3 +902,52 @@ def test_limit_bstress_known_answer():
     o2.set_indices(d); o2.run_phase("set_vbc")
     for n in ("bustr", "bvstr", "u1", "zeta1"):
         assert np.array_equal(o.field(n), o2.field(n)), n
+
+
+def _flux_corr_oracle(kind="chk", **kw):
+    """BENCHMARK run with the surface-flux data fields of set_vbc's corrections filled in analytically."""
+    o = orc.Oracle(orc.APP_BENCHMARK, kind=kind, Lm=48, Mm=32, N=10, **kw)
+    o.run_phase("set_data"); o.run_phase("ini")
+    a = o.field("sst"); LBi, LBj, _ = o.origin("sst")
+    J = (np.arange(a.shape[1]) + LBj)[None, :, None]; I = (np.arange(a.shape[2]) + LBi)[None, None, :]
+    o.field("sst")[:] = 2.0 + 0.05 * J + 0.0 * I
+    o.field("dqdt")[:] = -40.0 / (1025.0 * 3985.0) * (1.0 + 0.0 * J * I)          # -40 W/m2/K as degC m/s per K
+    o.field("sss")[:] = 34.5 + 0.01 * J + 0.0 * I
+    return o
+
+
+def test_set_vbc_flux_corrections_known_answers():
+    """set_vbc.F:285-351.  QCORRECTION: stflx(itemp) = stflux + dqdt (SST - sst); LIMIT_STFLX_COOLING: a cooling flux vanishes where the
+    surface is colder than -2 degC and is kept elsewhere; SCORRECTION / SRELAXATION: stflx(isalt) = [EmP S] - Tnudg Hz(N) (S - sss).
+    Checked point by point after the phase, and over 6 steps for tiling invariance."""
+    o = _flux_corr_oracle(qcorrection=1, scorrection=1, Tnudg_salt=1.0 / (30.0 * 86400.0))
+    d = o.indices(); d["nstp"] = 1; d["nnew"] = 2; d["nrhs"] = 1; o.set_indices(d)
+    o.field("stflux_1")[:] = 3.0e-8
+    o.run_phase("set_vbc")
+    T, S, Hz = o.field("t1_0")[-1], o.field("t1_1")[-1], o.field("Hz")[-1]
+    want_t = o.field("stflux_0")[0] + o.field("dqdt")[0] * (T - o.field("sst")[0])
+    R = (slice(None), slice(3, -2))                                              # IstrR:IendR = 1:Lm in a periodic domain (the fluxes are not exchanged)
+    assert np.array_equal(o.field("stflx_0")[0][R], want_t[R]) and np.abs(want_t).max() > 0
+    want_s = 3.0e-8 * S - (1.0 / (30.0 * 86400.0)) * Hz * (S - o.field("sss")[0])
+    assert np.array_equal(o.field("stflx_1")[0][R], want_s[R])
+    o2 = _flux_corr_oracle(scorrection=2, Tnudg_salt=2.0e-7, limit_stflx_cooling=1)
+    o2.set_indices(d)
+    o2.field("t1_0")[-1, :, :24] = -2.5                                           # part of the surface below the threshold
+    o2.field("stflux_0")[:] = -1.0e-5; o2.field("stflux_0")[0, :12, :] = 2.0e-5    # cooling, except a warming strip
+    o2.run_phase("set_vbc")
+    got = o2.field("stflx_0")[0][R]; flux = o2.field("stflux_0")[0][R]
+    cold = o2.field("t1_0")[-1][R] < -2.0
+    assert np.all(got[cold & (flux < 0)] == 0.0)                                  # cooling of a freezing surface is suppressed
+    keep = ~(cold & (flux < 0))
+    assert np.array_equal(got[keep], flux[keep]) and (got > 0).any() and (got < 0).any()
+    assert np.array_equal(o2.field("stflx_1")[0][R], (-2.0e-7 * o2.field("Hz")[-1] * (o2.field("t1_1")[-1] - o2.field("sss")[0]))[R])
+    # tiling invariance over a few steps with all corrections on
+    kw = dict(qcorrection=1, limit_stflx_cooling=1, scorrection=1, Tnudg_salt=1.0e-6)
+    a = _flux_corr_oracle(**kw); a.step(6)
+    b_ = orc.Oracle(orc.APP_BENCHMARK, kind="chk", Lm=48, Mm=32, N=10, NtileI=2, NtileJ=2, **kw)
+    b_.run_phase("set_data"); b_.run_phase("ini")
+    for n in ("sst", "dqdt", "sss"):
+        b_.field(n)[:] = a.field(n)
+    b_.step(6, 4)
+    for n in ("t1_0", "t1_1", "t2_0", "stflx_0", "stflx_1", "u1"):
+        assert np.array_equal(a.field(n), b_.field(n)), n

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import orc
-from helpers import all_names, cfg_from_oracle, compare, make_pair
+from helpers import all_names, cfg_from_oracle, compare, fill_flux_data, make_pair, optional_names
 from roms_trunk_mgh_b200 import _lib
 from test_gpu_parity import STEP_PHASES, begin_step, test_tiling_invariance_across_gpus as _tiling_invariance
 
@@ -30,6 +30,8 @@ VARIANTS = {
     "nospl": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, nospl_vvisc=1, nospl_vdiff=1)),       # SPLINES_VVISC / SPLINES_VDIFF undefined
     "nospl_seamount": (orc.APP_SEAMOUNT, dict(nospl_vvisc=1, nospl_vdiff=1)),
     "nospl_n30": (orc.APP_BENCHMARK, dict(Lm=96, Mm=40, N=30, nospl_vvisc=0, nospl_vdiff=1, vadv=3)),
+    "flux_corr": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, qcorrection=1, limit_stflx_cooling=1, scorrection=1, Tnudg_salt=1.0e-6)),
+    "flux_relax": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, scorrection=2, Tnudg_salt=2.0e-7)),
     "uv_sadv": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, uv_adv=2)),                      # UV_SADVECTION: spline vertical advection
     "uv_sadv_seamount": (orc.APP_SEAMOUNT, dict(uv_adv=2)),
     "ts_dif4": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, ts_dif4=1, tnu4=TNU4)),
@@ -43,6 +45,11 @@ VARIANTS = {
 def test_variants_strict_bit_exact_every_phase(case, spinup):
     app, kw = VARIANTS[case]
     o, t = make_pair(app, strict=True, spinup=spinup, **kw)
+    if o.opt("qcorrection") or o.opt("scorrection"):            # the data of the surface-flux corrections (host fields in a real run)
+        fill_flux_data(o)
+        for n in ("sst", "dqdt", "sss", "stflux_0", "t1_0", "t2_0"):
+            if n in ("stflux_0", "t1_0", "t2_0") or n in optional_names(o):
+                t.set(n, o.field(n))
     names = all_names(int(o.opt("NT")))
     begin_step(o, t)
     k = STEP_PHASES.index("t3dmix") + 1
