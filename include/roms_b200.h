@@ -81,6 +81,8 @@ typedef struct roms_b200_config {
   int nospl_vvisc, nospl_vdiff; /* 1: SPLINES_VVISC / SPLINES_VDIFF NOT defined: centred implicit vertical viscosity / diffusion
                                    (step3d_uv.F:397-462, :730-795; step3d_t.F:1196-1198, :1430-1499) instead of the parabolic splines;
                                    0 (what upwelling.h, seamount.h and benchmark.h select): the splines                          */
+  int bodyforce, levsfrc, levbfrc; /* BODYFORCE: surface / bottom stress as a body force over levels levsfrc:N / 1:levbfrc (roms_*.in LEVSFRC,
+                                   LEVBFRC) in rhs3d (rhs3d.F:326-466, :1588-1599) and no stress boundary flux in pre_step3d (:931-937)   */
   int limit_bstress;            /* LIMIT_BSTRESS (set_vbc.F:533-540 and the three drag laws): |bustr| <= 0.75 |u(k=1)| Hz(k=1) / dt        */
   int uv_adv;                   /* momentum advection in rhs3d: 0 the default branch (third-order upstream horizontal, fourth-order
                                    centred vertical), 1 UV_C4ADVECTION (rhs3d.F:685-705, :761-781, :829-849, :902-921, :1108-1175,

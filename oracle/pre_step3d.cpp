@@ -194,7 +194,7 @@ void pre_step3d(Model& m, const Bnd& b) {
         double cff = 1.0 / (z_r(i, j, k + 1) + z_r(i - 1, j, k + 1) - z_r(i, j, k) - z_r(i - 1, j, k));
         FC(i, k) = cff3 * cff * (ust(i, j, k + 1) - ust(i, j, k)) * (Akv(i, j, k) + Akv(i - 1, j, k));
       }
-    for (int i = IstrU; i <= Iend; ++i) { FC(i, 0) = dt * m.bustr(i, j); FC(i, N) = dt * m.sustr(i, j); }
+    for (int i = IstrU; i <= Iend; ++i) { FC(i, 0) = dt * m.bustr(i, j); FC(i, N) = dt * m.sustr(i, j); if (c.bodyforce) { FC(i, 0) = 0.0; FC(i, N) = 0.0; } }   // :931-937
     double cff = dt * 0.25;
     for (int i = IstrU; i <= Iend; ++i) DC(i, 0) = cff * (pm(i, j) + pm(i - 1, j)) * (pn(i, j) + pn(i - 1, j));
     if (first) {
@@ -228,7 +228,7 @@ void pre_step3d(Model& m, const Bnd& b) {
           double cf = 1.0 / (z_r(i, j, k + 1) + z_r(i, j - 1, k + 1) - z_r(i, j, k) - z_r(i, j - 1, k));
           FC(i, k) = cff3 * cf * (vst(i, j, k + 1) - vst(i, j, k)) * (Akv(i, j, k) + Akv(i, j - 1, k));
         }
-      for (int i = Istr; i <= Iend; ++i) { FC(i, 0) = dt * m.bvstr(i, j); FC(i, N) = dt * m.svstr(i, j); }
+      for (int i = Istr; i <= Iend; ++i) { FC(i, 0) = dt * m.bvstr(i, j); FC(i, N) = dt * m.svstr(i, j); if (c.bodyforce) { FC(i, 0) = 0.0; FC(i, N) = 0.0; } }   // :1036-1042
       cff = dt * 0.25;
       for (int i = Istr; i <= Iend; ++i) DC(i, 0) = cff * (pm(i, j) + pm(i, j - 1)) * (pn(i, j) + pn(i, j - 1));
       if (first) {

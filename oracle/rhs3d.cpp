@@ -22,6 +22,40 @@ void rhs3d(Model& m, const Bnd& b) {
       UFx(IminS, ImaxS, JminS, JmaxS), UFe(IminS, ImaxS, JminS, JmaxS), VFx(IminS, ImaxS, JminS, JmaxS), VFe(IminS, ImaxS, JminS, JmaxS),
       uee(IminS, ImaxS, JminS, JmaxS), uxx(IminS, ImaxS, JminS, JmaxS), vee(IminS, ImaxS, JminS, JmaxS), vxx(IminS, ImaxS, JminS, JmaxS);
 
+  if (c.bodyforce) {                                                 // BODYFORCE :326-466
+    S2 wrk(IminS, ImaxS, JminS, JmaxS), Uwrk(IminS, ImaxS, JminS, JmaxS), Vwrk(IminS, ImaxS, JminS, JmaxS);
+    F2 &pm = m.pm, &pn = m.pn;
+    for (int pass = 0; pass < 2; ++pass) {                           // 0: surface stress over levsfrc:N (added), 1: bottom stress over 1:levbfrc (removed)
+      const int k0 = pass ? 1 : c.levsfrc, k1 = pass ? c.levbfrc : N;
+      for (int j = JstrV - 1; j <= Jend; ++j) for (int i = IstrU - 1; i <= Iend; ++i) wrk(i, j) = 0.0;
+      if (pass == 0) { for (int k = N; k >= c.levsfrc; --k) for (int j = JstrV - 1; j <= Jend; ++j) for (int i = IstrU - 1; i <= Iend; ++i) wrk(i, j) = wrk(i, j) + Hz(i, j, k); }
+      else { for (int k = 1; k <= c.levbfrc; ++k) for (int j = JstrV - 1; j <= Jend; ++j) for (int i = IstrU - 1; i <= Iend; ++i) wrk(i, j) = wrk(i, j) + Hz(i, j, k); }
+      for (int j = Jstr; j <= Jend; ++j)
+        for (int i = IstrU; i <= Iend; ++i) {
+          const double cff = 0.25 * (pm(i - 1, j) + pm(i, j)) * (pn(i - 1, j) + pn(i, j));
+          const double cff1 = 1.0 / (cff * (wrk(i - 1, j) + wrk(i, j)));
+          Uwrk(i, j) = (pass ? m.bustr(i, j) : m.sustr(i, j)) * cff1;
+        }
+      for (int j = JstrV; j <= Jend; ++j)
+        for (int i = Istr; i <= Iend; ++i) {
+          const double cff = 0.25 * (pm(i, j - 1) + pm(i, j)) * (pn(i, j - 1) + pn(i, j));
+          const double cff1 = 1.0 / (cff * (wrk(i, j - 1) + wrk(i, j)));
+          Vwrk(i, j) = (pass ? m.bvstr(i, j) : m.svstr(i, j)) * cff1;
+        }
+      for (int k = k0; k <= k1; ++k) {
+        for (int j = Jstr; j <= Jend; ++j)
+          for (int i = IstrU; i <= Iend; ++i) {
+            const double cff = Uwrk(i, j) * (Hz(i, j, k) + Hz(i - 1, j, k));
+            ru(i, j, k) = pass ? ru(i, j, k) - cff : ru(i, j, k) + cff;
+          }
+        for (int j = JstrV; j <= Jend; ++j)
+          for (int i = Istr; i <= Iend; ++i) {
+            const double cff = Vwrk(i, j) * (Hz(i, j, k) + Hz(i, j - 1, k));
+            rv(i, j, k) = pass ? rv(i, j, k) - cff : rv(i, j, k) + cff;
+          }
+      }
+    }
+  }
   for (int k = 1; k <= N; ++k) {
     // ---- UV_COR :473-507
     for (int j = JstrV - 1; j <= Jend; ++j)
@@ -279,6 +313,7 @@ void rhs3d(Model& m, const Bnd& b) {
     // ---- :1534-1598
     for (int i = IstrU; i <= Iend; ++i) m.rufrc(i, j) = ru(i, j, 1);
     for (int k = 2; k <= N; ++k) for (int i = IstrU; i <= Iend; ++i) m.rufrc(i, j) = m.rufrc(i, j) + ru(i, j, k);
+    if (!c.bodyforce)                                                 // # ifndef BODYFORCE :1588-1599
     for (int i = IstrU; i <= Iend; ++i) {
       double cff = m.om_u(i, j) * m.on_u(i, j);
       double cff1 = m.sustr(i, j) * cff;
@@ -288,6 +323,7 @@ void rhs3d(Model& m, const Bnd& b) {
     if (j >= JstrV) {   // :1600-1667
       for (int i = Istr; i <= Iend; ++i) m.rvfrc(i, j) = rv(i, j, 1);
       for (int k = 2; k <= N; ++k) for (int i = Istr; i <= Iend; ++i) m.rvfrc(i, j) = m.rvfrc(i, j) + rv(i, j, k);
+      if (!c.bodyforce)
       for (int i = Istr; i <= Iend; ++i) {
         double cff = m.om_v(i, j) * m.on_v(i, j);
         double cff1 = m.svstr(i, j) * cff;

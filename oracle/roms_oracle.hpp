@@ -144,6 +144,8 @@ struct Cfg {
   int limit_stflx_cooling = 0;    // LIMIT_STFLX_COOLING: no further cooling below -2 degC (:301-328)
   int scorrection = 0;            // 1 SCORRECTION, 2 SRELAXATION (:344-351), with Tnudg(isalt) = Tnudg_salt (1/s)
   double Tnudg_salt = 0.0;
+  int bodyforce = 0, levsfrc = 0, levbfrc = 0;   // BODYFORCE: surface / bottom stress as a body force over levels levsfrc:N / 1:levbfrc
+                                                 // (rhs3d.F:326-466, :1588-1599; pre_step3d.F:931-937, :1036-1042)
   int limit_bstress = 0;          // LIMIT_BSTRESS (set_vbc.F:533-540): |bottom stress| <= 0.75 |u| Hz / dt
   int ts_dif4 = 0;                // TS_DIF4 (+ MIX_S_TS): t3dmix4_s.h after t3dmix2 (rhs3d.F:81-97)
   // physical parameters

@@ -204,8 +204,9 @@ __global__ void __launch_bounds__(128, PRU_MINB) k_pre_step3d_uv(Par p, Flds f) 
     if (istart == 2) { L.rur = ru_r[o]; L.rvr = rv_r[o]; }
     return L;
   };
-  double FCum = p.dt * f.bustr[o2], FCvm = p.dt * f.bvstr[o2];
-  const double sus = f.sustr[o2], svs = f.svstr[o2];
+  // BODYFORCE (pre_step3d.F:931-937, :1036-1042): the stresses do not enter as boundary fluxes (dt * 0 = 0, the reference's FC = 0)
+  double FCum = p.dt * (p.bodyforce ? 0.0 : f.bustr[o2]), FCvm = p.dt * (p.bodyforce ? 0.0 : f.bvstr[o2]);
+  const double sus = p.bodyforce ? 0.0 : f.sustr[o2], svs = p.bodyforce ? 0.0 : f.svstr[o2];
   double uk = ust[o2 + PL], vk = vst[o2 + PL];
   double zk0 = z_r[o2 + PL], zkW = z_r[o2 + PL - 1], zkS = z_r[o2 + PL - P];
   auto level = [&](const Lvl& cur, const Lvl&, int k) {

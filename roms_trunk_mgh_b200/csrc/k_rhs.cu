@@ -32,7 +32,8 @@ __device__ __forceinline__ double d2y(const double* __restrict__ A, int o, int P
 // UV_C4ADVECTION (fourth-order centred horizontal :685-705, :761-781, :829-849, :902-921; vertical 9/32, 1/32 :1108-1175, :1362-1429);
 // 2 UV_SADVECTION (the default horizontal branch; conservative parabolic splines in the vertical :1016-1078, :1267-1329);
 // 3 UV_C2ADVECTION (second-order centred: horizontal :605-657, vertical :1079-1107, :1330-1361).
-template <int UADV>
+// BF: BODYFORCE -- the surface / bottom stress enters ru, rv as a body force over levels levsfrc:N / 1:levbfrc (:326-466) instead of rufrc (:1588-1599).
+template <int UADV, bool BF = false>
 __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
   const int i = p.Istr + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -95,6 +96,20 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
       for (int k = N - 1; k >= 1; --k) CFv[k] = CFv[k] - FCs[k] * CFv[k + 1];
     }
   }
+  double bfUs = 0.0, bfUb = 0.0, bfVs = 0.0, bfVb = 0.0;
+  if (BF) {                                                            // rhs3d.F:355-382, :411-438
+    const int ob = o2 + i;
+    const double cu = 0.25 * (f.pm[ob - 1] + f.pm[ob]) * (f.pn[ob - 1] + f.pn[ob]);
+    const double cv = 0.25 * (f.pm[ob - P] + f.pm[ob]) * (f.pn[ob - P] + f.pn[ob]);
+    double w0 = 0.0, wW = 0.0, wS = 0.0;
+    for (int k = N; k >= p.levsfrc; --k) { const int o = ob + k * p.PL; w0 = w0 + Hz[o]; wW = wW + Hz[o - 1]; wS = wS + Hz[o - P]; }
+    bfUs = f.sustr[ob] * (1.0 / (cu * (wW + w0)));
+    if (dov) bfVs = f.svstr[ob] * (1.0 / (cv * (wS + w0)));
+    w0 = 0.0; wW = 0.0; wS = 0.0;
+    for (int k = 1; k <= p.levbfrc; ++k) { const int o = ob + k * p.PL; w0 = w0 + Hz[o]; wW = wW + Hz[o - 1]; wS = wS + Hz[o - P]; }
+    bfUb = f.bustr[ob] * (1.0 / (cu * (wW + w0)));
+    if (dov) bfVb = f.bvstr[ob] * (1.0 / (cv * (wS + w0)));
+  }
   for (int k = 1; k <= N; ++k) {
     const int o = o2 + k * p.PL + i;                     // includes i
     const int oU = (k < N) ? o + p.PL : o, oUU = (k + 2 <= N) ? o + 2 * p.PL : oU, oD = (k > 1) ? o - p.PL : o;
@@ -116,6 +131,10 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
     const double uUp = u[oU], uUp2 = u[oUU], uDn = u[oD], vUp = v[oU], vUp2 = v[oUU], vDn = v[oD];
     double rux = ru[o];
     double rvx = rv[o];
+    if (BF) {                                                          // :383-410, :439-466 (before every other term, as the reference)
+      if (k >= p.levsfrc) { rux = rux + bfUs * (hz0 + hzW); if (dov) rvx = rvx + bfVs * (hz0 + hzS); }
+      if (k <= p.levbfrc) { rux = rux - bfUb * (hz0 + hzW); if (dov) rvx = rvx - bfVb * (hz0 + hzS); }
+    }
     // ---- Coriolis (rhs3d.F:473-507): UFx at rho(i,j), rho(i-1,j); VFe at rho(i,j), rho(i,j-1)
     {
       const double c0 = 0.5 * hz0 * fomn0;
@@ -277,13 +296,13 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs3d(Par p, Flds f) {
     const double c = f.om_u[o2 + i] * f.on_u[o2 + i];
     const double c1 = f.sustr[o2 + i] * c;
     const double c2 = -f.bustr[o2 + i] * c;
-    f.rufrc[o2 + i] = rufrc + c1 + c2;
+    f.rufrc[o2 + i] = BF ? rufrc : rufrc + c1 + c2;
   }
   if (dov) {
     const double c = f.om_v[o2 + i] * f.on_v[o2 + i];
     const double c1 = f.svstr[o2 + i] * c;
     const double c2 = -f.bvstr[o2 + i] * c;
-    f.rvfrc[o2 + i] = rvfrc + c1 + c2;
+    f.rvfrc[o2 + i] = BF ? rvfrc : rvfrc + c1 + c2;
   }
 }
 
@@ -385,6 +404,14 @@ __global__ void __launch_bounds__(128, UVM_MINB) k_uv3dmix2(Par p, Flds f) {
 static inline dim3 g2(dim3 b, int ni, int nj, int nz = 1) { return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nz); }
 void launch_rhs3d(const Par& p, const Flds& f, cudaStream_t s) {
   dim3 b(RHS_BX, 128 / RHS_BX);
+  if (p.bodyforce) {                                                   // BODYFORCE
+    const dim3 g = g2(b, p.Iend - p.Istr + 1, p.Mm);
+    if (p.uv_adv == 1) k_rhs3d<1, true><<<g, b, 0, s>>>(p, f);
+    else if (p.uv_adv == 2) k_rhs3d<2, true><<<g, b, 0, s>>>(p, f);
+    else if (p.uv_adv == 3) k_rhs3d<3, true><<<g, b, 0, s>>>(p, f);
+    else k_rhs3d<0, true><<<g, b, 0, s>>>(p, f);
+    return;
+  }
   if (p.uv_adv == 1) k_rhs3d<1><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
   else if (p.uv_adv == 2) k_rhs3d<2><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);
   else if (p.uv_adv == 3) k_rhs3d<3><<<g2(b, p.Iend - p.Istr + 1, p.Mm), b, 0, s>>>(p, f);

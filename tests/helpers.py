@@ -6,7 +6,7 @@ from roms_trunk_mgh_b200 import _lib
 from roms_trunk_mgh_b200.ocean import Tile, field_names
 
 APP_OPTS = ["nonlin_eos", "dj_gradps", "curvgrid", "mix_geo_ts", "uv_qdrag", "hadv", "vadv", "ana_vmix", "wvelocity_every_step",
-            "bv_frequency", "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "bvf_mixing", "uv_adv", "ts_dif4", "limit_bstress", "nospl_vvisc", "nospl_vdiff", "qcorrection", "limit_stflx_cooling", "scorrection"]
+            "bv_frequency", "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "bvf_mixing", "uv_adv", "ts_dif4", "limit_bstress", "nospl_vvisc", "nospl_vdiff", "qcorrection", "limit_stflx_cooling", "scorrection", "bodyforce", "levsfrc", "levbfrc"]
 
 
 def cfg_from_oracle(o, device=0):

@@ -951,3 +951,33 @@ def test_set_vbc_flux_corrections_known_answers():
     b_.step(6, 4)
     for n in ("t1_0", "t1_1", "t2_0", "stflx_0", "stflx_1", "u1"):
         assert np.array_equal(a.field(n), b_.field(n)), n
+
+
+def test_bodyforce_known_answer():
+    """BODYFORCE (rhs3d.F:326-466, :1588-1599): the stress spread over levels levsfrc:N / 1:levbfrc sums to the same depth-integrated
+    forcing that the default branch adds to rufrc -- sum_k Uwrk (Hz(i) + Hz(i-1)) = sustr om_u on_u -- so rufrc / rvfrc of the two
+    branches agree to rounding from identical states, while ru differs only inside the two level ranges; the run is tiling-invariant."""
+    kw = dict(Lm=48, Mm=32, N=10)
+    outs = {}
+    for bf in (0, 1):
+        o = orc.Oracle(orc.APP_BENCHMARK, kind="chk", bodyforce=bf, levsfrc=8, levbfrc=2, **kw)
+        o.run_phase("set_data"); o.run_phase("ini")
+        d = o.indices(); d["nstp"] = 1; d["nnew"] = 2; d["nrhs"] = 1; o.set_indices(d)
+        LBi, LBj, _ = o.origin("u1")
+        j = (np.arange(o.field("u1").shape[1]) + LBj)[None, :, None]
+        o.field("u1")[:] = 0.02 * np.sin(np.pi * j / 33.0); o.field("v1")[:] = 0.0          # a sheared current: a bottom stress exists
+        for ph in ("set_massflux", "rho_eos", "set_vbc", "omega", "prsgrd", "rhs3d"):
+            o.run_phase(ph)
+        outs[bf] = {n: o.field(n).copy() for n in ("rufrc", "rvfrc", "ru1", "bustr", "sustr")}
+    I = slice(3, -2); J = slice(1, -1)
+    a, b = outs[0], outs[1]
+    assert np.abs(a["bustr"]).max() > 0 and np.abs(a["sustr"]).max() > 0
+    scale = np.abs(b["ru1"][1:, J, I]).sum(axis=0).max()                                # (the state is xi-uniform: ru of the default branch is 0)
+    assert np.abs(a["rufrc"][0, J, I] - b["rufrc"][0, J, I]).max() < 1e-13 * scale
+    dif = np.abs(a["ru1"][1:, J, I] - b["ru1"][1:, J, I]).max(axis=(1, 2))               # per level k = 1..N
+    assert np.all(dif[2:7] == 0.0) and np.all(dif[:2] > 0) and np.all(dif[7:] > 0)      # levels 3..7 untouched, 1..2 and 8..10 forced
+    x = orc.Oracle(orc.APP_BENCHMARK, kind="chk", bodyforce=1, levsfrc=8, levbfrc=2, **kw); x.run_phase("set_data"); x.run_phase("ini"); x.step(6)
+    y = orc.Oracle(orc.APP_BENCHMARK, NtileI=2, NtileJ=2, kind="chk", bodyforce=1, levsfrc=8, levbfrc=2, **kw)
+    y.run_phase("set_data"); y.run_phase("ini"); y.step(6, 4)
+    for n in ("zeta1", "u1", "v1", "ru1", "rufrc"):
+        assert np.array_equal(x.field(n), y.field(n)), n
