@@ -66,7 +66,6 @@ def test_kernel_source_bit_exact_against_oracle(case, spinup):
     app, kw = CASES[case]
     o = orc.Oracle(app, **kw)
     o.run_phase("set_data"); o.run_phase("ini")
-    fill_flux_data(o)
     if spinup:
         o.step(spinup)
     d = o.indices()
@@ -74,6 +73,7 @@ def test_kernel_source_bit_exact_against_oracle(case, spinup):
     d["tdays"] = d["time"] / 86400.0
     o.set_indices(d)
     o.run_phase("set_data")
+    fill_flux_data(o)                                         # after set_data (which resets the analytical surface fluxes)
     t = EmuTile(o)
     names = all_names(int(o.opt("NT"))) + optional_names(o)
     phases = list(STEP_PHASES)

@@ -46,13 +46,13 @@ VARIANTS = {
 def test_variants_strict_bit_exact_every_phase(case, spinup):
     app, kw = VARIANTS[case]
     o, t = make_pair(app, strict=True, spinup=spinup, **kw)
-    if o.opt("qcorrection") or o.opt("scorrection"):            # the data of the surface-flux corrections (host fields in a real run)
-        fill_flux_data(o)
+    names = all_names(int(o.opt("NT")))
+    begin_step(o, t)
+    if o.opt("qcorrection") or o.opt("scorrection"):            # the data of the surface-flux corrections (host fields in a real run),
+        fill_flux_data(o)                                       # set after set_data, which resets the analytical surface fluxes
         for n in ("sst", "dqdt", "sss", "stflux_0", "t1_0", "t2_0"):
             if n in ("stflux_0", "t1_0", "t2_0") or n in optional_names(o):
                 t.set(n, o.field(n))
-    names = all_names(int(o.opt("NT")))
-    begin_step(o, t)
     k = STEP_PHASES.index("t3dmix") + 1
     for ph in STEP_PHASES[:k] + ["t3dmix4"] * int(o.opt("ts_dif4")) + STEP_PHASES[k:]:       # rhs3d.F:81-97
         o.run_phase(ph); t.run_phase(ph)
