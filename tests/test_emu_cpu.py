@@ -261,3 +261,70 @@ def test_kernel_source_on_ring_tiles(case):
     assert ran >= 16
     for t in tiles:
         t.close()
+
+
+class _EmuAsTile:
+    """Adapter that lets the body of a GPU parity test run against the emulation: the subset of ocean.Tile the every-phase tests use
+    (set / get / set_indices / indices / run_phase incl. the whole LOOP_2D / close)."""
+
+    def __init__(self, o):
+        self.o, self.e, self.idx = o, EmuTile(o), dict(o.indices())
+
+    def set(self, name, arr):
+        self.e.set(name, arr)
+
+    def get(self, name):
+        return self.e.get(name)
+
+    def set_indices(self, d):
+        self.idx = dict(d); self.e.set_indices(self.idx)
+
+    def indices(self):
+        return dict(self.idx)
+
+    def run_phase(self, ph):
+        if ph != "step2d_loop":
+            self.e.set_indices(self.idx); self.e.run_phase(ph)
+            return
+        e, nfast = self.idx, self.e.nfast
+        e["PREDICTOR"] = 0
+        for my_iif in range(1, nfast + 2):                        # csrc/api.cu loop2d_machine
+            nxt = 3 - e["indx1"]
+            e["PREDICTOR"] = 1; e["iif"] = my_iif
+            e["kstp"] = e["indx1"] if my_iif == 1 else 3 - e["indx1"]; e["knew"] = 3; e["krhs"] = e["indx1"]
+            self.e.set_indices(e); self.e.run_phase("step2d")
+            e["PREDICTOR"] = 0; e["knew"] = nxt; e["kstp"] = 3 - nxt; e["krhs"] = 3
+            if my_iif < nfast + 1:
+                e["indx1"] = nxt
+                self.e.set_indices(e); self.e.run_phase("step2d")
+
+    def close(self):
+        self.e.close()
+
+
+@pytest.mark.parametrize("case", ["flux_corr", "flux_relax", "bodyforce", "limit_bstress", "nospl", "uv_c2"])
+def test_gpu_variant_test_bodies_dry_run_on_the_emulation(case, monkeypatch):
+    """The BODY of tests/test_zz_variants_gpu.py::test_variants_strict_bit_exact_every_phase executed with the emulation standing in
+    for the device tile (same make_pair / begin_step / fill / compare sequence, small grids): checks the test's own host logic for
+    the cases that had no GPU run when the round closed, and once more that the kernel chain keeps its state consistent phase after
+    phase WITHOUT re-upload."""
+    import helpers
+    import test_zz_variants_gpu as G
+    small = {"flux_corr": dict(Lm=24, Mm=16, N=7), "flux_relax": dict(Lm=24, Mm=16, N=7), "bodyforce": dict(Lm=24, Mm=16, N=7, levsfrc=5),
+             "limit_bstress": dict(Lm=24, Mm=16, N=7), "nospl": dict(Lm=24, Mm=16, N=7), "uv_c2": dict(Lm=24, Mm=16, N=7)}[case]
+    app, kw = G.VARIANTS[case]
+    monkeypatch.setitem(G.VARIANTS, case, (app, dict(kw, **small)))
+
+    def fake_make_pair(app, strict=True, spinup=0, **kw):
+        o = orc.Oracle(app, **kw)
+        o.run_phase("set_data"); o.run_phase("ini")
+        if spinup:
+            o.step(spinup)
+        t = _EmuAsTile(o)
+        NT = int(o.opt("NT"))
+        for n in all_names(NT) + optional_names(o):
+            t.set(n, o.field(n))
+        t.set_indices(o.indices())
+        return o, t
+    monkeypatch.setattr(G, "make_pair", fake_make_pair)
+    G.test_variants_strict_bit_exact_every_phase(case, 3)
