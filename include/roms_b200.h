@@ -81,6 +81,8 @@ typedef struct roms_b200_config {
   int nospl_vvisc, nospl_vdiff; /* 1: SPLINES_VVISC / SPLINES_VDIFF NOT defined: centred implicit vertical viscosity / diffusion
                                    (step3d_uv.F:397-462, :730-795; step3d_t.F:1196-1198, :1430-1499) instead of the parabolic splines;
                                    0 (what upwelling.h, seamount.h and benchmark.h select): the splines                          */
+  int vtransform;               /* Vtransform of roms_*.in in set_depth: 2 (or 0) set_depth.F:210-262, 1 the original transformation :160-208;
+                                   hc is the host's SCALARS(ng)%hc either way (MIN(hmin, Tcline) for 1: set_scoord.F:157-163)            */
   int bodyforce, levsfrc, levbfrc; /* BODYFORCE: surface / bottom stress as a body force over levels levsfrc:N / 1:levbfrc (roms_*.in LEVSFRC,
                                    LEVBFRC) in rhs3d (rhs3d.F:326-466, :1588-1599) and no stress boundary flux in pre_step3d (:931-937)   */
   int limit_bstress;            /* LIMIT_BSTRESS (set_vbc.F:533-540 and the three drag laws): |bustr| <= 0.75 |u(k=1)| Hz(k=1) / dt        */

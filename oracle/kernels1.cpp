@@ -350,10 +350,30 @@ void set_zeta(Model& m, const Bnd& b) {
   exchange_r2d(m, b, m.zeta[1]); exchange_r2d(m, b, m.zeta[2]);
 }
 
-// ROMS/Nonlinear/set_depth.F:210-262 (Vtransform = 2)
+// ROMS/Nonlinear/set_depth.F:160-208 (Vtransform = 1: the original transformation), :210-262 (Vtransform = 2)
 void set_depth(Model& m, const Bnd& b) {
   const Cfg& c = m.c; ORC_UNPACK_BOUNDS(b);
   const int N = c.N; const double hc = m.hc;
+  if (c.Vtransform == 1) {
+    for (int j = JstrT; j <= JendT; ++j) {
+      for (int i = IstrT; i <= IendT; ++i) m.z_w(i, j, 0) = -m.h(i, j);
+      for (int k = 1; k <= N; ++k) {
+        const double cff_r = hc * (m.sc_r[k] - m.Cs_r[k]), cff_w = hc * (m.sc_w[k] - m.Cs_w[k]);
+        const double cff1_r = m.Cs_r[k], cff1_w = m.Cs_w[k];
+        for (int i = IstrT; i <= IendT; ++i) {
+          const double hwater = m.h(i, j);
+          const double hinv = 1.0 / hwater;
+          const double z_w0 = cff_w + cff1_w * hwater;
+          m.z_w(i, j, k) = z_w0 + m.Zt_avg1(i, j) * (1.0 + z_w0 * hinv);
+          const double z_r0 = cff_r + cff1_r * hwater;
+          m.z_r(i, j, k) = z_r0 + m.Zt_avg1(i, j) * (1.0 + z_r0 * hinv);
+          m.Hz(i, j, k) = m.z_w(i, j, k) - m.z_w(i, j, k - 1);
+        }
+      }
+    }
+    exchange_r2d(m, b, m.h); exchange_w3d(m, b, m.z_w); exchange_r3d(m, b, m.z_r); exchange_r3d(m, b, m.Hz);
+    return;
+  }
   for (int j = JstrT; j <= JendT; ++j) {
     for (int i = IstrT; i <= IendT; ++i) m.z_w(i, j, 0) = -m.h(i, j);
     for (int k = 1; k <= N; ++k) {

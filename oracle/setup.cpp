@@ -182,7 +182,7 @@ void Model::allocate() {
 // ROMS/Utility/set_scoord.F:170-178 (hc), :393-440 (Vstretching=4)
 void set_scoord(Model& m) {
   const Cfg& c = m.c; const int N = c.N;
-  if (c.Vtransform != 2 || c.Vstretching != 4) { std::fprintf(stderr, "oracle: only Vtransform=2/Vstretching=4\n"); std::abort(); }
+  if ((c.Vtransform != 1 && c.Vtransform != 2) || c.Vstretching != 4) { std::fprintf(stderr, "oracle: only Vtransform=1|2 / Vstretching=4\n"); std::abort(); }
   m.hc = c.Tcline;
   const double ds = 1.0 / (double)N;
   m.sc_w[N] = 0.0; m.Cs_w[N] = 0.0;
@@ -546,6 +546,11 @@ void initialize(Model& m) {
   set_weights(m, nullptr);
   for (const Bnd& b : m.tiles) ana_grid(m, b);
   for (const Bnd& b : m.tiles) metrics(m, b);
+  if (m.c.Vtransform == 1) {                           // set_scoord.F:157-163: hc = MIN(hmin, Tcline), hmin from metrics.F (IstrT:IendT, JstrT:JendT)
+    double hmin = 1.0e300;
+    for (int j = 0; j <= m.c.Mm + 1; ++j) for (int i = 1; i <= m.c.Lm; ++i) hmin = std::min(hmin, m.h(i, j));
+    m.hc = std::min(hmin, m.c.Tcline);
+  }
   for (const Bnd& b : m.tiles) ini_hmixcoef(m, b);
   for (const Bnd& b : m.tiles) set_depth(m, b);        // initial.F:337 (Zt_avg1 = 0)
   for (const Bnd& b : m.tiles) ana_initial(m, b);      // initial.F:354

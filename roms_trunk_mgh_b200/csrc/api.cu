@@ -698,7 +698,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   if (cfg->lmd_mixing && !(cfg->bv_frequency && cfg->eos_tderivative && cfg->solar_source && cfg->lmd_nonlocal)) return ConfigError;
   if (cfg->bvf_mixing && !cfg->bv_frequency) return ConfigError;
   if (cfg->uv_adv < 0 || cfg->uv_adv > 3) return ConfigError;
-  if (cfg->dj_gradps < 0 || cfg->dj_gradps > 3) return ConfigError;
+  if (cfg->dj_gradps < 0 || cfg->dj_gradps > 3 || cfg->vtransform < 0 || cfg->vtransform > 2) return ConfigError;
   if (cfg->bodyforce && (cfg->levsfrc < 1 || cfg->levsfrc > cfg->N || cfg->levbfrc < 1 || cfg->levbfrc > cfg->N)) return ConfigError;
   if (cfg->scorrection < 0 || cfg->scorrection > 2 || (cfg->scorrection && !(cfg->salinity && cfg->NT >= 2))) return ConfigError;
   if (cfg->ts_dif4 && cfg->mix_geo_ts) return ConfigError;                          // t3dmix4_geo.h is not built
@@ -749,7 +749,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   p.nospl_vvisc = cfg->nospl_vvisc ? 1 : 0; p.nospl_vdiff = cfg->nospl_vdiff ? 1 : 0;
   p.qcorrection = cfg->qcorrection ? 1 : 0; p.limit_stflx_cooling = cfg->limit_stflx_cooling ? 1 : 0; p.scorrection = cfg->scorrection;
   p.pad2_ = 0; p.Tnudg_salt = cfg->Tnudg_salt;
-  p.bodyforce = cfg->bodyforce ? 1 : 0; p.levsfrc = cfg->levsfrc; p.levbfrc = cfg->levbfrc; p.pad3_ = 0;
+  p.bodyforce = cfg->bodyforce ? 1 : 0; p.levsfrc = cfg->levsfrc; p.levbfrc = cfg->levbfrc; p.vtransform = (cfg->vtransform == 1) ? 1 : 2;
   p.blk_ZQ = cfg->blk_ZQ > 0.0 ? cfg->blk_ZQ : 10.0; p.blk_ZT = cfg->blk_ZT > 0.0 ? cfg->blk_ZT : 10.0; p.blk_ZW = cfg->blk_ZW > 0.0 ? cfg->blk_ZW : 10.0;
   p.dt = cfg->dt; p.g = cfg->g; p.rho0 = cfg->rho0; p.R0 = cfg->R0; p.T0 = cfg->T0; p.S0 = cfg->S0; p.Tcoef = cfg->Tcoef; p.Scoef = cfg->Scoef;
   p.gamma2 = cfg->gamma2; p.lambda = cfg->lambda; p.hc = cfg->hc; p.Akv_bak = cfg->Akv_bak;

@@ -366,6 +366,8 @@ __global__ void __launch_bounds__(256) k_set_zeta(Par p, Flds f) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // set_depth_tile (ROMS/Nonlinear/set_depth.F:210-262, Vtransform = 2)
+// VT = 1: the original transformation (set_depth.F:160-208): z = z0 + zeta (1 + z0 / h), z0 = hc (s - C) + C h
+template <int VT>
 __global__ void __launch_bounds__(256) k_set_depth(Par p, Flds f) {
   const int i = xcol0(p, blockIdx.x * blockDim.x) + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;          // 0..Mm+1
@@ -375,15 +377,24 @@ __global__ void __launch_bounds__(256) k_set_depth(Par p, Flds f) {
   const double zt = f.Zt_avg1[o2 + i];
   double zw_prev = -hwater;
   st_w(f.z_w, o2, i, zw_prev, p);
-  const double hinv = 1.0 / (p.hc + hwater);
+  const double hinv = (VT == 1) ? 1.0 / hwater : 1.0 / (p.hc + hwater);
   for (int k = 1; k <= p.N; ++k) {
     const int o = o2 + k * p.PL;
-    const double cff_r = p.hc * f.sc_r[k], cff_w = p.hc * f.sc_w[k];
     const double cff1_r = f.Cs_r[k], cff1_w = f.Cs_w[k];
+    double zw, zr;
+    if (VT == 1) {
+      const double cff_r = p.hc * (f.sc_r[k] - cff1_r), cff_w = p.hc * (f.sc_w[k] - cff1_w);
+      const double z_w0 = cff_w + cff1_w * hwater;
+      zw = z_w0 + zt * (1.0 + z_w0 * hinv);
+      const double z_r0 = cff_r + cff1_r * hwater;
+      zr = z_r0 + zt * (1.0 + z_r0 * hinv);
+    } else {
+    const double cff_r = p.hc * f.sc_r[k], cff_w = p.hc * f.sc_w[k];
     const double cff2_r = (cff_r + cff1_r * hwater) * hinv;
     const double cff2_w = (cff_w + cff1_w * hwater) * hinv;
-    const double zw = zt + (zt + hwater) * cff2_w;
-    const double zr = zt + (zt + hwater) * cff2_r;
+    zw = zt + (zt + hwater) * cff2_w;
+    zr = zt + (zt + hwater) * cff2_r;
+    }
     st_w(f.z_w, o, i, zw, p);
     st_w(f.z_r, o, i, zr, p);
     st_w(f.Hz, o, i, zw - zw_prev, p);
@@ -482,7 +493,11 @@ void launch_set_avg(const Par& p, const Flds& f, int mode, int norm, double fac,
   k_set_avg<<<g2(p, b, p.Mm + 2, p.N + 1), b, 0, s>>>(p, f, mode, norm, fac, Kout, Nout);
 }
 void launch_set_zeta(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_zeta<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
-void launch_set_depth(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_set_depth<<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f); }
+void launch_set_depth(const Par& p, const Flds& f, cudaStream_t s) {
+  dim3 b(64, 4);
+  if (p.vtransform == 1) k_set_depth<1><<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f);
+  else k_set_depth<2><<<g2(p, b, p.Mm + 2), b, 0, s>>>(p, f);
+}
 void launch_bvf_mix(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_bvf_mix<<<g2(p, b, p.Mm, p.N - 1), b, 0, s>>>(p, f); }
 void launch_ana_vmix(const Par& p, const Flds& f, cudaStream_t s) { dim3 b(64, 4); k_ana_vmix<<<g2(p, b, p.Mm + 2, p.N - 1), b, 0, s>>>(p, f); }
 

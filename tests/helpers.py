@@ -7,6 +7,7 @@ from roms_trunk_mgh_b200.ocean import Tile, field_names
 
 APP_OPTS = ["nonlin_eos", "dj_gradps", "curvgrid", "mix_geo_ts", "uv_qdrag", "hadv", "vadv", "ana_vmix", "wvelocity_every_step",
             "bv_frequency", "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "bvf_mixing", "uv_adv", "ts_dif4", "limit_bstress", "nospl_vvisc", "nospl_vdiff", "qcorrection", "limit_stflx_cooling", "scorrection", "bodyforce", "levsfrc", "levbfrc"]
+# (Vtransform is copied separately: the oracle spells it with a capital)
 
 
 def cfg_from_oracle(o, device=0):
@@ -23,6 +24,7 @@ def cfg_from_oracle(o, device=0):
     cfg.Akt_bak[0] = cfg.Akt_bak[1] = o.opt("Akt_bak"); cfg.Akv_bak = o.opt("Akv_bak")
     cfg.gamma2 = o.opt("gamma2"); cfg.lambda_ = o.opt("lambda"); cfg.hc = o.opt("hc")
     cfg.Tnudg_salt = o.opt("Tnudg_salt")
+    cfg.vtransform = int(o.opt("Vtransform"))
     cfg.blk_ZQ = o.opt("blk_ZQ"); cfg.blk_ZT = o.opt("blk_ZT"); cfg.blk_ZW = o.opt("blk_ZW")
     cfg.device = device
     return cfg

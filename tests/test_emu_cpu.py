@@ -39,6 +39,8 @@ CASES = {
     "flux_relax": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, scorrection=2, Tnudg_salt=2.0e-7)),
     "bodyforce": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, bodyforce=1, levsfrc=5, levbfrc=2)),
     "bodyforce_upwelling_c4": (orc.APP_UPWELLING, dict(Lm=20, Mm=24, N=8, bodyforce=1, levsfrc=8, levbfrc=1, uv_adv=1)),
+    "vtransform1": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, Vtransform=1)),
+    "vtransform1_seamount": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, Vtransform=1)),
     "benchmark_splines": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, vadv=3)),
     "benchmark_bvf": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, bv_frequency=1, bvf_mixing=1)),
     "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, mix_geo_ts=1)),

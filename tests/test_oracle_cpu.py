@@ -981,3 +981,29 @@ def test_bodyforce_known_answer():
     y.run_phase("set_data"); y.run_phase("ini"); y.step(6, 4)
     for n in ("zeta1", "u1", "v1", "ru1", "rufrc"):
         assert np.array_equal(x.field(n), y.field(n)), n
+
+
+def test_vtransform1_known_answer():
+    """set_depth.F:160-208 (Vtransform = 1, hc = MIN(hmin, Tcline): set_scoord.F:157-163): the surface follows the free surface exactly
+    (z_w(N) = zeta), the bottom is z_w(0) = -h, the layers sum to h + zeta, at rest z = hc (s - C) + C h; the run is tiling-invariant
+    and differs from Vtransform = 2."""
+    o = orc.Oracle(orc.APP_SEAMOUNT, kind="chk", Vtransform=1)
+    o.run_phase("set_data"); o.run_phase("ini")
+    h = o.field("h")[0]
+    assert o.opt("hc") == min(float(h[:, 3:-2].min()), 100.0)                       # Tcline = 100 m in roms_seamount.in
+    N = int(o.opt("N"))
+    sw, Cw = o.vector(2, N + 1), o.vector(3, N + 1)
+    zw = o.field("z_w")
+    R = (slice(None), slice(3, -2))
+    for k in (0, 3, N):
+        assert np.allclose(zw[k][R], (o.opt("hc") * (sw[k] - Cw[k]) + Cw[k] * h)[R], rtol=1e-14, atol=1e-9)
+    o.field("Zt_avg1")[:] = 0.3
+    o.run_phase("set_depth")
+    assert np.all(zw[N][R] == 0.3) and np.array_equal(zw[0][R], -h[R])
+    assert np.abs(o.field("Hz")[:, R[0], R[1]].sum(axis=0) - (h[R] + 0.3)).max() < 1e-9
+    a = orc.Oracle(orc.APP_SEAMOUNT, kind="chk", Vtransform=1); a.run_phase("set_data"); a.run_phase("ini"); a.step(4)
+    b = orc.Oracle(orc.APP_SEAMOUNT, NtileI=2, NtileJ=2, kind="chk", Vtransform=1); b.run_phase("set_data"); b.run_phase("ini"); b.step(4, 4)
+    c = orc.Oracle(orc.APP_SEAMOUNT, kind="chk"); c.run_phase("set_data"); c.run_phase("ini"); c.step(4)
+    for n in ("zeta1", "u1", "t1_0", "z_r", "Hz"):
+        assert np.array_equal(a.field(n), b.field(n)), n
+    assert not np.array_equal(a.field("z_r"), c.field("z_r"))

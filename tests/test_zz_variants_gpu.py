@@ -33,6 +33,7 @@ VARIANTS = {
     "flux_corr": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, qcorrection=1, limit_stflx_cooling=1, scorrection=1, Tnudg_salt=1.0e-6)),
     "flux_relax": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, scorrection=2, Tnudg_salt=2.0e-7)),
     "bodyforce": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, bodyforce=1, levsfrc=8, levbfrc=2)),
+    "vtransform1": (orc.APP_SEAMOUNT, dict(Vtransform=1)),                                   # the original vertical transformation in set_depth
     "uv_sadv": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, uv_adv=2)),                      # UV_SADVECTION: spline vertical advection
     "uv_sadv_seamount": (orc.APP_SEAMOUNT, dict(uv_adv=2)),
     "ts_dif4": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, ts_dif4=1, tnu4=TNU4)),
