@@ -62,7 +62,8 @@ def test_variants_strict_bit_exact_every_phase(case, spinup):
     t.close()
 
 
-@pytest.mark.parametrize("case", ["uv_c4", "uv_c2", "uv_sadv", "p40", "wj", "ts_dif4", "both_n30", "nospl", "nospl_seamount"])
+@pytest.mark.parametrize("case", ["uv_c4", "uv_c2", "uv_sadv", "p40", "wj", "ts_dif4", "both_n30", "nospl", "nospl_seamount", "bodyforce", "vtransform1",
+                                  "limit_bstress"])
 def test_variants_strict_bit_exact_multistep(case):
     """Whole steps (the captured step graph; t3dmix2_s fused into pre_step3d_t with t3dmix4_s behind it)."""
     app, kw = VARIANTS[case]
