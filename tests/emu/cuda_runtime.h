@@ -41,7 +41,7 @@ inline double __longlong_as_double(long long v) { double r; __builtin_memcpy(&r,
 inline void __nanosleep(unsigned) {}
 inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 using std::sqrt; using std::exp; using std::log; using std::pow; using std::atan; using std::tanh; using std::fabs; using std::cos; using std::sin;
-using std::fmin; using std::fmax; using std::floor; using std::copysign;
+using std::fmin; using std::fmax; using std::floor; using std::copysign; using std::min; using std::max;
 // one kernel launch = every thread of every block, in order (valid for kernels without barriers or inter-thread communication)
 template <class F>
 inline void emu_launch(dim3 g, dim3 b, F body) {
@@ -104,4 +104,30 @@ inline void emu_launch_mt(dim3 g, dim3 b, F body) {
   std::vector<std::thread> th;
   for (int t = 0; t < T; ++t) th.emplace_back(worker, t);
   for (auto& x : th) x.join();
+}
+
+// Warp shuffles (k_diag_final): the 32 lanes of a warp exchange through a mailbox with a barrier among the lanes.  Valid when every
+// lane of the warp executes the same sequence of shuffles (full mask), which is how the kernels use them.
+struct EmuWarp {
+  std::mutex m; std::condition_variable cv; int waiting = 0; unsigned long gen = 0; unsigned long long box[32];
+  void sync() {
+    std::unique_lock<std::mutex> lk(m);
+    if (++waiting == 32) { waiting = 0; ++gen; cv.notify_all(); return; }
+    const unsigned long g = gen;
+    cv.wait(lk, [&] { return gen != g; });
+  }
+};
+extern EmuWarp emu_warps[64];
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int d) {
+  const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  EmuWarp& W = emu_warps[tid >> 5];
+  const unsigned lane = tid & 31;
+  unsigned long long bits = 0; __builtin_memcpy(&bits, &v, sizeof(T));
+  W.box[lane] = bits;
+  W.sync();
+  const unsigned long long o = W.box[lane ^ (unsigned)d];
+  W.sync();
+  T r; __builtin_memcpy(&r, &o, sizeof(T));
+  return r;
 }

@@ -12,6 +12,7 @@
 thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
 EmuBlockBarrier emu_block_barrier;
+EmuWarp emu_warps[64];
 void __syncthreads() { emu_block_barrier.wait(); }
 double* emu_dynsmem() { static std::vector<double> buf(64 * 1024); return buf.data(); }      // 512 KB >= any CTA's dynamic shared memory
 unsigned long long atomicAdd(unsigned long long* a, unsigned long long v) { static std::mutex m; std::lock_guard<std::mutex> g(m); const unsigned long long o = *a; *a = o + v; return o; }
@@ -25,6 +26,7 @@ struct Emu {
   Par p; Flds f;
   int ni, nj, LBi, LBj, ioff, dj_gradps, mix_geo_ts, ana_vmix, ts_dif4;
   std::map<std::string, Slot> reg;
+  std::vector<double> diag_partial, diag_out;
   void add(const std::string& name, double** slot, int LBk, int nk) {
     Slot& s = reg[name];
     s.slot = slot; s.LBk = LBk; s.nk = nk;
@@ -118,6 +120,14 @@ int emu_xfer(void* h, const char* name, double* host, int up) {
     }
   return 0;
 }
+// the 12 scalars of roms_b200_diag from the device-side results of phase 18 (csrc/api.cu finish_diag)
+void emu_diag(void* h, double* out12) {
+  const double* d = ((Emu*)h)->diag_out.data();
+  const double vol = d[2];
+  out12[0] = d[0] / vol; out12[1] = d[1] / vol; out12[2] = out12[0] + out12[1]; out12[3] = vol;
+  out12[4] = d[7]; out12[5] = d[4]; out12[6] = d[5]; out12[7] = d[6];
+  out12[8] = d[11]; out12[9] = d[12]; out12[10] = d[9]; out12[11] = d[10];
+}
 // first array column (Fortran index) and number of columns of this tile's arrays
 void emu_extent(void* h, int* out2) { Emu* e = (Emu*)h; out2[0] = e->LBi; out2[1] = e->ni; }
 int emu_levels(void* h, const char* name) { Emu* e = (Emu*)h; auto it = e->reg.find(name); return it == e->reg.end() ? -1 : it->second.nk; }
@@ -159,6 +169,10 @@ int emu_run(void* h, int phase) {
     case 14: launch_set_depth(p, f, s); break;
     case 15: launch_step3d_uv(p, f, s); break;
     case 17: launch_step3d_t(p, f, s); break;
+    case 18:                                                       // diag.F: the three kernels, then csrc/api.cu finish_diag
+      e->diag_partial.assign((size_t)diag_partial_doubles(p) + 16, 0.0); e->diag_out.assign(16, 0.0);
+      launch_diag(p, f, e->diag_partial.data(), e->diag_out.data(), p.knew, s);
+      break;
     case 23: launch_bulk_flux(p, f, s); break;
     case 24: launch_lmd_vmix(p, f, s); break;
     case 25: launch_bvf_mix(p, f, s); break;

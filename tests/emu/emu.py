@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DP = C.POINTER(C.c_double)
 EMULATED = {"set_massflux": 1, "rho_eos": 2, "set_vbc": 3, "ana_vmix": 4, "omega": 5, "wvelocity": 6, "set_zeta": 7, "pre_step3d": 8,
             "prsgrd": 9, "t3dmix": 10, "rhs3d": 11, "uv3dmix": 12, "step2d": 13, "set_depth": 14, "step3d_uv": 15, "omega2": 16, "step3d_t": 17,
-            "bulk_flux": 23, "lmd_vmix": 24, "bvf_mix": 25, "t3dmix4": 26}
+            "diag": 18, "bulk_flux": 23, "lmd_vmix": 24, "bvf_mix": 25, "t3dmix4": 26}
 IOPT = ["Lm", "Mm", "N", "NT", "nonlin_eos", "curvgrid", "uv_qdrag", "salinity", "hadv", "vadv", "itemp", "isalt", "bv_frequency",
         "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "uv_adv", "ts_dif4", "dj_gradps", "mix_geo_ts",
         "ana_vmix", "ndtfast", "limit_bstress", "NtileI_", "tile_", "nospl_vvisc", "nospl_vdiff", "qcorrection", "limit_stflx_cooling", "scorrection", "bodyforce", "levsfrc", "levbfrc", "Vtransform"]
@@ -28,6 +28,7 @@ def lib():
         _L.emu_xfer.argtypes = [C.c_void_p, C.c_char_p, DP, C.c_int]
         _L.emu_levels.argtypes = [C.c_void_p, C.c_char_p]
         _L.emu_extent.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        _L.emu_diag.argtypes = [C.c_void_p, DP]
         _L.emu_scoord.argtypes = [C.c_void_p, C.c_int, DP, C.c_int]
         _L.emu_indices.argtypes = [C.c_void_p] + [C.c_int] * 4
         _L.emu_indices2d.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_double] * 3
@@ -76,6 +77,13 @@ class EmuTile:
         iif = d["iif"]
         w = lambda a, i: float(a[i]) if 0 <= i < len(a) else 0.0
         self.L.emu_indices2d(self.h, iif, d["kstp"], d["krhs"], d["knew"], d["PREDICTOR"], self.nfast, w(self.w1, iif - 1), w(self.w2, iif), w(self.w2, iif + 1))
+
+    def diag(self):
+        """The scalars of roms_b200_diag (diag.F), through the three device kernels and the host-side finish."""
+        self.run_phase("diag")
+        out = (C.c_double * 12)()
+        self.L.emu_diag(self.h, out)
+        return dict(zip(["avgke", "avgpe", "avgkp", "volume", "max_speed", "maxCu", "maxCv", "maxCw", "ubarmax", "vbarmax", "umax", "vmax"], list(out)))
 
     def run_phase(self, name):
         rc = self.L.emu_run(self.h, EMULATED[name])

@@ -5,7 +5,7 @@ step3d_t, bvf_mix) for the host and runs every thread of every launch -- in turn
 for the kernels that call __syncthreads().  Built like the oracle's parity build (-O2 -ffp-contract=off), each phase must reproduce
 the oracle BIT FOR BIT from the oracle's own inputs: loop ranges, wall / periodic-image handling, upstream selects, shared-memory
 tile indexing and the operation order of the kernel text are pinned without a device.  What it cannot see: the cooperative loop
-kernel (k_step2d_loop), diag (warp shuffles), the multi-GPU exchange, device libm, data races.  The -m gpu tests remain the parity
+kernel (k_step2d_loop), the multi-GPU exchange, device libm, data races.  The -m gpu tests remain the parity
 tests proper."""
 import os
 import sys
@@ -333,3 +333,23 @@ def test_gpu_variant_test_bodies_dry_run_on_the_emulation(case, monkeypatch):
         return o, t
     monkeypatch.setattr(G, "make_pair", fake_make_pair)
     G.test_variants_strict_bit_exact_every_phase(case, 3)
+
+
+@pytest.mark.parametrize("case", ["seamount", "benchmark", "upwelling"])
+def test_diag_kernels_bit_exact(case):
+    """diag.F through the three device kernels (column sums, row sums in the reference's order, the final CTA whose warp 1 reduces the
+    maxima with shuffles -- emulated with a mailbox per warp) and the host-side finish of roms_b200_diag: the 12 scalars (KE, PE,
+    volume, maximum speed, the Courant numbers AT the location of the largest one, ...) equal the oracle's exactly."""
+    app, kw = CASES[case]
+    o = orc.Oracle(app, **kw)
+    o.run_phase("set_data"); o.run_phase("ini")
+    o.step(5)
+    t = EmuTile(o)
+    for n in all_names(int(o.opt("NT"))) + optional_names(o):
+        t.set(n, o.field(n))
+    t.set_indices(o.indices())
+    want, got = o.diag(), t.diag()
+    assert want["max_speed"] > 0 and want["avgke"] > 0
+    for k in want:
+        assert want[k] == got[k], (k, want[k], got[k])
+    t.close()
