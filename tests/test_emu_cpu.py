@@ -353,3 +353,36 @@ def test_diag_kernels_bit_exact(case):
     for k in want:
         assert want[k] == got[k], (k, want[k], got[k])
     t.close()
+
+
+def test_emulation_negative_controls():
+    """The comparison has teeth: a relative change of 1e-7 in ONE diff4 value, or the emulated kernel running the default advection
+    while the oracle runs UV_C4ADVECTION, makes the phase differ."""
+    o = orc.Oracle(orc.APP_BENCHMARK, Lm=37, Mm=19, N=7, uv_adv=1, ts_dif4=1, tnu4=1.0e15)
+    o.run_phase("set_data"); o.run_phase("ini"); o.step(3)
+    d = o.indices(); d["nstp"] = 1 + ((d["iic"] - d["ntstart"]) % 2); d["nnew"] = 3 - d["nstp"]; d["nrhs"] = d["nstp"]; o.set_indices(d)
+    names = all_names(2) + optional_names(o)
+    for ph in STEP_PHASES[:STEP_PHASES.index("t3dmix") + 1]:
+        o.run_phase(ph)
+    t = EmuTile(o)
+    for n in names:
+        t.set(n, o.field(n))
+    t.set_indices(o.indices())
+    a = o.field("diff4_0").copy(); a[0, 5, 7] *= 1.0000001; t.set("diff4_0", a)
+    o.run_phase("t3dmix4"); t.run_phase("t3dmix4")
+    new = "t%d_" % d["nnew"]
+    assert not np.array_equal(o.field(new + "0"), t.get(new + "0"))                 # the perturbed tracer differs ...
+    assert np.array_equal(o.field(new + "1"), t.get(new + "1"))                     # ... the other one does not
+    t.close()
+
+    class WrongScheme:                                                              # an oracle front that reports uv_adv = 0
+        def __init__(self, o): self.o = o
+        def opt(self, k): return 0 if k == "uv_adv" else self.o.opt(k)
+        def vector(self, *a): return self.o.vector(*a)
+    t = EmuTile(WrongScheme(o))
+    for n in names:
+        t.set(n, o.field(n))
+    t.set_indices(o.indices())
+    o.run_phase("rhs3d"); t.run_phase("rhs3d")
+    assert not np.array_equal(o.field("rv%d" % d["nrhs"]), t.get("rv%d" % d["nrhs"]))
+    t.close()
