@@ -97,7 +97,7 @@ int orc_set_option(void* hp, const char* key, double val) {
   else if (k == "tnu4") { c.tnu4[0] = c.tnu4[1] = val; } else if (k == "limit_bstress") c.limit_bstress = (int)val;
   else if (k == "qcorrection") c.qcorrection = (int)val; else if (k == "limit_stflx_cooling") c.limit_stflx_cooling = (int)val;
   else if (k == "scorrection") c.scorrection = (int)val; else if (k == "Tnudg_salt") c.Tnudg_salt = val;
-  else if (k == "Vtransform") c.Vtransform = (int)val;
+  else if (k == "Vtransform") c.Vtransform = (int)val; else if (k == "atm_press") c.atm_press = (int)val;
   else if (k == "bodyforce") c.bodyforce = (int)val; else if (k == "levsfrc") c.levsfrc = (int)val; else if (k == "levbfrc") c.levbfrc = (int)val;
   else if (k == "nospl_vvisc") c.nospl_vvisc = (int)val; else if (k == "nospl_vdiff") c.nospl_vdiff = (int)val;
   else if (k == "rdrg2") c.rdrg2 = val; else if (k == "rdrg") c.rdrg = val;
@@ -121,7 +121,7 @@ double orc_get_option(void* hp, const char* key) {
   if (k == "bvf_mixing") return c.bvf_mixing; if (k == "itemp") return c.itemp; if (k == "isalt") return c.isalt;
   if (k == "qcorrection") return c.qcorrection; if (k == "limit_stflx_cooling") return c.limit_stflx_cooling;
   if (k == "scorrection") return c.scorrection; if (k == "Tnudg_salt") return c.Tnudg_salt;
-  if (k == "Vtransform") return c.Vtransform;
+  if (k == "Vtransform") return c.Vtransform; if (k == "atm_press") return c.atm_press;
   if (k == "bodyforce") return c.bodyforce; if (k == "levsfrc") return c.levsfrc; if (k == "levbfrc") return c.levbfrc;
   if (k == "nospl_vvisc") return c.nospl_vvisc; if (k == "nospl_vdiff") return c.nospl_vdiff;
   if (k == "limit_bstress") return c.limit_bstress; if (k == "rdrg2") return c.rdrg2; if (k == "rdrg") return c.rdrg;

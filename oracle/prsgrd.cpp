@@ -30,6 +30,9 @@ static void prsgrd32(Model& m, const Bnd& b) {
     for (int i = IstrU - 1; i <= Iend; ++i) {
       double cff1 = 1.0 / (z_r(i, j, N) - z_r(i, j, N - 1));
       double cff2 = 0.5 * (rho(i, j, N) - rho(i, j, N - 1)) * (z_w(i, j, N) - z_r(i, j, N)) * cff1;
+      if (c.atm_press)                                                          // ATM_PRESS :229-232, :265-267
+        P(i, j, N) = g * z_w(i, j, N) + (100.0 / rho0) * (m.Pair(i, j) - 1013.25) + GRho * (rho(i, j, N) + cff2) * (z_w(i, j, N) - z_r(i, j, N));
+      else
       P(i, j, N) = g * z_w(i, j, N) + GRho * (rho(i, j, N) + cff2) * (z_w(i, j, N) - z_r(i, j, N));
     }
     for (int k = N - 1; k >= 1; --k)
@@ -90,6 +93,7 @@ static void prsgrd31(Model& m, const Bnd& b, bool wj) {
     for (int i = IstrU; i <= Iend; ++i) {
       double cff1 = z_w(i, j, N) - z_r(i, j, N) + z_w(i - 1, j, N) - z_r(i - 1, j, N);
       phix[i] = fac1 * (rho(i, j, N) - rho(i - 1, j, N)) * cff1;
+      if (c.atm_press) phix[i] = phix[i] + (100.0 / rho0) * (m.Pair(i, j) - m.Pair(i - 1, j));        // ATM_PRESS :186-188, :211-213
       phix[i] = phix[i] + (fac2 + fac1 * (rho(i, j, N) + rho(i - 1, j, N))) * (z_w(i, j, N) - z_w(i - 1, j, N));
       ru(i, j, N) = -0.5 * (Hz(i, j, N) + Hz(i - 1, j, N)) * phix[i] * m.on_u(i, j);
     }
@@ -118,6 +122,7 @@ static void prsgrd31(Model& m, const Bnd& b, bool wj) {
       for (int i = Istr; i <= Iend; ++i) {
         double cff1 = z_w(i, j, N) - z_r(i, j, N) + z_w(i, j - 1, N) - z_r(i, j - 1, N);
         phie[i] = fac1 * (rho(i, j, N) - rho(i, j - 1, N)) * cff1;
+        if (c.atm_press) phie[i] = phie[i] + (100.0 / rho0) * (m.Pair(i, j) - m.Pair(i, j - 1));
         phie[i] = phie[i] + (fac2 + fac1 * (rho(i, j, N) + rho(i, j - 1, N))) * (z_w(i, j, N) - z_w(i, j - 1, N));
         rv(i, j, N) = -0.5 * (Hz(i, j, N) + Hz(i, j - 1, N)) * phie[i] * m.om_v(i, j);
       }
@@ -154,7 +159,7 @@ static void prsgrd40(Model& m, const Bnd& b) {
   SK FC(IminS, ImaxS, 0, N);
   S3 FX(IminS, ImaxS, JminS, JmaxS, 1, N), P(IminS, ImaxS, JminS, JmaxS, 0, N);
   for (int j = JstrV - 1; j <= Jend; ++j) {
-    for (int i = IstrU - 1; i <= Iend; ++i) P(i, j, N) = 0.0;
+    for (int i = IstrU - 1; i <= Iend; ++i) { P(i, j, N) = 0.0; if (c.atm_press) P(i, j, N) = P(i, j, N) + (100.0 / g) * (m.Pair(i, j) - 1013.25); }   // prsgrd40.h:172-175, :181-183
     for (int k = N; k >= 1; --k)
       for (int i = IstrU - 1; i <= Iend; ++i) {
         P(i, j, k - 1) = P(i, j, k) + Hz(i, j, k) * rho(i, j, k);

@@ -146,6 +146,7 @@ struct Cfg {
   double Tnudg_salt = 0.0;
   int bodyforce = 0, levsfrc = 0, levbfrc = 0;   // BODYFORCE: surface / bottom stress as a body force over levels levsfrc:N / 1:levbfrc
                                                  // (rhs3d.F:326-466, :1588-1599; pre_step3d.F:931-937, :1036-1042)
+  int atm_press = 0;              // ATM_PRESS: the atmospheric pressure Pair (mb) in the pressure gradient (prsgrd31/32/40)
   int limit_bstress = 0;          // LIMIT_BSTRESS (set_vbc.F:533-540): |bottom stress| <= 0.75 |u| Hz / dt
   int ts_dif4 = 0;                // TS_DIF4 (+ MIX_S_TS): t3dmix4_s.h after t3dmix2 (rhs3d.F:81-97)
   // physical parameters

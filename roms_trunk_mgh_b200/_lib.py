@@ -24,7 +24,7 @@ class Config(C.Structure):
         ("bv_frequency", C.c_int), ("eos_tderivative", C.c_int), ("solar_source", C.c_int), ("lmd_nonlocal", C.c_int),
         ("bulk_fluxes", C.c_int), ("lmd_mixing", C.c_int), ("blk_ZQ", C.c_double), ("blk_ZT", C.c_double), ("blk_ZW", C.c_double),
         ("bvf_mixing", C.c_int), ("nospl_vvisc", C.c_int), ("nospl_vdiff", C.c_int), ("vtransform", C.c_int), ("bodyforce", C.c_int), ("levsfrc", C.c_int), ("levbfrc", C.c_int),
-        ("limit_bstress", C.c_int), ("uv_adv", C.c_int), ("qcorrection", C.c_int), ("limit_stflx_cooling", C.c_int), ("scorrection", C.c_int), ("ts_dif4", C.c_int),
+        ("atm_press", C.c_int), ("limit_bstress", C.c_int), ("uv_adv", C.c_int), ("qcorrection", C.c_int), ("limit_stflx_cooling", C.c_int), ("scorrection", C.c_int), ("ts_dif4", C.c_int),
         ("Tnudg_salt", C.c_double),
     ]
 

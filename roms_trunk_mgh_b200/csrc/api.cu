@@ -750,6 +750,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   p.qcorrection = cfg->qcorrection ? 1 : 0; p.limit_stflx_cooling = cfg->limit_stflx_cooling ? 1 : 0; p.scorrection = cfg->scorrection;
   p.pad2_ = 0; p.Tnudg_salt = cfg->Tnudg_salt;
   p.bodyforce = cfg->bodyforce ? 1 : 0; p.levsfrc = cfg->levsfrc; p.levbfrc = cfg->levbfrc; p.vtransform = (cfg->vtransform == 1) ? 1 : 2;
+  p.atm_press = cfg->atm_press ? 1 : 0; p.pad4_ = 0;
   p.blk_ZQ = cfg->blk_ZQ > 0.0 ? cfg->blk_ZQ : 10.0; p.blk_ZT = cfg->blk_ZT > 0.0 ? cfg->blk_ZT : 10.0; p.blk_ZW = cfg->blk_ZW > 0.0 ? cfg->blk_ZW : 10.0;
   p.dt = cfg->dt; p.g = cfg->g; p.rho0 = cfg->rho0; p.R0 = cfg->R0; p.T0 = cfg->T0; p.S0 = cfg->S0; p.Tcoef = cfg->Tcoef; p.Scoef = cfg->Scoef;
   p.gamma2 = cfg->gamma2; p.lambda = cfg->lambda; p.hc = cfg->hc; p.Akv_bak = cfg->Akv_bak;
@@ -804,6 +805,7 @@ static int create_impl(const roms_b200_config* cfg, roms_b200_handle* out, bool 
   if (cfg->eos_tderivative) { rc |= alloc_field(h, "alpha", &f.alpha, 0, 1); rc |= alloc_field(h, "beta", &f.beta, 0, 1); }
   if (cfg->solar_source || cfg->bulk_fluxes) rc |= alloc_field(h, "srflx", &f.srflx, 0, 1);
   if (cfg->solar_source) rc |= alloc_field(h, "Jwtype", &f.Jwtype, 0, 1);
+  if (cfg->atm_press && !cfg->bulk_fluxes) rc |= alloc_field(h, "Pair", &f.Pair, 0, 1);
   if (cfg->bulk_fluxes) {
 #define A2(name) rc |= alloc_field(h, #name, &f.name, 0, 1)
     A2(Uwind); A2(Vwind); A2(Tair); A2(Pair); A2(Hair); A2(rain); A2(cloud); A2(lrflx); A2(lhflx); A2(shflx); A2(Taux); A2(Tauy);

@@ -134,7 +134,7 @@ const RoutineArgs kRoutineArgs[] = {
      "Hz,Huon,Hvom,W,z_r,Akv,Akt_*,pm,pn,stflx_*,btflx_*,sustr,svstr,bustr,bvstr,ru1,ru2,rv1,rv2,u1,u2,v1,v2,t1_*,t2_*,"
      "?z_w,?srflx,?Jwtype,?ghats_*",
      "t3_*,t1_*,t2_*,u1,u2,v1,v2"},
-    {ROMS_B200_PRSGRD, "Hz,z_r,z_w,rho,on_u,om_v", "ru1,ru2,rv1,rv2"},
+    {ROMS_B200_PRSGRD, "Hz,z_r,z_w,rho,on_u,om_v,?Pair", "ru1,ru2,rv1,rv2"},
     {ROMS_B200_T3DMIX, "Hz,z_r,pm,pn,on_u,om_v,pmon_u,pnom_v,diff2_*,t1_*,t2_*", "t1_*,t2_*"},
     {ROMS_B200_T3DMIX4, "Hz,pm,pn,pmon_u,pnom_v,diff4_*,t1_*,t2_*", "t1_*,t2_*"},
     {ROMS_B200_RHS3D, "Hz,Huon,Hvom,W,u1,u2,v1,v2,fomn,dndx,dmde,om_u,on_u,om_v,on_v,sustr,svstr,bustr,bvstr,ru1,ru2,rv1,rv2",

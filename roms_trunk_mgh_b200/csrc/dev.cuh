@@ -46,7 +46,8 @@ struct Par {
   int nospl_vvisc, nospl_vdiff;   // 1: SPLINES_VVISC / SPLINES_VDIFF not defined (centred implicit systems in step3d_uv / step3d_t)
   int qcorrection, limit_stflx_cooling, scorrection, pad2_;   // set_vbc surface-flux corrections (set_vbc.F:285-351)
   double Tnudg_salt;
-  int bodyforce, levsfrc, levbfrc, vtransform;   // BODYFORCE and its level ranges (mod_scalars.F levsfrc, levbfrc)
+  int bodyforce, levsfrc, levbfrc, vtransform;
+  int atm_press, pad4_;           // ATM_PRESS: Pair in the pressure gradient   // BODYFORCE and its level ranges (mod_scalars.F levsfrc, levbfrc)
 };
 
 // Field table (all pointers pre-offset; [0] slots of time-indexed arrays are unused so Fortran indices apply)

@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(128) k_prsgrd32_P(Par p, Flds f) {
   double dZ_kp = 2.0 * rawZ_k * rawZ_km / (rawZ_k + rawZ_km);          // dZ(N)
   const double cff1 = 1.0 / (z_kp - z_k);
   const double cff2 = 0.5 * (r_kp - r_k) * (zwN - z_kp) * cff1;
-  double Pk = p.g * zwN + GRho * (r_kp + cff2) * (zwN - z_kp);
+  double Pk = p.atm_press ? p.g * zwN + (100.0 / p.rho0) * (f.Pair[o2] - 1013.25) + GRho * (r_kp + cff2) * (zwN - z_kp)   // ATM_PRESS :265-267
+                          : p.g * zwN + GRho * (r_kp + cff2) * (zwN - z_kp);
   P3[oN] = Pk;
   for (int kt = N - 1; kt >= 1; kt -= CH) {
     double lr[CH], lz[CH];
@@ -386,6 +387,7 @@ __global__ void __launch_bounds__(128) k_prsgrd31(Par p, Flds f) {
     const int oN = o2 + N * p.PL + i;
     double cff1 = z_w[oN] - z_r[oN] + z_w[oN - s] - z_r[oN - s];
     double phi = fac1 * (rho[oN] - rho[oN - s]) * cff1;
+    if (p.atm_press) phi = phi + (100.0 / p.rho0) * (f.Pair[o2 + i] - f.Pair[o2 + i - s]);                  // ATM_PRESS
     phi = phi + (fac2 + fac1 * (rho[oN] + rho[oN - s])) * (z_w[oN] - z_w[oN - s]);
     R[oN] = -0.5 * (Hz[oN] + Hz[oN - s]) * phi * met;
     for (int k = N - 1; k >= 1; --k) {
@@ -431,6 +433,10 @@ __global__ void __launch_bounds__(128) k_prsgrd40(Par p, Flds f) {
   const int oN = o2 + N * p.PL;
   const double dzu = z_w[oN - 1] - z_w[oN], dzv = z_w[oN - P] - z_w[oN];          // z_w(i-1,j,N) - z_w(i,j,N), z_w(i,j-1,N) - z_w(i,j,N)
   double P0 = 0.0, PW = 0.0, PS = 0.0, FCu = 0.0, FCv = 0.0;
+  if (p.atm_press) {                                                   // prsgrd40.h:181-183
+    const double fac = 100.0 / p.g;
+    P0 = P0 + fac * (f.Pair[o2] - 1013.25); PW = PW + fac * (f.Pair[o2 - 1] - 1013.25); PS = PS + fac * (f.Pair[o2 - P] - 1013.25);
+  }
   for (int k = N; k >= 1; --k) {
     const int o = o2 + k * p.PL, od = o - p.PL;
     const double hz0 = Hz[o], hzW = Hz[o - 1];

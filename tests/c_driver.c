@@ -200,7 +200,7 @@ static void print_layout(void) {
   OFFC(rho0); OFFC(g); OFFC(R0); OFFC(T0); OFFC(S0); OFFC(Tcoef); OFFC(Scoef); OFFC(Akt_bak); OFFC(Akv_bak); OFFC(gamma2); OFFC(lambda);
   OFFC(hc); OFFC(itemp); OFFC(isalt); OFFC(device);
   OFFC(bv_frequency); OFFC(eos_tderivative); OFFC(solar_source); OFFC(lmd_nonlocal);
-  OFFC(bulk_fluxes); OFFC(lmd_mixing); OFFC(blk_ZQ); OFFC(blk_ZT); OFFC(blk_ZW); OFFC(bvf_mixing); OFFC(nospl_vvisc); OFFC(nospl_vdiff); OFFC(vtransform); OFFC(bodyforce); OFFC(levsfrc); OFFC(levbfrc); OFFC(limit_bstress); OFFC(uv_adv); OFFC(qcorrection); OFFC(limit_stflx_cooling); OFFC(scorrection); OFFC(ts_dif4); OFFC(Tnudg_salt);
+  OFFC(bulk_fluxes); OFFC(lmd_mixing); OFFC(blk_ZQ); OFFC(blk_ZT); OFFC(blk_ZW); OFFC(bvf_mixing); OFFC(nospl_vvisc); OFFC(nospl_vdiff); OFFC(vtransform); OFFC(bodyforce); OFFC(levsfrc); OFFC(levbfrc); OFFC(atm_press); OFFC(limit_bstress); OFFC(uv_adv); OFFC(qcorrection); OFFC(limit_stflx_cooling); OFFC(scorrection); OFFC(ts_dif4); OFFC(Tnudg_salt);
   OFFT(cfg); OFFT(iic); OFFT(ntfirst); OFFT(nstp); OFFT(nnew); OFFT(nrhs); OFFT(iif); OFFT(kstp); OFFT(krhs); OFFT(knew); OFFT(predictor);
 }
 

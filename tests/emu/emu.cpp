@@ -70,7 +70,7 @@ void* emu_create(const int* io, const double* dv) {
   p.blk_ZQ = dv[14]; p.blk_ZT = dv[15]; p.blk_ZW = dv[16];
   p.dtfast = p.dt / (double)io[23]; p.limit_bstress = io[24]; p.nospl_vvisc = io[27]; p.nospl_vdiff = io[28];
   p.qcorrection = io[29]; p.limit_stflx_cooling = io[30]; p.scorrection = io[31]; p.Tnudg_salt = dv[17];
-  p.bodyforce = io[32]; p.levsfrc = io[33]; p.levbfrc = io[34]; p.vtransform = (io[35] == 1) ? 1 : 2;
+  p.bodyforce = io[32]; p.levsfrc = io[33]; p.levbfrc = io[34]; p.vtransform = (io[35] == 1) ? 1 : 2; p.atm_press = io[36];
 #define A2(name) e->add(#name, &f.name, 0, 1)
 #define A3(name, k0, nk) e->add(#name, &f.name, k0, nk)
   A2(h); A2(f); A2(pm); A2(pn); A2(om_r); A2(on_r); A2(om_u); A2(on_u); A2(om_v); A2(on_v); A2(om_p); A2(on_p); A2(omn); A2(fomn);

@@ -12,7 +12,7 @@ EMULATED = {"set_massflux": 1, "rho_eos": 2, "set_vbc": 3, "ana_vmix": 4, "omega
             "diag": 18, "bulk_flux": 23, "lmd_vmix": 24, "bvf_mix": 25, "t3dmix4": 26}
 IOPT = ["Lm", "Mm", "N", "NT", "nonlin_eos", "curvgrid", "uv_qdrag", "salinity", "hadv", "vadv", "itemp", "isalt", "bv_frequency",
         "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "uv_adv", "ts_dif4", "dj_gradps", "mix_geo_ts",
-        "ana_vmix", "ndtfast", "limit_bstress", "NtileI_", "tile_", "nospl_vvisc", "nospl_vdiff", "qcorrection", "limit_stflx_cooling", "scorrection", "bodyforce", "levsfrc", "levbfrc", "Vtransform"]
+        "ana_vmix", "ndtfast", "limit_bstress", "NtileI_", "tile_", "nospl_vvisc", "nospl_vdiff", "qcorrection", "limit_stflx_cooling", "scorrection", "bodyforce", "levsfrc", "levbfrc", "Vtransform", "atm_press"]
 DOPT = ["dt", "g", "rho0", "R0", "T0", "S0", "Tcoef", "Scoef", "gamma2", "lambda", "hc", "Akv_bak", "Akt_bak", "Akt_bak", "blk_ZQ", "blk_ZT", "blk_ZW", "Tnudg_salt"]
 _L = None
 

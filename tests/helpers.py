@@ -6,7 +6,7 @@ from roms_trunk_mgh_b200 import _lib
 from roms_trunk_mgh_b200.ocean import Tile, field_names
 
 APP_OPTS = ["nonlin_eos", "dj_gradps", "curvgrid", "mix_geo_ts", "uv_qdrag", "hadv", "vadv", "ana_vmix", "wvelocity_every_step",
-            "bv_frequency", "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "bvf_mixing", "uv_adv", "ts_dif4", "limit_bstress", "nospl_vvisc", "nospl_vdiff", "qcorrection", "limit_stflx_cooling", "scorrection", "bodyforce", "levsfrc", "levbfrc"]
+            "bv_frequency", "eos_tderivative", "solar_source", "lmd_nonlocal", "bulk_fluxes", "lmd_mixing", "bvf_mixing", "uv_adv", "ts_dif4", "limit_bstress", "nospl_vvisc", "nospl_vdiff", "qcorrection", "limit_stflx_cooling", "scorrection", "bodyforce", "levsfrc", "levbfrc", "atm_press"]
 # (Vtransform is copied separately: the oracle spells it with a capital)
 
 
@@ -45,6 +45,7 @@ def optional_names(o):
     if o.opt("bulk_fluxes"): v += [n for n in ATMOSPHERE if n not in v] + ["lrflx", "lhflx", "shflx"]
     if o.opt("lmd_mixing"): v += ["hsbl", "ksbl"]
     if o.opt("ts_dif4"): v += [f"diff4_{it}" for it in range(NT)]
+    if o.opt("atm_press") and "Pair" not in v: v += ["Pair"]
     if o.opt("qcorrection"): v += ["sst", "dqdt"]
     if o.opt("scorrection"): v += ["sss"]
     return v
@@ -96,6 +97,9 @@ def all_names(NT):
 
 
 def fill_flux_data(o):
+    if o.opt("atm_press") and not o.opt("bulk_fluxes"):      # ATM_PRESS: a pressure field (mb) with gradients in both directions
+        a = o.field("Pair"); j = np.arange(a.shape[1])[None, :, None]; i = np.arange(a.shape[2])[None, None, :]
+        a[:] = 1013.25 + 6.0 * np.sin(2.0 * np.pi * (i - 2) / (a.shape[2] - 5)) + 0.2 * j
     """sst, dqdt, sss of set_vbc's QCORRECTION / SCORRECTION / SRELAXATION (host data in a real run): analytical, part below -2 degC."""
     if o.opt("qcorrection"):
         a = o.field("sst"); j = np.arange(a.shape[1])[None, :, None]; i = np.arange(a.shape[2])[None, None, :]

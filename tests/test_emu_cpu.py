@@ -41,6 +41,9 @@ CASES = {
     "bodyforce_upwelling_c4": (orc.APP_UPWELLING, dict(Lm=20, Mm=24, N=8, bodyforce=1, levsfrc=8, levbfrc=1, uv_adv=1)),
     "vtransform1": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, Vtransform=1)),
     "vtransform1_seamount": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, Vtransform=1)),
+    "atm_press": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, atm_press=1)),                          # ATM_PRESS with prsgrd32
+    "atm_press_p31": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, atm_press=1, dj_gradps=3)),          # ... the weighted prsgrd31
+    "atm_press_p40": (orc.APP_SEAMOUNT, dict(Lm=24, Mm=20, N=8, atm_press=1, dj_gradps=2)),           # ... prsgrd40
     "benchmark_splines": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, vadv=3)),
     "benchmark_bvf": (orc.APP_BENCHMARK, dict(Lm=32, Mm=16, N=8, bv_frequency=1, bvf_mixing=1)),
     "benchmark_geo": (orc.APP_BENCHMARK, dict(Lm=37, Mm=19, N=7, mix_geo_ts=1)),

@@ -1007,3 +1007,33 @@ def test_vtransform1_known_answer():
     for n in ("zeta1", "u1", "t1_0", "z_r", "Hz"):
         assert np.array_equal(a.field(n), b.field(n)), n
     assert not np.array_equal(a.field("z_r"), c.field("z_r"))
+
+
+@pytest.mark.parametrize("alg", [1, 0, 2])
+def test_atm_press_known_answer(alg):
+    """ATM_PRESS in prsgrd32 / prsgrd31 / prsgrd40 (prsgrd32.h:265-267, prsgrd31.h:211-213, prsgrd40.h:181-183): the pressure Pair (mb)
+    adds the same barotropic force at every level, ru += -(100 / rho0) * 0.5 (Hz(i) + Hz(i-1)) (Pair(i) - Pair(i-1)) on_u, whatever the
+    algorithm (for prsgrd40 the pressure enters as a mass 100 / g * (Pair - 1 atm) on top of the column and the finite-volume sums
+    reduce to the same expression)."""
+    from helpers import fill_flux_data
+    out = {}
+    for ap in (0, 1):
+        o = orc.Oracle(orc.APP_SEAMOUNT, kind="chk", dj_gradps=alg, atm_press=ap)
+        o.run_phase("set_data"); o.run_phase("ini")
+        d = o.indices(); d["nstp"] = 1; d["nnew"] = 2; d["nrhs"] = 1; o.set_indices(d)
+        if ap:
+            fill_flux_data(o)
+        o.run_phase("rho_eos"); o.run_phase("prsgrd")
+        out[ap] = (o.field("ru1").copy(), o.field("rv1").copy())
+    Hz, Pair, on_u, om_v = o.field("Hz"), o.field("Pair")[0], o.field("on_u")[0], o.field("om_v")[0]
+    fac = 100.0 / o.opt("rho0")
+    I = slice(3, -2); J = slice(1, -1)
+    du = out[1][0][1:] - out[0][0][1:]
+    want_u = -fac * 0.5 * (Hz + np.roll(Hz, 1, axis=2)) * (Pair - np.roll(Pair, 1, axis=1))[None] * on_u[None]
+    scale = np.abs(out[1][0]).max()
+    assert np.abs(want_u[:, J, I]).max() > 1e-4 * scale
+    assert np.abs(du[:, J, I] - want_u[:, J, I]).max() < 1e-11 * scale
+    dv = out[1][1][1:] - out[0][1][1:]
+    want_v = -fac * 0.5 * (Hz + np.roll(Hz, 1, axis=1)) * (Pair - np.roll(Pair, 1, axis=0))[None] * om_v[None]
+    Jv = slice(2, -1)
+    assert np.abs(dv[:, Jv, I] - want_v[:, Jv, I]).max() < 1e-11 * max(scale, np.abs(out[1][1]).max())

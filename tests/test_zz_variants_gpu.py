@@ -33,6 +33,8 @@ VARIANTS = {
     "flux_corr": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, qcorrection=1, limit_stflx_cooling=1, scorrection=1, Tnudg_salt=1.0e-6)),
     "flux_relax": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, scorrection=2, Tnudg_salt=2.0e-7)),
     "bodyforce": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, bodyforce=1, levsfrc=8, levbfrc=2)),
+    "atm_press": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, atm_press=1)),                    # ATM_PRESS in prsgrd32
+    "atm_press_p40": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, atm_press=1, dj_gradps=2)),
     "vtransform1": (orc.APP_SEAMOUNT, dict(Vtransform=1)),                                   # the original vertical transformation in set_depth
     "uv_sadv": (orc.APP_BENCHMARK, dict(Lm=64, Mm=32, N=10, uv_adv=2)),                      # UV_SADVECTION: spline vertical advection
     "uv_sadv_seamount": (orc.APP_SEAMOUNT, dict(uv_adv=2)),
@@ -49,9 +51,9 @@ def test_variants_strict_bit_exact_every_phase(case, spinup):
     o, t = make_pair(app, strict=True, spinup=spinup, **kw)
     names = all_names(int(o.opt("NT")))
     begin_step(o, t)
-    if o.opt("qcorrection") or o.opt("scorrection"):            # the data of the surface-flux corrections (host fields in a real run),
+    if o.opt("qcorrection") or o.opt("scorrection") or o.opt("atm_press"):   # host data fields of these options,
         fill_flux_data(o)                                       # set after set_data, which resets the analytical surface fluxes
-        for n in ("sst", "dqdt", "sss", "stflux_0", "t1_0", "t2_0"):
+        for n in ("sst", "dqdt", "sss", "Pair", "stflux_0", "t1_0", "t2_0"):
             if n in ("stflux_0", "t1_0", "t2_0") or n in optional_names(o):
                 t.set(n, o.field(n))
     k = STEP_PHASES.index("t3dmix") + 1
