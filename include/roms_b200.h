@@ -85,8 +85,8 @@ typedef struct roms_b200_config {
                                    hc is the host's SCALARS(ng)%hc either way (MIN(hmin, Tcline) for 1: set_scoord.F:157-163)            */
   int bodyforce, levsfrc, levbfrc; /* BODYFORCE: surface / bottom stress as a body force over levels levsfrc:N / 1:levbfrc (roms_*.in LEVSFRC,
                                    LEVBFRC) in rhs3d (rhs3d.F:326-466, :1588-1599) and no stress boundary flux in pre_step3d (:931-937)   */
-  int atm_press;                /* ATM_PRESS: the atmospheric pressure "Pair" (mb, FORCES) enters the pressure gradient (prsgrd31.h:211-213,
-                                   prsgrd32.h:265-267, prsgrd40.h:181-183)                                                                      */
+  int atm_press;                /* ATM_PRESS: the atmospheric pressure "Pair" (mb, FORCES) enters the pressure gradient (prsgrd31.h:213-215, :294-296,
+                                   prsgrd32.h:265-267, prsgrd40.h:194-196)                                                                      */
   int limit_bstress;            /* LIMIT_BSTRESS (set_vbc.F:533-540 and the three drag laws): |bustr| <= 0.75 |u(k=1)| Hz(k=1) / dt        */
   int uv_adv;                   /* momentum advection in rhs3d: 0 the default branch (third-order upstream horizontal, fourth-order
                                    centred vertical), 1 UV_C4ADVECTION (rhs3d.F:685-705, :761-781, :829-849, :902-921, :1108-1175,

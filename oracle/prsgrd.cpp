@@ -93,7 +93,7 @@ static void prsgrd31(Model& m, const Bnd& b, bool wj) {
     for (int i = IstrU; i <= Iend; ++i) {
       double cff1 = z_w(i, j, N) - z_r(i, j, N) + z_w(i - 1, j, N) - z_r(i - 1, j, N);
       phix[i] = fac1 * (rho(i, j, N) - rho(i - 1, j, N)) * cff1;
-      if (c.atm_press) phix[i] = phix[i] + (100.0 / rho0) * (m.Pair(i, j) - m.Pair(i - 1, j));        // ATM_PRESS :186-188, :211-213
+      if (c.atm_press) phix[i] = phix[i] + (100.0 / rho0) * (m.Pair(i, j) - m.Pair(i - 1, j));        // ATM_PRESS prsgrd31.h:196-198, :213-215
       phix[i] = phix[i] + (fac2 + fac1 * (rho(i, j, N) + rho(i - 1, j, N))) * (z_w(i, j, N) - z_w(i - 1, j, N));
       ru(i, j, N) = -0.5 * (Hz(i, j, N) + Hz(i - 1, j, N)) * phix[i] * m.on_u(i, j);
     }
@@ -159,7 +159,7 @@ static void prsgrd40(Model& m, const Bnd& b) {
   SK FC(IminS, ImaxS, 0, N);
   S3 FX(IminS, ImaxS, JminS, JmaxS, 1, N), P(IminS, ImaxS, JminS, JmaxS, 0, N);
   for (int j = JstrV - 1; j <= Jend; ++j) {
-    for (int i = IstrU - 1; i <= Iend; ++i) { P(i, j, N) = 0.0; if (c.atm_press) P(i, j, N) = P(i, j, N) + (100.0 / g) * (m.Pair(i, j) - 1013.25); }   // prsgrd40.h:172-175, :181-183
+    for (int i = IstrU - 1; i <= Iend; ++i) { P(i, j, N) = 0.0; if (c.atm_press) P(i, j, N) = P(i, j, N) + (100.0 / g) * (m.Pair(i, j) - 1013.25); }   // prsgrd40.h:169-172, :194-196
     for (int k = N; k >= 1; --k)
       for (int i = IstrU - 1; i <= Iend; ++i) {
         P(i, j, k - 1) = P(i, j, k) + Hz(i, j, k) * rho(i, j, k);

@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(128) k_prsgrd40(Par p, Flds f) {
   const int oN = o2 + N * p.PL;
   const double dzu = z_w[oN - 1] - z_w[oN], dzv = z_w[oN - P] - z_w[oN];          // z_w(i-1,j,N) - z_w(i,j,N), z_w(i,j-1,N) - z_w(i,j,N)
   double P0 = 0.0, PW = 0.0, PS = 0.0, FCu = 0.0, FCv = 0.0;
-  if (p.atm_press) {                                                   // prsgrd40.h:181-183
+  if (p.atm_press) {                                                   // prsgrd40.h:194-196
     const double fac = 100.0 / p.g;
     P0 = P0 + fac * (f.Pair[o2] - 1013.25); PW = PW + fac * (f.Pair[o2 - 1] - 1013.25); PS = PS + fac * (f.Pair[o2 - P] - 1013.25);
   }

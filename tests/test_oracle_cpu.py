@@ -1011,7 +1011,7 @@ def test_vtransform1_known_answer():
 
 @pytest.mark.parametrize("alg", [1, 0, 2])
 def test_atm_press_known_answer(alg):
-    """ATM_PRESS in prsgrd32 / prsgrd31 / prsgrd40 (prsgrd32.h:265-267, prsgrd31.h:211-213, prsgrd40.h:181-183): the pressure Pair (mb)
+    """ATM_PRESS in prsgrd32 / prsgrd31 / prsgrd40 (prsgrd32.h:265-267, prsgrd31.h:213-215, prsgrd40.h:194-196): the pressure Pair (mb)
     adds the same barotropic force at every level, ru += -(100 / rho0) * 0.5 (Hz(i) + Hz(i-1)) (Pair(i) - Pair(i-1)) on_u, whatever the
     algorithm (for prsgrd40 the pressure enters as a mass 100 / g * (Pair - 1 atm) on top of the column and the finite-volume sums
     reduce to the same expression)."""
